@@ -358,10 +358,16 @@ def p_losses_flow(sd, sched, x0: Tensor, cond: Tensor, t: Tensor, noise: Tensor,
 # --------------------------------------------------------------------------------------
 
 
+def _fma(a: Tensor, b: Tensor, c: Tensor) -> Tensor:
+    """fp32 fused multiply-add emulated through float64 (the fp32 product is exact in float64)."""
+    return (a.double() * b.double() + c.double()).float()
+
+
 def backwarp_coords(flow: Tensor) -> Tuple[Tensor, Tensor]:
     """Un-normalised sampling coordinates (ix, iy) exactly as the reference op sequence produces
-    them: vgrid = grid + flow.flip(1); 2*v/max(S-1,1)-1 (warp.py:105-109); then grid_sample's
-    align_corners un-normalisation ((g+1)/2)*(S-1).  The fp32 round trip is NOT the identity."""
+    them on the CPU: vgrid = grid + flow.flip(1); 2*v/max(S-1,1)-1 (warp.py:105-109, true fp32
+    division); then grid_sample's align_corners un-normalisation as ATen's CPU kernel evaluates it,
+    (g + 1) * ((S-1)/2).  The fp32 round trip is NOT the identity."""
     B, _, H, W = flow.shape
     xx = torch.arange(W, dtype=torch.float32).view(1, 1, W).expand(B, H, W)
     yy = torch.arange(H, dtype=torch.float32).view(1, H, 1).expand(B, H, W)
@@ -369,39 +375,46 @@ def backwarp_coords(flow: Tensor) -> Tuple[Tensor, Tensor]:
     vy = yy + flow[:, 0]
     gx = 2.0 * vx / max(W - 1, 1) - 1.0
     gy = 2.0 * vy / max(H - 1, 1) - 1.0
-    ix = ((gx + 1) / 2) * (W - 1)
-    iy = ((gy + 1) / 2) * (H - 1)
+    ix = (gx + 1) * torch.tensor((W - 1) / 2, dtype=torch.float32)
+    iy = (gy + 1) * torch.tensor((H - 1) / 2, dtype=torch.float32)
     return ix, iy
 
 
 def backwarp(image: Tensor, flow: Tensor) -> Tuple[Tensor, Tensor]:
     """warp_backward_flow(first, second=image, flow) -> (output, mask), explicit 4-tap form.
 
-    Follows ATen's grid_sampler_2d (bilinear, padding zeros, align_corners=True): taps at
-    floor(ix), floor(ix)+1 with weights (x1-ix)(y1-iy) ...; out-of-range taps contribute 0.
-    mask = grid_sample(ones) thresholded: <0.999 -> 0, >0 -> 1 (warp.py:113-117)."""
+    Follows ATen's CPU grid_sampler_2d (bilinear, padding zeros, align_corners=True) operation by
+    operation -- w = ix - floor(ix), e = 1 - w, (nw, ne, sw, se) = (s*e, s*w, n*e, n*w); out-of-range
+    taps read 0; the four taps are accumulated as nw_v*nw, then three fused multiply-adds in the
+    order ne, sw, se -- which makes it BIT-EXACT against the reference's CPU output (checked by
+    tests/test_oracle_vs_golden.py).  mask = grid_sample(ones) thresholded: <0.999 -> 0, >0 -> 1
+    (warp.py:113-117)."""
     B, C, H, W = image.shape
     ix, iy = backwarp_coords(flow)
     x0 = torch.floor(ix)
     y0 = torch.floor(iy)
     x1 = x0 + 1
     y1 = y0 + 1
-    w_nw = (x1 - ix) * (y1 - iy)
-    w_ne = (ix - x0) * (y1 - iy)
-    w_sw = (x1 - ix) * (iy - y0)
-    w_se = (ix - x0) * (iy - y0)
-    out = torch.zeros_like(image)
-    msk = torch.zeros(B, H, W)
+    w = ix - x0
+    e = 1 - w
+    n = iy - y0
+    s = 1 - n
+    out = None
+    msk = None
     flat = image.reshape(B, C, H * W)
-    for xs, ys, wt in ((x0, y0, w_nw), (x1, y0, w_ne), (x0, y1, w_sw), (x1, y1, w_se)):
+    for xs, ys, wt in ((x0, y0, s * e), (x1, y0, s * w), (x0, y1, n * e), (x1, y1, n * w)):
         ok = (xs >= 0) & (xs <= W - 1) & (ys >= 0) & (ys <= H - 1)
         xi = xs.clamp(0, W - 1).long()
         yi = ys.clamp(0, H - 1).long()
         idx = (yi * W + xi).reshape(B, 1, H * W).expand(B, C, H * W)
-        val = flat.gather(2, idx).reshape(B, C, H, W)
-        wz = torch.where(ok, wt, torch.zeros_like(wt))
-        out = out + val * wz[:, None]
-        msk = msk + wz
+        val = flat.gather(2, idx).reshape(B, C, H, W) * ok[:, None]
+        one = ok.float()
+        if out is None:
+            out = val * wt[:, None]
+            msk = one * wt
+        else:
+            out = _fma(val, wt[:, None].expand_as(val), out)
+            msk = _fma(one, wt, msk)
     mask = msk[:, None].expand(B, C, H, W).clone()
     mask[mask < 0.999] = 0
     mask[mask > 0] = 1
