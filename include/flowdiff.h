@@ -19,6 +19,12 @@
 #include <stddef.h>
 #include <stdint.h>
 
+#if defined(FD_BUILDING_LIB)
+#define FD_API __attribute__((visibility("default")))
+#else
+#define FD_API
+#endif
+
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -29,19 +35,20 @@ extern "C" {
 #define FD_EARCH (-3)    /* device is not sm_100 */
 
 /* ---- library info ------------------------------------------------------------------ */
-int fd_version(void);                 /* 100 * major + minor */
-const char* fd_arch(void);            /* "sm_100a" */
-const char* fd_last_error(void);
-int fd_device_check(void);            /* FD_OK iff the current device is compute capability 10.x */
+FD_API int fd_version(void);                 /* 100 * major + minor */
+FD_API const char* fd_arch(void);            /* "sm_100a" */
+FD_API const char* fd_last_error(void);
+FD_API int fd_device_check(void);            /* FD_OK iff the current device is compute capability 10.x */
+FD_API int fd_num_sms(void);
 
 /* ---- backward bilinear warp:  warp.py:95-119 (warp_backward_flow) --------------------
  * flow channel 0 = dy, channel 1 = dx (the reference flips).  out is NOT multiplied by mask.
  * The coordinate / weight / accumulation sequence is the one torch's CPU grid_sample performs
  * (see oracle/flowdiff_oracle.py:backwarp) and is bit-exact against it. */
-int fd_backwarp_fwd(const float* image, const float* flow, float* out, float* mask,
+FD_API int fd_backwarp_fwd(const float* image, const float* flow, float* out, float* mask,
                     int B, int C, int H, int W, void* stream);
 /* grads of sum(out * gout): gimage (B,C,H,W) is zero-filled by the call; either may be NULL */
-int fd_backwarp_bwd(const float* image, const float* flow, const float* gout,
+FD_API int fd_backwarp_bwd(const float* image, const float* flow, const float* gout,
                     float* gimage, float* gflow, int B, int C, int H, int W, void* stream);
 
 /* fused warp + Charbonnier photometric + end-point error (BASELINE config #4):
@@ -50,51 +57,54 @@ int fd_backwarp_bwd(const float* image, const float* flow, const float* gout,
  *   sums[1] = sum(mask)                                     (over B*C*H*W, like the reference's mask)
  *   sums[2] = sum_px sqrt(du^2 + dv^2),  sums[3] = B*H*W
  * partials: workspace of fd_photo_epe_workspace_floats(B,H,W) floats.  Deterministic. */
-size_t fd_photo_epe_workspace_floats(int B, int H, int W);
-int fd_backwarp_photo_epe_fwd(const float* frame1, const float* frame2, const float* flow,
+FD_API size_t fd_photo_epe_workspace_floats(int B, int H, int W);
+FD_API int fd_backwarp_photo_epe_fwd(const float* frame1, const float* frame2, const float* flow,
                               const float* flow_gt, float* sums, float* partials,
                               int B, int C, int H, int W, void* stream);
 /* backward of  L = g_photo * sums[0]/sums[1] + g_epe * sums[2]/sums[3]  (mask treated as constant,
  * as autograd does through the reference's thresholding): gflow (B,2,H,W), gframe2 (B,C,H,W, zero-filled) */
-int fd_backwarp_photo_epe_bwd(const float* frame1, const float* frame2, const float* flow,
+FD_API int fd_backwarp_photo_epe_bwd(const float* frame1, const float* frame2, const float* flow,
                               const float* flow_gt, const float* sums, float g_photo, float g_epe,
                               float* gflow, float* gframe2, int B, int C, int H, int W, void* stream);
 
 /* ---- forward splat: softsplat_new.py:352-423 / 489-565 / 600-700 ----------------------
  * flow channel 0 = dx, channel 1 = dy.  out is (B,C,H/scale,W/scale) and is zero-filled by the call. */
-int fd_splat_fwd(const float* in, const float* flow, float* out,
+FD_API int fd_splat_fwd(const float* in, const float* flow, float* out,
                  int B, int C, int H, int W, int scale, int off_x, int off_y, void* stream);
-int fd_splat_ingrad(const float* flow, const float* gout, float* gin,
+FD_API int fd_splat_ingrad(const float* flow, const float* gout, float* gin,
                     int B, int C, int H, int W, int scale, int off_x, int off_y, void* stream);
-int fd_splat_flowgrad(const float* in, const float* flow, const float* gout, float* gflow,
+FD_API int fd_splat_flowgrad(const float* in, const float* flow, const float* gout, float* gflow,
                       int B, int C, int H, int W, int scale, int off_x, int off_y, void* stream);
-/* warp_forward_flow post-processing (warp.py:139-156): img[b,c] = wsum>0 ? splat[b,c] : NaN */
-int fd_splat_finish(const float* splat, float* img, int B, int C, int HW, int set_nans, void* stream);
+/* warp_forward_flow pre-processing (warp.py:122-126 + softsplat_new.py:301-302, mode linear_unn):
+ * ten_in (B,C+1,HW): [:C] = nan_to_zero(first) * w, [C] = w, w = any_c(isnan(first)) ? 0 : 1 */
+FD_API int fd_splat_prepare(const float* first, float* ten_in, int B, int C, int HW, void* stream);
+/* warp_forward_flow post-processing (warp.py:139-156): img[b,c] = splat[b,C]>0 ? splat[b,c] : NaN; splat is (B,C+1,HW) */
+FD_API int fd_splat_finish(const float* splat, float* img, int B, int C, int HW, int set_nans, void* stream);
 
 /* ---- NaN-aware MSE: warp.py:260-271 + torch.nanmean (denoising_diffusion.py:908,973) --------
- * sums[0] = sum over non-NaN pairs of (pred-target)^2, sums[1] = count; strided channel-slice views:
+ * sums[0] = sum over non-NaN pairs of (pred-target)^2, sums[1] = count, sums[2] = their ratio; strided channel-slice views:
  * element (b, c, i) lives at ptr[b*bstride + c*HW + i], c < C. */
-int fd_nan_mse_fwd(const float* pred, const float* target, float* sums, float* partials,
+FD_API int fd_nan_mse_fwd(const float* pred, const float* target, float* sums, float* partials,
                    int B, int C, int HW, long pred_bstride, long target_bstride, void* stream);
-size_t fd_nan_mse_workspace_floats(int B, int C, int HW);
+FD_API size_t fd_nan_mse_workspace_floats(int B, int C, int HW);
 /* gpred = gscale * 2 (pred-target) on non-NaN pairs else 0, gscale = upstream / count */
-int fd_nan_mse_bwd(const float* pred, const float* target, const float* sums, float upstream,
+FD_API int fd_nan_mse_bwd(const float* pred, const float* target, const float* sums, float upstream,
                    float* gpred, int B, int C, int HW, long pred_bstride, long target_bstride,
                    long gpred_bstride, void* stream);
 
 /* ---- scheduler: denoising_diffusion.py:806-812 (q_sample), 653-656 + 752-767 (DDIM),
  *      666-698 + 613-623 (DDPM ancestral) ---------------------------------------------------- */
 /* out = a[t_b] * x0 + s[t_b] * noise ; t int64 (B), tables fp32 device (T) */
-int fd_q_sample(const float* x0, const float* noise, const int64_t* t, const float* sqrt_ac,
+FD_API int fd_q_sample(const float* x0, const float* noise, const int64_t* t, const float* sqrt_ac,
                 const float* sqrt_1mac, float* out, int B, long per_sample, void* stream);
 /* x0 = clamp(model_out,-1,1); eps = (recip*x - x0)/recipm1;
  * last ? x_next = x0 : x_next = x0*sqrt_alpha_next + c*eps + sigma*noise (noise may be NULL iff sigma==0).
  * x0_out optional. In-place (x_next == x) allowed. */
-int fd_ddim_step(const float* x, const float* model_out, const float* noise, float* x_next, float* x0_out,
+FD_API int fd_ddim_step(const float* x, const float* model_out, const float* noise, float* x_next, float* x0_out,
                  long n, float recip, float recipm1, float sqrt_alpha_next, float c, float sigma,
                  int last, void* stream);
 /* x0 = clamp(model_out,-1,1); x_next = coef1*x0 + coef2*x + (noise ? sigma*noise : 0) */
-int fd_ddpm_step(const float* x, const float* model_out, const float* noise, float* x_next, float* x0_out,
+FD_API int fd_ddpm_step(const float* x, const float* model_out, const float* noise, float* x_next, float* x0_out,
                  long n, float coef1, float coef2, float sigma, void* stream);
 
 /* ---- UNet building blocks: denoising_diffusion.py:81-417 ---------------------------------- */
@@ -103,7 +113,7 @@ int fd_ddpm_step(const float* x, const float* model_out, const float* noise, flo
  * (bf16, 64 channels per pixel, zero outside the image / above Cpad*7).  x:(B,Cx,H,W) cond:(B,Cc,H,W)
  * fp32 NCHW; if nan_mask: NaNs of x become 0 and a channel any_c(isnan(x)) is inserted after x.
  * Ctot = Cx + nan_mask + Cc must be <= 9. */
-int fd_pack_input(const float* x, const float* cond, void* packed, int B, int Cx, int Cc, int H, int W,
+FD_API int fd_pack_input(const float* x, const float* cond, void* packed, int B, int Cx, int Cc, int H, int W,
                   int nan_mask, void* stream);
 
 /* Weight preparation.  w: fp32 [Cout][Cin][KH][KW] (torch layout) -> bf16 [Cout][K] K-major.
@@ -111,7 +121,7 @@ int fd_pack_input(const float* x, const float* cond, void* packed, int B, int Cx
  * kind 1: pixel-unshuffle 1x1 (:95-99): Cin = 4*C, torch channel c*4+p1*2+p2 -> K = (p1*2+p2)*C + c
  * kind 2: 7x7 init conv as 7 taps of 64: K = ky*64 + kx*Cin + ci, zero padded
  * standardize != 0 applies WeightStandardizedConv2d (:106-114) with eps before packing. */
-int fd_prep_weight(const float* w, void* packed, int Cout, int Cin, int KH, int KW, int kind,
+FD_API int fd_prep_weight(const float* w, void* packed, int Cout, int Cin, int KH, int KW, int kind,
                    int standardize, float eps, void* stream);
 
 /* Implicit-GEMM convolution on tcgen05 tensor cores (the nn.Conv2d / WeightStandardizedConv2d calls
@@ -123,51 +133,52 @@ int fd_prep_weight(const float* w, void* packed, int Cout, int Cin, int KH, int 
  * multiple of 128/192/256 tiles).
  * mode 0: KHxKW taps, zero padding (pad_h, pad_w), stride 1; H,W = spatial size of src and out.
  * mode 1: pixel-unshuffle + 1x1: src is (N, 2H, 2W, C0), taps (p1,p2), out (N,H,W,Cout).
- * gn_stats (optional): float [N][8][2]; (sum, sum of squares) of the stored values per sample and
+ * gn_stats (optional): double [N][8][2]; (sum, sum of squares) of the fp32 results per sample and
  *   GroupNorm group are atomically accumulated (caller zero-fills) -- the statistics pass of
- *   Block.forward's GroupNorm (:176,181) fused into the producer. */
-int fd_conv_igemm(const void* src0, int C0, const void* src1, int C1, const void* wpacked,
-                  const float* bias, const void* residual, void* out, float* gn_stats,
+ *   Block.forward's GroupNorm (:176,181) fused into the producer.
+ * 1x1 convolutions without statistics treat the whole batch as one row of pixels (any H, W). */
+FD_API int fd_conv_igemm(const void* src0, int C0, const void* src1, int C1, const void* wpacked,
+                  const float* bias, const void* residual, void* out, double* gn_stats,
                   int N, int H, int W, int Cout, int KH, int KW, int pad_h, int pad_w, int mode,
                   void* stream);
 
 /* GroupNorm(8) apply + optional (scale+1, shift) + SiLU (+ optional residual add), bf16 NHWC:
  * Block.forward :181-187 and ResnetBlock's "+ res_conv(x)" :214.  stats from fd_conv_igemm.
  * scale_shift: fp32 [N][2*C] (scale first, then shift: time_emb.chunk(2), :208) or NULL. */
-int fd_gn_silu(const void* x, const float* gn_stats, const float* gamma, const float* beta,
+FD_API int fd_gn_silu(const void* x, const double* gn_stats, const float* gamma, const float* beta,
                const float* scale_shift, const void* residual, void* out,
                int N, int HW, int C, float eps, void* stream);
 
 /* channel LayerNorm (:116-125) over C per pixel, out = (x-mean)*rsqrt(var+eps)*g (+ residual) */
-int fd_chan_layernorm(const void* x, const float* g, const void* residual, void* out,
+FD_API int fd_chan_layernorm(const void* x, const float* g, const void* residual, void* out,
                       long npix, int C, float eps, void* stream);
 
 /* nearest 2x upsample (:91), bf16 NHWC (N,H,W,C) -> (N,2H,2W,C) */
-int fd_upsample2x(const void* x, void* out, int N, int H, int W, int C, void* stream);
+FD_API int fd_upsample2x(const void* x, void* out, int N, int H, int W, int C, void* stream);
 
 /* SinusoidalPosEmb + time_mlp (:144-151, 319-324): t int64 (B) -> temb fp32 (B,256) */
-int fd_time_embed(const int64_t* t, const float* w1, const float* b1, const float* w2, const float* b2,
+FD_API int fd_time_embed(const int64_t* t, const float* w1, const float* b1, const float* w2, const float* b2,
                   float* temb, int B, int dim, int time_dim, void* stream);
 /* ResnetBlock.mlp (:193-196, 206): out[b][j] = bias[j] + sum_k silu(temb[b][k]) * w[j][k] ; w [J][time_dim] */
-int fd_time_proj(const float* temb, const float* w, const float* bias, float* out, int B, int time_dim,
+FD_API int fd_time_proj(const float* temb, const float* w, const float* bias, float* out, int B, int time_dim,
                  int J, void* stream);
 
 /* LinearAttention core (:229-243) on qkv bf16 (N, HW, 384) [q | k | v, each heads*32]:
  *   q softmax over d, *scale; k softmax over pixels; v / HW; ctx = k v^T; out = ctx^T q  -> bf16 (N,HW,128).
  * workspace floats: fd_linattn_workspace_floats(N, HW). */
-size_t fd_linattn_workspace_floats(int N, int HW);
-int fd_linattn(const void* qkv, void* out, float* workspace, int N, int HW, void* stream);
+FD_API size_t fd_linattn_workspace_floats(int N, int HW);
+FD_API int fd_linattn(const void* qkv, void* out, float* workspace, int N, int HW, void* stream);
 
 /* Attention core (:256-267): softmax(q^T k * 32^-0.5) v, flash-style, bf16 (N,HW,384) -> (N,HW,128) */
-int fd_attention(const void* qkv, void* out, int N, int HW, void* stream);
+FD_API int fd_attention(const void* qkv, void* out, int N, int HW, void* stream);
 
 /* final 1x1 conv (:361,417) 64 -> Cout (<=4) from bf16 NHWC to fp32 NCHW */
-int fd_final_conv(const void* x, const float* w, const float* bias, float* out, int N, int HW, int Cin,
+FD_API int fd_final_conv(const void* x, const float* w, const float* bias, float* out, int N, int HW, int Cin,
                   int Cout, void* stream);
 
 /* debug / test helpers: fp32 NCHW <-> bf16 NHWC */
-int fd_nchw_to_nhwc_bf16(const float* x, void* out, int N, int C, int HW, void* stream);
-int fd_nhwc_bf16_to_nchw(const void* x, float* out, int N, int C, int HW, void* stream);
+FD_API int fd_nchw_to_nhwc_bf16(const float* x, void* out, int N, int C, int HW, void* stream);
+FD_API int fd_nhwc_bf16_to_nchw(const void* x, float* out, int N, int C, int HW, void* stream);
 
 #ifdef __cplusplus
 }

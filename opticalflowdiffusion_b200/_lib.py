@@ -1,0 +1,92 @@
+"""ctypes binding of ``libflowdiff.so`` (the C ABI declared in ``include/flowdiff.h``).
+
+There is no fallback: if the library is missing or the device is not sm_100 every op raises.
+PyTorch is used for device memory and streams only; pointers are passed as plain integers.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_char_p, c_float, c_int, c_int64, c_long, c_size_t, c_void_p
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libflowdiff.so")
+
+_P, _I, _L, _F = c_void_p, c_int, c_long, c_float
+
+# name -> (restype, argtypes); must list every symbol include/flowdiff.h declares
+SIGNATURES = {
+    "fd_version": (c_int, []),
+    "fd_arch": (c_char_p, []),
+    "fd_last_error": (c_char_p, []),
+    "fd_device_check": (c_int, []),
+    "fd_num_sms": (c_int, []),
+    "fd_backwarp_fwd": (c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),
+    "fd_backwarp_bwd": (c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
+    "fd_photo_epe_workspace_floats": (c_size_t, [_I, _I, _I]),
+    "fd_backwarp_photo_epe_fwd": (c_int, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
+    "fd_backwarp_photo_epe_bwd": (c_int, [_P, _P, _P, _P, _P, _F, _F, _P, _P, _I, _I, _I, _I, _P]),
+    "fd_splat_fwd": (c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
+    "fd_splat_ingrad": (c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
+    "fd_splat_flowgrad": (c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
+    "fd_splat_prepare": (c_int, [_P, _P, _I, _I, _I, _P]),
+    "fd_splat_finish": (c_int, [_P, _P, _I, _I, _I, _I, _P]),
+    "fd_nan_mse_workspace_floats": (c_size_t, [_I, _I, _I]),
+    "fd_nan_mse_fwd": (c_int, [_P, _P, _P, _P, _I, _I, _I, _L, _L, _P]),
+    "fd_nan_mse_bwd": (c_int, [_P, _P, _P, _F, _P, _I, _I, _I, _L, _L, _L, _P]),
+    "fd_q_sample": (c_int, [_P, _P, _P, _P, _P, _P, _I, _L, _P]),
+    "fd_ddim_step": (c_int, [_P, _P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _I, _P]),
+    "fd_ddpm_step": (c_int, [_P, _P, _P, _P, _P, _L, _F, _F, _F, _P]),
+    "fd_conv_igemm": (c_int, [_P, _I, _P, _I, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
+}
+
+
+class FlowDiffError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load(check_device: bool = False):
+    """Load the shared library (once).  Raises FlowDiffError if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise FlowDiffError(
+                f"{LIB_PATH} is missing: build it with `python -m opticalflowdiffusion_b200.build` "
+                "(there is no CPU or PyTorch fallback for the flow_diffuser kernels)")
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)            # AttributeError if the symbol is not exported
+            fn.restype, fn.argtypes = res, args
+        _lib = lib
+    if check_device:
+        rc = _lib.fd_device_check()
+        if rc != 0:
+            raise FlowDiffError(_lib.fd_last_error().decode())
+    return _lib
+
+
+def check(rc: int):
+    if rc != 0:
+        raise FlowDiffError(f"libflowdiff error {rc}: {load().fd_last_error().decode()}")
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL)."""
+    if t is None:
+        return None
+    return t.data_ptr()
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise FlowDiffError("libflowdiff operates on CUDA tensors only (no CPU fallback)")

@@ -76,3 +76,45 @@ __device__ __forceinline__ float2 fd_unpack_bf16(uint32_t u) {
   __nv_bfloat162 h = *reinterpret_cast<__nv_bfloat162*>(&u);
   return __bfloat1622float2(h);
 }
+
+// ---------------------------------------------------------------------------------------------
+// scatter with in-thread and neighbour-lane merging.  Must be called by all 32 lanes of a warp.
+// addr[k] < 0 marks "no contribution".  Entries are ordered left to right along the row, so equal
+// addresses are adjacent whenever the flow is locally smooth.
+// ---------------------------------------------------------------------------------------------
+template <int N>
+__device__ __forceinline__ void fd_scatter_merged(float* __restrict__ plane, const int (&addr)[N], const float (&val)[N]) {
+  int haddr = -1, taddr = -1;
+  float hval = 0.f, tval = 0.f;
+  bool have_head = false;
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    if (addr[k] < 0) continue;
+    if (addr[k] == taddr) {
+      tval += val[k];
+    } else {
+      if (taddr >= 0) {
+        if (!have_head) {
+          haddr = taddr; hval = tval; have_head = true;
+        } else {
+          atomicAdd(plane + taddr, tval);
+        }
+      }
+      taddr = addr[k];
+      tval = val[k];
+    }
+  }
+  if (!have_head) {  // zero or one group: it is the head, nothing is offered to the next lane
+    haddr = taddr; hval = tval; taddr = -1; tval = 0.f;
+  }
+  const int lane = threadIdx.x & 31;
+  // offer the tail group to lane+1; it absorbs it when its head hits the same address
+  int raddr = __shfl_up_sync(0xffffffffu, taddr, 1);
+  float rval = __shfl_up_sync(0xffffffffu, tval, 1);
+  bool absorb = (lane > 0) && (raddr >= 0) && (raddr == haddr);
+  if (absorb) hval += rval;
+  const bool taken = __shfl_down_sync(0xffffffffu, (int)absorb, 1) != 0 && lane < 31;
+  if (haddr >= 0) atomicAdd(plane + haddr, hval);
+  if (taddr >= 0 && !taken) atomicAdd(plane + taddr, tval);
+}
+

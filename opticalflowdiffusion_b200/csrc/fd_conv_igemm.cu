@@ -1,0 +1,405 @@
+// Implicit-GEMM convolution on the 5th-generation tensor cores (tcgen05 + TMEM), operands staged
+// by TMA.  Replaces every nn.Conv2d / WeightStandardizedConv2d call of the reference UNet
+// (denoising_diffusion.py:92,98,114,200,222,225,253,254,297,339,354).
+//
+//   GEMM view:  M = output pixels (tile of 128 = R rows x Wt columns of ONE image),
+//               N = output channels (tile BLOCK_N in {64,128,256}),
+//               K = taps x input channels, consumed in blocks of 64 channels of one tap.
+//
+//   A operand:  activations are bf16 NHWC, i.e. every pixel is a 128-byte row per 64 channels.  A
+//               K-block of A for tap (ky,kx) is the box {64 ch, Wt, R} of the input shifted by
+//               (ky-pad, kx-pad): one TMA box load.  TMA zero-fills out-of-bounds elements, which
+//               implements the convolution's zero padding with no branches and no im2col buffer;
+//               the 128B-swizzled box lands in shared memory exactly in the canonical K-major
+//               UMMA layout.  The skip-connection concat (:405,408,414) is a second tensor map
+//               whose channels simply extend K; the pixel-unshuffle downsample (:95-99) is a 5-d
+//               view (c, p2, w, p1, h) of the same tensor so its 1x1 conv needs no rearranged copy.
+//   B operand:  weights packed bf16 [Cout][K] (K-major), 2-d TMA box {64, BLOCK_N}.
+//   D:          fp32 in TMEM, double buffered (2 x BLOCK_N columns) so the epilogue of tile i
+//               overlaps the MMAs of tile i+1.
+//
+//   Warp roles (192 threads, persistent CTA per SM, static round-robin tile schedule):
+//     warp 0    TMA producer (one elected lane), STAGES-deep mbarrier ring
+//     warp 1    TMEM allocator + MMA issuer (one lane issues tcgen05.mma, tcgen05.commit frees slots)
+//     warps 2-5 epilogue: tcgen05.ld -> +bias (+residual) -> GroupNorm partial statistics
+//               (sum, sum of squares per (sample, group), :176,181) -> bf16 NHWC store
+#include "fd_tc.cuh"
+
+using namespace fdtc;
+
+namespace {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;
+constexpr int kATileBytes = kBlockM * kBlockK * 2;  // 16 KiB
+constexpr int kThreads = 192;
+constexpr int kEpiThreads = 128;
+
+struct ConvParams {
+  int N, H, W;        // images, output rows, output columns (after flattening / merging)
+  int Cout;
+  int KW;             // taps per row
+  int taps;           // KH*KW (4 for the pixel-unshuffle mode)
+  int pad_h, pad_w;
+  int mode;           // 0: conv taps with zero padding, 1: pixel-unshuffle + 1x1
+  int chunks0, chunks1;  // 64-channel chunks of src0 / src1
+  int R, Wt;          // tile = R rows x Wt columns, R*Wt == 128
+  int tiles_w, tiles_h, n_tiles, total_tiles;
+  int cpg;            // channels per GroupNorm group (Cout/8)
+  const float* bias;
+  const __nv_bfloat16* residual;
+  __nv_bfloat16* out;
+  double* gn_stats;   // [N][8][2] or null
+};
+
+template <int BLOCK_N>
+struct Cfg {
+  static constexpr int kBTileBytes = BLOCK_N * kBlockK * 2;
+  static constexpr int kStageBytes = kATileBytes + kBTileBytes;
+  static constexpr int kStages = BLOCK_N == 64 ? 8 : (BLOCK_N == 128 ? 6 : 4);
+  static constexpr int kTmemCols = 2 * BLOCK_N;
+  // ring + barriers + bias (2 x BLOCK_N floats) + stats (2 x 16 floats) + tmem ptr, plus 1 KiB alignment slack
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256 + 2 * BLOCK_N * 4 + 2 * 16 * 4 + 64;
+};
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
+                  const __grid_constant__ CUtensorMap map_b, const ConvParams p) {
+  using C = Cfg<BLOCK_N>;
+  constexpr int STAGES = C::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // SWIZZLE_128B tiles need 1024-byte alignment
+  uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t a_smem = base;
+  const uint32_t b_smem = base + STAGES * kATileBytes;
+  const uint32_t bar_base = base + STAGES * C::kStageBytes;
+  // barriers: full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2]
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 2 + s); };
+  uint8_t* gtail = gbase + STAGES * C::kStageBytes + 256;
+  float* s_bias = reinterpret_cast<float*>(gtail);                       // [2][BLOCK_N]
+  float* s_stats = reinterpret_cast<float*>(gtail + 2 * BLOCK_N * 4);    // [2][16]
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(gtail + 2 * BLOCK_N * 4 + 2 * 16 * 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int cpt = p.chunks0 + p.chunks1;       // 64-channel chunks per tap
+  const int num_kb = p.taps * cpt;
+  const int tiles_per_img = p.tiles_w * p.tiles_h;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a0);
+    tma_prefetch_desc(&map_a1);
+    tma_prefetch_desc(&map_b);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tfull_bar(s), 1);
+      mbar_init(tempty_bar(s), kEpiThreads);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(smem_u32(s_tmem), C::kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *s_tmem;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const int n_tile = tile % p.n_tiles;
+        const int m_tile = tile / p.n_tiles;
+        const int img = m_tile / tiles_per_img;
+        const int rem = m_tile - img * tiles_per_img;
+        const int h0 = (rem / p.tiles_w) * p.R;
+        const int w0 = (rem % p.tiles_w) * p.Wt;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          const int tap = kb / cpt;
+          const int chunk = kb - tap * cpt;
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          mbar_expect_tx(full_bar(stage), C::kStageBytes);
+          const CUtensorMap* ma = chunk < p.chunks0 ? &map_a0 : &map_a1;
+          const int c0 = (chunk < p.chunks0 ? chunk : chunk - p.chunks0) * kBlockK;
+          const uint32_t dst_a = a_smem + stage * kATileBytes;
+          if (p.mode == 0) {
+            const int ky = tap / p.KW, kx = tap - ky * p.KW;
+            tma_load_5d(dst_a, ma, full_bar(stage), c0, w0 + kx - p.pad_w, h0 + ky - p.pad_h, img, 0);
+          } else {
+            tma_load_5d(dst_a, ma, full_bar(stage), c0, tap & 1, w0, tap >> 1, h0);
+          }
+          tma_load_2d(b_smem + stage * C::kBTileBytes, &map_b, full_bar(stage), kb * kBlockK, n_tile * BLOCK_N);
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc = umma_idesc_bf16(kBlockM, BLOCK_N);
+    int stage = 0;
+    uint32_t phase = 0;
+    int iter = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++iter) {
+      const int as = iter & 1;
+      const uint32_t aphase = (iter >> 1) & 1;
+      mbar_wait(tempty_bar(as), aphase ^ 1u);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + as * BLOCK_N;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(full_bar(stage), phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint64_t adesc = umma_desc_sw128(a_smem + stage * kATileBytes);
+          const uint64_t bdesc = umma_desc_sw128(b_smem + stage * C::kBTileBytes);
+#pragma unroll
+          for (int k = 0; k < kBlockK / 16; ++k) {
+            // advance 16 bf16 (32 B) along K inside the 128-byte swizzle atom: +2 in the (addr >> 4) field
+            umma_bf16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(empty_bar(stage));                      // frees the smem slot when the MMAs retire
+          if (kb == num_kb - 1) umma_commit(tfull_bar(as));   // accumulator complete -> epilogue
+        }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int et = threadIdx.x - 64;          // 0..127
+    const int quarter = warp & 3;             // TMEM lane quarter this warp may access
+    const int row = quarter * 32 + lane;      // accumulator row = pixel within the tile
+    const int rr = row / p.Wt, ww = row - rr * p.Wt;
+    int iter = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++iter) {
+      const int as = iter & 1;
+      const uint32_t aphase = (iter >> 1) & 1;
+      const int n_tile = tile % p.n_tiles;
+      const int m_tile = tile / p.n_tiles;
+      const int img = m_tile / tiles_per_img;
+      const int rem = m_tile - img * tiles_per_img;
+      const int h = (rem / p.tiles_w) * p.R + rr;
+      const int w = (rem % p.tiles_w) * p.Wt + ww;
+      const bool valid = (h < p.H) && (w < p.W);
+      const int n0 = n_tile * BLOCK_N;
+      float* bias_s = s_bias + as * BLOCK_N;
+      float* stats_s = s_stats + as * 16;
+      for (int i = et; i < BLOCK_N; i += kEpiThreads) bias_s[i] = p.bias ? __ldg(p.bias + n0 + i) : 0.f;
+      if (et < 16) stats_s[et] = 0.f;
+      named_bar_sync(1, kEpiThreads);
+
+      mbar_wait(tfull_bar(as), aphase);
+      tc_fence_after();
+      const long pix = ((long)img * p.H + h) * p.W + w;
+      __nv_bfloat16* orow = p.out + pix * p.Cout + n0;
+      const __nv_bfloat16* rrow = p.residual ? p.residual + pix * p.Cout + n0 : nullptr;
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N; c += 32) {
+        uint32_t acc[32];
+        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BLOCK_N + c), acc);
+        tmem_ld_wait();
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]) + bias_s[c + j];
+        if (rrow != nullptr && valid) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const uint4 r4 = __ldg(reinterpret_cast<const uint4*>(rrow + c) + q);
+            const uint32_t rw[4] = {r4.x, r4.y, r4.z, r4.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 f = fd_unpack_bf16(rw[e]);
+              v[q * 8 + e * 2] += f.x;
+              v[q * 8 + e * 2 + 1] += f.y;
+            }
+          }
+        }
+        if (p.gn_stats != nullptr) {
+          // channels [n0+c, n0+c+32) belong to 32/cpg groups (cpg < 32) or to a part of one group
+          const int span = p.cpg < 32 ? p.cpg : 32;
+#pragma unroll 1
+          for (int g0 = 0; g0 < 32; g0 += span) {
+            float s = 0.f, ss = 0.f;
+            if (valid) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (j >= g0 && j < g0 + span) { s += v[j]; ss += v[j] * v[j]; }
+            }
+            s = fd_warp_sum(s);
+            ss = fd_warp_sum(ss);
+            if (lane == 0) {
+              const int grp = (n0 + c + g0) / p.cpg;
+              atomicAdd(stats_s + grp * 2, s);
+              atomicAdd(stats_s + grp * 2 + 1, ss);
+            }
+          }
+        }
+        if (valid) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            uint4 o;
+            o.x = fd_pack_bf16(v[q * 8 + 0], v[q * 8 + 1]);
+            o.y = fd_pack_bf16(v[q * 8 + 2], v[q * 8 + 3]);
+            o.z = fd_pack_bf16(v[q * 8 + 4], v[q * 8 + 5]);
+            o.w = fd_pack_bf16(v[q * 8 + 6], v[q * 8 + 7]);
+            reinterpret_cast<uint4*>(orow + c)[q] = o;
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(tempty_bar(as));             // accumulator stage may be overwritten
+      if (p.gn_stats != nullptr) {
+        named_bar_sync(2, kEpiThreads);
+        if (et < 16) {
+          const float sv = stats_s[et];
+          if (sv != 0.f) atomicAdd(p.gn_stats + (long)img * 16 + et, (double)sv);
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C::kTmemCols);
+  }
+}
+
+struct TileShape {
+  int R, Wt;
+};
+
+// R x Wt = 128 covering an H x W image with the least padding waste (ties -> widest tile)
+TileShape pick_tile(int H, int W) {
+  TileShape best{1, 128};
+  long best_cost = -1;
+  for (int wt = 128; wt >= 8; wt >>= 1) {
+    const int r = 128 / wt;
+    const long cost = (long)((W + wt - 1) / wt) * wt * (long)((H + r - 1) / r) * r;
+    if (best_cost < 0 || cost < best_cost) {
+      best_cost = cost;
+      best = TileShape{r, wt};
+    }
+  }
+  return best;
+}
+
+template <int BLOCK_N>
+int launch(const CUtensorMap& ma0, const CUtensorMap& ma1, const CUtensorMap& mb, const ConvParams& p, int sms,
+           cudaStream_t st) {
+  using C = Cfg<BLOCK_N>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    FD_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
+    attr_set = true;
+  }
+  const int grid = p.total_tiles < sms ? p.total_tiles : sms;
+  conv_igemm_kernel<BLOCK_N><<<grid, kThreads, C::kSmemBytes, st>>>(ma0, ma1, mb, p);
+  FD_LAUNCH_CHECK();
+  return FD_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int fd_conv_igemm(const void* src0, int C0, const void* src1, int C1, const void* wpacked, const float* bias,
+                  const void* residual, void* out, double* gn_stats, int N, int H, int W, int Cout, int KH, int KW,
+                  int pad_h, int pad_w, int mode, void* stream) {
+  FD_REQUIRE(src0 && wpacked && out, "conv_igemm: null pointer");
+  FD_REQUIRE(N > 0 && H > 0 && W > 0, "conv_igemm: bad geometry N=%d H=%d W=%d", N, H, W);
+  FD_REQUIRE(C0 > 0 && C0 % 64 == 0 && C1 >= 0 && C1 % 64 == 0, "conv_igemm: C0=%d C1=%d must be multiples of 64", C0, C1);
+  FD_REQUIRE(src1 != nullptr || C1 == 0, "conv_igemm: C1 > 0 needs src1");
+  FD_REQUIRE(Cout > 0 && Cout % 64 == 0, "conv_igemm: Cout=%d must be a multiple of 64", Cout);
+  FD_REQUIRE(mode == 0 || mode == 1, "conv_igemm: mode %d", mode);
+  FD_REQUIRE(mode == 0 || (C1 == 0 && gn_stats == nullptr), "conv_igemm: mode 1 takes one source and no statistics");
+  FD_REQUIRE(KH >= 1 && KW >= 1 && KH * KW <= 64, "conv_igemm: bad kernel %dx%d", KH, KW);
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    FD_CUDA(cudaGetDevice(&dev));
+    FD_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  ConvParams p{};
+  p.Cout = Cout;
+  p.mode = mode;
+  p.chunks0 = C0 / 64;
+  p.chunks1 = C1 / 64;
+  p.bias = bias;
+  p.residual = static_cast<const __nv_bfloat16*>(residual);
+  p.out = static_cast<__nv_bfloat16*>(out);
+  p.gn_stats = gn_stats;
+  p.cpg = Cout / 8;
+  CUtensorMap ma0, ma1, mb;
+  TileShape ts;
+  if (mode == 0) {
+    int n = N, h = H, w = W;
+    if (KH == 1 && KW == 1 && pad_h == 0 && pad_w == 0 && gn_stats == nullptr) {
+      // 1x1: no halo, so every pixel of the batch is one long row -> full 128-pixel tiles for any W
+      FD_REQUIRE((long)N * H * W < (1L << 31), "conv_igemm: too many pixels");
+      w = N * H * W;
+      h = 1;
+      n = 1;
+    }
+    p.N = n; p.H = h; p.W = w;
+    p.KW = KW;
+    p.taps = KH * KW;
+    p.pad_h = pad_h;
+    p.pad_w = pad_w;
+    ts = pick_tile(h, w);
+    const uint32_t box[5] = {64, (uint32_t)ts.Wt, (uint32_t)ts.R, 1, 1};
+    {
+      const uint64_t dims[5] = {(uint64_t)C0, (uint64_t)w, (uint64_t)h, (uint64_t)n, 1};
+      const uint64_t str[4] = {(uint64_t)C0 * 2, (uint64_t)w * C0 * 2, (uint64_t)h * w * C0 * 2, (uint64_t)n * h * w * C0 * 2};
+      if (int e = make_tmap_bf16(&ma0, src0, 5, dims, str, box)) return e;
+    }
+    if (C1 > 0) {
+      const uint64_t dims[5] = {(uint64_t)C1, (uint64_t)w, (uint64_t)h, (uint64_t)n, 1};
+      const uint64_t str[4] = {(uint64_t)C1 * 2, (uint64_t)w * C1 * 2, (uint64_t)h * w * C1 * 2, (uint64_t)n * h * w * C1 * 2};
+      if (int e = make_tmap_bf16(&ma1, src1, 5, dims, str, box)) return e;
+    } else {
+      ma1 = ma0;
+    }
+  } else {
+    // src is (N, 2H, 2W, C0); output rows of all images are merged (no halo -> tiles may span images)
+    p.N = 1; p.H = N * H; p.W = W;
+    p.KW = 2;
+    p.taps = 4;
+    ts = pick_tile(p.H, p.W);
+    const uint64_t dims[5] = {(uint64_t)C0, 2, (uint64_t)W, 2, (uint64_t)N * H};
+    const uint64_t str[4] = {(uint64_t)C0 * 2, (uint64_t)2 * C0 * 2, (uint64_t)2 * W * C0 * 2, (uint64_t)4 * W * C0 * 2};
+    const uint32_t box[5] = {64, 1, (uint32_t)ts.Wt, 1, (uint32_t)ts.R};
+    if (int e = make_tmap_bf16(&ma0, src0, 5, dims, str, box)) return e;
+    ma1 = ma0;
+  }
+  p.R = ts.R;
+  p.Wt = ts.Wt;
+  p.tiles_w = (p.W + ts.Wt - 1) / ts.Wt;
+  p.tiles_h = (p.H + ts.R - 1) / ts.R;
+  const int block_n = (Cout % 256 == 0) ? 256 : ((Cout % 128 == 0) ? 128 : 64);
+  p.n_tiles = Cout / block_n;
+  const long total = (long)p.N * p.tiles_w * p.tiles_h * p.n_tiles;
+  FD_REQUIRE(total < (1L << 31), "conv_igemm: too many tiles");
+  p.total_tiles = (int)total;
+  {
+    const uint64_t K = (uint64_t)p.taps * (C0 + C1);
+    const uint64_t dims[2] = {K, (uint64_t)Cout};
+    const uint64_t str[1] = {K * 2};
+    const uint32_t box[2] = {64, (uint32_t)block_n};
+    if (int e = make_tmap_bf16(&mb, wpacked, 2, dims, str, box)) return e;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  if (block_n == 256) return launch<256>(ma0, ma1, mb, p, sms, st);
+  if (block_n == 128) return launch<128>(ma0, ma1, mb, p, sms, st);
+  return launch<64>(ma0, ma1, mb, p, sms, st);
+}
+
+}  // extern "C"

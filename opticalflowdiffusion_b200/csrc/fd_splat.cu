@@ -1,0 +1,378 @@
+// Forward splat ("softsplat") trio: softsplat_new.py:352-423 (out), :489-565 (ingrad),
+// :600-700 (flowgrad) of the reference, plus warp_forward_flow's pre/post-processing
+// (warp.py:121-156).  fp32 NCHW, flow channel 0 = dx, channel 1 = dy.
+//
+// B200 layout: the reference runs one thread per *element* and recomputes the geometry per
+// channel; here one thread owns VEC (=4 when W % 4 == 0) consecutive pixels of a row, computes the
+// remapped coordinate once and loops over channels, with 128-bit loads of flow / input.  The
+// forward scatter merges equal target addresses inside a thread and with the neighbouring lane
+// before issuing red.global.add.f32 (several source pixels land in one target cell whenever
+// scale > 1 or the flow is smooth).
+//
+// The reference's scale/offset remap mixes float and double arithmetic and differs between the
+// three kernels; every such quirk is kept:
+//   out      : the ">= size-1" branch only when scale > 1                        (:374-390)
+//   ingrad   : that branch always; X additionally applies "* offset_x"           (:515-532)
+//   flowgrad : that branch always; Y uses "* offset_y" instead of the abs/% form; the derivative
+//              factor is 1/scale only in the last branch ("freeze gradient") and channel 0 (d/dx)
+//              is scaled by the Y factor, channel 1 by the X factor               (:626-672)
+#include "fd_common.cuh"
+
+namespace {
+
+enum { KIND_OUT = 0, KIND_INGRAD = 1, KIND_FLOWGRAD = 2 };
+enum { AXIS_X = 0, AXIS_Y = 1 };
+
+template <int KIND, int AXIS>
+__device__ __forceinline__ float splat_remap(float f, int size, int scale, int offset, float& dflt) {
+  dflt = 0.f;
+  const float fsize = (float)size;
+  bool upper = (double)f >= (double)fsize - 1.0;
+  if (KIND == KIND_OUT) upper = upper && (scale > 1);
+  if (upper) {
+    int k = abs(offset - (size % scale)) % scale;
+    if (KIND == KIND_FLOWGRAD && AXIS == AXIS_Y) k = offset;
+    float r = (float)((double)f + ((double)__fsub_rn(f, fsize) + 1.0) * (double)(float)k);
+    if (KIND == KIND_INGRAD && AXIS == AXIS_X)
+      r = (float)((double)r + ((double)__fsub_rn(r, fsize) + 1.0) * (double)(float)offset);
+    return __fdiv_rn(__fsub_rn(r, (float)offset), (float)scale);
+  }
+  const float fo = __fsub_rn(f, (float)offset);
+  if ((double)fo < 0.0) return fo;
+  dflt = __fdiv_rn(1.0f, (float)scale);
+  return __fdiv_rn(fo, (float)scale);
+}
+
+struct SplatTaps {
+  float nw, ne, sw, se;
+  float fx, fy;
+  float dxx, dyy;
+  int x0, y0;
+  bool ok;                       // finite
+  bool okx0, okx1, oky0, oky1;   // inside the target plane
+};
+
+template <int KIND>
+__device__ __forceinline__ void splat_taps(float flow_x, float flow_y, int x, int y, int H, int W, int Ho, int Wo,
+                                           int scale, int off_x, int off_y, SplatTaps& t) {
+  float fx = __fadd_rn((float)x, flow_x);
+  float fy = __fadd_rn((float)y, flow_y);
+  t.ok = isfinite(fx) && isfinite(fy);
+  if (!t.ok) { fx = 0.f; fy = 0.f; }
+  fx = splat_remap<KIND, AXIS_X>(fx, W, scale, off_x, t.dxx);
+  fy = splat_remap<KIND, AXIS_Y>(fy, H, scale, off_y, t.dyy);
+  t.fx = fx;
+  t.fy = fy;
+  const float x0f = floorf(fx), y0f = floorf(fy);
+  // the reference converts floor() to int; out-of-range values fail the bounds test either way
+  const bool xr = x0f >= -2.f && x0f <= (float)Wo;
+  const bool yr = y0f >= -2.f && y0f <= (float)Ho;
+  t.x0 = xr ? (int)x0f : -4;
+  t.y0 = yr ? (int)y0f : -4;
+  const float x1 = (float)(t.x0 + 1), y1 = (float)(t.y0 + 1), x0 = (float)t.x0, y0 = (float)t.y0;
+  t.nw = __fmul_rn(__fsub_rn(x1, fx), __fsub_rn(y1, fy));
+  t.ne = __fmul_rn(__fsub_rn(fx, x0), __fsub_rn(y1, fy));
+  t.sw = __fmul_rn(__fsub_rn(x1, fx), __fsub_rn(fy, y0));
+  t.se = __fmul_rn(__fsub_rn(fx, x0), __fsub_rn(fy, y0));
+  t.okx0 = t.ok && t.x0 >= 0 && t.x0 < Wo;
+  t.okx1 = t.ok && t.x0 + 1 >= 0 && t.x0 + 1 < Wo;
+  t.oky0 = t.y0 >= 0 && t.y0 < Ho;
+  t.oky1 = t.y0 + 1 >= 0 && t.y0 + 1 < Ho;
+}
+
+template <int VEC>
+struct SVec;
+template <>
+struct SVec<1> {
+  float v[1];
+  __device__ __forceinline__ void load(const float* p) { v[0] = __ldg(p); }
+  __device__ __forceinline__ void store(float* p) const { *p = v[0]; }
+};
+template <>
+struct SVec<4> {
+  float v[4];
+  __device__ __forceinline__ void load(const float* p) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(p));
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  }
+  __device__ __forceinline__ void store(float* p) const {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+};
+
+template <int VEC>
+__device__ __forceinline__ void s_item_to_byx(long item, int H, int W, int& b, int& y, int& x) {
+  const int wq = W / VEC;
+  x = (int)(item % wq) * VEC;
+  const long r = item / wq;
+  y = (int)(r % H);
+  b = (int)(r / H);
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(256) splat_fwd_kernel(const float* __restrict__ in, const float* __restrict__ flow,
+                                                        float* __restrict__ out, int B, int C, int H, int W, int Ho,
+                                                        int Wo, int scale, int off_x, int off_y, long items) {
+  const long HW = (long)H * W, HWo = (long)Ho * Wo;
+  const int lane = threadIdx.x & 31;
+  for (long base = (long)blockIdx.x * blockDim.x + (threadIdx.x & ~31); base < items;
+       base += (long)gridDim.x * blockDim.x) {
+    const long item = base + lane;
+    const bool valid = item < items;
+    int b = 0, y = 0, x = 0;
+    if (valid) s_item_to_byx<VEC>(item, H, W, b, y, x);
+    const long pix = (long)y * W + x;
+    SVec<VEC> fx, fy;
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) fx.v[j] = fy.v[j] = 0.f;
+    if (valid) {
+      fx.load(flow + ((long)b * 2 + 0) * HW + pix);
+      fy.load(flow + ((long)b * 2 + 1) * HW + pix);
+    }
+    SplatTaps t[VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) splat_taps<KIND_OUT>(fx.v[j], fy.v[j], x + j, y, H, W, Ho, Wo, scale, off_x, off_y, t[j]);
+    for (int c = 0; c < C; ++c) {
+      SVec<VEC> a;
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) a.v[j] = 0.f;
+      if (valid) a.load(in + ((long)b * C + c) * HW + pix);
+      int a0[2 * VEC], a1[2 * VEC];
+      float v0[2 * VEC], v1[2 * VEC];
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) {
+        const int r0 = t[j].y0 * Wo + t[j].x0;
+        a0[2 * j] = (valid && t[j].okx0 && t[j].oky0) ? r0 : -1;
+        a0[2 * j + 1] = (valid && t[j].okx1 && t[j].oky0) ? r0 + 1 : -1;
+        a1[2 * j] = (valid && t[j].okx0 && t[j].oky1) ? r0 + Wo : -1;
+        a1[2 * j + 1] = (valid && t[j].okx1 && t[j].oky1) ? r0 + Wo + 1 : -1;
+        v0[2 * j] = __fmul_rn(a.v[j], t[j].nw);
+        v0[2 * j + 1] = __fmul_rn(a.v[j], t[j].ne);
+        v1[2 * j] = __fmul_rn(a.v[j], t[j].sw);
+        v1[2 * j + 1] = __fmul_rn(a.v[j], t[j].se);
+      }
+      float* plane = out + ((long)b * C + c) * HWo;
+      fd_scatter_merged<2 * VEC>(plane, a0, v0);
+      fd_scatter_merged<2 * VEC>(plane, a1, v1);
+    }
+  }
+}
+
+__device__ __forceinline__ float tap_or_zero(const float* __restrict__ plane, bool ok, int idx) {
+  return ok ? __ldg(plane + idx) : 0.f;
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(256) splat_ingrad_kernel(const float* __restrict__ flow,
+                                                           const float* __restrict__ gout, float* __restrict__ gin,
+                                                           int B, int C, int H, int W, int Ho, int Wo, int scale,
+                                                           int off_x, int off_y, long items) {
+  const long HW = (long)H * W, HWo = (long)Ho * Wo;
+  for (long item = (long)blockIdx.x * blockDim.x + threadIdx.x; item < items; item += (long)gridDim.x * blockDim.x) {
+    int b, y, x;
+    s_item_to_byx<VEC>(item, H, W, b, y, x);
+    const long pix = (long)y * W + x;
+    SVec<VEC> fx, fy;
+    fx.load(flow + ((long)b * 2 + 0) * HW + pix);
+    fy.load(flow + ((long)b * 2 + 1) * HW + pix);
+    SplatTaps t[VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j)
+      splat_taps<KIND_INGRAD>(fx.v[j], fy.v[j], x + j, y, H, W, Ho, Wo, scale, off_x, off_y, t[j]);
+    for (int c = 0; c < C; ++c) {
+      const float* plane = gout + ((long)b * C + c) * HWo;
+      SVec<VEC> g;
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) {
+        const int r0 = t[j].y0 * Wo + t[j].x0;
+        float acc = 0.f;
+        acc += tap_or_zero(plane, t[j].okx0 && t[j].oky0, r0) * t[j].nw;
+        acc += tap_or_zero(plane, t[j].okx1 && t[j].oky0, r0 + 1) * t[j].ne;
+        acc += tap_or_zero(plane, t[j].okx0 && t[j].oky1, r0 + Wo) * t[j].sw;
+        acc += tap_or_zero(plane, t[j].okx1 && t[j].oky1, r0 + Wo + 1) * t[j].se;
+        g.v[j] = acc;
+      }
+      g.store(gin + ((long)b * C + c) * HW + pix);
+    }
+  }
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(256) splat_flowgrad_kernel(const float* __restrict__ in,
+                                                             const float* __restrict__ flow,
+                                                             const float* __restrict__ gout,
+                                                             float* __restrict__ gflow, int B, int C, int H, int W,
+                                                             int Ho, int Wo, int scale, int off_x, int off_y,
+                                                             long items) {
+  const long HW = (long)H * W, HWo = (long)Ho * Wo;
+  for (long item = (long)blockIdx.x * blockDim.x + threadIdx.x; item < items; item += (long)gridDim.x * blockDim.x) {
+    int b, y, x;
+    s_item_to_byx<VEC>(item, H, W, b, y, x);
+    const long pix = (long)y * W + x;
+    SVec<VEC> fx, fy;
+    fx.load(flow + ((long)b * 2 + 0) * HW + pix);
+    fy.load(flow + ((long)b * 2 + 1) * HW + pix);
+    SplatTaps t[VEC];
+    float gx[VEC], gy[VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      splat_taps<KIND_FLOWGRAD>(fx.v[j], fy.v[j], x + j, y, H, W, Ho, Wo, scale, off_x, off_y, t[j]);
+      gx[j] = gy[j] = 0.f;
+    }
+    for (int c = 0; c < C; ++c) {
+      const float* plane = gout + ((long)b * C + c) * HWo;
+      SVec<VEC> a;
+      a.load(in + ((long)b * C + c) * HW + pix);
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) {
+        const int r0 = t[j].y0 * Wo + t[j].x0;
+        const float x0 = (float)t[j].x0, y0 = (float)t[j].y0, x1 = (float)(t[j].x0 + 1), y1 = (float)(t[j].y0 + 1);
+        const float g_nw = tap_or_zero(plane, t[j].okx0 && t[j].oky0, r0);
+        const float g_ne = tap_or_zero(plane, t[j].okx1 && t[j].oky0, r0 + 1);
+        const float g_sw = tap_or_zero(plane, t[j].okx0 && t[j].oky1, r0 + Wo);
+        const float g_se = tap_or_zero(plane, t[j].okx1 && t[j].oky1, r0 + Wo + 1);
+        const float fxx = t[j].fx, fyy = t[j].fy;
+        // channel 0 (d/dx): weights -(y1-fy), +(y1-fy), -(fy-y0), +(fy-y0), factor dfltYY (:664-668)
+        gx[j] += g_nw * a.v[j] * (-1.f * (y1 - fyy)) * t[j].dyy;
+        gx[j] += g_ne * a.v[j] * (+1.f * (y1 - fyy)) * t[j].dyy;
+        gx[j] += g_sw * a.v[j] * (-1.f * (fyy - y0)) * t[j].dyy;
+        gx[j] += g_se * a.v[j] * (+1.f * (fyy - y0)) * t[j].dyy;
+        // channel 1 (d/dy): weights -(x1-fx), -(fx-x0), +(x1-fx), +(fx-x0), factor dfltXX (:670-675)
+        gy[j] += g_nw * a.v[j] * ((x1 - fxx) * -1.f) * t[j].dxx;
+        gy[j] += g_ne * a.v[j] * ((fxx - x0) * -1.f) * t[j].dxx;
+        gy[j] += g_sw * a.v[j] * ((x1 - fxx) * +1.f) * t[j].dxx;
+        gy[j] += g_se * a.v[j] * ((fxx - x0) * +1.f) * t[j].dxx;
+      }
+    }
+    SVec<VEC> ox, oy;
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      ox.v[j] = t[j].ok ? gx[j] : 0.f;
+      oy.v[j] = t[j].ok ? gy[j] : 0.f;
+    }
+    ox.store(gflow + ((long)b * 2 + 0) * HW + pix);
+    oy.store(gflow + ((long)b * 2 + 1) * HW + pix);
+  }
+}
+
+// warp_forward_flow pre-processing (warp.py:122-126, softsplat_new.py:301-302):
+// ten_in[:, :C] = nan_to_zero(first) * w ; ten_in[:, C] = w ; w = any_c(isnan(first)) ? 0 : 1
+__global__ void __launch_bounds__(256) splat_prepare_kernel(const float* __restrict__ first, float* __restrict__ ten_in,
+                                                            int B, int C, long HW) {
+  const long total = (long)B * HW;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const long b = i / HW, p = i % HW;
+    bool any_nan = false;
+    for (int c = 0; c < C; ++c) any_nan |= isnan(__ldg(first + (b * C + c) * HW + p));
+    const float w = any_nan ? 0.f : 1.f;
+    for (int c = 0; c < C; ++c) {
+      float v = __ldg(first + (b * C + c) * HW + p);
+      if (isnan(v)) v = 0.f;
+      ten_in[(b * (C + 1) + c) * HW + p] = v * w;
+    }
+    ten_in[(b * (C + 1) + C) * HW + p] = w;
+  }
+}
+
+// warp_forward_flow post-processing (warp.py:139-156): img = wsum > 0 ? splat[:, :C] : NaN
+__global__ void __launch_bounds__(256) splat_finish_kernel(const float* __restrict__ splat, float* __restrict__ img,
+                                                           int B, int C, long HW, int set_nans) {
+  const long total = (long)B * HW;
+  const float qnan = __int_as_float(0x7fc00000);
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const long b = i / HW, p = i % HW;
+    const float w = __ldg(splat + (b * (C + 1) + C) * HW + p);
+    for (int c = 0; c < C; ++c) {
+      const float v = __ldg(splat + (b * (C + 1) + c) * HW + p);
+      img[(b * C + c) * HW + p] = (!set_nans || w > 0.f) ? v : qnan;
+    }
+  }
+}
+
+int sgrid(long items) {
+  long blocks = (items + 255) / 256;
+  const long cap = (long)FD_NUM_SMS * 16;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+int check(int B, int C, int H, int W, int scale, int off_x, int off_y) {
+  FD_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0, "splat: non-positive dimension");
+  FD_REQUIRE(scale >= 1 && H / scale > 0 && W / scale > 0, "splat: bad scale %d for %dx%d", scale, H, W);
+  FD_REQUIRE(off_x >= 0 && off_y >= 0, "splat: offsets must be reduced modulo scale (warp.py:129)");
+  FD_REQUIRE((long)H * W < (1L << 31), "splat: plane too large");
+  return FD_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int fd_splat_fwd(const float* in, const float* flow, float* out, int B, int C, int H, int W, int scale, int off_x,
+                 int off_y, void* stream) {
+  if (int e = check(B, C, H, W, scale, off_x, off_y)) return e;
+  FD_REQUIRE(in && flow && out, "splat_fwd: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int Ho = H / scale, Wo = W / scale;
+  FD_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)B * C * Ho * Wo, st));
+  if (W % 4 == 0) {
+    const long items = (long)B * H * (W / 4);
+    splat_fwd_kernel<4><<<sgrid(items), 256, 0, st>>>(in, flow, out, B, C, H, W, Ho, Wo, scale, off_x, off_y, items);
+  } else {
+    const long items = (long)B * H * W;
+    splat_fwd_kernel<1><<<sgrid(items), 256, 0, st>>>(in, flow, out, B, C, H, W, Ho, Wo, scale, off_x, off_y, items);
+  }
+  FD_LAUNCH_CHECK();
+  return FD_OK;
+}
+
+int fd_splat_ingrad(const float* flow, const float* gout, float* gin, int B, int C, int H, int W, int scale,
+                    int off_x, int off_y, void* stream) {
+  if (int e = check(B, C, H, W, scale, off_x, off_y)) return e;
+  FD_REQUIRE(flow && gout && gin, "splat_ingrad: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int Ho = H / scale, Wo = W / scale;
+  if (W % 4 == 0) {
+    const long items = (long)B * H * (W / 4);
+    splat_ingrad_kernel<4><<<sgrid(items), 256, 0, st>>>(flow, gout, gin, B, C, H, W, Ho, Wo, scale, off_x, off_y, items);
+  } else {
+    const long items = (long)B * H * W;
+    splat_ingrad_kernel<1><<<sgrid(items), 256, 0, st>>>(flow, gout, gin, B, C, H, W, Ho, Wo, scale, off_x, off_y, items);
+  }
+  FD_LAUNCH_CHECK();
+  return FD_OK;
+}
+
+int fd_splat_flowgrad(const float* in, const float* flow, const float* gout, float* gflow, int B, int C, int H, int W,
+                      int scale, int off_x, int off_y, void* stream) {
+  if (int e = check(B, C, H, W, scale, off_x, off_y)) return e;
+  FD_REQUIRE(in && flow && gout && gflow, "splat_flowgrad: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int Ho = H / scale, Wo = W / scale;
+  if (W % 4 == 0) {
+    const long items = (long)B * H * (W / 4);
+    splat_flowgrad_kernel<4><<<sgrid(items), 256, 0, st>>>(in, flow, gout, gflow, B, C, H, W, Ho, Wo, scale, off_x, off_y, items);
+  } else {
+    const long items = (long)B * H * W;
+    splat_flowgrad_kernel<1><<<sgrid(items), 256, 0, st>>>(in, flow, gout, gflow, B, C, H, W, Ho, Wo, scale, off_x, off_y, items);
+  }
+  FD_LAUNCH_CHECK();
+  return FD_OK;
+}
+
+int fd_splat_prepare(const float* first, float* ten_in, int B, int C, int HW, void* stream) {
+  FD_REQUIRE(first && ten_in && B > 0 && C > 0 && HW > 0, "splat_prepare: bad argument");
+  splat_prepare_kernel<<<sgrid((long)B * HW), 256, 0, (cudaStream_t)stream>>>(first, ten_in, B, C, HW);
+  FD_LAUNCH_CHECK();
+  return FD_OK;
+}
+
+int fd_splat_finish(const float* splat, float* img, int B, int C, int HW, int set_nans, void* stream) {
+  FD_REQUIRE(splat && img && B > 0 && C > 0 && HW > 0, "splat_finish: bad argument");
+  splat_finish_kernel<<<sgrid((long)B * HW), 256, 0, (cudaStream_t)stream>>>(splat, img, B, C, HW, set_nans);
+  FD_LAUNCH_CHECK();
+  return FD_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,527 @@
+// Backward bilinear warp (warp.py:95-119 of the reference) and the fused
+// warp + Charbonnier photometric + end-point-error objective (losses.py:3-6,46-47).
+//
+// HBM-bound gather/scatter work on fp32 NCHW planes.  Layout choices:
+//   * one thread owns VEC (=4 when W % 4 == 0) consecutive pixels of a row, so flow / flow_gt /
+//     frame1 / out / mask move as 128-bit coalesced accesses;
+//   * the 4-tap gathers of the warped frame go through the read-only path (L1/L2 resident: a
+//     warp's taps fall in a few rows of the source plane);
+//   * the scatter of the image gradient merges contributions that hit the same address inside a
+//     thread and across neighbouring lanes (shuffle) before falling back to red.global.add.f32.
+//
+// The coordinate / weight / accumulation sequence is written with explicit round-to-nearest
+// intrinsics in the exact order ATen's CPU grid_sampler_2d evaluates it, which makes the forward
+// bit-identical to the reference's CPU output (oracle/flowdiff_oracle.py:backwarp).
+#include "fd_common.cuh"
+
+namespace {
+
+struct BwGeom {
+  float wm1n, hm1n;    // max(W-1,1), max(H-1,1): the reference's normalisation divisor
+  float half_w, half_h;  // (W-1)/2, (H-1)/2: grid_sample's align_corners un-normalisation
+  float wl, hl;        // W-1, H-1 as float (bounds)
+  int H, W;
+};
+
+static BwGeom make_geom(int H, int W) {
+  BwGeom g;
+  g.H = H;
+  g.W = W;
+  g.wm1n = (float)(W - 1 > 1 ? W - 1 : 1);
+  g.hm1n = (float)(H - 1 > 1 ? H - 1 : 1);
+  g.half_w = (float)((double)(W - 1) / 2.0);
+  g.half_h = (float)((double)(H - 1) / 2.0);
+  g.wl = (float)(W - 1);
+  g.hl = (float)(H - 1);
+  return g;
+}
+
+struct BwTaps {
+  float nw, ne, sw, se;  // bilinear weights
+  float wx, ex, ny, sy;  // fractional parts and complements
+  int x0, y0;
+  bool okx0, okx1, oky0, oky1;
+};
+
+// flow_dx = flow[:,1], flow_dy = flow[:,0] (the reference flips the channels, warp.py:105)
+__device__ __forceinline__ void bw_taps(float flow_dx, float flow_dy, int x, int y, const BwGeom& g, BwTaps& t) {
+  const float vx = __fadd_rn((float)x, flow_dx);
+  const float vy = __fadd_rn((float)y, flow_dy);
+  const float gx = __fsub_rn(__fdiv_rn(__fmul_rn(2.f, vx), g.wm1n), 1.f);
+  const float gy = __fsub_rn(__fdiv_rn(__fmul_rn(2.f, vy), g.hm1n), 1.f);
+  const float ix = __fmul_rn(__fadd_rn(gx, 1.f), g.half_w);
+  const float iy = __fmul_rn(__fadd_rn(gy, 1.f), g.half_h);
+  const float x0f = floorf(ix), y0f = floorf(iy);
+  const float x1f = __fadd_rn(x0f, 1.f), y1f = __fadd_rn(y0f, 1.f);
+  t.wx = __fsub_rn(ix, x0f);
+  t.ex = __fsub_rn(1.f, t.wx);
+  t.ny = __fsub_rn(iy, y0f);
+  t.sy = __fsub_rn(1.f, t.ny);
+  t.nw = __fmul_rn(t.sy, t.ex);
+  t.ne = __fmul_rn(t.sy, t.wx);
+  t.sw = __fmul_rn(t.ny, t.ex);
+  t.se = __fmul_rn(t.ny, t.wx);
+  t.okx0 = (x0f >= 0.f) && (x0f <= g.wl);
+  t.okx1 = (x1f >= 0.f) && (x1f <= g.wl);
+  t.oky0 = (y0f >= 0.f) && (y0f <= g.hl);
+  t.oky1 = (y1f >= 0.f) && (y1f <= g.hl);
+  t.x0 = (t.okx0 || t.okx1) ? (int)x0f : 0;
+  t.y0 = (t.oky0 || t.oky1) ? (int)y0f : 0;
+}
+
+__device__ __forceinline__ float bw_mask(const BwTaps& t) {
+  float m = __fmul_rn((t.okx0 && t.oky0) ? 1.f : 0.f, t.nw);
+  m = __fmaf_rn((t.okx1 && t.oky0) ? 1.f : 0.f, t.ne, m);
+  m = __fmaf_rn((t.okx0 && t.oky1) ? 1.f : 0.f, t.sw, m);
+  m = __fmaf_rn((t.okx1 && t.oky1) ? 1.f : 0.f, t.se, m);
+  if (m < 0.999f) m = 0.f;   // warp.py:116
+  if (m > 0.f) m = 1.f;      // warp.py:117
+  return m;
+}
+
+struct BwVals {
+  float nw, ne, sw, se;
+};
+
+__device__ __forceinline__ BwVals bw_gather(const float* __restrict__ plane, const BwTaps& t, int W) {
+  BwVals v;
+  const float* r0 = plane + (long)t.y0 * W + t.x0;
+  const float* r1 = r0 + W;
+  v.nw = (t.okx0 && t.oky0) ? __ldg(r0) : 0.f;
+  v.ne = (t.okx1 && t.oky0) ? __ldg(r0 + 1) : 0.f;
+  v.sw = (t.okx0 && t.oky1) ? __ldg(r1) : 0.f;
+  v.se = (t.okx1 && t.oky1) ? __ldg(r1 + 1) : 0.f;
+  return v;
+}
+
+__device__ __forceinline__ float bw_sample(const BwVals& v, const BwTaps& t) {
+  float o = __fmul_rn(v.nw, t.nw);
+  o = __fmaf_rn(v.ne, t.ne, o);
+  o = __fmaf_rn(v.sw, t.sw, o);
+  o = __fmaf_rn(v.se, t.se, o);
+  return o;
+}
+
+template <int VEC>
+struct Vec;
+template <>
+struct Vec<1> {
+  float v[1];
+  __device__ __forceinline__ void load(const float* p) { v[0] = __ldg(p); }
+  __device__ __forceinline__ void store(float* p) const { *p = v[0]; }
+};
+template <>
+struct Vec<4> {
+  float v[4];
+  __device__ __forceinline__ void load(const float* p) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(p));
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  }
+  __device__ __forceinline__ void store(float* p) const {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+};
+
+// A thread's item = VEC consecutive pixels of one row: item -> (b, y, x)
+template <int VEC>
+__device__ __forceinline__ void item_to_byx(long item, int H, int W, int& b, int& y, int& x) {
+  const int wq = W / VEC;
+  x = (int)(item % wq) * VEC;
+  const long r = item / wq;
+  y = (int)(r % H);
+  b = (int)(r / H);
+}
+
+// ---------------------------------------------------------------------------------------------
+// forward: out, mask
+// ---------------------------------------------------------------------------------------------
+template <int VEC>
+__global__ void __launch_bounds__(256) backwarp_fwd_kernel(const float* __restrict__ image,
+                                                           const float* __restrict__ flow,
+                                                           float* __restrict__ out, float* __restrict__ mask,
+                                                           int B, int C, BwGeom g, long items) {
+  const int H = g.H, W = g.W;
+  const long HW = (long)H * W;
+  for (long item = (long)blockIdx.x * blockDim.x + threadIdx.x; item < items; item += (long)gridDim.x * blockDim.x) {
+    int b, y, x;
+    item_to_byx<VEC>(item, H, W, b, y, x);
+    const long pix = (long)y * W + x;
+    Vec<VEC> fdy, fdx;
+    fdy.load(flow + ((long)b * 2 + 0) * HW + pix);
+    fdx.load(flow + ((long)b * 2 + 1) * HW + pix);
+    BwTaps t[VEC];
+    Vec<VEC> m;
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      bw_taps(fdx.v[j], fdy.v[j], x + j, y, g, t[j]);
+      m.v[j] = bw_mask(t[j]);
+    }
+    for (int c = 0; c < C; ++c) {
+      const float* plane = image + ((long)b * C + c) * HW;
+      Vec<VEC> o;
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) o.v[j] = bw_sample(bw_gather(plane, t[j], W), t[j]);
+      o.store(out + ((long)b * C + c) * HW + pix);
+      if (mask != nullptr) m.store(mask + ((long)b * C + c) * HW + pix);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// backward of sum(out * gout): gimage (scatter), gflow (gather)
+// ---------------------------------------------------------------------------------------------
+template <int VEC>
+__global__ void __launch_bounds__(256) backwarp_bwd_kernel(const float* __restrict__ image,
+                                                           const float* __restrict__ flow,
+                                                           const float* __restrict__ gout,
+                                                           float* __restrict__ gimage, float* __restrict__ gflow,
+                                                           int B, int C, BwGeom g, long items) {
+  const int H = g.H, W = g.W;
+  const long HW = (long)H * W;
+  const int lane = threadIdx.x & 31;
+  for (long base = (long)blockIdx.x * blockDim.x + (threadIdx.x & ~31); base < items;
+       base += (long)gridDim.x * blockDim.x) {
+    const long item = base + lane;
+    const bool valid = item < items;
+    int b = 0, y = 0, x = 0;
+    if (valid) item_to_byx<VEC>(item, H, W, b, y, x);
+    const long pix = (long)y * W + x;
+    Vec<VEC> fdy, fdx;
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) fdy.v[j] = fdx.v[j] = 0.f;
+    if (valid) {
+      fdy.load(flow + ((long)b * 2 + 0) * HW + pix);
+      fdx.load(flow + ((long)b * 2 + 1) * HW + pix);
+    }
+    BwTaps t[VEC];
+    float dix[VEC], diy[VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      bw_taps(fdx.v[j], fdy.v[j], x + j, y, g, t[j]);
+      dix[j] = diy[j] = 0.f;
+    }
+    for (int c = 0; c < C; ++c) {
+      const long plane_off = ((long)b * C + c) * HW;
+      Vec<VEC> go;
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) go.v[j] = 0.f;
+      if (valid) go.load(gout + plane_off + pix);
+      if (gflow != nullptr && valid) {
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+          const BwVals v = bw_gather(image + plane_off, t[j], W);
+          dix[j] += go.v[j] * ((v.ne - v.nw) * t[j].sy + (v.se - v.sw) * t[j].ny);
+          diy[j] += go.v[j] * ((v.sw - v.nw) * t[j].ex + (v.se - v.ne) * t[j].wx);
+        }
+      }
+      if (gimage != nullptr) {
+        int a0[2 * VEC], a1[2 * VEC];
+        float v0[2 * VEC], v1[2 * VEC];
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+          const int r0 = t[j].y0 * W + t[j].x0;
+          a0[2 * j] = (valid && t[j].okx0 && t[j].oky0) ? r0 : -1;
+          a0[2 * j + 1] = (valid && t[j].okx1 && t[j].oky0) ? r0 + 1 : -1;
+          a1[2 * j] = (valid && t[j].okx0 && t[j].oky1) ? r0 + W : -1;
+          a1[2 * j + 1] = (valid && t[j].okx1 && t[j].oky1) ? r0 + W + 1 : -1;
+          v0[2 * j] = go.v[j] * t[j].nw;
+          v0[2 * j + 1] = go.v[j] * t[j].ne;
+          v1[2 * j] = go.v[j] * t[j].sw;
+          v1[2 * j + 1] = go.v[j] * t[j].se;
+        }
+        fd_scatter_merged<2 * VEC>(gimage + plane_off, a0, v0);
+        fd_scatter_merged<2 * VEC>(gimage + plane_off, a1, v1);
+      }
+    }
+    if (gflow != nullptr && valid) {
+      Vec<VEC> gy, gx;
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) {
+        gx.v[j] = ((dix[j] * g.half_w) / g.wm1n) * 2.f;
+        gy.v[j] = ((diy[j] * g.half_h) / g.hm1n) * 2.f;
+      }
+      gy.store(gflow + ((long)b * 2 + 0) * HW + pix);
+      gx.store(gflow + ((long)b * 2 + 1) * HW + pix);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// fused warp + photometric + EPE
+// ---------------------------------------------------------------------------------------------
+constexpr int kPhotoThreads = 256;
+
+static int photo_grid(long items) {
+  long blocks = (items + kPhotoThreads - 1) / kPhotoThreads;
+  const long cap = (long)FD_NUM_SMS * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(kPhotoThreads) photo_epe_fwd_kernel(
+    const float* __restrict__ frame1, const float* __restrict__ frame2, const float* __restrict__ flow,
+    const float* __restrict__ flow_gt, float* __restrict__ partials, int B, int C, BwGeom g, long items) {
+  __shared__ float red[3 * 32];
+  const int H = g.H, W = g.W;
+  const long HW = (long)H * W;
+  float s[3] = {0.f, 0.f, 0.f};
+  for (long item = (long)blockIdx.x * blockDim.x + threadIdx.x; item < items; item += (long)gridDim.x * blockDim.x) {
+    int b, y, x;
+    item_to_byx<VEC>(item, H, W, b, y, x);
+    const long pix = (long)y * W + x;
+    const long fo = (long)b * 2 * HW + pix;
+    Vec<VEC> f0, f1, g0, g1;
+    f0.load(flow + fo);
+    f1.load(flow + fo + HW);
+    g0.load(flow_gt + fo);
+    g1.load(flow_gt + fo + HW);
+    BwTaps t[VEC];
+    float m[VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      bw_taps(f1.v[j], f0.v[j], x + j, y, g, t[j]);
+      m[j] = bw_mask(t[j]);
+      const float du = f0.v[j] - g0.v[j], dv = f1.v[j] - g1.v[j];
+      s[2] += sqrtf(du * du + dv * dv);
+    }
+    for (int c = 0; c < C; ++c) {
+      const long po = ((long)b * C + c) * HW;
+      Vec<VEC> a;
+      a.load(frame1 + po + pix);
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) {
+        const float wv = bw_sample(bw_gather(frame2 + po, t[j], W), t[j]);
+        const float d = a.v[j] - wv;
+        s[0] += m[j] * sqrtf(d * d + 1e-6f);
+        s[1] += m[j];
+      }
+    }
+  }
+  fd_block_sum<3>(s, red);
+  if (threadIdx.x == 0) {
+    partials[blockIdx.x * 3 + 0] = s[0];
+    partials[blockIdx.x * 3 + 1] = s[1];
+    partials[blockIdx.x * 3 + 2] = s[2];
+  }
+}
+
+// fixed-order (deterministic) final reduction of per-block partials, in double
+template <int NV>
+__global__ void __launch_bounds__(256) finalize_sums_kernel(const float* __restrict__ partials, int nblocks,
+                                                            float* __restrict__ sums, float extra, int extra_slot) {
+  __shared__ double sh[NV][256];
+  double acc[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) acc[i] = 0.0;
+  for (int k = threadIdx.x; k < nblocks; k += 256)
+#pragma unroll
+    for (int i = 0; i < NV; ++i) acc[i] += (double)partials[k * NV + i];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) sh[i][threadIdx.x] = acc[i];
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o)
+#pragma unroll
+      for (int i = 0; i < NV; ++i) sh[i][threadIdx.x] += sh[i][threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) sums[i] = (float)sh[i][0];
+    if (extra_slot >= 0) sums[extra_slot] = extra;
+  }
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(256) photo_epe_bwd_kernel(
+    const float* __restrict__ frame1, const float* __restrict__ frame2, const float* __restrict__ flow,
+    const float* __restrict__ flow_gt, const float* __restrict__ sums, float g_photo, float g_epe,
+    float* __restrict__ gflow, float* __restrict__ gframe2, int B, int C, BwGeom g, long items) {
+  const int H = g.H, W = g.W;
+  const long HW = (long)H * W;
+  const int lane = threadIdx.x & 31;
+  const float kp = g_photo / __ldg(sums + 1);
+  const float ke = g_epe / __ldg(sums + 3);
+  for (long base = (long)blockIdx.x * blockDim.x + (threadIdx.x & ~31); base < items;
+       base += (long)gridDim.x * blockDim.x) {
+    const long item = base + lane;
+    const bool valid = item < items;
+    int b = 0, y = 0, x = 0;
+    if (valid) item_to_byx<VEC>(item, H, W, b, y, x);
+    const long pix = (long)y * W + x;
+    const long fo = (long)b * 2 * HW + pix;
+    Vec<VEC> f0, f1, g0, g1;
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) f0.v[j] = f1.v[j] = g0.v[j] = g1.v[j] = 0.f;
+    if (valid) {
+      f0.load(flow + fo);
+      f1.load(flow + fo + HW);
+      g0.load(flow_gt + fo);
+      g1.load(flow_gt + fo + HW);
+    }
+    BwTaps t[VEC];
+    float m[VEC], dix[VEC], diy[VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      bw_taps(f1.v[j], f0.v[j], x + j, y, g, t[j]);
+      m[j] = bw_mask(t[j]);
+      dix[j] = diy[j] = 0.f;
+    }
+    for (int c = 0; c < C; ++c) {
+      const long po = ((long)b * C + c) * HW;
+      Vec<VEC> a;
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) a.v[j] = 0.f;
+      if (valid) a.load(frame1 + po + pix);
+      float gw[VEC];
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) {
+        gw[j] = 0.f;
+        if (valid) {
+          const BwVals v = bw_gather(frame2 + po, t[j], W);
+          const float d = a.v[j] - bw_sample(v, t[j]);
+          gw[j] = -kp * m[j] * d / sqrtf(d * d + 1e-6f);   // dL/dwarped
+          dix[j] += gw[j] * ((v.ne - v.nw) * t[j].sy + (v.se - v.sw) * t[j].ny);
+          diy[j] += gw[j] * ((v.sw - v.nw) * t[j].ex + (v.se - v.ne) * t[j].wx);
+        }
+      }
+      if (gframe2 != nullptr) {
+        int a0[2 * VEC], a1[2 * VEC];
+        float v0[2 * VEC], v1[2 * VEC];
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+          const int r0 = t[j].y0 * W + t[j].x0;
+          const bool on = valid && gw[j] != 0.f;
+          a0[2 * j] = (on && t[j].okx0 && t[j].oky0) ? r0 : -1;
+          a0[2 * j + 1] = (on && t[j].okx1 && t[j].oky0) ? r0 + 1 : -1;
+          a1[2 * j] = (on && t[j].okx0 && t[j].oky1) ? r0 + W : -1;
+          a1[2 * j + 1] = (on && t[j].okx1 && t[j].oky1) ? r0 + W + 1 : -1;
+          v0[2 * j] = gw[j] * t[j].nw;
+          v0[2 * j + 1] = gw[j] * t[j].ne;
+          v1[2 * j] = gw[j] * t[j].sw;
+          v1[2 * j + 1] = gw[j] * t[j].se;
+        }
+        fd_scatter_merged<2 * VEC>(gframe2 + po, a0, v0);
+        fd_scatter_merged<2 * VEC>(gframe2 + po, a1, v1);
+      }
+    }
+    if (gflow != nullptr && valid) {
+      Vec<VEC> gy, gx;
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) {
+        const float du = f0.v[j] - g0.v[j], dv = f1.v[j] - g1.v[j];
+        const float nrm = sqrtf(du * du + dv * dv);
+        const float inv = nrm > 0.f ? ke / nrm : 0.f;
+        gy.v[j] = ((diy[j] * g.half_h) / g.hm1n) * 2.f + du * inv;
+        gx.v[j] = ((dix[j] * g.half_w) / g.wm1n) * 2.f + dv * inv;
+      }
+      gy.store(gflow + fo);
+      gx.store(gflow + fo + HW);
+    }
+  }
+}
+
+static int stream_grid(long items, int threads) {
+  long blocks = (items + threads - 1) / threads;
+  const long cap = (long)FD_NUM_SMS * 16;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+static int check_dims(int B, int C, int H, int W) {
+  FD_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0, "backwarp: non-positive dimension B=%d C=%d H=%d W=%d", B, C, H, W);
+  FD_REQUIRE((long)H * W < (1L << 31), "backwarp: plane too large");
+  return FD_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int fd_backwarp_fwd(const float* image, const float* flow, float* out, float* mask, int B, int C, int H, int W,
+                    void* stream) {
+  if (int e = check_dims(B, C, H, W)) return e;
+  FD_REQUIRE(image && flow && out, "backwarp_fwd: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  const BwGeom g = make_geom(H, W);
+  if (W % 4 == 0) {
+    const long items = (long)B * H * (W / 4);
+    backwarp_fwd_kernel<4><<<stream_grid(items, 256), 256, 0, st>>>(image, flow, out, mask, B, C, g, items);
+  } else {
+    const long items = (long)B * H * W;
+    backwarp_fwd_kernel<1><<<stream_grid(items, 256), 256, 0, st>>>(image, flow, out, mask, B, C, g, items);
+  }
+  FD_LAUNCH_CHECK();
+  return FD_OK;
+}
+
+int fd_backwarp_bwd(const float* image, const float* flow, const float* gout, float* gimage, float* gflow, int B,
+                    int C, int H, int W, void* stream) {
+  if (int e = check_dims(B, C, H, W)) return e;
+  FD_REQUIRE(image && flow && gout, "backwarp_bwd: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  const BwGeom g = make_geom(H, W);
+  if (gimage) FD_CUDA(cudaMemsetAsync(gimage, 0, sizeof(float) * (size_t)B * C * H * W, st));
+  if (W % 4 == 0) {
+    const long items = (long)B * H * (W / 4);
+    backwarp_bwd_kernel<4><<<stream_grid(items, 256), 256, 0, st>>>(image, flow, gout, gimage, gflow, B, C, g, items);
+  } else {
+    const long items = (long)B * H * W;
+    backwarp_bwd_kernel<1><<<stream_grid(items, 256), 256, 0, st>>>(image, flow, gout, gimage, gflow, B, C, g, items);
+  }
+  FD_LAUNCH_CHECK();
+  return FD_OK;
+}
+
+size_t fd_photo_epe_workspace_floats(int B, int H, int W) {
+  const long items = (W % 4 == 0) ? (long)B * H * (W / 4) : (long)B * H * W;
+  return (size_t)photo_grid(items) * 3;
+}
+
+int fd_backwarp_photo_epe_fwd(const float* frame1, const float* frame2, const float* flow, const float* flow_gt,
+                              float* sums, float* partials, int B, int C, int H, int W, void* stream) {
+  if (int e = check_dims(B, C, H, W)) return e;
+  FD_REQUIRE(frame1 && frame2 && flow && flow_gt && sums && partials, "photo_epe_fwd: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  const BwGeom g = make_geom(H, W);
+  int grid;
+  if (W % 4 == 0) {
+    const long items = (long)B * H * (W / 4);
+    grid = photo_grid(items);
+    photo_epe_fwd_kernel<4><<<grid, kPhotoThreads, 0, st>>>(frame1, frame2, flow, flow_gt, partials, B, C, g, items);
+  } else {
+    const long items = (long)B * H * W;
+    grid = photo_grid(items);
+    photo_epe_fwd_kernel<1><<<grid, kPhotoThreads, 0, st>>>(frame1, frame2, flow, flow_gt, partials, B, C, g, items);
+  }
+  FD_LAUNCH_CHECK();
+  finalize_sums_kernel<3><<<1, 256, 0, st>>>(partials, grid, sums, (float)((double)B * H * W), 3);
+  FD_LAUNCH_CHECK();
+  return FD_OK;
+}
+
+int fd_backwarp_photo_epe_bwd(const float* frame1, const float* frame2, const float* flow, const float* flow_gt,
+                              const float* sums, float g_photo, float g_epe, float* gflow, float* gframe2, int B,
+                              int C, int H, int W, void* stream) {
+  if (int e = check_dims(B, C, H, W)) return e;
+  FD_REQUIRE(frame1 && frame2 && flow && flow_gt && sums, "photo_epe_bwd: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  const BwGeom g = make_geom(H, W);
+  if (gframe2) FD_CUDA(cudaMemsetAsync(gframe2, 0, sizeof(float) * (size_t)B * C * H * W, st));
+  if (W % 4 == 0) {
+    const long items = (long)B * H * (W / 4);
+    photo_epe_bwd_kernel<4><<<stream_grid(items, 256), 256, 0, st>>>(frame1, frame2, flow, flow_gt, sums, g_photo,
+                                                                     g_epe, gflow, gframe2, B, C, g, items);
+  } else {
+    const long items = (long)B * H * W;
+    photo_epe_bwd_kernel<1><<<stream_grid(items, 256), 256, 0, st>>>(frame1, frame2, flow, flow_gt, sums, g_photo,
+                                                                     g_epe, gflow, gframe2, B, C, g, items);
+  }
+  FD_LAUNCH_CHECK();
+  return FD_OK;
+}
+
+}  // extern "C"

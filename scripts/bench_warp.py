@@ -1,0 +1,72 @@
+"""BASELINE config #4 microbench: fused backward-warp + photometric/EPE fwd and bwd at 8x2x436x1024,
+plus the plain warp / splat kernels.  Prints achieved GB/s against the algorithmic bytes
+(fwd 40 B/px, bwd 60 B/px)."""
+import json
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from opticalflowdiffusion_b200 import _lib  # noqa: E402
+
+
+def timeit(fn, iters=50, warmup=10, flush=None):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        if flush is not None:
+            flush.zero_()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        fn()
+        e.record()
+        torch.cuda.synchronize()
+        ts.append(s.elapsed_time(e) * 1e-3)
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
+def main():
+    lib = _lib.load(check_device=True)
+    B, C, H, W = 8, 3, 436, 1024
+    g = torch.Generator().manual_seed(3)
+    flow = (torch.randn(B, 2, H, W, generator=g) * 4).cuda()
+    f1 = torch.rand(B, C, H, W, generator=g).cuda()
+    f2 = torch.rand(B, C, H, W, generator=g).cuda()
+    gt = flow + torch.randn(B, 2, H, W, generator=g).cuda()
+    sums = torch.empty(4, device="cuda")
+    ws = torch.empty(lib.fd_photo_epe_workspace_floats(B, H, W), device="cuda")
+    gflow = torch.empty_like(flow)
+    gf2 = torch.empty_like(f2)
+    out = torch.empty_like(f2)
+    mask = torch.empty_like(f2)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    st = _lib.stream()
+    P = _lib.ptr
+    px = B * H * W
+    res = {}
+
+    def rec(name, t, nbytes):
+        res[name] = {"us": round(t * 1e6, 2), "GBps": round(nbytes / t / 1e9, 1), "bytes": nbytes}
+
+    t = timeit(lambda: _lib.check(lib.fd_backwarp_photo_epe_fwd(P(f1), P(f2), P(flow), P(gt), P(sums), P(ws), B, C, H, W, st)), flush=flush)
+    rec("photo_epe_fwd", t, 40 * px)
+    t = timeit(lambda: _lib.check(lib.fd_backwarp_photo_epe_bwd(P(f1), P(f2), P(flow), P(gt), P(sums), 1.0, 1.0, P(gflow), P(gf2), B, C, H, W, st)), flush=flush)
+    rec("photo_epe_bwd", t, 60 * px)
+    t = timeit(lambda: _lib.check(lib.fd_backwarp_fwd(P(f2), P(flow), P(out), P(mask), B, C, H, W, st)), flush=flush)
+    rec("backwarp_fwd", t, (8 + 12 + 12 + 12) * px)
+    t = timeit(lambda: _lib.check(lib.fd_backwarp_bwd(P(f2), P(flow), P(out), P(gf2), P(gflow), B, C, H, W, st)), flush=flush)
+    rec("backwarp_bwd", t, (8 + 12 + 12 + 12 + 8) * px)
+    so = torch.empty_like(f2)
+    t = timeit(lambda: _lib.check(lib.fd_splat_fwd(P(f2), P(flow), P(so), B, C, H, W, 1, 0, 0, st)), flush=flush)
+    rec("splat_fwd", t, (8 + 12 + 12) * px)
+    t = timeit(lambda: _lib.check(lib.fd_splat_flowgrad(P(f2), P(flow), P(out), P(gflow), B, C, H, W, 1, 0, 0, st)), flush=flush)
+    rec("splat_flowgrad", t, (8 + 12 + 12 + 8) * px)
+    print(json.dumps(res))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,115 @@
+"""-m gpu: the tcgen05 implicit-GEMM convolution against torch fp32 conv2d on the same bf16-rounded
+operands (tolerance: fp32 accumulation-order noise + one bf16 rounding of the output)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def L():
+    from opticalflowdiffusion_b200 import _lib
+    _lib.load(check_device=True)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    return _lib
+
+
+def nhwc_bf16(x):
+    return x.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)
+
+
+def pack_w(w):
+    """[Cout][Cin][KH][KW] -> bf16 [Cout][(ky*KW+kx)*Cin + ci]"""
+    return w.permute(0, 2, 3, 1).reshape(w.shape[0], -1).contiguous().to(torch.bfloat16)
+
+
+def run_conv(L, xs, w, bias, pad, residual=None, stats=False, mode=0):
+    lib = L.load()
+    N = xs[0].shape[0]
+    srcs = [nhwc_bf16(x) for x in xs]
+    Cout = w.shape[0]
+    if mode == 0:
+        H, W = xs[0].shape[2:]
+        KH, KW = w.shape[2:]
+        wp = pack_w(w)
+    else:
+        H, W = xs[0].shape[2] // 2, xs[0].shape[3] // 2
+        KH = KW = 1
+        C = xs[0].shape[1]
+        # torch channel c*4 + p1*2 + p2 -> K = (p1*2+p2)*C + c
+        wp = w.reshape(Cout, C, 4).permute(0, 2, 1).reshape(Cout, 4 * C).contiguous().to(torch.bfloat16)
+    out = torch.empty(N, H, W, Cout, device="cuda", dtype=torch.bfloat16)
+    res = nhwc_bf16(residual) if residual is not None else None
+    gn = torch.zeros(N, 8, 2, device="cuda", dtype=torch.float64) if stats else None
+    L.check(lib.fd_conv_igemm(L.ptr(srcs[0]), srcs[0].shape[-1], L.ptr(srcs[1]) if len(srcs) > 1 else None,
+                              srcs[1].shape[-1] if len(srcs) > 1 else 0, L.ptr(wp), L.ptr(bias), L.ptr(res),
+                              L.ptr(out), L.ptr(gn), N, H, W, Cout, KH, KW, pad[0], pad[1], mode, L.stream()))
+    torch.cuda.synchronize()
+    return out.permute(0, 3, 1, 2).float(), gn
+
+
+def ref_conv(xs, w, bias, pad, residual=None, mode=0):
+    x = torch.cat([t.to(torch.bfloat16).float() for t in xs], 1)
+    wq = w.to(torch.bfloat16).float()
+    if mode == 1:
+        b, c, H, W = x.shape
+        x = x.reshape(b, c, H // 2, 2, W // 2, 2).permute(0, 1, 3, 5, 2, 4).reshape(b, c * 4, H // 2, W // 2)
+    y = F.conv2d(x, wq, bias, padding=pad)
+    if residual is not None:
+        y = y + residual.to(torch.bfloat16).float()
+    return y
+
+
+def close(out, ref):
+    err = (out - ref).abs()
+    tol = 2e-2 * ref.abs().clamp(min=1.0)   # bf16 output rounding is 2^-9 relative; K up to 7k
+    assert bool((err <= tol).all()), f"max err {err.max().item()} at ref scale {ref.abs().max().item()}"
+    # and much tighter on average
+    assert err.mean().item() < 4e-3 * ref.abs().mean().clamp(min=0.1).item()
+
+
+CASES = [
+    # N, Cins, Cout, H, W, k, pad, bias, residual, stats
+    (2, (64,), 64, 16, 128, (3, 3), (1, 1), True, False, True),
+    (1, (64,), 64, 3, 128, (3, 3), (1, 1), True, False, False),
+    (2, (64, 64), 128, 12, 24, (3, 3), (1, 1), True, False, True),
+    (2, (128, 64), 128, 8, 16, (3, 3), (1, 1), True, False, True),
+    (2, (64,), 384, 10, 12, (1, 1), (0, 0), False, False, False),
+    (2, (128,), 64, 10, 12, (1, 1), (0, 0), True, True, False),
+    (1, (64,), 64, 20, 40, (7, 1), (3, 0), True, False, False),
+    (2, (512,), 256, 2, 3, (3, 3), (1, 1), True, False, False),
+    (2, (512, 256), 512, 4, 6, (3, 3), (1, 1), True, False, True),
+    (1, (256,), 256, 33, 70, (3, 3), (1, 1), True, False, True),
+    (2, (64,), 64, 220, 512, (3, 3), (1, 1), True, False, True),
+]
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_conv_igemm(L, case):
+    N, cins, Cout, H, W, k, pad, has_bias, has_res, stats = case
+    g = torch.Generator().manual_seed(hash(case) % 1000)
+    xs = [torch.randn(N, c, H, W, generator=g).cuda() for c in cins]
+    cin = sum(cins)
+    w = (torch.randn(Cout, cin, k[0], k[1], generator=g) / (cin * k[0] * k[1]) ** 0.5).cuda()
+    bias = torch.randn(Cout, generator=g).cuda() if has_bias else None
+    res = torch.randn(N, Cout, H, W, generator=g).cuda() if has_res else None
+    out, gn = run_conv(L, xs, w, bias, pad, res, stats)
+    ref = ref_conv(xs, w, bias, pad, res)
+    close(out, ref)
+    if stats:
+        r = ref.double().reshape(N, 8, -1)
+        s = torch.stack((r.sum(-1), (r * r).sum(-1)), -1)
+        assert torch.allclose(gn, s, rtol=1e-3, atol=1e-2 * r.shape[-1] ** 0.5), (gn - s).abs().max()
+
+
+@pytest.mark.parametrize("case", [(2, 64, 128, 8, 12), (1, 128, 256, 32, 64), (2, 256, 512, 3, 5)])
+def test_conv_pixel_unshuffle(L, case):
+    N, C, Cout, H, W = case
+    g = torch.Generator().manual_seed(C + H)
+    x = torch.randn(N, C, 2 * H, 2 * W, generator=g).cuda()
+    w = (torch.randn(Cout, 4 * C, 1, 1, generator=g) / (4 * C) ** 0.5).cuda()
+    bias = torch.randn(Cout, generator=g).cuda()
+    out, _ = run_conv(L, [x], w, bias, (0, 0), mode=1)
+    close(out, ref_conv([x], w, bias, (0, 0), mode=1))

@@ -1,0 +1,227 @@
+"""-m gpu: the CUDA warp / splat / loss kernels (through the C ABI) against the oracle and the
+reference-generated golden vectors."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import flowdiff_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def T(a):
+    return torch.from_numpy(np.asarray(a))
+
+
+@pytest.fixture(scope="module")
+def W():
+    from opticalflowdiffusion_b200 import _lib, warp
+    _lib.load(check_device=True)
+    return warp
+
+
+def test_backwarp_golden_bit_exact(W, golden):
+    g = golden("backwarp")
+    out, mask = W.warp_backward_flow(None, T(g["img"]).cuda(), T(g["flow"]).cuda())
+    assert np.array_equal(mask.cpu().numpy(), g["mask"])
+    assert np.array_equal(out.cpu().numpy(), g["out"])
+
+
+def test_backwarp_sintel_rows_bit_exact(W, golden):
+    g = golden("backwarp")
+    full = torch.zeros(1, 2, 436, 1024)
+    full[:, :, 200:204] = T(g["big_flow_rows"])
+    img = T(g["big_img"].astype(np.float32))
+    out, mask = W.warp_backward_flow(None, img.cuda(), full.cuda())
+    assert np.array_equal(mask[:, :, 200:204].cpu().numpy(), g["big_mask_rows"])
+    assert np.array_equal(out[:, :, 200:204].cpu().numpy(), g["big_out_rows"])
+
+
+@pytest.mark.parametrize("shape", [(2, 3, 20, 28), (1, 1, 7, 5), (2, 3, 33, 64), (1, 2, 1, 9)])
+def test_backwarp_vs_oracle_bit_exact(W, shape):
+    B, C, H, Wd = shape
+    g = torch.Generator().manual_seed(100 + H)
+    img = torch.rand(B, C, H, Wd, generator=g)
+    flow = torch.randn(B, 2, H, Wd, generator=g) * 3.0
+    flow[0, :, 0, 0] = torch.tensor([-100.0, 100.0])
+    o_ref, m_ref = O.backwarp(img, flow)
+    o, m = W.warp_backward_flow(None, img.cuda(), flow.cuda())
+    assert torch.equal(m.cpu(), m_ref)
+    assert torch.equal(o.cpu(), o_ref)
+
+
+def test_backwarp_grads_golden(W, golden):
+    g = golden("backwarp")
+    img = T(g["img"]).cuda().requires_grad_(True)
+    flow = T(g["flow"]).cuda().requires_grad_(True)
+    out, _ = W.warp_backward_flow(None, img, flow)
+    (out * T(g["gout"]).cuda()).sum().backward()
+    np.testing.assert_allclose(img.grad.cpu().numpy(), g["grad_img"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(flow.grad.cpu().numpy(), g["grad_flow"], rtol=1e-5, atol=1e-5)
+
+
+def test_backwarp_grads_smooth_flow_merging(W):
+    """Smooth flow -> neighbouring pixels hit the same taps: exercises the in-thread / cross-lane merge."""
+    B, C, H, Wd = 2, 3, 24, 64
+    g = torch.Generator().manual_seed(5)
+    img = torch.rand(B, C, H, Wd, generator=g)
+    flow = torch.zeros(B, 2, H, Wd)
+    flow[:, 0] = 1.25
+    flow[:, 1] = -2.5
+    flow[1, 1, :, 32:] = 0.75
+    gout = torch.randn(B, C, H, Wd, generator=g)
+    ir, fr = img.clone().requires_grad_(True), flow.clone().requires_grad_(True)
+    o, _ = O.backwarp_torch(ir, fr)
+    (o * gout).sum().backward()
+    ic, fc = img.cuda().requires_grad_(True), flow.cuda().requires_grad_(True)
+    o2, _ = W.warp_backward_flow(None, ic, fc)
+    (o2 * gout.cuda()).sum().backward()
+    np.testing.assert_allclose(ic.grad.cpu().numpy(), ir.grad.numpy(), rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(fc.grad.cpu().numpy(), fr.grad.numpy(), rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("shape", [(2, 3, 20, 28), (2, 3, 17, 23), (1, 3, 64, 128)])
+def test_photo_epe_fwd_bwd(W, shape):
+    B, C, H, Wd = shape
+    g = torch.Generator().manual_seed(3)
+    flow = torch.randn(B, 2, H, Wd, generator=g) * 4.0
+    f1 = torch.rand(B, C, H, Wd, generator=g)
+    f2 = torch.rand(B, C, H, Wd, generator=g)
+    gt = flow + torch.randn(B, 2, H, Wd, generator=g)
+    fr, f2r = flow.clone().requires_grad_(True), f2.clone().requires_grad_(True)
+    photo, epe, _, _ = O.photometric_epe(f1, f2r, fr, gt)
+    (photo * 0.7 + epe * 1.3).backward()
+    fc, f2c = flow.cuda().requires_grad_(True), f2.cuda().requires_grad_(True)
+    p2, e2 = W.photometric_epe(f1.cuda(), f2c, fc, gt.cuda())
+    (p2 * 0.7 + e2 * 1.3).backward()
+    np.testing.assert_allclose(p2.item(), photo.item(), rtol=1e-5)
+    np.testing.assert_allclose(e2.item(), epe.item(), rtol=1e-5)
+    np.testing.assert_allclose(fc.grad.cpu().numpy(), fr.grad.numpy(), rtol=2e-4, atol=1e-7)
+    np.testing.assert_allclose(f2c.grad.cpu().numpy(), f2r.grad.numpy(), rtol=2e-4, atol=1e-8)
+
+
+def test_photo_epe_deterministic(W):
+    g = torch.Generator().manual_seed(8)
+    B, C, H, Wd = 2, 3, 64, 96
+    args = [torch.rand(B, C, H, Wd, generator=g).cuda(), torch.rand(B, C, H, Wd, generator=g).cuda(),
+            (torch.randn(B, 2, H, Wd, generator=g) * 4).cuda(), (torch.randn(B, 2, H, Wd, generator=g) * 4).cuda()]
+    a = W.photometric_epe(*args)
+    b = W.photometric_epe(*args)
+    assert a[0].item() == b[0].item() and a[1].item() == b[1].item()
+
+
+@pytest.mark.parametrize("cfg", [(1, 0, 0), (2, 0, 0), (2, 1, 1), (4, 1, 3), (8, 0, 0)])
+def test_splat_golden(W, golden, cfg):
+    g = golden("splat")
+    scale, ox, oy = cfg
+    tag = f"s{scale}_{ox}_{oy}"
+    x = T(g["x"]).cuda().requires_grad_(True)
+    flow = T(g["flow"]).cuda().requires_grad_(True)
+    out = W.softsplat_func.apply(x, flow, scale, ox, oy)
+    np.testing.assert_allclose(out.detach().cpu().numpy(), g[f"out_{tag}"], rtol=1e-5, atol=1e-5)
+    out.backward(T(g[f"gout_{tag}"]).cuda())
+    np.testing.assert_allclose(x.grad.cpu().numpy(), g[f"gin_{tag}"], rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(flow.grad.cpu().numpy(), g[f"gflow_{tag}"], rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize("shape_scale", [((2, 4, 16, 24), 1), ((1, 3, 19, 21), 1), ((2, 4, 32, 64), 2), ((1, 4, 48, 40), 4),
+                                         ((1, 4, 64, 64), 16)])
+def test_splat_vs_oracle(W, shape_scale):
+    (B, C, H, Wd), scale = shape_scale
+    g = torch.Generator().manual_seed(31 + scale)
+    x = torch.randn(B, C, H, Wd, generator=g)
+    flow = torch.randn(B, 2, H, Wd, generator=g) * 3.0
+    flow[0, 0, 1, 1] = float("nan")
+    flow[0, :, 2, 2] = torch.tensor([float(Wd), float(H)])     # the ">= size-1" remap branch
+    flow[0, :, H - 1, Wd - 1] = torch.tensor([0.3, 0.6])
+    for ox, oy in ((0, 0), (scale - 1, scale // 2)):
+        ref = O.splat_forward(x, flow, scale, ox, oy)
+        xc, fc = x.cuda().requires_grad_(True), flow.cuda().requires_grad_(True)
+        out = W.softsplat_func.apply(xc, fc, scale, ox, oy)
+        # each target cell sums ~scale^2 atomically-ordered contributions: tolerance grows with scale
+        tol = 1e-5 * max(1, scale)
+        np.testing.assert_allclose(out.detach().cpu().numpy(), ref.numpy(), rtol=tol, atol=tol)
+        gout = torch.randn(ref.shape, generator=g)
+        out.backward(gout.cuda())
+        np.testing.assert_allclose(xc.grad.cpu().numpy(), O.splat_ingrad(x.shape, flow, gout, scale, ox, oy).numpy(),
+                                   rtol=1e-5, atol=1e-5)
+        np.testing.assert_allclose(fc.grad.cpu().numpy(), O.splat_flowgrad(x, flow, gout, scale, ox, oy).numpy(),
+                                   rtol=1e-4, atol=1e-4)
+
+
+def test_splat_scale_consistency_property(W):
+    """The property the reference fuzzes in warp_test.py:59-75:
+    splat(src, flow, scale=L, offset)/L^2 == splat(splat(src, flow), 0, scale=L, offset)/L^2."""
+    g = torch.Generator().manual_seed(77)
+    src = torch.rand(1, 1, 128, 128, generator=g).cuda()
+    for L, off in ((2, (0, 0)), (2, (1, 1)), (4, (1, 2))):
+        ints = torch.randint(-2, 3, (1, 2, 128, 128), generator=g).float()
+        frac = torch.rand(1, 2, 128, 128, generator=g) * 4 - 2
+        pick = torch.rand(1, 1, 128, 128, generator=g) < 0.5
+        flow = torch.where(pick, ints, frac).cuda()
+        a = W.warp_forward_flow(src, None, flow, scale=L, set_nans=False, offset=off) / L ** 2
+        full = W.warp_forward_flow(src, None, flow, set_nans=False)
+        b = W.warp_forward_flow(full, None, torch.zeros_like(flow), scale=L, set_nans=False, offset=off) / L ** 2
+        inner = (slice(None), slice(None), slice(2, -2), slice(2, -2))
+        np.testing.assert_allclose(a[inner].cpu().numpy(), b[inner].cpu().numpy(), atol=1e-4)
+
+
+def test_warp_forward_flow_vs_oracle(W):
+    g = torch.Generator().manual_seed(12)
+    first = torch.rand(2, 3, 24, 32, generator=g)
+    first[0, 1, 3, 3] = float("nan")
+    flow = torch.randn(2, 2, 24, 32, generator=g) * 2
+    for scale, off in ((1, (0, 0)), (2, (1, 0))):
+        ref = O.warp_forward_flow(first, flow, scale, True, off)
+        out = W.warp_forward_flow(first.cuda(), None, flow.cuda(), scale=scale, offset=off).cpu()
+        assert torch.equal(torch.isnan(out), torch.isnan(ref))
+        np.testing.assert_allclose(torch.nan_to_num(out).numpy(), torch.nan_to_num(ref).numpy(), rtol=1e-5, atol=1e-5)
+        # the generic (python-wrapper) path agrees with the fused one
+        gen = W.warp_forward_flow(first.cuda(), None, flow.cuda(), scale=scale, offset=off, warp_style="sum",
+                                  get_variance=False)
+        assert gen.shape == out.shape
+
+
+def test_nan_mse(W, golden):
+    g = golden("misc")
+    a = T(g["a"]).cuda().requires_grad_(True)
+    b = T(g["b"]).cuda()
+    loss = W.nan_mse(a, b)
+    np.testing.assert_allclose(loss.item(), float(g["nan_mse_mean"]), rtol=1e-6)
+    loss.backward()
+    ar = T(g["a"]).clone().requires_grad_(True)
+    O.nan_mse(ar, T(g["b"])).backward()
+    np.testing.assert_allclose(a.grad.cpu().numpy(), ar.grad.numpy(), rtol=1e-5, atol=1e-8)
+    np.testing.assert_array_equal(W.nan_mse(a.detach(), b, "none").cpu().numpy(), g["nan_mse_none"])
+    # empty after filtering -> NaN like torch.nanmean of an empty tensor
+    z = torch.full((4,), float("nan")).cuda()
+    assert torch.isnan(W.nan_mse(z, z))
+
+
+def test_full_size_properties(W):
+    """BASELINE config #4 size (8x436x1024): size-independent properties instead of an oracle run."""
+    B, C, H, Wd = 8, 3, 436, 1024
+    g = torch.Generator().manual_seed(3)
+    img = torch.rand(B, C, H, Wd, generator=g).cuda()
+    zero = torch.zeros(B, 2, H, Wd).cuda()
+    out, mask = W.warp_backward_flow(None, img, zero)
+    assert torch.equal(out, img) and bool((mask == 1).all())          # identity flow
+    shift = zero.clone()
+    shift[:, 1] = 3.0                                                  # dx = +3: columns move left
+    out, mask = W.warp_backward_flow(None, img, shift)
+    assert torch.allclose(out[..., :-3], img[..., 3:], atol=1e-6)
+    assert bool((mask[..., -3:] == 0).all()) and bool((mask[..., :-3] == 1).all())
+    # linearity in the image
+    flow = (torch.randn(B, 2, H, Wd, generator=g) * 4).cuda()
+    img2 = torch.rand(B, C, H, Wd, generator=g).cuda()
+    a, _ = W.warp_backward_flow(None, img, flow)
+    b, _ = W.warp_backward_flow(None, img2, flow)
+    c, _ = W.warp_backward_flow(None, img + img2, flow)
+    assert torch.allclose(a + b, c, atol=1e-5)
+    # splat conserves mass for in-bounds integer flow; photo loss of identical frames with zero flow = sqrt(1e-6)
+    ones = torch.ones(B, 1, H, Wd).cuda()
+    s = W.softsplat_func.apply(ones, zero, 1, 0, 0)
+    assert torch.equal(s, ones)
+    p, e = W.photometric_epe(img, img, zero, zero)
+    np.testing.assert_allclose(p.item(), 1e-3, rtol=1e-4)
+    assert e.item() == 0.0
