@@ -144,9 +144,10 @@ FD_API int fd_conv_igemm(const void* src0, int C0, const void* src1, int C1, con
 
 /* GroupNorm(8) apply + optional (scale+1, shift) + SiLU (+ optional residual add), bf16 NHWC:
  * Block.forward :181-187 and ResnetBlock's "+ res_conv(x)" :214.  stats from fd_conv_igemm.
- * scale_shift: fp32 [N][2*C] (scale first, then shift: time_emb.chunk(2), :208) or NULL. */
+ * scale_shift: fp32, row n at scale_shift + n*ss_stride holds [scale(C) | shift(C)] (time_emb.chunk(2), :208)
+ * or NULL.  gn_stats: double [N][8][2] as accumulated by fd_conv_igemm. */
 FD_API int fd_gn_silu(const void* x, const double* gn_stats, const float* gamma, const float* beta,
-               const float* scale_shift, const void* residual, void* out,
+               const float* scale_shift, long ss_stride, const void* residual, void* out,
                int N, int HW, int C, float eps, void* stream);
 
 /* channel LayerNorm (:116-125) over C per pixel, out = (x-mean)*rsqrt(var+eps)*g (+ residual) */

@@ -58,8 +58,8 @@ struct Cfg {
   static constexpr int kStageBytes = kATileBytes + kBTileBytes;
   static constexpr int kStages = BLOCK_N == 64 ? 8 : (BLOCK_N == 128 ? 6 : 4);
   static constexpr int kTmemCols = 2 * BLOCK_N;
-  // ring + barriers + bias (2 x BLOCK_N floats) + stats (2 x 16 floats) + tmem ptr, plus 1 KiB alignment slack
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256 + 2 * BLOCK_N * 4 + 2 * 16 * 4 + 64;
+  // ring + barriers + bias (2 x BLOCK_N floats) + stats (2 stages x 4 warps x 16 floats) + tmem ptr, plus 1 KiB slack
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256 + 2 * BLOCK_N * 4 + 2 * 4 * 16 * 4 + 64;
 };
 
 template <int BLOCK_N>
@@ -81,8 +81,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
   auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 2 + s); };
   uint8_t* gtail = gbase + STAGES * C::kStageBytes + 256;
   float* s_bias = reinterpret_cast<float*>(gtail);                       // [2][BLOCK_N]
-  float* s_stats = reinterpret_cast<float*>(gtail + 2 * BLOCK_N * 4);    // [2][16]
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(gtail + 2 * BLOCK_N * 4 + 2 * 16 * 4);
+  float* s_stats = reinterpret_cast<float*>(gtail + 2 * BLOCK_N * 4);    // [2][4 warps][16]
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(gtail + 2 * BLOCK_N * 4 + 2 * 4 * 16 * 4);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -190,9 +190,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
       const bool valid = (h < p.H) && (w < p.W);
       const int n0 = n_tile * BLOCK_N;
       float* bias_s = s_bias + as * BLOCK_N;
-      float* stats_s = s_stats + as * 16;
+      float* stats_s = s_stats + as * 64;            // [4 warps][16]: one private row per epilogue warp
+      float* stats_w = stats_s + (warp - 2) * 16;
       for (int i = et; i < BLOCK_N; i += kEpiThreads) bias_s[i] = p.bias ? __ldg(p.bias + n0 + i) : 0.f;
-      if (et < 16) stats_s[et] = 0.f;
+      if (et < 64) stats_s[et] = 0.f;
       named_bar_sync(1, kEpiThreads);
 
       mbar_wait(tfull_bar(as), aphase);
@@ -234,10 +235,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
             }
             s = fd_warp_sum(s);
             ss = fd_warp_sum(ss);
-            if (lane == 0) {
+            if (lane == 0) {        // only this warp touches its row: fixed summation order
               const int grp = (n0 + c + g0) / p.cpg;
-              atomicAdd(stats_s + grp * 2, s);
-              atomicAdd(stats_s + grp * 2 + 1, ss);
+              stats_w[grp * 2] += s;
+              stats_w[grp * 2 + 1] += ss;
             }
           }
         }
@@ -258,7 +259,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
       if (p.gn_stats != nullptr) {
         named_bar_sync(2, kEpiThreads);
         if (et < 16) {
-          const float sv = stats_s[et];
+          const float sv = (stats_s[et] + stats_s[16 + et]) + (stats_s[32 + et] + stats_s[48 + et]);
           if (sv != 0.f) atomicAdd(p.gn_stats + (long)img * 16 + et, (double)sv);
         }
       }

@@ -1,0 +1,497 @@
+// HBM-bound pieces of the UNet forward (denoising_diffusion.py:81-417) on bf16 NHWC activations:
+// input packing for the 7x7 init conv, weight standardisation + packing, GroupNorm apply (+ scale /
+// shift + SiLU + residual), channel LayerNorm, nearest upsample, time embedding MLPs, final 1x1
+// conv, layout conversions.  Every activation kernel moves 16 bytes (8 channels) per access and
+// keeps per-channel coefficients in registers across its pixel loop.
+#include "fd_common.cuh"
+
+namespace {
+
+int egrid(long items, int threads, int per_sm = 16) {
+  long blocks = (items + threads - 1) / threads;
+  const long cap = (long)FD_NUM_SMS * per_sm;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Unet.forward input assembly (:367-368) + UnetWithWarp NaN mask (flow_diffuser.py:39-45), emitted
+// as the horizontally unrolled tensor the 7x7 init conv consumes as a 7x1 conv over 64 channels:
+//   packed[b,h,w, kx*Ctot + c] = in[b,c,h,w+kx-3]   (zero outside the row, zero above 7*Ctot)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) pack_input_kernel(const float* __restrict__ x, const float* __restrict__ cond,
+                                                         __nv_bfloat16* __restrict__ packed, int B, int Cx, int Cc,
+                                                         int H, int W, int nan_mask) {
+  const long HW = (long)H * W;
+  const long total = (long)B * HW;
+  const int Ctot = Cx + (nan_mask ? 1 : 0) + Cc;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int b = (int)(i / HW);
+    const long p = i - (long)b * HW;
+    const int w = (int)(p % W);
+    float vals[64];
+#pragma unroll
+    for (int k = 0; k < 64; ++k) vals[k] = 0.f;
+#pragma unroll
+    for (int kx = 0; kx < 7; ++kx) {
+      const int ws = w + kx - 3;
+      if (ws < 0 || ws >= W) continue;
+      const long q = p + (kx - 3);
+      bool any_nan = false;
+      int c = 0;
+      for (int cx = 0; cx < Cx; ++cx, ++c) {
+        float v = __ldg(x + ((long)b * Cx + cx) * HW + q);
+        if (nan_mask && v != v) { any_nan = true; v = 0.f; }
+        vals[kx * Ctot + c] = v;
+      }
+      if (nan_mask) vals[kx * Ctot + (c++)] = any_nan ? 1.f : 0.f;
+      for (int cc = 0; cc < Cc; ++cc, ++c) vals[kx * Ctot + c] = __ldg(cond + ((long)b * Cc + cc) * HW + q);
+    }
+    uint4* dst = reinterpret_cast<uint4*>(packed + i * 64);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      uint4 o;
+      o.x = fd_pack_bf16(vals[q * 8 + 0], vals[q * 8 + 1]);
+      o.y = fd_pack_bf16(vals[q * 8 + 2], vals[q * 8 + 3]);
+      o.z = fd_pack_bf16(vals[q * 8 + 4], vals[q * 8 + 5]);
+      o.w = fd_pack_bf16(vals[q * 8 + 6], vals[q * 8 + 7]);
+      dst[q] = o;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// weight standardisation (:106-114) + bf16 packing into the implicit-GEMM K order.  One block per
+// output channel; statistics in fp32 (biased variance), two passes like the reference's reduce.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) prep_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ packed,
+                                                          int Cout, int Cin, int KH, int KW, int kind, int standardize,
+                                                          float eps, int Kpacked) {
+  __shared__ float red[32];
+  __shared__ float s_mean, s_rstd;
+  const int o = blockIdx.x;
+  const int n = Cin * KH * KW;
+  const float* wo = w + (long)o * n;
+  float mean = 0.f, rstd = 1.f;
+  if (standardize) {
+    float s[1] = {0.f};
+    for (int i = threadIdx.x; i < n; i += blockDim.x) s[0] += wo[i];
+    fd_block_sum<1>(s, red);
+    if (threadIdx.x == 0) s_mean = s[0] / (float)n;
+    __syncthreads();
+    mean = s_mean;
+    float v[1] = {0.f};
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const float d = wo[i] - mean;
+      v[0] += d * d;
+    }
+    fd_block_sum<1>(v, red);
+    if (threadIdx.x == 0) s_rstd = rsqrtf(v[0] / (float)n + eps);
+    __syncthreads();
+    rstd = s_rstd;
+  }
+  __nv_bfloat16* po = packed + (long)o * Kpacked;
+  if (kind == 2) {
+    for (int k = threadIdx.x; k < Kpacked; k += blockDim.x) po[k] = __float2bfloat16(0.f);
+    __syncthreads();
+  }
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    // torch order: i = (ci*KH + ky)*KW + kx
+    const int kx = i % KW;
+    const int ky = (i / KW) % KH;
+    const int ci = i / (KW * KH);
+    int k;
+    if (kind == 0) {
+      k = (ky * KW + kx) * Cin + ci;
+    } else if (kind == 1) {
+      const int C = Cin / 4;
+      k = (ci & 3) * C + (ci >> 2);       // torch channel c*4 + p1*2 + p2 -> (p1*2+p2)*C + c
+    } else {
+      k = ky * 64 + kx * Cin + ci;
+    }
+    po[k] = __float2bfloat16((wo[i] - mean) * rstd);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// GroupNorm(8) apply + (scale+1, shift) + SiLU (+ residual): Block.forward :181-187, ResnetBlock :214
+// y = silu(a[c] * x + b[c]) (+ res);  a = rstd*gamma*(scale+1), b = (beta - mean*rstd*gamma)*(scale+1) + shift
+// grid = (pixel blocks, N); thread owns one 8-channel chunk for a strided set of pixels.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) gn_silu_kernel(const __nv_bfloat16* __restrict__ x, const double* __restrict__ stats,
+                                                      const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                      const float* __restrict__ scale_shift, long ss_stride,
+                                                      const __nv_bfloat16* __restrict__ residual,
+                                                      __nv_bfloat16* __restrict__ out, long HW, int C, float eps) {
+  const int n = blockIdx.y;
+  const int chunks = C >> 3;
+  const int chunk = threadIdx.x % chunks;
+  const int prow = threadIdx.x / chunks;
+  const int ppb = blockDim.x / chunks;     // pixels per block pass
+  const int cpg = C >> 3;                  // channels per group (8 groups)
+  float a[8], b[8];
+  const double cnt = (double)HW * cpg;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = chunk * 8 + j;
+    const int g = c / cpg;
+    const double s = stats[((long)n * 8 + g) * 2], ss = stats[((long)n * 8 + g) * 2 + 1];
+    const double mean = s / cnt;
+    double var = ss / cnt - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+    float ga = __ldg(gamma + c) * rstd;
+    float be = __ldg(beta + c) - (float)mean * ga;
+    if (scale_shift != nullptr) {
+      const float sc = __ldg(scale_shift + (long)n * ss_stride + c) + 1.f;
+      const float sh = __ldg(scale_shift + (long)n * ss_stride + C + c);
+      ga *= sc;
+      be = be * sc + sh;
+    }
+    a[j] = ga;
+    b[j] = be;
+  }
+  const long base = (long)n * HW;
+  for (long p = (long)blockIdx.x * ppb + prow; p < HW; p += (long)gridDim.x * ppb) {
+    const long off = ((base + p) * C + chunk * 8);
+    const uint4 xv = __ldg(reinterpret_cast<const uint4*>(x + off));
+    const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w};
+    float y[8];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 f = fd_unpack_bf16(xw[e]);
+      y[2 * e] = fd_silu(a[2 * e] * f.x + b[2 * e]);
+      y[2 * e + 1] = fd_silu(a[2 * e + 1] * f.y + b[2 * e + 1]);
+    }
+    if (residual != nullptr) {
+      const uint4 rv = __ldg(reinterpret_cast<const uint4*>(residual + off));
+      const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 f = fd_unpack_bf16(rw[e]);
+        y[2 * e] += f.x;
+        y[2 * e + 1] += f.y;
+      }
+    }
+    uint4 o;
+    o.x = fd_pack_bf16(y[0], y[1]);
+    o.y = fd_pack_bf16(y[2], y[3]);
+    o.z = fd_pack_bf16(y[4], y[5]);
+    o.w = fd_pack_bf16(y[6], y[7]);
+    *reinterpret_cast<uint4*>(out + off) = o;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// channel LayerNorm (:116-125): per pixel over C, biased variance, gain only (+ residual).
+// LANES = min(C/8, 32) lanes cooperate on one pixel, each holding C/8/LANES 8-channel chunks.
+// ---------------------------------------------------------------------------------------------
+template <int LANES, int CHUNKS>
+__global__ void __launch_bounds__(256) chan_ln_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ g,
+                                                      const __nv_bfloat16* __restrict__ residual,
+                                                      __nv_bfloat16* __restrict__ out, long npix, float eps) {
+  constexpr int C = LANES * CHUNKS * 8;
+  const int sub = threadIdx.x % LANES;
+  const long gid = ((long)blockIdx.x * blockDim.x + threadIdx.x) / LANES;
+  const long gstride = ((long)gridDim.x * blockDim.x) / LANES;
+  float gain[CHUNKS][8];
+#pragma unroll
+  for (int k = 0; k < CHUNKS; ++k)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) gain[k][j] = __ldg(g + (k * LANES + sub) * 8 + j);
+  // all lanes of a warp iterate together (shuffles below), out-of-range pixel groups are masked
+  const long iters = (npix + gstride - 1) / gstride;
+  for (long it = 0; it < iters; ++it) {
+    const long p = gid + it * gstride;
+    const bool valid = p < npix;
+    float v[CHUNKS][8];
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < CHUNKS; ++k) {
+      uint4 xv = make_uint4(0, 0, 0, 0);
+      if (valid) xv = __ldg(reinterpret_cast<const uint4*>(x + p * C + (k * LANES + sub) * 8));
+      const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 f = fd_unpack_bf16(xw[e]);
+        v[k][2 * e] = f.x;
+        v[k][2 * e + 1] = f.y;
+        s += f.x + f.y;
+      }
+    }
+#pragma unroll
+    for (int o = LANES / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s * (1.f / C);
+    float ss = 0.f;
+#pragma unroll
+    for (int k = 0; k < CHUNKS; ++k)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float d = v[k][j] - mean;
+        ss += d * d;
+      }
+#pragma unroll
+    for (int o = LANES / 2; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    const float rstd = rsqrtf(ss * (1.f / C) + eps);
+    if (valid) {
+#pragma unroll
+      for (int k = 0; k < CHUNKS; ++k) {
+        const long off = p * C + (k * LANES + sub) * 8;
+        float y[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) y[j] = (v[k][j] - mean) * rstd * gain[k][j];
+        if (residual != nullptr) {
+          const uint4 rv = __ldg(reinterpret_cast<const uint4*>(residual + off));
+          const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 f = fd_unpack_bf16(rw[e]);
+            y[2 * e] += f.x;
+            y[2 * e + 1] += f.y;
+          }
+        }
+        uint4 o;
+        o.x = fd_pack_bf16(y[0], y[1]);
+        o.y = fd_pack_bf16(y[2], y[3]);
+        o.z = fd_pack_bf16(y[4], y[5]);
+        o.w = fd_pack_bf16(y[6], y[7]);
+        *reinterpret_cast<uint4*>(out + off) = o;
+      }
+    }
+  }
+}
+
+// nearest 2x upsample (:91): (N,H,W,C) -> (N,2H,2W,C), 16-byte granules
+__global__ void __launch_bounds__(256) upsample2x_kernel(const uint4* __restrict__ x, uint4* __restrict__ out, long N,
+                                                         int H, int W, int C8) {
+  const long total = N * H * W * C8;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C8);
+    long r = i / C8;
+    const int w = (int)(r % W);
+    r /= W;
+    const int h = (int)(r % H);
+    const long n = r / H;
+    const uint4 v = __ldg(x + i);
+    const long o = ((n * 2 * H + 2 * h) * 2 * W + 2 * w) * C8 + c;
+    out[o] = v;
+    out[o + C8] = v;
+    out[o + (long)2 * W * C8] = v;
+    out[o + (long)2 * W * C8 + C8] = v;
+  }
+}
+
+// SinusoidalPosEmb + Linear + GELU(erf) + Linear (:144-151, 319-324); one block per batch element
+__global__ void __launch_bounds__(256) time_embed_kernel(const int64_t* __restrict__ t, const float* __restrict__ w1,
+                                                         const float* __restrict__ b1, const float* __restrict__ w2,
+                                                         const float* __restrict__ b2, float* __restrict__ temb, int dim,
+                                                         int time_dim) {
+  extern __shared__ float sm[];
+  float* pe = sm;             // [dim]
+  float* hid = sm + dim;      // [time_dim]
+  const int b = blockIdx.x;
+  const int half = dim / 2;
+  const float tv = (float)t[b];
+  const float lg = logf(10000.f) / (float)(half - 1);
+  for (int i = threadIdx.x; i < half; i += blockDim.x) {
+    const float f = expf((float)i * -lg);
+    const float arg = tv * f;
+    pe[i] = sinf(arg);
+    pe[half + i] = cosf(arg);
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < time_dim; j += blockDim.x) {
+    float acc = b1[j];
+    for (int k = 0; k < dim; ++k) acc += pe[k] * __ldg(w1 + (long)j * dim + k);
+    hid[j] = 0.5f * acc * (1.f + erff(acc * 0.70710678118654752440f));
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < time_dim; j += blockDim.x) {
+    float acc = b2[j];
+    for (int k = 0; k < time_dim; ++k) acc += hid[k] * __ldg(w2 + (long)j * time_dim + k);
+    temb[(long)b * time_dim + j] = acc;
+  }
+}
+
+// ResnetBlock.mlp (:193-196,206) for all blocks at once: out[b][j] = bias[j] + sum_k silu(temb[b][k]) w[j][k]
+// one warp per (b, j)
+__global__ void __launch_bounds__(256) time_proj_kernel(const float* __restrict__ temb, const float* __restrict__ w,
+                                                        const float* __restrict__ bias, float* __restrict__ out, int B,
+                                                        int time_dim, int J) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= B * J) return;
+  const int b = warp / J, j = warp % J;
+  float acc = 0.f;
+  for (int k = lane; k < time_dim; k += 32) acc += fd_silu(temb[(long)b * time_dim + k]) * __ldg(w + (long)j * time_dim + k);
+  acc = fd_warp_sum(acc);
+  if (lane == 0) out[(long)b * J + j] = acc + bias[j];
+}
+
+// final 1x1 conv (:361,417): bf16 NHWC (Cin) -> fp32 NCHW (Cout <= 4); thread per pixel
+__global__ void __launch_bounds__(256) final_conv_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w,
+                                                         const float* __restrict__ bias, float* __restrict__ out, int N,
+                                                         long HW, int Cin, int Cout) {
+  extern __shared__ float sw[];   // [Cout][Cin] + [Cout]
+  for (int i = threadIdx.x; i < Cout * Cin; i += blockDim.x) sw[i] = w[i];
+  for (int i = threadIdx.x; i < Cout; i += blockDim.x) sw[Cout * Cin + i] = bias[i];
+  __syncthreads();
+  const long total = (long)N * HW;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    const uint4* row = reinterpret_cast<const uint4*>(x + i * Cin);
+    for (int q = 0; q < Cin / 8; ++q) {
+      const uint4 xv = __ldg(row + q);
+      const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 f = fd_unpack_bf16(xw[e]);
+#pragma unroll
+        for (int o = 0; o < 4; ++o)
+          if (o < Cout) acc[o] += f.x * sw[o * Cin + q * 8 + 2 * e] + f.y * sw[o * Cin + q * 8 + 2 * e + 1];
+      }
+    }
+    const long n = i / HW, p = i - n * HW;
+#pragma unroll
+    for (int o = 0; o < 4; ++o)
+      if (o < Cout) out[(n * Cout + o) * HW + p] = acc[o] + sw[Cout * Cin + o];
+  }
+}
+
+__global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out,
+                                                           int N, int C, long HW) {
+  const long total = (long)N * HW * C;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const long r = i / C;
+    const long p = r % HW, n = r / HW;
+    out[i] = __float2bfloat16(x[(n * C + c) * HW + p]);
+  }
+}
+__global__ void __launch_bounds__(256) nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out,
+                                                           int N, int C, long HW) {
+  const long total = (long)N * HW * C;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const long p = i % HW;
+    const long r = i / HW;
+    const int c = (int)(r % C);
+    const long n = r / C;
+    out[i] = __bfloat162float(x[(n * HW + p) * C + c]);
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+int fd_pack_input(const float* x, const float* cond, void* packed, int B, int Cx, int Cc, int H, int W, int nan_mask,
+                  void* stream) {
+  FD_REQUIRE(x && packed && B > 0 && H > 0 && W > 0 && Cx > 0 && Cc >= 0, "pack_input: bad argument");
+  FD_REQUIRE(cond != nullptr || Cc == 0, "pack_input: Cc > 0 needs cond");
+  FD_REQUIRE(Cx + (nan_mask ? 1 : 0) + Cc <= 9, "pack_input: at most 9 input channels (7 taps x 9 <= 64)");
+  pack_input_kernel<<<egrid((long)B * H * W, 256), 256, 0, (cudaStream_t)stream>>>(
+      x, cond, static_cast<__nv_bfloat16*>(packed), B, Cx, Cc, H, W, nan_mask);
+  FD_LAUNCH_CHECK();
+  return FD_OK;
+}
+
+int fd_prep_weight(const float* w, void* packed, int Cout, int Cin, int KH, int KW, int kind, int standardize, float eps,
+                   void* stream) {
+  FD_REQUIRE(w && packed && Cout > 0 && Cin > 0 && KH > 0 && KW > 0, "prep_weight: bad argument");
+  FD_REQUIRE(kind >= 0 && kind <= 2, "prep_weight: kind %d", kind);
+  FD_REQUIRE(kind != 1 || (Cin % 4 == 0 && KH == 1 && KW == 1), "prep_weight: kind 1 is a 1x1 over 4*C channels");
+  FD_REQUIRE(kind != 2 || KW * Cin <= 64, "prep_weight: kind 2 needs KW*Cin <= 64");
+  const int Kp = kind == 2 ? KH * 64 : Cin * KH * KW;
+  prep_weight_kernel<<<Cout, 256, 0, (cudaStream_t)stream>>>(w, static_cast<__nv_bfloat16*>(packed), Cout, Cin, KH, KW,
+                                                             kind, standardize, eps, Kp);
+  FD_LAUNCH_CHECK();
+  return FD_OK;
+}
+
+int fd_gn_silu(const void* x, const double* gn_stats, const float* gamma, const float* beta, const float* scale_shift,
+               long ss_stride, const void* residual, void* out, int N, int HW, int C, float eps, void* stream) {
+  FD_REQUIRE(x && gn_stats && gamma && beta && out && N > 0 && HW > 0, "gn_silu: bad argument");
+  FD_REQUIRE(C % 64 == 0 && C <= 2048, "gn_silu: C=%d must be a multiple of 64", C);
+  const int chunks = C / 8;
+  const int ppb = 256 / chunks > 0 ? 256 / chunks : 1;
+  FD_REQUIRE(chunks <= 256, "gn_silu: C too large");
+  long bx = ((long)HW + ppb - 1) / ppb;
+  const long cap = (long)FD_NUM_SMS * 16 / N + 1;
+  if (bx > cap) bx = cap;
+  dim3 grid((unsigned)bx, (unsigned)N);
+  gn_silu_kernel<<<grid, ppb * chunks, 0, (cudaStream_t)stream>>>(
+      static_cast<const __nv_bfloat16*>(x), gn_stats, gamma, beta, scale_shift, ss_stride,
+      static_cast<const __nv_bfloat16*>(residual), static_cast<__nv_bfloat16*>(out), (long)HW, C, eps);
+  FD_LAUNCH_CHECK();
+  return FD_OK;
+}
+
+int fd_chan_layernorm(const void* x, const float* g, const void* residual, void* out, long npix, int C, float eps,
+                      void* stream) {
+  FD_REQUIRE(x && g && out && npix > 0, "chan_layernorm: bad argument");
+  const __nv_bfloat16* xp = static_cast<const __nv_bfloat16*>(x);
+  const __nv_bfloat16* rp = static_cast<const __nv_bfloat16*>(residual);
+  __nv_bfloat16* op = static_cast<__nv_bfloat16*>(out);
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (C) {
+    case 64: chan_ln_kernel<8, 1><<<egrid(npix * 8, 256), 256, 0, st>>>(xp, g, rp, op, npix, eps); break;
+    case 128: chan_ln_kernel<16, 1><<<egrid(npix * 16, 256), 256, 0, st>>>(xp, g, rp, op, npix, eps); break;
+    case 256: chan_ln_kernel<32, 1><<<egrid(npix * 32, 256), 256, 0, st>>>(xp, g, rp, op, npix, eps); break;
+    case 512: chan_ln_kernel<32, 2><<<egrid(npix * 32, 256), 256, 0, st>>>(xp, g, rp, op, npix, eps); break;
+    default: FD_REQUIRE(false, "chan_layernorm: C=%d not in {64,128,256,512}", C);
+  }
+  FD_LAUNCH_CHECK();
+  return FD_OK;
+}
+
+int fd_upsample2x(const void* x, void* out, int N, int H, int W, int C, void* stream) {
+  FD_REQUIRE(x && out && N > 0 && H > 0 && W > 0 && C % 8 == 0, "upsample2x: bad argument");
+  const long total = (long)N * H * W * (C / 8);
+  upsample2x_kernel<<<egrid(total, 256), 256, 0, (cudaStream_t)stream>>>(static_cast<const uint4*>(x),
+                                                                        static_cast<uint4*>(out), N, H, W, C / 8);
+  FD_LAUNCH_CHECK();
+  return FD_OK;
+}
+
+int fd_time_embed(const int64_t* t, const float* w1, const float* b1, const float* w2, const float* b2, float* temb,
+                  int B, int dim, int time_dim, void* stream) {
+  FD_REQUIRE(t && w1 && b1 && w2 && b2 && temb && B > 0 && dim >= 4 && dim % 2 == 0 && time_dim > 0, "time_embed: bad argument");
+  time_embed_kernel<<<B, 256, (dim + time_dim) * sizeof(float), (cudaStream_t)stream>>>(t, w1, b1, w2, b2, temb, dim, time_dim);
+  FD_LAUNCH_CHECK();
+  return FD_OK;
+}
+
+int fd_time_proj(const float* temb, const float* w, const float* bias, float* out, int B, int time_dim, int J,
+                 void* stream) {
+  FD_REQUIRE(temb && w && bias && out && B > 0 && J > 0 && time_dim > 0, "time_proj: bad argument");
+  const long threads = (long)B * J * 32;
+  time_proj_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(temb, w, bias, out, B, time_dim, J);
+  FD_LAUNCH_CHECK();
+  return FD_OK;
+}
+
+int fd_final_conv(const void* x, const float* w, const float* bias, float* out, int N, int HW, int Cin, int Cout,
+                  void* stream) {
+  FD_REQUIRE(x && w && bias && out && N > 0 && HW > 0 && Cin % 8 == 0 && Cout >= 1 && Cout <= 4, "final_conv: bad argument");
+  final_conv_kernel<<<egrid((long)N * HW, 256), 256, (Cout * Cin + Cout) * sizeof(float), (cudaStream_t)stream>>>(
+      static_cast<const __nv_bfloat16*>(x), w, bias, out, N, (long)HW, Cin, Cout);
+  FD_LAUNCH_CHECK();
+  return FD_OK;
+}
+
+int fd_nchw_to_nhwc_bf16(const float* x, void* out, int N, int C, int HW, void* stream) {
+  FD_REQUIRE(x && out && N > 0 && C > 0 && HW > 0, "nchw_to_nhwc: bad argument");
+  nchw_to_nhwc_kernel<<<egrid((long)N * C * HW, 256), 256, 0, (cudaStream_t)stream>>>(x, static_cast<__nv_bfloat16*>(out), N, C, (long)HW);
+  FD_LAUNCH_CHECK();
+  return FD_OK;
+}
+
+int fd_nhwc_bf16_to_nchw(const void* x, float* out, int N, int C, int HW, void* stream) {
+  FD_REQUIRE(x && out && N > 0 && C > 0 && HW > 0, "nhwc_to_nchw: bad argument");
+  nhwc_to_nchw_kernel<<<egrid((long)N * C * HW, 256), 256, 0, (cudaStream_t)stream>>>(static_cast<const __nv_bfloat16*>(x), out, N, C, (long)HW);
+  FD_LAUNCH_CHECK();
+  return FD_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,296 @@
+"""The noise-prediction UNet of flow_diffuser (reference: ``Unet``, denoising_diffusion.py:272-417)
+executed by the sm_100a kernels of ``libflowdiff.so``.
+
+``Unet`` *is* the reference's parameter tree (same attribute names -> same ``state_dict`` keys, same
+construction order -> same random init under a given ``torch.manual_seed``); its ``forward`` walks
+that tree and launches kernels through the C ABI:
+
+* activations are bf16 NHWC; every convolution is ``fd_conv_igemm`` (tcgen05 + TMA), which also
+  accumulates the GroupNorm statistics of its output, so ``Block`` = conv + one ``fd_gn_silu`` pass;
+* skip concats, the pixel-unshuffle of ``Downsample`` and the ``+ res_conv(x)`` of ``ResnetBlock`` are
+  folded into the conv's operand maps / epilogue, never materialised;
+* weight standardisation + bf16 packing is one tiny launch per conv (``prepare``), cached while
+  the parameters are unchanged;
+* all 18 ResnetBlock time-MLPs run as one ``fd_time_proj`` over their concatenated weights.
+
+There is no PyTorch fallback: a missing library or a non-sm_100 device raises.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Tuple
+
+import torch
+
+from . import _lib
+from .unet_params import UnetParams, _ResnetBlock
+
+Tensor = torch.Tensor
+BF16 = torch.bfloat16
+
+
+class _PackedConv:
+    __slots__ = ("w", "bias", "cout", "kh", "kw", "pad", "mode", "src", "kind", "ws")
+
+    def __init__(self, src, kind: int, ws: bool, kh: int, kw: int, pad: Tuple[int, int], mode: int):
+        self.src, self.kind, self.ws = src, kind, ws
+        self.kh, self.kw, self.pad, self.mode = kh, kw, pad, mode
+        self.cout = src.weight.shape[0]
+        self.w: Optional[Tensor] = None
+        self.bias: Optional[Tensor] = None
+
+
+class Unet(UnetParams):
+    """Unet(dim=64, channels=C_in, out_dim=2): same constructor meaning as the reference (:272-293)."""
+
+    GN_EPS = 1e-5       # nn.GroupNorm default (:176)
+    WS_EPS = 1e-5       # WeightStandardizedConv2d with fp32 input (:107)
+    LN_EPS = 1e-5       # LayerNorm with fp32 input (:122)
+
+    def __init__(self, dim: int = 64, channels: int = 5, out_dim: int = 2, dim_mults=(1, 2, 4, 8), groups: int = 8):
+        super().__init__(dim, channels, out_dim, tuple(dim_mults), groups)
+        assert dim == 64 and tuple(dim_mults) == (1, 2, 4, 8) and groups == 8, \
+            "the sm_100a path is specialised to the flow_diffuser UNet (dim 64, mults 1-2-4-8, 8 groups)"
+        assert channels <= 9, "init_conv takes at most 9 input channels (7 taps x 9 <= 64)"
+        self._convs: Optional[Dict[str, _PackedConv]] = None
+        self._resblocks: List[Tuple[str, _ResnetBlock]] = []
+        self._tproj_w: Optional[Tensor] = None
+        self._tproj_b: Optional[Tensor] = None
+        self._tproj_off: Dict[str, int] = {}
+        self._prepared_versions = None
+
+    # ------------------------------------------------------------------ weight preparation
+    def _build_conv_table(self):
+        convs: Dict[str, _PackedConv] = {}
+
+        def add(name, mod, kind=0, ws=False, mode=0):
+            kh, kw = mod.weight.shape[2:]
+            if kind == 2:
+                convs[name] = _PackedConv(mod, 2, False, 7, 1, (3, 0), 0)
+            else:
+                convs[name] = _PackedConv(mod, kind, ws, kh, kw, (kh // 2, kw // 2), mode)
+
+        def add_res(name, rb: _ResnetBlock):
+            add(name + ".block1.proj", rb.block1.proj, ws=True)
+            add(name + ".block2.proj", rb.block2.proj, ws=True)
+            if not isinstance(rb.res_conv, torch.nn.Identity):
+                add(name + ".res_conv", rb.res_conv)
+            self._resblocks.append((name, rb))
+
+        def add_attn(name, res):
+            fn = res.fn.fn
+            add(name + ".to_qkv", fn.to_qkv)
+            add(name + ".to_out", fn.to_out[0] if isinstance(fn.to_out, torch.nn.Sequential) else fn.to_out)
+
+        self._resblocks = []
+        add("init_conv", self.init_conv, kind=2)
+        n = len(self.downs)
+        for i, (b1, b2, attn, down) in enumerate(self.downs):
+            add_res(f"downs.{i}.0", b1)
+            add_res(f"downs.{i}.1", b2)
+            add_attn(f"downs.{i}.2", attn)
+            if i < n - 1:
+                add(f"downs.{i}.3", down[1], kind=1, mode=1)
+            else:
+                add(f"downs.{i}.3", down)
+        add_res("mid_block1", self.mid_block1)
+        add_attn("mid_attn", self.mid_attn)
+        add_res("mid_block2", self.mid_block2)
+        for i, (b1, b2, attn, up) in enumerate(self.ups):
+            add_res(f"ups.{i}.0", b1)
+            add_res(f"ups.{i}.1", b2)
+            add_attn(f"ups.{i}.2", attn)
+            add(f"ups.{i}.3", up[1] if i < n - 1 else up)
+        add_res("final_res_block", self.final_res_block)
+        self._convs = convs
+
+    def _versions(self):
+        return tuple(p._version for p in self.parameters()) + tuple(p.data_ptr() for p in self.parameters())
+
+    @torch.no_grad()
+    def prepare(self, force: bool = False):
+        """Standardise + pack every conv weight to bf16 [Cout][K]; concatenate the time-MLP weights.
+        Cached until a parameter is modified in place or replaced."""
+        ver = self._versions()
+        if not force and self._convs is not None and ver == self._prepared_versions:
+            return
+        lib = _lib.load(check_device=True)
+        if self._convs is None:
+            self._build_conv_table()
+        st = _lib.stream()
+        for pc in self._convs.values():
+            w = pc.src.weight
+            _lib.require_cuda(w)
+            cout, cin, kh, kw = w.shape
+            kp = 7 * 64 if pc.kind == 2 else cin * kh * kw
+            if pc.w is None or pc.w.device != w.device:
+                pc.w = torch.empty(cout, kp, device=w.device, dtype=BF16)
+            _lib.check(lib.fd_prep_weight(_lib.ptr(w.detach().float().contiguous()), _lib.ptr(pc.w), cout, cin, kh, kw,
+                                          pc.kind, int(pc.ws), self.WS_EPS, st))
+            pc.bias = pc.src.bias.detach().float().contiguous() if pc.src.bias is not None else None
+        ws, bs, off = [], [], 0
+        self._tproj_off = {}
+        for name, rb in self._resblocks:
+            lin = rb.mlp[1]
+            self._tproj_off[name] = off
+            off += lin.weight.shape[0]
+            ws.append(lin.weight.detach().float())
+            bs.append(lin.bias.detach().float())
+        self._tproj_w = torch.cat(ws, 0).contiguous()
+        self._tproj_b = torch.cat(bs, 0).contiguous()
+        self._prepared_versions = ver
+
+    # ------------------------------------------------------------------ kernel wrappers
+    def _conv(self, name: str, src0: Tensor, src1: Optional[Tensor] = None, residual: Optional[Tensor] = None,
+              stats: Optional[Tensor] = None) -> Tensor:
+        pc = self._convs[name]
+        n, h, w, c0 = src0.shape
+        c1 = src1.shape[-1] if src1 is not None else 0
+        if pc.mode == 1:
+            h, w = h // 2, w // 2
+        out = torch.empty(n, h, w, pc.cout, device=src0.device, dtype=BF16)
+        _lib.check(self._lib.fd_conv_igemm(_lib.ptr(src0), c0, _lib.ptr(src1), c1, _lib.ptr(pc.w), _lib.ptr(pc.bias),
+                                           _lib.ptr(residual), _lib.ptr(out), _lib.ptr(stats), n, h, w, pc.cout,
+                                           pc.kh, pc.kw, pc.pad[0], pc.pad[1], pc.mode, self._st))
+        return out
+
+    def _gn_silu(self, x: Tensor, stats: Tensor, norm, ss: Optional[Tensor], ss_off: int,
+                 residual: Optional[Tensor]) -> Tensor:
+        n, h, w, c = x.shape
+        out = torch.empty_like(x)
+        ss_ptr = ss.data_ptr() + 4 * ss_off if ss is not None else None
+        _lib.check(self._lib.fd_gn_silu(_lib.ptr(x), _lib.ptr(stats), _lib.ptr(norm.weight), _lib.ptr(norm.bias), ss_ptr,
+                                        ss.shape[1] if ss is not None else 0, _lib.ptr(residual), _lib.ptr(out), n,
+                                        h * w, c, self.GN_EPS, self._st))
+        return out
+
+    def _chan_ln(self, x: Tensor, g: Tensor, residual: Optional[Tensor] = None) -> Tensor:
+        n, h, w, c = x.shape
+        out = torch.empty_like(x)
+        _lib.check(self._lib.fd_chan_layernorm(_lib.ptr(x), _lib.ptr(g), _lib.ptr(residual), _lib.ptr(out), n * h * w, c,
+                                               self.LN_EPS, self._st))
+        return out
+
+    def _resnet(self, name: str, rb: _ResnetBlock, x0: Tensor, x1: Optional[Tensor], ss: Tensor) -> Tensor:
+        """ResnetBlock.forward (:202-214)."""
+        st1, st2 = self._next_stats(), self._next_stats()
+        h1 = self._conv(name + ".block1.proj", x0, x1, stats=st1)
+        a1 = self._gn_silu(h1, st1, rb.block1.norm, ss, self._tproj_off[name], None)
+        h2 = self._conv(name + ".block2.proj", a1, stats=st2)
+        if (name + ".res_conv") in self._convs:
+            a2 = self._gn_silu(h2, st2, rb.block2.norm, None, 0, None)
+            return self._conv(name + ".res_conv", x0, x1, residual=a2)
+        assert x1 is None
+        return self._gn_silu(h2, st2, rb.block2.norm, None, 0, x0)
+
+    def _linear_attention(self, name: str, res, x: Tensor) -> Tensor:
+        """Residual(PreNorm(LinearAttention)) (:81-87,127-135,229-244)."""
+        n, h, w, c = x.shape
+        y = self._chan_ln(x, res.fn.norm.g)
+        qkv = self._conv(name + ".to_qkv", y)
+        att = torch.empty(n, h, w, 128, device=x.device, dtype=BF16)
+        ws = torch.empty(self._lib.fd_linattn_workspace_floats(n, h * w), device=x.device, dtype=torch.float32)
+        _lib.check(self._lib.fd_linattn(_lib.ptr(qkv), _lib.ptr(att), _lib.ptr(ws), n, h * w, self._st))
+        o = self._conv(name + ".to_out", att)
+        return self._chan_ln(o, res.fn.fn.to_out[1].g, residual=x)
+
+    def _attention(self, name: str, res, x: Tensor) -> Tensor:
+        """Residual(PreNorm(Attention)) (:246-268)."""
+        n, h, w, c = x.shape
+        y = self._chan_ln(x, res.fn.norm.g)
+        qkv = self._conv(name + ".to_qkv", y)
+        att = torch.empty(n, h, w, 128, device=x.device, dtype=BF16)
+        _lib.check(self._lib.fd_attention(_lib.ptr(qkv), _lib.ptr(att), n, h * w, self._st))
+        return self._conv(name + ".to_out", att, residual=x)
+
+    def _next_stats(self) -> Tensor:
+        s = self._stats[self._stats_i]
+        self._stats_i += 1
+        return s
+
+    # ------------------------------------------------------------------ forward
+    @torch.no_grad()
+    def forward(self, x: Tensor, external_cond: Optional[Tensor], time: Tensor, nan_mask: bool = False,
+                return_taps: bool = False):
+        """``Unet.forward(x, external_cond, time)`` (:363-417): x (B,Cx,H,W) fp32, cond (B,Cc,H,W) fp32, time (B,)
+        int64 -> (B,out_dim,H,W) fp32.  ``nan_mask`` folds UnetWithWarp's NaN -> 0 + mask channel
+        (flow_diffuser.py:39-45) into the input packing."""
+        _lib.require_cuda(x, external_cond, time)
+        self.prepare()
+        self._lib = _lib.load()
+        self._st = _lib.stream()
+        lib, st = self._lib, self._st
+        B, Cx, H, W = x.shape
+        assert H % 8 == 0 and W % 8 == 0, "pad to a multiple of 8 first (three 2x downsamples, :95-99)"
+        Cc = external_cond.shape[1] if external_cond is not None else 0
+        assert Cx + int(nan_mask) + Cc == self.channels, (Cx, nan_mask, Cc, self.channels)
+        dev = x.device
+        x = x.float().contiguous()
+        cond = external_cond.float().contiguous() if external_cond is not None else None
+        time = time.to(torch.int64).contiguous()
+        taps = {}
+
+        # time embedding (:319-324) and every block's (scale, shift) (:206-208)
+        temb = torch.empty(B, self.time_dim, device=dev, dtype=torch.float32)
+        tm = self.time_mlp
+        _lib.check(lib.fd_time_embed(_lib.ptr(time), _lib.ptr(tm[1].weight), _lib.ptr(tm[1].bias), _lib.ptr(tm[3].weight),
+                                     _lib.ptr(tm[3].bias), _lib.ptr(temb), B, self.dim, self.time_dim, st))
+        J = self._tproj_w.shape[0]
+        ss = torch.empty(B, J, device=dev, dtype=torch.float32)
+        _lib.check(lib.fd_time_proj(_lib.ptr(temb), _lib.ptr(self._tproj_w), _lib.ptr(self._tproj_b), _lib.ptr(ss), B,
+                                    self.time_dim, J, st))
+        self._stats = torch.zeros(2 * len(self._resblocks), B, 8, 2, device=dev, dtype=torch.float64)
+        self._stats_i = 0
+
+        # init_conv 7x7 (:297,374) as a 7x1 conv over the horizontally unrolled input
+        packed = torch.empty(B, H, W, 64, device=dev, dtype=BF16)
+        _lib.check(lib.fd_pack_input(_lib.ptr(x), _lib.ptr(cond), _lib.ptr(packed), B, Cx, Cc, H, W, int(nan_mask), st))
+        h = self._conv("init_conv", packed)
+        del packed
+        r = h
+        if return_taps:
+            taps["temb"] = temb
+            taps["init_conv"] = h
+
+        skips: List[Tensor] = []
+        n_levels = len(self.downs)
+        for i, (b1, b2, attn, down) in enumerate(self.downs):
+            h = self._resnet(f"downs.{i}.0", b1, h, None, ss)
+            skips.append(h)
+            if return_taps and i == 0:
+                taps["downs.0.0"] = h
+            h = self._resnet(f"downs.{i}.1", b2, h, None, ss)
+            h = self._linear_attention(f"downs.{i}.2", attn, h)
+            if return_taps and i == 0:
+                taps["downs.0.2"] = h
+            skips.append(h)
+            h = self._conv(f"downs.{i}.3", h)
+        h = self._resnet("mid_block1", self.mid_block1, h, None, ss)
+        if return_taps:
+            taps["mid_block1"] = h
+        h = self._attention("mid_attn", self.mid_attn, h)
+        if return_taps:
+            taps["mid_attn"] = h
+        h = self._resnet("mid_block2", self.mid_block2, h, None, ss)
+        for i, (b1, b2, attn, up) in enumerate(self.ups):
+            h = self._resnet(f"ups.{i}.0", b1, h, skips.pop(), ss)
+            h = self._resnet(f"ups.{i}.1", b2, h, skips.pop(), ss)
+            h = self._linear_attention(f"ups.{i}.2", attn, h)
+            if i < n_levels - 1:
+                n_, hh, ww, cc = h.shape
+                up_t = torch.empty(n_, 2 * hh, 2 * ww, cc, device=dev, dtype=BF16)
+                _lib.check(lib.fd_upsample2x(_lib.ptr(h), _lib.ptr(up_t), n_, hh, ww, cc, st))
+                h = self._conv(f"ups.{i}.3", up_t)
+                del up_t
+            else:
+                h = self._conv(f"ups.{i}.3", h)
+        h = self._resnet("final_res_block", self.final_res_block, h, r, ss)
+        if return_taps:
+            taps["final_res_block"] = h
+        out = torch.empty(B, self.out_dim, H, W, device=dev, dtype=torch.float32)
+        fc = self.final_conv
+        _lib.check(lib.fd_final_conv(_lib.ptr(h), _lib.ptr(fc.weight), _lib.ptr(fc.bias), _lib.ptr(out), B, H * W, self.dim,
+                                     self.out_dim, st))
+        self._stats = None
+        if return_taps:
+            return out, {k: (v if v.dim() == 2 else v.permute(0, 3, 1, 2).float()) for k, v in taps.items()}
+        return out

@@ -1,0 +1,60 @@
+"""Times fd_conv_igemm on the implicit-GEMM shapes of SURVEY.md appendix A (batch 8, 440x1024)."""
+import json
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from opticalflowdiffusion_b200 import _lib  # noqa: E402
+
+SHAPES = [
+    # name, C0, C1, Cout, H, W, k
+    ("3x3 64->64 full", 64, 0, 64, 440, 1024, 3),
+    ("3x3 128->64 full", 64, 64, 64, 440, 1024, 3),
+    ("3x3 192->128 half", 128, 64, 128, 220, 512, 3),
+    ("3x3 128->128 half", 128, 0, 128, 220, 512, 3),
+    ("3x3 384->256 quarter", 256, 128, 256, 110, 256, 3),
+    ("3x3 256->256 quarter", 256, 0, 256, 110, 256, 3),
+    ("3x3 512->512 eighth", 512, 0, 512, 55, 128, 3),
+    ("3x3 768->512 eighth", 512, 256, 512, 55, 128, 3),
+    ("1x1 64->384 full", 64, 0, 384, 440, 1024, 1),
+    ("1x1 128->64 full", 128, 0, 64, 440, 1024, 1),
+]
+
+
+def main():
+    lib = _lib.load(check_device=True)
+    N = int(os.environ.get("BATCH", 8))
+    res = {}
+    for name, c0, c1, cout, H, W, k in SHAPES:
+        x0 = torch.randn(N, H, W, c0, device="cuda").to(torch.bfloat16)
+        x1 = torch.randn(N, H, W, c1, device="cuda").to(torch.bfloat16) if c1 else None
+        wp = (torch.randn(cout, k * k * (c0 + c1), device="cuda") * 0.02).to(torch.bfloat16)
+        bias = torch.zeros(cout, device="cuda")
+        out = torch.empty(N, H, W, cout, device="cuda", dtype=torch.bfloat16)
+        gn = torch.zeros(N, 8, 2, device="cuda", dtype=torch.float64) if k == 3 else None
+        P = _lib.ptr
+
+        def fn():
+            _lib.check(lib.fd_conv_igemm(P(x0), c0, P(x1), c1, P(wp), P(bias), None, P(out), P(gn), N, H, W, cout, k, k,
+                                         k // 2, k // 2, 0, _lib.stream()))
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        iters = 10
+        s.record()
+        for _ in range(iters):
+            fn()
+        e.record()
+        torch.cuda.synchronize()
+        t = s.elapsed_time(e) * 1e-3 / iters
+        flops = 2.0 * N * H * W * cout * k * k * (c0 + c1)
+        res[name] = {"ms": round(t * 1e3, 3), "TFLOPs": round(flops / t / 1e12, 1)}
+        del x0, x1, out
+    print(json.dumps(res, indent=1))
+
+
+if __name__ == "__main__":
+    main()

@@ -98,7 +98,10 @@ def test_conv_igemm(L, case):
     out, gn = run_conv(L, xs, w, bias, pad, res, stats)
     ref = ref_conv(xs, w, bias, pad, res)
     close(out, ref)
+    out2, gn2 = run_conv(L, xs, w, bias, pad, res, stats)
+    assert torch.equal(out, out2)                      # run-to-run bit-stable
     if stats:
+        assert torch.allclose(gn, gn2, rtol=1e-12, atol=1e-9)
         r = ref.double().reshape(N, 8, -1)
         s = torch.stack((r.sum(-1), (r * r).sum(-1)), -1)
         assert torch.allclose(gn, s, rtol=1e-3, atol=1e-2 * r.shape[-1] ** 0.5), (gn - s).abs().max()

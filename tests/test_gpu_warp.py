@@ -205,11 +205,13 @@ def test_full_size_properties(W):
     img = torch.rand(B, C, H, Wd, generator=g).cuda()
     zero = torch.zeros(B, 2, H, Wd).cuda()
     out, mask = W.warp_backward_flow(None, img, zero)
-    assert torch.equal(out, img) and bool((mask == 1).all())          # identity flow
+    # zero flow: the reference's fp32 normalise/un-normalise round trip is not exactly the identity
+    # (SURVEY.md section 8a W1), so the warp reproduces the image only to a few ulps of the coordinate
+    assert torch.allclose(out, img, atol=2e-4) and bool((mask == 1).all())
     shift = zero.clone()
     shift[:, 1] = 3.0                                                  # dx = +3: columns move left
     out, mask = W.warp_backward_flow(None, img, shift)
-    assert torch.allclose(out[..., :-3], img[..., 3:], atol=1e-6)
+    assert torch.allclose(out[..., :-3], img[..., 3:], atol=2e-4)
     assert bool((mask[..., -3:] == 0).all()) and bool((mask[..., :-3] == 1).all())
     # linearity in the image
     flow = (torch.randn(B, 2, H, Wd, generator=g) * 4).cuda()
