@@ -1,0 +1,257 @@
+#!/usr/bin/env python
+"""Headline benchmark of the flow_diffuser hot path (BASELINE.json configs[1]):
+DDIM-50 flow sampling, Sintel-shaped synthetic 436x1024 frames, batch 8 per GPU.
+
+    python bench.py --gpus N --steps K --warmup W            # this implementation (CUDA, sm_100a)
+    python bench.py --impl reference --gpus N ...            # the reference algorithm on the host CPU cores
+
+One "step" = one DDIM-50 sampling pass over one batch of 8 frame pairs = 8 flows.
+Prints ONE JSON line (rank 0).  Multi-GPU: one process per GPU under torchrun, the batch is sharded
+by rank with no data-path collective (sampling has no exchange step) -> weak scaling.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+H, W, BATCH, DDIM_STEPS, TIMESTEPS = 436, 1024, 8, 50, 1000
+CONV_GF_PER_SAMPLE = 1590.3      # algorithmic conv GFLOP per UNet forward at 440x1024
+FWD_GF_PER_SAMPLE = 1635.28      # whole forward (conv + attention matmuls)
+CONFIG = {"workload": "flow_diffuser DDIM-50 sampling, Sintel-shaped synthetic 436x1024 (UNet runs on 440x1024), "
+                      "target=flow, batch 8 per GPU, random-init weights seed 0",
+          "batch_per_gpu": BATCH, "ddim_steps": DDIM_STEPS, "timesteps": TIMESTEPS, "parallelism": "batch-sharded replicas",
+          "l2": "working set >> L2: every bf16 activation tensor is 461 MB at full resolution, no reuse between steps"}
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return {"hbm": p["hbm_gbs"], "tf_burst": p["bf16_tflops"], "tf_sustained": p["bf16_tflops_sustained"],
+                "src": "MEASURED_PEAKS.json"}
+    except Exception:  # noqa: BLE001
+        return {"hbm": 6650.0, "tf_burst": 1590.0, "tf_sustained": 1400.0, "src": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU reference arm / cpu_baseline: the oracle's fp32 restatement of the reference algorithm
+# (the reference tree itself cannot travel to the GPU box) on all host threads.
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_step_seconds(steps: int, warmup: int):
+    """Each step = ONE of the 50 DDIM steps of ONE 436x1024 sample (UNet forward + update); flows/s = 1/(50 t)."""
+    from oracle import flowdiff_oracle as O
+    from opticalflowdiffusion_b200.unet_params import UnetParams
+    torch.manual_seed(0)
+    sd = UnetParams(64, channels=5, out_dim=2).state_dict()
+    sched = O.make_schedule(TIMESTEPS)
+    cond = O.replicate_pad_to_multiple(O.synthetic_frames(1, H, W, seed=0) * 2 - 1)[0]
+    x = torch.randn(1, 2, cond.shape[-2], cond.shape[-1], generator=torch.Generator().manual_seed(1234))
+    times = O.ddim_times(TIMESTEPS, DDIM_STEPS)
+    ts = []
+    with torch.no_grad():
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            tt = torch.full((1,), times[0], dtype=torch.long)
+            out = O.unet_forward(sd, x, cond, tt)
+            O.ddim_update(sched, x, out, times[0], times[1])
+            if i >= warmup:
+                ts.append(time.perf_counter() - t0)
+    return ts
+
+
+def run_reference(args, rank: int):
+    if rank != 0:
+        return
+    threads = torch.get_num_threads()
+    ts = cpu_reference_step_seconds(args.steps, min(args.warmup, 1))
+    t = sum(ts) / len(ts)
+    value = 1.0 / (DDIM_STEPS * t)
+    sample = "one of the 50 DDIM steps of ONE 436x1024 sample per step (UNet forward + update), x50 extrapolated"
+    line = {"impl": "reference", "metric": "flows/sec DDIM-50 @436x1024", "value": value, "unit": "flows/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": t * 1e3 * DDIM_STEPS * BATCH,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": CONFIG,
+            "cpu_baseline": {"value": value, "unit": "flows/s", "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "flows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+def run_ours(args, rank: int, world: int, local_rank: int):
+    import torch.distributed as dist
+    from opticalflowdiffusion_b200 import FlowDiffuser, _lib
+    from opticalflowdiffusion_b200.config import compose
+    from opticalflowdiffusion_b200.datasets import synthetic_frames
+
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    lib = _lib.load(check_device=True)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    cfg = compose(["algorithm.target=flow", f"algorithm.sampling_timesteps={DDIM_STEPS}",
+                   f"algorithm.image_size=[{H},{W}]", "algorithm.return_all_timesteps=true"])
+    torch.manual_seed(0)
+    algo = FlowDiffuser(cfg.algorithm).to(dev)
+    algo.unet.prepare()
+    frames = synthetic_frames(BATCH, H, W, seed=100 + rank)
+    cond_host = (2 * frames - 1).pin_memory()
+    flow_host = torch.zeros(BATCH, 2, H, W).pin_memory()
+    out_host = torch.empty(BATCH, 2, H, W).pin_memory()
+    cond_dev = cond_host.to(dev)
+    flow_dev = flow_host.to(dev)
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    x_T = torch.randn(BATCH, 2, H, W, device=dev, generator=gen)
+
+    def sync():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def step_resident():
+        return algo.sample(cond_dev, flow_dev, x_T=x_T)
+
+    def step_e2e():
+        c = cond_host.to(dev, non_blocking=True)
+        f = flow_host.to(dev, non_blocking=True)
+        _, flows = algo.sample(c, f, x_T=x_T)
+        out_host.copy_(flows[:, -1], non_blocking=True)
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        sync()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(steps):
+            fn()
+        e.record()
+        sync()
+        t = torch.tensor([s.elapsed_time(e) * 1e-3], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t)
+
+    for _ in range(max(args.warmup, 3) if args.warmup >= 0 else 3):
+        step_resident()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    l0 = lib.fd_launch_count()
+    t_res = timed(step_resident, args.steps)
+    launches = int(lib.fd_launch_count() - l0)
+    t_e2e = timed(step_e2e, args.steps)
+    clk = clocks.stop() if rank == 0 else None
+
+    # roofline pass (not timed above): CUDA events around every tensor-core conv launch of one UNet forward
+    algo.unet._conv_timing = []
+    t = torch.full((BATCH,), 999, device=dev, dtype=torch.long)
+    algo.unet(x_T, cond_dev, t)
+    torch.cuda.synchronize()
+    conv_s = sum(ev[0].elapsed_time(ev[1]) for _, _, ev in algo.unet._conv_timing) * 1e-3
+    conv_launches = len(algo.unet._conv_timing)
+    algo.unet._conv_timing = None
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    algo.unet(x_T, cond_dev, t)
+    e.record()
+    torch.cuda.synchronize()
+    fwd_s = s.elapsed_time(e) * 1e-3
+
+    if rank != 0:
+        return
+    peaks = load_peaks()
+    flows = world * BATCH * args.steps
+    value = flows / t_res
+    conv_tf = CONV_GF_PER_SAMPLE * BATCH * 1e9 / conv_s / 1e12
+    line = {
+        "metric": "flows/sec DDIM-50 @436x1024", "value": value, "unit": "flows/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": t_res / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": CONFIG,
+        "e2e": {"value": flows / t_e2e, "unit": "flows/s", "h2d_bytes_per_step": cond_host.numel() * 4 + flow_host.numel() * 4,
+                "d2h_bytes_per_step": out_host.numel() * 4},
+        "gpu_launches": launches,
+        "clocks": clk,
+        "roofline": {"bound": "tensor", "kernel": "conv_igemm_kernel (tcgen05 implicit GEMM, all %d conv launches of one forward)" % conv_launches,
+                     "achieved": conv_tf, "peak": peaks["tf_sustained"], "unit": "TFLOP/s", "frac": conv_tf / peaks["tf_sustained"],
+                     "traffic": None, "peak_source": peaks["src"] + " (sustained: the kernel is timed inside a long step)",
+                     "conv_share_of_forward": conv_s / fwd_s, "forward_ms": fwd_s * 1e3,
+                     "whole_step_tflops": FWD_GF_PER_SAMPLE * DDIM_STEPS * 1e9 * value / 1e12},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        ts = cpu_reference_step_seconds(1, 1)
+        tcpu = sum(ts) / len(ts)
+        line["cpu_baseline"] = {"value": 1.0 / (DDIM_STEPS * tcpu), "unit": "flows/s", "cores": torch.get_num_threads(),
+                                "kind": "port",
+                                "sample": "one of the 50 DDIM steps of ONE 436x1024 sample (UNet forward + update) on the host "
+                                          "cores after one warm-up, x50 extrapolated"}
+    print(json.dumps(line))
+    if world > 1:
+        pass
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    run_ours(args, rank, world, local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -40,6 +40,7 @@ FD_API const char* fd_arch(void);            /* "sm_100a" */
 FD_API const char* fd_last_error(void);
 FD_API int fd_device_check(void);            /* FD_OK iff the current device is compute capability 10.x */
 FD_API int fd_num_sms(void);
+FD_API unsigned long long fd_launch_count(void);   /* kernels launched by the library so far (this process) */
 
 /* ---- backward bilinear warp:  warp.py:95-119 (warp_backward_flow) --------------------
  * flow channel 0 = dy, channel 1 = dx (the reference flips).  out is NOT multiplied by mask.

@@ -23,6 +23,7 @@ SIGNATURES = {
     "fd_last_error": (c_char_p, []),
     "fd_device_check": (c_int, []),
     "fd_num_sms": (c_int, []),
+    "fd_launch_count": (ctypes.c_ulonglong, []),
     "fd_backwarp_fwd": (c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "fd_backwarp_bwd": (c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "fd_photo_epe_workspace_floats": (c_size_t, [_I, _I, _I]),

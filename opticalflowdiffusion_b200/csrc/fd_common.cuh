@@ -30,7 +30,12 @@ void fd_set_error(const char* fmt, ...);
     }                                                                              \
   } while (0)
 
-#define FD_LAUNCH_CHECK() FD_CUDA(cudaGetLastError())
+extern unsigned long long g_fd_launches;   // kernels launched by this library (bench.py's gpu_launches)
+#define FD_LAUNCH_CHECK()          \
+  do {                             \
+    ++g_fd_launches;               \
+    FD_CUDA(cudaGetLastError());   \
+  } while (0)
 
 static inline int fd_ceil_div(long a, long b) { return (int)((a + b - 1) / b); }
 

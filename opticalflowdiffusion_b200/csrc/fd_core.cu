@@ -4,6 +4,7 @@
 #include <string.h>
 
 static thread_local char g_fd_err[512] = "";
+unsigned long long g_fd_launches = 0;
 
 void fd_set_error(const char* fmt, ...) {
   va_list ap;
@@ -31,6 +32,8 @@ int fd_device_check(void) {
   }
   return FD_OK;
 }
+
+unsigned long long fd_launch_count(void) { return g_fd_launches; }
 
 int fd_num_sms(void) {
   int dev = 0, n = 0;

@@ -148,9 +148,17 @@ class Unet(UnetParams):
         if pc.mode == 1:
             h, w = h // 2, w // 2
         out = torch.empty(n, h, w, pc.cout, device=src0.device, dtype=BF16)
+        timing = getattr(self, "_conv_timing", None)
+        if timing is not None:      # bench.py's roofline pass: CUDA events around every conv launch
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            flops = 2.0 * n * h * w * pc.cout * pc.w.shape[1] if pc.kind != 2 else 2.0 * n * h * w * pc.cout * 49 * self.channels
+            timing.append((name, flops, ev))
+            ev[0].record()
         _lib.check(self._lib.fd_conv_igemm(_lib.ptr(src0), c0, _lib.ptr(src1), c1, _lib.ptr(pc.w), _lib.ptr(pc.bias),
                                            _lib.ptr(residual), _lib.ptr(out), _lib.ptr(stats), n, h, w, pc.cout,
                                            pc.kh, pc.kw, pc.pad[0], pc.pad[1], pc.mode, self._st))
+        if timing is not None:
+            ev[1].record()
         return out
 
     def _gn_silu(self, x: Tensor, stats: Tensor, norm, ss: Optional[Tensor], ss_off: int,
@@ -219,13 +227,23 @@ class Unet(UnetParams):
         self._lib = _lib.load()
         self._st = _lib.stream()
         lib, st = self._lib, self._st
-        B, Cx, H, W = x.shape
-        assert H % 8 == 0 and W % 8 == 0, "pad to a multiple of 8 first (three 2x downsamples, :95-99)"
+        B, Cx, H0, W0 = x.shape
         Cc = external_cond.shape[1] if external_cond is not None else 0
         assert Cx + int(nan_mask) + Cc == self.channels, (Cx, nan_mask, Cc, self.channels)
         dev = x.device
-        x = x.float().contiguous()
-        cond = external_cond.float().contiguous() if external_cond is not None else None
+        x = x.float()
+        cond = external_cond.float() if external_cond is not None else None
+        # three 2x pixel-unshuffle downsamples (:95-99) need H, W % 8 == 0 (436 -> 440): replicate-pad like the
+        # repo's own InputPadder(mode='sintel') (future/raft_utils.py:7-25) and crop the prediction back
+        ph, pw = (-H0) % 8, (-W0) % 8
+        pad = (pw // 2, pw - pw // 2, ph // 2, ph - ph // 2)
+        if ph or pw:
+            x = torch.nn.functional.pad(x, pad, mode="replicate")
+            if cond is not None:
+                cond = torch.nn.functional.pad(cond, pad, mode="replicate")
+        x = x.contiguous()
+        cond = cond.contiguous() if cond is not None else None
+        H, W = H0 + ph, W0 + pw
         time = time.to(torch.int64).contiguous()
         taps = {}
 
@@ -291,6 +309,8 @@ class Unet(UnetParams):
         _lib.check(lib.fd_final_conv(_lib.ptr(h), _lib.ptr(fc.weight), _lib.ptr(fc.bias), _lib.ptr(out), B, H * W, self.dim,
                                      self.out_dim, st))
         self._stats = None
+        if ph or pw:
+            out = out[:, :, pad[2]:pad[2] + H0, pad[0]:pad[0] + W0].contiguous()
         if return_taps:
             return out, {k: (v if v.dim() == 2 else v.permute(0, 3, 1, 2).float()) for k, v in taps.items()}
         return out

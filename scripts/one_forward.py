@@ -1,0 +1,22 @@
+"""One UNet forward (batch 8, 436x1024) after a warm-up forward: the command profiled by ncu for profiles/."""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from opticalflowdiffusion_b200 import FlowDiffuser  # noqa: E402
+from opticalflowdiffusion_b200.config import compose  # noqa: E402
+from opticalflowdiffusion_b200.datasets import synthetic_frames  # noqa: E402
+
+B = int(os.environ.get("BATCH", 8))
+H, W = int(os.environ.get("HEIGHT", 436)), int(os.environ.get("WIDTH", 1024))
+torch.manual_seed(0)
+algo = FlowDiffuser(compose(["algorithm.target=flow", "algorithm.sampling_timesteps=50"]).algorithm).cuda()
+cond = (2 * synthetic_frames(B, H, W, 0) - 1).cuda()
+x = torch.randn(B, 2, H, W, device="cuda")
+t = torch.full((B,), 999, device="cuda", dtype=torch.long)
+for i in range(int(os.environ.get("FORWARDS", 2))):
+    out = algo.unet(x, cond, t)
+torch.cuda.synchronize()
+print("ok", float(out.abs().mean()))
