@@ -32,8 +32,10 @@ namespace {
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;
 constexpr int kATileBytes = kBlockM * kBlockK * 2;  // 16 KiB
-constexpr int kThreads = 192;
-constexpr int kEpiThreads = 128;
+constexpr int kEpiWarps = 8;
+constexpr int kEpiThreads = kEpiWarps * 32;
+constexpr int kThreads = 64 + kEpiThreads;          // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+constexpr int kSlabBytes = kBlockM * 128;           // 128 rows x 64 bf16: one TMA-store slab
 
 struct ConvParams {
   int N, H, W;        // images, output rows, output columns (after flattening / merging)
@@ -45,10 +47,8 @@ struct ConvParams {
   int chunks0, chunks1;  // 64-channel chunks of src0 / src1
   int R, Wt;          // tile = R rows x Wt columns, R*Wt == 128
   int tiles_w, tiles_h, n_tiles, total_tiles;
-  int cpg;            // channels per GroupNorm group (Cout/8)
   const float* bias;
   const __nv_bfloat16* residual;
-  __nv_bfloat16* out;
   double* gn_stats;   // [N][8][2] or null
 };
 
@@ -56,33 +56,42 @@ template <int BLOCK_N>
 struct Cfg {
   static constexpr int kBTileBytes = BLOCK_N * kBlockK * 2;
   static constexpr int kStageBytes = kATileBytes + kBTileBytes;
-  static constexpr int kStages = BLOCK_N == 64 ? 8 : (BLOCK_N == 128 ? 6 : 4);
+  static constexpr int kStages = BLOCK_N == 64 ? 7 : (BLOCK_N == 128 ? 5 : 4);
+  static constexpr int kStoreBufs = BLOCK_N == 256 ? 1 : 2;      // output staging slabs (ping-pong when they fit)
   static constexpr int kTmemCols = 2 * BLOCK_N;
-  // ring + barriers + bias (2 x BLOCK_N floats) + stats (2 stages x 4 warps x 16 floats) + tmem ptr, plus 1 KiB slack
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256 + 2 * BLOCK_N * 4 + 2 * 4 * 16 * 4 + 64;
+  static constexpr int kTailBytes = 256 /*barriers*/ + 2 * BLOCK_N * 4 /*bias*/ + kEpiWarps * 16 * 4 /*stats*/ + 64;
+  static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + kStoreBufs * kSlabBytes + kTailBytes;
 };
 
-template <int BLOCK_N>
+// GPT = GroupNorm groups covered by one N-tile (8 when Cout == BLOCK_N, 4 when Cout == 2*BLOCK_N, 0 = no statistics)
+template <int BLOCK_N, int GPT>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
-                  const __grid_constant__ CUtensorMap map_b, const ConvParams p) {
+                  const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_out,
+                  const ConvParams p) {
   using C = Cfg<BLOCK_N>;
   constexpr int STAGES = C::kStages;
+  constexpr int NBUF = C::kStoreBufs;
+  constexpr int NCHUNK = BLOCK_N / 32;                 // 32-column accumulator chunks per tile
+  constexpr int CPW = NCHUNK / 2;                      // chunks per epilogue warp (warps split even / odd chunks)
+  constexpr int CPGT = GPT > 0 ? BLOCK_N / GPT : 32;   // columns per group inside the tile
+  constexpr int GIC = CPGT < 32 ? 32 / CPGT : 1;       // groups inside one 32-column chunk
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // SWIZZLE_128B tiles need 1024-byte alignment
   uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
   const uint32_t a_smem = base;
   const uint32_t b_smem = base + STAGES * kATileBytes;
-  const uint32_t bar_base = base + STAGES * C::kStageBytes;
+  const uint32_t o_smem = base + STAGES * C::kStageBytes;
+  const uint32_t bar_base = o_smem + NBUF * kSlabBytes;
   // barriers: full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2]
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
   auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
   auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 2 + s); };
-  uint8_t* gtail = gbase + STAGES * C::kStageBytes + 256;
+  uint8_t* gtail = gbase + STAGES * C::kStageBytes + NBUF * kSlabBytes + 256;
   float* s_bias = reinterpret_cast<float*>(gtail);                       // [2][BLOCK_N]
-  float* s_stats = reinterpret_cast<float*>(gtail + 2 * BLOCK_N * 4);    // [2][4 warps][16]
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(gtail + 2 * BLOCK_N * 4 + 2 * 4 * 16 * 4);
+  float* s_stats = reinterpret_cast<float*>(gtail + 2 * BLOCK_N * 4);    // [8 warps][16]
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(gtail + 2 * BLOCK_N * 4 + kEpiWarps * 16 * 4);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -94,6 +103,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
     tma_prefetch_desc(&map_a0);
     tma_prefetch_desc(&map_a1);
     tma_prefetch_desc(&map_b);
+    tma_prefetch_desc(&map_out);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
@@ -122,9 +132,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
         const int rem = m_tile - img * tiles_per_img;
         const int h0 = (rem / p.tiles_w) * p.R;
         const int w0 = (rem % p.tiles_w) * p.Wt;
+        int tap = 0, chunk = 0;
         for (int kb = 0; kb < num_kb; ++kb) {
-          const int tap = kb / cpt;
-          const int chunk = kb - tap * cpt;
           mbar_wait(empty_bar(stage), phase ^ 1u);
           mbar_expect_tx(full_bar(stage), C::kStageBytes);
           const CUtensorMap* ma = chunk < p.chunks0 ? &map_a0 : &map_a1;
@@ -138,6 +147,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
           }
           tma_load_2d(b_smem + stage * C::kBTileBytes, &map_b, full_bar(stage), kb * kBlockK, n_tile * BLOCK_N);
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+          if (++chunk == cpt) { chunk = 0; ++tap; }
         }
       }
     }
@@ -172,11 +182,55 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
       }
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
-    const int et = threadIdx.x - 64;          // 0..127
-    const int quarter = warp & 3;             // TMEM lane quarter this warp may access
+    // ===================== epilogue (warps 2..9) =====================
+    // TMEM lane quarter q = warp % 4 (hardware rule); the two warps of a quarter split the 32-column chunks
+    // (even / odd).  Output goes registers -> swizzled smem slab (64 channels) -> one TMA store per slab, which
+    // also clips rows / columns outside the image.  GroupNorm partial sums stay in registers across the tiles
+    // of one (image, N-tile) and are flushed once.
+    const int ew = warp - 2;                  // 0..7
+    const int et = threadIdx.x - 64;          // 0..255
+    const int quarter = warp & 3;
+    const int half = ew >> 2;                 // which chunk parity this warp owns
     const int row = quarter * 32 + lane;      // accumulator row = pixel within the tile
     const int rr = row / p.Wt, ww = row - rr * p.Wt;
+    const bool issuer = (et == 0);
+    float st_s[CPW > 0 ? CPW : 1][GIC], st_q[CPW > 0 ? CPW : 1][GIC];
+#pragma unroll
+    for (int a = 0; a < (CPW > 0 ? CPW : 1); ++a)
+#pragma unroll
+      for (int b = 0; b < GIC; ++b) st_s[a][b] = st_q[a][b] = 0.f;
+    int st_img = -1, st_ntile = 0;
+    uint32_t slab_count = 0;
+
+    auto flush_stats = [&]() {
+      // all epilogue warps call this at the same tile boundary
+      if (GPT == 0 || st_img < 0) return;
+      float* mine = s_stats + ew * 16;
+      if (lane < 16) mine[lane] = 0.f;
+      __syncwarp();
+#pragma unroll
+      for (int a = 0; a < (CPW > 0 ? CPW : 1); ++a)
+#pragma unroll
+        for (int b = 0; b < GIC; ++b) {
+          const float s = fd_warp_sum(st_s[a][b]), q = fd_warp_sum(st_q[a][b]);
+          if (lane == 0) {
+            const int col = (2 * a + half) * 32 + b * CPGT;      // first column of this partial inside the tile
+            const int grp = col / CPGT;
+            mine[grp * 2] += s;
+            mine[grp * 2 + 1] += q;
+          }
+          st_s[a][b] = st_q[a][b] = 0.f;
+        }
+      named_bar_sync(2, kEpiThreads);
+      if (et < 2 * GPT) {
+        float sv = 0.f;
+#pragma unroll
+        for (int w8 = 0; w8 < kEpiWarps; ++w8) sv += s_stats[w8 * 16 + et];     // fixed order
+        atomicAdd(p.gn_stats + (long)st_img * 16 + st_ntile * 2 * GPT + et, (double)sv);
+      }
+      named_bar_sync(2, kEpiThreads);
+    };
+
     int iter = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++iter) {
       const int as = iter & 1;
@@ -185,30 +239,43 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
       const int m_tile = tile / p.n_tiles;
       const int img = m_tile / tiles_per_img;
       const int rem = m_tile - img * tiles_per_img;
-      const int h = (rem / p.tiles_w) * p.R + rr;
-      const int w = (rem % p.tiles_w) * p.Wt + ww;
+      const int h0 = (rem / p.tiles_w) * p.R, w0 = (rem % p.tiles_w) * p.Wt;
+      const int h = h0 + rr, w = w0 + ww;
       const bool valid = (h < p.H) && (w < p.W);
       const int n0 = n_tile * BLOCK_N;
+      if (GPT > 0 && (img != st_img || n_tile != st_ntile)) {
+        flush_stats();
+        st_img = img;
+        st_ntile = n_tile;
+      }
       float* bias_s = s_bias + as * BLOCK_N;
-      float* stats_s = s_stats + as * 64;            // [4 warps][16]: one private row per epilogue warp
-      float* stats_w = stats_s + (warp - 2) * 16;
       for (int i = et; i < BLOCK_N; i += kEpiThreads) bias_s[i] = p.bias ? __ldg(p.bias + n0 + i) : 0.f;
-      if (et < 64) stats_s[et] = 0.f;
-      named_bar_sync(1, kEpiThreads);
+      // (the slab barrier below also publishes the bias)
 
       mbar_wait(tfull_bar(as), aphase);
       tc_fence_after();
       const long pix = ((long)img * p.H + h) * p.W + w;
-      __nv_bfloat16* orow = p.out + pix * p.Cout + n0;
       const __nv_bfloat16* rrow = p.residual ? p.residual + pix * p.Cout + n0 : nullptr;
-#pragma unroll 1
-      for (int c = 0; c < BLOCK_N; c += 32) {
+#pragma unroll
+      for (int slab = 0; slab < (BLOCK_N + 63) / 64; ++slab) {
+        const uint32_t buf = o_smem + (slab_count % NBUF) * kSlabBytes;
+        ++slab_count;
+        if (issuer) tma_store_wait_read<NBUF - 1>();      // the store that last used this buffer has read it
+        named_bar_sync(1, kEpiThreads);
+        const int ci = slab * 2 + half;                   // this warp's chunk inside the slab
+        const int c = ci * 32;
         uint32_t acc[32];
         tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BLOCK_N + c), acc);
         tmem_ld_wait();
         float v[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]) + bias_s[c + j];
+        for (int j4 = 0; j4 < 8; ++j4) {
+          const float4 b4 = *reinterpret_cast<const float4*>(bias_s + c + j4 * 4);
+          v[j4 * 4 + 0] = __uint_as_float(acc[j4 * 4 + 0]) + b4.x;
+          v[j4 * 4 + 1] = __uint_as_float(acc[j4 * 4 + 1]) + b4.y;
+          v[j4 * 4 + 2] = __uint_as_float(acc[j4 * 4 + 2]) + b4.z;
+          v[j4 * 4 + 3] = __uint_as_float(acc[j4 * 4 + 3]) + b4.w;
+        }
         if (rrow != nullptr && valid) {
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
@@ -222,48 +289,49 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
             }
           }
         }
-        if (p.gn_stats != nullptr) {
-          // channels [n0+c, n0+c+32) belong to 32/cpg groups (cpg < 32) or to a part of one group
-          const int span = p.cpg < 32 ? p.cpg : 32;
-#pragma unroll 1
-          for (int g0 = 0; g0 < 32; g0 += span) {
-            float s = 0.f, ss = 0.f;
-            if (valid) {
+        if (GPT > 0 && valid) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (j >= g0 && j < g0 + span) { s += v[j]; ss += v[j] * v[j]; }
+          for (int b = 0; b < GIC; ++b) {
+            constexpr int span = CPGT < 32 ? CPGT : 32;
+            float s = 0.f, q = 0.f;
+#pragma unroll
+            for (int j = 0; j < span; ++j) {
+              const float x = v[b * span + j];
+              s += x;
+              q = fmaf(x, x, q);
             }
-            s = fd_warp_sum(s);
-            ss = fd_warp_sum(ss);
-            if (lane == 0) {        // only this warp touches its row: fixed summation order
-              const int grp = (n0 + c + g0) / p.cpg;
-              stats_w[grp * 2] += s;
-              stats_w[grp * 2 + 1] += ss;
-            }
+            st_s[slab][b] += s;
+            st_q[slab][b] += q;
           }
         }
-        if (valid) {
+        // 64-byte piece of this row inside the 128-byte slab row, 16-byte granules XOR-swizzled by (row & 7)
+        const uint32_t rbase = buf + (uint32_t)row * 128u;
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            uint4 o;
-            o.x = fd_pack_bf16(v[q * 8 + 0], v[q * 8 + 1]);
-            o.y = fd_pack_bf16(v[q * 8 + 2], v[q * 8 + 3]);
-            o.z = fd_pack_bf16(v[q * 8 + 4], v[q * 8 + 5]);
-            o.w = fd_pack_bf16(v[q * 8 + 6], v[q * 8 + 7]);
-            reinterpret_cast<uint4*>(orow + c)[q] = o;
-          }
+        for (int q = 0; q < 4; ++q) {
+          const uint32_t piece = (uint32_t)(half * 4 + q) ^ (uint32_t)(row & 7);
+          const uint32_t o0 = fd_pack_bf16(v[q * 8 + 0], v[q * 8 + 1]), o1 = fd_pack_bf16(v[q * 8 + 2], v[q * 8 + 3]);
+          const uint32_t o2 = fd_pack_bf16(v[q * 8 + 4], v[q * 8 + 5]), o3 = fd_pack_bf16(v[q * 8 + 6], v[q * 8 + 7]);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rbase + piece * 16u), "r"(o0), "r"(o1), "r"(o2),
+                       "r"(o3)
+                       : "memory");
         }
-      }
-      tc_fence_before();
-      mbar_arrive(tempty_bar(as));             // accumulator stage may be overwritten
-      if (p.gn_stats != nullptr) {
-        named_bar_sync(2, kEpiThreads);
-        if (et < 16) {
-          const float sv = (stats_s[et] + stats_s[16 + et]) + (stats_s[32 + et] + stats_s[48 + et]);
-          if (sv != 0.f) atomicAdd(p.gn_stats + (long)img * 16 + et, (double)sv);
+        fence_proxy_async_smem();
+        if (slab == (BLOCK_N + 63) / 64 - 1) {
+          tc_fence_before();
+          mbar_arrive(tempty_bar(as));          // all TMEM reads of this tile are done
+        }
+        named_bar_sync(1, kEpiThreads);
+        if (issuer) {
+          if (p.mode == 0)
+            tma_store_5d(&map_out, buf, n0 + slab * 64, w0, h0, img, 0);
+          else
+            tma_store_5d(&map_out, buf, n0 + slab * 64, w0, h0, 0, 0);
+          tma_store_commit();
         }
       }
     }
+    flush_stats();
+    if (issuer) tma_store_wait_all();
   }
 
   tc_fence_before();
@@ -293,17 +361,18 @@ TileShape pick_tile(int H, int W) {
   return best;
 }
 
-template <int BLOCK_N>
-int launch(const CUtensorMap& ma0, const CUtensorMap& ma1, const CUtensorMap& mb, const ConvParams& p, int sms,
-           cudaStream_t st) {
+template <int BLOCK_N, int GPT>
+int launch(const CUtensorMap& ma0, const CUtensorMap& ma1, const CUtensorMap& mb, const CUtensorMap& mo,
+           const ConvParams& p, int sms, cudaStream_t st) {
   using C = Cfg<BLOCK_N>;
   static bool attr_set = false;
   if (!attr_set) {
-    FD_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
+    FD_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BLOCK_N, GPT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 C::kSmemBytes));
     attr_set = true;
   }
   const int grid = p.total_tiles < sms ? p.total_tiles : sms;
-  conv_igemm_kernel<BLOCK_N><<<grid, kThreads, C::kSmemBytes, st>>>(ma0, ma1, mb, p);
+  conv_igemm_kernel<BLOCK_N, GPT><<<grid, kThreads, C::kSmemBytes, st>>>(ma0, ma1, mb, mo, p);
   FD_LAUNCH_CHECK();
   return FD_OK;
 }
@@ -336,10 +405,8 @@ int fd_conv_igemm(const void* src0, int C0, const void* src1, int C1, const void
   p.chunks1 = C1 / 64;
   p.bias = bias;
   p.residual = static_cast<const __nv_bfloat16*>(residual);
-  p.out = static_cast<__nv_bfloat16*>(out);
   p.gn_stats = gn_stats;
-  p.cpg = Cout / 8;
-  CUtensorMap ma0, ma1, mb;
+  CUtensorMap ma0, ma1, mb, mo;
   TileShape ts;
   if (mode == 0) {
     int n = N, h = H, w = W;
@@ -397,10 +464,23 @@ int fd_conv_igemm(const void* src0, int C0, const void* src1, int C1, const void
     const uint32_t box[2] = {64, (uint32_t)block_n};
     if (int e = make_tmap_bf16(&mb, wpacked, 2, dims, str, box)) return e;
   }
+  {
+    // output (N, H, W, Cout) in the same (possibly flattened / merged) geometry: box = one 64-channel slab of a tile
+    const uint64_t dims[5] = {(uint64_t)Cout, (uint64_t)p.W, (uint64_t)p.H, (uint64_t)p.N, 1};
+    const uint64_t str[4] = {(uint64_t)Cout * 2, (uint64_t)p.W * Cout * 2, (uint64_t)p.H * p.W * Cout * 2,
+                             (uint64_t)p.N * p.H * p.W * Cout * 2};
+    const uint32_t box[5] = {64, (uint32_t)ts.Wt, (uint32_t)ts.R, 1, 1};
+    if (int e = make_tmap_bf16(&mo, out, 5, dims, str, box)) return e;
+  }
   cudaStream_t st = (cudaStream_t)stream;
-  if (block_n == 256) return launch<256>(ma0, ma1, mb, p, sms, st);
-  if (block_n == 128) return launch<128>(ma0, ma1, mb, p, sms, st);
-  return launch<64>(ma0, ma1, mb, p, sms, st);
+  const bool stats = gn_stats != nullptr;
+  if (stats) FD_REQUIRE(p.n_tiles == 1 || p.n_tiles == 2, "conv_igemm: statistics need Cout in {64,128,256,512}");
+  if (block_n == 256) {
+    if (!stats) return launch<256, 0>(ma0, ma1, mb, mo, p, sms, st);
+    return p.n_tiles == 1 ? launch<256, 8>(ma0, ma1, mb, mo, p, sms, st) : launch<256, 4>(ma0, ma1, mb, mo, p, sms, st);
+  }
+  if (block_n == 128) return stats ? launch<128, 8>(ma0, ma1, mb, mo, p, sms, st) : launch<128, 0>(ma0, ma1, mb, mo, p, sms, st);
+  return stats ? launch<64, 8>(ma0, ma1, mb, mo, p, sms, st) : launch<64, 0>(ma0, ma1, mb, mo, p, sms, st);
 }
 
 }  // extern "C"

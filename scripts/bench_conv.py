@@ -27,7 +27,11 @@ def main():
     lib = _lib.load(check_device=True)
     N = int(os.environ.get("BATCH", 8))
     res = {}
+    only = os.environ.get("ONLY")
+    iters = int(os.environ.get("ITERS", 10))
     for name, c0, c1, cout, H, W, k in SHAPES:
+        if only and only not in name:
+            continue
         x0 = torch.randn(N, H, W, c0, device="cuda").to(torch.bfloat16)
         x1 = torch.randn(N, H, W, c1, device="cuda").to(torch.bfloat16) if c1 else None
         wp = (torch.randn(cout, k * k * (c0 + c1), device="cuda") * 0.02).to(torch.bfloat16)
@@ -43,7 +47,6 @@ def main():
             fn()
         torch.cuda.synchronize()
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        iters = 10
         s.record()
         for _ in range(iters):
             fn()
