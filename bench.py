@@ -126,6 +126,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     from opticalflowdiffusion_b200 import FlowDiffuser, _lib
     from opticalflowdiffusion_b200.config import compose
     from opticalflowdiffusion_b200.datasets import synthetic_frames
+    from opticalflowdiffusion_b200.parallel import max_over_ranks
 
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
@@ -170,10 +171,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             fn()
         e.record()
         sync()
-        t = torch.tensor([s.elapsed_time(e) * 1e-3], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t)
+        return max_over_ranks(s.elapsed_time(e) * 1e-3, device=dev)
 
     for _ in range(max(args.warmup, 3) if args.warmup >= 0 else 3):
         step_resident()

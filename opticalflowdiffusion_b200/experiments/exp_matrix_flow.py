@@ -15,6 +15,7 @@ import torch.distributed as dist
 
 from ..datasets import SyntheticSintelDataset
 from ..flow_diffuser import FlowDiffuser
+from ..parallel import reduce_metrics
 
 
 class MatrixFlowExperiment:
@@ -78,9 +79,4 @@ class MatrixFlowExperiment:
                 break
             self.algo.validation_step(tuple(t.to(dev) for t in batch), i)
             out = {k: float(v) for k, v in self.algo.logged.items()} if hasattr(self.algo, "logged") else {}
-        if self.world > 1 and dist.is_initialized() and out:     # sync_dist=True semantics for the scalars
-            keys = sorted(out)
-            t = torch.tensor([out[k] for k in keys], device=dev, dtype=torch.float64)
-            dist.all_reduce(t)
-            out = {k: float(v) / self.world for k, v in zip(keys, t)}
-        return out
+        return reduce_metrics(out, device=dev)     # sync_dist=True semantics for the scalars
