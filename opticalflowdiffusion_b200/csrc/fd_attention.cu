@@ -20,103 +20,170 @@ constexpr int kHidden = kHeads * kD;   // 128
 constexpr int kQkv = 3 * kHidden;      // 384
 
 // ------------------------------------------------------------------------------------------------
-// linear attention, pass 1
+// warp-level tensor-core helpers (bf16 mma.sync m16n8k16, fp32 accumulate)
 // ------------------------------------------------------------------------------------------------
-constexpr int kLaTile = 32;                       // pixels per shared-memory tile
-constexpr int kLaPartial = 2 * kHidden + kHeads * kD * kD;   // m[128], s[128], ctx[4][32][32]
+__device__ __forceinline__ void mma_bf16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], uint32_t saddr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(saddr));
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], uint32_t saddr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(saddr));
+}
+__device__ __forceinline__ void cp_async16(uint32_t saddr, const void* g, bool valid) {
+  const int sz = valid ? 16 : 0;      // src-size 0 -> the 16 bytes are zero-filled
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(saddr), "l"(g), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// ------------------------------------------------------------------------------------------------
+// linear attention, pass 1: per pixel-chunk partial (running max m, sum of exp s, 32x32 context per head)
+//   ctx[d,e] = sum_n exp(k[d,n] - m[d]) v[e,n]  as a tensor-core GEMM with K = pixels:
+//   A[d][n] = exp(k) and B[n][e] = v both live in smem as [pixel][channel] rows -> ldmatrix.trans.
+//   8 warps = 4 heads x 2 halves of d; cp.async double-buffered 64-pixel tiles.
+// ------------------------------------------------------------------------------------------------
+constexpr int kLaTile = 64;                                   // pixels per smem tile
+constexpr int kLaRowBytes = 2 * kHidden * 2 + 16;             // k|v bf16 row + 16 B pad (conflict-free ldmatrix)
+constexpr int kLaTileBytes = kLaTile * kLaRowBytes;
+constexpr int kLaSmemBytes = 2 * kLaTileBytes;
+constexpr int kLaPartial = 2 * kHidden + kHeads * kD * kD;    // m[128], s[128], ctx[4][32][32]
 
 __global__ void __launch_bounds__(256) linattn_partial_kernel(const __nv_bfloat16* __restrict__ qkv,
                                                               float* __restrict__ partial, int HW, int chunk_px) {
-  __shared__ float s_k[kLaTile][kHidden];   // raw k, then exp(k - m)
-  __shared__ float s_v[kLaTile][kHidden];
+  extern __shared__ __align__(16) uint8_t la_smem[];
+  __shared__ float s_pmax[2][kHidden];
   __shared__ float s_fac[kHidden];
-  const int n = blockIdx.y;
-  const int chunk = blockIdx.x;
+  __shared__ float s_sum1[kHidden];
+  const int n = blockIdx.y, chunk = blockIdx.x;
   const int p_begin = chunk * chunk_px;
   const int p_end = min(HW, p_begin + chunk_px);
-  const int t = threadIdx.x;
-  const int head = t >> 6, d = (t & 63) >> 1, eh = t & 1;
-  float acc[16];
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const int g = lane >> 2, tq = lane & 3;
+  const int head = warp & 3, mhalf = warp >> 2;
+  const int ch = t & 127, phalf = t >> 7;          // exp pass: channel, pixel half
+  const __nv_bfloat16* base = qkv + (long)n * HW * kQkv + kHidden;   // k|v start at channel 128
+  const uint32_t smem0 = smem_addr(la_smem);
+  float acc[4][4];
 #pragma unroll
-  for (int e = 0; e < 16; ++e) acc[e] = 0.f;
-  float m_run = -INFINITY, s_run = 0.f;   // threads < 128: channel t
-  const __nv_bfloat16* base = qkv + (long)n * HW * kQkv;
-  for (int p0 = p_begin; p0 < p_end; p0 += kLaTile) {
-    // load k|v of kLaTile pixels: 512 B per pixel = 32 x 16 B
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  float m_run = -INFINITY, s_run = 0.f;
+
+  auto issue_tile = [&](int p0, int buf) {
+    // 64 pixels x 32 granules of 16 B (k|v = 512 B per pixel): 8 cp.async per thread
 #pragma unroll
     for (int it = 0; it < (kLaTile * 32) / 256; ++it) {
       const int idx = it * 256 + t;
       const int px = idx >> 5, q16 = idx & 31;
       const int p = p0 + px;
-      float vals[8];
-      if (p < p_end) {
-        const uint4 raw = __ldg(reinterpret_cast<const uint4*>(base + (long)p * kQkv + kHidden) + q16);
-        const uint32_t rw[4] = {raw.x, raw.y, raw.z, raw.w};
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float2 f = fd_unpack_bf16(rw[e]);
-          vals[2 * e] = f.x;
-          vals[2 * e + 1] = f.y;
-        }
-      } else {
-        const float fill = q16 < 16 ? -INFINITY : 0.f;
-#pragma unroll
-        for (int e = 0; e < 8; ++e) vals[e] = fill;
-      }
-      float* dst = q16 < 16 ? &s_k[px][q16 * 8] : &s_v[px][(q16 - 16) * 8];
-      *reinterpret_cast<float4*>(dst) = make_float4(vals[0], vals[1], vals[2], vals[3]);
-      *reinterpret_cast<float4*>(dst + 4) = make_float4(vals[4], vals[5], vals[6], vals[7]);
+      const bool ok = p < p_end;
+      cp_async16(smem0 + buf * kLaTileBytes + px * kLaRowBytes + q16 * 16, base + (long)(ok ? p : p_begin) * kQkv + q16 * 8, ok);
+    }
+    cp_async_commit();
+  };
+
+  const int ntiles = (p_end - p_begin + kLaTile - 1) / kLaTile;
+  if (ntiles > 0) issue_tile(p_begin, 0);
+  for (int ti = 0; ti < ntiles; ++ti) {
+    const int buf = ti & 1;
+    const int p0 = p_begin + ti * kLaTile;
+    if (ti + 1 < ntiles) {
+      issue_tile(p0 + kLaTile, buf ^ 1);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
     }
     __syncthreads();
-    if (t < kHidden) {
-      float tmax = -INFINITY;
+    uint8_t* tile = la_smem + buf * kLaTileBytes;
+    // ---- per-channel max over this thread's 32 pixels
+    const int px_lo = phalf * 32;
+    float tmax = -INFINITY;
 #pragma unroll 8
-      for (int px = 0; px < kLaTile; ++px) tmax = fmaxf(tmax, s_k[px][t]);
-      const float m_new = fmaxf(m_run, tmax);
-      const float fac = (m_run == -INFINITY) ? 0.f : __expf(m_run - m_new);
-      float sum = 0.f;
+    for (int i = 0; i < 32; ++i) {
+      const int px = px_lo + i;
+      if (p0 + px < p_end)
+        tmax = fmaxf(tmax, __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(tile + px * kLaRowBytes + ch * 2)));
+    }
+    s_pmax[phalf][ch] = tmax;
+    __syncthreads();
+    const float m_new = fmaxf(m_run, fmaxf(s_pmax[0][ch], s_pmax[1][ch]));
+    const float fac = (m_run == -INFINITY) ? 0.f : __expf(m_run - m_new);
+    float sum = 0.f;
 #pragma unroll 8
-      for (int px = 0; px < kLaTile; ++px) {
-        const float e = __expf(s_k[px][t] - m_new);
-        s_k[px][t] = e;
-        sum += e;
-      }
-      s_run = s_run * fac + sum;
-      m_run = m_new;
-      s_fac[t] = fac;
+    for (int i = 0; i < 32; ++i) {
+      const int px = px_lo + i;
+      __nv_bfloat16* kp = reinterpret_cast<__nv_bfloat16*>(tile + px * kLaRowBytes + ch * 2);
+      float e = 0.f;
+      if (p0 + px < p_end) e = __expf(__bfloat162float(*kp) - m_new);
+      const __nv_bfloat16 eb = __float2bfloat16(e);
+      *kp = eb;
+      sum += __bfloat162float(eb);          // the normaliser sums exactly what the GEMM consumes
     }
+    s_run = s_run * fac + sum;
+    m_run = m_new;
+    if (phalf == 0) s_fac[ch] = fac;
     __syncthreads();
-    const float fac = s_fac[head * kD + d];
+    // ---- rescale + tensor-core accumulate: warp = (head, 16 rows of d), N = 32 e, K = 64 pixels
+    {
+      const float f0 = s_fac[head * kD + mhalf * 16 + g], f1 = s_fac[head * kD + mhalf * 16 + g + 8];
 #pragma unroll
-    for (int e = 0; e < 16; ++e) acc[e] *= fac;
-#pragma unroll 4
-    for (int px = 0; px < kLaTile; ++px) {
-      const float ke = s_k[px][head * kD + d];
-      const float4* vr = reinterpret_cast<const float4*>(&s_v[px][head * kD + eh * 16]);
+      for (int nt = 0; nt < 4; ++nt) {
+        acc[nt][0] *= f0; acc[nt][1] *= f0; acc[nt][2] *= f1; acc[nt][3] *= f1;
+      }
+      const uint32_t tb = smem0 + buf * kLaTileBytes;
+      const int mi = lane >> 3, r = lane & 7;       // ldmatrix: lanes 8*mi..8*mi+7 address matrix mi, row r
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const float4 vv = vr[q];
-        acc[q * 4 + 0] += ke * vv.x;
-        acc[q * 4 + 1] += ke * vv.y;
-        acc[q * 4 + 2] += ke * vv.z;
-        acc[q * 4 + 3] += ke * vv.w;
+      for (int ks = 0; ks < kLaTile / 16; ++ks) {
+        uint32_t a[4], b01[4], b23[4];
+        // A (trans): m0 (px 0-7, d 0-7), m1 (px 0-7, d 8-15), m2 (px 8-15, d 0-7), m3 (px 8-15, d 8-15)
+        ldmatrix_x4_trans(a, tb + (ks * 16 + (mi >> 1) * 8 + r) * kLaRowBytes + (head * kD + mhalf * 16 + (mi & 1) * 8) * 2);
+        // B (trans): m0 (px 0-7, e 0-7) m1 (px 8-15, e 0-7) m2 (px 0-7, e 8-15) m3 (px 8-15, e 8-15)
+        const uint32_t vb = tb + (ks * 16 + (mi & 1) * 8 + r) * kLaRowBytes + (kHidden + head * kD + (mi >> 1) * 8) * 2;
+        ldmatrix_x4_trans(b01, vb);
+        ldmatrix_x4_trans(b23, vb + 16 * 2);
+        mma_bf16(acc[0], a, b01[0], b01[1]);
+        mma_bf16(acc[1], a, b01[2], b01[3]);
+        mma_bf16(acc[2], a, b23[0], b23[1]);
+        mma_bf16(acc[3], a, b23[2], b23[3]);
       }
     }
-    __syncthreads();
+    __syncthreads();     // tile buffer may be refilled two iterations later; s_pmax / s_fac reused next iteration
   }
   float* out = partial + ((long)n * gridDim.x + chunk) * kLaPartial;
-  if (t < kHidden) {
-    out[t] = m_run;
-    out[kHidden + t] = s_run;
+  if (phalf == 1) s_sum1[ch] = s_run;
+  __syncthreads();
+  if (phalf == 0) {
+    out[ch] = m_run;
+    out[kHidden + ch] = s_run + s_sum1[ch];
   }
-  float* c = out + 2 * kHidden + (head * kD + d) * kD + eh * 16;
+  float* c = out + 2 * kHidden + (head * kD + mhalf * 16) * kD;
 #pragma unroll
-  for (int e = 0; e < 16; ++e) c[e] = acc[e];
+  for (int nt = 0; nt < 4; ++nt) {
+    c[g * kD + nt * 8 + 2 * tq] = acc[nt][0];
+    c[g * kD + nt * 8 + 2 * tq + 1] = acc[nt][1];
+    c[(g + 8) * kD + nt * 8 + 2 * tq] = acc[nt][2];
+    c[(g + 8) * kD + nt * 8 + 2 * tq + 1] = acc[nt][3];
+  }
 }
 
-// pass 2: one block per (n, head), thread = (d, e)
-__global__ void __launch_bounds__(1024) linattn_combine_kernel(const float* __restrict__ partial, float* __restrict__ ctx,
-                                                               int nchunks, float inv_hw) {
+// pass 2: one block per (n, head), thread = (d, e); emits ctx^T in bf16 ([e][d]) for the apply GEMM
+__global__ void __launch_bounds__(1024) linattn_combine_kernel(const float* __restrict__ partial,
+                                                               __nv_bfloat16* __restrict__ ctx_t, int nchunks,
+                                                               float inv_hw) {
   const int n = blockIdx.x / kHeads, head = blockIdx.x % kHeads;
   const int d = threadIdx.x >> 5, e = threadIdx.x & 31;
   const float* base = partial + (long)n * nchunks * kLaPartial;
@@ -130,78 +197,124 @@ __global__ void __launch_bounds__(1024) linattn_combine_kernel(const float* __re
     S += pc[kHidden + head * kD + d] * f;
     acc += pc[2 * kHidden + (head * kD + d) * kD + e] * f;
   }
-  ctx[((long)n * kHeads + head) * kD * kD + d * kD + e] = acc / S * inv_hw;
+  // 32^-0.5 (the q scale, :238) is folded in here so the apply pass only normalises its softmax
+  ctx_t[((long)n * kHeads + head) * kD * kD + e * kD + d] = __float2bfloat16(acc / S * inv_hw * 0.17677669529663687f);
 }
 
-// pass 3: warp = (32 pixels, one head); ctx of the sample in shared memory
-__global__ void __launch_bounds__(256) linattn_apply_kernel(const __nv_bfloat16* __restrict__ qkv,
-                                                            const float* __restrict__ ctx,
-                                                            __nv_bfloat16* __restrict__ out, int HW, float scale) {
-  __shared__ __align__(16) float s_ctx[kHeads * kD * kD];
+// pass 3: out[n, e] = sum_d softmax_d(q[n, :])[d] ctx[d, e] on tensor cores.
+//   block = 4 warps, tile = 64 pixels; warp = 16 pixels x 4 heads; q tile staged by cp.async, A fragments by
+//   ldmatrix, softmax in registers (4 lanes share a row), result staged in the warp's own smem rows and
+//   written back as 16-byte coalesced stores.
+constexpr int kApRowBytes = kHidden * 2 + 16;
+constexpr int kCtStride = kD + 8;                   // bf16 per ctx^T row (conflict-free 32-bit fragment loads)
+
+__global__ void __launch_bounds__(128) linattn_apply_kernel(const __nv_bfloat16* __restrict__ qkv,
+                                                            const __nv_bfloat16* __restrict__ ctx_t,
+                                                            __nv_bfloat16* __restrict__ out, int HW) {
+  __shared__ __align__(16) uint8_t s_q[64 * kApRowBytes];
+  __shared__ __align__(16) __nv_bfloat16 s_ct[kHeads * kD * kCtStride];
   const int n = blockIdx.y;
-  for (int i = threadIdx.x; i < kHeads * kD * kD; i += blockDim.x) s_ctx[i] = ctx[(long)n * kHeads * kD * kD + i];
-  __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int head = warp & 3, grp = warp >> 2;
-  const float* cx = s_ctx + head * kD * kD;
-  for (int p0 = (blockIdx.x * 2 + grp) * 32; p0 < HW; p0 += gridDim.x * 64) {
-    const int p = p0 + lane;
-    if (p >= HW) continue;
-    const uint4* src = reinterpret_cast<const uint4*>(qkv + ((long)n * HW + p) * kQkv + head * kD);
-    float q[kD];
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const int g = lane >> 2, tq = lane & 3;
+  for (int i = t; i < kHeads * kD * kD; i += 128) {
+    const int hd = i / kD, d = i % kD;               // hd = head*32 + e
+    s_ct[hd * kCtStride + d] = ctx_t[(long)n * kHeads * kD * kD + i];
+  }
+  const __nv_bfloat16* base = qkv + (long)n * HW * kQkv;
+  const uint32_t sq = smem_addr(s_q);
+  const int ntiles = (HW + 63) / 64;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int p0 = tile * 64;
+    __syncthreads();       // previous tile fully written out (and s_ct ready on the first pass)
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const uint4 raw = __ldg(src + i);
-      const uint32_t rw[4] = {raw.x, raw.y, raw.z, raw.w};
+    for (int it = 0; it < (64 * 16) / 128; ++it) {
+      const int idx = it * 128 + t;
+      const int px = idx >> 4, q16 = idx & 15;
+      const bool ok = p0 + px < HW;
+      cp_async16(sq + px * kApRowBytes + q16 * 16, base + (long)(ok ? p0 + px : p0) * kQkv + q16 * 8, ok);
+    }
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
+    const uint32_t wrow = sq + (warp * 16) * kApRowBytes;
+    const int mi = lane >> 3, r = lane & 7;
+    uint32_t qa[kHeads][2][4];
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float2 f = fd_unpack_bf16(rw[e]);
-        q[i * 8 + 2 * e] = f.x;
-        q[i * 8 + 2 * e + 1] = f.y;
+    for (int h = 0; h < kHeads; ++h)
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks)   // m0 (px 0-7, d 0-7) m1 (px 8-15, d 0-7) m2 (px 0-7, d 8-15) m3 (px 8-15, d 8-15)
+        ldmatrix_x4(qa[h][ks], wrow + ((mi & 1) * 8 + r) * kApRowBytes + (h * kD + ks * 16 + (mi >> 1) * 8) * 2);
+    __syncwarp();          // all q fragments are in registers: the warp's rows can now receive the output
+#pragma unroll
+    for (int h = 0; h < kHeads; ++h) {
+      float q0[8], q1[8];  // row g / row g+8: d = ks*16 + {2t, 2t+1, 2t+8, 2t+9}
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks) {
+        const float2 a0 = fd_unpack_bf16(qa[h][ks][0]), a1 = fd_unpack_bf16(qa[h][ks][1]);
+        const float2 a2 = fd_unpack_bf16(qa[h][ks][2]), a3 = fd_unpack_bf16(qa[h][ks][3]);
+        q0[ks * 4 + 0] = a0.x; q0[ks * 4 + 1] = a0.y; q0[ks * 4 + 2] = a2.x; q0[ks * 4 + 3] = a2.y;
+        q1[ks * 4 + 0] = a1.x; q1[ks * 4 + 1] = a1.y; q1[ks * 4 + 2] = a3.x; q1[ks * 4 + 3] = a3.y;
+      }
+      float m0 = q0[0], m1 = q1[0];
+#pragma unroll
+      for (int i = 1; i < 8; ++i) { m0 = fmaxf(m0, q0[i]); m1 = fmaxf(m1, q1[i]); }
+      m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1));
+      m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+      m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1));
+      m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+      float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        q0[i] = __expf(q0[i] - m0); s0 += q0[i];
+        q1[i] = __expf(q1[i] - m1); s1 += q1[i];
+      }
+      s0 += __shfl_xor_sync(0xffffffffu, s0, 1);
+      s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
+      s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
+      s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+      const float i0 = __fdividef(1.f, s0), i1 = __fdividef(1.f, s1);
+      float o[4][4];
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o[nt][j] = 0.f;
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks) {
+        uint32_t a[4];
+        a[0] = fd_pack_bf16(q0[ks * 4 + 0] * i0, q0[ks * 4 + 1] * i0);
+        a[1] = fd_pack_bf16(q1[ks * 4 + 0] * i1, q1[ks * 4 + 1] * i1);
+        a[2] = fd_pack_bf16(q0[ks * 4 + 2] * i0, q0[ks * 4 + 3] * i0);
+        a[3] = fd_pack_bf16(q1[ks * 4 + 2] * i1, q1[ks * 4 + 3] * i1);
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+          const __nv_bfloat16* cr = s_ct + (h * kD + nt * 8 + g) * kCtStride + ks * 16 + 2 * tq;
+          mma_bf16(o[nt], a, *reinterpret_cast<const uint32_t*>(cr), *reinterpret_cast<const uint32_t*>(cr + 8));
+        }
+      }
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        uint8_t* r0 = s_q + (warp * 16 + g) * kApRowBytes + (h * kD + nt * 8 + 2 * tq) * 2;
+        *reinterpret_cast<uint32_t*>(r0) = fd_pack_bf16(o[nt][0], o[nt][1]);
+        *reinterpret_cast<uint32_t*>(r0 + 8 * kApRowBytes) = fd_pack_bf16(o[nt][2], o[nt][3]);
       }
     }
-    float mx = q[0];
+    __syncwarp();
+    // 16 rows x 16 granules per warp -> coalesced 16-byte stores
 #pragma unroll
-    for (int i = 1; i < kD; ++i) mx = fmaxf(mx, q[i]);
-    float sum = 0.f;
-#pragma unroll
-    for (int i = 0; i < kD; ++i) {
-      q[i] = __expf(q[i] - mx);
-      sum += q[i];
-    }
-    const float norm = scale / sum;
-    float acc[kD];
-#pragma unroll
-    for (int e = 0; e < kD; ++e) acc[e] = 0.f;
-#pragma unroll
-    for (int dd = 0; dd < kD; ++dd) {
-      const float qd = q[dd] * norm;
-      const float4* row = reinterpret_cast<const float4*>(cx + dd * kD);
-#pragma unroll
-      for (int e4 = 0; e4 < kD / 4; ++e4) {
-        const float4 c4 = row[e4];
-        acc[e4 * 4 + 0] += c4.x * qd;
-        acc[e4 * 4 + 1] += c4.y * qd;
-        acc[e4 * 4 + 2] += c4.z * qd;
-        acc[e4 * 4 + 3] += c4.w * qd;
-      }
-    }
-    uint4* dst = reinterpret_cast<uint4*>(out + ((long)n * HW + p) * kHidden + head * kD);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      uint4 o;
-      o.x = fd_pack_bf16(acc[i * 8 + 0], acc[i * 8 + 1]);
-      o.y = fd_pack_bf16(acc[i * 8 + 2], acc[i * 8 + 3]);
-      o.z = fd_pack_bf16(acc[i * 8 + 4], acc[i * 8 + 5]);
-      o.w = fd_pack_bf16(acc[i * 8 + 6], acc[i * 8 + 7]);
-      dst[i] = o;
+    for (int it = 0; it < 8; ++it) {
+      const int idx = it * 32 + lane;
+      const int px = idx >> 4, q16 = idx & 15;
+      const int p = p0 + warp * 16 + px;
+      if (p < HW)
+        *reinterpret_cast<uint4*>(out + ((long)n * HW + p) * kHidden + q16 * 8) =
+            *reinterpret_cast<const uint4*>(s_q + (warp * 16 + px) * kApRowBytes + q16 * 16);
     }
   }
 }
 
 int la_chunks(int N, int HW, int* chunk_px) {
-  // enough blocks for ~4 per SM, chunk a multiple of the tile
-  int want = (FD_NUM_SMS * 4 + N - 1) / N;
+  // one wave: at most 3 resident blocks per SM (68 KB smem each) in total, chunk a multiple of the tile
+  int want = (FD_NUM_SMS * 3) / N;
   if (want < 1) want = 1;
   int px = (HW + want - 1) / want;
   px = ((px + kLaTile - 1) / kLaTile) * kLaTile;
@@ -216,13 +329,6 @@ int la_chunks(int N, int HW, int* chunk_px) {
 constexpr int kBQ = 64, kBK = 64;
 constexpr int kKStride = 40;   // bf16 per K row (32 + 8 pad): conflict-free fragment loads
 constexpr int kVStride = 72;   // bf16 per V^T row (64 + 8 pad)
-
-__device__ __forceinline__ void mma_bf16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm volatile(
-      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
 
 __global__ void __launch_bounds__(128) attention_kernel(const __nv_bfloat16* __restrict__ qkv,
                                                         __nv_bfloat16* __restrict__ out, int HW, float scale_log2) {
@@ -360,7 +466,7 @@ extern "C" {
 size_t fd_linattn_workspace_floats(int N, int HW) {
   int px;
   const int chunks = la_chunks(N, HW, &px);
-  return (size_t)N * chunks * kLaPartial + (size_t)N * kHeads * kD * kD;
+  return (size_t)N * chunks * kLaPartial + (size_t)N * kHeads * kD * kD / 2 + 16;
 }
 
 int fd_linattn(const void* qkv, void* out, float* workspace, int N, int HW, void* stream) {
@@ -369,16 +475,23 @@ int fd_linattn(const void* qkv, void* out, float* workspace, int N, int HW, void
   int px;
   const int chunks = la_chunks(N, HW, &px);
   float* partial = workspace;
-  float* ctx = workspace + (size_t)N * chunks * kLaPartial;
+  size_t off = (size_t)N * chunks * kLaPartial;
+  off = (off + 3) & ~(size_t)3;                                     // 16-byte aligned bf16 ctx^T
+  __nv_bfloat16* ctx_t = reinterpret_cast<__nv_bfloat16*>(workspace + off);
   const __nv_bfloat16* q = static_cast<const __nv_bfloat16*>(qkv);
-  linattn_partial_kernel<<<dim3(chunks, N), 256, 0, st>>>(q, partial, HW, px);
+  static bool attr_set = false;
+  if (!attr_set) {
+    FD_CUDA(cudaFuncSetAttribute(linattn_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kLaSmemBytes));
+    attr_set = true;
+  }
+  linattn_partial_kernel<<<dim3(chunks, N), 256, kLaSmemBytes, st>>>(q, partial, HW, px);
   FD_LAUNCH_CHECK();
-  linattn_combine_kernel<<<N * kHeads, 1024, 0, st>>>(partial, ctx, chunks, 1.f / (float)HW);
+  linattn_combine_kernel<<<N * kHeads, 1024, 0, st>>>(partial, ctx_t, chunks, 1.f / (float)HW);
   FD_LAUNCH_CHECK();
   int bx = (HW + 63) / 64;
   const int cap = (FD_NUM_SMS * 8 + N - 1) / N;
   if (bx > cap) bx = cap;
-  linattn_apply_kernel<<<dim3(bx, N), 256, 0, st>>>(q, ctx, static_cast<__nv_bfloat16*>(out), HW, 0.17677669529663687f);
+  linattn_apply_kernel<<<dim3(bx, N), 128, 0, st>>>(q, ctx_t, static_cast<__nv_bfloat16*>(out), HW);
   FD_LAUNCH_CHECK();
   return FD_OK;
 }

@@ -71,7 +71,7 @@ __device__ __forceinline__ void fd_block_sum(float (&v)[NV], float* smem /* >= N
   __syncthreads();
 }
 
-__device__ __forceinline__ float fd_silu(float x) { return x / (1.f + __expf(-x)); }
+__device__ __forceinline__ float fd_silu(float x) { return __fdividef(x, 1.f + __expf(-x)); }
 
 __device__ __forceinline__ uint32_t fd_pack_bf16(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);

@@ -1,0 +1,197 @@
+// Epilogue shared by the tensor-core convolution kernels (fd_conv_igemm.cu, fd_conv_strip.cu):
+// 8 warps drain the fp32 accumulator of a 128 x BLOCK_N tile from TMEM.
+//   TMEM lane quarter q = warp % 4 (hardware rule); the two warps of a quarter split the 32-column chunks
+//   (even / odd).  Output goes registers -> +bias (+residual) -> bf16 -> 128B-swizzled smem slab (64 channels) ->
+//   one TMA store per slab, which also clips rows / columns outside the image.  GroupNorm partial sums
+//   (sum, sum of squares per (sample, group); Block.forward :176,181 of the reference) stay in registers across
+//   the tiles of one (image, N-tile) and are flushed once: fixed-order reduction in smem, then double atomics.
+#pragma once
+
+#include "fd_tc.cuh"
+
+namespace fdtc {
+
+constexpr int kBlockM = 128;
+constexpr int kEpiWarps = 8;
+constexpr int kEpiThreads = kEpiWarps * 32;
+constexpr int kSlabBytes = kBlockM * 128;           // 128 rows x 64 bf16: one TMA-store slab
+
+struct EpiTile {
+  int img, h0, w0, n_tile;
+};
+
+struct EpiCtx {
+  uint32_t tmem_base;
+  uint32_t o_smem;              // NBUF staging slabs, 1024-byte aligned
+  uint32_t tfull0, tempty0;     // mbarrier addresses of accumulator stage 0 (stage 1 at +8)
+  float* s_bias;                // [2][BLOCK_N]
+  float* s_stats;               // [8 warps][16]
+  const CUtensorMap* map_out;   // (Cout, W, H, N, 1), box {64, Wt, R, 1, 1}
+  const float* bias;
+  const __nv_bfloat16* residual;
+  double* gn_stats;
+  int H, W, Cout, Wt;
+};
+
+// GPT = GroupNorm groups covered by one N-tile (8 when Cout == BLOCK_N, 4 when Cout == 2*BLOCK_N, 0 = no statistics).
+// Must be called by warps 2..9 of the CTA (threads 64..319); next_tile(iter, tile) enumerates this CTA's tiles in
+// the same order as the MMA warp.
+template <int BLOCK_N, int GPT, int NBUF, class NextTile>
+__device__ __forceinline__ void conv_epilogue(const EpiCtx& ec, NextTile next_tile) {
+  constexpr int NCHUNK = BLOCK_N / 32;                 // 32-column accumulator chunks per tile
+  constexpr int CPW = NCHUNK / 2;                      // chunks per epilogue warp
+  constexpr int CPGT = GPT > 0 ? BLOCK_N / GPT : 32;   // columns per group inside the tile
+  constexpr int GIC = CPGT < 32 ? 32 / CPGT : 1;       // groups inside one 32-column chunk
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t tmem_base = ec.tmem_base;
+  const uint32_t o_smem = ec.o_smem;
+  float* const s_bias = ec.s_bias;
+  float* const s_stats = ec.s_stats;
+  {
+    // TMEM lane quarter q = warp % 4 (hardware rule); the two warps of a quarter split the 32-column chunks
+    // (even / odd).  Output goes registers -> swizzled smem slab (64 channels) -> one TMA store per slab, which
+    // also clips rows / columns outside the image.  GroupNorm partial sums stay in registers across the tiles
+    // of one (image, N-tile) and are flushed once.
+    const int ew = warp - 2;                  // 0..7
+    const int et = threadIdx.x - 64;          // 0..255
+    const int quarter = warp & 3;
+    const int half = ew >> 2;                 // which chunk parity this warp owns
+    const int row = quarter * 32 + lane;      // accumulator row = pixel within the tile
+    const int rr = row / ec.Wt, ww = row - rr * ec.Wt;
+    const bool issuer = (et == 0);
+    float st_s[CPW > 0 ? CPW : 1][GIC], st_q[CPW > 0 ? CPW : 1][GIC];
+#pragma unroll
+    for (int a = 0; a < (CPW > 0 ? CPW : 1); ++a)
+#pragma unroll
+      for (int b = 0; b < GIC; ++b) st_s[a][b] = st_q[a][b] = 0.f;
+    int st_img = -1, st_ntile = 0;
+    uint32_t slab_count = 0;
+
+    auto flush_stats = [&]() {
+      // all epilogue warps call this at the same tile boundary
+      if (GPT == 0 || st_img < 0) return;
+      float* mine = s_stats + ew * 16;
+      if (lane < 16) mine[lane] = 0.f;
+      __syncwarp();
+#pragma unroll
+      for (int a = 0; a < (CPW > 0 ? CPW : 1); ++a)
+#pragma unroll
+        for (int b = 0; b < GIC; ++b) {
+          const float s = fd_warp_sum(st_s[a][b]), q = fd_warp_sum(st_q[a][b]);
+          if (lane == 0) {
+            const int col = (2 * a + half) * 32 + b * CPGT;      // first column of this partial inside the tile
+            const int grp = col / CPGT;
+            mine[grp * 2] += s;
+            mine[grp * 2 + 1] += q;
+          }
+          st_s[a][b] = st_q[a][b] = 0.f;
+        }
+      named_bar_sync(2, kEpiThreads);
+      if (et < 2 * GPT) {
+        float sv = 0.f;
+#pragma unroll
+        for (int w8 = 0; w8 < kEpiWarps; ++w8) sv += s_stats[w8 * 16 + et];     // fixed order
+        atomicAdd(ec.gn_stats + (long)st_img * 16 + st_ntile * 2 * GPT + et, (double)sv);
+      }
+      named_bar_sync(2, kEpiThreads);
+    };
+
+    EpiTile tc;
+    for (int iter = 0; next_tile(iter, tc); ++iter) {
+      const int as = iter & 1;
+      const uint32_t aphase = (iter >> 1) & 1;
+      const int n_tile = tc.n_tile, img = tc.img, h0 = tc.h0, w0 = tc.w0;
+      const int h = h0 + rr, w = w0 + ww;
+      const bool valid = (h < ec.H) && (w < ec.W);
+      const int n0 = n_tile * BLOCK_N;
+      if (GPT > 0 && (img != st_img || n_tile != st_ntile)) {
+        flush_stats();
+        st_img = img;
+        st_ntile = n_tile;
+      }
+      float* bias_s = s_bias + as * BLOCK_N;
+      for (int i = et; i < BLOCK_N; i += kEpiThreads) bias_s[i] = ec.bias ? __ldg(ec.bias + n0 + i) : 0.f;
+      // (the slab barrier below also publishes the bias)
+
+      mbar_wait(ec.tfull0 + 8u * as, aphase);
+      tc_fence_after();
+      const long pix = ((long)img * ec.H + h) * ec.W + w;
+      const __nv_bfloat16* rrow = ec.residual ? ec.residual + pix * ec.Cout + n0 : nullptr;
+#pragma unroll
+      for (int slab = 0; slab < (BLOCK_N + 63) / 64; ++slab) {
+        const uint32_t buf = o_smem + (slab_count % NBUF) * kSlabBytes;
+        ++slab_count;
+        if (issuer) tma_store_wait_read<NBUF - 1>();      // the store that last used this buffer has read it
+        named_bar_sync(1, kEpiThreads);
+        const int ci = slab * 2 + half;                   // this warp's chunk inside the slab
+        const int c = ci * 32;
+        uint32_t acc[32];
+        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BLOCK_N + c), acc);
+        tmem_ld_wait();
+        float v[32];
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) {
+          const float4 b4 = *reinterpret_cast<const float4*>(bias_s + c + j4 * 4);
+          v[j4 * 4 + 0] = __uint_as_float(acc[j4 * 4 + 0]) + b4.x;
+          v[j4 * 4 + 1] = __uint_as_float(acc[j4 * 4 + 1]) + b4.y;
+          v[j4 * 4 + 2] = __uint_as_float(acc[j4 * 4 + 2]) + b4.z;
+          v[j4 * 4 + 3] = __uint_as_float(acc[j4 * 4 + 3]) + b4.w;
+        }
+        if (rrow != nullptr && valid) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const uint4 r4 = __ldg(reinterpret_cast<const uint4*>(rrow + c) + q);
+            const uint32_t rw[4] = {r4.x, r4.y, r4.z, r4.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 f = fd_unpack_bf16(rw[e]);
+              v[q * 8 + e * 2] += f.x;
+              v[q * 8 + e * 2 + 1] += f.y;
+            }
+          }
+        }
+        if (GPT > 0 && valid) {
+#pragma unroll
+          for (int b = 0; b < GIC; ++b) {
+            constexpr int span = CPGT < 32 ? CPGT : 32;
+            float s = 0.f, q = 0.f;
+#pragma unroll
+            for (int j = 0; j < span; ++j) {
+              const float x = v[b * span + j];
+              s += x;
+              q = fmaf(x, x, q);
+            }
+            st_s[slab][b] += s;
+            st_q[slab][b] += q;
+          }
+        }
+        // 64-byte piece of this row inside the 128-byte slab row, 16-byte granules XOR-swizzled by (row & 7)
+        const uint32_t rbase = buf + (uint32_t)row * 128u;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const uint32_t piece = (uint32_t)(half * 4 + q) ^ (uint32_t)(row & 7);
+          const uint32_t o0 = fd_pack_bf16(v[q * 8 + 0], v[q * 8 + 1]), o1 = fd_pack_bf16(v[q * 8 + 2], v[q * 8 + 3]);
+          const uint32_t o2 = fd_pack_bf16(v[q * 8 + 4], v[q * 8 + 5]), o3 = fd_pack_bf16(v[q * 8 + 6], v[q * 8 + 7]);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rbase + piece * 16u), "r"(o0), "r"(o1), "r"(o2),
+                       "r"(o3)
+                       : "memory");
+        }
+        fence_proxy_async_smem();
+        if (slab == (BLOCK_N + 63) / 64 - 1) {
+          tc_fence_before();
+          mbar_arrive(ec.tempty0 + 8u * as);          // all TMEM reads of this tile are done
+        }
+        named_bar_sync(1, kEpiThreads);
+        if (issuer) {
+          tma_store_5d(ec.map_out, buf, n0 + slab * 64, w0, h0, img, 0);
+          tma_store_commit();
+        }
+      }
+    }
+    flush_stats();
+    if (issuer) tma_store_wait_all();
+  }
+}
+
+}  // namespace fdtc

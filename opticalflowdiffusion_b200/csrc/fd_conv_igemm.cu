@@ -23,19 +23,17 @@
 //     warp 1    TMEM allocator + MMA issuer (one lane issues tcgen05.mma, tcgen05.commit frees slots)
 //     warps 2-5 epilogue: tcgen05.ld -> +bias (+residual) -> GroupNorm partial statistics
 //               (sum, sum of squares per (sample, group), :176,181) -> bf16 NHWC store
-#include "fd_tc.cuh"
+#include <stdlib.h>
+
+#include "fd_conv_epi.cuh"
 
 using namespace fdtc;
 
 namespace {
 
-constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;
 constexpr int kATileBytes = kBlockM * kBlockK * 2;  // 16 KiB
-constexpr int kEpiWarps = 8;
-constexpr int kEpiThreads = kEpiWarps * 32;
 constexpr int kThreads = 64 + kEpiThreads;          // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
-constexpr int kSlabBytes = kBlockM * 128;           // 128 rows x 64 bf16: one TMA-store slab
 
 struct ConvParams {
   int N, H, W;        // images, output rows, output columns (after flattening / merging)
@@ -72,10 +70,6 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
   using C = Cfg<BLOCK_N>;
   constexpr int STAGES = C::kStages;
   constexpr int NBUF = C::kStoreBufs;
-  constexpr int NCHUNK = BLOCK_N / 32;                 // 32-column accumulator chunks per tile
-  constexpr int CPW = NCHUNK / 2;                      // chunks per epilogue warp (warps split even / odd chunks)
-  constexpr int CPGT = GPT > 0 ? BLOCK_N / GPT : 32;   // columns per group inside the tile
-  constexpr int GIC = CPGT < 32 ? 32 / CPGT : 1;       // groups inside one 32-column chunk
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // SWIZZLE_128B tiles need 1024-byte alignment
   uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
@@ -183,155 +177,29 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
     }
   } else {
     // ===================== epilogue (warps 2..9) =====================
-    // TMEM lane quarter q = warp % 4 (hardware rule); the two warps of a quarter split the 32-column chunks
-    // (even / odd).  Output goes registers -> swizzled smem slab (64 channels) -> one TMA store per slab, which
-    // also clips rows / columns outside the image.  GroupNorm partial sums stay in registers across the tiles
-    // of one (image, N-tile) and are flushed once.
-    const int ew = warp - 2;                  // 0..7
-    const int et = threadIdx.x - 64;          // 0..255
-    const int quarter = warp & 3;
-    const int half = ew >> 2;                 // which chunk parity this warp owns
-    const int row = quarter * 32 + lane;      // accumulator row = pixel within the tile
-    const int rr = row / p.Wt, ww = row - rr * p.Wt;
-    const bool issuer = (et == 0);
-    float st_s[CPW > 0 ? CPW : 1][GIC], st_q[CPW > 0 ? CPW : 1][GIC];
-#pragma unroll
-    for (int a = 0; a < (CPW > 0 ? CPW : 1); ++a)
-#pragma unroll
-      for (int b = 0; b < GIC; ++b) st_s[a][b] = st_q[a][b] = 0.f;
-    int st_img = -1, st_ntile = 0;
-    uint32_t slab_count = 0;
-
-    auto flush_stats = [&]() {
-      // all epilogue warps call this at the same tile boundary
-      if (GPT == 0 || st_img < 0) return;
-      float* mine = s_stats + ew * 16;
-      if (lane < 16) mine[lane] = 0.f;
-      __syncwarp();
-#pragma unroll
-      for (int a = 0; a < (CPW > 0 ? CPW : 1); ++a)
-#pragma unroll
-        for (int b = 0; b < GIC; ++b) {
-          const float s = fd_warp_sum(st_s[a][b]), q = fd_warp_sum(st_q[a][b]);
-          if (lane == 0) {
-            const int col = (2 * a + half) * 32 + b * CPGT;      // first column of this partial inside the tile
-            const int grp = col / CPGT;
-            mine[grp * 2] += s;
-            mine[grp * 2 + 1] += q;
-          }
-          st_s[a][b] = st_q[a][b] = 0.f;
-        }
-      named_bar_sync(2, kEpiThreads);
-      if (et < 2 * GPT) {
-        float sv = 0.f;
-#pragma unroll
-        for (int w8 = 0; w8 < kEpiWarps; ++w8) sv += s_stats[w8 * 16 + et];     // fixed order
-        atomicAdd(p.gn_stats + (long)st_img * 16 + st_ntile * 2 * GPT + et, (double)sv);
-      }
-      named_bar_sync(2, kEpiThreads);
-    };
-
-    int iter = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++iter) {
-      const int as = iter & 1;
-      const uint32_t aphase = (iter >> 1) & 1;
-      const int n_tile = tile % p.n_tiles;
+    EpiCtx ec;
+    ec.tmem_base = tmem_base;
+    ec.o_smem = o_smem;
+    ec.tfull0 = tfull_bar(0);
+    ec.tempty0 = tempty_bar(0);
+    ec.s_bias = s_bias;
+    ec.s_stats = s_stats;
+    ec.map_out = &map_out;
+    ec.bias = p.bias;
+    ec.residual = p.residual;
+    ec.gn_stats = p.gn_stats;
+    ec.H = p.H; ec.W = p.W; ec.Cout = p.Cout; ec.Wt = p.Wt;
+    conv_epilogue<BLOCK_N, GPT, NBUF>(ec, [&](int iter, EpiTile& t) {
+      const int tile = blockIdx.x + iter * gridDim.x;
+      if (tile >= p.total_tiles) return false;
+      t.n_tile = tile % p.n_tiles;
       const int m_tile = tile / p.n_tiles;
-      const int img = m_tile / tiles_per_img;
-      const int rem = m_tile - img * tiles_per_img;
-      const int h0 = (rem / p.tiles_w) * p.R, w0 = (rem % p.tiles_w) * p.Wt;
-      const int h = h0 + rr, w = w0 + ww;
-      const bool valid = (h < p.H) && (w < p.W);
-      const int n0 = n_tile * BLOCK_N;
-      if (GPT > 0 && (img != st_img || n_tile != st_ntile)) {
-        flush_stats();
-        st_img = img;
-        st_ntile = n_tile;
-      }
-      float* bias_s = s_bias + as * BLOCK_N;
-      for (int i = et; i < BLOCK_N; i += kEpiThreads) bias_s[i] = p.bias ? __ldg(p.bias + n0 + i) : 0.f;
-      // (the slab barrier below also publishes the bias)
-
-      mbar_wait(tfull_bar(as), aphase);
-      tc_fence_after();
-      const long pix = ((long)img * p.H + h) * p.W + w;
-      const __nv_bfloat16* rrow = p.residual ? p.residual + pix * p.Cout + n0 : nullptr;
-#pragma unroll
-      for (int slab = 0; slab < (BLOCK_N + 63) / 64; ++slab) {
-        const uint32_t buf = o_smem + (slab_count % NBUF) * kSlabBytes;
-        ++slab_count;
-        if (issuer) tma_store_wait_read<NBUF - 1>();      // the store that last used this buffer has read it
-        named_bar_sync(1, kEpiThreads);
-        const int ci = slab * 2 + half;                   // this warp's chunk inside the slab
-        const int c = ci * 32;
-        uint32_t acc[32];
-        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BLOCK_N + c), acc);
-        tmem_ld_wait();
-        float v[32];
-#pragma unroll
-        for (int j4 = 0; j4 < 8; ++j4) {
-          const float4 b4 = *reinterpret_cast<const float4*>(bias_s + c + j4 * 4);
-          v[j4 * 4 + 0] = __uint_as_float(acc[j4 * 4 + 0]) + b4.x;
-          v[j4 * 4 + 1] = __uint_as_float(acc[j4 * 4 + 1]) + b4.y;
-          v[j4 * 4 + 2] = __uint_as_float(acc[j4 * 4 + 2]) + b4.z;
-          v[j4 * 4 + 3] = __uint_as_float(acc[j4 * 4 + 3]) + b4.w;
-        }
-        if (rrow != nullptr && valid) {
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const uint4 r4 = __ldg(reinterpret_cast<const uint4*>(rrow + c) + q);
-            const uint32_t rw[4] = {r4.x, r4.y, r4.z, r4.w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float2 f = fd_unpack_bf16(rw[e]);
-              v[q * 8 + e * 2] += f.x;
-              v[q * 8 + e * 2 + 1] += f.y;
-            }
-          }
-        }
-        if (GPT > 0 && valid) {
-#pragma unroll
-          for (int b = 0; b < GIC; ++b) {
-            constexpr int span = CPGT < 32 ? CPGT : 32;
-            float s = 0.f, q = 0.f;
-#pragma unroll
-            for (int j = 0; j < span; ++j) {
-              const float x = v[b * span + j];
-              s += x;
-              q = fmaf(x, x, q);
-            }
-            st_s[slab][b] += s;
-            st_q[slab][b] += q;
-          }
-        }
-        // 64-byte piece of this row inside the 128-byte slab row, 16-byte granules XOR-swizzled by (row & 7)
-        const uint32_t rbase = buf + (uint32_t)row * 128u;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const uint32_t piece = (uint32_t)(half * 4 + q) ^ (uint32_t)(row & 7);
-          const uint32_t o0 = fd_pack_bf16(v[q * 8 + 0], v[q * 8 + 1]), o1 = fd_pack_bf16(v[q * 8 + 2], v[q * 8 + 3]);
-          const uint32_t o2 = fd_pack_bf16(v[q * 8 + 4], v[q * 8 + 5]), o3 = fd_pack_bf16(v[q * 8 + 6], v[q * 8 + 7]);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rbase + piece * 16u), "r"(o0), "r"(o1), "r"(o2),
-                       "r"(o3)
-                       : "memory");
-        }
-        fence_proxy_async_smem();
-        if (slab == (BLOCK_N + 63) / 64 - 1) {
-          tc_fence_before();
-          mbar_arrive(tempty_bar(as));          // all TMEM reads of this tile are done
-        }
-        named_bar_sync(1, kEpiThreads);
-        if (issuer) {
-          if (p.mode == 0)
-            tma_store_5d(&map_out, buf, n0 + slab * 64, w0, h0, img, 0);
-          else
-            tma_store_5d(&map_out, buf, n0 + slab * 64, w0, h0, 0, 0);
-          tma_store_commit();
-        }
-      }
-    }
-    flush_stats();
-    if (issuer) tma_store_wait_all();
+      t.img = m_tile / tiles_per_img;
+      const int rem = m_tile - t.img * tiles_per_img;
+      t.h0 = (rem / p.tiles_w) * p.R;
+      t.w0 = (rem % p.tiles_w) * p.Wt;
+      return true;
+    });
   }
 
   tc_fence_before();
@@ -379,6 +247,9 @@ int launch(const CUtensorMap& ma0, const CUtensorMap& ma1, const CUtensorMap& mb
 
 }  // namespace
 
+int fd_conv3x3_strip_launch(const void* src, const void* wpacked, const float* bias, void* out, double* gn_stats, int N,
+                            int H, int W, int base_offset_mode, cudaStream_t st);   // fd_conv_strip.cu
+
 extern "C" {
 
 int fd_conv_igemm(const void* src0, int C0, const void* src1, int C1, const void* wpacked, const float* bias,
@@ -392,6 +263,18 @@ int fd_conv_igemm(const void* src0, int C0, const void* src1, int C1, const void
   FD_REQUIRE(mode == 0 || mode == 1, "conv_igemm: mode %d", mode);
   FD_REQUIRE(mode == 0 || (C1 == 0 && gn_stats == nullptr), "conv_igemm: mode 1 takes one source and no statistics");
   FD_REQUIRE(KH >= 1 && KW >= 1 && KH * KW <= 64, "conv_igemm: bad kernel %dx%d", KH, KW);
+  {
+    // full-resolution 64 -> 64 3x3 layers: rolling-strip kernel with resident weights (each input pixel is
+    // fetched from L2 once instead of nine times).  FD_CONV_STRIP=0 disables it.
+    static int strip_mode = -1;
+    if (strip_mode < 0) {
+      const char* e = getenv("FD_CONV_STRIP");
+      strip_mode = e ? atoi(e) : 2;
+    }
+    if (strip_mode > 0 && mode == 0 && KH == 3 && KW == 3 && pad_h == 1 && pad_w == 1 && C0 == 64 && C1 == 0 &&
+        Cout == 64 && residual == nullptr && W >= 128)
+      return fd_conv3x3_strip_launch(src0, wpacked, bias, out, gn_stats, N, H, W, strip_mode, (cudaStream_t)stream);
+  }
   static int sms = 0;
   if (sms == 0) {
     int dev = 0;

@@ -1,0 +1,262 @@
+// 3x3 / pad 1 / 64 -> 64 channel convolution for large images (the full-resolution ResnetBlock convs of the
+// UNet, denoising_diffusion.py:172-214: 8 launches and 15 % of the forward FLOPs at 440x1024).
+//
+// The generic implicit GEMM (fd_conv_igemm.cu) re-reads every input pixel once per tap and the weights once
+// per tile: 216 KB of L2->smem traffic per 9.4 MFLOP tile, which bounds it at ~0.45 PFLOP/s.  Here
+//   * the 72 KB of packed weights are loaded ONCE per CTA and stay resident in shared memory;
+//   * a CTA walks down a column strip of the image (128 output pixels wide, SEG rows tall).  Input rows are
+//     TMA-loaded once as 130-pixel strips (left/right halo included; rows / columns outside the image are
+//     zero-filled by TMA) into a 5-slot ring; the 9 taps of an output row are 9 UMMA A-operands that alias
+//     three strips at a 0/1/2-pixel (0/128/256-byte) offset -- no data is re-fetched or re-arranged;
+//   * so each output row costs one new 16.6 KB strip: ~13x less L2 traffic, the kernel becomes MMA/epilogue bound.
+// Warp roles and the epilogue (GroupNorm partial sums, swizzled smem + TMA store) are those of the generic kernel.
+#include "fd_conv_epi.cuh"
+
+using namespace fdtc;
+
+namespace {
+
+constexpr int kC = 64;                         // input = output channels
+constexpr int kTileW = 128;                    // output pixels per tile (one image row segment)
+constexpr int kStripPx = kTileW + 2;           // + left/right halo
+constexpr int kStripTx = kStripPx * 128;       // bytes TMA delivers per strip
+constexpr int kStripBytes = 136 * 128;         // slot size: multiple of 1024 keeps the swizzle phase of every slot
+constexpr int kNS = 5;                         // strips in flight: 3 in use + 2 prefetched
+constexpr int kWTapBytes = kC * kC * 2;        // one tap of weights: [64 cout][64 cin] bf16
+constexpr int kWBytes = 9 * kWTapBytes;        // 72 KB, resident
+constexpr int kThreads = 64 + kEpiThreads;
+constexpr int kTail = 256 + 2 * kC * 4 + kEpiWarps * 16 * 4 + 64;
+constexpr int kSmemBytes = 1024 + kWBytes + kNS * kStripBytes + 2 * kSlabBytes + kTail;
+
+struct StripParams {
+  int N, H, W;
+  int wblocks, segs, seg_rows, total_items;
+  int base_offset_mode;      // 2 (default): base_offset 0 -- correct; 1: (addr >> 7) & 7 -- measured WRONG, kept as an experiment
+  const float* bias;
+  double* gn_stats;
+};
+
+__device__ __forceinline__ void decode_item(const StripParams& p, int item, int& n, int& w0, int& ra, int& rb) {
+  const int seg = item % p.segs;
+  const int rest = item / p.segs;
+  const int wb = rest % p.wblocks;
+  n = rest / p.wblocks;
+  w0 = wb * kTileW;
+  ra = seg * p.seg_rows;
+  rb = min(p.H, ra + p.seg_rows);
+}
+
+template <int GPT>
+__global__ void __launch_bounds__(kThreads, 1)
+conv3x3_strip_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CUtensorMap map_w,
+                     const __grid_constant__ CUtensorMap map_out, const StripParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t w_smem = base;
+  const uint32_t s_smem = base + kWBytes;
+  const uint32_t o_smem = s_smem + kNS * kStripBytes;
+  const uint32_t bar_base = o_smem + 2 * kSlabBytes;
+  const uint32_t wfull_bar = bar_base;
+  auto full_bar = [&](int s) { return bar_base + 8u * (1 + s); };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (1 + kNS + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (1 + 2 * kNS + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (3 + 2 * kNS + s); };
+  uint8_t* gtail = gbase + kWBytes + kNS * kStripBytes + 2 * kSlabBytes + 256;
+  float* s_bias = reinterpret_cast<float*>(gtail);
+  float* s_stats = reinterpret_cast<float*>(gtail + 2 * kC * 4);
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(gtail + 2 * kC * 4 + kEpiWarps * 16 * 4);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_in);
+    tma_prefetch_desc(&map_w);
+    tma_prefetch_desc(&map_out);
+    mbar_init(wfull_bar, 1);
+    for (int s = 0; s < kNS; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tfull_bar(s), 1);
+      mbar_init(tempty_bar(s), kEpiThreads);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(smem_u32(s_tmem), 2 * kC);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *s_tmem;
+
+  if (warp == 0) {
+    // ===================== TMA producer: weights once, then one strip per input row =====================
+    if (lane == 0) {
+      mbar_expect_tx(wfull_bar, kWBytes);
+      for (int tap = 0; tap < 9; ++tap) tma_load_2d(w_smem + tap * kWTapBytes, &map_w, wfull_bar, tap * kC, 0);
+      uint32_t seq = 0;
+      for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+        int n, w0, ra, rb;
+        decode_item(p, item, n, w0, ra, rb);
+        for (int y = ra - 1; y <= rb; ++y, ++seq) {
+          const int slot = seq % kNS;
+          const uint32_t phase = (seq / kNS) & 1u;
+          mbar_wait(empty_bar(slot), phase ^ 1u);
+          mbar_expect_tx(full_bar(slot), kStripTx);
+          tma_load_5d(s_smem + slot * kStripBytes, &map_in, full_bar(slot), 0, w0 - 1, y, n, 0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc = umma_idesc_bf16(kBlockM, kC);
+    mbar_wait(wfull_bar, 0);
+    uint32_t seq0 = 0;       // sequence number of the first strip (input row ra-1) of the current item
+    int iter = 0;
+    for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+      int n, w0, ra, rb;
+      decode_item(p, item, n, w0, ra, rb);
+      const int rows = rb - ra;
+      for (int j = 0; j < rows; ++j, ++iter) {
+        const int as = iter & 1;
+        const uint32_t aphase = (iter >> 1) & 1;
+        mbar_wait(tempty_bar(as), aphase ^ 1u);
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+          const uint32_t s = seq0 + j + ky;
+          mbar_wait(full_bar(s % kNS), (s / kNS) & 1u);
+        }
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t tmem_d = tmem_base + as * kC;
+#pragma unroll
+          for (int ky = 0; ky < 3; ++ky) {
+            const uint32_t strip = s_smem + ((seq0 + j + ky) % kNS) * kStripBytes;
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+              // output pixel i of the tile reads strip pixel i + kx: same strip, start shifted by kx rows of 128 B
+              const uint64_t adesc = p.base_offset_mode == 1 ? umma_desc_sw128_base_offset(strip + kx * 128)
+                                                             : umma_desc_sw128(strip + kx * 128);
+              const uint64_t bdesc = umma_desc_sw128(w_smem + (ky * 3 + kx) * kWTapBytes);
+#pragma unroll
+              for (int k = 0; k < kC / 16; ++k)
+                umma_bf16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (ky | kx | k) != 0 ? 1u : 0u);
+            }
+          }
+          umma_commit(tfull_bar(as));
+          umma_commit(empty_bar((seq0 + j) % kNS));                 // input row ra-1+j is no longer needed
+          if (j == rows - 1) {
+            umma_commit(empty_bar((seq0 + j + 1) % kNS));
+            umma_commit(empty_bar((seq0 + j + 2) % kNS));
+          }
+        }
+        __syncwarp();
+      }
+      seq0 += rows + 2;
+    }
+  } else {
+    // ===================== epilogue =====================
+    EpiCtx ec;
+    ec.tmem_base = tmem_base;
+    ec.o_smem = o_smem;
+    ec.tfull0 = tfull_bar(0);
+    ec.tempty0 = tempty_bar(0);
+    ec.s_bias = s_bias;
+    ec.s_stats = s_stats;
+    ec.map_out = &map_out;
+    ec.bias = p.bias;
+    ec.residual = nullptr;
+    ec.gn_stats = p.gn_stats;
+    ec.H = p.H; ec.W = p.W; ec.Cout = kC; ec.Wt = kTileW;
+    int item = blockIdx.x, j = 0, n = 0, w0 = 0, ra = 0, rb = 0;
+    bool have = false;
+    conv_epilogue<kC, GPT, 2>(ec, [&](int, EpiTile& t) {
+      while (true) {
+        if (!have) {
+          if (item >= p.total_items) return false;
+          decode_item(p, item, n, w0, ra, rb);
+          j = 0;
+          have = true;
+        }
+        if (ra + j < rb) break;
+        have = false;
+        item += gridDim.x;
+      }
+      t.img = n;
+      t.h0 = ra + j;
+      t.w0 = w0;
+      t.n_tile = 0;
+      ++j;
+      return true;
+    });
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 2 * kC);
+  }
+}
+
+}  // namespace
+
+int fd_conv3x3_strip_launch(const void* src, const void* wpacked, const float* bias, void* out, double* gn_stats, int N,
+                            int H, int W, int base_offset_mode, cudaStream_t st) {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    FD_CUDA(cudaGetDevice(&dev));
+    FD_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  StripParams p{};
+  p.N = N; p.H = H; p.W = W;
+  p.wblocks = (W + kTileW - 1) / kTileW;
+  // rows per item: 16..64, chosen for the best last-wave fill (ties -> taller segments: fewer halo reloads)
+  int best_segs = 1;
+  double best_eff = -1.0;
+  for (int segs = (H + 63) / 64; segs <= (H + 15) / 16; ++segs) {
+    const long items = (long)N * p.wblocks * segs;
+    const double eff = (double)items / (double)(((items + sms - 1) / sms) * sms);
+    if (eff > best_eff + 1e-9) { best_eff = eff; best_segs = segs; }
+  }
+  p.segs = best_segs;
+  p.seg_rows = (H + best_segs - 1) / best_segs;
+  p.segs = (H + p.seg_rows - 1) / p.seg_rows;
+  p.total_items = N * p.wblocks * p.segs;
+  p.base_offset_mode = base_offset_mode;
+  p.bias = bias;
+  p.gn_stats = gn_stats;
+  CUtensorMap mi, mw, mo;
+  {
+    const uint64_t dims[5] = {(uint64_t)kC, (uint64_t)W, (uint64_t)H, (uint64_t)N, 1};
+    const uint64_t str[4] = {(uint64_t)kC * 2, (uint64_t)W * kC * 2, (uint64_t)H * W * kC * 2, (uint64_t)N * H * W * kC * 2};
+    const uint32_t box_in[5] = {64, (uint32_t)kStripPx, 1, 1, 1};
+    const uint32_t box_out[5] = {64, (uint32_t)kTileW, 1, 1, 1};
+    if (int e = make_tmap_bf16(&mi, src, 5, dims, str, box_in)) return e;
+    if (int e = make_tmap_bf16(&mo, out, 5, dims, str, box_out)) return e;
+  }
+  {
+    const uint64_t dims[2] = {(uint64_t)9 * kC, (uint64_t)kC};
+    const uint64_t str[1] = {(uint64_t)9 * kC * 2};
+    const uint32_t box[2] = {64, 64};
+    if (int e = make_tmap_bf16(&mw, wpacked, 2, dims, str, box)) return e;
+  }
+  const int grid = p.total_items < sms ? p.total_items : sms;
+  static bool attr_set[2] = {false, false};
+  if (gn_stats != nullptr) {
+    if (!attr_set[1]) {
+      FD_CUDA(cudaFuncSetAttribute(conv3x3_strip_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+      attr_set[1] = true;
+    }
+    conv3x3_strip_kernel<8><<<grid, kThreads, kSmemBytes, st>>>(mi, mw, mo, p);
+  } else {
+    if (!attr_set[0]) {
+      FD_CUDA(cudaFuncSetAttribute(conv3x3_strip_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+      attr_set[0] = true;
+    }
+    conv3x3_strip_kernel<0><<<grid, kThreads, kSmemBytes, st>>>(mi, mw, mo, p);
+  }
+  FD_LAUNCH_CHECK();
+  return FD_OK;
+}

@@ -130,14 +130,19 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 
 // K-major operand tile, rows of 64 bf16 (128 B) written by TMA with 128-byte swizzle:
 // 8-row groups are 1024 B apart (SBO), LBO unused, descriptor version 1 (sm_100), layout SWIZZLE_128B.
-// `base_offset` = (start address >> 7) & 7 when the start is not 1024-byte aligned.
+// MEASURED on B200 (tests/test_gpu_conv.py with FD_CONV_STRIP=1 vs 2): the tensor core applies the 128B swizzle
+// XOR to the ABSOLUTE shared-memory address bits [7:9], exactly like TMA does when writing, so a descriptor may
+// start at any 128-byte row of a 1024-byte-aligned TMA tile (rows shifted by 1 or 2 pixels for the conv taps)
+// with base_offset = 0; setting base_offset = (addr >> 7) & 7 for such starts gives WRONG results.
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
   uint64_t d = (uint64_t)((saddr & 0x3FFFFu) >> 4);
   d |= (uint64_t)(1024u >> 4) << 32;
   d |= 1ull << 46;
-  d |= (uint64_t)((saddr >> 7) & 7u) << 49;
   d |= 2ull << 61;
   return d;
+}
+__device__ __forceinline__ uint64_t umma_desc_sw128_base_offset(uint32_t saddr) {   // kept for the experiment above
+  return umma_desc_sw128(saddr) | ((uint64_t)((saddr >> 7) & 7u) << 49);
 }
 // instruction descriptor: D fp32, A/B bf16, both K-major, M x N
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {

@@ -153,33 +153,48 @@ __global__ void __launch_bounds__(256) gn_silu_kernel(const __nv_bfloat16* __res
     b[j] = be;
   }
   const long base = (long)n * HW;
-  for (long p = (long)blockIdx.x * ppb + prow; p < HW; p += (long)gridDim.x * ppb) {
-    const long off = ((base + p) * C + chunk * 8);
-    const uint4 xv = __ldg(reinterpret_cast<const uint4*>(x + off));
-    const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w};
-    float y[8];
+  constexpr int U = 4;     // pixels in flight per thread: U independent 16-byte loads before any use
+  const long stride = (long)gridDim.x * ppb;
+  for (long p0 = (long)blockIdx.x * ppb + prow; p0 < HW; p0 += stride * U) {
+    uint4 xv[U], rv[U];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const float2 f = fd_unpack_bf16(xw[e]);
-      y[2 * e] = fd_silu(a[2 * e] * f.x + b[2 * e]);
-      y[2 * e + 1] = fd_silu(a[2 * e + 1] * f.y + b[2 * e + 1]);
-    }
-    if (residual != nullptr) {
-      const uint4 rv = __ldg(reinterpret_cast<const uint4*>(residual + off));
-      const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float2 f = fd_unpack_bf16(rw[e]);
-        y[2 * e] += f.x;
-        y[2 * e + 1] += f.y;
+    for (int u = 0; u < U; ++u) {
+      const long p = p0 + u * stride;
+      if (p < HW) {
+        const long off = ((base + p) * C + chunk * 8);
+        xv[u] = __ldcs(reinterpret_cast<const uint4*>(x + off));
+        if (residual != nullptr) rv[u] = __ldcs(reinterpret_cast<const uint4*>(residual + off));
       }
     }
-    uint4 o;
-    o.x = fd_pack_bf16(y[0], y[1]);
-    o.y = fd_pack_bf16(y[2], y[3]);
-    o.z = fd_pack_bf16(y[4], y[5]);
-    o.w = fd_pack_bf16(y[6], y[7]);
-    *reinterpret_cast<uint4*>(out + off) = o;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long p = p0 + u * stride;
+      if (p >= HW) break;
+      const long off = ((base + p) * C + chunk * 8);
+      const uint32_t xw[4] = {xv[u].x, xv[u].y, xv[u].z, xv[u].w};
+      float y[8];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 f = fd_unpack_bf16(xw[e]);
+        y[2 * e] = fd_silu(a[2 * e] * f.x + b[2 * e]);
+        y[2 * e + 1] = fd_silu(a[2 * e + 1] * f.y + b[2 * e + 1]);
+      }
+      if (residual != nullptr) {
+        const uint32_t rw[4] = {rv[u].x, rv[u].y, rv[u].z, rv[u].w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 f = fd_unpack_bf16(rw[e]);
+          y[2 * e] += f.x;
+          y[2 * e + 1] += f.y;
+        }
+      }
+      uint4 o;
+      o.x = fd_pack_bf16(y[0], y[1]);
+      o.y = fd_pack_bf16(y[2], y[3]);
+      o.z = fd_pack_bf16(y[4], y[5]);
+      o.w = fd_pack_bf16(y[6], y[7]);
+      *reinterpret_cast<uint4*>(out + off) = o;
+    }
   }
 }
 
@@ -416,7 +431,7 @@ int fd_gn_silu(const void* x, const double* gn_stats, const float* gamma, const 
   const int chunks = C / 8;
   const int ppb = 256 / chunks > 0 ? 256 / chunks : 1;
   FD_REQUIRE(chunks <= 256, "gn_silu: C too large");
-  long bx = ((long)HW + ppb - 1) / ppb;
+  long bx = ((long)HW + ppb * 4 - 1) / (ppb * 4);
   const long cap = (long)FD_NUM_SMS * 16 / N + 1;
   if (bx > cap) bx = cap;
   dim3 grid((unsigned)bx, (unsigned)N);
