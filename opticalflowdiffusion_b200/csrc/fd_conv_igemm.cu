@@ -247,8 +247,9 @@ int launch(const CUtensorMap& ma0, const CUtensorMap& ma1, const CUtensorMap& mb
 
 }  // namespace
 
-int fd_conv3x3_strip_launch(const void* src, const void* wpacked, const float* bias, void* out, double* gn_stats, int N,
-                            int H, int W, int base_offset_mode, cudaStream_t st);   // fd_conv_strip.cu
+int fd_conv3x3_strip_launch(const void* src0, int C0, const void* src1, int C1, const void* wpacked, const float* bias,
+                            void* out, double* gn_stats, int N, int H, int W, int base_offset_mode,
+                            cudaStream_t st);   // fd_conv_strip.cu
 
 extern "C" {
 
@@ -264,16 +265,18 @@ int fd_conv_igemm(const void* src0, int C0, const void* src1, int C1, const void
   FD_REQUIRE(mode == 0 || (C1 == 0 && gn_stats == nullptr), "conv_igemm: mode 1 takes one source and no statistics");
   FD_REQUIRE(KH >= 1 && KW >= 1 && KH * KW <= 64, "conv_igemm: bad kernel %dx%d", KH, KW);
   {
-    // full-resolution 64 -> 64 3x3 layers: rolling-strip kernel with resident weights (each input pixel is
-    // fetched from L2 once instead of nine times).  FD_CONV_STRIP=0 disables it.
+    // large-image {64,128} -> 64 3x3 layers: rolling-strip kernel (each input pixel is fetched from L2 once
+    // instead of nine times; the 64 -> 64 weights stay resident in shared memory).  FD_CONV_STRIP=0 disables it.
     static int strip_mode = -1;
     if (strip_mode < 0) {
       const char* e = getenv("FD_CONV_STRIP");
       strip_mode = e ? atoi(e) : 2;
     }
-    if (strip_mode > 0 && mode == 0 && KH == 3 && KW == 3 && pad_h == 1 && pad_w == 1 && C0 == 64 && C1 == 0 &&
-        Cout == 64 && residual == nullptr && W >= 128)
-      return fd_conv3x3_strip_launch(src0, wpacked, bias, out, gn_stats, N, H, W, strip_mode, (cudaStream_t)stream);
+    const bool chans_ok = (C0 == 64 && (C1 == 0 || C1 == 64)) || (C0 == 128 && C1 == 0);
+    if (strip_mode > 0 && mode == 0 && KH == 3 && KW == 3 && pad_h == 1 && pad_w == 1 && chans_ok && Cout == 64 &&
+        residual == nullptr && W >= 128)
+      return fd_conv3x3_strip_launch(src0, C0, src1, C1, wpacked, bias, out, gn_stats, N, H, W, strip_mode,
+                                     (cudaStream_t)stream);
   }
   static int sms = 0;
   if (sms == 0) {

@@ -10,6 +10,12 @@
 //     three strips at a 0/1/2-pixel (0/128/256-byte) offset -- no data is re-fetched or re-arranged;
 //   * so each output row costs one new 16.6 KB strip: ~13x less L2 traffic, the kernel becomes MMA/epilogue bound.
 // Warp roles and the epilogue (GroupNorm partial sums, swizzled smem + TMA store) are those of the generic kernel.
+//
+// 128 input channels (the skip-concat convs ups.3.x / final_res_block, and the upsample conv ups.2.3) run as TWO
+// passes of this kernel, one per 64-channel half: pass 1 writes the partial sum to `out`, pass 2 adds it back as
+// its residual (same tile reads then overwrites the same rows) and produces bias + statistics.  Streaming the
+// 144 KB of weights per tile instead was measured to be no faster than the generic kernel (chip-level L2->SM
+// bandwidth), while two resident-weight passes cost 0.75 ms instead of 1.09 ms.
 #include "fd_conv_epi.cuh"
 
 using namespace fdtc;
@@ -32,7 +38,10 @@ struct StripParams {
   int N, H, W;
   int wblocks, segs, seg_rows, total_items;
   int base_offset_mode;      // 2 (default): base_offset 0 -- correct; 1: (addr >> 7) & 7 -- measured WRONG, kept as an experiment
+  int c_off;                 // first input channel of this pass inside the source tensor (0 or 64)
+  int w_k0, w_kstride;       // weight K coordinate of tap t = t * w_kstride + w_k0
   const float* bias;
+  const __nv_bfloat16* residual;
   double* gn_stats;
 };
 
@@ -93,7 +102,8 @@ conv3x3_strip_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_co
     // ===================== TMA producer: weights once, then one strip per input row =====================
     if (lane == 0) {
       mbar_expect_tx(wfull_bar, kWBytes);
-      for (int tap = 0; tap < 9; ++tap) tma_load_2d(w_smem + tap * kWTapBytes, &map_w, wfull_bar, tap * kC, 0);
+      for (int tap = 0; tap < 9; ++tap)
+        tma_load_2d(w_smem + tap * kWTapBytes, &map_w, wfull_bar, tap * p.w_kstride + p.w_k0, 0);
       uint32_t seq = 0;
       for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
         int n, w0, ra, rb;
@@ -103,7 +113,7 @@ conv3x3_strip_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_co
           const uint32_t phase = (seq / kNS) & 1u;
           mbar_wait(empty_bar(slot), phase ^ 1u);
           mbar_expect_tx(full_bar(slot), kStripTx);
-          tma_load_5d(s_smem + slot * kStripBytes, &map_in, full_bar(slot), 0, w0 - 1, y, n, 0);
+          tma_load_5d(s_smem + slot * kStripBytes, &map_in, full_bar(slot), p.c_off, w0 - 1, y, n, 0);
         }
       }
     }
@@ -165,7 +175,7 @@ conv3x3_strip_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_co
     ec.s_stats = s_stats;
     ec.map_out = &map_out;
     ec.bias = p.bias;
-    ec.residual = nullptr;
+    ec.residual = p.residual;
     ec.gn_stats = p.gn_stats;
     ec.H = p.H; ec.W = p.W; ec.Cout = kC; ec.Wt = kTileW;
     int item = blockIdx.x, j = 0, n = 0, w0 = 0, ra = 0, rb = 0;
@@ -201,14 +211,17 @@ conv3x3_strip_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_co
 
 }  // namespace
 
-int fd_conv3x3_strip_launch(const void* src, const void* wpacked, const float* bias, void* out, double* gn_stats, int N,
-                            int H, int W, int base_offset_mode, cudaStream_t st) {
+// (C0, C1) in {(64, 0), (64, 64), (128, 0)}; Cout = 64; 3x3, pad 1
+int fd_conv3x3_strip_launch(const void* src0, int C0, const void* src1, int C1, const void* wpacked, const float* bias,
+                            void* out, double* gn_stats, int N, int H, int W, int base_offset_mode, cudaStream_t st) {
   static int sms = 0;
   if (sms == 0) {
     int dev = 0;
     FD_CUDA(cudaGetDevice(&dev));
     FD_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   }
+  const int cin = C0 + C1;
+  const int passes = cin / 64;
   StripParams p{};
   p.N = N; p.H = H; p.W = W;
   p.wblocks = (W + kTileW - 1) / kTileW;
@@ -220,43 +233,50 @@ int fd_conv3x3_strip_launch(const void* src, const void* wpacked, const float* b
     const double eff = (double)items / (double)(((items + sms - 1) / sms) * sms);
     if (eff > best_eff + 1e-9) { best_eff = eff; best_segs = segs; }
   }
-  p.segs = best_segs;
   p.seg_rows = (H + best_segs - 1) / best_segs;
   p.segs = (H + p.seg_rows - 1) / p.seg_rows;
   p.total_items = N * p.wblocks * p.segs;
   p.base_offset_mode = base_offset_mode;
-  p.bias = bias;
-  p.gn_stats = gn_stats;
-  CUtensorMap mi, mw, mo;
+  p.w_kstride = cin;
+  CUtensorMap mw, mo;
   {
-    const uint64_t dims[5] = {(uint64_t)kC, (uint64_t)W, (uint64_t)H, (uint64_t)N, 1};
-    const uint64_t str[4] = {(uint64_t)kC * 2, (uint64_t)W * kC * 2, (uint64_t)H * W * kC * 2, (uint64_t)N * H * W * kC * 2};
-    const uint32_t box_in[5] = {64, (uint32_t)kStripPx, 1, 1, 1};
+    const uint64_t dO[5] = {(uint64_t)kC, (uint64_t)W, (uint64_t)H, (uint64_t)N, 1};
+    const uint64_t sO[4] = {(uint64_t)kC * 2, (uint64_t)W * kC * 2, (uint64_t)H * W * kC * 2, (uint64_t)N * H * W * kC * 2};
     const uint32_t box_out[5] = {64, (uint32_t)kTileW, 1, 1, 1};
-    if (int e = make_tmap_bf16(&mi, src, 5, dims, str, box_in)) return e;
-    if (int e = make_tmap_bf16(&mo, out, 5, dims, str, box_out)) return e;
-  }
-  {
-    const uint64_t dims[2] = {(uint64_t)9 * kC, (uint64_t)kC};
-    const uint64_t str[1] = {(uint64_t)9 * kC * 2};
+    if (int e = make_tmap_bf16(&mo, out, 5, dO, sO, box_out)) return e;
+    const uint64_t K = (uint64_t)9 * cin;
+    const uint64_t dims[2] = {K, (uint64_t)kC};
+    const uint64_t str[1] = {K * 2};
     const uint32_t box[2] = {64, 64};
     if (int e = make_tmap_bf16(&mw, wpacked, 2, dims, str, box)) return e;
   }
   const int grid = p.total_items < sms ? p.total_items : sms;
-  static bool attr_set[2] = {false, false};
-  if (gn_stats != nullptr) {
-    if (!attr_set[1]) {
-      FD_CUDA(cudaFuncSetAttribute(conv3x3_strip_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-      attr_set[1] = true;
-    }
-    conv3x3_strip_kernel<8><<<grid, kThreads, kSmemBytes, st>>>(mi, mw, mo, p);
-  } else {
-    if (!attr_set[0]) {
-      FD_CUDA(cudaFuncSetAttribute(conv3x3_strip_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-      attr_set[0] = true;
-    }
-    conv3x3_strip_kernel<0><<<grid, kThreads, kSmemBytes, st>>>(mi, mw, mo, p);
+  static bool attr_set = false;
+  if (!attr_set) {
+    FD_CUDA(cudaFuncSetAttribute(conv3x3_strip_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    FD_CUDA(cudaFuncSetAttribute(conv3x3_strip_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    attr_set = true;
   }
-  FD_LAUNCH_CHECK();
+  for (int pass = 0; pass < passes; ++pass) {
+    const bool last = pass == passes - 1;
+    const bool from1 = pass == 1 && C1 > 0;                 // second half comes from the second tensor
+    const void* src = from1 ? src1 : src0;
+    const int csrc = from1 ? C1 : C0;
+    CUtensorMap mi;
+    const uint64_t d[5] = {(uint64_t)csrc, (uint64_t)W, (uint64_t)H, (uint64_t)N, 1};
+    const uint64_t sB[4] = {(uint64_t)csrc * 2, (uint64_t)W * csrc * 2, (uint64_t)H * W * csrc * 2, (uint64_t)N * H * W * csrc * 2};
+    const uint32_t box_in[5] = {64, (uint32_t)kStripPx, 1, 1, 1};
+    if (int e = make_tmap_bf16(&mi, src, 5, d, sB, box_in)) return e;
+    p.c_off = (pass == 1 && C1 == 0) ? 64 : 0;
+    p.w_k0 = pass * 64;
+    p.bias = last ? bias : nullptr;
+    p.residual = pass > 0 ? static_cast<const __nv_bfloat16*>(out) : nullptr;   // partial sum of the previous pass
+    p.gn_stats = last ? gn_stats : nullptr;
+    if (p.gn_stats != nullptr)
+      conv3x3_strip_kernel<8><<<grid, kThreads, kSmemBytes, st>>>(mi, mw, mo, p);
+    else
+      conv3x3_strip_kernel<0><<<grid, kThreads, kSmemBytes, st>>>(mi, mw, mo, p);
+    FD_LAUNCH_CHECK();
+  }
   return FD_OK;
 }

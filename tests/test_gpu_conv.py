@@ -83,6 +83,9 @@ CASES = [
     (2, (512, 256), 512, 4, 6, (3, 3), (1, 1), True, False, True),
     (1, (256,), 256, 33, 70, (3, 3), (1, 1), True, False, True),
     (2, (64,), 64, 220, 512, (3, 3), (1, 1), True, False, True),
+    (2, (64, 64), 64, 21, 256, (3, 3), (1, 1), True, False, True),      # rolling-strip kernel, two sources
+    (1, (128,), 64, 70, 200, (3, 3), (1, 1), True, False, False),       # rolling-strip kernel, 128-channel source, ragged W
+    (2, (64,), 64, 37, 130, (3, 3), (1, 1), True, False, True),         # ragged W: second column block is 2 pixels wide
 ]
 
 
