@@ -12,6 +12,8 @@
 // The coordinate / weight / accumulation sequence is written with explicit round-to-nearest
 // intrinsics in the exact order ATen's CPU grid_sampler_2d evaluates it, which makes the forward
 // bit-identical to the reference's CPU output (oracle/flowdiff_oracle.py:backwarp).
+#include <stdlib.h>
+
 #include "fd_common.cuh"
 
 namespace {
@@ -111,6 +113,15 @@ struct Vec<1> {
   __device__ __forceinline__ void store(float* p) const { *p = v[0]; }
 };
 template <>
+struct Vec<2> {
+  float v[2];
+  __device__ __forceinline__ void load(const float* p) {
+    const float2 t = __ldg(reinterpret_cast<const float2*>(p));
+    v[0] = t.x; v[1] = t.y;
+  }
+  __device__ __forceinline__ void store(float* p) const { *reinterpret_cast<float2*>(p) = make_float2(v[0], v[1]); }
+};
+template <>
 struct Vec<4> {
   float v[4];
   __device__ __forceinline__ void load(const float* p) {
@@ -136,7 +147,7 @@ __device__ __forceinline__ void item_to_byx(long item, int H, int W, int& b, int
 // forward: out, mask
 // ---------------------------------------------------------------------------------------------
 template <int VEC>
-__global__ void __launch_bounds__(256) backwarp_fwd_kernel(const float* __restrict__ image,
+__global__ void __launch_bounds__(256, VEC == 4 ? 2 : 4) backwarp_fwd_kernel(const float* __restrict__ image,
                                                            const float* __restrict__ flow,
                                                            float* __restrict__ out, float* __restrict__ mask,
                                                            int B, int C, BwGeom g, long items) {
@@ -171,7 +182,7 @@ __global__ void __launch_bounds__(256) backwarp_fwd_kernel(const float* __restri
 // backward of sum(out * gout): gimage (scatter), gflow (gather)
 // ---------------------------------------------------------------------------------------------
 template <int VEC>
-__global__ void __launch_bounds__(256) backwarp_bwd_kernel(const float* __restrict__ image,
+__global__ void __launch_bounds__(256, VEC == 4 ? 1 : 3) backwarp_bwd_kernel(const float* __restrict__ image,
                                                            const float* __restrict__ flow,
                                                            const float* __restrict__ gout,
                                                            float* __restrict__ gimage, float* __restrict__ gflow,
@@ -260,7 +271,7 @@ static int photo_grid(long items) {
 }
 
 template <int VEC>
-__global__ void __launch_bounds__(kPhotoThreads) photo_epe_fwd_kernel(
+__global__ void __launch_bounds__(kPhotoThreads, VEC == 4 ? 2 : 4) photo_epe_fwd_kernel(
     const float* __restrict__ frame1, const float* __restrict__ frame2, const float* __restrict__ flow,
     const float* __restrict__ flow_gt, float* __restrict__ partials, int B, int C, BwGeom g, long items) {
   __shared__ float red[3 * 32];
@@ -335,7 +346,7 @@ __global__ void __launch_bounds__(256) finalize_sums_kernel(const float* __restr
 }
 
 template <int VEC>
-__global__ void __launch_bounds__(256) photo_epe_bwd_kernel(
+__global__ void __launch_bounds__(256, VEC == 4 ? 1 : 3) photo_epe_bwd_kernel(
     const float* __restrict__ frame1, const float* __restrict__ frame2, const float* __restrict__ flow,
     const float* __restrict__ flow_gt, const float* __restrict__ sums, float g_photo, float g_epe,
     float* __restrict__ gflow, float* __restrict__ gframe2, int B, int C, BwGeom g, long items) {
@@ -431,6 +442,18 @@ static int stream_grid(long items, int threads) {
   return (int)blocks;
 }
 
+// pixels per thread: 4 or 2 consecutive pixels when W allows (FD_WARP_VEC overrides for experiments)
+static int pick_vec(int W) {
+  static int forced = -1;
+  if (forced < 0) {
+    const char* e = getenv("FD_WARP_VEC");
+    forced = e ? atoi(e) : 0;
+  }
+  int v = forced > 0 ? forced : 2;
+  while (v > 1 && W % v != 0) v >>= 1;
+  return v;
+}
+
 static int check_dims(int B, int C, int H, int W) {
   FD_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0, "backwarp: non-positive dimension B=%d C=%d H=%d W=%d", B, C, H, W);
   FD_REQUIRE((long)H * W < (1L << 31), "backwarp: plane too large");
@@ -447,13 +470,14 @@ int fd_backwarp_fwd(const float* image, const float* flow, float* out, float* ma
   FD_REQUIRE(image && flow && out, "backwarp_fwd: null pointer");
   cudaStream_t st = (cudaStream_t)stream;
   const BwGeom g = make_geom(H, W);
-  if (W % 4 == 0) {
-    const long items = (long)B * H * (W / 4);
+  const int vec = pick_vec(W);
+  const long items = (long)B * H * (W / vec);
+  if (vec == 4)
     backwarp_fwd_kernel<4><<<stream_grid(items, 256), 256, 0, st>>>(image, flow, out, mask, B, C, g, items);
-  } else {
-    const long items = (long)B * H * W;
+  else if (vec == 2)
+    backwarp_fwd_kernel<2><<<stream_grid(items, 256), 256, 0, st>>>(image, flow, out, mask, B, C, g, items);
+  else
     backwarp_fwd_kernel<1><<<stream_grid(items, 256), 256, 0, st>>>(image, flow, out, mask, B, C, g, items);
-  }
   FD_LAUNCH_CHECK();
   return FD_OK;
 }
@@ -465,19 +489,20 @@ int fd_backwarp_bwd(const float* image, const float* flow, const float* gout, fl
   cudaStream_t st = (cudaStream_t)stream;
   const BwGeom g = make_geom(H, W);
   if (gimage) FD_CUDA(cudaMemsetAsync(gimage, 0, sizeof(float) * (size_t)B * C * H * W, st));
-  if (W % 4 == 0) {
-    const long items = (long)B * H * (W / 4);
+  const int vec = pick_vec(W);
+  const long items = (long)B * H * (W / vec);
+  if (vec == 4)
     backwarp_bwd_kernel<4><<<stream_grid(items, 256), 256, 0, st>>>(image, flow, gout, gimage, gflow, B, C, g, items);
-  } else {
-    const long items = (long)B * H * W;
+  else if (vec == 2)
+    backwarp_bwd_kernel<2><<<stream_grid(items, 256), 256, 0, st>>>(image, flow, gout, gimage, gflow, B, C, g, items);
+  else
     backwarp_bwd_kernel<1><<<stream_grid(items, 256), 256, 0, st>>>(image, flow, gout, gimage, gflow, B, C, g, items);
-  }
   FD_LAUNCH_CHECK();
   return FD_OK;
 }
 
 size_t fd_photo_epe_workspace_floats(int B, int H, int W) {
-  const long items = (W % 4 == 0) ? (long)B * H * (W / 4) : (long)B * H * W;
+  const long items = (long)B * H * (W / pick_vec(W));
   return (size_t)photo_grid(items) * 3;
 }
 
@@ -487,16 +512,15 @@ int fd_backwarp_photo_epe_fwd(const float* frame1, const float* frame2, const fl
   FD_REQUIRE(frame1 && frame2 && flow && flow_gt && sums && partials, "photo_epe_fwd: null pointer");
   cudaStream_t st = (cudaStream_t)stream;
   const BwGeom g = make_geom(H, W);
-  int grid;
-  if (W % 4 == 0) {
-    const long items = (long)B * H * (W / 4);
-    grid = photo_grid(items);
+  const int vec = pick_vec(W);
+  const long items = (long)B * H * (W / vec);
+  const int grid = photo_grid(items);
+  if (vec == 4)
     photo_epe_fwd_kernel<4><<<grid, kPhotoThreads, 0, st>>>(frame1, frame2, flow, flow_gt, partials, B, C, g, items);
-  } else {
-    const long items = (long)B * H * W;
-    grid = photo_grid(items);
+  else if (vec == 2)
+    photo_epe_fwd_kernel<2><<<grid, kPhotoThreads, 0, st>>>(frame1, frame2, flow, flow_gt, partials, B, C, g, items);
+  else
     photo_epe_fwd_kernel<1><<<grid, kPhotoThreads, 0, st>>>(frame1, frame2, flow, flow_gt, partials, B, C, g, items);
-  }
   FD_LAUNCH_CHECK();
   finalize_sums_kernel<3><<<1, 256, 0, st>>>(partials, grid, sums, (float)((double)B * H * W), 3);
   FD_LAUNCH_CHECK();
@@ -511,15 +535,14 @@ int fd_backwarp_photo_epe_bwd(const float* frame1, const float* frame2, const fl
   cudaStream_t st = (cudaStream_t)stream;
   const BwGeom g = make_geom(H, W);
   if (gframe2) FD_CUDA(cudaMemsetAsync(gframe2, 0, sizeof(float) * (size_t)B * C * H * W, st));
-  if (W % 4 == 0) {
-    const long items = (long)B * H * (W / 4);
-    photo_epe_bwd_kernel<4><<<stream_grid(items, 256), 256, 0, st>>>(frame1, frame2, flow, flow_gt, sums, g_photo,
-                                                                     g_epe, gflow, gframe2, B, C, g, items);
-  } else {
-    const long items = (long)B * H * W;
-    photo_epe_bwd_kernel<1><<<stream_grid(items, 256), 256, 0, st>>>(frame1, frame2, flow, flow_gt, sums, g_photo,
-                                                                     g_epe, gflow, gframe2, B, C, g, items);
-  }
+  const int vec = pick_vec(W);
+  const long items = (long)B * H * (W / vec);
+  if (vec == 4)
+    photo_epe_bwd_kernel<4><<<stream_grid(items, 256), 256, 0, st>>>(frame1, frame2, flow, flow_gt, sums, g_photo, g_epe, gflow, gframe2, B, C, g, items);
+  else if (vec == 2)
+    photo_epe_bwd_kernel<2><<<stream_grid(items, 256), 256, 0, st>>>(frame1, frame2, flow, flow_gt, sums, g_photo, g_epe, gflow, gframe2, B, C, g, items);
+  else
+    photo_epe_bwd_kernel<1><<<stream_grid(items, 256), 256, 0, st>>>(frame1, frame2, flow, flow_gt, sums, g_photo, g_epe, gflow, gframe2, B, C, g, items);
   FD_LAUNCH_CHECK();
   return FD_OK;
 }
