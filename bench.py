@@ -84,6 +84,11 @@ def cpu_reference_step_seconds(steps: int, warmup: int):
     """Each step = ONE of the 50 DDIM steps of ONE 436x1024 sample (UNet forward + update); flows/s = 1/(50 t)."""
     from oracle import flowdiff_oracle as O
     from opticalflowdiffusion_b200.unet_params import UnetParams
+    # all host cores this process may use (torchrun pins OMP_NUM_THREADS=1 by default)
+    try:
+        torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
+    except Exception:  # noqa: BLE001
+        torch.set_num_threads(max(1, os.cpu_count() or 1))
     torch.manual_seed(0)
     sd = UnetParams(64, channels=5, out_dim=2).state_dict()
     sched = O.make_schedule(TIMESTEPS)
@@ -105,8 +110,8 @@ def cpu_reference_step_seconds(steps: int, warmup: int):
 def run_reference(args, rank: int):
     if rank != 0:
         return
-    threads = torch.get_num_threads()
     ts = cpu_reference_step_seconds(args.steps, min(args.warmup, 1))
+    threads = torch.get_num_threads()
     t = sum(ts) / len(ts)
     value = 1.0 / (DDIM_STEPS * t)
     sample = "one of the 50 DDIM steps of ONE 436x1024 sample per step (UNet forward + update), x50 extrapolated"
