@@ -49,6 +49,8 @@ SIGNATURES = {
     "fd_time_proj": (c_int, [_P, _P, _P, _P, _I, _I, _I, _P]),
     "fd_linattn_workspace_floats": (c_size_t, [_I, _I]),
     "fd_linattn": (c_int, [_P, _P, _P, _I, _I, _P]),
+    "fd_linattn_context": (c_int, [_P, _I, _P, _P, _I, _I, _P]),
+    "fd_linattn_apply_fused": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _P]),
     "fd_attention": (c_int, [_P, _P, _I, _I, _P]),
     "fd_final_conv": (c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "fd_nchw_to_nhwc_bf16": (c_int, [_P, _P, _I, _I, _I, _P]),

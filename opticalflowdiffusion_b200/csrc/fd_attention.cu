@@ -61,7 +61,7 @@ constexpr int kLaTileBytes = kLaTile * kLaRowBytes;
 constexpr int kLaSmemBytes = 2 * kLaTileBytes;
 constexpr int kLaPartial = 2 * kHidden + kHeads * kD * kD;    // m[128], s[128], ctx[4][32][32]
 
-__global__ void __launch_bounds__(256) linattn_partial_kernel(const __nv_bfloat16* __restrict__ qkv,
+__global__ void __launch_bounds__(256) linattn_partial_kernel(const __nv_bfloat16* __restrict__ kv, int row_stride,
                                                               float* __restrict__ partial, int HW, int chunk_px) {
   extern __shared__ __align__(16) uint8_t la_smem[];
   __shared__ float s_pmax[2][kHidden];
@@ -74,7 +74,7 @@ __global__ void __launch_bounds__(256) linattn_partial_kernel(const __nv_bfloat1
   const int g = lane >> 2, tq = lane & 3;
   const int head = warp & 3, mhalf = warp >> 2;
   const int ch = t & 127, phalf = t >> 7;          // exp pass: channel, pixel half
-  const __nv_bfloat16* base = qkv + (long)n * HW * kQkv + kHidden;   // k|v start at channel 128
+  const __nv_bfloat16* base = kv + (long)n * HW * row_stride;        // rows of [k(128) | v(128)], row_stride elements apart
   const uint32_t smem0 = smem_addr(la_smem);
   float acc[4][4];
 #pragma unroll
@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(256) linattn_partial_kernel(const __nv_bfloat1
       const int px = idx >> 5, q16 = idx & 31;
       const int p = p0 + px;
       const bool ok = p < p_end;
-      cp_async16(smem0 + buf * kLaTileBytes + px * kLaRowBytes + q16 * 16, base + (long)(ok ? p : p_begin) * kQkv + q16 * 8, ok);
+      cp_async16(smem0 + buf * kLaTileBytes + px * kLaRowBytes + q16 * 16, base + (long)(ok ? p : p_begin) * row_stride + q16 * 8, ok);
     }
     cp_async_commit();
   };
@@ -312,6 +312,234 @@ __global__ void __launch_bounds__(128) linattn_apply_kernel(const __nv_bfloat16*
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// pass 3, fully fused for C in {64, 128} (the full- and half-resolution LinearAttention blocks):
+//   out = LayerNorm_g2( W_out * (softmax_d(W_q * LayerNorm_g1(x)) . ctx) + b_out ) + x
+// i.e. PreNorm (:127-135), the q third of to_qkv (:234), the q softmax and context product (:237-242), to_out's
+// 1x1 conv and LayerNorm (:224-227) and the Residual add (:81-87) -- one read of x, one write of out.  Three
+// chained bf16 mma.sync GEMMs per 16-pixel warp tile with the intermediate results kept in registers
+// (accumulator fragments are re-packed as the next GEMM's A fragments); weights live in shared memory.
+// ------------------------------------------------------------------------------------------------
+template <int C>
+struct ApCfg {
+  static constexpr int XS = C + 8, WQS = C + 8, WOS = kHidden + 8;      // padded bf16 row strides
+  static constexpr int kXBytes = 64 * XS * 2, kWqBytes = kHidden * WQS * 2, kCtBytes = kHidden * kCtStride * 2;
+  static constexpr int kWoBytes = C * WOS * 2, kVecBytes = 3 * C * 4;
+  static constexpr int kSmem = kXBytes + kWqBytes + kCtBytes + kWoBytes + kVecBytes;
+};
+
+template <int C>
+__global__ void __launch_bounds__(128) linattn_apply_fused_kernel(
+    const __nv_bfloat16* __restrict__ x, const float* __restrict__ g1, const __nv_bfloat16* __restrict__ wq,
+    const __nv_bfloat16* __restrict__ ctx_t, const __nv_bfloat16* __restrict__ wout, const float* __restrict__ bias,
+    const float* __restrict__ g2, __nv_bfloat16* __restrict__ out, int HW, float eps) {
+  using A = ApCfg<C>;
+  constexpr int KS = C / 16;       // k-steps of the q GEMM
+  constexpr int NT = C / 8;        // n-tiles of the output GEMM
+  extern __shared__ __align__(16) uint8_t ap_smem[];
+  __nv_bfloat16* s_x = reinterpret_cast<__nv_bfloat16*>(ap_smem);
+  __nv_bfloat16* s_wq = reinterpret_cast<__nv_bfloat16*>(ap_smem + A::kXBytes);
+  __nv_bfloat16* s_ct = reinterpret_cast<__nv_bfloat16*>(ap_smem + A::kXBytes + A::kWqBytes);
+  __nv_bfloat16* s_wo = reinterpret_cast<__nv_bfloat16*>(ap_smem + A::kXBytes + A::kWqBytes + A::kCtBytes);
+  float* s_vec = reinterpret_cast<float*>(ap_smem + A::kXBytes + A::kWqBytes + A::kCtBytes + A::kWoBytes);
+  float* s_g1 = s_vec;
+  float* s_g2 = s_vec + C;
+  float* s_b = s_vec + 2 * C;
+  const int n = blockIdx.y;
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const int g = lane >> 2, tq = lane & 3;
+  // ---- stage weights once per block
+  for (int i = t; i < kHidden * (C / 8); i += 128) {          // Wq: [128][C], 16-byte granules
+    const int r = i / (C / 8), c8 = i % (C / 8);
+    *reinterpret_cast<uint4*>(s_wq + r * A::WQS + c8 * 8) = __ldg(reinterpret_cast<const uint4*>(wq + (long)r * C) + c8);
+  }
+  for (int i = t; i < C * (kHidden / 8); i += 128) {          // Wout: [C][128]
+    const int r = i / (kHidden / 8), c8 = i % (kHidden / 8);
+    *reinterpret_cast<uint4*>(s_wo + r * A::WOS + c8 * 8) = __ldg(reinterpret_cast<const uint4*>(wout + (long)r * kHidden) + c8);
+  }
+  for (int i = t; i < kHidden * (kD / 8); i += 128) {         // ctx^T: [head*32 + e][d]
+    const int r = i / (kD / 8), c8 = i % (kD / 8);
+    *reinterpret_cast<uint4*>(s_ct + r * kCtStride + c8 * 8) =
+        __ldg(reinterpret_cast<const uint4*>(ctx_t + ((long)n * kHidden + r) * kD) + c8);
+  }
+  for (int i = t; i < C; i += 128) {
+    s_g1[i] = g1[i];
+    s_g2[i] = g2[i];
+    s_b[i] = bias[i];
+  }
+  const __nv_bfloat16* xb = x + (long)n * HW * C;
+  __nv_bfloat16* ob = out + (long)n * HW * C;
+  const uint32_t sx = smem_addr(s_x);
+  const int ntiles = (HW + 63) / 64;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int p0 = tile * 64;
+    __syncthreads();       // previous tile written out; weights staged (first pass)
+    for (int i = t; i < 64 * (C / 8); i += 128) {
+      const int px = i / (C / 8), c8 = i % (C / 8);
+      const bool ok = p0 + px < HW;
+      cp_async16(sx + (px * A::XS + c8 * 8) * 2, xb + (long)(ok ? p0 + px : p0) * C + c8 * 8, ok);
+    }
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
+    // ---- (1) PreNorm LayerNorm over channels, in A-fragment layout
+    const int mi = lane >> 3, r8 = lane & 7;
+    uint32_t xa[KS][4];
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks)
+      ldmatrix_x4(xa[ks], sx + ((warp * 16 + (mi & 1) * 8 + r8) * A::XS + ks * 16 + (mi >> 1) * 8) * 2);
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+      const float2 a0 = fd_unpack_bf16(xa[ks][0]), a1 = fd_unpack_bf16(xa[ks][1]);
+      const float2 a2 = fd_unpack_bf16(xa[ks][2]), a3 = fd_unpack_bf16(xa[ks][3]);
+      s0 += a0.x + a0.y + a2.x + a2.y;
+      s1 += a1.x + a1.y + a3.x + a3.y;
+    }
+    s0 += __shfl_xor_sync(0xffffffffu, s0, 1); s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
+    s1 += __shfl_xor_sync(0xffffffffu, s1, 1); s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+    const float mu0 = s0 * (1.f / C), mu1 = s1 * (1.f / C);
+    float v0 = 0.f, v1 = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+      const float2 a0 = fd_unpack_bf16(xa[ks][0]), a1 = fd_unpack_bf16(xa[ks][1]);
+      const float2 a2 = fd_unpack_bf16(xa[ks][2]), a3 = fd_unpack_bf16(xa[ks][3]);
+      v0 += (a0.x - mu0) * (a0.x - mu0) + (a0.y - mu0) * (a0.y - mu0) + (a2.x - mu0) * (a2.x - mu0) + (a2.y - mu0) * (a2.y - mu0);
+      v1 += (a1.x - mu1) * (a1.x - mu1) + (a1.y - mu1) * (a1.y - mu1) + (a3.x - mu1) * (a3.x - mu1) + (a3.y - mu1) * (a3.y - mu1);
+    }
+    v0 += __shfl_xor_sync(0xffffffffu, v0, 1); v0 += __shfl_xor_sync(0xffffffffu, v0, 2);
+    v1 += __shfl_xor_sync(0xffffffffu, v1, 1); v1 += __shfl_xor_sync(0xffffffffu, v1, 2);
+    const float r0 = rsqrtf(v0 * (1.f / C) + eps), r1 = rsqrtf(v1 * (1.f / C) + eps);
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+      const int c = ks * 16 + 2 * tq;
+      const float ga = s_g1[c], gb = s_g1[c + 1], gc = s_g1[c + 8], gd = s_g1[c + 9];
+      const float2 a0 = fd_unpack_bf16(xa[ks][0]), a1 = fd_unpack_bf16(xa[ks][1]);
+      const float2 a2 = fd_unpack_bf16(xa[ks][2]), a3 = fd_unpack_bf16(xa[ks][3]);
+      xa[ks][0] = fd_pack_bf16((a0.x - mu0) * r0 * ga, (a0.y - mu0) * r0 * gb);
+      xa[ks][1] = fd_pack_bf16((a1.x - mu1) * r1 * ga, (a1.y - mu1) * r1 * gb);
+      xa[ks][2] = fd_pack_bf16((a2.x - mu0) * r0 * gc, (a2.y - mu0) * r0 * gd);
+      xa[ks][3] = fd_pack_bf16((a3.x - mu1) * r1 * gc, (a3.y - mu1) * r1 * gd);
+    }
+    // ---- (2) per head: q = y Wq^T, softmax over d, out_h = softmax(q) ctx_h ; collected as A fragments (K = 128)
+    uint32_t oa[8][4];
+#pragma unroll
+    for (int h = 0; h < kHeads; ++h) {
+      float q[4][4];
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) q[nt][j] = 0.f;
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+          const __nv_bfloat16* wr = s_wq + (h * kD + nt * 8 + g) * A::WQS + ks * 16 + 2 * tq;
+          mma_bf16(q[nt], xa[ks], *reinterpret_cast<const uint32_t*>(wr), *reinterpret_cast<const uint32_t*>(wr + 8));
+        }
+      float m0 = q[0][0], m1 = q[0][2];
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        m0 = fmaxf(m0, fmaxf(q[nt][0], q[nt][1]));
+        m1 = fmaxf(m1, fmaxf(q[nt][2], q[nt][3]));
+      }
+      m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1)); m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+      m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+      float e0 = 0.f, e1 = 0.f;
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        q[nt][0] = __expf(q[nt][0] - m0); q[nt][1] = __expf(q[nt][1] - m0);
+        q[nt][2] = __expf(q[nt][2] - m1); q[nt][3] = __expf(q[nt][3] - m1);
+        e0 += q[nt][0] + q[nt][1];
+        e1 += q[nt][2] + q[nt][3];
+      }
+      e0 += __shfl_xor_sync(0xffffffffu, e0, 1); e0 += __shfl_xor_sync(0xffffffffu, e0, 2);
+      e1 += __shfl_xor_sync(0xffffffffu, e1, 1); e1 += __shfl_xor_sync(0xffffffffu, e1, 2);
+      const float i0 = __fdividef(1.f, e0), i1 = __fdividef(1.f, e1);
+      float o[4][4];
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o[nt][j] = 0.f;
+#pragma unroll
+      for (int kk = 0; kk < 2; ++kk) {
+        uint32_t qa[4];
+        qa[0] = fd_pack_bf16(q[2 * kk][0] * i0, q[2 * kk][1] * i0);
+        qa[1] = fd_pack_bf16(q[2 * kk][2] * i1, q[2 * kk][3] * i1);
+        qa[2] = fd_pack_bf16(q[2 * kk + 1][0] * i0, q[2 * kk + 1][1] * i0);
+        qa[3] = fd_pack_bf16(q[2 * kk + 1][2] * i1, q[2 * kk + 1][3] * i1);
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+          const __nv_bfloat16* cr = s_ct + (h * kD + nt * 8 + g) * kCtStride + kk * 16 + 2 * tq;
+          mma_bf16(o[nt], qa, *reinterpret_cast<const uint32_t*>(cr), *reinterpret_cast<const uint32_t*>(cr + 8));
+        }
+      }
+#pragma unroll
+      for (int kk = 0; kk < 2; ++kk) {
+        oa[2 * h + kk][0] = fd_pack_bf16(o[2 * kk][0], o[2 * kk][1]);
+        oa[2 * h + kk][1] = fd_pack_bf16(o[2 * kk][2], o[2 * kk][3]);
+        oa[2 * h + kk][2] = fd_pack_bf16(o[2 * kk + 1][0], o[2 * kk + 1][1]);
+        oa[2 * h + kk][3] = fd_pack_bf16(o[2 * kk + 1][2], o[2 * kk + 1][3]);
+      }
+    }
+    // ---- (3) to_out 1x1 conv: o2 = out Wout^T + b
+    float o2[NT][4];
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      const float b0 = s_b[nt * 8 + 2 * tq], b1 = s_b[nt * 8 + 2 * tq + 1];
+      o2[nt][0] = b0; o2[nt][1] = b1; o2[nt][2] = b0; o2[nt][3] = b1;
+    }
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks)
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        const __nv_bfloat16* wr = s_wo + (nt * 8 + g) * A::WOS + ks * 16 + 2 * tq;
+        mma_bf16(o2[nt], oa[ks], *reinterpret_cast<const uint32_t*>(wr), *reinterpret_cast<const uint32_t*>(wr + 8));
+      }
+    // ---- (4) LayerNorm over the C outputs of each pixel, gain g2, + residual x
+    float t0 = 0.f, t1 = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      t0 += o2[nt][0] + o2[nt][1];
+      t1 += o2[nt][2] + o2[nt][3];
+    }
+    t0 += __shfl_xor_sync(0xffffffffu, t0, 1); t0 += __shfl_xor_sync(0xffffffffu, t0, 2);
+    t1 += __shfl_xor_sync(0xffffffffu, t1, 1); t1 += __shfl_xor_sync(0xffffffffu, t1, 2);
+    const float n0 = t0 * (1.f / C), n1 = t1 * (1.f / C);
+    float w0 = 0.f, w1 = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      w0 += (o2[nt][0] - n0) * (o2[nt][0] - n0) + (o2[nt][1] - n0) * (o2[nt][1] - n0);
+      w1 += (o2[nt][2] - n1) * (o2[nt][2] - n1) + (o2[nt][3] - n1) * (o2[nt][3] - n1);
+    }
+    w0 += __shfl_xor_sync(0xffffffffu, w0, 1); w0 += __shfl_xor_sync(0xffffffffu, w0, 2);
+    w1 += __shfl_xor_sync(0xffffffffu, w1, 1); w1 += __shfl_xor_sync(0xffffffffu, w1, 2);
+    const float q0 = rsqrtf(w0 * (1.f / C) + eps), q1 = rsqrtf(w1 * (1.f / C) + eps);
+    __nv_bfloat16* row0 = s_x + (warp * 16 + g) * A::XS;
+    __nv_bfloat16* row1 = row0 + 8 * A::XS;
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      const int c = nt * 8 + 2 * tq;
+      const float ga = s_g2[c], gb = s_g2[c + 1];
+      const float2 x0 = fd_unpack_bf16(*reinterpret_cast<const uint32_t*>(row0 + c));     // residual: this thread's own elements
+      const float2 x1 = fd_unpack_bf16(*reinterpret_cast<const uint32_t*>(row1 + c));
+      *reinterpret_cast<uint32_t*>(row0 + c) = fd_pack_bf16((o2[nt][0] - n0) * q0 * ga + x0.x, (o2[nt][1] - n0) * q0 * gb + x0.y);
+      *reinterpret_cast<uint32_t*>(row1 + c) = fd_pack_bf16((o2[nt][2] - n1) * q1 * ga + x1.x, (o2[nt][3] - n1) * q1 * gb + x1.y);
+    }
+    __syncwarp();
+    // ---- (5) the warp's 16 rows -> global, 16-byte coalesced
+#pragma unroll
+    for (int it = 0; it < (16 * (C / 8)) / 32; ++it) {
+      const int idx = it * 32 + lane;
+      const int px = idx / (C / 8), c8 = idx % (C / 8);
+      const int p = p0 + warp * 16 + px;
+      if (p < HW)
+        *reinterpret_cast<uint4*>(ob + (long)p * C + c8 * 8) =
+            *reinterpret_cast<const uint4*>(s_x + (warp * 16 + px) * A::XS + c8 * 8);
+    }
+  }
+}
+
 int la_chunks(int N, int HW, int* chunk_px) {
   // one wave: at most 3 resident blocks per SM (68 KB smem each) in total, chunk a multiple of the tile
   int want = (FD_NUM_SMS * 3) / N;
@@ -459,6 +687,27 @@ __global__ void __launch_bounds__(128) attention_kernel(const __nv_bfloat16* __r
   }
 }
 
+template <int C>
+int launch_apply_fused(const void* x, const float* g1, const void* wq, const void* ctx_t, const void* wout,
+                              const float* bias, const float* g2, void* out, int N, int HW, float eps, cudaStream_t st) {
+  using A = ApCfg<C>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    FD_CUDA(cudaFuncSetAttribute(linattn_apply_fused_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, A::kSmem));
+    attr_set = true;
+  }
+  int bx = (HW + 63) / 64;
+  const int per_sm = A::kSmem > 64 * 1024 ? 2 : 3;
+  const int cap = (FD_NUM_SMS * per_sm) / N > 0 ? (FD_NUM_SMS * per_sm) / N : 1;
+  if (bx > cap) bx = cap;
+  linattn_apply_fused_kernel<C><<<dim3(bx, N), 128, A::kSmem, st>>>(
+      static_cast<const __nv_bfloat16*>(x), g1, static_cast<const __nv_bfloat16*>(wq),
+      static_cast<const __nv_bfloat16*>(ctx_t), static_cast<const __nv_bfloat16*>(wout), bias, g2,
+      static_cast<__nv_bfloat16*>(out), HW, eps);
+  FD_LAUNCH_CHECK();
+  return FD_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -469,31 +718,54 @@ size_t fd_linattn_workspace_floats(int N, int HW) {
   return (size_t)N * chunks * kLaPartial + (size_t)N * kHeads * kD * kD / 2 + 16;
 }
 
-int fd_linattn(const void* qkv, void* out, float* workspace, int N, int HW, void* stream) {
-  FD_REQUIRE(qkv && out && workspace && N > 0 && HW > 0, "linattn: bad argument");
+// passes 1 + 2: kv rows = [k(128) | v(128)] bf16, row_stride elements apart -> ctx_t bf16 [N][4][32 e][32 d]
+// (softmax over pixels, /HW and the 32^-0.5 q scale folded in)
+int fd_linattn_context(const void* kv, int row_stride, void* ctx_t, float* workspace, int N, int HW, void* stream) {
+  FD_REQUIRE(kv && ctx_t && workspace && N > 0 && HW > 0 && row_stride >= 2 * kHidden && row_stride % 8 == 0,
+             "linattn_context: bad argument");
   cudaStream_t st = (cudaStream_t)stream;
   int px;
   const int chunks = la_chunks(N, HW, &px);
-  float* partial = workspace;
-  size_t off = (size_t)N * chunks * kLaPartial;
-  off = (off + 3) & ~(size_t)3;                                     // 16-byte aligned bf16 ctx^T
-  __nv_bfloat16* ctx_t = reinterpret_cast<__nv_bfloat16*>(workspace + off);
-  const __nv_bfloat16* q = static_cast<const __nv_bfloat16*>(qkv);
   static bool attr_set = false;
   if (!attr_set) {
     FD_CUDA(cudaFuncSetAttribute(linattn_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kLaSmemBytes));
     attr_set = true;
   }
-  linattn_partial_kernel<<<dim3(chunks, N), 256, kLaSmemBytes, st>>>(q, partial, HW, px);
+  linattn_partial_kernel<<<dim3(chunks, N), 256, kLaSmemBytes, st>>>(static_cast<const __nv_bfloat16*>(kv), row_stride,
+                                                                     workspace, HW, px);
   FD_LAUNCH_CHECK();
-  linattn_combine_kernel<<<N * kHeads, 1024, 0, st>>>(partial, ctx_t, chunks, 1.f / (float)HW);
+  linattn_combine_kernel<<<N * kHeads, 1024, 0, st>>>(workspace, static_cast<__nv_bfloat16*>(ctx_t), chunks,
+                                                      1.f / (float)HW);
   FD_LAUNCH_CHECK();
+  return FD_OK;
+}
+
+int fd_linattn(const void* qkv, void* out, float* workspace, int N, int HW, void* stream) {
+  FD_REQUIRE(qkv && out && workspace && N > 0 && HW > 0, "linattn: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  int px;
+  const int chunks = la_chunks(N, HW, &px);
+  size_t off = (size_t)N * chunks * kLaPartial;
+  off = (off + 3) & ~(size_t)3;                                     // 16-byte aligned bf16 ctx^T
+  __nv_bfloat16* ctx_t = reinterpret_cast<__nv_bfloat16*>(workspace + off);
+  const __nv_bfloat16* q = static_cast<const __nv_bfloat16*>(qkv);
+  if (int e = fd_linattn_context(q + kHidden, kQkv, ctx_t, workspace, N, HW, stream)) return e;
   int bx = (HW + 63) / 64;
   const int cap = (FD_NUM_SMS * 8 + N - 1) / N;
   if (bx > cap) bx = cap;
   linattn_apply_kernel<<<dim3(bx, N), 128, 0, st>>>(q, ctx_t, static_cast<__nv_bfloat16*>(out), HW);
   FD_LAUNCH_CHECK();
   return FD_OK;
+}
+
+int fd_linattn_apply_fused(const void* x, const float* g1, const void* wq, const void* ctx_t, const void* wout,
+                           const float* bias, const float* g2, void* out, int N, int HW, int C, float eps, void* stream) {
+  FD_REQUIRE(x && g1 && wq && ctx_t && wout && bias && g2 && out && N > 0 && HW > 0, "linattn_apply_fused: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (C == 64) return launch_apply_fused<64>(x, g1, wq, ctx_t, wout, bias, g2, out, N, HW, eps, st);
+  if (C == 128) return launch_apply_fused<128>(x, g1, wq, ctx_t, wout, bias, g2, out, N, HW, eps, st);
+  FD_REQUIRE(false, "linattn_apply_fused: C=%d not in {64, 128}", C);
+  return FD_EINVAL;
 }
 
 int fd_attention(const void* qkv, void* out, int N, int HW, void* stream) {

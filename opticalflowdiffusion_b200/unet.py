@@ -76,10 +76,25 @@ class Unet(UnetParams):
                 add(name + ".res_conv", rb.res_conv)
             self._resblocks.append((name, rb))
 
+        class _Slice:
+            """A row range of a conv weight, presented like a bias-free conv module."""
+
+            def __init__(self, conv, lo, hi):
+                self._conv, self._lo, self._hi, self.bias = conv, lo, hi, None
+
+            @property
+            def weight(self):
+                return self._conv.weight[self._lo:self._hi]
+
         def add_attn(name, res):
             fn = res.fn.fn
+            linear = isinstance(fn.to_out, torch.nn.Sequential)
             add(name + ".to_qkv", fn.to_qkv)
-            add(name + ".to_out", fn.to_out[0] if isinstance(fn.to_out, torch.nn.Sequential) else fn.to_out)
+            add(name + ".to_out", fn.to_out[0] if linear else fn.to_out)
+            if linear and fn.dim in (64, 128):
+                # fused LinearAttention tail (fd_linattn_apply_fused): k|v and q thirds of to_qkv are packed apart
+                add(name + ".to_kv", _Slice(fn.to_qkv, 128, 384))
+                add(name + ".to_q", _Slice(fn.to_qkv, 0, 128))
 
         self._resblocks = []
         add("init_conv", self.init_conv, kind=2)
@@ -193,6 +208,22 @@ class Unet(UnetParams):
     def _linear_attention(self, name: str, res, x: Tensor) -> Tensor:
         """Residual(PreNorm(LinearAttention)) (:81-87,127-135,229-244)."""
         n, h, w, c = x.shape
+        if (name + ".to_kv") in self._convs and not getattr(self, "_no_fused_attn", False):
+            # C in {64,128}: k|v through the conv engine, then ONE fused pass for q / softmax / context / to_out /
+            # LayerNorm / residual (the q third of to_qkv and to_out run as in-kernel GEMMs)
+            y = self._chan_ln(x, res.fn.norm.g)
+            kv = self._conv(name + ".to_kv", y)
+            del y
+            ws = torch.empty(self._lib.fd_linattn_workspace_floats(n, h * w), device=x.device, dtype=torch.float32)
+            ctx_t = torch.empty(n, 4, 32, 32, device=x.device, dtype=BF16)
+            _lib.check(self._lib.fd_linattn_context(_lib.ptr(kv), 256, _lib.ptr(ctx_t), _lib.ptr(ws), n, h * w, self._st))
+            out = torch.empty_like(x)
+            to_out = self._convs[name + ".to_out"]
+            _lib.check(self._lib.fd_linattn_apply_fused(
+                _lib.ptr(x), _lib.ptr(res.fn.norm.g), _lib.ptr(self._convs[name + ".to_q"].w), _lib.ptr(ctx_t),
+                _lib.ptr(to_out.w), _lib.ptr(to_out.bias), _lib.ptr(res.fn.fn.to_out[1].g), _lib.ptr(out), n, h * w, c,
+                self.LN_EPS, self._st))
+            return out
         y = self._chan_ln(x, res.fn.norm.g)
         qkv = self._conv(name + ".to_qkv", y)
         att = torch.empty(n, h, w, 128, device=x.device, dtype=BF16)

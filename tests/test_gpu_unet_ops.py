@@ -221,3 +221,36 @@ def test_full_attention_core(L, hw):
     L.check(lib.fd_attention(L.ptr(qh), L.ptr(out), N, H * W, L.stream()))
     ref = _attn_ref(qkv, False)
     assert rel_err(nchw(out), ref) < 2e-2
+
+
+@pytest.mark.parametrize("C", [64, 128])
+def test_linear_attention_block_fused(L, C):
+    """fd_linattn_context + fd_linattn_apply_fused == the oracle's Residual(PreNorm(LinearAttention)) block."""
+    lib = L.load()
+    g = torch.Generator().manual_seed(C)
+    N, H, W = 2, 9, 14          # 126 pixels: ragged last tile
+    x = (torch.randn(N, C, H, W, generator=g) * 1.5).to(BF).float()
+    sd = {"norm.g": torch.randn(1, C, 1, 1, generator=g) * 0.3 + 1,
+          "fn.to_qkv.weight": torch.randn(384, C, 1, 1, generator=g) / C ** 0.5,
+          "fn.to_out.0.weight": torch.randn(C, 128, 1, 1, generator=g) / 128 ** 0.5 * 30,
+          "fn.to_out.0.bias": torch.randn(C, generator=g) * 0.1,
+          "fn.to_out.1.g": torch.randn(1, C, 1, 1, generator=g) * 0.3 + 1}
+    sdq = {k: (v.to(BF).float() if "weight" in k else v) for k, v in sd.items()}
+    ref = O._linear_attention(sdq, "", x)
+    xc = nhwc(x.cuda())
+    g1, g2, b = sd["norm.g"].cuda(), sd["fn.to_out.1.g"].cuda(), sd["fn.to_out.0.bias"].cuda()
+    wqkv = sd["fn.to_qkv.weight"].reshape(384, C).to(BF).cuda()
+    wq, wkv = wqkv[:128].contiguous(), wqkv[128:].contiguous()
+    wout = sd["fn.to_out.0.weight"].reshape(C, 128).to(BF).cuda().contiguous()
+    y = torch.empty_like(xc)
+    L.check(lib.fd_chan_layernorm(L.ptr(xc), L.ptr(g1), None, L.ptr(y), N * H * W, C, 1e-5, L.stream()))
+    kv = torch.empty(N, H, W, 256, device="cuda", dtype=BF)
+    L.check(lib.fd_conv_igemm(L.ptr(y), C, None, 0, L.ptr(wkv), None, None, L.ptr(kv), None, N, H, W, 256, 1, 1, 0, 0, 0,
+                              L.stream()))
+    ws = torch.empty(lib.fd_linattn_workspace_floats(N, H * W), device="cuda")
+    ctx_t = torch.empty(N, 4, 32, 32, device="cuda", dtype=BF)
+    L.check(lib.fd_linattn_context(L.ptr(kv), 256, L.ptr(ctx_t), L.ptr(ws), N, H * W, L.stream()))
+    out = torch.empty_like(xc)
+    L.check(lib.fd_linattn_apply_fused(L.ptr(xc), L.ptr(g1), L.ptr(wq), L.ptr(ctx_t), L.ptr(wout), L.ptr(b), L.ptr(g2),
+                                       L.ptr(out), N, H * W, C, 1e-5, L.stream()))
+    assert rel_err(nchw(out).cpu(), ref) < 2e-2
