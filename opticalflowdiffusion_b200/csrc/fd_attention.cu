@@ -61,19 +61,15 @@ constexpr int kLaTileBytes = kLaTile * kLaRowBytes;
 constexpr int kLaSmemBytes = 2 * kLaTileBytes;
 constexpr int kLaPartial = 2 * kHidden + kHeads * kD * kD;    // m[128], s[128], ctx[4][32][32]
 
-__global__ void __launch_bounds__(256) linattn_partial_kernel(const __nv_bfloat16* __restrict__ kv, int row_stride,
+__global__ void __launch_bounds__(256, 3) linattn_partial_kernel(const __nv_bfloat16* __restrict__ kv, int row_stride,
                                                               float* __restrict__ partial, int HW, int chunk_px) {
   extern __shared__ __align__(16) uint8_t la_smem[];
-  __shared__ float s_pmax[2][kHidden];
-  __shared__ float s_fac[kHidden];
-  __shared__ float s_sum1[kHidden];
   const int n = blockIdx.y, chunk = blockIdx.x;
   const int p_begin = chunk * chunk_px;
   const int p_end = min(HW, p_begin + chunk_px);
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
   const int g = lane >> 2, tq = lane & 3;
-  const int head = warp & 3, mhalf = warp >> 2;
-  const int ch = t & 127, phalf = t >> 7;          // exp pass: channel, pixel half
+  const int head = warp & 3, mhalf = warp >> 2;      // this warp owns ctx rows d = mhalf*16 + {g, g+8} of `head`
   const __nv_bfloat16* base = kv + (long)n * HW * row_stride;        // rows of [k(128) | v(128)], row_stride elements apart
   const uint32_t smem0 = smem_addr(la_smem);
   float acc[4][4];
@@ -81,7 +77,9 @@ __global__ void __launch_bounds__(256) linattn_partial_kernel(const __nv_bfloat1
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-  float m_run = -INFINITY, s_run = 0.f;
+  // running max / sum of exp of the two k channels (rows) this thread sees; the 4 lanes of a quad hold the same max
+  // and disjoint partial sums
+  float m0 = -INFINITY, m1 = -INFINITY, s0 = 0.f, s1 = 0.f;
 
   auto issue_tile = [&](int p0, int buf) {
     // 64 pixels x 32 granules of 16 B (k|v = 512 B per pixel): 8 cp.async per thread
@@ -98,6 +96,7 @@ __global__ void __launch_bounds__(256) linattn_partial_kernel(const __nv_bfloat1
 
   const int ntiles = (p_end - p_begin + kLaTile - 1) / kLaTile;
   if (ntiles > 0) issue_tile(p_begin, 0);
+  const int mi = lane >> 3, r = lane & 7;       // ldmatrix: lanes 8*mi..8*mi+7 address matrix mi, row r
   for (int ti = 0; ti < ntiles; ++ti) {
     const int buf = ti & 1;
     const int p0 = p_begin + ti * kLaTile;
@@ -108,67 +107,76 @@ __global__ void __launch_bounds__(256) linattn_partial_kernel(const __nv_bfloat1
       cp_async_wait<0>();
     }
     __syncthreads();
-    uint8_t* tile = la_smem + buf * kLaTileBytes;
-    // ---- per-channel max over this thread's 32 pixels
-    const int px_lo = phalf * 32;
-    float tmax = -INFINITY;
-#pragma unroll 8
-    for (int i = 0; i < 32; ++i) {
-      const int px = px_lo + i;
-      if (p0 + px < p_end)
-        tmax = fmaxf(tmax, __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(tile + px * kLaRowBytes + ch * 2)));
-    }
-    s_pmax[phalf][ch] = tmax;
-    __syncthreads();
-    const float m_new = fmaxf(m_run, fmaxf(s_pmax[0][ch], s_pmax[1][ch]));
-    const float fac = (m_run == -INFINITY) ? 0.f : __expf(m_run - m_new);
-    float sum = 0.f;
-#pragma unroll 8
-    for (int i = 0; i < 32; ++i) {
-      const int px = px_lo + i;
-      __nv_bfloat16* kp = reinterpret_cast<__nv_bfloat16*>(tile + px * kLaRowBytes + ch * 2);
-      float e = 0.f;
-      if (p0 + px < p_end) e = __expf(__bfloat162float(*kp) - m_new);
-      const __nv_bfloat16 eb = __float2bfloat16(e);
-      *kp = eb;
-      sum += __bfloat162float(eb);          // the normaliser sums exactly what the GEMM consumes
-    }
-    s_run = s_run * fac + sum;
-    m_run = m_new;
-    if (phalf == 0) s_fac[ch] = fac;
-    __syncthreads();
-    // ---- rescale + tensor-core accumulate: warp = (head, 16 rows of d), N = 32 e, K = 64 pixels
-    {
-      const float f0 = s_fac[head * kD + mhalf * 16 + g], f1 = s_fac[head * kD + mhalf * 16 + g + 8];
+    const uint32_t tb = smem0 + buf * kLaTileBytes;
+    const int nvalid = p_end - p0;                 // >= 64 except in the chunk's last tile
+    // ---- raw k as A fragments (d x pixel): m0 (px 0-7, d 0-7), m1 (px 0-7, d 8-15), m2 (px 8-15, d 0-7), m3 (px 8-15, d 8-15)
+    uint32_t ka[kLaTile / 16][4];
 #pragma unroll
-      for (int nt = 0; nt < 4; ++nt) {
-        acc[nt][0] *= f0; acc[nt][1] *= f0; acc[nt][2] *= f1; acc[nt][3] *= f1;
-      }
-      const uint32_t tb = smem0 + buf * kLaTileBytes;
-      const int mi = lane >> 3, r = lane & 7;       // ldmatrix: lanes 8*mi..8*mi+7 address matrix mi, row r
+    for (int ks = 0; ks < kLaTile / 16; ++ks)
+      ldmatrix_x4_trans(ka[ks], tb + (ks * 16 + (mi >> 1) * 8 + r) * kLaRowBytes + (head * kD + mhalf * 16 + (mi & 1) * 8) * 2);
+    // element (ks, reg, half): row d = g (+8 for reg 1,3), pixel = ks*16 + 2*tq + half (+8 for reg 2,3)
+    float t0 = -INFINITY, t1 = -INFINITY;
 #pragma unroll
-      for (int ks = 0; ks < kLaTile / 16; ++ks) {
-        uint32_t a[4], b01[4], b23[4];
-        // A (trans): m0 (px 0-7, d 0-7), m1 (px 0-7, d 8-15), m2 (px 8-15, d 0-7), m3 (px 8-15, d 8-15)
-        ldmatrix_x4_trans(a, tb + (ks * 16 + (mi >> 1) * 8 + r) * kLaRowBytes + (head * kD + mhalf * 16 + (mi & 1) * 8) * 2);
-        // B (trans): m0 (px 0-7, e 0-7) m1 (px 8-15, e 0-7) m2 (px 0-7, e 8-15) m3 (px 8-15, e 8-15)
-        const uint32_t vb = tb + (ks * 16 + (mi & 1) * 8 + r) * kLaRowBytes + (kHidden + head * kD + (mi >> 1) * 8) * 2;
-        ldmatrix_x4_trans(b01, vb);
-        ldmatrix_x4_trans(b23, vb + 16 * 2);
-        mma_bf16(acc[0], a, b01[0], b01[1]);
-        mma_bf16(acc[1], a, b01[2], b01[3]);
-        mma_bf16(acc[2], a, b23[0], b23[1]);
-        mma_bf16(acc[3], a, b23[2], b23[3]);
+    for (int ks = 0; ks < kLaTile / 16; ++ks) {
+#pragma unroll
+      for (int rg = 0; rg < 4; ++rg) {
+        const float2 f = fd_unpack_bf16(ka[ks][rg]);
+        const int px = ks * 16 + 2 * tq + (rg >> 1) * 8;
+        const float a = px < nvalid ? f.x : -INFINITY, b = px + 1 < nvalid ? f.y : -INFINITY;
+        if (rg & 1) t1 = fmaxf(t1, fmaxf(a, b)); else t0 = fmaxf(t0, fmaxf(a, b));
       }
     }
-    __syncthreads();     // tile buffer may be refilled two iterations later; s_pmax / s_fac reused next iteration
+    t0 = fmaxf(t0, __shfl_xor_sync(0xffffffffu, t0, 1)); t0 = fmaxf(t0, __shfl_xor_sync(0xffffffffu, t0, 2));
+    t1 = fmaxf(t1, __shfl_xor_sync(0xffffffffu, t1, 1)); t1 = fmaxf(t1, __shfl_xor_sync(0xffffffffu, t1, 2));
+    const float mn0 = fmaxf(m0, t0), mn1 = fmaxf(m1, t1);
+    const float f0 = (m0 == -INFINITY) ? 0.f : __expf(m0 - mn0), f1 = (m1 == -INFINITY) ? 0.f : __expf(m1 - mn1);
+    m0 = mn0;
+    m1 = mn1;
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      acc[nt][0] *= f0; acc[nt][1] *= f0; acc[nt][2] *= f1; acc[nt][3] *= f1;
+    }
+    float e0 = 0.f, e1 = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < kLaTile / 16; ++ks) {
+#pragma unroll
+      for (int rg = 0; rg < 4; ++rg) {
+        const float2 f = fd_unpack_bf16(ka[ks][rg]);
+        const int px = ks * 16 + 2 * tq + (rg >> 1) * 8;
+        const float mm = (rg & 1) ? mn1 : mn0;
+        const float a = px < nvalid ? __expf(f.x - mm) : 0.f, b = px + 1 < nvalid ? __expf(f.y - mm) : 0.f;
+        const uint32_t pk = fd_pack_bf16(a, b);
+        ka[ks][rg] = pk;
+        const float2 rq = fd_unpack_bf16(pk);     // the normaliser sums exactly what the GEMM consumes
+        if (rg & 1) e1 += rq.x + rq.y; else e0 += rq.x + rq.y;
+      }
+    }
+    s0 = s0 * f0 + e0;
+    s1 = s1 * f1 + e1;
+    // ---- ctx += exp(k) v^T : K = 64 pixels, N = 32 e
+#pragma unroll
+    for (int ks = 0; ks < kLaTile / 16; ++ks) {
+      uint32_t b01[4], b23[4];
+      // B (trans): m0 (px 0-7, e 0-7) m1 (px 8-15, e 0-7) m2 (px 0-7, e 8-15) m3 (px 8-15, e 8-15)
+      const uint32_t vb = tb + (ks * 16 + (mi & 1) * 8 + r) * kLaRowBytes + (kHidden + head * kD + (mi >> 1) * 8) * 2;
+      ldmatrix_x4_trans(b01, vb);
+      ldmatrix_x4_trans(b23, vb + 16 * 2);
+      mma_bf16(acc[0], ka[ks], b01[0], b01[1]);
+      mma_bf16(acc[1], ka[ks], b01[2], b01[3]);
+      mma_bf16(acc[2], ka[ks], b23[0], b23[1]);
+      mma_bf16(acc[3], ka[ks], b23[2], b23[3]);
+    }
+    __syncthreads();     // this buffer is refilled by the prefetch of the next iteration
   }
+  s0 += __shfl_xor_sync(0xffffffffu, s0, 1); s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
+  s1 += __shfl_xor_sync(0xffffffffu, s1, 1); s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
   float* out = partial + ((long)n * gridDim.x + chunk) * kLaPartial;
-  if (phalf == 1) s_sum1[ch] = s_run;
-  __syncthreads();
-  if (phalf == 0) {
-    out[ch] = m_run;
-    out[kHidden + ch] = s_run + s_sum1[ch];
+  if (tq == 0) {
+    const int d0 = head * kD + mhalf * 16 + g;
+    out[d0] = m0;
+    out[d0 + 8] = m1;
+    out[kHidden + d0] = s0;
+    out[kHidden + d0 + 8] = s1;
   }
   float* c = out + 2 * kHidden + (head * kD + mhalf * 16) * kD;
 #pragma unroll
@@ -322,18 +330,21 @@ __global__ void __launch_bounds__(128) linattn_apply_kernel(const __nv_bfloat16*
 // ------------------------------------------------------------------------------------------------
 template <int C>
 struct ApCfg {
+  static constexpr int NW = C == 64 ? 8 : 4;                             // warps per block (16 pixels each)
+  static constexpr int TP = NW * 16;                                     // pixels per tile
   static constexpr int XS = C + 8, WQS = C + 8, WOS = kHidden + 8;      // padded bf16 row strides
-  static constexpr int kXBytes = 64 * XS * 2, kWqBytes = kHidden * WQS * 2, kCtBytes = kHidden * kCtStride * 2;
+  static constexpr int kXBytes = TP * XS * 2, kWqBytes = kHidden * WQS * 2, kCtBytes = kHidden * kCtStride * 2;
   static constexpr int kWoBytes = C * WOS * 2, kVecBytes = 3 * C * 4;
   static constexpr int kSmem = kXBytes + kWqBytes + kCtBytes + kWoBytes + kVecBytes;
 };
 
 template <int C>
-__global__ void __launch_bounds__(128) linattn_apply_fused_kernel(
+__global__ void __launch_bounds__(ApCfg<C>::NW * 32) linattn_apply_fused_kernel(
     const __nv_bfloat16* __restrict__ x, const float* __restrict__ g1, const __nv_bfloat16* __restrict__ wq,
     const __nv_bfloat16* __restrict__ ctx_t, const __nv_bfloat16* __restrict__ wout, const float* __restrict__ bias,
     const float* __restrict__ g2, __nv_bfloat16* __restrict__ out, int HW, float eps) {
   using A = ApCfg<C>;
+  constexpr int NTH = A::NW * 32, TP = A::TP;
   constexpr int KS = C / 16;       // k-steps of the q GEMM
   constexpr int NT = C / 8;        // n-tiles of the output GEMM
   extern __shared__ __align__(16) uint8_t ap_smem[];
@@ -349,20 +360,20 @@ __global__ void __launch_bounds__(128) linattn_apply_fused_kernel(
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
   const int g = lane >> 2, tq = lane & 3;
   // ---- stage weights once per block
-  for (int i = t; i < kHidden * (C / 8); i += 128) {          // Wq: [128][C], 16-byte granules
+  for (int i = t; i < kHidden * (C / 8); i += NTH) {          // Wq: [128][C], 16-byte granules
     const int r = i / (C / 8), c8 = i % (C / 8);
     *reinterpret_cast<uint4*>(s_wq + r * A::WQS + c8 * 8) = __ldg(reinterpret_cast<const uint4*>(wq + (long)r * C) + c8);
   }
-  for (int i = t; i < C * (kHidden / 8); i += 128) {          // Wout: [C][128]
+  for (int i = t; i < C * (kHidden / 8); i += NTH) {          // Wout: [C][128]
     const int r = i / (kHidden / 8), c8 = i % (kHidden / 8);
     *reinterpret_cast<uint4*>(s_wo + r * A::WOS + c8 * 8) = __ldg(reinterpret_cast<const uint4*>(wout + (long)r * kHidden) + c8);
   }
-  for (int i = t; i < kHidden * (kD / 8); i += 128) {         // ctx^T: [head*32 + e][d]
+  for (int i = t; i < kHidden * (kD / 8); i += NTH) {         // ctx^T: [head*32 + e][d]
     const int r = i / (kD / 8), c8 = i % (kD / 8);
     *reinterpret_cast<uint4*>(s_ct + r * kCtStride + c8 * 8) =
         __ldg(reinterpret_cast<const uint4*>(ctx_t + ((long)n * kHidden + r) * kD) + c8);
   }
-  for (int i = t; i < C; i += 128) {
+  for (int i = t; i < C; i += NTH) {
     s_g1[i] = g1[i];
     s_g2[i] = g2[i];
     s_b[i] = bias[i];
@@ -370,11 +381,11 @@ __global__ void __launch_bounds__(128) linattn_apply_fused_kernel(
   const __nv_bfloat16* xb = x + (long)n * HW * C;
   __nv_bfloat16* ob = out + (long)n * HW * C;
   const uint32_t sx = smem_addr(s_x);
-  const int ntiles = (HW + 63) / 64;
+  const int ntiles = (HW + TP - 1) / TP;
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const int p0 = tile * 64;
+    const int p0 = tile * TP;
     __syncthreads();       // previous tile written out; weights staged (first pass)
-    for (int i = t; i < 64 * (C / 8); i += 128) {
+    for (int i = t; i < TP * (C / 8); i += NTH) {
       const int px = i / (C / 8), c8 = i % (C / 8);
       const bool ok = p0 + px < HW;
       cp_async16(sx + (px * A::XS + c8 * 8) * 2, xb + (long)(ok ? p0 + px : p0) * C + c8 * 8, ok);
@@ -696,11 +707,11 @@ int launch_apply_fused(const void* x, const float* g1, const void* wq, const voi
     FD_CUDA(cudaFuncSetAttribute(linattn_apply_fused_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, A::kSmem));
     attr_set = true;
   }
-  int bx = (HW + 63) / 64;
-  const int per_sm = A::kSmem > 64 * 1024 ? 2 : 3;
+  int bx = (HW + A::TP - 1) / A::TP;
+  const int per_sm = A::kSmem > 76 * 1024 ? 2 : 3;
   const int cap = (FD_NUM_SMS * per_sm) / N > 0 ? (FD_NUM_SMS * per_sm) / N : 1;
   if (bx > cap) bx = cap;
-  linattn_apply_fused_kernel<C><<<dim3(bx, N), 128, A::kSmem, st>>>(
+  linattn_apply_fused_kernel<C><<<dim3(bx, N), A::NW * 32, A::kSmem, st>>>(
       static_cast<const __nv_bfloat16*>(x), g1, static_cast<const __nv_bfloat16*>(wq),
       static_cast<const __nv_bfloat16*>(ctx_t), static_cast<const __nv_bfloat16*>(wout), bias, g2,
       static_cast<__nv_bfloat16*>(out), HW, eps);
