@@ -564,26 +564,29 @@ int la_chunks(int N, int HW, int* chunk_px) {
 
 // ------------------------------------------------------------------------------------------------
 // full attention (flash-style), mma.sync m16n8k16 bf16
+//   block = 8 warps x 16 queries, K/V tiles of 64 keys double-buffered with cp.async (one __syncthreads per tile);
+//   Q fragments live in registers, K fragments come from ldmatrix, V fragments from ldmatrix.trans (V stays
+//   row-major [key][d] in smem), S / P never leave registers; online softmax in the exp2 domain.
 // ------------------------------------------------------------------------------------------------
-constexpr int kBQ = 64, kBK = 64;
-constexpr int kKStride = 40;   // bf16 per K row (32 + 8 pad): conflict-free fragment loads
-constexpr int kVStride = 72;   // bf16 per V^T row (64 + 8 pad)
+constexpr int kBQ = 128, kBK = 64;
+constexpr int kKvStride = kD + 8;                  // bf16 per K / V row: 80 B, conflict-free ldmatrix
+constexpr int kKvTile = kBK * kKvStride;           // elements per K (or V) tile
 
-__global__ void __launch_bounds__(128) attention_kernel(const __nv_bfloat16* __restrict__ qkv,
+__global__ void __launch_bounds__(256) attention_kernel(const __nv_bfloat16* __restrict__ qkv,
                                                         __nv_bfloat16* __restrict__ out, int HW, float scale_log2) {
-  __shared__ __align__(16) __nv_bfloat16 s_k[kBK * kKStride];
-  __shared__ __align__(16) __nv_bfloat16 s_vt[kD * kVStride];
+  __shared__ __align__(16) __nv_bfloat16 s_k[2][kKvTile];
+  __shared__ __align__(16) __nv_bfloat16 s_v[2][kKvTile];
   const int n = blockIdx.z, head = blockIdx.y;
   const int q0 = blockIdx.x * kBQ;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int g = lane >> 2, t = lane & 3;
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const int g = lane >> 2, tq = lane & 3;
   const __nv_bfloat16* base = qkv + (long)n * HW * kQkv;
   const int row0 = q0 + warp * 16 + g, row1 = row0 + 8;
 
   uint32_t qa[2][4];
 #pragma unroll
   for (int kk = 0; kk < 2; ++kk) {
-    const int c0 = head * kD + kk * 16 + 2 * t;
+    const int c0 = head * kD + kk * 16 + 2 * tq;
     qa[kk][0] = row0 < HW ? __ldg(reinterpret_cast<const uint32_t*>(base + (long)row0 * kQkv + c0)) : 0u;
     qa[kk][1] = row1 < HW ? __ldg(reinterpret_cast<const uint32_t*>(base + (long)row1 * kQkv + c0)) : 0u;
     qa[kk][2] = row0 < HW ? __ldg(reinterpret_cast<const uint32_t*>(base + (long)row0 * kQkv + c0 + 8)) : 0u;
@@ -596,45 +599,47 @@ __global__ void __launch_bounds__(128) attention_kernel(const __nv_bfloat16* __r
     for (int i = 0; i < 4; ++i) o[dt][i] = 0.f;
   float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
 
-  for (int k0 = 0; k0 < HW; k0 += kBK) {
-    // stage K (row-major, padded) and V^T
+  const uint32_t sk = smem_addr(&s_k[0][0]), sv = smem_addr(&s_v[0][0]);
+  auto issue_tile = [&](int k0, int buf) {
+    // 64 keys x (4 + 4) granules of 16 B: 512 cp.async for 256 threads
 #pragma unroll
     for (int it = 0; it < 2; ++it) {
-      const int idx = it * 128 + threadIdx.x;     // 0..255
-      const int key = idx >> 2, part = idx & 3;   // 4 x 16 B per key
+      const int idx = it * 256 + t;
+      const int key = (idx >> 2) & 63, part = idx & 3, is_v = idx >> 8;
       const int kg = k0 + key;
-      uint4 kr = make_uint4(0, 0, 0, 0), vr = make_uint4(0, 0, 0, 0);
-      if (kg < HW) {
-        const __nv_bfloat16* rowp = base + (long)kg * kQkv + head * kD + part * 8;
-        kr = __ldg(reinterpret_cast<const uint4*>(rowp + kHidden));
-        vr = __ldg(reinterpret_cast<const uint4*>(rowp + 2 * kHidden));
-      }
-      *reinterpret_cast<uint4*>(&s_k[key * kKStride + part * 8]) = kr;
-      const __nv_bfloat16* ve = reinterpret_cast<const __nv_bfloat16*>(&vr);
-#pragma unroll
-      for (int e = 0; e < 8; ++e) s_vt[(part * 8 + e) * kVStride + key] = ve[e];
+      const bool ok = kg < HW;
+      const __nv_bfloat16* src = base + (long)(ok ? kg : 0) * kQkv + (1 + is_v) * kHidden + head * kD + part * 8;
+      cp_async16((is_v ? sv : sk) + (buf * kKvTile + key * kKvStride + part * 8) * 2, src, ok);
     }
-    __syncthreads();
+    cp_async_commit();
+  };
+  const int ntiles = (HW + kBK - 1) / kBK;
+  issue_tile(0, 0);
+  const int mi = lane >> 3, r8 = lane & 7;
+  for (int ti = 0; ti < ntiles; ++ti) {
+    const int buf = ti & 1, k0 = ti * kBK;
+    cp_async_wait<0>();
+    __syncthreads();                       // tile ti landed for everyone; everyone is done with tile ti-1
+    if (ti + 1 < ntiles) issue_tile(k0 + kBK, buf ^ 1);
+    const uint32_t kb = sk + buf * kKvTile * 2, vb = sv + buf * kKvTile * 2;
 
     float s[8][4];
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) s[nt][i] = 0.f;
-#pragma unroll
-      for (int kk = 0; kk < 2; ++kk) {
-        const uint32_t b0 = *reinterpret_cast<const uint32_t*>(&s_k[(nt * 8 + g) * kKStride + kk * 16 + 2 * t]);
-        const uint32_t b1 = *reinterpret_cast<const uint32_t*>(&s_k[(nt * 8 + g) * kKStride + kk * 16 + 8 + 2 * t]);
-        mma_bf16(s[nt], qa[kk], b0, b1);
-      }
+      uint32_t kf[4];    // m0 (keys 0-7, d 0-7) m1 (d 8-15) m2 (d 16-23) m3 (d 24-31): b0,b1 of k-step 0 then 1
+      ldmatrix_x4(kf, kb + ((nt * 8 + r8) * kKvStride + mi * 8) * 2);
+      mma_bf16(s[nt], qa[0], kf[0], kf[1]);
+      mma_bf16(s[nt], qa[1], kf[2], kf[3]);
     }
     float mx0 = -INFINITY, mx1 = -INFINITY;
+    const bool tail = k0 + kBK > HW;
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
-      const int key = k0 + nt * 8 + 2 * t;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const bool ok = (key + (i & 1)) < HW;
+        const bool ok = !tail || (k0 + nt * 8 + 2 * tq + (i & 1)) < HW;
         s[nt][i] = ok ? s[nt][i] * scale_log2 : -INFINITY;
       }
       mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
@@ -653,10 +658,7 @@ __global__ void __launch_bounds__(128) attention_kernel(const __nv_bfloat16* __r
     l1 *= c1;
 #pragma unroll
     for (int dt = 0; dt < 4; ++dt) {
-      o[dt][0] *= c0;
-      o[dt][1] *= c0;
-      o[dt][2] *= c1;
-      o[dt][3] *= c1;
+      o[dt][0] *= c0; o[dt][1] *= c0; o[dt][2] *= c1; o[dt][3] *= c1;
     }
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
@@ -674,14 +676,15 @@ __global__ void __launch_bounds__(128) attention_kernel(const __nv_bfloat16* __r
       pa[1] = fd_pack_bf16(s[2 * kk][2], s[2 * kk][3]);
       pa[2] = fd_pack_bf16(s[2 * kk + 1][0], s[2 * kk + 1][1]);
       pa[3] = fd_pack_bf16(s[2 * kk + 1][2], s[2 * kk + 1][3]);
-#pragma unroll
-      for (int dt = 0; dt < 4; ++dt) {
-        const uint32_t b0 = *reinterpret_cast<const uint32_t*>(&s_vt[(dt * 8 + g) * kVStride + kk * 16 + 2 * t]);
-        const uint32_t b1 = *reinterpret_cast<const uint32_t*>(&s_vt[(dt * 8 + g) * kVStride + kk * 16 + 8 + 2 * t]);
-        mma_bf16(o[dt], pa, b0, b1);
-      }
+      uint32_t v01[4], v23[4];   // (trans) m0 (keys 0-7, d 0-7) m1 (keys 8-15, d 0-7) m2 (keys 0-7, d 8-15) m3 (keys 8-15, d 8-15)
+      const uint32_t va = vb + ((kk * 16 + (mi & 1) * 8 + r8) * kKvStride + (mi >> 1) * 8) * 2;
+      ldmatrix_x4_trans(v01, va);
+      ldmatrix_x4_trans(v23, va + 16 * 2);
+      mma_bf16(o[0], pa, v01[0], v01[1]);
+      mma_bf16(o[1], pa, v01[2], v01[3]);
+      mma_bf16(o[2], pa, v23[0], v23[1]);
+      mma_bf16(o[3], pa, v23[2], v23[3]);
     }
-    __syncthreads();
   }
   l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
   l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
@@ -692,9 +695,9 @@ __global__ void __launch_bounds__(128) attention_kernel(const __nv_bfloat16* __r
 #pragma unroll
   for (int dt = 0; dt < 4; ++dt) {
     if (row0 < HW)
-      *reinterpret_cast<uint32_t*>(ob + (long)row0 * kHidden + dt * 8 + 2 * t) = fd_pack_bf16(o[dt][0] * i0, o[dt][1] * i0);
+      *reinterpret_cast<uint32_t*>(ob + (long)row0 * kHidden + dt * 8 + 2 * tq) = fd_pack_bf16(o[dt][0] * i0, o[dt][1] * i0);
     if (row1 < HW)
-      *reinterpret_cast<uint32_t*>(ob + (long)row1 * kHidden + dt * 8 + 2 * t) = fd_pack_bf16(o[dt][2] * i1, o[dt][3] * i1);
+      *reinterpret_cast<uint32_t*>(ob + (long)row1 * kHidden + dt * 8 + 2 * tq) = fd_pack_bf16(o[dt][2] * i1, o[dt][3] * i1);
   }
 }
 
@@ -783,7 +786,7 @@ int fd_attention(const void* qkv, void* out, int N, int HW, void* stream) {
   FD_REQUIRE(qkv && out && N > 0 && HW > 0, "attention: bad argument");
   FD_REQUIRE(N <= 65535, "attention: batch too large");
   const float scale_log2 = 0.17677669529663687f * 1.4426950408889634f;   // 32^-0.5 * log2(e)
-  attention_kernel<<<dim3((HW + kBQ - 1) / kBQ, kHeads, N), 128, 0, (cudaStream_t)stream>>>(
+  attention_kernel<<<dim3((HW + kBQ - 1) / kBQ, kHeads, N), 256, 0, (cudaStream_t)stream>>>(
       static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(out), HW, scale_log2);
   FD_LAUNCH_CHECK();
   return FD_OK;
