@@ -139,7 +139,8 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     cfg = compose(["algorithm.target=flow", f"algorithm.sampling_timesteps={DDIM_STEPS}",
-                   f"algorithm.image_size=[{H},{W}]", "algorithm.return_all_timesteps=true"])
+                   f"algorithm.image_size=[{H},{W}]", "algorithm.return_all_timesteps=true",
+                   f"algorithm.use_cuda_graph={'true' if args.graph else 'false'}"])
     torch.manual_seed(0)
     algo = FlowDiffuser(cfg.algorithm).to(dev)
     algo.unet.prepare()
@@ -183,9 +184,9 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
-    l0 = lib.fd_launch_count()
+    l0 = lib.fd_launch_count() + algo.model.graph_replayed_launches
     t_res = timed(step_resident, args.steps)
-    launches = int(lib.fd_launch_count() - l0)
+    launches = int(lib.fd_launch_count() + algo.model.graph_replayed_launches - l0)
     t_e2e = timed(step_e2e, args.steps)
     clk = clocks.stop() if rank == 0 else None
 
@@ -216,7 +217,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": CONFIG,
         "e2e": {"value": flows / t_e2e, "unit": "flows/s", "h2d_bytes_per_step": cond_host.numel() * 4 + flow_host.numel() * 4,
                 "d2h_bytes_per_step": out_host.numel() * 4},
-        "gpu_launches": launches,
+        "gpu_launches": launches, "cuda_graph": bool(args.graph),
         "clocks": clk,
         "roofline": {"bound": "tensor", "kernel": "conv_igemm_kernel (tcgen05 implicit GEMM, all %d conv launches of one forward)" % conv_launches,
                      "achieved": conv_tf, "peak": peaks["tf_sustained"], "unit": "TFLOP/s", "frac": conv_tf / peaks["tf_sustained"],
@@ -243,6 +244,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--graph", type=int, default=1, help="replay the DDIM loop as one CUDA graph (1) or launch eagerly (0)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))

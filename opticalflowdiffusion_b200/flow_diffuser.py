@@ -177,6 +177,7 @@ class FlowDiffuser(_Base):
             noise_space="image" if cfg.noiser == "image" else "flow", timesteps=cfg.timesteps,
             sampling_timesteps=_cfg_get(cfg, "sampling_timesteps"), min_snr_loss_weight=True)
         self.return_all_timesteps = bool(_cfg_get(cfg, "return_all_timesteps", True))
+        self.use_cuda_graph = bool(_cfg_get(cfg, "use_cuda_graph", False))
 
     @property
     def augmentor(self) -> Augmentor:
@@ -223,7 +224,8 @@ class FlowDiffuser(_Base):
             joint = self.model.sample(batch_size=bsz, external_cond=cond, return_all_timesteps=all_t, **kw)
             samples, flow = (joint[:, :, :self.dim], joint[:, :, self.dim:]) if all_t else (joint[:, :self.dim], joint[:, self.dim:])
         else:
-            flow = self.model.sample(batch_size=bsz, external_cond=cond, return_all_timesteps=all_t, **kw)
+            flow = self.model.sample(batch_size=bsz, external_cond=cond, return_all_timesteps=all_t,
+                                     use_cuda_graph=self.use_cuda_graph, **kw)
             last = flow[:, -1] if all_t else flow
             samples = W.warp(cond[:, :self.dim], None, last.contiguous(), mode="forward")
         return samples, flow

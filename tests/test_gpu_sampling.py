@@ -121,3 +121,26 @@ def test_flow_diffuser_joint_target():
     # level 1 is exactly zero, the pyramid levels differ only by the splat's scale-consistency residual
     ideal = m.model._loss(tgt_[:, :3], tgt_[:, :3], None, flow_, cond, flow_, 0.0)
     assert bool(torch.isfinite(ideal)) and ideal.item() < loss.item()
+
+
+def test_ddim_epe_vs_oracle_and_cuda_graph():
+    """EPE parity (BASELINE metric): DDIM-5 at 64x128 (config #1 shape) against the fp32 CPU oracle, in pixels
+    (x flow_max), and the CUDA-graph replay of the same loop."""
+    m = make_algo(["algorithm.target=flow", "algorithm.sampling_timesteps=5"], seed=3)
+    sd = {k: v.detach().cpu().clone() for k, v in m.unet.state_dict().items()}
+    B, H, W = 1, 64, 128
+    cond = O.synthetic_frames(B, H, W, seed=6) * 2 - 1
+    x_T = torch.randn(B, 2, H, W, generator=torch.Generator().manual_seed(7))
+    with torch.no_grad():
+        ref = O.ddim_sample(sd, O.make_schedule(1000), x_T, cond, 1000, 5)
+    out = m.model.sample(B, external_cond=cond.cuda(), x_T=x_T)
+    epe = torch.sqrt(((out.cpu() - ref) * m.flow_max).pow(2).sum(1)).mean().item()
+    assert epe < 0.25, f"EPE between the CUDA path and the reference = {epe} px"      # tolerance: 0.25 px of a +-20 px range
+    gt = torch.zeros_like(ref)
+    epe_new = torch.sqrt(((out.cpu() - gt) * m.flow_max).pow(2).sum(1)).mean().item()
+    epe_ref = torch.sqrt(((ref - gt) * m.flow_max).pow(2).sum(1)).mean().item()
+    assert abs(epe_new - epe_ref) < 0.1, (epe_new, epe_ref)
+    g1 = m.model.sample(B, external_cond=cond.cuda(), x_T=x_T, use_cuda_graph=True)
+    g2 = m.model.sample(B, external_cond=cond.cuda(), x_T=x_T, use_cuda_graph=True)     # replay
+    assert torch.equal(g1, g2)
+    assert (g1 - out).abs().max().item() < 5e-3
