@@ -295,7 +295,8 @@ __global__ void __launch_bounds__(kPhotoThreads, VEC == 4 ? 2 : 4) photo_epe_fwd
       bw_taps(f1.v[j], f0.v[j], x + j, y, g, t[j]);
       m[j] = bw_mask(t[j]);
       const float du = f0.v[j] - g0.v[j], dv = f1.v[j] - g1.v[j];
-      s[2] += sqrtf(du * du + dv * dv);
+      const float e2 = du * du + dv * dv;
+      s[2] += e2 > 0.f ? e2 * rsqrtf(e2) : 0.f;
     }
     for (int c = 0; c < C; ++c) {
       const long po = ((long)b * C + c) * HW;
@@ -305,7 +306,8 @@ __global__ void __launch_bounds__(kPhotoThreads, VEC == 4 ? 2 : 4) photo_epe_fwd
       for (int j = 0; j < VEC; ++j) {
         const float wv = bw_sample(bw_gather(frame2 + po, t[j], W), t[j]);
         const float d = a.v[j] - wv;
-        s[0] += m[j] * sqrtf(d * d + 1e-6f);
+        const float q = d * d + 1e-6f;
+        s[0] += m[j] * (q * rsqrtf(q));          // sqrt(q), q >= 1e-6: 2-ulp approximation, one MUFU instead of IEEE sqrt
         s[1] += m[j];
       }
     }
