@@ -12,6 +12,10 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    # the C-ABI library is a build artefact (git-ignored); compile it once if this checkout does not have it yet
+    from opticalflowdiffusion_b200 import build as fd_build
+    if not os.path.exists(fd_build.LIB):
+        fd_build.build()
 
 
 def pytest_collection_modifyitems(config, items):
