@@ -50,24 +50,26 @@ struct ConvParams {
   double* gn_stats;   // [N][8][2] or null
 };
 
-template <int BLOCK_N>
+// SH ("store heavy"): few K-blocks per tile (1x1 convs), so the epilogue / output stores dominate: shallow operand
+// ring, one staging slab per 64 output channels so no TMA store ever waits for a buffer.
+template <int BLOCK_N, int SH = 0>
 struct Cfg {
   static constexpr int kBTileBytes = BLOCK_N * kBlockK * 2;
   static constexpr int kStageBytes = kATileBytes + kBTileBytes;
-  static constexpr int kStages = BLOCK_N == 64 ? 7 : (BLOCK_N == 128 ? 5 : 4);
-  static constexpr int kStoreBufs = BLOCK_N == 256 ? 1 : 2;      // output staging slabs (ping-pong when they fit)
+  static constexpr int kStages = SH ? 3 : (BLOCK_N == 64 ? 7 : (BLOCK_N == 128 ? 5 : 4));
+  static constexpr int kStoreBufs = SH ? (BLOCK_N / 64 > 2 ? BLOCK_N / 64 : 2) : (BLOCK_N == 256 ? 1 : 2);   // staging slabs
   static constexpr int kTmemCols = 2 * BLOCK_N;
   static constexpr int kTailBytes = 256 /*barriers*/ + 2 * BLOCK_N * 4 /*bias*/ + kEpiWarps * 16 * 4 /*stats*/ + 64;
   static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + kStoreBufs * kSlabBytes + kTailBytes;
 };
 
 // GPT = GroupNorm groups covered by one N-tile (8 when Cout == BLOCK_N, 4 when Cout == 2*BLOCK_N, 0 = no statistics)
-template <int BLOCK_N, int GPT>
+template <int BLOCK_N, int GPT, int SH>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
                   const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_out,
                   const ConvParams p) {
-  using C = Cfg<BLOCK_N>;
+  using C = Cfg<BLOCK_N, SH>;
   constexpr int STAGES = C::kStages;
   constexpr int NBUF = C::kStoreBufs;
   extern __shared__ uint8_t smem_raw[];
@@ -229,18 +231,18 @@ TileShape pick_tile(int H, int W) {
   return best;
 }
 
-template <int BLOCK_N, int GPT>
+template <int BLOCK_N, int GPT, int SH = 0>
 int launch(const CUtensorMap& ma0, const CUtensorMap& ma1, const CUtensorMap& mb, const CUtensorMap& mo,
            const ConvParams& p, int sms, cudaStream_t st) {
-  using C = Cfg<BLOCK_N>;
+  using C = Cfg<BLOCK_N, SH>;
   static bool attr_set = false;
   if (!attr_set) {
-    FD_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BLOCK_N, GPT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    FD_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BLOCK_N, GPT, SH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  C::kSmemBytes));
     attr_set = true;
   }
   const int grid = p.total_tiles < sms ? p.total_tiles : sms;
-  conv_igemm_kernel<BLOCK_N, GPT><<<grid, kThreads, C::kSmemBytes, st>>>(ma0, ma1, mb, mo, p);
+  conv_igemm_kernel<BLOCK_N, GPT, SH><<<grid, kThreads, C::kSmemBytes, st>>>(ma0, ma1, mb, mo, p);
   FD_LAUNCH_CHECK();
   return FD_OK;
 }
@@ -361,6 +363,12 @@ int fd_conv_igemm(const void* src0, int C0, const void* src1, int C1, const void
   cudaStream_t st = (cudaStream_t)stream;
   const bool stats = gn_stats != nullptr;
   if (stats) FD_REQUIRE(p.n_tiles == 1 || p.n_tiles == 2, "conv_igemm: statistics need Cout in {64,128,256,512}");
+  const bool store_heavy = !stats && p.taps * (p.chunks0 + p.chunks1) <= 4;
+  if (store_heavy) {
+    if (block_n == 256) return launch<256, 0, 1>(ma0, ma1, mb, mo, p, sms, st);
+    if (block_n == 128) return launch<128, 0, 1>(ma0, ma1, mb, mo, p, sms, st);
+    return launch<64, 0, 1>(ma0, ma1, mb, mo, p, sms, st);
+  }
   if (block_n == 256) {
     if (!stats) return launch<256, 0>(ma0, ma1, mb, mo, p, sms, st);
     return p.n_tiles == 1 ? launch<256, 8>(ma0, ma1, mb, mo, p, sms, st) : launch<256, 4>(ma0, ma1, mb, mo, p, sms, st);

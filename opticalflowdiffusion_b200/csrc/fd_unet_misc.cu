@@ -20,44 +20,74 @@ int egrid(long items, int threads, int per_sm = 16) {
 // as the horizontally unrolled tensor the 7x7 init conv consumes as a 7x1 conv over 64 channels:
 //   packed[b,h,w, kx*Ctot + c] = in[b,c,h,w+kx-3]   (zero outside the row, zero above 7*Ctot)
 // ---------------------------------------------------------------------------------------------
+constexpr int kPackPx = 256;       // pixels of one image row per block
+
 __global__ void __launch_bounds__(256) pack_input_kernel(const float* __restrict__ x, const float* __restrict__ cond,
                                                          __nv_bfloat16* __restrict__ packed, int B, int Cx, int Cc,
-                                                         int H, int W, int nan_mask) {
-  const long HW = (long)H * W;
-  const long total = (long)B * HW;
+                                                         int H, int W, int nan_mask, int segs) {
+  // A block owns kPackPx consecutive pixels of one row: the <= 9 input planes (+3 halo pixels per side) are read
+  // once, coalesced, into shared memory; then lane q of every 8-lane group writes the q-th 16-byte granule of its
+  // pixel, so a warp store covers 4 pixels x 128 B of contiguous memory.
+  __shared__ float s_in[9][kPackPx + 6];
   const int Ctot = Cx + (nan_mask ? 1 : 0) + Cc;
-  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-    const int b = (int)(i / HW);
-    const long p = i - (long)b * HW;
-    const int w = (int)(p % W);
-    float vals[64];
-#pragma unroll
-    for (int k = 0; k < 64; ++k) vals[k] = 0.f;
-#pragma unroll
-    for (int kx = 0; kx < 7; ++kx) {
-      const int ws = w + kx - 3;
-      if (ws < 0 || ws >= W) continue;
-      const long q = p + (kx - 3);
-      bool any_nan = false;
-      int c = 0;
-      for (int cx = 0; cx < Cx; ++cx, ++c) {
-        float v = __ldg(x + ((long)b * Cx + cx) * HW + q);
-        if (nan_mask && v != v) { any_nan = true; v = 0.f; }
-        vals[kx * Ctot + c] = v;
+  const int seg = blockIdx.x % segs;
+  const long row = blockIdx.x / segs;              // b * H + h
+  const int b = (int)(row / H), h = (int)(row % H);
+  const int w0 = seg * kPackPx;
+  const long HW = (long)H * W;
+  const int t = threadIdx.x;
+  for (int idx = t; idx < Ctot * (kPackPx + 6); idx += 256) {
+    const int c = idx / (kPackPx + 6), i = idx - c * (kPackPx + 6);
+    const int w = w0 + i - 3;
+    float v = 0.f;
+    if (w >= 0 && w < W) {
+      const long p = (long)h * W + w;
+      if (c < Cx) {
+        v = __ldg(x + ((long)b * Cx + c) * HW + p);
+      } else if (nan_mask && c == Cx) {
+        v = 0.f;                                  // filled below
+      } else {
+        v = __ldg(cond + ((long)b * Cc + (c - Cx - (nan_mask ? 1 : 0))) * HW + p);
       }
-      if (nan_mask) vals[kx * Ctot + (c++)] = any_nan ? 1.f : 0.f;
-      for (int cc = 0; cc < Cc; ++cc, ++c) vals[kx * Ctot + c] = __ldg(cond + ((long)b * Cc + cc) * HW + q);
     }
-    uint4* dst = reinterpret_cast<uint4*>(packed + i * 64);
+    s_in[c][i] = v;
+  }
+  __syncthreads();
+  if (nan_mask) {       // UnetWithWarp (flow_diffuser.py:39-45): NaN -> 0, mask channel = any NaN over the x channels
+    for (int i = t; i < kPackPx + 6; i += 256) {
+      bool any_nan = false;
+      for (int c = 0; c < Cx; ++c) {
+        const float v = s_in[c][i];
+        if (v != v) { any_nan = true; s_in[c][i] = 0.f; }
+      }
+      s_in[Cx][i] = any_nan ? 1.f : 0.f;
+    }
+    __syncthreads();
+  }
+  // this thread's granule q = t % 8 is the same for all its pixels: resolve (tap, channel) of its 8 values once
+  const int q = t & 7;
+  int off[8];
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      uint4 o;
-      o.x = fd_pack_bf16(vals[q * 8 + 0], vals[q * 8 + 1]);
-      o.y = fd_pack_bf16(vals[q * 8 + 2], vals[q * 8 + 3]);
-      o.z = fd_pack_bf16(vals[q * 8 + 4], vals[q * 8 + 5]);
-      o.w = fd_pack_bf16(vals[q * 8 + 6], vals[q * 8 + 7]);
-      dst[q] = o;
-    }
+  for (int j = 0; j < 8; ++j) {
+    const int k = q * 8 + j;
+    const int kx = k / Ctot, c = k - kx * Ctot;
+    off[j] = kx < 7 ? c * (kPackPx + 6) + kx : -1;     // s_in[c][px + kx]  (px + kx - 3 + 3)
+  }
+  const float* sflat = &s_in[0][0];
+  uint4* dst = reinterpret_cast<uint4*>(packed + (row * W + w0) * 64);
+#pragma unroll 4
+  for (int it = 0; it < kPackPx / 32; ++it) {
+    const int px = it * 32 + (t >> 3);
+    if (w0 + px >= W) break;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = off[j] >= 0 ? sflat[off[j] + px] : 0.f;
+    uint4 o;
+    o.x = fd_pack_bf16(v[0], v[1]);
+    o.y = fd_pack_bf16(v[2], v[3]);
+    o.z = fd_pack_bf16(v[4], v[5]);
+    o.w = fd_pack_bf16(v[6], v[7]);
+    dst[px * 8 + q] = o;
   }
 }
 
@@ -344,33 +374,54 @@ __global__ void __launch_bounds__(256) time_proj_kernel(const float* __restrict_
   if (lane == 0) out[(long)b * J + j] = acc + bias[j];
 }
 
-// final 1x1 conv (:361,417): bf16 NHWC (Cin) -> fp32 NCHW (Cout <= 4); thread per pixel
+// final 1x1 conv (:361,417): bf16 NHWC (Cin) -> fp32 NCHW (Cout <= 4).  4 lanes share a pixel, each owning a
+// contiguous quarter of the channels whose weights it keeps in registers (a warp reads whole 128-byte lines),
+// combined with two shuffles.  PER = Cin / 4 (16 for the UNet's 64 channels).
+template <int PER>
 __global__ void __launch_bounds__(256) final_conv_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w,
                                                          const float* __restrict__ bias, float* __restrict__ out, int N,
-                                                         long HW, int Cin, int Cout) {
-  extern __shared__ float sw[];   // [Cout][Cin] + [Cout]
-  for (int i = threadIdx.x; i < Cout * Cin; i += blockDim.x) sw[i] = w[i];
-  for (int i = threadIdx.x; i < Cout; i += blockDim.x) sw[Cout * Cin + i] = bias[i];
-  __syncthreads();
+                                                         long HW, int Cout) {
+  constexpr int Cin = PER * 4;
+  const int sub = threadIdx.x & 3;
+  float wr[4][PER];
+#pragma unroll
+  for (int o = 0; o < 4; ++o)
+#pragma unroll
+    for (int c = 0; c < PER; ++c) wr[o][c] = o < Cout ? __ldg(w + o * Cin + sub * PER + c) : 0.f;
+  float br[4];
+#pragma unroll
+  for (int o = 0; o < 4; ++o) br[o] = o < Cout ? __ldg(bias + o) : 0.f;
   const long total = (long)N * HW;
-  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+  const long gstride = ((long)gridDim.x * blockDim.x) >> 2;
+  const long iters = (total + gstride - 1) / gstride;
+  long i = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 2;
+  for (long it = 0; it < iters; ++it, i += gstride) {
+    const bool valid = i < total;
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    const uint4* row = reinterpret_cast<const uint4*>(x + i * Cin);
-    for (int q = 0; q < Cin / 8; ++q) {
-      const uint4 xv = __ldg(row + q);
-      const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w};
+    if (valid) {
+      const uint4* row = reinterpret_cast<const uint4*>(x + i * Cin + sub * PER);
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float2 f = fd_unpack_bf16(xw[e]);
+      for (int q = 0; q < PER / 8; ++q) {
+        const uint4 xv = __ldg(row + q);
+        const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w};
 #pragma unroll
-        for (int o = 0; o < 4; ++o)
-          if (o < Cout) acc[o] += f.x * sw[o * Cin + q * 8 + 2 * e] + f.y * sw[o * Cin + q * 8 + 2 * e + 1];
+        for (int e = 0; e < 4; ++e) {
+          const float2 f = fd_unpack_bf16(xw[e]);
+#pragma unroll
+          for (int o = 0; o < 4; ++o) acc[o] += f.x * wr[o][q * 8 + 2 * e] + f.y * wr[o][q * 8 + 2 * e + 1];
+        }
       }
     }
-    const long n = i / HW, p = i - n * HW;
 #pragma unroll
-    for (int o = 0; o < 4; ++o)
-      if (o < Cout) out[(n * Cout + o) * HW + p] = acc[o] + sw[Cout * Cin + o];
+    for (int o = 0; o < 4; ++o) {
+      acc[o] += __shfl_xor_sync(0xffffffffu, acc[o], 1);
+      acc[o] += __shfl_xor_sync(0xffffffffu, acc[o], 2);
+    }
+    if (valid && sub < Cout) {       // lane `sub` writes output channel `sub`
+      const long n = i / HW, p = i - n * HW;
+      const float r = sub == 0 ? acc[0] + br[0] : (sub == 1 ? acc[1] + br[1] : (sub == 2 ? acc[2] + br[2] : acc[3] + br[3]));
+      out[(n * Cout + sub) * HW + p] = r;
+    }
   }
 }
 
@@ -405,8 +456,10 @@ int fd_pack_input(const float* x, const float* cond, void* packed, int B, int Cx
   FD_REQUIRE(x && packed && B > 0 && H > 0 && W > 0 && Cx > 0 && Cc >= 0, "pack_input: bad argument");
   FD_REQUIRE(cond != nullptr || Cc == 0, "pack_input: Cc > 0 needs cond");
   FD_REQUIRE(Cx + (nan_mask ? 1 : 0) + Cc <= 9, "pack_input: at most 9 input channels (7 taps x 9 <= 64)");
-  pack_input_kernel<<<egrid((long)B * H * W, 256), 256, 0, (cudaStream_t)stream>>>(
-      x, cond, static_cast<__nv_bfloat16*>(packed), B, Cx, Cc, H, W, nan_mask);
+  const int segs = (W + kPackPx - 1) / kPackPx;
+  FD_REQUIRE((long)B * H * segs < (1L << 31), "pack_input: too many rows");
+  pack_input_kernel<<<(unsigned)((long)B * H * segs), 256, 0, (cudaStream_t)stream>>>(
+      x, cond, static_cast<__nv_bfloat16*>(packed), B, Cx, Cc, H, W, nan_mask, segs);
   FD_LAUNCH_CHECK();
   return FD_OK;
 }
@@ -489,8 +542,9 @@ int fd_time_proj(const float* temb, const float* w, const float* bias, float* ou
 int fd_final_conv(const void* x, const float* w, const float* bias, float* out, int N, int HW, int Cin, int Cout,
                   void* stream) {
   FD_REQUIRE(x && w && bias && out && N > 0 && HW > 0 && Cin % 8 == 0 && Cout >= 1 && Cout <= 4, "final_conv: bad argument");
-  final_conv_kernel<<<egrid((long)N * HW, 256), 256, (Cout * Cin + Cout) * sizeof(float), (cudaStream_t)stream>>>(
-      static_cast<const __nv_bfloat16*>(x), w, bias, out, N, (long)HW, Cin, Cout);
+  FD_REQUIRE(Cin == 64, "final_conv: the UNet's final conv has 64 input channels (got %d)", Cin);
+  final_conv_kernel<16><<<egrid((long)N * HW * 4, 256), 256, 0, (cudaStream_t)stream>>>(
+      static_cast<const __nv_bfloat16*>(x), w, bias, out, N, (long)HW, Cout);
   FD_LAUNCH_CHECK();
   return FD_OK;
 }
