@@ -143,6 +143,22 @@ FD_API int fd_conv_igemm(const void* src0, int C0, const void* src1, int C1, con
                   int N, int H, int W, int Cout, int KH, int KW, int pad_h, int pad_w, int mode,
                   void* stream);
 
+/* fd_conv_igemm with an output mode.  out_mode 0: as fd_conv_igemm.  out_mode 1 (the data gradient of
+ * Downsample, :95-99): a 1x1 conv whose Cout = 4*Cq channels are stored pixel-shuffled, channel
+ * (p1*2+p2)*Cq + c of pixel (h, w) -> pixel (2h+p1, 2w+p2), channel c of out (N, 2H, 2W, Cq); Cout % 256 == 0,
+ * no residual / statistics. */
+FD_API int fd_conv_igemm_ex(const void* src0, int C0, const void* src1, int C1, const void* wpacked,
+                     const float* bias, const void* residual, void* out, double* gn_stats,
+                     int N, int H, int W, int Cout, int KH, int KW, int pad_h, int pad_w, int mode,
+                     int out_mode, void* stream);
+
+/* Weight gradient of the same convolutions (autograd of the nn.Conv2d calls above) on tcgen05, K = pixels:
+ *   dw[co][tap*Cin + ci] += sum_{n,h,w} src[n, h+dy(tap), w+dx(tap), ci] * dy[n,h,w,co]      (fp32, packed order of
+ * fd_prep_weight kind 0 / 1; caller zero-fills).  src = concat(src0, src1) as in fd_conv_igemm; mode as there
+ * (mode 1: src is (N, 2H, 2W, C0), dy (N,H,W,Cout), taps (p1,p2)).  fp32 atomics: summation order is not fixed. */
+FD_API int fd_conv_wgrad(const void* src0, int C0, const void* src1, int C1, const void* dy, float* dw,
+                  int N, int H, int W, int Cout, int KH, int KW, int pad_h, int pad_w, int mode, void* stream);
+
 /* GroupNorm(8) apply + optional (scale+1, shift) + SiLU (+ optional residual add), bf16 NHWC:
  * Block.forward :181-187 and ResnetBlock's "+ res_conv(x)" :214.  stats from fd_conv_igemm.
  * scale_shift: fp32, row n at scale_shift + n*ss_stride holds [scale(C) | shift(C)] (time_emb.chunk(2), :208)

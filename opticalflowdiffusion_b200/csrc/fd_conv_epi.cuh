@@ -31,6 +31,7 @@ struct EpiCtx {
   const __nv_bfloat16* residual;
   double* gn_stats;
   int H, W, Cout, Wt;
+  int shuffle_cq;               // > 0: pixel-shuffle store (dgrad of Downsample): map_out is (Cq, 2, W, 2, H), Cq = Cout / 4
 };
 
 // GPT = GroupNorm groups covered by one N-tile (8 when Cout == BLOCK_N, 4 when Cout == 2*BLOCK_N, 0 = no statistics).
@@ -184,7 +185,13 @@ __device__ __forceinline__ void conv_epilogue(const EpiCtx& ec, NextTile next_ti
         }
         named_bar_sync(1, kEpiThreads);
         if (issuer) {
-          tma_store_5d(ec.map_out, buf, n0 + slab * 64, w0, h0, img, 0);
+          const int cc = n0 + slab * 64;
+          if (ec.shuffle_cq > 0) {
+            const int pq = cc / ec.shuffle_cq;          // p1 * 2 + p2
+            tma_store_5d(ec.map_out, buf, cc - pq * ec.shuffle_cq, pq & 1, w0, pq >> 1, h0);
+          } else {
+            tma_store_5d(ec.map_out, buf, cc, w0, h0, img, 0);
+          }
           tma_store_commit();
         }
       }

@@ -48,6 +48,7 @@ struct ConvParams {
   const float* bias;
   const __nv_bfloat16* residual;
   double* gn_stats;   // [N][8][2] or null
+  int shuffle_cq;     // > 0: pixel-shuffle store, out is (N, 2H, 2W, Cout/4)
 };
 
 // SH ("store heavy"): few K-blocks per tile (1x1 convs), so the epilogue / output stores dominate: shallow operand
@@ -191,6 +192,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
     ec.residual = p.residual;
     ec.gn_stats = p.gn_stats;
     ec.H = p.H; ec.W = p.W; ec.Cout = p.Cout; ec.Wt = p.Wt;
+    ec.shuffle_cq = p.shuffle_cq;
     conv_epilogue<BLOCK_N, GPT, NBUF>(ec, [&](int iter, EpiTile& t) {
       const int tile = blockIdx.x + iter * gridDim.x;
       if (tile >= p.total_tiles) return false;
@@ -258,6 +260,17 @@ extern "C" {
 int fd_conv_igemm(const void* src0, int C0, const void* src1, int C1, const void* wpacked, const float* bias,
                   const void* residual, void* out, double* gn_stats, int N, int H, int W, int Cout, int KH, int KW,
                   int pad_h, int pad_w, int mode, void* stream) {
+  return fd_conv_igemm_ex(src0, C0, src1, C1, wpacked, bias, residual, out, gn_stats, N, H, W, Cout, KH, KW, pad_h,
+                          pad_w, mode, 0, stream);
+}
+
+int fd_conv_igemm_ex(const void* src0, int C0, const void* src1, int C1, const void* wpacked, const float* bias,
+                     const void* residual, void* out, double* gn_stats, int N, int H, int W, int Cout, int KH, int KW,
+                     int pad_h, int pad_w, int mode, int out_mode, void* stream) {
+  FD_REQUIRE(out_mode == 0 || out_mode == 1, "conv_igemm: out_mode %d", out_mode);
+  FD_REQUIRE(out_mode == 0 || (mode == 0 && KH == 1 && KW == 1 && pad_h == 0 && pad_w == 0 && C1 == 0 &&
+                               residual == nullptr && gn_stats == nullptr && Cout % 256 == 0),
+             "conv_igemm: the pixel-shuffle store is for 1x1 convs with Cout %% 256 == 0, no residual / statistics");
   FD_REQUIRE(src0 && wpacked && out, "conv_igemm: null pointer");
   FD_REQUIRE(N > 0 && H > 0 && W > 0, "conv_igemm: bad geometry N=%d H=%d W=%d", N, H, W);
   FD_REQUIRE(C0 > 0 && C0 % 64 == 0 && C1 >= 0 && C1 % 64 == 0, "conv_igemm: C0=%d C1=%d must be multiples of 64", C0, C1);
@@ -298,7 +311,11 @@ int fd_conv_igemm(const void* src0, int C0, const void* src1, int C1, const void
   TileShape ts;
   if (mode == 0) {
     int n = N, h = H, w = W;
-    if (KH == 1 && KW == 1 && pad_h == 0 && pad_w == 0 && gn_stats == nullptr) {
+    if (out_mode == 1) {
+      // no halo: rows of all images merge; the real (h, w) geometry is kept for the shuffled store
+      n = 1;
+      h = N * H;
+    } else if (KH == 1 && KW == 1 && pad_h == 0 && pad_w == 0 && gn_stats == nullptr) {
       // 1x1: no halo, so every pixel of the batch is one long row -> full 128-pixel tiles for any W
       FD_REQUIRE((long)N * H * W < (1L << 31), "conv_igemm: too many pixels");
       w = N * H * W;
@@ -352,7 +369,15 @@ int fd_conv_igemm(const void* src0, int C0, const void* src1, int C1, const void
     const uint32_t box[2] = {64, (uint32_t)block_n};
     if (int e = make_tmap_bf16(&mb, wpacked, 2, dims, str, box)) return e;
   }
-  {
+  if (out_mode == 1) {
+    // dgrad of Downsample (:95-99): channel (p1*2+p2)*Cq + c of pixel (h, w) goes to pixel (2h+p1, 2w+p2), channel c
+    const uint64_t cq = (uint64_t)Cout / 4;
+    p.shuffle_cq = (int)cq;
+    const uint64_t dims[5] = {cq, 2, (uint64_t)p.W, 2, (uint64_t)p.H};
+    const uint64_t str[4] = {cq * 2, 2 * cq * 2, (uint64_t)2 * p.W * cq * 2, (uint64_t)4 * p.W * cq * 2};
+    const uint32_t box[5] = {64, 1, (uint32_t)ts.Wt, 1, (uint32_t)ts.R};
+    if (int e = make_tmap_bf16(&mo, out, 5, dims, str, box)) return e;
+  } else {
     // output (N, H, W, Cout) in the same (possibly flattened / merged) geometry: box = one 64-channel slab of a tile
     const uint64_t dims[5] = {(uint64_t)Cout, (uint64_t)p.W, (uint64_t)p.H, (uint64_t)p.N, 1};
     const uint64_t str[4] = {(uint64_t)Cout * 2, (uint64_t)p.W * Cout * 2, (uint64_t)p.H * p.W * Cout * 2,
