@@ -204,6 +204,71 @@ FD_API int fd_attention(const void* qkv, void* out, int N, int HW, void* stream)
 FD_API int fd_final_conv(const void* x, const float* w, const float* bias, float* out, int N, int HW, int Cin,
                   int Cout, void* stream);
 
+/* ==== backward pass: the autograd graph `loss.backward()` walks in training_step (flow_diffuser.py:217-235,
+ *      exp_base.py:193-214) for the modules above ================================================ */
+
+/* Attention core that also saves the log2-domain log-sum-exp of the scaled scores, lse fp32 [N][4][HW] (may be NULL) */
+FD_API int fd_attention_lse(const void* qkv, void* out, float* lse, int N, int HW, void* stream);
+/* backward of fd_attention: out / dout bf16 (N,HW,128), dqkv bf16 (N,HW,384); deterministic (no atomics).
+ * workspace floats: fd_attention_bwd_workspace_floats(N, HW). */
+FD_API size_t fd_attention_bwd_workspace_floats(int N, int HW);
+FD_API int fd_attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,
+                     float* workspace, int N, int HW, void* stream);
+
+/* fp32 statistics of LinearAttention's k softmax: stats [N][ max(128) | sum-exp(128) | ctx(4*32*32) ];
+ * workspace as fd_linattn_workspace_floats. */
+FD_API int fd_linattn_stats(const void* kv, int row_stride, float* stats, float* workspace, int N, int HW, void* stream);
+/* backward of fd_linattn: dout bf16 (N,HW,128) -> dqkv bf16 (N,HW,384); workspace fd_linattn_bwd_workspace_floats */
+FD_API size_t fd_linattn_bwd_workspace_floats(int N, int HW);
+FD_API int fd_linattn_bwd(const void* qkv, const void* dout, void* dqkv, float* workspace, int N, int HW, void* stream);
+
+/* backward of fd_gn_silu (Block.forward :181-187): h = the conv output the forward normalised, da = gradient of the
+ * activation output -> dh (bf16), and ACCUMULATES (+=, fp32) dgamma[C], dbeta[C], dbias[C] (the producing conv's bias
+ * gradient = sum over pixels of dh; may be NULL); writes dscale_shift rows like scale_shift (NULL iff scale_shift NULL).
+ * workspace floats: fd_gn_silu_bwd_workspace_floats(N, C). */
+FD_API size_t fd_gn_silu_bwd_workspace_floats(int N, int C);
+FD_API int fd_gn_silu_bwd(const void* h, const void* da, const double* gn_stats, const float* gamma, const float* beta,
+                   const float* scale_shift, long ss_stride, void* dh, float* dgamma, float* dbeta,
+                   float* dscale_shift, float* dbias, float* workspace, int N, int HW, int C, float eps, void* stream);
+/* backward of fd_chan_layernorm: dx = LN'(dy) (+ add, bf16, may be NULL), dg[C] += sum_px dy * xhat */
+FD_API int fd_chan_layernorm_bwd(const void* x, const float* g, const void* dy, const void* add, void* dx, float* dg,
+                          long npix, int C, float eps, void* stream);
+/* backward of fd_upsample2x: dy (N,2H,2W,C) -> dx (N,H,W,C) */
+FD_API int fd_upsample2x_bwd(const void* dy, void* dx, int N, int H, int W, int C, void* stream);
+/* out = a + b over n bf16 elements (n % 8 == 0); out may alias a or b */
+FD_API int fd_add_bf16(const void* a, const void* b, void* out, long n, void* stream);
+/* db[C] += sum over pixels of dy (bf16 [npix][C]) */
+FD_API int fd_bias_grad(const void* dy, float* db, long npix, int C, void* stream);
+/* backward of fd_final_conv: dout fp32 NCHW (N,Cout,HW) -> dx bf16 (N,HW,64); dw[Cout][64], db[Cout] += */
+FD_API int fd_final_conv_bwd(const void* x, const float* w, const float* dout, void* dx, float* dw, float* db,
+                      int N, int HW, int Cin, int Cout, void* stream);
+/* dgrad weights from the forward's packed weights: wd[ci][(T-1-tap)*Cout + co] = wpacked[co][tap*Cin + ci]
+ * (for kind 1 use T = 1, Cin = 4*C).  The data gradient is then fd_conv_igemm(_ex) on dy with wd. */
+FD_API int fd_prep_weight_dgrad(const void* wpacked, void* wd, int Cout, int Cin, int taps, void* stream);
+/* fd_conv_wgrad result (fp32 packed [Cout][K]) -> parameter gradient dw (+=, torch layout), through the
+ * weight-standardisation backward when standardize != 0 (arguments as fd_prep_weight). */
+FD_API int fd_prep_weight_bwd(const float* g, const float* w, float* dw, int Cout, int Cin, int KH, int KW, int kind,
+                       int standardize, float eps, void* stream);
+/* small fp32 dense layers of the time path (:319-324, :193-196); act 0 none, 1 SiLU, 2 GELU(erf):
+ *   bwd_w: dW[J][K] += sum_b dY[b][j] act(X[b][k]), db[J] += sum_b dY[b][j] (db may be NULL)
+ *   bwd_x: dX[b][k] = act'(A[b][k]) * sum_j dY[b][j] W[j][k] */
+FD_API int fd_linear_bwd_w(const float* dY, long dy_stride, const float* X, long x_stride, float* dW, float* db,
+                    int B, int J, int K, int act, void* stream);
+FD_API int fd_linear_bwd_x(const float* dY, long dy_stride, const float* W, const float* A, long a_stride, float* dX,
+                    long dx_stride, int B, int J, int K, int act, void* stream);
+/* fd_time_embed that also saves its intermediates for the backward: pe fp32 (B,dim), pre fp32 (B,time_dim) = the
+ * pre-GELU activations (either may be NULL) */
+FD_API int fd_time_embed_save(const int64_t* t, const float* w1, const float* b1, const float* w2, const float* b2,
+                       float* temb, float* pe, float* pre, int B, int dim, int time_dim, void* stream);
+
+/* optimiser (flow_diffuser.py:129-134 torch.optim.Adam with L2-in-gradient weight decay; Lightning's
+ * gradient_clip_val, exp_base.py:192,205): out[0] += sum of squares of g; then one fused update over flat buffers:
+ *   g' = g * grad_scale * min(1, max_norm / (grad_scale * sqrt(*grad_sumsq) + 1e-6)) + wd * p ;  Adam(m, v, step) */
+FD_API int fd_sumsq(const float* g, long n, float* out, void* stream);
+FD_API int fd_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long n, float lr,
+                 float beta1, float beta2, float eps, float weight_decay, int step, const float* grad_sumsq,
+                 float max_norm, float grad_scale, void* stream);
+
 /* debug / test helpers: fp32 NCHW <-> bf16 NHWC */
 FD_API int fd_nchw_to_nhwc_bf16(const float* x, void* out, int N, int C, int HW, void* stream);
 FD_API int fd_nhwc_bf16_to_nchw(const void* x, float* out, int N, int C, int HW, void* stream);

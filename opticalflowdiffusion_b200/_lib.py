@@ -57,6 +57,26 @@ SIGNATURES = {
     "fd_nhwc_bf16_to_nchw": (c_int, [_P, _P, _I, _I, _I, _P]),
     "fd_conv_igemm": (c_int, [_P, _I, _P, _I, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
     "fd_conv_igemm_ex": (c_int, [_P, _I, _P, _I, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
+    "fd_attention_lse": (c_int, [_P, _P, _P, _I, _I, _P]),
+    "fd_attention_bwd_workspace_floats": (c_size_t, [_I, _I]),
+    "fd_attention_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _I, _I, _P]),
+    "fd_linattn_stats": (c_int, [_P, _I, _P, _P, _I, _I, _P]),
+    "fd_linattn_bwd_workspace_floats": (c_size_t, [_I, _I]),
+    "fd_linattn_bwd": (c_int, [_P, _P, _P, _P, _I, _I, _P]),
+    "fd_gn_silu_bwd_workspace_floats": (c_size_t, [_I, _I]),
+    "fd_gn_silu_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _L, _P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _P]),
+    "fd_chan_layernorm_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _L, _I, _F, _P]),
+    "fd_upsample2x_bwd": (c_int, [_P, _P, _I, _I, _I, _I, _P]),
+    "fd_add_bf16": (c_int, [_P, _P, _P, _L, _P]),
+    "fd_bias_grad": (c_int, [_P, _P, _L, _I, _P]),
+    "fd_final_conv_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
+    "fd_prep_weight_dgrad": (c_int, [_P, _P, _I, _I, _I, _P]),
+    "fd_prep_weight_bwd": (c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _P]),
+    "fd_linear_bwd_w": (c_int, [_P, _L, _P, _L, _P, _P, _I, _I, _I, _I, _P]),
+    "fd_linear_bwd_x": (c_int, [_P, _L, _P, _P, _L, _P, _L, _I, _I, _I, _I, _P]),
+    "fd_time_embed_save": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P]),
+    "fd_sumsq": (c_int, [_P, _L, _P, _P]),
+    "fd_adam_step": (c_int, [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _I, _P, _F, _F, _P]),
     "fd_conv_wgrad": (c_int, [_P, _I, _P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
 }
 

@@ -10,44 +10,12 @@
 //   (flash-style) kernel: S and P never leave registers, so the reference's N x N matrix (6.3 GB at
 //   batch 8, 440x1024) is never materialised.  bf16 mma.sync m16n8k16 with fp32 accumulation and
 //   online softmax; 1.6 % of the forward FLOPs.
-#include "fd_common.cuh"
+#include "fd_mma.cuh"
+
+using namespace fdmma;
 
 namespace {
 
-constexpr int kHeads = 4;
-constexpr int kD = 32;
-constexpr int kHidden = kHeads * kD;   // 128
-constexpr int kQkv = 3 * kHidden;      // 384
-
-// ------------------------------------------------------------------------------------------------
-// warp-level tensor-core helpers (bf16 mma.sync m16n8k16, fp32 accumulate)
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void mma_bf16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm volatile(
-      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
-__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], uint32_t saddr) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
-               : "r"(saddr));
-}
-__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], uint32_t saddr) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
-               : "r"(saddr));
-}
-__device__ __forceinline__ void cp_async16(uint32_t saddr, const void* g, bool valid) {
-  const int sz = valid ? 16 : 0;      // src-size 0 -> the 16 bytes are zero-filled
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(saddr), "l"(g), "r"(sz) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-}
-__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 // ------------------------------------------------------------------------------------------------
 // linear attention, pass 1: per pixel-chunk partial (running max m, sum of exp s, 32x32 context per head)
@@ -207,6 +175,31 @@ __global__ void __launch_bounds__(1024) linattn_combine_kernel(const float* __re
   }
   // 32^-0.5 (the q scale, :238) is folded in here so the apply pass only normalises its softmax
   ctx_t[((long)n * kHeads + head) * kD * kD + e * kD + d] = __float2bfloat16(acc / S * inv_hw * 0.17677669529663687f);
+}
+
+// pass 2 for the backward pass: fp32 statistics per sample: m[128] (max over pixels of k), Z[128] (sum of exp(k - m)),
+// ctx[4][32 d][32 e] = softmax_n(k) v^T / HW (without the q scale)
+__global__ void __launch_bounds__(1024) linattn_combine_stats_kernel(const float* __restrict__ partial,
+                                                                     float* __restrict__ stats, int nchunks, float inv_hw) {
+  const int n = blockIdx.x / kHeads, head = blockIdx.x % kHeads;
+  const int d = threadIdx.x >> 5, e = threadIdx.x & 31;
+  const float* base = partial + (long)n * nchunks * kLaPartial;
+  float M = -INFINITY;
+  for (int c = 0; c < nchunks; ++c) M = fmaxf(M, base[(long)c * kLaPartial + head * kD + d]);
+  float S = 0.f, acc = 0.f;
+  for (int c = 0; c < nchunks; ++c) {
+    const float* pc = base + (long)c * kLaPartial;
+    const float mc = pc[head * kD + d];
+    const float f = (mc == -INFINITY) ? 0.f : __expf(mc - M);
+    S += pc[kHidden + head * kD + d] * f;
+    acc += pc[2 * kHidden + (head * kD + d) * kD + e] * f;
+  }
+  float* so = stats + (long)n * kLaPartial;
+  if (e == 0) {
+    so[head * kD + d] = M;
+    so[kHidden + head * kD + d] = S;
+  }
+  so[2 * kHidden + (head * kD + d) * kD + e] = acc / S * inv_hw;
 }
 
 // pass 3: out[n, e] = sum_d softmax_d(q[n, :])[d] ctx[d, e] on tensor cores.
@@ -573,7 +566,8 @@ constexpr int kKvStride = kD + 8;                  // bf16 per K / V row: 80 B, 
 constexpr int kKvTile = kBK * kKvStride;           // elements per K (or V) tile
 
 __global__ void __launch_bounds__(256) attention_kernel(const __nv_bfloat16* __restrict__ qkv,
-                                                        __nv_bfloat16* __restrict__ out, int HW, float scale_log2) {
+                                                        __nv_bfloat16* __restrict__ out, float* __restrict__ lse, int HW,
+                                                        float scale_log2) {
   __shared__ __align__(16) __nv_bfloat16 s_k[2][kKvTile];
   __shared__ __align__(16) __nv_bfloat16 s_v[2][kKvTile];
   const int n = blockIdx.z, head = blockIdx.y;
@@ -691,6 +685,11 @@ __global__ void __launch_bounds__(256) attention_kernel(const __nv_bfloat16* __r
   l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
   l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
   const float i0 = 1.f / l0, i1 = 1.f / l1;
+  if (lse != nullptr && tq == 0) {      // log2-domain log-sum-exp of the scaled scores, saved for the backward pass
+    float* lp = lse + ((long)n * kHeads + head) * HW;
+    if (row0 < HW) lp[row0] = m0 + log2f(l0);
+    if (row1 < HW) lp[row1] = m1 + log2f(l1);
+  }
   __nv_bfloat16* ob = out + (long)n * HW * kHidden + head * kD;
 #pragma unroll
   for (int dt = 0; dt < 4; ++dt) {
@@ -754,6 +753,26 @@ int fd_linattn_context(const void* kv, int row_stride, void* ctx_t, float* works
   return FD_OK;
 }
 
+// fp32 statistics of the k softmax and the context for the backward pass: stats [N][m(128) | Z(128) | ctx(4*32*32)]
+int fd_linattn_stats(const void* kv, int row_stride, float* stats, float* workspace, int N, int HW, void* stream) {
+  FD_REQUIRE(kv && stats && workspace && N > 0 && HW > 0 && row_stride >= 2 * kHidden && row_stride % 8 == 0,
+             "linattn_stats: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  int px;
+  const int chunks = la_chunks(N, HW, &px);
+  static bool attr_set = false;
+  if (!attr_set) {
+    FD_CUDA(cudaFuncSetAttribute(linattn_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kLaSmemBytes));
+    attr_set = true;
+  }
+  linattn_partial_kernel<<<dim3(chunks, N), 256, kLaSmemBytes, st>>>(static_cast<const __nv_bfloat16*>(kv), row_stride,
+                                                                     workspace, HW, px);
+  FD_LAUNCH_CHECK();
+  linattn_combine_stats_kernel<<<N * kHeads, 1024, 0, st>>>(workspace, stats, chunks, 1.f / (float)HW);
+  FD_LAUNCH_CHECK();
+  return FD_OK;
+}
+
 int fd_linattn(const void* qkv, void* out, float* workspace, int N, int HW, void* stream) {
   FD_REQUIRE(qkv && out && workspace && N > 0 && HW > 0, "linattn: bad argument");
   cudaStream_t st = (cudaStream_t)stream;
@@ -783,11 +802,15 @@ int fd_linattn_apply_fused(const void* x, const float* g1, const void* wq, const
 }
 
 int fd_attention(const void* qkv, void* out, int N, int HW, void* stream) {
+  return fd_attention_lse(qkv, out, nullptr, N, HW, stream);
+}
+
+int fd_attention_lse(const void* qkv, void* out, float* lse, int N, int HW, void* stream) {
   FD_REQUIRE(qkv && out && N > 0 && HW > 0, "attention: bad argument");
   FD_REQUIRE(N <= 65535, "attention: batch too large");
   const float scale_log2 = 0.17677669529663687f * 1.4426950408889634f;   // 32^-0.5 * log2(e)
   attention_kernel<<<dim3((HW + kBQ - 1) / kBQ, kHeads, N), 256, 0, (cudaStream_t)stream>>>(
-      static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(out), HW, scale_log2);
+      static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(out), lse, HW, scale_log2);
   FD_LAUNCH_CHECK();
   return FD_OK;
 }

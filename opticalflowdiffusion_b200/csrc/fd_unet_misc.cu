@@ -330,7 +330,8 @@ __global__ void __launch_bounds__(256) upsample2x_kernel(const uint4* __restrict
 // SinusoidalPosEmb + Linear + GELU(erf) + Linear (:144-151, 319-324); one block per batch element
 __global__ void __launch_bounds__(256) time_embed_kernel(const int64_t* __restrict__ t, const float* __restrict__ w1,
                                                          const float* __restrict__ b1, const float* __restrict__ w2,
-                                                         const float* __restrict__ b2, float* __restrict__ temb, int dim,
+                                                         const float* __restrict__ b2, float* __restrict__ temb,
+                                                         float* __restrict__ pe_out, float* __restrict__ pre_out, int dim,
                                                          int time_dim) {
   extern __shared__ float sm[];
   float* pe = sm;             // [dim]
@@ -344,12 +345,17 @@ __global__ void __launch_bounds__(256) time_embed_kernel(const int64_t* __restri
     const float arg = tv * f;
     pe[i] = sinf(arg);
     pe[half + i] = cosf(arg);
+    if (pe_out != nullptr) {
+      pe_out[(long)b * dim + i] = pe[i];
+      pe_out[(long)b * dim + half + i] = pe[half + i];
+    }
   }
   __syncthreads();
   for (int j = threadIdx.x; j < time_dim; j += blockDim.x) {
     float acc = b1[j];
     for (int k = 0; k < dim; ++k) acc += pe[k] * __ldg(w1 + (long)j * dim + k);
     hid[j] = 0.5f * acc * (1.f + erff(acc * 0.70710678118654752440f));
+    if (pre_out != nullptr) pre_out[(long)b * time_dim + j] = acc;
   }
   __syncthreads();
   for (int j = threadIdx.x; j < time_dim; j += blockDim.x) {
@@ -524,8 +530,14 @@ int fd_upsample2x(const void* x, void* out, int N, int H, int W, int C, void* st
 
 int fd_time_embed(const int64_t* t, const float* w1, const float* b1, const float* w2, const float* b2, float* temb,
                   int B, int dim, int time_dim, void* stream) {
+  return fd_time_embed_save(t, w1, b1, w2, b2, temb, nullptr, nullptr, B, dim, time_dim, stream);
+}
+
+int fd_time_embed_save(const int64_t* t, const float* w1, const float* b1, const float* w2, const float* b2, float* temb,
+                       float* pe, float* pre, int B, int dim, int time_dim, void* stream) {
   FD_REQUIRE(t && w1 && b1 && w2 && b2 && temb && B > 0 && dim >= 4 && dim % 2 == 0 && time_dim > 0, "time_embed: bad argument");
-  time_embed_kernel<<<B, 256, (dim + time_dim) * sizeof(float), (cudaStream_t)stream>>>(t, w1, b1, w2, b2, temb, dim, time_dim);
+  time_embed_kernel<<<B, 256, (dim + time_dim) * sizeof(float), (cudaStream_t)stream>>>(t, w1, b1, w2, b2, temb, pe, pre, dim,
+                                                                                       time_dim);
   FD_LAUNCH_CHECK();
   return FD_OK;
 }

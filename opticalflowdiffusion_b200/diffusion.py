@@ -40,6 +40,33 @@ def ddim_time_pairs(total: int, steps: int) -> List[Tuple[int, int]]:
     return list(zip(times[:-1], times[1:]))
 
 
+class _SqErrSums(torch.autograd.Function):
+    """(sum over non-NaN pairs of (a-b)^2, their count) with the gradient wrt ``a`` (warp.py:260-271 under autograd)."""
+
+    @staticmethod
+    def forward(ctx, a: Tensor, b: Tensor):
+        a, b = a.detach().float().contiguous(), b.detach().float().contiguous()
+        lib = _lib.load()
+        n = a.numel()
+        sums = torch.empty(3, device=a.device, dtype=torch.float32)
+        ws = torch.empty(lib.fd_nan_mse_workspace_floats(1, 1, n), device=a.device, dtype=torch.float32)
+        _lib.check(lib.fd_nan_mse_fwd(_lib.ptr(a), _lib.ptr(b), _lib.ptr(sums), _lib.ptr(ws), 1, 1, n, n, n, _lib.stream()))
+        ctx.save_for_backward(a, b)
+        ctx.mark_non_differentiable(sums)
+        return sums[0].clone(), sums[1].clone()
+
+    @staticmethod
+    def backward(ctx, gnum: Tensor, _gden):
+        a, b = ctx.saved_tensors
+        n = a.numel()
+        ga = torch.empty_like(a)
+        lib = _lib.load()
+        unit = torch.tensor([0.0, 1.0, 0.0], device=a.device, dtype=torch.float32)      # "count" 1: plain 2 (a - b) g
+        _lib.check(lib.fd_nan_mse_bwd(_lib.ptr(a), _lib.ptr(b), _lib.ptr(unit), float(gnum), _lib.ptr(ga), 1, 1, n, n, n, n,
+                                      _lib.stream()))
+        return ga, None
+
+
 class ConditionalDiffusion(nn.Module):
     BUFFERS = ("betas", "alphas_cumprod", "alphas_cumprod_prev", "sqrt_alphas_cumprod",
                "sqrt_one_minus_alphas_cumprod", "log_one_minus_alphas_cumprod", "sqrt_recip_alphas_cumprod",
@@ -298,13 +325,8 @@ class ConditionalDiffusion(nn.Module):
 
     @staticmethod
     def _sq_err_sums(a: Tensor, b: Tensor, weight: float):
-        a, b = a.float().contiguous(), b.float().contiguous()
-        lib = _lib.load()
-        n = a.numel()
-        sums = torch.empty(3, device=a.device, dtype=torch.float32)
-        ws = torch.empty(lib.fd_nan_mse_workspace_floats(1, 1, n), device=a.device, dtype=torch.float32)
-        _lib.check(lib.fd_nan_mse_fwd(_lib.ptr(a), _lib.ptr(b), _lib.ptr(sums), _lib.ptr(ws), 1, 1, n, n, n, _lib.stream()))
-        return sums[0] * weight, sums[1]
+        num, den = _SqErrSums.apply(a, b)
+        return num * weight, den
 
     def forward(self, img: Tensor, external_cond: Optional[Tensor] = None, *args, t: Optional[Tensor] = None, **kwargs):
         """:985-993: t ~ randint(0, T, (B,)) then p_losses (RNG order: randint, then randn_like inside)."""

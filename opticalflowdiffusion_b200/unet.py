@@ -23,6 +23,7 @@ import torch
 
 from . import _lib
 from .unet_params import UnetParams, _ResnetBlock
+from .unet_train import TrainMixin, UnetFunction
 
 Tensor = torch.Tensor
 BF16 = torch.bfloat16
@@ -39,7 +40,7 @@ class _PackedConv:
         self.bias: Optional[Tensor] = None
 
 
-class Unet(UnetParams):
+class Unet(UnetParams, TrainMixin):
     """Unet(dim=64, channels=C_in, out_dim=2): same constructor meaning as the reference (:272-293)."""
 
     GN_EPS = 1e-5       # nn.GroupNorm default (:176)
@@ -57,6 +58,7 @@ class Unet(UnetParams):
         self._tproj_b: Optional[Tensor] = None
         self._tproj_off: Dict[str, int] = {}
         self._prepared_versions = None
+        self.weights_epoch = 0      # bumped by optimisers that update the parameters through raw pointers
 
     # ------------------------------------------------------------------ weight preparation
     def _build_conv_table(self):
@@ -119,7 +121,8 @@ class Unet(UnetParams):
         self._convs = convs
 
     def _versions(self):
-        return tuple(p._version for p in self.parameters()) + tuple(p.data_ptr() for p in self.parameters())
+        return (self.weights_epoch,) + tuple(p._version for p in self.parameters()) + \
+            tuple(p.data_ptr() for p in self.parameters())
 
     @torch.no_grad()
     def prepare(self, force: bool = False):
@@ -247,12 +250,21 @@ class Unet(UnetParams):
         return s
 
     # ------------------------------------------------------------------ forward
-    @torch.no_grad()
     def forward(self, x: Tensor, external_cond: Optional[Tensor], time: Tensor, nan_mask: bool = False,
                 return_taps: bool = False):
         """``Unet.forward(x, external_cond, time)`` (:363-417): x (B,Cx,H,W) fp32, cond (B,Cc,H,W) fp32, time (B,)
         int64 -> (B,out_dim,H,W) fp32.  ``nan_mask`` folds UnetWithWarp's NaN -> 0 + mask channel
-        (flow_diffuser.py:39-45) into the input packing."""
+        (flow_diffuser.py:39-45) into the input packing.
+
+        With autograd enabled (training_step) the call is one ``UnetFunction`` node whose backward runs the backward
+        kernels (unet_train.py); under ``torch.no_grad()`` (sampling, validation) it is the inference path."""
+        if torch.is_grad_enabled() and not return_taps and any(p.requires_grad for p in self.parameters()):
+            return UnetFunction.apply(self, x, external_cond, time, nan_mask, *self.parameters())
+        return self._forward_infer(x, external_cond, time, nan_mask, return_taps)
+
+    @torch.no_grad()
+    def _forward_infer(self, x: Tensor, external_cond: Optional[Tensor], time: Tensor, nan_mask: bool = False,
+                       return_taps: bool = False):
         _lib.require_cuda(x, external_cond, time)
         self.prepare()
         self._lib = _lib.load()
