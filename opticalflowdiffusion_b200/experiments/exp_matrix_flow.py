@@ -3,8 +3,9 @@ experiments/exp_base.py:47-59,120-238 + exp_99.py:18-45 that drives the hot path
 
 The reference builds a ``pl.Trainer`` (DDP when more than one GPU is visible, exp_base.py:198).
 Lightning is not part of this path's contract, so the loop here is explicit: one process per GPU
-(torchrun), batch-sharded data, ``validation`` / ``sample`` tasks run the CUDA sampling path;
-``train`` needs the backward kernels and says so instead of silently doing something else."""
+(torchrun), batch-sharded data, ``validation`` / ``sample`` tasks run the CUDA sampling path; ``train`` is
+``training_step`` -> ``loss.backward()`` (the UnetFunction backward kernels) -> one NCCL all-reduce of the flat
+gradient (DDPStrategy's exchange, exp_base.py:198) -> fused clip + Adam."""
 from __future__ import annotations
 
 import os
@@ -62,10 +63,42 @@ class MatrixFlowExperiment:
             return self.validate()
         raise ValueError(f"Specified task '{task}' not implemented for class {self.__class__.__name__}.")
 
-    def train(self):
-        raise NotImplementedError(
-            "training needs the dgrad/wgrad/normalisation backward kernels, which are the next build step; "
-            "there is deliberately no autograd/PyTorch fallback.  training_step() computes the forward loss.")
+    def train(self, max_steps: Optional[int] = None):
+        """exp_base.py:178-214 without Lightning: epochs over the training loader; gradient clipping
+        (experiment.training.clipping, :192) and accumulate_grad_batches (:203) as configured."""
+        from ..optim import allreduce_gradients
+        dev = torch.device("cuda", self.local_rank)
+        torch.cuda.set_device(dev)
+        self.algo.to(dev)
+        self.algo.train()
+        opt = self.algo.configure_optimizers()
+        tr = self.cfg.experiment.training
+        clip = tr.get("clipping") if hasattr(tr, "get") else getattr(tr, "clipping", None)
+        if clip:
+            opt.max_grad_norm = float(clip)
+        accum = int(tr.optim.accumulate_grad_batches)
+        epochs = int(self.cfg.experiment.epochs)
+        losses, step, epoch = [], 0, 0
+        while (epochs < 0 or epoch < epochs) and (max_steps is None or step < max_steps):
+            loader = self._loader("training", tr)
+            if hasattr(loader.sampler, "set_epoch"):
+                loader.sampler.set_epoch(epoch)
+            for i, batch in enumerate(loader):
+                loss = self.algo.training_step(tuple(t.to(dev, non_blocking=True) for t in batch), i)
+                (loss / accum).backward()
+                if (i + 1) % accum == 0:
+                    allreduce_gradients(opt)
+                    opt.step()
+                    opt.zero_grad(set_to_none=True)
+                    step += 1
+                    self.algo.global_step = step
+                    losses.append(loss.detach())
+                    if max_steps is not None and step >= max_steps:
+                        break
+            epoch += 1
+            if max_steps is None and epochs < 0:
+                break          # "epochs: -1" means until stopped in the reference; one pass without a step budget
+        return {"train/loss": [float(x) for x in losses], "steps": step}
 
     @torch.no_grad()
     def validate(self, max_batches: Optional[int] = None):

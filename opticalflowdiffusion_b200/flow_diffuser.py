@@ -148,7 +148,7 @@ class UnetWithWarp(nn.Module):
 
 
 class FlowDiffuser(_Base):
-    backward_supported = False   # round 1 ships the forward / sampling kernels; dgrad / wgrad are next
+    backward_supported = True    # training_step's loss carries the UnetFunction autograd node (unet_train.py)
 
     def __init__(self, cfg):
         super().__init__()
@@ -186,7 +186,16 @@ class FlowDiffuser(_Base):
         return self._augmentor
 
     def configure_optimizers(self):
-        self.optimizers = torch.optim.Adam(self.model.parameters(), lr=self.cfg.lr, weight_decay=self.cfg.weight_decay)
+        """flow_diffuser.py:129-134: Adam(lr, weight_decay) over the model's parameters -- here the fused flat-buffer
+        implementation with the same update rule; ``clipping`` (experiment.training.clipping, exp_base.py:192) can be
+        folded into the step by setting ``optimizer.max_grad_norm``."""
+        from .optim import FusedAdam
+
+        def invalidate():
+            self.unet.weights_epoch += 1
+
+        self.optimizers = FusedAdam(self.model.parameters(), lr=self.cfg.lr, weight_decay=self.cfg.weight_decay,
+                                    max_grad_norm=float(_cfg_get(self.cfg, "clipping", 0.0) or 0.0), on_step=invalidate)
         return self.optimizers
 
     # ------------------------------------------------------------------ data

@@ -30,13 +30,14 @@ BF16 = torch.bfloat16
 
 
 class _PackedConv:
-    __slots__ = ("w", "bias", "cout", "kh", "kw", "pad", "mode", "src", "kind", "ws")
+    __slots__ = ("w", "wd", "bias", "cout", "kh", "kw", "pad", "mode", "src", "kind", "ws")
 
     def __init__(self, src, kind: int, ws: bool, kh: int, kw: int, pad: Tuple[int, int], mode: int):
         self.src, self.kind, self.ws = src, kind, ws
         self.kh, self.kw, self.pad, self.mode = kh, kw, pad, mode
         self.cout = src.weight.shape[0]
         self.w: Optional[Tensor] = None
+        self.wd: Optional[Tensor] = None     # dgrad packing (unet_train.py)
         self.bias: Optional[Tensor] = None
 
 
