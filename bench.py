@@ -142,6 +142,11 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                    f"algorithm.image_size=[{H},{W}]", "algorithm.return_all_timesteps=true",
                    f"algorithm.use_cuda_graph={'true' if args.graph else 'false'}"])
     torch.manual_seed(0)
+    if args.skip_sample:
+        tr = run_train_leg(args, cfg.algorithm, rank, world, dev)
+        if rank == 0:
+            print(json.dumps({"train": tr, "n_gpus": world}))
+        return
     algo = FlowDiffuser(cfg.algorithm).to(dev)
     algo.unet.prepare()
     frames = synthetic_frames(BATCH, H, W, seed=100 + rank)
@@ -205,6 +210,11 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     torch.cuda.synchronize()
     fwd_s = s.elapsed_time(e) * 1e-3
 
+    train = None
+    if not args.skip_train:
+        del algo
+        torch.cuda.empty_cache()
+        train = run_train_leg(args, cfg.algorithm, rank, world, dev)
     if rank != 0:
         return
     peaks = load_peaks()
@@ -225,6 +235,8 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                      "conv_share_of_forward": conv_s / fwd_s, "forward_ms": fwd_s * 1e3,
                      "whole_step_tflops": FWD_GF_PER_SAMPLE * DDIM_STEPS * 1e9 * value / 1e12},
     }
+    if train is not None:
+        line["train"] = train
     if world == 1 and not args.no_cpu_baseline:
         ts = cpu_reference_step_seconds(1, 1)
         tcpu = sum(ts) / len(ts)
@@ -237,6 +249,101 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         pass
 
 
+TRAIN_H, TRAIN_W = 368, 768
+TRAIN_GF_PER_SAMPLE = 3.0 * 1019.83      # forward 1019.83 GF at 368x768, fwd + bwd ~ 3x
+
+
+def run_train_leg(args, algo_cfg, rank: int, world: int, dev):
+    """BASELINE configs[2]: one training step (preprocess -> q_sample -> UNet fwd -> loss -> UNet bwd -> gradient
+    all-reduce -> fused clip + Adam) at 368x768 crops, batch-sharded data parallel.  Returns the "train" object."""
+    import torch.distributed as dist
+    from opticalflowdiffusion_b200 import FlowDiffuser, _lib
+    from opticalflowdiffusion_b200.datasets import synthetic_frames
+    from opticalflowdiffusion_b200.optim import allreduce_gradients
+    from opticalflowdiffusion_b200.parallel import max_over_ranks
+    lib = _lib.load()
+    B = args.train_batch
+    torch.manual_seed(0)
+    algo = FlowDiffuser(algo_cfg).to(dev)
+    algo.train()
+    opt = algo.configure_optimizers()
+    opt.max_grad_norm = 100.0                                   # experiment=matrix_flow: training.clipping = 100
+    g = torch.Generator().manual_seed(7 + rank)
+    img_h = synthetic_frames(B, TRAIN_H, TRAIN_W, seed=200 + rank).pin_memory()
+    tgt_h = synthetic_frames(B, TRAIN_H, TRAIN_W, seed=300 + rank).pin_memory()
+    flow_h = (torch.randn(B, 2, TRAIN_H, TRAIN_W, generator=g) * 5.0).pin_memory()
+    batch_dev = tuple(t.to(dev) for t in (img_h, tgt_h, flow_h))
+    loss_host = torch.empty((), pin_memory=True)
+
+    def sync():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def one_step(batch):
+        first, cond, _ = algo.preprocess(batch, aug=False)
+        loss = algo.loss(first, cond, None)
+        loss.backward()
+        allreduce_gradients(opt)
+        opt.step()
+        opt.zero_grad(set_to_none=True)
+        return loss
+
+    def step_resident():
+        return one_step(batch_dev)
+
+    def step_e2e():
+        batch = tuple(t.to(dev, non_blocking=True) for t in (img_h, tgt_h, flow_h))
+        loss = one_step(batch)
+        loss_host.copy_(loss.detach(), non_blocking=True)
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        sync()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(steps):
+            fn()
+        e.record()
+        sync()
+        return max_over_ranks(s.elapsed_time(e) * 1e-3, device=dev)
+
+    for _ in range(3):
+        first_loss = step_resident()
+    steps = max(args.steps, 3)
+    l0 = lib.fd_launch_count()
+    t_res = timed(step_resident, steps)
+    launches = int(lib.fd_launch_count() - l0)
+    t_e2e = timed(step_e2e, steps)
+    # phase split of one step (events on the launching stream)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    first, cond, _ = algo.preprocess(batch_dev, aug=False)
+    ev[0].record()
+    loss = algo.loss(first, cond, None)
+    ev[1].record()
+    loss.backward()
+    ev[2].record()
+    allreduce_gradients(opt)
+    opt.step()
+    opt.zero_grad(set_to_none=True)
+    ev[3].record()
+    torch.cuda.synchronize()
+    samples = world * B * steps
+    value = samples / t_res
+    peak_mem = torch.cuda.max_memory_allocated(dev) / 2 ** 30
+    return {"metric": "train samples/sec @368x768", "value": value, "unit": "samples/s", "ms_per_step": t_res / steps * 1e3,
+            "batch_per_gpu": B, "global_batch": B * world, "steps": steps, "warmup": 3, "dtype": "bf16 activations / fp32 master weights, grads, Adam",
+            "e2e": {"value": samples / t_e2e, "unit": "samples/s", "h2d_bytes_per_step": 4 * (img_h.numel() + tgt_h.numel() + flow_h.numel()),
+                    "d2h_bytes_per_step": 4},
+            "gpu_launches": launches, "loss_first": float(first_loss), "loss_last": float(loss),
+            "phases_ms": {"forward+loss": ev[0].elapsed_time(ev[1]), "backward": ev[1].elapsed_time(ev[2]),
+                          "allreduce+clip+adam": ev[2].elapsed_time(ev[3])},
+            "tensor_tflops": TRAIN_GF_PER_SAMPLE * value / 1e3 / world, "peak_mem_gib": peak_mem,
+            "config": "flow_diffuser training step, target=flow, synthetic 368x768 crops, aug off (the Augmentor is host-side "
+                      "python RNG), Adam lr 1e-5 wd 1e-6, clip 100, gradient all-reduce over NCCL when n_gpus > 1"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -245,6 +352,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--graph", type=int, default=1, help="replay the DDIM loop as one CUDA graph (1) or launch eagerly (0)")
+    ap.add_argument("--train-batch", type=int, default=8, help="per-GPU batch of the training leg (368x768 crops)")
+    ap.add_argument("--skip-train", action="store_true", help="omit the training leg (BASELINE configs[2])")
+    ap.add_argument("--skip-sample", action="store_true", help="training leg only (debug; prints a reduced line)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
