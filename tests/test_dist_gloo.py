@@ -36,7 +36,24 @@ def _worker(rank, world, port, q):
         for img, tgt, flow in exp._loader("validation", cfg.experiment.validation):
             assert img.shape == (2, 3, 16, 24) and flow.shape == (2, 2, 16, 24)
             seen.append(float(img.sum()))
-        q.put((rank, mine[0].flatten().tolist(), red, tmax, seen))
+        # training's exchange step (optim.allreduce_gradients): SUM all-reduce of the flat gradient, mean folded into
+        # the optimiser's grad_scale, and the next step() must consume exactly the reduced buffer
+        from opticalflowdiffusion_b200 import optim
+
+        class FlatStandIn:            # the slice of FusedAdam that allreduce_gradients touches (no CUDA here)
+            def __init__(self, g):
+                self.g, self.grad_scale, self._reduced = g, 1.0, None
+
+            def _still_flat(self):
+                return True
+
+            def flat_gradient(self):
+                return self.g
+
+        fs = FlatStandIn(torch.full((5,), float(rank + 1)))
+        optim.allreduce_gradients(fs)
+        mean = optim.allreduce_flat(torch.tensor([float(rank), 10.0]))
+        q.put((rank, mine[0].flatten().tolist(), red, tmax, seen, (fs._reduced.tolist(), fs.grad_scale, mean.tolist())))
     finally:
         dist.destroy_process_group()
 
@@ -53,7 +70,8 @@ def test_world_size_2_gloo():
     for p in procs:
         p.join(60)
         assert p.exitcode == 0
-    (r0, s0, red0, t0, seen0), (r1, s1, red1, t1, seen1) = out
+    (r0, s0, red0, t0, seen0, g0), (r1, s1, red1, t1, seen1, g1) = out
+    assert g0 == g1 == ([3.0] * 5, 0.5, [0.5, 10.0])                                  # SUM all-reduce, 1/world in grad_scale
     assert s0 == [0.0, 1.0, 2.0, 3.0, 4.0] and s1 == [5.0, 6.0, 7.0, 8.0, 9.0]       # disjoint, complete
     assert red0 == red1 == {"val/loss": 1.5, "val/mse": 1.0}
     assert t0 == t1 == 1.5
