@@ -574,16 +574,26 @@ __global__ void __launch_bounds__(256) lin_bwd_w_kernel(const float* __restrict_
   if (k == 0 && db != nullptr) db[j] += accb;
 }
 
+// block = (b, 32 consecutive k); 8 j-lanes x 32 k: coalesced rows of W, then a shared-memory reduction over the j-lanes
 __global__ void __launch_bounds__(256) lin_bwd_x_kernel(const float* __restrict__ dY, long dy_stride,
                                                         const float* __restrict__ W, const float* __restrict__ A,
                                                         long a_stride, float* __restrict__ dX, long dx_stride, int B, int J,
                                                         int K, int act) {
-  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (long)B * K) return;
-  const int b = (int)(i / K), k = (int)(i % K);
+  __shared__ float red[8][33];
+  const int kb = blockIdx.x, b = blockIdx.y;
+  const int kl = threadIdx.x & 31, jl = threadIdx.x >> 5;
+  const int k = kb * 32 + kl;
   float acc = 0.f;
-  for (int j = 0; j < J; ++j) acc += dY[(long)b * dy_stride + j] * __ldg(W + (long)j * K + k);
-  dX[(long)b * dx_stride + k] = acc * act_bwd(A[(long)b * a_stride + k], act);
+  if (k < K)
+    for (int j = jl; j < J; j += 8) acc += __ldg(dY + (long)b * dy_stride + j) * __ldg(W + (long)j * K + k);
+  red[jl][kl] = acc;
+  __syncthreads();
+  if (jl == 0 && k < K) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += red[i][kl];
+    dX[(long)b * dx_stride + k] = s * act_bwd(A[(long)b * a_stride + k], act);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -756,9 +766,9 @@ int fd_linear_bwd_x(const float* dY, long dy_stride, const float* W, const float
                     long dx_stride, int B, int J, int K, int act, void* stream) {
   FD_REQUIRE(dY && W && dX && B > 0 && J > 0 && K > 0 && act >= 0 && act <= 2, "linear_bwd_x: bad argument");
   FD_REQUIRE(act == 0 || A != nullptr, "linear_bwd_x: activation needs its forward input");
-  const long total = (long)B * K;
-  lin_bwd_x_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(dY, dy_stride, W, A ? A : dY, a_stride,
-                                                                                     dX, dx_stride, B, J, K, act);
+  FD_REQUIRE(B <= 65535, "linear_bwd_x: batch too large");
+  lin_bwd_x_kernel<<<dim3((K + 31) / 32, B), 256, 0, (cudaStream_t)stream>>>(dY, dy_stride, W, A ? A : dY, a_stride, dX,
+                                                                            dx_stride, B, J, K, act);
   FD_LAUNCH_CHECK();
   return FD_OK;
 }

@@ -42,7 +42,11 @@ WG_CASES = [
     (1, (64,), 64, 20, 40, (7, 1), (3, 0), 0),
     (2, (512, 256), 512, 4, 6, (3, 3), (1, 1), 0),
     (1, (256,), 256, 33, 70, (3, 3), (1, 1), 0),
-    (2, (64,), 64, 110, 256, (3, 3), (1, 1), 0),
+    (2, (64,), 64, 110, 256, (3, 3), (1, 1), 0),           # rolling-strip wgrad: two column blocks
+    (1, (64,), 64, 37, 130, (3, 3), (1, 1), 0),            # ragged W: second column block is 2 pixels wide
+    (2, (64, 64), 64, 21, 200, (3, 3), (1, 1), 0),         # two sources -> two ci chunks
+    (1, (128,), 128, 19, 96, (3, 3), (1, 1), 0),           # 2 x 2 block pairs, W < 128
+    (3, (192,), 128, 7, 64, (3, 3), (1, 1), 0),            # more block pairs than rows per CTA range
     (2, (64,), 128, 8, 12, (1, 1), (0, 0), 1),
     (1, (128,), 256, 16, 32, (1, 1), (0, 0), 1),
 ]
