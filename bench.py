@@ -203,6 +203,8 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     conv_s = sum(ev[0].elapsed_time(ev[1]) for _, _, ev in algo.unet._conv_timing) * 1e-3
     conv_launches = len(algo.unet._conv_timing)
     algo.unet._conv_timing = None
+    algo.unet(x_T, cond_dev, t)            # warm: the eager path's allocations are cached before it is timed
+    torch.cuda.synchronize()
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s.record()
     algo.unet(x_T, cond_dev, t)
@@ -336,7 +338,7 @@ def run_train_leg(args, algo_cfg, rank: int, world: int, dev):
             "batch_per_gpu": B, "global_batch": B * world, "steps": steps, "warmup": 3, "dtype": "bf16 activations / fp32 master weights, grads, Adam",
             "e2e": {"value": samples / t_e2e, "unit": "samples/s", "h2d_bytes_per_step": 4 * (img_h.numel() + tgt_h.numel() + flow_h.numel()),
                     "d2h_bytes_per_step": 4},
-            "gpu_launches": launches, "loss_first": float(first_loss), "loss_last": float(loss),
+            "gpu_launches": launches, "loss_first": float(first_loss.detach()), "loss_last": float(loss.detach()),
             "phases_ms": {"forward+loss": ev[0].elapsed_time(ev[1]), "backward": ev[1].elapsed_time(ev[2]),
                           "allreduce+clip+adam": ev[2].elapsed_time(ev[3])},
             "tensor_tflops": TRAIN_GF_PER_SAMPLE * value / 1e3 / world, "peak_mem_gib": peak_mem,

@@ -44,186 +44,319 @@ __device__ __forceinline__ uint4 pack8(const float* f) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// linear attention backward, pass 1: dctx[n][head][d][e] += sum over a pixel chunk of qs[d,p] dout[e,p]
-// block = 256 threads; tile = 32 pixels staged in shared memory as fp32 (softmaxed q, dout)
+// linear attention backward, pass 1 (tensor cores, K = pixels):
+//   dctx[n][head][d][e] += sum over a pixel chunk of qs[p,d] dout[p,e]
+// 8 warps = 4 heads x 2 halves of e; 64-pixel tiles of [q(128) | dout(128)] rows, cp.async double buffered.
+// A = qs^T via ldmatrix.trans of the raw q rows, softmax over d done in the A-fragment registers (4 values per
+// pixel column in a thread, the rest across the 8 lanes that share tq); B = dout via ldmatrix.trans.
 // ------------------------------------------------------------------------------------------------
-constexpr int kLbTile = 32;
+constexpr int kLbTile = 64;
+constexpr int kLbRowBytes = 2 * kHidden * 2 + 16;       // 528: conflict-free ldmatrix
+constexpr int kLbTileBytes = kLbTile * kLbRowBytes;
+constexpr int kLbSmemBytes = 2 * kLbTileBytes;
 
-__global__ void __launch_bounds__(256) linattn_bwd_dctx_kernel(const __nv_bfloat16* __restrict__ qkv,
-                                                               const __nv_bfloat16* __restrict__ dout,
-                                                               float* __restrict__ dctx, int HW, int chunk_px) {
-  __shared__ __align__(16) float s_q[kLbTile][kHidden];
-  __shared__ __align__(16) float s_do[kLbTile][kHidden];
+__global__ void __launch_bounds__(256, 3) linattn_bwd_dctx_kernel(const __nv_bfloat16* __restrict__ qkv,
+                                                                  const __nv_bfloat16* __restrict__ dout,
+                                                                  float* __restrict__ dctx, int HW, int chunk_px) {
+  extern __shared__ __align__(16) uint8_t lb_smem[];
   const int n = blockIdx.y;
-  const int t = threadIdx.x;
   const int p_begin = blockIdx.x * chunk_px;
   const int p_end = min(HW, p_begin + chunk_px);
-  // staging role: pixel = t / 8, 16-channel slice = t % 8 (two slices = one head)
-  const int spx = t >> 3, ssl = t & 7;
-  // accumulation role: head, d, 16 e's
-  const int head = t >> 6, d = (t & 63) >> 1, e0 = (t & 1) * 16;
-  float acc[16];
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const int g = lane >> 2, tq = lane & 3;
+  const int head = warp & 3, nhalf = warp >> 2;
+  const __nv_bfloat16* qbase = qkv + (long)n * HW * kQkv;
+  const __nv_bfloat16* dbase = dout + (long)n * HW * kHidden;
+  const uint32_t smem0 = smem_addr(lb_smem);
+  float acc[2][2][4];
 #pragma unroll
-  for (int j = 0; j < 16; ++j) acc[j] = 0.f;
-  for (int p0 = p_begin; p0 < p_end; p0 += kLbTile) {
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int b = 0; b < 2; ++b)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[a][b][c] = 0.f;
+
+  auto issue_tile = [&](int p0, int buf) {
+    // 64 pixels x 32 granules of 16 B: granules 0..15 = q, 16..31 = dout
+#pragma unroll
+    for (int it = 0; it < (kLbTile * 32) / 256; ++it) {
+      const int idx = it * 256 + t;
+      const int px = idx >> 5, q16 = idx & 31;
+      const int p = p0 + px;
+      const bool ok = p < p_end;
+      const long pp = ok ? p : p_begin;
+      const __nv_bfloat16* src = q16 < 16 ? qbase + pp * kQkv + q16 * 8 : dbase + pp * kHidden + (q16 - 16) * 8;
+      cp_async16(smem0 + buf * kLbTileBytes + px * kLbRowBytes + q16 * 16, src, ok);
+    }
+    cp_async_commit();
+  };
+  const int ntiles = (p_end - p_begin + kLbTile - 1) / kLbTile;
+  if (ntiles > 0) issue_tile(p_begin, 0);
+  const int mi = lane >> 3, r = lane & 7;
+  for (int ti = 0; ti < ntiles; ++ti) {
+    const int buf = ti & 1;
+    const int p0 = p_begin + ti * kLbTile;
+    if (ti + 1 < ntiles) {
+      issue_tile(p0 + kLbTile, buf ^ 1);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
     __syncthreads();
-    {
-      const int p = p0 + spx;
-      float q[16], dv[16];
-      if (p < p_end) {
-        const __nv_bfloat16* qp = qkv + ((long)n * HW + p) * kQkv + ssl * 16;
-        const __nv_bfloat16* dp = dout + ((long)n * HW + p) * kHidden + ssl * 16;
-        unpack8(__ldg(reinterpret_cast<const uint4*>(qp)), q);
-        unpack8(__ldg(reinterpret_cast<const uint4*>(qp + 8)), q + 8);
-        unpack8(__ldg(reinterpret_cast<const uint4*>(dp)), dv);
-        unpack8(__ldg(reinterpret_cast<const uint4*>(dp + 8)), dv + 8);
-      } else {
+    const uint32_t tb = smem0 + buf * kLbTileBytes;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) { q[j] = 0.f; dv[j] = 0.f; }
-      }
-      float mx = q[0];
+    for (int ks = 0; ks < kLbTile / 16; ++ks) {
+      // raw q as A fragments (d x pixel) for both 16-row halves of d
+      uint32_t qa[2][4];
 #pragma unroll
-      for (int j = 1; j < 16; ++j) mx = fmaxf(mx, q[j]);
-      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
-      float sum = 0.f;
+      for (int mt = 0; mt < 2; ++mt)
+        ldmatrix_x4_trans(qa[mt], tb + (ks * 16 + (mi >> 1) * 8 + r) * kLbRowBytes + (head * kD + mt * 16 + (mi & 1) * 8) * 2);
+      // element (mt, rg, half): d = mt*16 + g (+8 for rg odd), pixel = ks*16 + 2*tq + half (+8 for rg >= 2)
+      float v[2][4][2];
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        q[j] = __expf(q[j] - mx);
-        sum += q[j];
-      }
-      sum += __shfl_xor_sync(0xffffffffu, sum, 1);
-      const float inv = p < p_end ? kScale / sum : 0.f;
+      for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        s_q[spx][ssl * 16 + j] = q[j] * inv;
-        s_do[spx][ssl * 16 + j] = dv[j];
+        for (int rg = 0; rg < 4; ++rg) {
+          const float2 f = fd_unpack_bf16(qa[mt][rg]);
+          v[mt][rg][0] = f.x;
+          v[mt][rg][1] = f.y;
+        }
+#pragma unroll
+      for (int ph = 0; ph < 2; ++ph)          // pixel half: rg >> 1
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          float mx = fmaxf(fmaxf(v[0][2 * ph][hf], v[0][2 * ph + 1][hf]), fmaxf(v[1][2 * ph][hf], v[1][2 * ph + 1][hf]));
+          mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 4));
+          mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 8));
+          mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 16));
+          float sum = 0.f;
+#pragma unroll
+          for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int o = 0; o < 2; ++o) {
+              const float e = __expf(v[mt][2 * ph + o][hf] - mx);
+              v[mt][2 * ph + o][hf] = e;
+              sum += e;
+            }
+          sum += __shfl_xor_sync(0xffffffffu, sum, 4);
+          sum += __shfl_xor_sync(0xffffffffu, sum, 8);
+          sum += __shfl_xor_sync(0xffffffffu, sum, 16);
+          const float inv = kScale / sum;
+#pragma unroll
+          for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int o = 0; o < 2; ++o) v[mt][2 * ph + o][hf] *= inv;
+        }
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int rg = 0; rg < 4; ++rg) qa[mt][rg] = fd_pack_bf16(v[mt][rg][0], v[mt][rg][1]);
+      // B (trans): m0 (px 0-7, e 0-7) m1 (px 8-15, e 0-7) m2 (px 0-7, e 8-15) m3 (px 8-15, e 8-15) of this warp's 16 e's
+      uint32_t b[4];
+      ldmatrix_x4_trans(b, tb + (ks * 16 + (mi & 1) * 8 + r) * kLbRowBytes + (kHidden + head * kD + nhalf * 16 + (mi >> 1) * 8) * 2);
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        mma_bf16(acc[mt][0], qa[mt], b[0], b[1]);
+        mma_bf16(acc[mt][1], qa[mt], b[2], b[3]);
       }
     }
     __syncthreads();
-#pragma unroll 4
-    for (int p = 0; p < kLbTile; ++p) {
-      const float qv = s_q[p][head * kD + d];
-      const float4* dr = reinterpret_cast<const float4*>(&s_do[p][head * kD + e0]);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float4 v = dr[j];
-        acc[4 * j] += qv * v.x;
-        acc[4 * j + 1] += qv * v.y;
-        acc[4 * j + 2] += qv * v.z;
-        acc[4 * j + 3] += qv * v.w;
-      }
-    }
   }
-  float* dst = dctx + (((long)n * kHeads + head) * kD + d) * kD + e0;
+  float* dst = dctx + ((long)n * kHeads + head) * kD * kD;
 #pragma unroll
-  for (int j = 0; j < 16; ++j) atomicAdd(dst + j, acc[j]);
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt) {
+      const int d = mt * 16 + g, e = nhalf * 16 + nt * 8 + 2 * tq;
+      atomicAdd(dst + d * kD + e, acc[mt][nt][0]);
+      atomicAdd(dst + d * kD + e + 1, acc[mt][nt][1]);
+      atomicAdd(dst + (d + 8) * kD + e, acc[mt][nt][2]);
+      atomicAdd(dst + (d + 8) * kD + e + 1, acc[mt][nt][3]);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
-// linear attention backward, pass 2: per (pixel, head) thread; block = 32 pixels x 4 heads
+// linear attention backward, pass 2 (tensor cores): per 16-pixel warp tile and head, three 16x32x32 products
+//   dqs = dout ctx^T ;  dks = v dctx^T ;  dv = ks dctx
+// with the operands loaded straight into accumulator (C) layout from global memory, so that the softmaxes, the
+// elementwise backward formulas and the re-packing into A fragments all happen in registers.  ctx / dctx are bf16
+// in shared memory ([d][e], rows padded to 80 B).
 // ------------------------------------------------------------------------------------------------
+constexpr int kMatStride = kD + 8;
+
+__device__ __forceinline__ void load_c(uint32_t (&r)[4][2], const __nv_bfloat16* row0, const __nv_bfloat16* row1, bool ok0,
+                                       bool ok1, int tq) {
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt) {
+    r[nt][0] = ok0 ? __ldg(reinterpret_cast<const uint32_t*>(row0 + nt * 8 + 2 * tq)) : 0u;
+    r[nt][1] = ok1 ? __ldg(reinterpret_cast<const uint32_t*>(row1 + nt * 8 + 2 * tq)) : 0u;
+  }
+}
+__device__ __forceinline__ void c_to_a(uint32_t (&a)[2][4], const uint32_t (&c)[4][2]) {
+#pragma unroll
+  for (int kk = 0; kk < 2; ++kk) {
+    a[kk][0] = c[2 * kk][0];
+    a[kk][1] = c[2 * kk][1];
+    a[kk][2] = c[2 * kk + 1][0];
+    a[kk][3] = c[2 * kk + 1][1];
+  }
+}
+
 __global__ void __launch_bounds__(128) linattn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ qkv,
                                                                 const __nv_bfloat16* __restrict__ dout,
                                                                 const float* __restrict__ stats,
                                                                 const float* __restrict__ dctx,
                                                                 __nv_bfloat16* __restrict__ dqkv, int HW) {
-  __shared__ __align__(16) float s_ctx[kHeads][kD][kD];
-  __shared__ __align__(16) float s_dctx[kHeads][kD][kD];
+  __shared__ __align__(16) __nv_bfloat16 s_ctx[kHeads * kD * kMatStride];
+  __shared__ __align__(16) __nv_bfloat16 s_dctx[kHeads * kD * kMatStride];
   __shared__ float s_m[kHidden], s_iz[kHidden], s_r[kHidden];
   const int n = blockIdx.y;
-  const int t = threadIdx.x;
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const int g = lane >> 2, tq = lane & 3;
   const float* st = stats + (long)n * kStatsFloats;
+  const float* dc = dctx + (long)n * kHeads * kD * kD;
   const float inv_hw = 1.f / (float)HW;
   for (int i = t; i < kHeads * kD * kD; i += 128) {
-    (&s_ctx[0][0][0])[i] = st[2 * kHidden + i];
-    (&s_dctx[0][0][0])[i] = dctx[(long)n * kHeads * kD * kD + i];
+    const int row = i >> 5, e = i & 31;
+    s_ctx[row * kMatStride + e] = __float2bfloat16(st[2 * kHidden + i]);
+    s_dctx[row * kMatStride + e] = __float2bfloat16(dc[i]);
   }
   s_m[t] = st[t];
   s_iz[t] = 1.f / st[kHidden + t];
-  __syncthreads();
   {
-    float r = 0.f;      // r[d] = sum_e dctx[d,e] ctx[d,e]
-    const float* a = &s_dctx[0][0][0] + t * kD;
-    const float* b = &s_ctx[0][0][0] + t * kD;
+    float r = 0.f;      // r[d] = sum_e dctx[d,e] ctx[d,e]   (fp32 sources)
 #pragma unroll
-    for (int e = 0; e < kD; ++e) r += a[e] * b[e];
+    for (int e = 0; e < kD; ++e) r += dc[t * kD + e] * st[2 * kHidden + t * kD + e];
     s_r[t] = r;
   }
   __syncthreads();
-  const int head = t >> 5, lane = t & 31;
-  for (int p0 = blockIdx.x * 32; p0 < HW; p0 += gridDim.x * 32) {
-    const int p = p0 + lane;
-    if (p >= HW) continue;
-    const __nv_bfloat16* row = qkv + ((long)n * HW + p) * kQkv + head * kD;
-    __nv_bfloat16* drow = dqkv + ((long)n * HW + p) * kQkv + head * kD;
-    // ---- phase A: dq
-    {
-      float sm[kD], dO[kD], dqs[kD];
+  const uint32_t ctx_s = smem_addr(s_ctx), dctx_s = smem_addr(s_dctx);
+  const int mi = lane >> 3, r8 = lane & 7;
+  const long nbase = (long)n * HW;
+  for (int p0 = (blockIdx.x * 4 + warp) * 16; p0 < HW; p0 += gridDim.x * 64) {
+    const int pr0 = p0 + g, pr1 = p0 + g + 8;
+    const bool ok0 = pr0 < HW, ok1 = pr1 < HW;
+    const __nv_bfloat16* row0 = qkv + (nbase + (ok0 ? pr0 : 0)) * kQkv;
+    const __nv_bfloat16* row1 = qkv + (nbase + (ok1 ? pr1 : 0)) * kQkv;
+    const __nv_bfloat16* do0 = dout + (nbase + (ok0 ? pr0 : 0)) * kHidden;
+    const __nv_bfloat16* do1 = dout + (nbase + (ok1 ? pr1 : 0)) * kHidden;
+    __nv_bfloat16* dr0 = dqkv + (nbase + (ok0 ? pr0 : 0)) * kQkv;
+    __nv_bfloat16* dr1 = dqkv + (nbase + (ok1 ? pr1 : 0)) * kQkv;
+#pragma unroll 1
+    for (int head = 0; head < kHeads; ++head) {
+      const int hc = head * kD;
+      const uint32_t cm = ctx_s + head * kD * kMatStride * 2, dm = dctx_s + head * kD * kMatStride * 2;
+      // ---------------- dq
+      {
+        uint32_t qc[4][2], dc_[4][2], da[2][4];
+        load_c(qc, row0 + hc, row1 + hc, ok0, ok1, tq);
+        load_c(dc_, do0 + hc, do1 + hc, ok0, ok1, tq);
+        c_to_a(da, dc_);
+        float sm[4][4], dqs[4][4];
+        float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        unpack8(__ldg(reinterpret_cast<const uint4*>(row + j * 8)), sm + j * 8);
-        unpack8(__ldg(reinterpret_cast<const uint4*>(dout + ((long)n * HW + p) * kHidden + head * kD + j * 8)), dO + j * 8);
-      }
-      float mx = sm[0];
-#pragma unroll
-      for (int j = 1; j < kD; ++j) mx = fmaxf(mx, sm[j]);
-      float sum = 0.f;
-#pragma unroll
-      for (int j = 0; j < kD; ++j) {
-        sm[j] = __expf(sm[j] - mx);
-        sum += sm[j];
-      }
-      const float inv = 1.f / sum;
-      float dot = 0.f;
-#pragma unroll
-      for (int d = 0; d < kD; ++d) {
-        sm[d] *= inv;
-        const float4* cr = reinterpret_cast<const float4*>(&s_ctx[head][d][0]);
-        float a = 0.f;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float4 c = cr[j];
-          a += c.x * dO[4 * j] + c.y * dO[4 * j + 1] + c.z * dO[4 * j + 2] + c.w * dO[4 * j + 3];
+        for (int nt = 0; nt < 4; ++nt) {
+          const float2 a = fd_unpack_bf16(qc[nt][0]), b = fd_unpack_bf16(qc[nt][1]);
+          sm[nt][0] = a.x; sm[nt][1] = a.y; sm[nt][2] = b.x; sm[nt][3] = b.y;
+          mx0 = fmaxf(mx0, fmaxf(a.x, a.y));
+          mx1 = fmaxf(mx1, fmaxf(b.x, b.y));
         }
-        dqs[d] = a;
-        dot += sm[d] * a;
-      }
+        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+        float s0 = 0.f, s1 = 0.f;
 #pragma unroll
-      for (int d = 0; d < kD; ++d) dqs[d] = kScale * sm[d] * (dqs[d] - dot);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(drow + j * 8) = pack8(dqs + j * 8);
-    }
-    // ---- phase B: dk, dv
-    {
-      float ks[kD], v[kD], dv[kD], dk[kD];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        unpack8(__ldg(reinterpret_cast<const uint4*>(row + kHidden + j * 8)), ks + j * 8);
-        unpack8(__ldg(reinterpret_cast<const uint4*>(row + 2 * kHidden + j * 8)), v + j * 8);
-      }
-#pragma unroll
-      for (int e = 0; e < kD; ++e) dv[e] = 0.f;
-#pragma unroll
-      for (int d = 0; d < kD; ++d) {
-        const float kv = __expf(ks[d] - s_m[head * kD + d]) * s_iz[head * kD + d];
-        const float kvh = kv * inv_hw;
-        const float4* dr = reinterpret_cast<const float4*>(&s_dctx[head][d][0]);
-        float a = 0.f;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float4 c = dr[j];
-          a += c.x * v[4 * j] + c.y * v[4 * j + 1] + c.z * v[4 * j + 2] + c.w * v[4 * j + 3];
-          dv[4 * j] += kvh * c.x;
-          dv[4 * j + 1] += kvh * c.y;
-          dv[4 * j + 2] += kvh * c.z;
-          dv[4 * j + 3] += kvh * c.w;
+        for (int nt = 0; nt < 4; ++nt) {
+          sm[nt][0] = __expf(sm[nt][0] - mx0); sm[nt][1] = __expf(sm[nt][1] - mx0);
+          sm[nt][2] = __expf(sm[nt][2] - mx1); sm[nt][3] = __expf(sm[nt][3] - mx1);
+          s0 += sm[nt][0] + sm[nt][1];
+          s1 += sm[nt][2] + sm[nt][3];
         }
-        dk[d] = kv * (a * inv_hw - s_r[head * kD + d]);
-      }
+        s0 += __shfl_xor_sync(0xffffffffu, s0, 1); s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
+        s1 += __shfl_xor_sync(0xffffffffu, s1, 1); s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+        const float i0 = 1.f / s0, i1 = 1.f / s1;
+        float dot0 = 0.f, dot1 = 0.f;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        *reinterpret_cast<uint4*>(drow + kHidden + j * 8) = pack8(dk + j * 8);
-        *reinterpret_cast<uint4*>(drow + 2 * kHidden + j * 8) = pack8(dv + j * 8);
+        for (int nt = 0; nt < 4; ++nt) {       // n = d tile; B[k = e][n = d] = ctx[d][e]
+#pragma unroll
+          for (int i = 0; i < 4; ++i) dqs[nt][i] = 0.f;
+          uint32_t bf[4];
+          ldmatrix_x4(bf, cm + ((nt * 8 + r8) * kMatStride + mi * 8) * 2);
+          mma_bf16(dqs[nt], da[0], bf[0], bf[1]);
+          mma_bf16(dqs[nt], da[1], bf[2], bf[3]);
+          sm[nt][0] *= i0; sm[nt][1] *= i0; sm[nt][2] *= i1; sm[nt][3] *= i1;
+          dot0 += sm[nt][0] * dqs[nt][0] + sm[nt][1] * dqs[nt][1];
+          dot1 += sm[nt][2] * dqs[nt][2] + sm[nt][3] * dqs[nt][3];
+        }
+        dot0 += __shfl_xor_sync(0xffffffffu, dot0, 1); dot0 += __shfl_xor_sync(0xffffffffu, dot0, 2);
+        dot1 += __shfl_xor_sync(0xffffffffu, dot1, 1); dot1 += __shfl_xor_sync(0xffffffffu, dot1, 2);
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+          const int c = hc + nt * 8 + 2 * tq;
+          if (ok0)
+            *reinterpret_cast<uint32_t*>(dr0 + c) = fd_pack_bf16(kScale * sm[nt][0] * (dqs[nt][0] - dot0),
+                                                                 kScale * sm[nt][1] * (dqs[nt][1] - dot0));
+          if (ok1)
+            *reinterpret_cast<uint32_t*>(dr1 + c) = fd_pack_bf16(kScale * sm[nt][2] * (dqs[nt][2] - dot1),
+                                                                 kScale * sm[nt][3] * (dqs[nt][3] - dot1));
+        }
+      }
+      // ---------------- dk, dv
+      {
+        uint32_t kc[4][2], vc[4][2], va[2][4], ka[2][4];
+        load_c(kc, row0 + kHidden + hc, row1 + kHidden + hc, ok0, ok1, tq);
+        load_c(vc, row0 + 2 * kHidden + hc, row1 + 2 * kHidden + hc, ok0, ok1, tq);
+        c_to_a(va, vc);
+        float ks[4][4];
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+          const int d = hc + nt * 8 + 2 * tq;
+          const float2 a = fd_unpack_bf16(kc[nt][0]), b = fd_unpack_bf16(kc[nt][1]);
+          ks[nt][0] = __expf(a.x - s_m[d]) * s_iz[d];
+          ks[nt][1] = __expf(a.y - s_m[d + 1]) * s_iz[d + 1];
+          ks[nt][2] = __expf(b.x - s_m[d]) * s_iz[d];
+          ks[nt][3] = __expf(b.y - s_m[d + 1]) * s_iz[d + 1];
+          kc[nt][0] = fd_pack_bf16(ks[nt][0], ks[nt][1]);
+          kc[nt][1] = fd_pack_bf16(ks[nt][2], ks[nt][3]);
+        }
+        c_to_a(ka, kc);
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {       // dks[p, d] = sum_e v[p,e] dctx[d,e]
+          float dks[4] = {0.f, 0.f, 0.f, 0.f};
+          uint32_t bf[4];
+          ldmatrix_x4(bf, dm + ((nt * 8 + r8) * kMatStride + mi * 8) * 2);
+          mma_bf16(dks, va[0], bf[0], bf[1]);
+          mma_bf16(dks, va[1], bf[2], bf[3]);
+          const int d = hc + nt * 8 + 2 * tq;
+          const float r0 = s_r[d], r1 = s_r[d + 1];
+          if (ok0)
+            *reinterpret_cast<uint32_t*>(dr0 + kHidden + d) = fd_pack_bf16(ks[nt][0] * (dks[0] * inv_hw - r0),
+                                                                           ks[nt][1] * (dks[1] * inv_hw - r1));
+          if (ok1)
+            *reinterpret_cast<uint32_t*>(dr1 + kHidden + d) = fd_pack_bf16(ks[nt][2] * (dks[2] * inv_hw - r0),
+                                                                           ks[nt][3] * (dks[3] * inv_hw - r1));
+        }
+        float dv[4][4];
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) dv[nt][i] = 0.f;
+#pragma unroll
+        for (int kk = 0; kk < 2; ++kk) {       // dv[p, e] = sum_d ks[p,d] dctx[d,e] : B[k = d][n = e] row-major -> trans
+          uint32_t b01[4], b23[4];
+          const uint32_t ba = dm + ((kk * 16 + (mi & 1) * 8 + r8) * kMatStride + (mi >> 1) * 8) * 2;
+          ldmatrix_x4_trans(b01, ba);
+          ldmatrix_x4_trans(b23, ba + 16 * 2);
+          mma_bf16(dv[0], ka[kk], b01[0], b01[1]);
+          mma_bf16(dv[1], ka[kk], b01[2], b01[3]);
+          mma_bf16(dv[2], ka[kk], b23[0], b23[1]);
+          mma_bf16(dv[3], ka[kk], b23[2], b23[3]);
+        }
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+          const int c = 2 * kHidden + hc + nt * 8 + 2 * tq;
+          if (ok0) *reinterpret_cast<uint32_t*>(dr0 + c) = fd_pack_bf16(dv[nt][0] * inv_hw, dv[nt][1] * inv_hw);
+          if (ok1) *reinterpret_cast<uint32_t*>(dr1 + c) = fd_pack_bf16(dv[nt][2] * inv_hw, dv[nt][3] * inv_hw);
+        }
       }
     }
   }
@@ -509,14 +642,19 @@ int fd_linattn_bwd(const void* qkv, const void* dout, void* dqkv, float* workspa
   const __nv_bfloat16* dO = static_cast<const __nv_bfloat16*>(dout);
   if (int e = fd_linattn_stats(q + kHidden, kQkv, stats, fwd_ws, N, HW, stream)) return e;
   FD_CUDA(cudaMemsetAsync(dctx, 0, (size_t)N * kHeads * kD * kD * sizeof(float), st));
-  int want = (FD_NUM_SMS * 4) / N;
+  static bool attr_set = false;
+  if (!attr_set) {
+    FD_CUDA(cudaFuncSetAttribute(linattn_bwd_dctx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kLbSmemBytes));
+    attr_set = true;
+  }
+  int want = (FD_NUM_SMS * 3) / N;
   if (want < 1) want = 1;
   int px = (HW + want - 1) / want;
   px = ((px + kLbTile - 1) / kLbTile) * kLbTile;
   const int chunks = (HW + px - 1) / px;
-  linattn_bwd_dctx_kernel<<<dim3(chunks, N), 256, 0, st>>>(q, dO, dctx, HW, px);
+  linattn_bwd_dctx_kernel<<<dim3(chunks, N), 256, kLbSmemBytes, st>>>(q, dO, dctx, HW, px);
   FD_LAUNCH_CHECK();
-  int bx = (HW + 31) / 32;
+  int bx = (HW + 63) / 64;
   const int cap = (FD_NUM_SMS * 8 + N - 1) / N;
   if (bx > cap) bx = cap;
   linattn_bwd_apply_kernel<<<dim3(bx, N), 128, 0, st>>>(q, dO, stats, dctx, static_cast<__nv_bfloat16*>(dqkv), HW);
