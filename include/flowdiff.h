@@ -218,9 +218,14 @@ FD_API int fd_attention_bwd(const void* qkv, const void* out, const void* dout, 
 /* fp32 statistics of LinearAttention's k softmax: stats [N][ max(128) | sum-exp(128) | ctx(4*32*32) ];
  * workspace as fd_linattn_workspace_floats. */
 FD_API int fd_linattn_stats(const void* kv, int row_stride, float* stats, float* workspace, int N, int HW, void* stream);
-/* backward of fd_linattn: dout bf16 (N,HW,128) -> dqkv bf16 (N,HW,384); workspace fd_linattn_bwd_workspace_floats */
+/* fd_linattn that also writes those statistics (N * fd_linattn_stats_floats() floats) from the same partial sums */
+FD_API size_t fd_linattn_stats_floats(void);
+FD_API int fd_linattn_save(const void* qkv, void* out, float* stats, float* workspace, int N, int HW, void* stream);
+/* backward of fd_linattn: dout bf16 (N,HW,128) -> dqkv bf16 (N,HW,384); saved_stats from fd_linattn_save or NULL
+ * (then they are recomputed); workspace fd_linattn_bwd_workspace_floats */
 FD_API size_t fd_linattn_bwd_workspace_floats(int N, int HW);
-FD_API int fd_linattn_bwd(const void* qkv, const void* dout, void* dqkv, float* workspace, int N, int HW, void* stream);
+FD_API int fd_linattn_bwd(const void* qkv, const void* dout, void* dqkv, const float* saved_stats, float* workspace,
+                   int N, int HW, void* stream);
 
 /* backward of fd_gn_silu (Block.forward :181-187): h = the conv output the forward normalised, da = gradient of the
  * activation output -> dh (bf16), and ACCUMULATES (+=, fp32) dgamma[C], dbeta[C], dbias[C] (the producing conv's bias

@@ -62,7 +62,9 @@ SIGNATURES = {
     "fd_attention_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _I, _I, _P]),
     "fd_linattn_stats": (c_int, [_P, _I, _P, _P, _I, _I, _P]),
     "fd_linattn_bwd_workspace_floats": (c_size_t, [_I, _I]),
-    "fd_linattn_bwd": (c_int, [_P, _P, _P, _P, _I, _I, _P]),
+    "fd_linattn_bwd": (c_int, [_P, _P, _P, _P, _P, _I, _I, _P]),
+    "fd_linattn_stats_floats": (c_size_t, []),
+    "fd_linattn_save": (c_int, [_P, _P, _P, _P, _I, _I, _P]),
     "fd_gn_silu_bwd_workspace_floats": (c_size_t, [_I, _I]),
     "fd_gn_silu_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _L, _P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _P]),
     "fd_chan_layernorm_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _L, _I, _F, _P]),

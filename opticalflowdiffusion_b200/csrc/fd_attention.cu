@@ -774,6 +774,11 @@ int fd_linattn_stats(const void* kv, int row_stride, float* stats, float* worksp
 }
 
 int fd_linattn(const void* qkv, void* out, float* workspace, int N, int HW, void* stream) {
+  return fd_linattn_save(qkv, out, nullptr, workspace, N, HW, stream);
+}
+
+// fd_linattn that also emits the fp32 statistics of fd_linattn_stats (from the same partial sums) for the backward pass
+int fd_linattn_save(const void* qkv, void* out, float* stats, float* workspace, int N, int HW, void* stream) {
   FD_REQUIRE(qkv && out && workspace && N > 0 && HW > 0, "linattn: bad argument");
   cudaStream_t st = (cudaStream_t)stream;
   int px;
@@ -783,6 +788,10 @@ int fd_linattn(const void* qkv, void* out, float* workspace, int N, int HW, void
   __nv_bfloat16* ctx_t = reinterpret_cast<__nv_bfloat16*>(workspace + off);
   const __nv_bfloat16* q = static_cast<const __nv_bfloat16*>(qkv);
   if (int e = fd_linattn_context(q + kHidden, kQkv, ctx_t, workspace, N, HW, stream)) return e;
+  if (stats != nullptr) {
+    linattn_combine_stats_kernel<<<N * kHeads, 1024, 0, st>>>(workspace, stats, chunks, 1.f / (float)HW);
+    FD_LAUNCH_CHECK();
+  }
   int bx = (HW + 63) / 64;
   const int cap = (FD_NUM_SMS * 8 + N - 1) / N;
   if (bx > cap) bx = cap;

@@ -202,7 +202,7 @@ __device__ __forceinline__ void c_to_a(uint32_t (&a)[2][4], const uint32_t (&c)[
   }
 }
 
-__global__ void __launch_bounds__(128) linattn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ qkv,
+__global__ void __launch_bounds__(128, 6) linattn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ qkv,
                                                                 const __nv_bfloat16* __restrict__ dout,
                                                                 const float* __restrict__ stats,
                                                                 const float* __restrict__ dctx,
@@ -627,11 +627,14 @@ __global__ void __launch_bounds__(256) attn_bwd_dkv_kernel(const __nv_bfloat16* 
 
 extern "C" {
 
+size_t fd_linattn_stats_floats(void) { return kStatsFloats; }
+
 size_t fd_linattn_bwd_workspace_floats(int N, int HW) {
   return (size_t)N * kStatsFloats + (size_t)N * kHeads * kD * kD + fd_linattn_workspace_floats(N, HW);
 }
 
-int fd_linattn_bwd(const void* qkv, const void* dout, void* dqkv, float* workspace, int N, int HW, void* stream) {
+int fd_linattn_bwd(const void* qkv, const void* dout, void* dqkv, const float* saved_stats, float* workspace, int N, int HW,
+                   void* stream) {
   FD_REQUIRE(qkv && dout && dqkv && workspace && N > 0 && HW > 0, "linattn_bwd: bad argument");
   FD_REQUIRE(N <= 65535, "linattn_bwd: batch too large");
   cudaStream_t st = (cudaStream_t)stream;
@@ -640,7 +643,11 @@ int fd_linattn_bwd(const void* qkv, const void* dout, void* dqkv, float* workspa
   float* fwd_ws = dctx + (size_t)N * kHeads * kD * kD;
   const __nv_bfloat16* q = static_cast<const __nv_bfloat16*>(qkv);
   const __nv_bfloat16* dO = static_cast<const __nv_bfloat16*>(dout);
-  if (int e = fd_linattn_stats(q + kHidden, kQkv, stats, fwd_ws, N, HW, stream)) return e;
+  if (saved_stats != nullptr) {
+    stats = const_cast<float*>(saved_stats);      // from fd_linattn_save: no recomputation of the k softmax statistics
+  } else if (int e = fd_linattn_stats(q + kHidden, kQkv, stats, fwd_ws, N, HW, stream)) {
+    return e;
+  }
   FD_CUDA(cudaMemsetAsync(dctx, 0, (size_t)N * kHeads * kD * kD * sizeof(float), st));
   static bool attr_set = false;
   if (!attr_set) {

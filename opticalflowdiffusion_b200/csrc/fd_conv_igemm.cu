@@ -252,6 +252,7 @@ int launch(const CUtensorMap& ma0, const CUtensorMap& ma1, const CUtensorMap& mb
 }  // namespace
 
 int fd_conv3x3_strip_launch(const void* src0, int C0, const void* src1, int C1, const void* wpacked, const float* bias,
+                            const void* residual,
                             void* out, double* gn_stats, int N, int H, int W, int base_offset_mode,
                             cudaStream_t st);   // fd_conv_strip.cu
 
@@ -289,8 +290,8 @@ int fd_conv_igemm_ex(const void* src0, int C0, const void* src1, int C1, const v
     }
     const bool chans_ok = (C0 == 64 && (C1 == 0 || C1 == 64)) || (C0 == 128 && C1 == 0);
     if (strip_mode > 0 && mode == 0 && KH == 3 && KW == 3 && pad_h == 1 && pad_w == 1 && chans_ok && Cout == 64 &&
-        residual == nullptr && W >= 128)
-      return fd_conv3x3_strip_launch(src0, C0, src1, C1, wpacked, bias, out, gn_stats, N, H, W, strip_mode,
+        W >= 128 && out_mode == 0)
+      return fd_conv3x3_strip_launch(src0, C0, src1, C1, wpacked, bias, residual, out, gn_stats, N, H, W, strip_mode,
                                      (cudaStream_t)stream);
   }
   static int sms = 0;

@@ -219,7 +219,7 @@ conv3x3_strip_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_co
 
 // (C0, C1) in {(64, 0), (64, 64), (128, 0)}; Cout = 64; 3x3, pad 1
 int fd_conv3x3_strip_launch(const void* src0, int C0, const void* src1, int C1, const void* wpacked, const float* bias,
-                            void* out, double* gn_stats, int N, int H, int W, int base_offset_mode, cudaStream_t st) {
+                            const void* residual, void* out, double* gn_stats, int N, int H, int W, int base_offset_mode, cudaStream_t st) {
   static int sms = 0;
   if (sms == 0) {
     int dev = 0;
@@ -276,7 +276,8 @@ int fd_conv3x3_strip_launch(const void* src0, int C0, const void* src1, int C1, 
     p.c_off = (pass == 1 && C1 == 0) ? 64 : 0;
     p.w_k0 = pass * 64;
     p.bias = last ? bias : nullptr;
-    p.residual = pass > 0 ? static_cast<const __nv_bfloat16*>(out) : nullptr;   // partial sum of the previous pass
+    // pass 0 adds the caller's residual (if any), pass 1 the partial sum of pass 0
+    p.residual = static_cast<const __nv_bfloat16*>(pass > 0 ? out : residual);
     p.gn_stats = last ? gn_stats : nullptr;
     if (p.gn_stats != nullptr)
       conv3x3_strip_kernel<8><<<grid, kThreads, kSmemBytes, st>>>(mi, mw, mo, p);

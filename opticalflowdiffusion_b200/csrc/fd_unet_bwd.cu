@@ -79,7 +79,7 @@ __device__ __forceinline__ float silu_grad(float z) {
   return sg * (1.f + z * (1.f - sg));
 }
 
-__global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ h,
+__global__ void __launch_bounds__(256, 2) gn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ h,
                                                             const __nv_bfloat16* __restrict__ da,
                                                             const double* __restrict__ stats,
                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(const __nv_bfloat16*
 #pragma unroll
   for (int j = 0; j < 8; ++j) s0[j] = s1[j] = s2[j] = 0.f;
   const long base = (long)n * HW;
-  constexpr int U = 2;
+  constexpr int U = 4;
   const long stride = (long)gridDim.x * ppb;
   for (long p0 = (long)blockIdx.x * ppb + prow; p0 < HW; p0 += stride * U) {
     uint4 hv[U], dv[U];
@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(1024) gn_bwd_finalize_kernel(const float* __re
   if (dbias != nullptr) atomicAdd(dbias + c, rstd * sc * ga * S0 + Q * S2 + R * (float)HW);   // sum over pixels of dh
 }
 
-__global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ h,
+__global__ void __launch_bounds__(256, 3) gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ h,
                                                            const __nv_bfloat16* __restrict__ da,
                                                            const double* __restrict__ stats, const float* __restrict__ gamma,
                                                            const float* __restrict__ beta,
@@ -198,13 +198,9 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const __nv_bfloat16* 
   const int cpg = C >> 3;
   GnCoef k;
   gn_fold(stats, gamma, beta, scale_shift, ss_stride, n, chunk, C, HW, eps, k);
-  float Q[8], R[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int g = (chunk * 8 + j) / cpg;
-    Q[j] = coef[((long)n * 8 + g) * 2];
-    R[j] = coef[((long)n * 8 + g) * 2 + 1];
-  }
+  // C % 64 == 0 -> channels-per-group is a multiple of 8: the thread's 8 channels share one group
+  const int grp = (chunk * 8) / cpg;
+  const float Q = coef[((long)n * 8 + grp) * 2], R = coef[((long)n * 8 + grp) * 2 + 1];
   // P_c = rstd (scale+1) gamma = k.a (the folded forward slope)
   const long base = (long)n * HW;
   constexpr int U = 4;
@@ -230,7 +226,7 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const __nv_bfloat16* 
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const float dz = df[j] * silu_grad(k.a[j] * hf[j] + k.b[j]);
-        o[j] = k.a[j] * dz + Q[j] * hf[j] + R[j];
+        o[j] = k.a[j] * dz + Q * hf[j] + R;
       }
       *reinterpret_cast<uint4*>(dh + (base + p) * C + chunk * 8) = pack8(o);
     }
@@ -652,7 +648,7 @@ int fd_gn_silu_bwd(const void* h, const void* da, const double* gn_stats, const 
   const int chunks = C / 8;
   const int ppb = 256 / chunks > 0 ? 256 / chunks : 1;
   const long cap = (long)FD_NUM_SMS * 8 / N + 1;
-  long bx = ((long)HW + ppb * 2 - 1) / (ppb * 2);
+  long bx = ((long)HW + ppb * 4 - 1) / (ppb * 4);
   if (bx > cap) bx = cap;
   const __nv_bfloat16* hp = static_cast<const __nv_bfloat16*>(h);
   const __nv_bfloat16* dp = static_cast<const __nv_bfloat16*>(da);

@@ -234,13 +234,16 @@ class TrainMixin:
         qkv = self._t_conv(tape, name + ".to_qkv", y)
         att = torch.empty(n, h, w, 128, device=x.device, dtype=BF16)
         ws = torch.empty(lib.fd_linattn_workspace_floats(n, h * w), device=x.device, dtype=torch.float32)
-        _lib.check(lib.fd_linattn(_lib.ptr(qkv), _lib.ptr(att), _lib.ptr(ws), n, h * w, st))
+        stats = torch.empty(n, lib.fd_linattn_stats_floats(), device=x.device, dtype=torch.float32)
+        _lib.check(lib.fd_linattn_save(_lib.ptr(qkv), _lib.ptr(att), _lib.ptr(stats), _lib.ptr(ws), n, h * w, st))
+        del ws
 
         def bwd():
             datt = tape.pop(att)
             dqkv = torch.empty_like(qkv)
             wsb = torch.empty(lib.fd_linattn_bwd_workspace_floats(n, h * w), device=x.device, dtype=torch.float32)
-            _lib.check(lib.fd_linattn_bwd(_lib.ptr(qkv), _lib.ptr(datt), _lib.ptr(dqkv), _lib.ptr(wsb), n, h * w, st))
+            _lib.check(lib.fd_linattn_bwd(_lib.ptr(qkv), _lib.ptr(datt), _lib.ptr(dqkv), _lib.ptr(stats), _lib.ptr(wsb), n, h * w,
+                                          st))
             tape.add_grad(qkv, dqkv)
 
         tape.record(bwd)

@@ -86,6 +86,8 @@ CASES = [
     (2, (64, 64), 64, 21, 256, (3, 3), (1, 1), True, False, True),      # rolling-strip kernel, two sources
     (1, (128,), 64, 70, 200, (3, 3), (1, 1), True, False, False),       # rolling-strip kernel, 128-channel source, ragged W
     (2, (64,), 64, 37, 130, (3, 3), (1, 1), True, False, True),         # ragged W: second column block is 2 pixels wide
+    (2, (64,), 64, 30, 256, (3, 3), (1, 1), True, True, True),          # rolling-strip kernel with a residual (dgrad accumulation)
+    (1, (64, 64), 64, 9, 130, (3, 3), (1, 1), False, True, False),      # two passes: caller's residual, then the partial sum
 ]
 
 

@@ -234,10 +234,19 @@ def test_linattn_bwd(L, hw):
     qh, dh = nhwc(qkv.detach()), nhwc(dout)
     dqkv = torch.empty_like(qh)
     ws = torch.empty(lib.fd_linattn_bwd_workspace_floats(N, H * W), device="cuda")
-    L.check(lib.fd_linattn_bwd(L.ptr(qh), L.ptr(dh), L.ptr(dqkv), L.ptr(ws), N, H * W, L.stream()))
+    L.check(lib.fd_linattn_bwd(L.ptr(qh), L.ptr(dh), L.ptr(dqkv), None, L.ptr(ws), N, H * W, L.stream()))
     got, want = nchw(dqkv), qkv.grad
     for name, sl in (("dq", slice(0, 128)), ("dk", slice(128, 256)), ("dv", slice(256, 384))):
         assert rel_err(got[:, sl], want[:, sl]) < 2e-2, (name, rel_err(got[:, sl], want[:, sl]))
+    # with the statistics saved by the forward pass: same result, and the forward output matches
+    att = torch.empty(N, H, W, 128, device="cuda", dtype=BF)
+    stats = torch.empty(N, lib.fd_linattn_stats_floats(), device="cuda")
+    wf = torch.empty(lib.fd_linattn_workspace_floats(N, H * W), device="cuda")
+    L.check(lib.fd_linattn_save(L.ptr(qh), L.ptr(att), L.ptr(stats), L.ptr(wf), N, H * W, L.stream()))
+    assert rel_err(nchw(att), out.detach()) < 1.5e-2
+    dq2 = torch.empty_like(qh)
+    L.check(lib.fd_linattn_bwd(L.ptr(qh), L.ptr(dh), L.ptr(dq2), L.ptr(stats), L.ptr(ws), N, H * W, L.stream()))
+    assert rel_err(nchw(dq2), nchw(dqkv)) < 1e-2
 
 
 @pytest.mark.parametrize("hw", [(4, 16), (9, 23), (24, 32)])
