@@ -184,13 +184,40 @@ __global__ void __launch_bounds__(256, 3) linattn_bwd_dctx_kernel(const __nv_bfl
 // ------------------------------------------------------------------------------------------------
 constexpr int kMatStride = kD + 8;
 
+// 4x4 transpose of 32-bit words across the 4 lanes of a quad: x[j] of lane i  <->  x[i] of lane j
+__device__ __forceinline__ void quad_transpose(uint32_t (&x)[4], int tq) {
+  const bool lo1 = (tq & 1) == 0, lo2 = (tq & 2) == 0;
+  uint32_t r0 = __shfl_xor_sync(0xffffffffu, lo1 ? x[1] : x[0], 1);
+  uint32_t r1 = __shfl_xor_sync(0xffffffffu, lo1 ? x[3] : x[2], 1);
+  if (lo1) { x[1] = r0; x[3] = r1; } else { x[0] = r0; x[2] = r1; }
+  r0 = __shfl_xor_sync(0xffffffffu, lo2 ? x[2] : x[0], 2);
+  r1 = __shfl_xor_sync(0xffffffffu, lo2 ? x[3] : x[1], 2);
+  if (lo2) { x[2] = r0; x[3] = r1; } else { x[0] = r0; x[1] = r1; }
+}
+// 32 channels of two pixel rows into accumulator (C) layout: each lane loads ONE 16-byte granule per row (a quad
+// covers the head's 64 contiguous bytes -> full sectors), then the quad transposes so that lane tq holds columns
+// nt*8 + 2*tq, +1 of every 8-column tile nt.
 __device__ __forceinline__ void load_c(uint32_t (&r)[4][2], const __nv_bfloat16* row0, const __nv_bfloat16* row1, bool ok0,
                                        bool ok1, int tq) {
+  uint4 a = make_uint4(0, 0, 0, 0), b = make_uint4(0, 0, 0, 0);
+  if (ok0) a = __ldg(reinterpret_cast<const uint4*>(row0 + tq * 8));
+  if (ok1) b = __ldg(reinterpret_cast<const uint4*>(row1 + tq * 8));
+  uint32_t x[4] = {a.x, a.y, a.z, a.w}, y[4] = {b.x, b.y, b.z, b.w};
+  quad_transpose(x, tq);
+  quad_transpose(y, tq);
 #pragma unroll
   for (int nt = 0; nt < 4; ++nt) {
-    r[nt][0] = ok0 ? __ldg(reinterpret_cast<const uint32_t*>(row0 + nt * 8 + 2 * tq)) : 0u;
-    r[nt][1] = ok1 ? __ldg(reinterpret_cast<const uint32_t*>(row1 + nt * 8 + 2 * tq)) : 0u;
+    r[nt][0] = x[nt];
+    r[nt][1] = y[nt];
   }
+}
+// the inverse: packed C-layout pairs -> one 16-byte store per lane and row
+__device__ __forceinline__ void store_c(uint32_t (&x)[4], uint32_t (&y)[4], __nv_bfloat16* row0, __nv_bfloat16* row1, bool ok0,
+                                        bool ok1, int tq) {
+  quad_transpose(x, tq);
+  quad_transpose(y, tq);
+  if (ok0) *reinterpret_cast<uint4*>(row0 + tq * 8) = make_uint4(x[0], x[1], x[2], x[3]);
+  if (ok1) *reinterpret_cast<uint4*>(row1 + tq * 8) = make_uint4(y[0], y[1], y[2], y[3]);
 }
 __device__ __forceinline__ void c_to_a(uint32_t (&a)[2][4], const uint32_t (&c)[4][2]) {
 #pragma unroll
@@ -289,16 +316,13 @@ __global__ void __launch_bounds__(128, 6) linattn_bwd_apply_kernel(const __nv_bf
         }
         dot0 += __shfl_xor_sync(0xffffffffu, dot0, 1); dot0 += __shfl_xor_sync(0xffffffffu, dot0, 2);
         dot1 += __shfl_xor_sync(0xffffffffu, dot1, 1); dot1 += __shfl_xor_sync(0xffffffffu, dot1, 2);
+        uint32_t o0[4], o1[4];
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt) {
-          const int c = hc + nt * 8 + 2 * tq;
-          if (ok0)
-            *reinterpret_cast<uint32_t*>(dr0 + c) = fd_pack_bf16(kScale * sm[nt][0] * (dqs[nt][0] - dot0),
-                                                                 kScale * sm[nt][1] * (dqs[nt][1] - dot0));
-          if (ok1)
-            *reinterpret_cast<uint32_t*>(dr1 + c) = fd_pack_bf16(kScale * sm[nt][2] * (dqs[nt][2] - dot1),
-                                                                 kScale * sm[nt][3] * (dqs[nt][3] - dot1));
+          o0[nt] = fd_pack_bf16(kScale * sm[nt][0] * (dqs[nt][0] - dot0), kScale * sm[nt][1] * (dqs[nt][1] - dot0));
+          o1[nt] = fd_pack_bf16(kScale * sm[nt][2] * (dqs[nt][2] - dot1), kScale * sm[nt][3] * (dqs[nt][3] - dot1));
         }
+        store_c(o0, o1, dr0 + hc, dr1 + hc, ok0, ok1, tq);
       }
       // ---------------- dk, dv
       {
@@ -319,6 +343,7 @@ __global__ void __launch_bounds__(128, 6) linattn_bwd_apply_kernel(const __nv_bf
           kc[nt][1] = fd_pack_bf16(ks[nt][2], ks[nt][3]);
         }
         c_to_a(ka, kc);
+        uint32_t k0[4], k1[4];
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt) {       // dks[p, d] = sum_e v[p,e] dctx[d,e]
           float dks[4] = {0.f, 0.f, 0.f, 0.f};
@@ -328,13 +353,10 @@ __global__ void __launch_bounds__(128, 6) linattn_bwd_apply_kernel(const __nv_bf
           mma_bf16(dks, va[1], bf[2], bf[3]);
           const int d = hc + nt * 8 + 2 * tq;
           const float r0 = s_r[d], r1 = s_r[d + 1];
-          if (ok0)
-            *reinterpret_cast<uint32_t*>(dr0 + kHidden + d) = fd_pack_bf16(ks[nt][0] * (dks[0] * inv_hw - r0),
-                                                                           ks[nt][1] * (dks[1] * inv_hw - r1));
-          if (ok1)
-            *reinterpret_cast<uint32_t*>(dr1 + kHidden + d) = fd_pack_bf16(ks[nt][2] * (dks[2] * inv_hw - r0),
-                                                                           ks[nt][3] * (dks[3] * inv_hw - r1));
+          k0[nt] = fd_pack_bf16(ks[nt][0] * (dks[0] * inv_hw - r0), ks[nt][1] * (dks[1] * inv_hw - r1));
+          k1[nt] = fd_pack_bf16(ks[nt][2] * (dks[2] * inv_hw - r0), ks[nt][3] * (dks[3] * inv_hw - r1));
         }
+        store_c(k0, k1, dr0 + kHidden + hc, dr1 + kHidden + hc, ok0, ok1, tq);
         float dv[4][4];
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt)
@@ -351,12 +373,13 @@ __global__ void __launch_bounds__(128, 6) linattn_bwd_apply_kernel(const __nv_bf
           mma_bf16(dv[2], ka[kk], b23[0], b23[1]);
           mma_bf16(dv[3], ka[kk], b23[2], b23[3]);
         }
+        uint32_t v0[4], v1[4];
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt) {
-          const int c = 2 * kHidden + hc + nt * 8 + 2 * tq;
-          if (ok0) *reinterpret_cast<uint32_t*>(dr0 + c) = fd_pack_bf16(dv[nt][0] * inv_hw, dv[nt][1] * inv_hw);
-          if (ok1) *reinterpret_cast<uint32_t*>(dr1 + c) = fd_pack_bf16(dv[nt][2] * inv_hw, dv[nt][3] * inv_hw);
+          v0[nt] = fd_pack_bf16(dv[nt][0] * inv_hw, dv[nt][1] * inv_hw);
+          v1[nt] = fd_pack_bf16(dv[nt][2] * inv_hw, dv[nt][3] * inv_hw);
         }
+        store_c(v0, v1, dr0 + 2 * kHidden + hc, dr1 + 2 * kHidden + hc, ok0, ok1, tq);
       }
     }
   }

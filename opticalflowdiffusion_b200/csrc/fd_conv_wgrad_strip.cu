@@ -14,7 +14,7 @@
 //   M = 128 = two taps' 64 input channels (kx = 0 and kx = 1 of one kernel row: the second 64-row chunk of the
 //       A operand starts LBO = 128 B after the first), or one tap (kx = 2) with an ignored upper half;
 //   N = 64 output channels;  K = 16 pixels per instruction;  6 fp32 accumulators of 128 x 64 live in TMEM for the
-//   whole pixel range (384 columns).
+//   whole pixel range (384 columns).  Source and dy strips live in two separate TMA rings (8 x 17 KB, 5 x 16 KB).
 //
 // Work = (block pair, image, column block, row) units, flattened and cut into equal contiguous ranges, one per
 // CTA (one CTA per SM); a CTA flushes its accumulators into dW with fp32 reductions whenever its range crosses
@@ -30,12 +30,14 @@ constexpr int kStripPx = kTileW + 2;
 constexpr int kSrcTx = kStripPx * 128;          // bytes TMA delivers per source strip
 constexpr int kSrcSlot = 136 * 128;             // multiple of 1024: every slot keeps the swizzle phase
 constexpr int kDyTx = kTileW * 128;
-constexpr int kStageBytes = kSrcSlot + kDyTx;   // 33792
-constexpr int kNS = 5;                          // 3 source rows in use + 2 prefetched
+constexpr int kNSS = 8;                         // source-strip ring: 3 rows in use + 5 prefetched
+constexpr int kNSD = 5;                         // dy-strip ring: 1 row in use + 4 prefetched
+constexpr int kRingBytes = kNSS * kSrcSlot + kNSD * kDyTx;     // 221184: TMA latency, not smem bandwidth, is what
+                                                // starves the tensor pipe (ncu: 52 % active with 2 rows prefetched)
 constexpr int kGroups = 6;
 constexpr int kTmemCols = 512;
 constexpr int kThreads = 7 * 32;                // warp 0 TMA, warps 1-2 MMA issuers, warps 3-6 flush
-constexpr int kSmemBytes = 1024 + kNS * kStageBytes + 256;
+constexpr int kSmemBytes = 1024 + kRingBytes + 512;
 
 struct WsParams {
   int N, H, W;
@@ -86,12 +88,15 @@ wgrad3x3_strip_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_c
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
-  const uint32_t bar_base = base + kNS * kStageBytes;
-  auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (kNS + s); };
-  const uint32_t acc_full = bar_base + 8u * (2 * kNS);
-  const uint32_t acc_empty = bar_base + 8u * (2 * kNS + 1);
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(gbase + kNS * kStageBytes + 8 * (2 * kNS + 2) + 8);
+  const uint32_t dy_base = base + kNSS * kSrcSlot;
+  const uint32_t bar_base = base + kRingBytes;
+  auto sfull_bar = [&](int s) { return bar_base + 8u * s; };
+  auto sempty_bar = [&](int s) { return bar_base + 8u * (kNSS + s); };
+  auto dfull_bar = [&](int s) { return bar_base + 8u * (2 * kNSS + s); };
+  auto dempty_bar = [&](int s) { return bar_base + 8u * (2 * kNSS + kNSD + s); };
+  const uint32_t acc_full = bar_base + 8u * (2 * kNSS + 2 * kNSD);
+  const uint32_t acc_empty = bar_base + 8u * (2 * kNSS + 2 * kNSD + 1);
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(gbase + kRingBytes + 8 * (2 * kNSS + 2 * kNSD + 2) + 8);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   const long u_begin = (p.total_units * blockIdx.x) / gridDim.x;
@@ -101,9 +106,13 @@ wgrad3x3_strip_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_c
     tma_prefetch_desc(&map_a0);
     tma_prefetch_desc(&map_a1);
     tma_prefetch_desc(&map_dy);
-    for (int s = 0; s < kNS; ++s) {
-      mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 2);
+    for (int s = 0; s < kNSS; ++s) {
+      mbar_init(sfull_bar(s), 1);
+      mbar_init(sempty_bar(s), 2);
+    }
+    for (int s = 0; s < kNSD; ++s) {
+      mbar_init(dfull_bar(s), 1);
+      mbar_init(dempty_bar(s), 2);
     }
     mbar_init(acc_full, 2);
     mbar_init(acc_empty, 128);
@@ -118,7 +127,7 @@ wgrad3x3_strip_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_c
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      uint32_t seq = 0;
+      uint32_t seq = 0, dseq = 0;
       for (long u = u_begin; u < u_end;) {
         const Item it = next_item(p, u, u_end);
         const int ci_chunk = it.pair / p.co_chunks, co_chunk = it.pair % p.co_chunks;
@@ -126,12 +135,17 @@ wgrad3x3_strip_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_c
         const int c0 = (ci_chunk < p.chunks0 ? ci_chunk : ci_chunk - p.chunks0) * 64;
         const int rows = it.hb - it.ha;
         for (int j = 0; j < rows + 2; ++j, ++seq) {
-          const int slot = seq % kNS;
-          mbar_wait(empty_bar(slot), ((seq / kNS) & 1u) ^ 1u);
-          const uint32_t dst = base + slot * kStageBytes;
-          mbar_expect_tx(full_bar(slot), j < rows ? kSrcTx + kDyTx : kSrcTx);
-          tma_load_5d(dst, ma, full_bar(slot), c0, it.w0 - 1, it.ha - 1 + j, it.n, 0);
-          if (j < rows) tma_load_5d(dst + kSrcSlot, &map_dy, full_bar(slot), co_chunk * 64, it.w0, it.ha + j, it.n, 0);
+          const int slot = seq % kNSS;
+          mbar_wait(sempty_bar(slot), ((seq / kNSS) & 1u) ^ 1u);
+          mbar_expect_tx(sfull_bar(slot), kSrcTx);
+          tma_load_5d(base + slot * kSrcSlot, ma, sfull_bar(slot), c0, it.w0 - 1, it.ha - 1 + j, it.n, 0);
+          if (j < rows) {
+            const int ds = dseq % kNSD;
+            mbar_wait(dempty_bar(ds), ((dseq / kNSD) & 1u) ^ 1u);
+            mbar_expect_tx(dfull_bar(ds), kDyTx);
+            tma_load_5d(dy_base + ds * kDyTx, &map_dy, dfull_bar(ds), co_chunk * 64, it.w0, it.ha + j, it.n, 0);
+            ++dseq;
+          }
         }
         u += rows;
       }
@@ -140,7 +154,7 @@ wgrad3x3_strip_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_c
     // ===================== MMA issuers: warp 1 -> accumulators 0..2 (taps kx = 0|1 of row ky), warp 2 -> 3..5 (kx = 2)
     constexpr uint32_t idesc = idesc_bf16_mn(128, 64);
     const bool pairs = warp == 1;
-    uint32_t seq0 = 0;
+    uint32_t seq0 = 0, dseq0 = 0;
     int cur_pair = -1;
     uint32_t flushes = 0;
     bool fresh = true;
@@ -163,14 +177,15 @@ wgrad3x3_strip_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_c
 #pragma unroll
         for (int ky = 0; ky < 3; ++ky) {
           const uint32_t s = seq0 + i + ky;
-          mbar_wait(full_bar(s % kNS), (s / kNS) & 1u);
+          mbar_wait(sfull_bar(s % kNSS), (s / kNSS) & 1u);
         }
+        mbar_wait(dfull_bar((dseq0 + i) % kNSD), ((dseq0 + i) / kNSD) & 1u);
         tc_fence_after();
         if (lane == 0) {
-          const uint32_t dy = base + ((seq0 + i) % kNS) * kStageBytes + kSrcSlot;
+          const uint32_t dy = dy_base + ((dseq0 + i) % kNSD) * kDyTx;
 #pragma unroll
           for (int ky = 0; ky < 3; ++ky) {
-            const uint32_t strip = base + ((seq0 + i + ky) % kNS) * kStageBytes;
+            const uint32_t strip = base + ((seq0 + i + ky) % kNSS) * kSrcSlot;
             const uint32_t a0 = strip + (pairs ? 0 : 2 * 128);
             const uint32_t lbo = pairs ? 128u : 0u;
             const uint32_t tmem_d = tmem_base + (uint32_t)((pairs ? ky : 3 + ky) * 64);
@@ -179,16 +194,18 @@ wgrad3x3_strip_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_c
               umma_bf16(tmem_d, desc_mn_sw128(a0 + k * 2048, lbo), desc_mn_sw128(dy + k * 2048, 0u), idesc,
                         (fresh && i == 0 && k == 0) ? 0u : 1u);
           }
-          umma_commit(empty_bar((seq0 + i) % kNS));
+          umma_commit(sempty_bar((seq0 + i) % kNSS));
+          umma_commit(dempty_bar((dseq0 + i) % kNSD));
           if (i == rows - 1) {
-            umma_commit(empty_bar((seq0 + i + 1) % kNS));
-            umma_commit(empty_bar((seq0 + i + 2) % kNS));
+            umma_commit(sempty_bar((seq0 + i + 1) % kNSS));
+            umma_commit(sempty_bar((seq0 + i + 2) % kNSS));
           }
         }
         __syncwarp();
       }
       fresh = false;
       seq0 += rows + 2;
+      dseq0 += rows;
       u += rows;
     }
     if (cur_pair >= 0 && lane == 0) umma_commit(acc_full);
