@@ -198,6 +198,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     # roofline pass (not timed above): CUDA events around every tensor-core conv launch of one UNet forward
     algo.unet._conv_timing = []
     t = torch.full((BATCH,), 999, device=dev, dtype=torch.long)
+    torch.set_grad_enabled(False)          # the inference forward (with autograd on, unet(...) is the training forward)
     algo.unet(x_T, cond_dev, t)
     torch.cuda.synchronize()
     conv_s = sum(ev[0].elapsed_time(ev[1]) for _, _, ev in algo.unet._conv_timing) * 1e-3
@@ -211,6 +212,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     e.record()
     torch.cuda.synchronize()
     fwd_s = s.elapsed_time(e) * 1e-3
+    torch.set_grad_enabled(True)
 
     train = None
     if not args.skip_train:

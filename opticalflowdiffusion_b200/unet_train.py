@@ -412,6 +412,9 @@ class UnetFunction(torch.autograd.Function):
     @torch.autograd.function.once_differentiable
     def backward(ctx, dout):
         unet = ctx.unet
+        if ctx.run_backward is None:
+            raise RuntimeError("UnetFunction: the activations were released by the first backward pass "
+                               "(retain_graph / double backward are not supported on this path)")
         gb = unet.grad_buffer
         gb.zero_()
         ctx.run_backward(dout)

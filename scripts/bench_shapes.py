@@ -25,6 +25,7 @@ def timed(fn, iters=3):
 
 
 res = {}
+torch.set_grad_enabled(False)      # inference forward (with autograd on, unet(...) is the training forward)
 torch.manual_seed(0)
 flow_algo = FlowDiffuser(compose(["algorithm.target=flow", "algorithm.sampling_timesteps=50"]).algorithm).cuda()
 joint_algo = FlowDiffuser(compose(["algorithm.target=joint", "algorithm.sampling_timesteps=50",

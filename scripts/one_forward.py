@@ -11,6 +11,7 @@ from opticalflowdiffusion_b200.datasets import synthetic_frames  # noqa: E402
 
 B = int(os.environ.get("BATCH", 8))
 H, W = int(os.environ.get("HEIGHT", 436)), int(os.environ.get("WIDTH", 1024))
+torch.set_grad_enabled(False)      # inference forward (with autograd on, unet(...) is the training forward)
 torch.manual_seed(0)
 algo = FlowDiffuser(compose(["algorithm.target=flow", "algorithm.sampling_timesteps=50"]).algorithm).cuda()
 cond = (2 * synthetic_frames(B, H, W, 0) - 1).cuda()

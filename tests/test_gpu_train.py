@@ -71,7 +71,7 @@ def test_unet_backward_golden_16x24(golden):
     assert out.requires_grad and out.grad_fn is not None
     from opticalflowdiffusion_b200 import warp
     loss = warp.nan_mse(out, x0.cuda())
-    assert abs(float(loss) - ref_loss) < 2e-3 * max(1.0, abs(ref_loss))
+    assert abs(float(loss.detach()) - ref_loss) < 2e-3 * max(1.0, abs(ref_loss))
     n0 = _lib.load().fd_launch_count()
     loss.backward()
     assert _lib.load().fd_launch_count() - n0 > 300          # the backward ran on the library's kernels
@@ -195,3 +195,21 @@ def test_training_step_through_the_splat(target):
         opt.zero_grad(set_to_none=True)
         losses.append(float(loss.detach()))
     assert losses[-1] < losses[0], losses
+
+
+def test_experiment_train_task():
+    """`experiment.tasks=[train]` through the runner (exp_base.py:178-214 without Lightning): loader -> training_step
+    (with the Augmentor, flow_diffuser.py:219) -> backward -> clip + FusedAdam, two optimiser steps."""
+    from opticalflowdiffusion_b200.config import compose
+    from opticalflowdiffusion_b200.experiments import build_experiment
+    cfg = compose(["algorithm.target=flow", "dataset.height=32", "dataset.width=32", "dataset.length=8",
+                   "experiment.training.data.batch_size=2", "experiment.training.data.shuffle=false"])
+    torch.manual_seed(0)
+    exp = build_experiment(cfg, None, None)
+    before = exp.algo.unet.init_conv.weight.detach().clone()
+    out = exp.train(max_steps=2)
+    assert out["steps"] == 2 and len(out["train/loss"]) == 2
+    assert all(np.isfinite(v) for v in out["train/loss"])
+    after = exp.algo.unet.init_conv.weight.detach().cpu()
+    assert not torch.equal(before, after)                        # the fused Adam moved the parameters
+    assert "train/loss" in exp.algo.logged
