@@ -241,6 +241,16 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     }
     if train is not None:
         line["train"] = train
+    if world == 1 and not args.skip_warp:
+        # BASELINE configs[3]: fused backward-warp + photometric / EPE microbench, 8x2x436x1024 flow over 3-channel frames,
+        # L2 flushed between iterations; GB/s over the ALGORITHMIC bytes (fwd 40 B/px, bwd 60 B/px)
+        sys.path.insert(0, os.path.join(ROOT, "scripts"))
+        import bench_warp
+        wm = bench_warp.measure(iters=20, warmup=5)
+        line["warp_microbench"] = {k: dict(v, frac_of_hbm_peak=round(v["GBps"] / peaks["hbm"], 3)) for k, v in wm.items()
+                                   if k in ("photo_epe_fwd", "photo_epe_bwd", "backwarp_fwd", "backwarp_bwd", "splat_fwd",
+                                            "splat_flowgrad")}
+        line["warp_microbench"]["hbm_peak_GBps"] = peaks["hbm"]
     if world == 1 and not args.no_cpu_baseline:
         ts = cpu_reference_step_seconds(1, 1)
         tcpu = sum(ts) / len(ts)
@@ -357,6 +367,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--graph", type=int, default=1, help="replay the DDIM loop as one CUDA graph (1) or launch eagerly (0)")
     ap.add_argument("--train-batch", type=int, default=8, help="per-GPU batch of the training leg (368x768 crops)")
+    ap.add_argument("--skip-warp", action="store_true", help="omit the warp + photometric/EPE microbench (BASELINE configs[3])")
     ap.add_argument("--skip-train", action="store_true", help="omit the training leg (BASELINE configs[2])")
     ap.add_argument("--skip-sample", action="store_true", help="training leg only (debug; prints a reduced line)")
     args = ap.parse_args()

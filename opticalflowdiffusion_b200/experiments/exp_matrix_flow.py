@@ -15,13 +15,14 @@ import torch
 import torch.distributed as dist
 
 from ..datasets import SyntheticSintelDataset
+from ..io_formats import SintelFlowDataset, load_checkpoint
 from ..flow_diffuser import FlowDiffuser
 from ..parallel import reduce_metrics
 
 
 class MatrixFlowExperiment:
     compatible_algorithms = dict(flow_diffuser=FlowDiffuser)
-    compatible_datasets = dict(synthetic_sintel=SyntheticSintelDataset)
+    compatible_datasets = dict(synthetic_sintel=SyntheticSintelDataset, sintel=SintelFlowDataset)
 
     def __init__(self, cfg, logger=None, ckpt_path: Optional[str] = None):
         self.cfg, self.logger, self.ckpt_path = cfg, logger, ckpt_path
@@ -37,8 +38,7 @@ class MatrixFlowExperiment:
                              f"(have: {sorted(self.compatible_algorithms)})")
         algo = self.compatible_algorithms[name](self.cfg.algorithm)
         if self.ckpt_path:
-            sd = torch.load(self.ckpt_path, map_location="cpu")
-            algo.load_state_dict(sd.get("state_dict", sd))
+            load_checkpoint(algo, self.ckpt_path)        # Lightning .ckpt or bare state_dict, any alias family
         algo.logger = self.logger
         return algo
 

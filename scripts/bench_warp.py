@@ -29,7 +29,7 @@ def timeit(fn, iters=50, warmup=10, flush=None):
     return ts[len(ts) // 2]
 
 
-def main():
+def measure(iters=50, warmup=10):
     lib = _lib.load(check_device=True)
     B, C, H, W = 8, 3, 436, 1024
     g = torch.Generator().manual_seed(3)
@@ -52,21 +52,21 @@ def main():
     def rec(name, t, nbytes):
         res[name] = {"us": round(t * 1e6, 2), "GBps": round(nbytes / t / 1e9, 1), "bytes": nbytes}
 
-    t = timeit(lambda: _lib.check(lib.fd_backwarp_photo_epe_fwd(P(f1), P(f2), P(flow), P(gt), P(sums), P(ws), B, C, H, W, st)), flush=flush)
+    t = timeit(lambda: _lib.check(lib.fd_backwarp_photo_epe_fwd(P(f1), P(f2), P(flow), P(gt), P(sums), P(ws), B, C, H, W, st)), flush=flush, iters=iters, warmup=warmup)
     rec("photo_epe_fwd", t, 40 * px)
-    t = timeit(lambda: _lib.check(lib.fd_backwarp_photo_epe_bwd(P(f1), P(f2), P(flow), P(gt), P(sums), 1.0, 1.0, P(gflow), P(gf2), B, C, H, W, st)), flush=flush)
+    t = timeit(lambda: _lib.check(lib.fd_backwarp_photo_epe_bwd(P(f1), P(f2), P(flow), P(gt), P(sums), 1.0, 1.0, P(gflow), P(gf2), B, C, H, W, st)), flush=flush, iters=iters, warmup=warmup)
     rec("photo_epe_bwd", t, 60 * px)
-    t = timeit(lambda: _lib.check(lib.fd_backwarp_fwd(P(f2), P(flow), P(out), P(mask), B, C, H, W, st)), flush=flush)
+    t = timeit(lambda: _lib.check(lib.fd_backwarp_fwd(P(f2), P(flow), P(out), P(mask), B, C, H, W, st)), flush=flush, iters=iters, warmup=warmup)
     rec("backwarp_fwd", t, (8 + 12 + 12 + 12) * px)
-    t = timeit(lambda: _lib.check(lib.fd_backwarp_bwd(P(f2), P(flow), P(out), P(gf2), P(gflow), B, C, H, W, st)), flush=flush)
+    t = timeit(lambda: _lib.check(lib.fd_backwarp_bwd(P(f2), P(flow), P(out), P(gf2), P(gflow), B, C, H, W, st)), flush=flush, iters=iters, warmup=warmup)
     rec("backwarp_bwd", t, (8 + 12 + 12 + 12 + 8) * px)
     so = torch.empty_like(f2)
-    t = timeit(lambda: _lib.check(lib.fd_splat_fwd(P(f2), P(flow), P(so), B, C, H, W, 1, 0, 0, st)), flush=flush)
+    t = timeit(lambda: _lib.check(lib.fd_splat_fwd(P(f2), P(flow), P(so), B, C, H, W, 1, 0, 0, st)), flush=flush, iters=iters, warmup=warmup)
     rec("splat_fwd", t, (8 + 12 + 12) * px)
-    t = timeit(lambda: _lib.check(lib.fd_splat_flowgrad(P(f2), P(flow), P(out), P(gflow), B, C, H, W, 1, 0, 0, st)), flush=flush)
+    t = timeit(lambda: _lib.check(lib.fd_splat_flowgrad(P(f2), P(flow), P(out), P(gflow), B, C, H, W, 1, 0, 0, st)), flush=flush, iters=iters, warmup=warmup)
     rec("splat_flowgrad", t, (8 + 12 + 12 + 8) * px)
-    print(json.dumps(res))
+    return res
 
 
 if __name__ == "__main__":
-    main()
+    print(json.dumps(measure()))
