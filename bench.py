@@ -296,7 +296,7 @@ def run_train_leg(args, algo_cfg, rank: int, world: int, dev):
             torch.cuda.synchronize()
 
     def one_step(batch):
-        first, cond, _ = algo.preprocess(batch, aug=False)
+        first, cond, _ = algo.preprocess(batch, aug=True)          # fused GPU augmentation (augment.py)
         loss = algo.loss(first, cond, None)
         loss.backward()
         allreduce_gradients(opt)
@@ -332,7 +332,9 @@ def run_train_leg(args, algo_cfg, rank: int, world: int, dev):
     t_e2e = timed(step_e2e, steps)
     # phase split of one step (events on the launching stream)
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
-    first, cond, _ = algo.preprocess(batch_dev, aug=False)
+    ev_aug = torch.cuda.Event(enable_timing=True)
+    ev_aug.record()
+    first, cond, _ = algo.preprocess(batch_dev, aug=True)
     ev[0].record()
     loss = algo.loss(first, cond, None)
     ev[1].record()
@@ -351,11 +353,11 @@ def run_train_leg(args, algo_cfg, rank: int, world: int, dev):
             "e2e": {"value": samples / t_e2e, "unit": "samples/s", "h2d_bytes_per_step": 4 * (img_h.numel() + tgt_h.numel() + flow_h.numel()),
                     "d2h_bytes_per_step": 4},
             "gpu_launches": launches, "loss_first": float(first_loss.detach()), "loss_last": float(loss.detach()),
-            "phases_ms": {"forward+loss": ev[0].elapsed_time(ev[1]), "backward": ev[1].elapsed_time(ev[2]),
+            "phases_ms": {"augment+preprocess": ev_aug.elapsed_time(ev[0]), "forward+loss": ev[0].elapsed_time(ev[1]), "backward": ev[1].elapsed_time(ev[2]),
                           "allreduce+clip+adam": ev[2].elapsed_time(ev[3])},
             "tensor_tflops": TRAIN_GF_PER_SAMPLE * value / 1e3 / world, "peak_mem_gib": peak_mem,
-            "config": "flow_diffuser training step, target=flow, synthetic 368x768 crops, aug off (the Augmentor is host-side "
-                      "python RNG), Adam lr 1e-5 wd 1e-6, clip 100, gradient all-reduce over NCCL when n_gpus > 1"}
+            "config": "flow_diffuser training step, target=flow, synthetic 368x768 crops, augmentation ON (GpuAugmentor: "
+                      "reference Augmentor semantics, decisions on the host, arithmetic in 4 launches), Adam lr 1e-5 wd 1e-6, clip 100, gradient all-reduce over NCCL when n_gpus > 1"}
 
 
 def main():

@@ -274,6 +274,25 @@ FD_API int fd_adam_step(float* param, const float* grad, float* exp_avg, float* 
                  float beta1, float beta2, float eps, float weight_decay, int step, const float* grad_sumsq,
                  float max_norm, float grad_scale, void* stream);
 
+/* ---- training augmentation on the GPU: augmentation.py:6-76 (torchvision ColorJitter / Grayscale / GaussianBlur(3) /
+ *      flips / RandomResizedCrop, applied item by item in the reference).  fp32 NCHW images in [0,1].
+ * frame tables have 2B rows (item*2 + {0: img, 1: tgt}):
+ *   frame_ints  [8] = {jitter_on, op0..op3 (0 brightness, 1 contrast, 2 saturation, 3 hue, applied in this order),
+ *                      gray_on, blur_on, -};   frame_floats [8] = {brightness, contrast, saturation, hue, k_edge, k_center, -, -}
+ * item_ints [8] = {hflip, vflip, crop_on, top, left, crop_h, crop_w, -}.
+ * photometric: frames_out (B,2,3,H,W) = Grayscale?(ColorJitter?(frame)); means: 2B floats of scratch.
+ * blur3: blurred[f] = GaussianBlur3(frames[f]) for the frames with blur_on (others untouched).
+ * geometric: reads frame f from `blurred` if blur_on else from `frames`; hflip negates the LAST flow channel, vflip the
+ *   second-last; the crop scales the flow by (crop_h/H, crop_w/W) and resamples all 8 channels bilinearly
+ *   (align_corners = False, no antialias) back to (H, W). */
+FD_API int fd_aug_photometric(const float* img, const float* tgt, const int* frame_ints, const float* frame_floats,
+                       float* means, float* frames_out, int B, int HW, void* stream);
+FD_API int fd_aug_blur3(const float* frames, const int* frame_ints, const float* frame_floats, float* blurred,
+                 int B, int H, int W, void* stream);
+FD_API int fd_aug_geometric(const float* frames, const float* blurred, const float* flow, const int* frame_ints,
+                     const int* item_ints, float* out_img, float* out_tgt, float* out_flow, int B, int H, int W,
+                     void* stream);
+
 /* debug / test helpers: fp32 NCHW <-> bf16 NHWC */
 FD_API int fd_nchw_to_nhwc_bf16(const float* x, void* out, int N, int C, int HW, void* stream);
 FD_API int fd_nhwc_bf16_to_nchw(const void* x, float* out, int N, int C, int HW, void* stream);

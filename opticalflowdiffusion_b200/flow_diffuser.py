@@ -64,7 +64,8 @@ def _cfg_get(cfg, key, default=None):
 
 
 class Augmentor:
-    """Training-time augmentation (augmentation.py:6-76), host-side torch/torchvision like the reference:
+    """Training-time augmentation (augmentation.py:6-76), host-side torch/torchvision like the reference (kept as the
+    executable specification of ``augment.GpuAugmentor``, which FlowDiffuser uses on CUDA batches):
     per item, (a) photometric jitter / grayscale / blur applied to both frames with jitter parameters drawn
     ONCE at construction, (b) horizontal flip negating the last flow channel, vertical flip negating the
     second-last, (c) random resized crop rescaling the flow by crop/size (square inputs, as in the reference)."""
@@ -180,9 +181,15 @@ class FlowDiffuser(_Base):
         self.use_cuda_graph = bool(_cfg_get(cfg, "use_cuda_graph", False))
 
     @property
-    def augmentor(self) -> Augmentor:
+    def augmentor(self):
+        """The reference builds its Augmentor in ``__init__`` (flow_diffuser.py:101); here it is the GPU implementation
+        (``gpu_augment: false`` in the algorithm config selects the per-item torchvision path)."""
         if self._augmentor is None:
-            self._augmentor = Augmentor()
+            if bool(_cfg_get(self.cfg, "gpu_augment", True)):
+                from .augment import GpuAugmentor
+                self._augmentor = GpuAugmentor()
+            else:
+                self._augmentor = Augmentor()
         return self._augmentor
 
     def configure_optimizers(self):
