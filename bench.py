@@ -267,6 +267,36 @@ TRAIN_H, TRAIN_W = 368, 768
 TRAIN_GF_PER_SAMPLE = 3.0 * 1019.83      # SURVEY.md section 8d: forward 1019.83 GF at 368x768, fwd + bwd ~ 3x
 
 
+def cpu_train_baseline():
+    """The reference algorithm's training step (p_losses + backward through the oracle's fp32 restatement, no optimiser)
+    on the host cores at a 64x64 crop, batch 1 (SURVEY.md 8d config #3), extrapolated to 368x768 by pixel count."""
+    from oracle import flowdiff_oracle as O
+    from opticalflowdiffusion_b200.unet_params import UnetParams
+    try:
+        torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
+    except Exception:  # noqa: BLE001
+        pass
+    torch.manual_seed(0)
+    sd = {k: v.clone().requires_grad_(True) for k, v in UnetParams(64, channels=5, out_dim=2).state_dict().items()}
+    sched = O.make_schedule(TIMESTEPS)
+    g = torch.Generator().manual_seed(3)
+    x0 = torch.rand(1, 2, 64, 64, generator=g) * 2 - 1
+    cond = torch.rand(1, 3, 64, 64, generator=g) * 2 - 1
+    noise = torch.randn(1, 2, 64, 64, generator=g)
+    t = torch.tensor([500])
+    ts = []
+    for i in range(3):
+        t0 = time.perf_counter()
+        loss = O.p_losses_flow(sd, sched, x0, cond, t, noise)
+        loss.backward()
+        ts.append(time.perf_counter() - t0)
+    sec = min(ts[1:])
+    scale = (TRAIN_H * TRAIN_W) / (64.0 * 64.0)
+    return {"value": 1.0 / (sec * scale), "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": "forward + backward of ONE 64x64 crop (p_losses, target=flow) after a warm-up, extrapolated x%.0f by "
+                      "pixel count to 368x768" % scale}
+
+
 def run_train_leg(args, algo_cfg, rank: int, world: int, dev):
     """BASELINE configs[2]: one training step (preprocess -> q_sample -> UNet fwd -> loss -> UNet bwd -> gradient
     all-reduce -> fused clip + Adam) at 368x768 crops, batch-sharded data parallel.  Returns the "train" object."""
@@ -345,6 +375,9 @@ def run_train_leg(args, algo_cfg, rank: int, world: int, dev):
     opt.zero_grad(set_to_none=True)
     ev[3].record()
     torch.cuda.synchronize()
+    cpu = None
+    if world == 1 and rank == 0 and not args.no_cpu_baseline:
+        cpu = cpu_train_baseline()
     samples = world * B * steps
     value = samples / t_res
     peak_mem = torch.cuda.max_memory_allocated(dev) / 2 ** 30
@@ -355,7 +388,7 @@ def run_train_leg(args, algo_cfg, rank: int, world: int, dev):
             "gpu_launches": launches, "loss_first": float(first_loss.detach()), "loss_last": float(loss.detach()),
             "phases_ms": {"augment+preprocess": ev_aug.elapsed_time(ev[0]), "forward+loss": ev[0].elapsed_time(ev[1]), "backward": ev[1].elapsed_time(ev[2]),
                           "allreduce+clip+adam": ev[2].elapsed_time(ev[3])},
-            "tensor_tflops": TRAIN_GF_PER_SAMPLE * value / 1e3 / world, "peak_mem_gib": peak_mem,
+            "tensor_tflops": TRAIN_GF_PER_SAMPLE * value / 1e3 / world, "peak_mem_gib": peak_mem, "cpu_baseline": cpu,
             "config": "flow_diffuser training step, target=flow, synthetic 368x768 crops, augmentation ON (GpuAugmentor: "
                       "reference Augmentor semantics, decisions on the host, arithmetic in 4 launches), Adam lr 1e-5 wd 1e-6, clip 100, gradient all-reduce over NCCL when n_gpus > 1"}
 

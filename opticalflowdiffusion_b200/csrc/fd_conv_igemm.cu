@@ -286,7 +286,7 @@ int fd_conv_igemm_ex(const void* src0, int C0, const void* src1, int C1, const v
     static int strip_mode = -1;
     if (strip_mode < 0) {
       const char* e = getenv("FD_CONV_STRIP");
-      strip_mode = e ? atoi(e) : 2;      // 2: nine N = 64 taps (default), 3: wide N = 192 variant, 1: base_offset experiment, 0: off
+      strip_mode = e ? atoi(e) : 2;      // 2: default, 1: base_offset experiment (measured wrong), 0: off
     }
     const bool chans_ok = (C0 == 64 && (C1 == 0 || C1 == 64)) || (C0 == 128 && C1 == 0);
     if (strip_mode > 0 && mode == 0 && KH == 3 && KW == 3 && pad_h == 1 && pad_w == 1 && chans_ok && Cout == 64 &&

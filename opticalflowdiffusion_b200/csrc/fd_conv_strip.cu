@@ -17,14 +17,14 @@
 // 144 KB of weights per tile instead was measured to be no faster than the generic kernel (chip-level L2->SM
 // bandwidth), while two resident-weight passes cost 0.75 ms instead of 1.09 ms.
 //
-// WIDE variant (FD_CONV_STRIP=3, experimental: correct, but its heavier epilogue makes it slower than the classic path --
-// 0.386 vs 0.278 ms for 64->64 at 8x440x1024 -- until the epilogue latency is hidden as well).  Measured (scripts/micro/umma_rate.cu, profiles/r1_umma_rate.txt): an SS-mode
-// 128xNx16 UMMA reads (128 + N) * 32 bytes of shared memory at 128 B/clk, so the N = 64 instruction takes 48 cycles, not
-// 32 -- nine N = 64 taps cap the kernel at 67 % of the tensor peak.  The three kx taps of one kernel row therefore run as
-// ONE N = 192 instruction on the UNSHIFTED strip: D[p][kx][co] = sum_ci A[p][ci] W[ky][kx][ci][co] (the three 8 KB weight
-// tiles of a kernel row are already contiguous in shared memory = a 192-row K-major tile), and the pixel shift moves to
-// the epilogue:  out[x] = D[x-1][0] + D[x][1] + D[x+1][2]  -- two warp shuffles per value plus a 3-row exchange between
-// the TMEM lane quarters.  12 instructions of 96 cycles per tile instead of 36 of 48; a tile yields 126 output pixels.
+// Where the time goes (ncu + scripts/micro/umma_rate.cu, profiles/r1_umma_rate.txt): an SS-mode 128xNx16 UMMA reads
+// (128 + N) * 32 bytes of shared memory at 128 B/clk, so an N = 64 instruction takes 48 cycles, not 32.  Per 128-pixel tile
+// the 36 MMAs read 216 KB, TMA writes 16.6 KB, the epilogue writes and the TMA store reads 16 KB each: 265 KB = 2070
+// cycles of the shared-memory pipe out of the 2680 the tile takes (l1tex throughput 77 %, tensor pipe "active" 51 %).
+// The kernel is shared-memory-bandwidth bound.  Tried and measured slower (0.387 vs 0.268 ms for 64->64 at 8x440x1024):
+// one N = 192 instruction per kernel row on the unshifted strip with the kx shift done in the epilogue by warp shuffles --
+// 44 % less operand traffic, but 192 accumulator columns leave room for only two TMEM stages and the longer epilogue
+// (3 x tcgen05.ld, quarter-to-quarter row exchange) then sits on the critical path.
 #include "fd_conv_epi.cuh"
 
 using namespace fdtc;
@@ -36,17 +36,17 @@ constexpr int kTileW = 128;                    // output pixels per tile (one im
 constexpr int kStripPx = kTileW + 2;           // + left/right halo
 constexpr int kStripTx = kStripPx * 128;       // bytes TMA delivers per strip
 constexpr int kStripBytes = 136 * 128;         // slot size: multiple of 1024 keeps the swizzle phase of every slot
-constexpr int kNS = 5;                         // strips in flight: 3 in use + 2 prefetched
+constexpr int kNS = 5;                         // strips in flight: 3 in use + 2 prefetched (6 measured no faster)
 constexpr int kWTapBytes = kC * kC * 2;        // one tap of weights: [64 cout][64 cin] bf16
 constexpr int kWBytes = 9 * kWTapBytes;        // 72 KB, resident
 constexpr int kThreads = 64 + kEpiThreads + 32;  // warp 0 TMA, warps 1 and 10 MMA issuers (even / odd tiles), warps 2..9 epilogue
-constexpr int kTail = 256 + 2 * kC * 4 + kEpiWarps * 16 * 4 + 64 + 4 * 2 * 3 * 32 * 4;   // barriers, bias, stats, tmem ptr, wide-epilogue exchange
+constexpr int kTail = 256 + 2 * kC * 4 + kEpiWarps * 16 * 4 + 64;
 constexpr int kSmemBytes = 1024 + kWBytes + kNS * kStripBytes + 2 * kSlabBytes + kTail;
 
 struct StripParams {
   int N, H, W;
   int wblocks, segs, seg_rows, total_items;
-  int tile_w;                // output pixels per tile: 128 (classic) or 126 (wide)
+  int tile_w;                // output pixels per tile
   int base_offset_mode;      // 2 (default): base_offset 0 -- correct; 1: (addr >> 7) & 7 -- measured WRONG, kept as an experiment
   int c_off;                 // first input channel of this pass inside the source tensor (0 or 64)
   int w_k0, w_kstride;       // weight K coordinate of tap t = t * w_kstride + w_k0
@@ -63,164 +63,6 @@ __device__ __forceinline__ void decode_item(const StripParams& p, int item, int&
   w0 = wb * p.tile_w;
   ra = seg * p.seg_rows;
   rb = min(p.H, ra + p.seg_rows);
-}
-
-// Epilogue of the WIDE variant: accumulator stage = 192 columns [kx][co]; thread (row r, 32-column half) computes
-//   v[co] = D[r][0][co] + D[r+1][1][co] + D[r+2][2][co]
-// rows r+1 / r+2 come from the neighbouring lanes by shuffle; across the 32-lane TMEM quarters the first two rows of
-// the next quarter travel through a small shared-memory exchange area.  Rows 126 and 127 of a tile produce no output.
-constexpr int kWideCols = 3 * kC;
-constexpr int kWideTileW = kTileW - 2;
-constexpr int kXchgFloats = 4 * 2 * 3 * 32;        // [quarter][half][{a1 of lane 0, a2 of lane 0, a2 of lane 1}][32]
-
-template <int GPT, class NextTile>
-__device__ __forceinline__ void strip_wide_epilogue(const EpiCtx& ec, float* s_xchg, NextTile next_tile) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int ew = warp - 2, et = threadIdx.x - 64;
-  const int quarter = warp & 3, half = ew >> 2;
-  const int row = quarter * 32 + lane;
-  const int c = half * 32;
-  const bool issuer = (et == 0);
-  float* const s_bias = ec.s_bias;
-  float* const s_stats = ec.s_stats;
-  constexpr int CPGT = GPT > 0 ? kC / GPT : 32;      // 8 columns per group
-  constexpr int GIC = GPT > 0 ? 32 / CPGT : 1;       // 4 groups inside this thread's 32 columns
-  float st_s[GIC], st_q[GIC];
-#pragma unroll
-  for (int b = 0; b < GIC; ++b) st_s[b] = st_q[b] = 0.f;
-  int st_img = -1;
-  uint32_t slab_count = 0;
-  float* const xmine = s_xchg + ((quarter * 2 + half) * 3) * 32;
-  const float* const xnext = s_xchg + ((((quarter + 1) & 3) * 2 + half) * 3) * 32;
-
-  auto flush_stats = [&]() {
-    if (GPT == 0 || st_img < 0) return;
-    float* mine = s_stats + ew * 16;
-    if (lane < 16) mine[lane] = 0.f;
-    __syncwarp();
-#pragma unroll
-    for (int b = 0; b < GIC; ++b) {
-      const float s = fd_warp_sum(st_s[b]), q = fd_warp_sum(st_q[b]);
-      if (lane == 0) {
-        const int grp = (c + b * CPGT) / CPGT;
-        mine[grp * 2] += s;
-        mine[grp * 2 + 1] += q;
-      }
-      st_s[b] = st_q[b] = 0.f;
-    }
-    named_bar_sync(2, kEpiThreads);
-    if (et < 2 * GPT) {
-      float sv = 0.f;
-#pragma unroll
-      for (int w8 = 0; w8 < kEpiWarps; ++w8) sv += s_stats[w8 * 16 + et];
-      atomicAdd(ec.gn_stats + (long)st_img * 16 + et, (double)sv);
-    }
-    named_bar_sync(2, kEpiThreads);
-  };
-
-  EpiTile tc;
-  for (int iter = 0; next_tile(iter, tc); ++iter) {
-    const int as = iter & 1;
-    const uint32_t aphase = (iter >> 1) & 1;
-    const int img = tc.img, h = tc.h0, w0 = tc.w0;
-    const int w = w0 + row;
-    const bool valid = (row < kWideTileW) && (w < ec.W);
-    if (GPT > 0 && img != st_img) {
-      flush_stats();
-      st_img = img;
-    }
-    float* bias_s = s_bias + as * kC;
-    for (int i = et; i < kC; i += kEpiThreads) bias_s[i] = ec.bias ? __ldg(ec.bias + i) : 0.f;
-
-    mbar_wait(ec.tfull0 + 8u * as, aphase);
-    tc_fence_after();
-    uint32_t a0[32], a1[32], a2[32];
-    const uint32_t taddr = ec.tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * kWideCols + c);
-    tmem_ld32(taddr, a0);
-    tmem_ld32(taddr + kC, a1);
-    tmem_ld32(taddr + 2 * kC, a2);
-    tmem_ld_wait();
-    tc_fence_before();
-    mbar_arrive(ec.tempty0 + 8u * as);                 // the accumulator stage can be overwritten
-    // rows 0 / 1 of this quarter are rows 32 / 33 of the previous one
-    if (lane == 0) {
-#pragma unroll
-      for (int j4 = 0; j4 < 8; ++j4) {
-        *reinterpret_cast<uint4*>(xmine + j4 * 4) = make_uint4(a1[j4 * 4], a1[j4 * 4 + 1], a1[j4 * 4 + 2], a1[j4 * 4 + 3]);
-        *reinterpret_cast<uint4*>(xmine + 32 + j4 * 4) = make_uint4(a2[j4 * 4], a2[j4 * 4 + 1], a2[j4 * 4 + 2], a2[j4 * 4 + 3]);
-      }
-    } else if (lane == 1) {
-#pragma unroll
-      for (int j4 = 0; j4 < 8; ++j4)
-        *reinterpret_cast<uint4*>(xmine + 64 + j4 * 4) = make_uint4(a2[j4 * 4], a2[j4 * 4 + 1], a2[j4 * 4 + 2], a2[j4 * 4 + 3]);
-    }
-    const uint32_t buf = ec.o_smem + (slab_count & 1u) * kSlabBytes;
-    ++slab_count;
-    if (issuer) tma_store_wait_read<1>();              // the store that last used this slab has read it
-    named_bar_sync(1, kEpiThreads);                    // exchange rows + bias published; slab free
-    // lanes 0 / 1 stand in for rows 32 / 33: after the rotation lane 31 (and 30) receive the next quarter's rows
-    const int sel1 = 0, sel2 = lane == 0 ? 1 : 2;
-#pragma unroll
-    for (int j4 = 0; j4 < 8; ++j4) {
-      const uint4 n1 = *reinterpret_cast<const uint4*>(xnext + sel1 * 32 + j4 * 4);
-      const uint4 n2 = *reinterpret_cast<const uint4*>(xnext + sel2 * 32 + j4 * 4);
-      if (lane == 0) { a1[j4 * 4] = n1.x; a1[j4 * 4 + 1] = n1.y; a1[j4 * 4 + 2] = n1.z; a1[j4 * 4 + 3] = n1.w; }
-      if (lane < 2) { a2[j4 * 4] = n2.x; a2[j4 * 4 + 1] = n2.y; a2[j4 * 4 + 2] = n2.z; a2[j4 * 4 + 3] = n2.w; }
-    }
-    float v[32];
-#pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      const float t1 = __uint_as_float(__shfl_sync(0xffffffffu, a1[j], (lane + 1) & 31));
-      const float t2 = __uint_as_float(__shfl_sync(0xffffffffu, a2[j], (lane + 2) & 31));
-      v[j] = (__uint_as_float(a0[j]) + t1) + (t2 + bias_s[c + j]);
-    }
-    const long pix = ((long)img * ec.H + h) * ec.W + w;
-    if (ec.residual != nullptr && valid) {
-      const __nv_bfloat16* rrow = ec.residual + pix * kC + c;
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const uint4 r4 = __ldg(reinterpret_cast<const uint4*>(rrow) + q);
-        const uint32_t rw[4] = {r4.x, r4.y, r4.z, r4.w};
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float2 f = fd_unpack_bf16(rw[e]);
-          v[q * 8 + e * 2] += f.x;
-          v[q * 8 + e * 2 + 1] += f.y;
-        }
-      }
-    }
-    if (GPT > 0 && valid) {
-#pragma unroll
-      for (int b = 0; b < GIC; ++b) {
-        float s = 0.f, q = 0.f;
-#pragma unroll
-        for (int j = 0; j < CPGT; ++j) {
-          const float x = v[b * CPGT + j];
-          s += x;
-          q = fmaf(x, x, q);
-        }
-        st_s[b] += s;
-        st_q[b] += q;
-      }
-    }
-    const uint32_t rbase = buf + (uint32_t)row * 128u;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const uint32_t piece = (uint32_t)(half * 4 + q) ^ (uint32_t)(row & 7);
-      const uint32_t o0 = fd_pack_bf16(v[q * 8 + 0], v[q * 8 + 1]), o1 = fd_pack_bf16(v[q * 8 + 2], v[q * 8 + 3]);
-      const uint32_t o2 = fd_pack_bf16(v[q * 8 + 4], v[q * 8 + 5]), o3 = fd_pack_bf16(v[q * 8 + 6], v[q * 8 + 7]);
-      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rbase + piece * 16u), "r"(o0), "r"(o1), "r"(o2), "r"(o3)
-                   : "memory");
-    }
-    fence_proxy_async_smem();
-    named_bar_sync(1, kEpiThreads);                    // slab complete; exchange area may be rewritten
-    if (issuer) {
-      tma_store_5d(ec.map_out, buf, 0, w0, h, img, 0);
-      tma_store_commit();
-    }
-  }
-  flush_stats();
-  if (issuer) tma_store_wait_all();
 }
 
 // Epilogue of the classic (nine N = 64 taps) variant.  Measured: with all 8 epilogue warps working on ONE tile the
@@ -356,7 +198,7 @@ __device__ __forceinline__ void strip_epilogue2(const EpiCtx& ec, NextTile next_
   if (issuer) tma_store_wait_all();
 }
 
-template <int GPT, bool WIDE>
+template <int GPT>
 __global__ void __launch_bounds__(kThreads, 1)
 conv3x3_strip_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CUtensorMap map_w,
                      const __grid_constant__ CUtensorMap map_out, const StripParams p) {
@@ -376,7 +218,6 @@ conv3x3_strip_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_co
   float* s_bias = reinterpret_cast<float*>(gtail);
   float* s_stats = reinterpret_cast<float*>(gtail + 2 * kC * 4);
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(gtail + 2 * kC * 4 + kEpiWarps * 16 * 4);
-  float* s_xchg = reinterpret_cast<float*>(gtail + 2 * kC * 4 + kEpiWarps * 16 * 4 + 64);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
@@ -390,11 +231,11 @@ conv3x3_strip_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_co
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), WIDE ? kEpiThreads : 128);      // classic: each stage is drained by one group of 4 warps
+      mbar_init(tempty_bar(s), 128);      // each accumulator stage is drained by one group of 4 epilogue warps
     }
     fence_barrier_init();
   }
-  constexpr uint32_t kTmemCols = WIDE ? 512 : 2 * kC;
+  constexpr uint32_t kTmemCols = 2 * kC;
   if (warp == 1) tmem_alloc(smem_u32(s_tmem), kTmemCols);
   tc_fence_before();
   __syncthreads();
@@ -446,19 +287,6 @@ conv3x3_strip_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_co
         }
         tc_fence_after();
         if (lane == 0) {
-          if (WIDE) {
-            constexpr uint32_t idesc_w = umma_idesc_bf16(kBlockM, kWideCols);
-            const uint32_t tmem_d = tmem_base + as * kWideCols;
-#pragma unroll
-            for (int ky = 0; ky < 3; ++ky) {
-              const uint32_t strip = s_smem + ((seq0 + j + ky) % kNS) * kStripBytes;
-              const uint64_t adesc = umma_desc_sw128(strip);                               // unshifted: the shift is in the epilogue
-              const uint64_t bdesc = umma_desc_sw128(w_smem + ky * 3 * kWTapBytes);        // [kx][co] x ci: 192 rows
-#pragma unroll
-              for (int k = 0; k < kC / 16; ++k)
-                umma_bf16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc_w, (ky | k) != 0 ? 1u : 0u);
-            }
-          } else {
           const uint32_t tmem_d = tmem_base + as * kC;
 #pragma unroll
           for (int ky = 0; ky < 3; ++ky) {
@@ -473,7 +301,6 @@ conv3x3_strip_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_co
               for (int k = 0; k < kC / 16; ++k)
                 umma_bf16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (ky | kx | k) != 0 ? 1u : 0u);
             }
-          }
           }
           umma_commit(tfull_bar(as));
           umma_commit(empty_bar((seq0 + j) % kNS));                 // input row ra-1+j is no longer needed
@@ -522,8 +349,7 @@ conv3x3_strip_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_co
       ++j;
       return true;
     };
-    if (WIDE) strip_wide_epilogue<GPT>(ec, s_xchg, next);
-    else strip_epilogue2<GPT>(ec, next);
+    strip_epilogue2<GPT>(ec, next);
   }
 
   tc_fence_before();
@@ -547,10 +373,9 @@ int fd_conv3x3_strip_launch(const void* src0, int C0, const void* src1, int C1, 
   }
   const int cin = C0 + C1;
   const int passes = cin / 64;
-  const bool wide = base_offset_mode >= 3;
   StripParams p{};
   p.N = N; p.H = H; p.W = W;
-  p.tile_w = wide ? kWideTileW : kTileW;
+  p.tile_w = kTileW;
   p.wblocks = (W + p.tile_w - 1) / p.tile_w;
   // rows per item: 16..64, chosen for the best last-wave fill (ties -> taller segments: fewer halo reloads)
   int best_segs = 1;
@@ -580,10 +405,8 @@ int fd_conv3x3_strip_launch(const void* src0, int C0, const void* src1, int C1, 
   const int grid = p.total_items < sms ? p.total_items : sms;
   static bool attr_set = false;
   if (!attr_set) {
-    FD_CUDA(cudaFuncSetAttribute(conv3x3_strip_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    FD_CUDA(cudaFuncSetAttribute(conv3x3_strip_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    FD_CUDA(cudaFuncSetAttribute(conv3x3_strip_kernel<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    FD_CUDA(cudaFuncSetAttribute(conv3x3_strip_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    FD_CUDA(cudaFuncSetAttribute(conv3x3_strip_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    FD_CUDA(cudaFuncSetAttribute(conv3x3_strip_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     attr_set = true;
   }
   for (int pass = 0; pass < passes; ++pass) {
@@ -602,16 +425,10 @@ int fd_conv3x3_strip_launch(const void* src0, int C0, const void* src1, int C1, 
     // pass 0 adds the caller's residual (if any), pass 1 the partial sum of pass 0
     p.residual = static_cast<const __nv_bfloat16*>(pass > 0 ? out : residual);
     p.gn_stats = last ? gn_stats : nullptr;
-    if (wide) {
-      if (p.gn_stats != nullptr)
-        conv3x3_strip_kernel<8, true><<<grid, kThreads, kSmemBytes, st>>>(mi, mw, mo, p);
-      else
-        conv3x3_strip_kernel<0, true><<<grid, kThreads, kSmemBytes, st>>>(mi, mw, mo, p);
-    } else if (p.gn_stats != nullptr) {
-      conv3x3_strip_kernel<8, false><<<grid, kThreads, kSmemBytes, st>>>(mi, mw, mo, p);
-    } else {
-      conv3x3_strip_kernel<0, false><<<grid, kThreads, kSmemBytes, st>>>(mi, mw, mo, p);
-    }
+    if (p.gn_stats != nullptr)
+      conv3x3_strip_kernel<8><<<grid, kThreads, kSmemBytes, st>>>(mi, mw, mo, p);
+    else
+      conv3x3_strip_kernel<0><<<grid, kThreads, kSmemBytes, st>>>(mi, mw, mo, p);
     FD_LAUNCH_CHECK();
   }
   return FD_OK;
