@@ -144,3 +144,21 @@ def test_ddim_epe_vs_oracle_and_cuda_graph():
     g2 = m.model.sample(B, external_cond=cond.cuda(), x_T=x_T, use_cuda_graph=True)     # replay
     assert torch.equal(g1, g2)
     assert (g1 - out).abs().max().item() < 5e-3
+
+
+def test_matrix_flow_resolution_1024x2048():
+    """BASELINE configs[4] shape: one 1024x2048 frame pair (32768 tokens in the mid attention block, which the
+    reference cannot even allocate: its N x N score matrix is 17 GB per sample).  DDIM-2, finite, bounded, repeatable."""
+    from opticalflowdiffusion_b200 import FlowDiffuser
+    from opticalflowdiffusion_b200.config import compose
+    from opticalflowdiffusion_b200.datasets import synthetic_frames
+    torch.manual_seed(0)
+    algo = FlowDiffuser(compose(["algorithm.target=flow", "algorithm.sampling_timesteps=2",
+                                 "algorithm.return_all_timesteps=false"]).algorithm).cuda()
+    cond = (2 * synthetic_frames(1, 1024, 2048, seed=5) - 1).cuda()
+    x_T = torch.randn(1, 2, 1024, 2048, generator=torch.Generator().manual_seed(6)).cuda()
+    _, a = algo.sample(cond, torch.zeros(1, 2, 1024, 2048, device="cuda"), x_T=x_T)
+    _, b = algo.sample(cond, torch.zeros(1, 2, 1024, 2048, device="cuda"), x_T=x_T)
+    assert a.shape == (1, 2, 1024, 2048) and torch.isfinite(a).all()
+    assert float(a.abs().max()) <= 1.0 + 1e-6                      # x0 prediction is clamped to [-1, 1] (DDIM, :653-656)
+    assert (a - b).abs().max().item() < 5e-3
