@@ -293,6 +293,21 @@ FD_API int fd_aug_geometric(const float* frames, const float* blurred, const flo
                      const int* item_ints, float* out_img, float* out_tgt, float* out_flow, int B, int H, int W,
                      void* stream);
 
+/* ---- FlowLearner objective: flow_learner.py:133-222 -------------------------------------------------
+ * soft_charb: one (level, offset) term.  S, T (B, C+1, HW) are the RAW soft splats (softsplat_new.py:306-307 before the
+ * normalisation): warped = S[:C] / (S[C] + 1e-7), NaN where S[C] is not > 0 (fill_holes_nan, warp.py:273-276),
+ * target = T[:C] / (T[C] + 1e-7); sums = {sum of sqrt((target - warped)^2 + 1e-6) over non-NaN pairs, count, mean}
+ * (nan_charbonnier, warp.py:281-287).  bwd: gS = d(upstream[0] * mean)/dS.  partials: fd_loss_workspace_floats(B*HW). */
+FD_API size_t fd_loss_workspace_floats(long items);
+FD_API int fd_soft_charb_fwd(const float* S, const float* T, float* sums, float* partials, int B, int C, int HW, void* stream);
+FD_API int fd_soft_charb_bwd(const float* S, const float* T, const float* sums, const float* upstream, float* gS,
+                      int B, int C, int HW, void* stream);
+/* edgeaware_smoothness1 (warp.py:289-303): out[0] = loss; bwd: gflow = upstream[0] * dloss/dflow (image has no gradient) */
+FD_API int fd_edge_smooth_fwd(const float* img, const float* flow, float* out, float* partials, int B, int Ci, int Cf,
+                       int H, int W, void* stream);
+FD_API int fd_edge_smooth_bwd(const float* img, const float* flow, const float* upstream, float* gflow, int B, int Ci,
+                       int Cf, int H, int W, void* stream);
+
 /* debug / test helpers: fp32 NCHW <-> bf16 NHWC */
 FD_API int fd_nchw_to_nhwc_bf16(const float* x, void* out, int N, int C, int HW, void* stream);
 FD_API int fd_nhwc_bf16_to_nchw(const void* x, float* out, int N, int C, int HW, void* stream);

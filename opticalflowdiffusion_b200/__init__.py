@@ -7,13 +7,16 @@ plumbing (device memory, streams, ``torch.distributed``).  Build: ``python -m op
 """
 __version__ = "0.1.0"
 
-__all__ = ["FlowDiffuser", "Unet", "ConditionalDiffusion", "compose"]
+__all__ = ["FlowDiffuser", "FlowLearner", "Unet", "ConditionalDiffusion", "compose"]
 
 
 def __getattr__(name):      # lazy: importing the package must not need the built library
     if name == "FlowDiffuser":
         from .flow_diffuser import FlowDiffuser
         return FlowDiffuser
+    if name == "FlowLearner":
+        from .flow_learner import FlowLearner
+        return FlowLearner
     if name == "Unet":
         from .unet import Unet
         return Unet

@@ -17,11 +17,12 @@ import torch.distributed as dist
 from ..datasets import SyntheticSintelDataset
 from ..io_formats import SintelFlowDataset, load_checkpoint
 from ..flow_diffuser import FlowDiffuser
+from ..flow_learner import FlowLearner
 from ..parallel import reduce_metrics
 
 
 class MatrixFlowExperiment:
-    compatible_algorithms = dict(flow_diffuser=FlowDiffuser)
+    compatible_algorithms = dict(flow_diffuser=FlowDiffuser, flow_learner=FlowLearner)      # exp_99.py:22-28
     compatible_datasets = dict(synthetic_sintel=SyntheticSintelDataset, sintel=SintelFlowDataset)
 
     def __init__(self, cfg, logger=None, ckpt_path: Optional[str] = None):

@@ -48,8 +48,9 @@ class Unet(UnetParams, TrainMixin):
     WS_EPS = 1e-5       # WeightStandardizedConv2d with fp32 input (:107)
     LN_EPS = 1e-5       # LayerNorm with fp32 input (:122)
 
-    def __init__(self, dim: int = 64, channels: int = 5, out_dim: int = 2, dim_mults=(1, 2, 4, 8), groups: int = 8):
-        super().__init__(dim, channels, out_dim, tuple(dim_mults), groups)
+    def __init__(self, dim: int = 64, channels: int = 5, out_dim: int = 2, dim_mults=(1, 2, 4, 8), groups: int = 8,
+                 time_in: bool = True):
+        super().__init__(dim, channels, out_dim, tuple(dim_mults), groups, time_in)
         assert dim == 64 and tuple(dim_mults) == (1, 2, 4, 8) and groups == 8, \
             "the sm_100a path is specialised to the flow_diffuser UNet (dim 64, mults 1-2-4-8, 8 groups)"
         assert channels <= 9, "init_conv takes at most 9 input channels (7 taps x 9 <= 64)"
@@ -149,13 +150,15 @@ class Unet(UnetParams, TrainMixin):
         ws, bs, off = [], [], 0
         self._tproj_off = {}
         for name, rb in self._resblocks:
-            lin = rb.mlp[1]
             self._tproj_off[name] = off
+            if rb.mlp is None:
+                continue
+            lin = rb.mlp[1]
             off += lin.weight.shape[0]
             ws.append(lin.weight.detach().float())
             bs.append(lin.bias.detach().float())
-        self._tproj_w = torch.cat(ws, 0).contiguous()
-        self._tproj_b = torch.cat(bs, 0).contiguous()
+        self._tproj_w = torch.cat(ws, 0).contiguous() if ws else None
+        self._tproj_b = torch.cat(bs, 0).contiguous() if bs else None
         self._prepared_versions = ver
 
     # ------------------------------------------------------------------ kernel wrappers
@@ -197,7 +200,7 @@ class Unet(UnetParams, TrainMixin):
                                                self.LN_EPS, self._st))
         return out
 
-    def _resnet(self, name: str, rb: _ResnetBlock, x0: Tensor, x1: Optional[Tensor], ss: Tensor) -> Tensor:
+    def _resnet(self, name: str, rb: _ResnetBlock, x0: Tensor, x1: Optional[Tensor], ss: Optional[Tensor]) -> Tensor:
         """ResnetBlock.forward (:202-214)."""
         st1, st2 = self._next_stats(), self._next_stats()
         h1 = self._conv(name + ".block1.proj", x0, x1, stats=st1)
@@ -251,8 +254,8 @@ class Unet(UnetParams, TrainMixin):
         return s
 
     # ------------------------------------------------------------------ forward
-    def forward(self, x: Tensor, external_cond: Optional[Tensor], time: Tensor, nan_mask: bool = False,
-                return_taps: bool = False):
+    def forward(self, x: Tensor, external_cond: Optional[Tensor] = None, time: Optional[Tensor] = None,
+                nan_mask: bool = False, return_taps: bool = False):
         """``Unet.forward(x, external_cond, time)`` (:363-417): x (B,Cx,H,W) fp32, cond (B,Cc,H,W) fp32, time (B,)
         int64 -> (B,out_dim,H,W) fp32.  ``nan_mask`` folds UnetWithWarp's NaN -> 0 + mask channel
         (flow_diffuser.py:39-45) into the input packing.
@@ -264,9 +267,11 @@ class Unet(UnetParams, TrainMixin):
         return self._forward_infer(x, external_cond, time, nan_mask, return_taps)
 
     @torch.no_grad()
-    def _forward_infer(self, x: Tensor, external_cond: Optional[Tensor], time: Tensor, nan_mask: bool = False,
+    def _forward_infer(self, x: Tensor, external_cond: Optional[Tensor], time: Optional[Tensor], nan_mask: bool = False,
                        return_taps: bool = False):
         _lib.require_cuda(x, external_cond, time)
+        if self.time_in and time is None:
+            raise ValueError("when Unet takes time arg, time argument must be passed in")      # :378-379
         self.prepare()
         self._lib = _lib.load()
         self._st = _lib.stream()
@@ -288,18 +293,20 @@ class Unet(UnetParams, TrainMixin):
         x = x.contiguous()
         cond = cond.contiguous() if cond is not None else None
         H, W = H0 + ph, W0 + pw
-        time = time.to(torch.int64).contiguous()
         taps = {}
 
-        # time embedding (:319-324) and every block's (scale, shift) (:206-208)
-        temb = torch.empty(B, self.time_dim, device=dev, dtype=torch.float32)
-        tm = self.time_mlp
-        _lib.check(lib.fd_time_embed(_lib.ptr(time), _lib.ptr(tm[1].weight), _lib.ptr(tm[1].bias), _lib.ptr(tm[3].weight),
-                                     _lib.ptr(tm[3].bias), _lib.ptr(temb), B, self.dim, self.time_dim, st))
-        J = self._tproj_w.shape[0]
-        ss = torch.empty(B, J, device=dev, dtype=torch.float32)
-        _lib.check(lib.fd_time_proj(_lib.ptr(temb), _lib.ptr(self._tproj_w), _lib.ptr(self._tproj_b), _lib.ptr(ss), B,
-                                    self.time_dim, J, st))
+        # time embedding (:319-324) and every block's (scale, shift) (:206-208); none at all for Unet(time_in=False)
+        ss = temb = None
+        if self.time_in:
+            time = time.to(torch.int64).contiguous()
+            temb = torch.empty(B, self.time_dim, device=dev, dtype=torch.float32)
+            tm = self.time_mlp
+            _lib.check(lib.fd_time_embed(_lib.ptr(time), _lib.ptr(tm[1].weight), _lib.ptr(tm[1].bias), _lib.ptr(tm[3].weight),
+                                         _lib.ptr(tm[3].bias), _lib.ptr(temb), B, self.dim, self.time_dim, st))
+            J = self._tproj_w.shape[0]
+            ss = torch.empty(B, J, device=dev, dtype=torch.float32)
+            _lib.check(lib.fd_time_proj(_lib.ptr(temb), _lib.ptr(self._tproj_w), _lib.ptr(self._tproj_b), _lib.ptr(ss), B,
+                                        self.time_dim, J, st))
         self._stats = torch.zeros(2 * len(self._resblocks), B, 8, 2, device=dev, dtype=torch.float64)
         self._stats_i = 0
 
@@ -310,7 +317,8 @@ class Unet(UnetParams, TrainMixin):
         del packed
         r = h
         if return_taps:
-            taps["temb"] = temb
+            if temb is not None:
+                taps["temb"] = temb
             taps["init_conv"] = h
 
         skips: List[Tensor] = []

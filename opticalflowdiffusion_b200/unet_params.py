@@ -44,9 +44,10 @@ class _Block(_Holder):
 class _ResnetBlock(_Holder):
     """mlp.1 / block1 / block2 / res_conv (denoising_diffusion.py:190-200)."""
 
-    def __init__(self, cin: int, cout: int, time_dim: int, groups: int = 8):
+    def __init__(self, cin: int, cout: int, time_dim, groups: int = 8):
         super().__init__()
-        self.mlp = nn.Sequential(nn.SiLU(), nn.Linear(time_dim, cout * 2))
+        # time_emb_dim = None (Unet(time_in=False), :193-196) -> no mlp, Block1 runs without (scale, shift)
+        self.mlp = nn.Sequential(nn.SiLU(), nn.Linear(time_dim, cout * 2)) if time_dim is not None else None
         self.block1 = _Block(cin, cout, groups)
         self.block2 = _Block(cout, cout, groups)
         self.res_conv = nn.Conv2d(cin, cout, 1) if cin != cout else nn.Identity()
@@ -94,16 +95,17 @@ class UnetParams(_Holder):
     """dim=64, dim_mults=(1,2,4,8), resnet groups 8, sinusoidal time embedding."""
 
     def __init__(self, dim: int = 64, channels: int = 5, out_dim: int = 2,
-                 dim_mults: Tuple[int, ...] = (1, 2, 4, 8), groups: int = 8):
+                 dim_mults: Tuple[int, ...] = (1, 2, 4, 8), groups: int = 8, time_in: bool = True):
         super().__init__()
-        self.dim, self.channels, self.out_dim = dim, channels, out_dim
+        self.dim, self.channels, self.out_dim, self.time_in = dim, channels, out_dim, time_in
         self.init_conv = nn.Conv2d(channels, dim, 7, padding=3)
         dims: List[int] = [dim] + [dim * m for m in dim_mults]
         self.in_out = list(zip(dims[:-1], dims[1:]))
-        time_dim = dim * 4
+        time_dim = dim * 4 if time_in else None          # :306-318: no time_mlp at all when time_in is False
         self.time_dim = time_dim
-        self.time_mlp = nn.Sequential(nn.Identity(), nn.Linear(dim, time_dim), nn.GELU(),
-                                      nn.Linear(time_dim, time_dim))
+        if time_in:
+            self.time_mlp = nn.Sequential(nn.Identity(), nn.Linear(dim, time_dim), nn.GELU(),
+                                          nn.Linear(time_dim, time_dim))
         self.downs = nn.ModuleList()
         self.ups = nn.ModuleList()
         n = len(self.in_out)

@@ -276,6 +276,8 @@ class TrainMixin:
         parameter gradient into ``self.grad_buffer`` (caller zero-fills) and returns nothing: the network input
         (noised target + conditioning frames) carries no gradient in the reference's training step."""
         _lib.require_cuda(x, external_cond, time)
+        if self.time_in and time is None:
+            raise ValueError("when Unet takes time arg, time argument must be passed in")
         self.prepare()
         self._lib = _lib.load()
         self._st = _lib.stream()
@@ -297,42 +299,44 @@ class TrainMixin:
         x = x.contiguous()
         cond = cond.contiguous() if cond is not None else None
         H, W = H0 + ph, W0 + pw
-        time = time.to(torch.int64).contiguous()
         tape = Tape(self)
         gb = self._gb
+        ss = dss = None
+        if self.time_in:
+            time = time.to(torch.int64).contiguous()
 
-        temb = torch.empty(B, self.time_dim, device=dev, dtype=torch.float32)
-        pe = torch.empty(B, self.dim, device=dev, dtype=torch.float32)
-        pre = torch.empty(B, self.time_dim, device=dev, dtype=torch.float32)
-        tm = self.time_mlp
-        _lib.check(lib.fd_time_embed_save(_lib.ptr(time), _lib.ptr(tm[1].weight), _lib.ptr(tm[1].bias), _lib.ptr(tm[3].weight),
-                                          _lib.ptr(tm[3].bias), _lib.ptr(temb), _lib.ptr(pe), _lib.ptr(pre), B, self.dim,
-                                          self.time_dim, st))
-        J = self._tproj_w.shape[0]
-        ss = torch.empty(B, J, device=dev, dtype=torch.float32)
-        dss = torch.zeros(B, J, device=dev, dtype=torch.float32)
-        _lib.check(lib.fd_time_proj(_lib.ptr(temb), _lib.ptr(self._tproj_w), _lib.ptr(self._tproj_b), _lib.ptr(ss), B,
-                                    self.time_dim, J, st))
+            temb = torch.empty(B, self.time_dim, device=dev, dtype=torch.float32)
+            pe = torch.empty(B, self.dim, device=dev, dtype=torch.float32)
+            pre = torch.empty(B, self.time_dim, device=dev, dtype=torch.float32)
+            tm = self.time_mlp
+            _lib.check(lib.fd_time_embed_save(_lib.ptr(time), _lib.ptr(tm[1].weight), _lib.ptr(tm[1].bias), _lib.ptr(tm[3].weight),
+                                              _lib.ptr(tm[3].bias), _lib.ptr(temb), _lib.ptr(pe), _lib.ptr(pre), B, self.dim,
+                                              self.time_dim, st))
+            J = self._tproj_w.shape[0]
+            ss = torch.empty(B, J, device=dev, dtype=torch.float32)
+            dss = torch.zeros(B, J, device=dev, dtype=torch.float32)
+            _lib.check(lib.fd_time_proj(_lib.ptr(temb), _lib.ptr(self._tproj_w), _lib.ptr(self._tproj_b), _lib.ptr(ss), B,
+                                        self.time_dim, J, st))
 
-        def time_bwd():
-            td = self.time_dim
-            for name, rb in self._resblocks:          # each ResnetBlock.mlp Linear reads its own column range of dss
-                lin = rb.mlp[1]
-                o, k = self._tproj_off[name], lin.weight.shape[0]
-                _lib.check(lib.fd_linear_bwd_w(dss.data_ptr() + 4 * o, J, _lib.ptr(temb), td, _lib.ptr(gb.of(lin.weight)),
-                                               _lib.ptr(gb.of(lin.bias)), B, k, td, 1, st))
-            dtemb = torch.empty(B, td, device=dev, dtype=torch.float32)
-            _lib.check(lib.fd_linear_bwd_x(_lib.ptr(dss), J, _lib.ptr(self._tproj_w), _lib.ptr(temb), td, _lib.ptr(dtemb), td,
-                                           B, J, td, 1, st))
-            _lib.check(lib.fd_linear_bwd_w(_lib.ptr(dtemb), td, _lib.ptr(pre), td, _lib.ptr(gb.of(tm[3].weight)),
-                                           _lib.ptr(gb.of(tm[3].bias)), B, td, td, 2, st))
-            dpre = torch.empty(B, td, device=dev, dtype=torch.float32)
-            _lib.check(lib.fd_linear_bwd_x(_lib.ptr(dtemb), td, _lib.ptr(tm[3].weight), _lib.ptr(pre), td, _lib.ptr(dpre), td,
-                                           B, td, td, 2, st))
-            _lib.check(lib.fd_linear_bwd_w(_lib.ptr(dpre), td, _lib.ptr(pe), self.dim, _lib.ptr(gb.of(tm[1].weight)),
-                                           _lib.ptr(gb.of(tm[1].bias)), B, td, self.dim, 0, st))
+            def time_bwd():
+                td = self.time_dim
+                for name, rb in self._resblocks:          # each ResnetBlock.mlp Linear reads its own column range of dss
+                    lin = rb.mlp[1]
+                    o, k = self._tproj_off[name], lin.weight.shape[0]
+                    _lib.check(lib.fd_linear_bwd_w(dss.data_ptr() + 4 * o, J, _lib.ptr(temb), td, _lib.ptr(gb.of(lin.weight)),
+                                                   _lib.ptr(gb.of(lin.bias)), B, k, td, 1, st))
+                dtemb = torch.empty(B, td, device=dev, dtype=torch.float32)
+                _lib.check(lib.fd_linear_bwd_x(_lib.ptr(dss), J, _lib.ptr(self._tproj_w), _lib.ptr(temb), td, _lib.ptr(dtemb), td,
+                                               B, J, td, 1, st))
+                _lib.check(lib.fd_linear_bwd_w(_lib.ptr(dtemb), td, _lib.ptr(pre), td, _lib.ptr(gb.of(tm[3].weight)),
+                                               _lib.ptr(gb.of(tm[3].bias)), B, td, td, 2, st))
+                dpre = torch.empty(B, td, device=dev, dtype=torch.float32)
+                _lib.check(lib.fd_linear_bwd_x(_lib.ptr(dtemb), td, _lib.ptr(tm[3].weight), _lib.ptr(pre), td, _lib.ptr(dpre), td,
+                                               B, td, td, 2, st))
+                _lib.check(lib.fd_linear_bwd_w(_lib.ptr(dpre), td, _lib.ptr(pe), self.dim, _lib.ptr(gb.of(tm[1].weight)),
+                                               _lib.ptr(gb.of(tm[1].bias)), B, td, self.dim, 0, st))
 
-        tape.record(time_bwd)          # runs last: every block's d(scale, shift) is in dss by then
+            tape.record(time_bwd)          # runs last: every block's d(scale, shift) is in dss by then
 
         self._stats = torch.zeros(2 * len(self._resblocks), B, 8, 2, device=dev, dtype=torch.float64)
         self._stats_i = 0

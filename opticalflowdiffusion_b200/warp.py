@@ -293,3 +293,81 @@ def nan_mse(pred: Tensor, target: Tensor, reduction: str = "mean") -> Tensor:
 def charbonnier(x: Tensor, alpha: float = 0.5, eps: float = 1e-3) -> Tensor:
     """warp.py:278-279 / losses.py:46-47."""
     return torch.pow(torch.square(x) + eps ** 2, alpha)
+
+
+# --------------------------------------------------------------------------------------
+# FlowLearner objective (flow_learner.py:133-222): fused loss terms
+# --------------------------------------------------------------------------------------
+
+
+class _SoftCharbFn(torch.autograd.Function):
+    """softsplat's normalisation (softsplat_new.py:316-331) + fill_holes_nan (warp.py:273-276) + nan_charbonnier
+    (warp.py:281-287) of one (level, offset) term, from the RAW soft splats S (prediction) and T (target)."""
+
+    @staticmethod
+    def forward(ctx, S: Tensor, T: Tensor):
+        S, T = _f32c(S), _f32c(T)
+        assert S.shape == T.shape
+        B, C1, H, W = S.shape
+        lib = _lib.load()
+        sums = torch.empty(3, device=S.device, dtype=torch.float32)
+        ws = torch.empty(lib.fd_loss_workspace_floats(B * H * W), device=S.device, dtype=torch.float32)
+        _lib.check(lib.fd_soft_charb_fwd(_lib.ptr(S), _lib.ptr(T), _lib.ptr(sums), _lib.ptr(ws), B, C1 - 1, H * W, _lib.stream()))
+        ctx.save_for_backward(S, T, sums)
+        return sums[2].clone()
+
+    @staticmethod
+    def backward(ctx, g: Tensor):
+        S, T, sums = ctx.saved_tensors
+        B, C1, H, W = S.shape
+        gS = torch.empty_like(S)
+        g = g.detach().float().reshape(1).contiguous()
+        _lib.check(_lib.load().fd_soft_charb_bwd(_lib.ptr(S), _lib.ptr(T), _lib.ptr(sums), _lib.ptr(g), _lib.ptr(gS), B, C1 - 1,
+                                                 H * W, _lib.stream()))
+        return gS, None
+
+
+def soft_splat_charbonnier(S: Tensor, T: Tensor) -> Tensor:
+    return _SoftCharbFn.apply(S, T)
+
+
+def soft_splat_raw(tenIn: Tensor, tenFlow: Tensor, tenMetric: Tensor, scale: int, offset: Sequence[int]) -> Tensor:
+    """The un-normalised 'soft' splat: softsplat_func(cat(in * exp(metric), exp(metric))) (softsplat_new.py:306-309)."""
+    e = tenMetric.exp()
+    return softsplat_func.apply(torch.cat([tenIn * e, e], 1), tenFlow, scale, offset[0], offset[1])
+
+
+class _EdgeSmoothFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, image: Tensor, flow: Tensor):
+        image, flow = _f32c(image), _f32c(flow)
+        B, Ci, H, W = image.shape
+        Cf = flow.shape[1]
+        lib = _lib.load()
+        out = torch.empty(1, device=flow.device, dtype=torch.float32)
+        ws = torch.empty(lib.fd_loss_workspace_floats(B * H * W), device=flow.device, dtype=torch.float32)
+        _lib.check(lib.fd_edge_smooth_fwd(_lib.ptr(image), _lib.ptr(flow), _lib.ptr(out), _lib.ptr(ws), B, Ci, Cf, H, W,
+                                          _lib.stream()))
+        ctx.save_for_backward(image, flow)
+        return out[0].clone()
+
+    @staticmethod
+    def backward(ctx, g: Tensor):
+        image, flow = ctx.saved_tensors
+        B, Ci, H, W = image.shape
+        gflow = torch.empty_like(flow)
+        g = g.detach().float().reshape(1).contiguous()
+        _lib.check(_lib.load().fd_edge_smooth_bwd(_lib.ptr(image), _lib.ptr(flow), _lib.ptr(g), _lib.ptr(gflow), B, Ci,
+                                                  flow.shape[1], H, W, _lib.stream()))
+        return None, gflow
+
+
+def edgeaware_smoothness1(image: Tensor, flow: Tensor, edge_weight: float = 30) -> Tensor:
+    """warp.py:289-303 (edge_weight is fixed at the reference's default of 30 in the kernel)."""
+    assert edge_weight == 30
+    return _EdgeSmoothFn.apply(image, flow)
+
+
+def fill_holes_nan(img: Tensor, weights: Tensor) -> Tensor:
+    """warp.py:273-276."""
+    return torch.where(weights.expand_as(img) > 0, img, torch.full_like(img, float("nan")))

@@ -145,8 +145,10 @@ def unet_forward(sd: Dict[str, Tensor], x: Tensor, cond: Optional[Tensor], t: Te
     x = F.conv2d(x, sd["init_conv.weight"], sd["init_conv.bias"], padding=3)
     r = x.clone()
     taps["init_conv"] = x
-    temb = time_embedding(sd, t)
-    taps["temb"] = temb
+    temb = None
+    if "time_mlp.1.weight" in sd:            # Unet(time_in=False) has no time path at all (:306-318, 377-383)
+        temb = time_embedding(sd, t)
+        taps["temb"] = temb
     skips: List[Tensor] = []
     n_levels = 4
     for i in range(n_levels):
@@ -585,6 +587,89 @@ def warp_forward_flow(first: Tensor, flow: Tensor, scale: int = 1, set_nans: boo
     if set_nans:
         img = torch.where(wsum > 0, img, torch.full_like(img, float("nan")))
     return img
+
+
+# --------------------------------------------------------------------------------------
+# FlowLearner objective (flow_learner.py:133-222, warp.py:273-303, softsplat_new.py:278-333)
+# --------------------------------------------------------------------------------------
+
+
+class _SplatFn(torch.autograd.Function):
+    """softsplat_func (softsplat_new.py:339-733) over the three restated kernels."""
+
+    @staticmethod
+    def forward(ctx, ten_in, flow, scale, off_x, off_y):
+        ctx.save_for_backward(ten_in, flow)
+        ctx.geom = (scale, off_x, off_y)
+        return splat_forward(ten_in, flow, scale, off_x, off_y)
+
+    @staticmethod
+    def backward(ctx, gout):
+        ten_in, flow = ctx.saved_tensors
+        scale, ox, oy = ctx.geom
+        gin = splat_ingrad(ten_in.shape, flow, gout, scale, ox, oy) if ctx.needs_input_grad[0] else None
+        gflow = splat_flowgrad(ten_in, flow, gout, scale, ox, oy) if ctx.needs_input_grad[1] else None
+        return gin, gflow, None, None, None
+
+
+def softsplat_soft(ten_in: Tensor, flow: Tensor, metric: Tensor, scale: int, offset) -> Tensor:
+    """softsplat(..., strMode='soft', scale, offset): softsplat_new.py:306-331."""
+    x = torch.cat([ten_in * metric.exp(), metric.exp()], 1)
+    out = _SplatFn.apply(x, flow, scale, offset[0], offset[1])
+    norm = out[:, -1:] + 0.0000001
+    return torch.cat((out[:, :-1] / norm, out[:, -1:]), dim=1)
+
+
+def fill_holes_nan(img: Tensor, weights: Tensor) -> Tensor:
+    """warp.py:273-276."""
+    weights = weights.repeat((1, img.shape[1], 1, 1))
+    return torch.where(weights > 0, img, torch.full_like(img, float("nan")))
+
+
+def nan_charbonnier(pred: Tensor, target: Tensor) -> Tensor:
+    """warp.py:281-287."""
+    pred, target = pred.flatten(), target.flatten()
+    keep = torch.logical_not(torch.logical_or(torch.isnan(target), torch.isnan(pred)))
+    return torch.mean(charbonnier(pred[keep] - target[keep]))
+
+
+def edgeaware_smoothness1(image: Tensor, flow: Tensor, edge_weight: float = 30) -> Tensor:
+    """warp.py:289-303."""
+    igy = image[:, :, 1:, :] - image[:, :, :-1, :]
+    igx = image[:, :, :, 1:] - image[:, :, :, :-1]
+    fgy = flow[:, :, 1:, :] - flow[:, :, :-1, :]
+    fgx = flow[:, :, :, 1:] - flow[:, :, :, :-1]
+    yw = torch.exp(-edge_weight * torch.mean(igy ** 2, dim=1, keepdim=True))
+    xw = torch.exp(-edge_weight * torch.mean(igx ** 2, dim=1, keepdim=True))
+    return (torch.mean(xw * charbonnier(fgx)) + torch.mean(yw * charbonnier(fgy))) / 2
+
+
+FLOW_LEARNER_LEVELS = (1, 2, 4, 5, 7, 8, 10, 11, 14, 16)
+
+
+def flow_learner_objective(img: Tensor, tgt: Tensor, flow_pred: Tensor, weights: Tensor,
+                           levels=FLOW_LEARNER_LEVELS) -> Tensor:
+    """The loop of FlowLearner.loss (flow_learner.py:160-205) given the prediction (flow in pixels, splat weights)."""
+    photo = []
+    for level in levels:
+        terms = []
+        for a in range(level):
+            for b in range(level):
+                ww = softsplat_soft(img, flow_pred, weights, level, (a, b))
+                filled = fill_holes_nan(ww[:, :-1], ww[:, -1:])
+                tt = softsplat_soft(tgt, torch.zeros_like(flow_pred), torch.ones_like(weights), level, (a, b))
+                terms.append(nan_charbonnier(tt[:, :-1], filled))
+        photo.append(sum(terms) / len(terms))
+    loss = sum(photo) / len(photo)
+    return loss + edgeaware_smoothness1(img, flow_pred) * 0.01
+
+
+def flow_learner_loss(sd, tgt: Tensor, cond: Tensor, flow_max: float = 20.0, levels=FLOW_LEARNER_LEVELS,
+                      prefix: str = "") -> Tensor:
+    """FlowLearner.loss (flow_learner.py:133-222) for the flow representation: UnetWithWarp's inner Unet
+    (channels 6, out_dim 3, time_in False) -> flow * flow_max + weights -> multi-scale soft-splat Charbonnier."""
+    fw = unet_forward(sd, cond, None, None, prefix)
+    return flow_learner_objective(cond[:, :3], tgt, fw[:, :2] * flow_max, fw[:, 2:], levels)
 
 
 # --------------------------------------------------------------------------------------

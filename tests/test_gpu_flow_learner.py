@@ -1,0 +1,122 @@
+"""-m gpu: FlowLearner on the CUDA path against the reference-generated golden
+(tests/golden/flow_learner_32x32.npz) and against autograd through the oracle.
+
+Tolerance (stated): the bf16 UNet's prediction within 3e-2 of the reference's, the end-to-end loss within 2 %; the objective
+and its gradient given the reference's own prediction (fp32 on both sides) to 2e-5; the time-free UNet's parameter
+gradients to the tolerance of tests/test_gpu_train.py."""
+import random
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import flowdiff_oracle as O
+from test_flow_learner_oracle import T, build_learner
+
+pytestmark = pytest.mark.gpu
+
+
+def test_loss_kernels_vs_oracle():
+    from opticalflowdiffusion_b200 import warp as W
+    g = torch.Generator().manual_seed(3)
+    B, H, Wd = 2, 24, 40
+    img = (torch.rand(B, 3, H, Wd, generator=g) * 2 - 1)
+    tgt = (torch.rand(B, 3, H, Wd, generator=g) * 2 - 1)
+    flow = (torch.randn(B, 2, H, Wd, generator=g) * 6).requires_grad_(True)
+    met = (torch.randn(B, 1, H, Wd, generator=g) * 0.5).requires_grad_(True)
+    for level, off in ((1, (0, 0)), (4, (1, 3)), (7, (6, 2))):
+        ww = O.softsplat_soft(img, flow, met, level, off)
+        ref = O.nan_charbonnier(O.softsplat_soft(tgt, torch.zeros_like(flow), torch.ones_like(met), level, off)[:, :-1],
+                                O.fill_holes_nan(ww[:, :-1], ww[:, -1:]))
+        gf_ref, gm_ref = torch.autograd.grad(ref, (flow, met))
+        fl, mt = flow.detach().cuda().requires_grad_(True), met.detach().cuda().requires_grad_(True)
+        S = W.soft_splat_raw(img.cuda(), fl, mt, level, off)
+        with torch.no_grad():
+            Tt = W.soft_splat_raw(tgt.cuda(), torch.zeros_like(fl), torch.ones_like(mt), level, off)
+        got = W.soft_splat_charbonnier(S, Tt)
+        gf, gm = torch.autograd.grad(got, (fl, mt))
+        assert abs(float(got) - float(ref)) <= 1e-5 * max(1.0, abs(float(ref))), (level, float(got), float(ref))
+        assert (gf.cpu() - gf_ref).abs().max().item() <= 1e-5 * max(1e-3, gf_ref.abs().max().item()) + 1e-8
+        assert (gm.cpu() - gm_ref).abs().max().item() <= 1e-5 * max(1e-3, gm_ref.abs().max().item()) + 1e-8
+    ref = O.edgeaware_smoothness1(img, flow)
+    (gref,) = torch.autograd.grad(ref, flow)
+    fl = flow.detach().cuda().requires_grad_(True)
+    got = W.edgeaware_smoothness1(img.cuda(), fl)
+    (gg,) = torch.autograd.grad(got, fl)
+    assert abs(float(got) - float(ref)) <= 1e-5 * abs(float(ref))
+    assert (gg.cpu() - gref).abs().max().item() <= 2e-5 * gref.abs().max().item()
+
+
+def test_flow_learner_loss_and_gradients(golden):
+    g = golden("flow_learner_32x32")
+    m = build_learner(g["seed"])
+    sd = {k: v.clone().requires_grad_(True) for k, v in m.unet.model.state_dict().items()}
+    m = m.cuda()
+    img, tgt, flow = T(g["img"]), T(g["tgt"]), T(g["flow"])
+    tgt_, cond, flow_ = m.preprocess((img.cuda(), tgt.cuda(), flow.cuda()), aug=False)
+    with torch.no_grad():
+        out = m.model(cond, additional_out=True)
+    assert (out[:, -3:].cpu() - T(g["model_out"])[:, -3:]).abs().max().item() < 3e-2
+    loss = m.loss(tgt_, cond, flow_)
+    assert loss.requires_grad
+    assert abs(float(loss.detach()) - float(g["loss"])) <= 2e-2 * float(g["loss"]), (float(loss.detach()), float(g["loss"]))
+    ideal = m.loss(tgt_, cond, flow_, override_flow=flow_)
+    assert abs(float(ideal) - float(g["ideal_loss"])) <= 1e-4 * float(g["ideal_loss"])       # no UNet involved: fp32 path
+    loss.backward()
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in m.unet.model.parameters())
+    # (a) the 832-term objective and its gradient with respect to the prediction, teacher-forced on the reference's own
+    #     prediction (both sides fp32): the composition with the bf16 UNet is ill-conditioned for gradient comparisons,
+    #     because a 0.1-pixel flow difference moves pixels across cell borders of the bilinear splat
+    fw = T(g["model_out"])[:, -3:]
+    fp_ref = (fw[:, :2] * 20.0).clone().requires_grad_(True)
+    ww_ref = fw[:, 2:].clone().requires_grad_(True)
+    img_n, tgt_n = 2 * img - 1, 2 * tgt - 1
+    ref = O.flow_learner_objective(img_n, tgt_n, fp_ref, ww_ref)
+    gfr, gwr = torch.autograd.grad(ref, (fp_ref, ww_ref))
+    fp, ww = fp_ref.detach().cuda().requires_grad_(True), ww_ref.detach().cuda().requires_grad_(True)
+    got = m.objective(img_n.cuda(), tgt_n.cuda(), fp, ww)
+    gf, gw = torch.autograd.grad(got, (fp, ww))
+    assert abs(float(got.detach()) - float(g["loss"])) <= 2e-5 * float(g["loss"])       # == the reference's loss value
+    assert (gf.cpu() - gfr).abs().max().item() <= 2e-5 * gfr.abs().max().item()
+    assert (gw.cpu() - gwr).abs().max().item() <= 2e-5 * gwr.abs().max().item()
+
+
+def test_time_free_unet_backward_vs_oracle():
+    """(b) Unet(channels=6, out_dim=3, time_in=False): every parameter gradient of sum(out * dout) vs oracle autograd,
+    same tolerance as tests/test_gpu_train.py."""
+    from test_gpu_train import compare_grads
+    m = build_learner(5)
+    net = m.unet.model
+    sd = {k: v.clone().requires_grad_(True) for k, v in net.state_dict().items()}
+    net = net.cuda()
+    gg = torch.Generator().manual_seed(6)
+    x = torch.rand(2, 6, 32, 48, generator=gg) * 2 - 1
+    dout = torch.randn(2, 3, 32, 48, generator=gg)
+    (O.unet_forward(sd, x, None, None) * dout).sum().backward()
+    out = net(x.cuda())
+    assert out.shape == (2, 3, 32, 48) and out.requires_grad
+    (out * dout.cuda()).sum().backward()
+    worst = compare_grads(net.named_parameters(), sd)
+    print("time-free UNet: worst relative L2 gradient error", worst)
+
+
+def test_flow_learner_training_and_sampling():
+    from opticalflowdiffusion_b200.config import compose
+    from opticalflowdiffusion_b200.experiments import build_experiment
+    random.seed(1)
+    torch.manual_seed(1)
+    cfg = compose(["algorithm=flow_learner", "algorithm.zero_init=false", "algorithm.lr=2e-4", "dataset.height=32",
+                   "dataset.width=32", "dataset.length=8", "experiment.training.data.batch_size=2",
+                   "experiment.training.data.shuffle=false"])
+    exp = build_experiment(cfg, None, None)
+    exp.algo.levels = (1, 2, 4, 8)                     # a shorter pyramid keeps the test quick
+    out = exp.train(max_steps=3)
+    assert out["steps"] == 3 and all(np.isfinite(v) for v in out["train/loss"])
+    img = O.synthetic_frames(2, 32, 32, seed=1).cuda()
+    tgt = O.synthetic_frames(2, 32, 32, seed=2).cuda()
+    flow = torch.zeros(2, 2, 32, 32, device="cuda")
+    exp.algo.validation_step((img, tgt, flow), 0)
+    for k in ("val/loss", "val/ideal_loss", "val/mse", "val/flow_mse"):
+        assert np.isfinite(float(exp.algo.logged[k])), k
+    samples, p_flow, weights = exp.algo.sample(torch.cat((2 * img - 1, 2 * tgt - 1), 1), flow)
+    assert samples.shape == (2, 3, 32, 32) and p_flow.shape == (2, 2, 32, 32) and weights.shape == (2, 1, 32, 32)
