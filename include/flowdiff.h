@@ -302,6 +302,20 @@ FD_API size_t fd_loss_workspace_floats(long items);
 FD_API int fd_soft_charb_fwd(const float* S, const float* T, float* sums, float* partials, int B, int C, int HW, void* stream);
 FD_API int fd_soft_charb_bwd(const float* S, const float* T, const float* sums, const float* upstream, float* gS,
                       int B, int C, int HW, void* stream);
+/* All scale^2 offsets of one pyramid level at once (the loop of flow_learner.py:184-196): offset index k = a*scale + b
+ * <-> offset = [a, b]; stacked tensors (K, B, C, H/scale, W/scale).  splat_*_multi: the per-offset arithmetic of
+ * fd_splat_fwd / _ingrad / _flowgrad, the two gradient kernels summing over k (C must be 4 for them).
+ * soft_charb_multi: sums [K][3], out[0] = mean_k mean_k; bwd: gS = d(upstream[0] * out[0])/dS. */
+FD_API int fd_splat_fwd_multi(const float* in, const float* flow, float* out, int B, int C, int H, int W, int scale, void* stream);
+FD_API int fd_splat_ingrad_multi(const float* flow, const float* gout, float* gin, int B, int C, int H, int W, int scale,
+                          void* stream);
+FD_API int fd_splat_flowgrad_multi(const float* in, const float* flow, const float* gout, float* gflow, int B, int C,
+                            int H, int W, int scale, void* stream);
+FD_API size_t fd_soft_charb_multi_workspace_floats(int B, int HW, int K);
+FD_API int fd_soft_charb_multi_fwd(const float* S, const float* T, float* sums, float* out, float* partials, int B, int C,
+                            int HW, int K, void* stream);
+FD_API int fd_soft_charb_multi_bwd(const float* S, const float* T, const float* sums, const float* upstream, float* gS,
+                            int B, int C, int HW, int K, void* stream);
 /* edgeaware_smoothness1 (warp.py:289-303): out[0] = loss; bwd: gflow = upstream[0] * dloss/dflow (image has no gradient) */
 FD_API int fd_edge_smooth_fwd(const float* img, const float* flow, float* out, float* partials, int B, int Ci, int Cf,
                        int H, int W, void* stream);

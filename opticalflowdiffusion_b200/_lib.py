@@ -87,6 +87,12 @@ SIGNATURES = {
     "fd_soft_charb_bwd": (c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _P]),
     "fd_edge_smooth_fwd": (c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "fd_edge_smooth_bwd": (c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
+    "fd_splat_fwd_multi": (c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _P]),
+    "fd_splat_ingrad_multi": (c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _P]),
+    "fd_splat_flowgrad_multi": (c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
+    "fd_soft_charb_multi_workspace_floats": (c_size_t, [_I, _I, _I]),
+    "fd_soft_charb_multi_fwd": (c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
+    "fd_soft_charb_multi_bwd": (c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "fd_conv_wgrad": (c_int, [_P, _I, _P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
 }
 

@@ -73,6 +73,97 @@ __global__ void __launch_bounds__(256) sum2_finalize_kernel(const float* __restr
   }
 }
 
+// K stacked terms (all offsets of one level): partials [K][gridDim.x][2]; level loss = mean_k (sum_k / count_k)
+__global__ void __launch_bounds__(kThreads) soft_charb_multi_fwd_kernel(const float* __restrict__ S, const float* __restrict__ T,
+                                                                       float* __restrict__ partials, int B, int C, long HW) {
+  __shared__ float red[64];
+  const int k = blockIdx.y;
+  const float* Sk = S + (long)k * B * (C + 1) * HW;
+  const float* Tk = T + (long)k * B * (C + 1) * HW;
+  float acc[2] = {0.f, 0.f};
+  const long total = (long)B * HW;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const long b = i / HW, p = i - b * HW;
+    const float* s = Sk + b * (C + 1) * HW + p;
+    const float* t = Tk + b * (C + 1) * HW + p;
+    const float sw = s[(long)C * HW], tw = t[(long)C * HW];
+    if (!(sw > 0.f)) continue;
+    const float sn = sw + kNormEps, tn = tw + kNormEps;
+    for (int c = 0; c < C; ++c) {
+      const float d = t[(long)c * HW] / tn - s[(long)c * HW] / sn;
+      if (d != d) continue;
+      acc[0] += sqrtf(d * d + kCharbEps2);
+      acc[1] += 1.f;
+    }
+  }
+  fd_block_sum<2>(acc, red);
+  if (threadIdx.x == 0) {
+    partials[((long)k * gridDim.x + blockIdx.x) * 2] = acc[0];
+    partials[((long)k * gridDim.x + blockIdx.x) * 2 + 1] = acc[1];
+  }
+}
+
+// one block: sums[k] = {sum_k, count_k, mean_k} for every k in a fixed order, out[0] = mean_k mean_k
+__global__ void __launch_bounds__(256) soft_charb_multi_finalize_kernel(const float* __restrict__ partials, int nblocks, int K,
+                                                                        float* __restrict__ sums, float* __restrict__ out) {
+  __shared__ double sh[256];
+  double local = 0.0;
+  for (int k = threadIdx.x; k < K; k += 256) {
+    double a = 0.0, b = 0.0;
+    for (int i = 0; i < nblocks; ++i) {
+      a += (double)partials[((long)k * nblocks + i) * 2];
+      b += (double)partials[((long)k * nblocks + i) * 2 + 1];
+    }
+    sums[k * 3] = (float)a;
+    sums[k * 3 + 1] = (float)b;
+    sums[k * 3 + 2] = (float)(a / b);
+    local += a / b;
+  }
+  sh[threadIdx.x] = local;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[0] = (float)(sh[0] / (double)K);
+}
+
+__global__ void __launch_bounds__(kThreads) soft_charb_multi_bwd_kernel(const float* __restrict__ S, const float* __restrict__ T,
+                                                                       const float* __restrict__ sums,
+                                                                       const float* __restrict__ upstream, float* __restrict__ gS,
+                                                                       int B, int C, long HW, int K) {
+  const int k = blockIdx.y;
+  const float g = upstream[0] / ((float)K * sums[k * 3 + 1]);
+  const float* Sk = S + (long)k * B * (C + 1) * HW;
+  const float* Tk = T + (long)k * B * (C + 1) * HW;
+  float* gk = gS + (long)k * B * (C + 1) * HW;
+  const long total = (long)B * HW;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const long b = i / HW, p = i - b * HW;
+    const float* s = Sk + b * (C + 1) * HW + p;
+    const float* t = Tk + b * (C + 1) * HW + p;
+    float* gs = gk + b * (C + 1) * HW + p;
+    const float sw = s[(long)C * HW], tw = t[(long)C * HW];
+    float gw = 0.f;
+    const bool live = sw > 0.f;
+    const float sn = sw + kNormEps, tn = tw + kNormEps;
+    for (int c = 0; c < C; ++c) {
+      float gc = 0.f;
+      if (live) {
+        const float sv = s[(long)c * HW];
+        const float d = t[(long)c * HW] / tn - sv / sn;
+        if (d == d) {
+          const float dw = -g * d * rsqrtf(d * d + kCharbEps2);
+          gc = dw / sn;
+          gw -= dw * sv / (sn * sn);
+        }
+      }
+      gs[(long)c * HW] = gc;
+    }
+    gs[(long)C * HW] = gw;
+  }
+}
+
 // dL/dS for L = upstream * sum / count
 __global__ void __launch_bounds__(kThreads) soft_charb_bwd_kernel(const float* __restrict__ S, const float* __restrict__ T,
                                                                  const float* __restrict__ sums, const float* __restrict__ upstream,
@@ -223,6 +314,35 @@ int fd_soft_charb_bwd(const float* S, const float* T, const float* sums, const f
                       void* stream) {
   FD_REQUIRE(S && T && sums && upstream && gS && B > 0 && C > 0 && HW > 0, "soft_charb_bwd: bad argument");
   soft_charb_bwd_kernel<<<lgrid((long)B * HW), kThreads, 0, (cudaStream_t)stream>>>(S, T, sums, upstream, gS, B, C, (long)HW);
+  FD_LAUNCH_CHECK();
+  return FD_OK;
+}
+
+static int multi_grid(long items, int K) {
+  long b = (items + kThreads - 1) / kThreads;
+  const long cap = (FD_NUM_SMS * 8 + K - 1) / K;
+  if (b > cap) b = cap;
+  return (int)(b < 1 ? 1 : b);
+}
+
+size_t fd_soft_charb_multi_workspace_floats(int B, int HW, int K) { return (size_t)multi_grid((long)B * HW, K) * K * 2; }
+
+int fd_soft_charb_multi_fwd(const float* S, const float* T, float* sums, float* out, float* partials, int B, int C, int HW, int K,
+                            void* stream) {
+  FD_REQUIRE(S && T && sums && out && partials && B > 0 && C > 0 && HW > 0 && K > 0 && K <= 65535, "soft_charb_multi_fwd: bad argument");
+  const int grid = multi_grid((long)B * HW, K);
+  soft_charb_multi_fwd_kernel<<<dim3(grid, K), kThreads, 0, (cudaStream_t)stream>>>(S, T, partials, B, C, (long)HW);
+  FD_LAUNCH_CHECK();
+  soft_charb_multi_finalize_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(partials, grid, K, sums, out);
+  FD_LAUNCH_CHECK();
+  return FD_OK;
+}
+
+int fd_soft_charb_multi_bwd(const float* S, const float* T, const float* sums, const float* upstream, float* gS, int B, int C,
+                            int HW, int K, void* stream) {
+  FD_REQUIRE(S && T && sums && upstream && gS && B > 0 && C > 0 && HW > 0 && K > 0 && K <= 65535, "soft_charb_multi_bwd: bad argument");
+  soft_charb_multi_bwd_kernel<<<dim3(multi_grid((long)B * HW, K), K), kThreads, 0, (cudaStream_t)stream>>>(S, T, sums, upstream, gS,
+                                                                                                          B, C, (long)HW, K);
   FD_LAUNCH_CHECK();
   return FD_OK;
 }

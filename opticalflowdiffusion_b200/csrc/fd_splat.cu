@@ -255,6 +255,132 @@ __global__ void __launch_bounds__(256) splat_flowgrad_kernel(const float* __rest
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// All scale^2 offsets of one pyramid level in ONE launch (FlowLearner's loss loops `for a in range(level): for b in
+// range(level): softsplat(..., scale=level, offset=[a, b])`, flow_learner.py:184-196 -- 832 splat pairs per step).
+// Offset index k = a * scale + b -> (off_x, off_y) = (a, b); outputs / output gradients are stacked (K, B, C, Ho, Wo).
+// The per-offset arithmetic is the single-offset kernels' (same taps, same order); the two gather kernels sum the
+// K contributions of a source pixel in registers instead of K separate passes.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) splat_fwd_multi_kernel(const float* __restrict__ in, const float* __restrict__ flow,
+                                                              float* __restrict__ out, int B, int C, int H, int W, int Ho,
+                                                              int Wo, int scale, long items) {
+  const int k = blockIdx.y;
+  const int off_x = k / scale, off_y = k - off_x * scale;
+  const long HW = (long)H * W, HWo = (long)Ho * Wo;
+  float* outk = out + (long)k * B * C * HWo;
+  const int lane = threadIdx.x & 31;
+  for (long base = (long)blockIdx.x * blockDim.x + (threadIdx.x & ~31); base < items; base += (long)gridDim.x * blockDim.x) {
+    const long item = base + lane;
+    const bool valid = item < items;
+    int b = 0, y = 0, x = 0;
+    if (valid) s_item_to_byx<1>(item, H, W, b, y, x);
+    const long pix = (long)y * W + x;
+    const float fx = valid ? __ldg(flow + ((long)b * 2 + 0) * HW + pix) : 0.f;
+    const float fy = valid ? __ldg(flow + ((long)b * 2 + 1) * HW + pix) : 0.f;
+    SplatTaps t;
+    splat_taps<KIND_OUT>(fx, fy, x, y, H, W, Ho, Wo, scale, off_x, off_y, t);
+    const int r0 = t.y0 * Wo + t.x0;
+    int a0[2], a1[2];
+    a0[0] = (valid && t.okx0 && t.oky0) ? r0 : -1;
+    a0[1] = (valid && t.okx1 && t.oky0) ? r0 + 1 : -1;
+    a1[0] = (valid && t.okx0 && t.oky1) ? r0 + Wo : -1;
+    a1[1] = (valid && t.okx1 && t.oky1) ? r0 + Wo + 1 : -1;
+    for (int c = 0; c < C; ++c) {
+      const float a = valid ? __ldg(in + ((long)b * C + c) * HW + pix) : 0.f;
+      float v0[2] = {__fmul_rn(a, t.nw), __fmul_rn(a, t.ne)}, v1[2] = {__fmul_rn(a, t.sw), __fmul_rn(a, t.se)};
+      float* plane = outk + ((long)b * C + c) * HWo;
+      fd_scatter_merged<2>(plane, a0, v0);
+      fd_scatter_merged<2>(plane, a1, v1);
+    }
+  }
+}
+
+template <int C>
+__global__ void __launch_bounds__(256) splat_ingrad_multi_kernel(const float* __restrict__ flow, const float* __restrict__ gout,
+                                                                 float* __restrict__ gin, int B, int H, int W, int Ho, int Wo,
+                                                                 int scale, long items) {
+  const long HW = (long)H * W, HWo = (long)Ho * Wo;
+  const int K = scale * scale;
+  for (long item = (long)blockIdx.x * blockDim.x + threadIdx.x; item < items; item += (long)gridDim.x * blockDim.x) {
+    int b, y, x;
+    s_item_to_byx<1>(item, H, W, b, y, x);
+    const long pix = (long)y * W + x;
+    const float fx = __ldg(flow + ((long)b * 2 + 0) * HW + pix), fy = __ldg(flow + ((long)b * 2 + 1) * HW + pix);
+    float acc[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) acc[c] = 0.f;
+    for (int k = 0; k < K; ++k) {
+      const int off_x = k / scale, off_y = k - off_x * scale;
+      SplatTaps t;
+      splat_taps<KIND_INGRAD>(fx, fy, x, y, H, W, Ho, Wo, scale, off_x, off_y, t);
+      const int r0 = t.y0 * Wo + t.x0;
+      const float* gk = gout + ((long)k * B + b) * C * HWo;
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        const float* plane = gk + (long)c * HWo;
+        float a = 0.f;
+        a += tap_or_zero(plane, t.okx0 && t.oky0, r0) * t.nw;
+        a += tap_or_zero(plane, t.okx1 && t.oky0, r0 + 1) * t.ne;
+        a += tap_or_zero(plane, t.okx0 && t.oky1, r0 + Wo) * t.sw;
+        a += tap_or_zero(plane, t.okx1 && t.oky1, r0 + Wo + 1) * t.se;
+        acc[c] += a;
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < C; ++c) gin[((long)b * C + c) * HW + pix] = acc[c];
+  }
+}
+
+template <int C>
+__global__ void __launch_bounds__(256) splat_flowgrad_multi_kernel(const float* __restrict__ in, const float* __restrict__ flow,
+                                                                   const float* __restrict__ gout, float* __restrict__ gflow,
+                                                                   int B, int H, int W, int Ho, int Wo, int scale, long items) {
+  const long HW = (long)H * W, HWo = (long)Ho * Wo;
+  const int K = scale * scale;
+  for (long item = (long)blockIdx.x * blockDim.x + threadIdx.x; item < items; item += (long)gridDim.x * blockDim.x) {
+    int b, y, x;
+    s_item_to_byx<1>(item, H, W, b, y, x);
+    const long pix = (long)y * W + x;
+    const float fx = __ldg(flow + ((long)b * 2 + 0) * HW + pix), fy = __ldg(flow + ((long)b * 2 + 1) * HW + pix);
+    float a[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) a[c] = __ldg(in + ((long)b * C + c) * HW + pix);
+    float gx = 0.f, gy = 0.f;
+    bool ok = true;
+    for (int k = 0; k < K; ++k) {
+      const int off_x = k / scale, off_y = k - off_x * scale;
+      SplatTaps t;
+      splat_taps<KIND_FLOWGRAD>(fx, fy, x, y, H, W, Ho, Wo, scale, off_x, off_y, t);
+      ok = t.ok;
+      const int r0 = t.y0 * Wo + t.x0;
+      const float x0 = (float)t.x0, y0 = (float)t.y0, x1 = (float)(t.x0 + 1), y1 = (float)(t.y0 + 1);
+      const float* gk = gout + ((long)k * B + b) * C * HWo;
+      float kx = 0.f, ky = 0.f;
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        const float* plane = gk + (long)c * HWo;
+        const float g_nw = tap_or_zero(plane, t.okx0 && t.oky0, r0);
+        const float g_ne = tap_or_zero(plane, t.okx1 && t.oky0, r0 + 1);
+        const float g_sw = tap_or_zero(plane, t.okx0 && t.oky1, r0 + Wo);
+        const float g_se = tap_or_zero(plane, t.okx1 && t.oky1, r0 + Wo + 1);
+        kx += g_nw * a[c] * (-1.f * (y1 - t.fy)) * t.dyy;
+        kx += g_ne * a[c] * (+1.f * (y1 - t.fy)) * t.dyy;
+        kx += g_sw * a[c] * (-1.f * (t.fy - y0)) * t.dyy;
+        kx += g_se * a[c] * (+1.f * (t.fy - y0)) * t.dyy;
+        ky += g_nw * a[c] * ((x1 - t.fx) * -1.f) * t.dxx;
+        ky += g_ne * a[c] * ((t.fx - x0) * -1.f) * t.dxx;
+        ky += g_sw * a[c] * ((x1 - t.fx) * +1.f) * t.dxx;
+        ky += g_se * a[c] * ((t.fx - x0) * +1.f) * t.dxx;
+      }
+      gx += kx;
+      gy += ky;
+    }
+    gflow[((long)b * 2 + 0) * HW + pix] = ok ? gx : 0.f;
+    gflow[((long)b * 2 + 1) * HW + pix] = ok ? gy : 0.f;
+  }
+}
+
 // warp_forward_flow pre-processing (warp.py:122-126, softsplat_new.py:301-302):
 // ten_in[:, :C] = nan_to_zero(first) * w ; ten_in[:, C] = w ; w = any_c(isnan(first)) ? 0 : 1
 __global__ void __launch_bounds__(256) splat_prepare_kernel(const float* __restrict__ first, float* __restrict__ ten_in,
@@ -357,6 +483,45 @@ int fd_splat_flowgrad(const float* in, const float* flow, const float* gout, flo
     const long items = (long)B * H * W;
     splat_flowgrad_kernel<1><<<sgrid(items), 256, 0, st>>>(in, flow, gout, gflow, B, C, H, W, Ho, Wo, scale, off_x, off_y, items);
   }
+  FD_LAUNCH_CHECK();
+  return FD_OK;
+}
+
+int fd_splat_fwd_multi(const float* in, const float* flow, float* out, int B, int C, int H, int W, int scale, void* stream) {
+  if (int e = check(B, C, H, W, scale, 0, 0)) return e;
+  FD_REQUIRE(in && flow && out && scale * scale <= 65535, "splat_fwd_multi: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int Ho = H / scale, Wo = W / scale, K = scale * scale;
+  FD_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)K * B * C * Ho * Wo, st));
+  const long items = (long)B * H * W;
+  int gx = sgrid(items);
+  const int cap = (FD_NUM_SMS * 16 + K - 1) / K;
+  if (gx > cap) gx = cap;
+  splat_fwd_multi_kernel<<<dim3(gx, K), 256, 0, st>>>(in, flow, out, B, C, H, W, Ho, Wo, scale, items);
+  FD_LAUNCH_CHECK();
+  return FD_OK;
+}
+
+int fd_splat_ingrad_multi(const float* flow, const float* gout, float* gin, int B, int C, int H, int W, int scale,
+                          void* stream) {
+  if (int e = check(B, C, H, W, scale, 0, 0)) return e;
+  FD_REQUIRE(flow && gout && gin, "splat_ingrad_multi: null pointer");
+  FD_REQUIRE(C == 4, "splat_ingrad_multi: built for the 4-channel soft splat input (3 colours + weight), got C=%d", C);
+  const long items = (long)B * H * W;
+  splat_ingrad_multi_kernel<4><<<sgrid(items), 256, 0, (cudaStream_t)stream>>>(flow, gout, gin, B, H, W, H / scale, W / scale,
+                                                                             scale, items);
+  FD_LAUNCH_CHECK();
+  return FD_OK;
+}
+
+int fd_splat_flowgrad_multi(const float* in, const float* flow, const float* gout, float* gflow, int B, int C, int H, int W,
+                            int scale, void* stream) {
+  if (int e = check(B, C, H, W, scale, 0, 0)) return e;
+  FD_REQUIRE(in && flow && gout && gflow, "splat_flowgrad_multi: null pointer");
+  FD_REQUIRE(C == 4, "splat_flowgrad_multi: built for the 4-channel soft splat input (3 colours + weight), got C=%d", C);
+  const long items = (long)B * H * W;
+  splat_flowgrad_multi_kernel<4><<<sgrid(items), 256, 0, (cudaStream_t)stream>>>(in, flow, gout, gflow, B, H, W, H / scale,
+                                                                               W / scale, scale, items);
   FD_LAUNCH_CHECK();
   return FD_OK;
 }

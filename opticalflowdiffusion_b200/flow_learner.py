@@ -32,6 +32,7 @@ class FlowLearner(_Base):
         self.flow_max = cfg.flow_max
         self.rep = "flow"
         self.levels = tuple(levels)
+        self.fused_levels = True            # False: one launch set per (level, a, b) like the reference's loop
         self._augmentor = None
         # 3 outputs: optical flow + splat weight map (:88-93)
         self.unet = UnetWithWarp(cfg, Unet(64, channels=6, out_dim=3, time_in=False), False, nan_safe=False)
@@ -91,6 +92,9 @@ class FlowLearner(_Base):
             zero_flow = torch.zeros_like(flow_pred)
         photo = []
         for level in self.levels:
+            if self.fused_levels:
+                photo.append(W.soft_level_loss(ten_in, flow_pred, tgt_in, level))       # all level^2 offsets in one go
+                continue
             terms = []
             for a in range(level):
                 for b in range(level):

@@ -371,3 +371,54 @@ def edgeaware_smoothness1(image: Tensor, flow: Tensor, edge_weight: float = 30) 
 def fill_holes_nan(img: Tensor, weights: Tensor) -> Tensor:
     """warp.py:273-276."""
     return torch.where(weights.expand_as(img) > 0, img, torch.full_like(img, float("nan")))
+
+
+class _SoftLevelLossFn(torch.autograd.Function):
+    """One pyramid level of FlowLearner's photometric loss (flow_learner.py:184-202) with all level^2 offsets batched:
+    mean over (a, b) of nan_charbonnier(softsplat(tgt, 0), fill_holes(softsplat(img, flow))).  Seven launches per level
+    (splat, target splat, loss, and their three backward kernels) instead of ~8 per offset."""
+
+    @staticmethod
+    def forward(ctx, ten_in: Tensor, flow: Tensor, tgt_in: Tensor, level: int):
+        ten_in, flow, tgt_in = _f32c(ten_in), _f32c(flow), _f32c(tgt_in)
+        B, C1, H, W = ten_in.shape
+        lib, st = _lib.load(), _lib.stream()
+        K, Ho, Wo = level * level, H // level, W // level
+        S = torch.empty(K, B, C1, Ho, Wo, device=ten_in.device, dtype=torch.float32)
+        T = torch.empty_like(S)
+        _lib.check(lib.fd_splat_fwd_multi(_lib.ptr(ten_in), _lib.ptr(flow), _lib.ptr(S), B, C1, H, W, level, st))
+        zero = torch.zeros_like(flow)
+        _lib.check(lib.fd_splat_fwd_multi(_lib.ptr(tgt_in), _lib.ptr(zero), _lib.ptr(T), B, C1, H, W, level, st))
+        sums = torch.empty(K, 3, device=S.device, dtype=torch.float32)
+        out = torch.empty(1, device=S.device, dtype=torch.float32)
+        ws = torch.empty(lib.fd_soft_charb_multi_workspace_floats(B, Ho * Wo, K), device=S.device, dtype=torch.float32)
+        _lib.check(lib.fd_soft_charb_multi_fwd(_lib.ptr(S), _lib.ptr(T), _lib.ptr(sums), _lib.ptr(out), _lib.ptr(ws), B, C1 - 1,
+                                               Ho * Wo, K, st))
+        ctx.save_for_backward(ten_in, flow, S, T, sums)
+        ctx.level = level
+        return out[0].clone()
+
+    @staticmethod
+    def backward(ctx, g: Tensor):
+        ten_in, flow, S, T, sums = ctx.saved_tensors
+        level = ctx.level
+        K, B, C1, Ho, Wo = S.shape
+        H, W = ten_in.shape[-2:]
+        lib, st = _lib.load(), _lib.stream()
+        g = g.detach().float().reshape(1).contiguous()
+        gS = torch.empty_like(S)
+        _lib.check(lib.fd_soft_charb_multi_bwd(_lib.ptr(S), _lib.ptr(T), _lib.ptr(sums), _lib.ptr(g), _lib.ptr(gS), B, C1 - 1,
+                                               Ho * Wo, K, st))
+        gin = gflow = None
+        if ctx.needs_input_grad[0]:
+            gin = torch.empty_like(ten_in)
+            _lib.check(lib.fd_splat_ingrad_multi(_lib.ptr(flow), _lib.ptr(gS), _lib.ptr(gin), B, C1, H, W, level, st))
+        if ctx.needs_input_grad[1]:
+            gflow = torch.empty_like(flow)
+            _lib.check(lib.fd_splat_flowgrad_multi(_lib.ptr(ten_in), _lib.ptr(flow), _lib.ptr(gS), _lib.ptr(gflow), B, C1, H, W,
+                                                   level, st))
+        return gin, gflow, None, None
+
+
+def soft_level_loss(ten_in: Tensor, flow: Tensor, tgt_in: Tensor, level: int) -> Tensor:
+    return _SoftLevelLossFn.apply(ten_in, flow, tgt_in, int(level))

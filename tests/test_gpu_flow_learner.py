@@ -74,11 +74,13 @@ def test_flow_learner_loss_and_gradients(golden):
     ref = O.flow_learner_objective(img_n, tgt_n, fp_ref, ww_ref)
     gfr, gwr = torch.autograd.grad(ref, (fp_ref, ww_ref))
     fp, ww = fp_ref.detach().cuda().requires_grad_(True), ww_ref.detach().cuda().requires_grad_(True)
-    got = m.objective(img_n.cuda(), tgt_n.cuda(), fp, ww)
-    gf, gw = torch.autograd.grad(got, (fp, ww))
-    assert abs(float(got.detach()) - float(g["loss"])) <= 2e-5 * float(g["loss"])       # == the reference's loss value
-    assert (gf.cpu() - gfr).abs().max().item() <= 2e-5 * gfr.abs().max().item()
-    assert (gw.cpu() - gwr).abs().max().item() <= 2e-5 * gwr.abs().max().item()
+    for fused in (True, False):                 # all offsets of a level in one launch / the reference's per-offset loop
+        m.fused_levels = fused
+        got = m.objective(img_n.cuda(), tgt_n.cuda(), fp, ww)
+        gf, gw = torch.autograd.grad(got, (fp, ww))
+        assert abs(float(got.detach()) - float(g["loss"])) <= 2e-5 * float(g["loss"])       # == the reference's loss value
+        assert (gf.cpu() - gfr).abs().max().item() <= 2e-5 * gfr.abs().max().item(), fused
+        assert (gw.cpu() - gwr).abs().max().item() <= 2e-5 * gwr.abs().max().item(), fused
 
 
 def test_time_free_unet_backward_vs_oracle():
