@@ -162,17 +162,29 @@ __global__ void __launch_bounds__(256, 3) linattn_bwd_dctx_kernel(const __nv_bfl
     }
     __syncthreads();
   }
-  float* dst = dctx + ((long)n * kHeads + head) * kD * kD;
+  // per-chunk partial (combined in a fixed order by linattn_bwd_dctx_combine_kernel: run-to-run stable, no atomics)
+  float* dst = dctx + (((long)n * gridDim.x + blockIdx.x) * kHeads + head) * kD * kD;
 #pragma unroll
   for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
     for (int nt = 0; nt < 2; ++nt) {
       const int d = mt * 16 + g, e = nhalf * 16 + nt * 8 + 2 * tq;
-      atomicAdd(dst + d * kD + e, acc[mt][nt][0]);
-      atomicAdd(dst + d * kD + e + 1, acc[mt][nt][1]);
-      atomicAdd(dst + (d + 8) * kD + e, acc[mt][nt][2]);
-      atomicAdd(dst + (d + 8) * kD + e + 1, acc[mt][nt][3]);
+      dst[d * kD + e] = acc[mt][nt][0];
+      dst[d * kD + e + 1] = acc[mt][nt][1];
+      dst[(d + 8) * kD + e] = acc[mt][nt][2];
+      dst[(d + 8) * kD + e + 1] = acc[mt][nt][3];
     }
+}
+
+__global__ void __launch_bounds__(256) linattn_bwd_dctx_combine_kernel(const float* __restrict__ partial, float* __restrict__ dctx,
+                                                                       int N, int chunks) {
+  const int per = kHeads * kD * kD;
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long)N * per) return;
+  const int n = (int)(i / per), j = (int)(i - (long)n * per);
+  float s = 0.f;
+  for (int c = 0; c < chunks; ++c) s += partial[((long)n * chunks + c) * per + j];
+  dctx[i] = s;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -652,8 +664,19 @@ extern "C" {
 
 size_t fd_linattn_stats_floats(void) { return kStatsFloats; }
 
+static int lb_chunks(int N, int HW, int* chunk_px) {
+  int want = (FD_NUM_SMS * 3) / N;
+  if (want < 1) want = 1;
+  int px = (HW + want - 1) / want;
+  px = ((px + kLbTile - 1) / kLbTile) * kLbTile;
+  *chunk_px = px;
+  return (HW + px - 1) / px;
+}
+
 size_t fd_linattn_bwd_workspace_floats(int N, int HW) {
-  return (size_t)N * kStatsFloats + (size_t)N * kHeads * kD * kD + fd_linattn_workspace_floats(N, HW);
+  int px;
+  const int chunks = lb_chunks(N, HW, &px);
+  return (size_t)N * kStatsFloats + (size_t)N * (chunks + 1) * kHeads * kD * kD + fd_linattn_workspace_floats(N, HW);
 }
 
 int fd_linattn_bwd(const void* qkv, const void* dout, void* dqkv, const float* saved_stats, float* workspace, int N, int HW,
@@ -661,9 +684,12 @@ int fd_linattn_bwd(const void* qkv, const void* dout, void* dqkv, const float* s
   FD_REQUIRE(qkv && dout && dqkv && workspace && N > 0 && HW > 0, "linattn_bwd: bad argument");
   FD_REQUIRE(N <= 65535, "linattn_bwd: batch too large");
   cudaStream_t st = (cudaStream_t)stream;
+  int px;
+  const int chunks = lb_chunks(N, HW, &px);
   float* stats = workspace;
   float* dctx = stats + (size_t)N * kStatsFloats;
-  float* fwd_ws = dctx + (size_t)N * kHeads * kD * kD;
+  float* dpart = dctx + (size_t)N * kHeads * kD * kD;                 // [N][chunks][4][32][32]
+  float* fwd_ws = dpart + (size_t)N * chunks * kHeads * kD * kD;
   const __nv_bfloat16* q = static_cast<const __nv_bfloat16*>(qkv);
   const __nv_bfloat16* dO = static_cast<const __nv_bfloat16*>(dout);
   if (saved_stats != nullptr) {
@@ -671,18 +697,14 @@ int fd_linattn_bwd(const void* qkv, const void* dout, void* dqkv, const float* s
   } else if (int e = fd_linattn_stats(q + kHidden, kQkv, stats, fwd_ws, N, HW, stream)) {
     return e;
   }
-  FD_CUDA(cudaMemsetAsync(dctx, 0, (size_t)N * kHeads * kD * kD * sizeof(float), st));
   static bool attr_set = false;
   if (!attr_set) {
     FD_CUDA(cudaFuncSetAttribute(linattn_bwd_dctx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kLbSmemBytes));
     attr_set = true;
   }
-  int want = (FD_NUM_SMS * 3) / N;
-  if (want < 1) want = 1;
-  int px = (HW + want - 1) / want;
-  px = ((px + kLbTile - 1) / kLbTile) * kLbTile;
-  const int chunks = (HW + px - 1) / px;
-  linattn_bwd_dctx_kernel<<<dim3(chunks, N), 256, kLbSmemBytes, st>>>(q, dO, dctx, HW, px);
+  linattn_bwd_dctx_kernel<<<dim3(chunks, N), 256, kLbSmemBytes, st>>>(q, dO, dpart, HW, px);
+  FD_LAUNCH_CHECK();
+  linattn_bwd_dctx_combine_kernel<<<(N * kHeads * kD * kD + 255) / 256, 256, 0, st>>>(dpart, dctx, N, chunks);
   FD_LAUNCH_CHECK();
   int bx = (HW + 63) / 64;
   const int cap = (FD_NUM_SMS * 8 + N - 1) / N;

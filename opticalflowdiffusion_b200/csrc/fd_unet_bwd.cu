@@ -88,18 +88,16 @@ __global__ void __launch_bounds__(256, 2) gn_bwd_reduce_kernel(const __nv_bfloat
                                                             const double* __restrict__ stats,
                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
                                                             const float* __restrict__ scale_shift, long ss_stride,
-                                                            float* __restrict__ sums /* [N][C][3], zero-filled */, long HW,
+                                                            float* __restrict__ partial /* [N][gridDim.x][C][3] */, long HW,
                                                             int C, float eps) {
-  extern __shared__ float s_acc[];      // [C][3]
+  extern __shared__ float s_acc[];      // [rows of the block][C][3]: fixed-order reduction, no atomics (run-to-run stable)
   const int n = blockIdx.y;
   const int chunks = C >> 3;
   const int chunk = threadIdx.x % chunks;
   const int prow = threadIdx.x / chunks;
   const int ppb = blockDim.x / chunks;
-  for (int i = threadIdx.x; i < C * 3; i += blockDim.x) s_acc[i] = 0.f;
   GnCoef k;
   gn_fold(stats, gamma, beta, scale_shift, ss_stride, n, chunk, C, HW, eps, k);
-  __syncthreads();
   float s0[8], s1[8], s2[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) s0[j] = s1[j] = s2[j] = 0.f;
@@ -132,19 +130,26 @@ __global__ void __launch_bounds__(256, 2) gn_bwd_reduce_kernel(const __nv_bfloat
       }
     }
   }
+  float* mine = s_acc + (long)prow * C * 3;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int c = chunk * 8 + j;
-    atomicAdd(&s_acc[c * 3 + 0], s0[j]);
-    atomicAdd(&s_acc[c * 3 + 1], s1[j]);
-    atomicAdd(&s_acc[c * 3 + 2], s2[j]);
+    mine[c * 3 + 0] = s0[j];
+    mine[c * 3 + 1] = s1[j];
+    mine[c * 3 + 2] = s2[j];
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < C * 3; i += blockDim.x) atomicAdd(sums + (long)n * C * 3 + i, s_acc[i]);
+  float* out = partial + ((long)n * gridDim.x + blockIdx.x) * C * 3;
+  for (int i = threadIdx.x; i < C * 3; i += blockDim.x) {
+    float v = 0.f;
+    for (int r = 0; r < ppb; ++r) v += s_acc[(long)r * C * 3 + i];
+    out[i] = v;
+  }
 }
 
 // one block per sample, one thread per channel
-__global__ void __launch_bounds__(1024) gn_bwd_finalize_kernel(const float* __restrict__ sums, const double* __restrict__ stats,
+__global__ void __launch_bounds__(1024) gn_bwd_finalize_kernel(const float* __restrict__ partial, int nblocks,
+                                                               const double* __restrict__ stats,
                                                                const float* __restrict__ gamma, const float* __restrict__ beta,
                                                                const float* __restrict__ scale_shift, long ss_stride,
                                                                float* __restrict__ dgamma, float* __restrict__ dbeta,
@@ -152,9 +157,8 @@ __global__ void __launch_bounds__(1024) gn_bwd_finalize_kernel(const float* __re
                                                                float* __restrict__ coef /* [N][8][2] */, long HW, int C,
                                                                float eps) {
   __shared__ float s_g[8][2];
+  __shared__ float s_c[1024][2];
   const int n = blockIdx.x, c = threadIdx.x;
-  if (c < 16) (&s_g[0][0])[c] = 0.f;
-  __syncthreads();
   const int cpg = C >> 3;
   const int g = c / cpg;
   const double cnt = (double)HW * cpg;
@@ -164,7 +168,13 @@ __global__ void __launch_bounds__(1024) gn_bwd_finalize_kernel(const float* __re
   if (var < 0.0) var = 0.0;
   const float rstd = (float)(1.0 / sqrt(var + (double)eps));
   const float mean = (float)mean_d;
-  const float S0 = sums[((long)n * C + c) * 3], S1 = sums[((long)n * C + c) * 3 + 1], S2 = sums[((long)n * C + c) * 3 + 2];
+  float S0 = 0.f, S1 = 0.f, S2 = 0.f;
+  for (int b = 0; b < nblocks; ++b) {          // fixed order over the reduce kernel's blocks
+    const float* pb = partial + (((long)n * nblocks + b) * C + c) * 3;
+    S0 += pb[0];
+    S1 += pb[1];
+    S2 += pb[2];
+  }
   const float Sx = rstd * (S1 - mean * S0);            // sum dz * xh
   const float ga = gamma[c], be = beta[c];
   const float sc = scale_shift != nullptr ? scale_shift[(long)n * ss_stride + c] + 1.f : 1.f;
@@ -174,8 +184,18 @@ __global__ void __launch_bounds__(1024) gn_bwd_finalize_kernel(const float* __re
     dss[(long)n * ss_stride + c] = ga * Sx + be * S0;  // d scale = sum dz * y
     dss[(long)n * ss_stride + C + c] = S0;             // d shift
   }
-  atomicAdd(&s_g[g][0], sc * ga * S0);                 // sum over the group of dxh
-  atomicAdd(&s_g[g][1], sc * ga * Sx);                 // ... of dxh * xh
+  s_c[c][0] = sc * ga * S0;                            // dxh summed over the pixels of this channel
+  s_c[c][1] = sc * ga * Sx;                            // ... dxh * xh
+  __syncthreads();
+  if (c < 8) {                                         // group sums in channel order
+    float a = 0.f, b = 0.f;
+    for (int i = 0; i < cpg; ++i) {
+      a += s_c[c * cpg + i][0];
+      b += s_c[c * cpg + i][1];
+    }
+    s_g[c][0] = a;
+    s_g[c][1] = b;
+  }
   __syncthreads();
   const float m1 = s_g[g][0] / (float)cnt, m2 = s_g[g][1] / (float)cnt;
   const float Q = -rstd * rstd * m2;
@@ -646,21 +666,20 @@ int fd_gn_silu_bwd(const void* h, const void* da, const double* gn_stats, const 
   FD_REQUIRE(C % 64 == 0 && C <= 1024, "gn_silu_bwd: C=%d must be a multiple of 64, <= 1024", C);
   FD_REQUIRE(scale_shift != nullptr || dscale_shift == nullptr, "gn_silu_bwd: dscale_shift without scale_shift");
   cudaStream_t st = (cudaStream_t)stream;
-  float* sums = workspace;                       // [N][C][3]
-  float* coef = workspace + (size_t)N * C * 3;   // [N][8][2]
-  FD_CUDA(cudaMemsetAsync(sums, 0, (size_t)N * C * 3 * sizeof(float), st));
   const int chunks = C / 8;
   const int ppb = 256 / chunks > 0 ? 256 / chunks : 1;
   const long cap = (long)FD_NUM_SMS * 8 / N + 1;
   long bx = ((long)HW + ppb * 4 - 1) / (ppb * 4);
   if (bx > cap) bx = cap;
+  float* coef = workspace;                       // [N][8][2]
+  float* partial = workspace + (size_t)N * 16;   // [N][bx][C][3]
   const __nv_bfloat16* hp = static_cast<const __nv_bfloat16*>(h);
   const __nv_bfloat16* dp = static_cast<const __nv_bfloat16*>(da);
-  gn_bwd_reduce_kernel<<<dim3((unsigned)bx, (unsigned)N), ppb * chunks, C * 3 * sizeof(float), st>>>(
-      hp, dp, gn_stats, gamma, beta, scale_shift, ss_stride, sums, (long)HW, C, eps);
+  gn_bwd_reduce_kernel<<<dim3((unsigned)bx, (unsigned)N), ppb * chunks, (size_t)ppb * C * 3 * sizeof(float), st>>>(
+      hp, dp, gn_stats, gamma, beta, scale_shift, ss_stride, partial, (long)HW, C, eps);
   FD_LAUNCH_CHECK();
-  gn_bwd_finalize_kernel<<<N, C, 0, st>>>(sums, gn_stats, gamma, beta, scale_shift, ss_stride, dgamma, dbeta, dscale_shift,
-                                          dbias, coef, (long)HW, C, eps);
+  gn_bwd_finalize_kernel<<<N, C, 0, st>>>(partial, (int)bx, gn_stats, gamma, beta, scale_shift, ss_stride, dgamma, dbeta,
+                                          dscale_shift, dbias, coef, (long)HW, C, eps);
   FD_LAUNCH_CHECK();
   long bx2 = ((long)HW + ppb * 4 - 1) / (ppb * 4);
   const long cap2 = (long)FD_NUM_SMS * 16 / N + 1;
@@ -671,7 +690,10 @@ int fd_gn_silu_bwd(const void* h, const void* da, const double* gn_stats, const 
   return FD_OK;
 }
 
-size_t fd_gn_silu_bwd_workspace_floats(int N, int C) { return (size_t)N * C * 3 + (size_t)N * 16; }
+size_t fd_gn_silu_bwd_workspace_floats(int N, int C) {
+  // coefficients [N][8][2] + per-block partial sums [N][<= 8 * SMs / N + 1 blocks][C][3]
+  return (size_t)N * 16 + ((size_t)FD_NUM_SMS * 8 + N) * C * 3;
+}
 
 int fd_chan_layernorm_bwd(const void* x, const float* g, const void* dy, const void* add, void* dx, float* dg, long npix,
                           int C, float eps, void* stream) {

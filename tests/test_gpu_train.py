@@ -129,7 +129,7 @@ def test_training_step_and_fused_adam():
         if step == 0:
             sd = {k[len("unet."):]: v.detach().cpu().clone() for k, v in algo.state_dict().items() if k.startswith("unet.")}
             ref = O.p_losses_flow(sd, O.make_schedule(1000), first.cpu(), cond.cpu(), t.cpu(), noise.cpu())
-            assert abs(float(loss) - float(ref)) < 2e-3 * max(1.0, float(ref))
+            assert abs(float(loss.detach()) - float(ref)) < 2e-3 * max(1.0, float(ref))
         loss.backward()
         grads = [p.grad for p in algo.unet.parameters()]
         assert all(gr is not None and torch.isfinite(gr).all() for gr in grads)
@@ -244,7 +244,8 @@ def test_backward_through_the_internal_padding():
         denom = q.norm().item() + 1e-12
         worst = max(worst, (q - r).norm().item() / denom)
         noise = max(noise, (p.grad - r).norm().item() / denom)
-        # fp32 atomics reorder the partial sums and a last-bit difference can flip a bf16 rounding downstream; apart
-        # from that the two backward passes are the same computation
-        assert (q - r).norm().item() <= 1.5e-2 * denom, (k, (q - r).norm().item() / denom)
+        # the activation-gradient chain is free of atomics (fixed-order reductions), so the two backward passes are the
+        # same computation; only the fp32 atomics of the final parameter-gradient sums (wgrad, bias, gains) reorder
+        assert (q - r).norm().item() <= 1e-4 * denom, (k, (q - r).norm().item() / denom)
+        assert (p.grad - r).norm().item() <= 1e-4 * denom, (k, (p.grad - r).norm().item() / denom)
     print(f"padded-vs-ragged worst rel L2 {worst:.2e}; run-to-run {noise:.2e}")
