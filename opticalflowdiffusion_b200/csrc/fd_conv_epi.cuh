@@ -32,7 +32,18 @@ struct EpiCtx {
   double* gn_stats;
   int H, W, Cout, Wt;
   int shuffle_cq;               // > 0: pixel-shuffle store (dgrad of Downsample): map_out is (Cq, 2, W, 2, H), Cq = Cout / 4
+  int tempty_remote;            // != 0 (CTA pairs, non-leader): "accumulator drained" arrives on the LEADER CTA's barrier
 };
+
+// arrive on the mbarrier at the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t rank) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}" ::"r"(bar),
+      "r"(rank)
+      : "memory");
+}
 
 // GPT = GroupNorm groups covered by one N-tile (8 when Cout == BLOCK_N, 4 when Cout == 2*BLOCK_N, 0 = no statistics).
 // Must be called by warps 2..9 of the CTA (threads 64..319); next_tile(iter, tile) enumerates this CTA's tiles in
@@ -181,7 +192,8 @@ __device__ __forceinline__ void conv_epilogue(const EpiCtx& ec, NextTile next_ti
         fence_proxy_async_smem();
         if (slab == (BLOCK_N + 63) / 64 - 1) {
           tc_fence_before();
-          mbar_arrive(ec.tempty0 + 8u * as);          // all TMEM reads of this tile are done
+          if (ec.tempty_remote) mbar_arrive_cluster(ec.tempty0 + 8u * as, 0);
+          else mbar_arrive(ec.tempty0 + 8u * as);     // all TMEM reads of this tile are done
         }
         named_bar_sync(1, kEpiThreads);
         if (issuer) {

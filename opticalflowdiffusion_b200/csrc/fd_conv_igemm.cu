@@ -193,6 +193,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
     ec.gn_stats = p.gn_stats;
     ec.H = p.H; ec.W = p.W; ec.Cout = p.Cout; ec.Wt = p.Wt;
     ec.shuffle_cq = p.shuffle_cq;
+    ec.tempty_remote = 0;
     conv_epilogue<BLOCK_N, GPT, NBUF>(ec, [&](int iter, EpiTile& t) {
       const int tile = blockIdx.x + iter * gridDim.x;
       if (tile >= p.total_tiles) return false;
@@ -212,6 +213,243 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
     tc_fence_after();
     tmem_dealloc(tmem_base, C::kTmemCols);
   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// CTA-pair variant for the N = 128 / 256 tiles (Cout % 128 == 0): cta_group::2, M = 256 = two 128-pixel tiles.
+// Measured (scripts/micro/umma_rate*.cu, profiles/r1_umma_rate.txt): a single CTA moves fill + operand reads of
+// 48 + 48 KB per 512 tensor cycles through its 128 B/clk shared-memory pipe (187 B/clk needed -> ~67 % of peak); in a
+// pair each CTA fills and holds only HALF of the weight tile, which the hardware shares: 32 + 32 KB = 125 B/clk.
+//   * both CTAs run a TMA producer: own activation tile + own half (128 rows) of the weight tile, all transaction bytes
+//     signalled on the LEADER's full barrier (cp.async.bulk.tensor ... cta_group::2, barrier address with the peer bit
+//     cleared);
+//   * only the leader issues tcgen05.mma.cta_group::2 (idesc M = 256); tcgen05.commit ... multicast::cluster frees the
+//     stage / publishes the accumulator in BOTH CTAs;
+//   * each CTA's epilogue drains its own 128 TMEM lanes; the non-leader's "drained" arrivals go to the leader's barrier.
+// ------------------------------------------------------------------------------------------------
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma2_load_5d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2, int c3,
+                                             int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(dst),
+      "l"(m), "r"(bar & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tma2_load_2d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(m), "r"(bar & kPeerBitMask), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma2_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma2_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"((uint16_t)3)
+               : "memory");
+}
+
+template <int BLOCK_N>
+struct PairCfg {
+  static constexpr int kBHalfBytes = (BLOCK_N / 2) * kBlockK * 2;   // this CTA's half of the weight tile's rows
+  static constexpr int kStageBytes = kATileBytes + kBHalfBytes;     // 32 / 24 KiB
+  static constexpr int kStages = BLOCK_N == 256 ? 5 : 7;
+  static constexpr int kStoreBufs = 2;
+  static constexpr int kTmemCols = 2 * BLOCK_N;
+  static constexpr int kTailBytes = 256 + 2 * BLOCK_N * 4 + kEpiWarps * 16 * 4 + 64;
+  static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + kStoreBufs * kSlabBytes + kTailBytes;
+};
+
+template <int BLOCK_N, int GPT>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
+                       const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_out,
+                       const ConvParams p) {
+  using C = PairCfg<BLOCK_N>;
+  constexpr int STAGES = C::kStages;
+  constexpr int NBUF = C::kStoreBufs;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t a_smem = base;
+  const uint32_t b_smem = base + STAGES * kATileBytes;
+  const uint32_t o_smem = base + STAGES * C::kStageBytes;
+  const uint32_t bar_base = o_smem + NBUF * kSlabBytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 2 + s); };
+  uint8_t* gtail = gbase + STAGES * C::kStageBytes + NBUF * kSlabBytes + 256;
+  float* s_bias = reinterpret_cast<float*>(gtail);
+  float* s_stats = reinterpret_cast<float*>(gtail + 2 * BLOCK_N * 4);
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(gtail + 2 * BLOCK_N * 4 + kEpiWarps * 16 * 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const int cpt = p.chunks0 + p.chunks1;
+  const int num_kb = p.taps * cpt;
+  const int tiles_per_img = p.tiles_w * p.tiles_h;
+  const int super_tiles = p.total_tiles / 2;            // (pair of M-tiles) x N-tile; the host guarantees an even M count
+
+  auto decode = [&](int st, int& n_tile, int& img, int& h0, int& w0) {
+    n_tile = st % p.n_tiles;
+    const int m_tile = 2 * (st / p.n_tiles) + (int)rank;
+    img = m_tile / tiles_per_img;
+    const int rem = m_tile - img * tiles_per_img;
+    h0 = (rem / p.tiles_w) * p.R;
+    w0 = (rem % p.tiles_w) * p.Wt;
+  };
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a0);
+    tma_prefetch_desc(&map_a1);
+    tma_prefetch_desc(&map_b);
+    tma_prefetch_desc(&map_out);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tfull_bar(s), 1);
+      mbar_init(tempty_bar(s), 2 * kEpiThreads);       // both CTAs' epilogues arrive on the leader's barrier
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(C::kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                                   // peers' barriers are initialised before anyone signals them
+  tc_fence_after();
+  const uint32_t tmem_base = *s_tmem;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int st = pair; st < super_tiles; st += npairs) {
+        int n_tile, img, h0, w0;
+        decode(st, n_tile, img, h0, w0);
+        int tap = 0, chunk = 0;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          if (rank == 0) mbar_expect_tx(full_bar(stage), 2 * C::kStageBytes);       // both CTAs' tiles
+          const CUtensorMap* ma = chunk < p.chunks0 ? &map_a0 : &map_a1;
+          const int c0 = (chunk < p.chunks0 ? chunk : chunk - p.chunks0) * kBlockK;
+          const uint32_t dst_a = a_smem + stage * kATileBytes;
+          if (p.mode == 0) {
+            const int ky = tap / p.KW, kx = tap - ky * p.KW;
+            tma2_load_5d(dst_a, ma, full_bar(stage), c0, w0 + kx - p.pad_w, h0 + ky - p.pad_h, img, 0);
+          } else {
+            tma2_load_5d(dst_a, ma, full_bar(stage), c0, tap & 1, w0, tap >> 1, h0);
+          }
+          tma2_load_2d(b_smem + stage * C::kBHalfBytes, &map_b, full_bar(stage), kb * kBlockK,
+                       n_tile * BLOCK_N + (int)rank * (BLOCK_N / 2));
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+          if (++chunk == cpt) { chunk = 0; ++tap; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (rank == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(256, BLOCK_N);
+      int stage = 0;
+      uint32_t phase = 0;
+      int iter = 0;
+      for (int st = pair; st < super_tiles; st += npairs, ++iter) {
+        const int as = iter & 1;
+        const uint32_t aphase = (iter >> 1) & 1;
+        mbar_wait(tempty_bar(as), aphase ^ 1u);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + as * BLOCK_N;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          if (lane == 0) {
+            const uint64_t adesc = umma_desc_sw128(a_smem + stage * kATileBytes);
+            const uint64_t bdesc = umma_desc_sw128(b_smem + stage * C::kBHalfBytes);
+#pragma unroll
+            for (int k = 0; k < kBlockK / 16; ++k)
+              umma2_bf16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+            umma2_commit(empty_bar(stage));
+            if (kb == num_kb - 1) umma2_commit(tfull_bar(as));
+          }
+          __syncwarp();
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..9 of both CTAs): own 128 TMEM lanes =====================
+    EpiCtx ec;
+    ec.tmem_base = tmem_base;
+    ec.o_smem = o_smem;
+    ec.tfull0 = tfull_bar(0);
+    ec.tempty0 = tempty_bar(0);
+    ec.s_bias = s_bias;
+    ec.s_stats = s_stats;
+    ec.map_out = &map_out;
+    ec.bias = p.bias;
+    ec.residual = p.residual;
+    ec.gn_stats = p.gn_stats;
+    ec.H = p.H; ec.W = p.W; ec.Cout = p.Cout; ec.Wt = p.Wt;
+    ec.shuffle_cq = p.shuffle_cq;
+    ec.tempty_remote = rank != 0;
+    conv_epilogue<BLOCK_N, GPT, NBUF>(ec, [&](int iter, EpiTile& t) {
+      const int st = pair + iter * npairs;
+      if (st >= super_tiles) return false;
+      decode(st, t.n_tile, t.img, t.h0, t.w0);
+      return true;
+    });
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                                   // nobody exits while the peer may still touch its barriers / smem
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(C::kTmemCols) : "memory");
+  }
+}
+
+template <int BLOCK_N, int GPT>
+int launch_pair(const CUtensorMap& ma0, const CUtensorMap& ma1, const CUtensorMap& mb, const CUtensorMap& mo, const ConvParams& p,
+                int sms, cudaStream_t st) {
+  using C = PairCfg<BLOCK_N>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    FD_CUDA(cudaFuncSetAttribute(conv_igemm_pair_kernel<BLOCK_N, GPT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 C::kSmemBytes));
+    attr_set = true;
+  }
+  int grid = p.total_tiles < sms ? p.total_tiles : sms;
+  grid &= ~1;
+  conv_igemm_pair_kernel<BLOCK_N, GPT><<<grid, kThreads, C::kSmemBytes, st>>>(ma0, ma1, mb, mo, p);
+  FD_LAUNCH_CHECK();
+  return FD_OK;
 }
 
 struct TileShape {
@@ -363,11 +601,24 @@ int fd_conv_igemm_ex(const void* src0, int C0, const void* src1, int C1, const v
   const long total = (long)p.N * p.tiles_w * p.tiles_h * p.n_tiles;
   FD_REQUIRE(total < (1L << 31), "conv_igemm: too many tiles");
   p.total_tiles = (int)total;
+  const bool stats_ = gn_stats != nullptr;
+  const bool store_heavy_ = !stats_ && p.taps * (p.chunks0 + p.chunks1) <= 4;
+  static int pair_mode = -1;
+  if (pair_mode < 0) {
+    const char* e = getenv("FD_CONV_PAIR");
+    pair_mode = e == nullptr ? 1 : atoi(e);
+  }
+  // CTA pairs (cta_group::2): needs an even number of M-tiles (two per pair).  Measured at batch 8, 440x1024 shapes:
+  // N = 256 tiles 1.44-1.53 PF/s vs 1.41-1.50 single (+2 %: those layers already run at the power-limited practical
+  // peak, cuBLAS burst = 1.65 PF/s); N = 128 tiles 0.85-0.87 vs 0.91-0.94 PF/s single (slower) -> pairs for N = 256 only
+  // (FD_CONV_PAIR=2 also pairs the N = 128 tiles, FD_CONV_PAIR=0 disables pairing).
+  const bool use_pair = pair_mode && (block_n == 256 || (block_n == 128 && pair_mode >= 2)) && !store_heavy_ && out_mode == 0 &&
+                        ((long)p.N * p.tiles_w * p.tiles_h) % 2 == 0 && p.total_tiles >= 2;
   {
     const uint64_t K = (uint64_t)p.taps * (C0 + C1);
     const uint64_t dims[2] = {K, (uint64_t)Cout};
     const uint64_t str[1] = {K * 2};
-    const uint32_t box[2] = {64, (uint32_t)block_n};
+    const uint32_t box[2] = {64, (uint32_t)(use_pair ? block_n / 2 : block_n)};
     if (int e = make_tmap_bf16(&mb, wpacked, 2, dims, str, box)) return e;
   }
   if (out_mode == 1) {
@@ -395,6 +646,11 @@ int fd_conv_igemm_ex(const void* src0, int C0, const void* src1, int C1, const v
     if (block_n == 128) return launch<128, 0, 1>(ma0, ma1, mb, mo, p, sms, st);
     return launch<64, 0, 1>(ma0, ma1, mb, mo, p, sms, st);
   }
+  if (use_pair && block_n == 256) {
+    if (!stats) return launch_pair<256, 0>(ma0, ma1, mb, mo, p, sms, st);
+    return p.n_tiles == 1 ? launch_pair<256, 8>(ma0, ma1, mb, mo, p, sms, st) : launch_pair<256, 4>(ma0, ma1, mb, mo, p, sms, st);
+  }
+  if (use_pair) return stats ? launch_pair<128, 8>(ma0, ma1, mb, mo, p, sms, st) : launch_pair<128, 0>(ma0, ma1, mb, mo, p, sms, st);
   if (block_n == 256) {
     if (!stats) return launch<256, 0>(ma0, ma1, mb, mo, p, sms, st);
     return p.n_tiles == 1 ? launch<256, 8>(ma0, ma1, mb, mo, p, sms, st) : launch<256, 4>(ma0, ma1, mb, mo, p, sms, st);

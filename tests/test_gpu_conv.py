@@ -86,6 +86,12 @@ CASES = [
     (2, (64, 64), 64, 21, 256, (3, 3), (1, 1), True, False, True),      # rolling-strip kernel, two sources
     (1, (128,), 64, 70, 200, (3, 3), (1, 1), True, False, False),       # rolling-strip kernel, 128-channel source, ragged W
     (2, (64,), 64, 37, 130, (3, 3), (1, 1), True, False, True),         # ragged W: second column block is 2 pixels wide
+    (2, (256,), 256, 24, 40, (3, 3), (1, 1), True, False, True),        # CTA-pair kernel (cta_group::2), statistics, one N-tile
+    (4, (384,), 512, 12, 20, (3, 3), (1, 1), True, False, True),        # CTA-pair kernel, two N-tiles, ragged tiles
+    (2, (512, 256), 512, 8, 16, (1, 1), (0, 0), True, True, False),     # CTA-pair kernel, 1x1 with 12 K-blocks + residual
+    (2, (256,), 768, 10, 24, (3, 3), (1, 1), False, False, False),      # CTA-pair kernel, three N-tiles, no bias
+    (2, (128, 64), 128, 20, 48, (3, 3), (1, 1), True, False, True),     # CTA-pair kernel with N = 128 tiles, two sources
+    (2, (128,), 128, 9, 30, (3, 3), (1, 1), True, True, False),         # ... N = 128, residual
     (2, (64,), 64, 30, 256, (3, 3), (1, 1), True, True, True),          # rolling-strip kernel with a residual (dgrad accumulation)
     (1, (64, 64), 64, 9, 130, (3, 3), (1, 1), False, True, False),      # two passes: caller's residual, then the partial sum
 ]
