@@ -38,8 +38,13 @@ class MatrixFlowExperiment:
             raise ValueError(f"algorithm '{name}' is outside the flow_diffuser hot path "
                              f"(have: {sorted(self.compatible_algorithms)})")
         algo = self.compatible_algorithms[name](self.cfg.algorithm)
+        self._resume = None
         if self.ckpt_path:
             load_checkpoint(algo, self.ckpt_path)        # Lightning .ckpt or bare state_dict, any alias family
+            ck = torch.load(self.ckpt_path, map_location="cpu", weights_only=False)
+            if isinstance(ck, dict) and "optimizer_states" in ck:
+                self._resume = {"optimizer": ck["optimizer_states"][0], "global_step": int(ck.get("global_step", 0)),
+                                "epoch": int(ck.get("epoch", 0))}
         algo.logger = self.logger
         return algo
 
@@ -80,7 +85,16 @@ class MatrixFlowExperiment:
         accum = int(tr.optim.accumulate_grad_batches)
         epochs = int(self.cfg.experiment.epochs)
         losses, step, epoch = [], 0, 0
-        while (epochs < 0 or epoch < epochs) and (max_steps is None or step < max_steps):
+        # checkpoint / resume (exp_base.py:184-190,213: ModelCheckpoint(every_n_train_steps) + fit(ckpt_path=...))
+        ck_cfg = tr.get("checkpointing") if hasattr(tr, "get") else None
+        every = int(ck_cfg.get("every_n_train_steps", 0)) if ck_cfg else 0
+        ck_dir = os.path.join(str(self.cfg.get("output_dir", "outputs")), "checkpoints")
+        if self._resume is not None:
+            opt.load_state_dict(self._resume["optimizer"])
+            step, epoch = self._resume["global_step"], self._resume["epoch"]
+            self.algo.global_step = step
+        start_step = step
+        while (epochs < 0 or epoch < epochs) and (max_steps is None or step - start_step < max_steps):
             loader = self._loader("training", tr)
             if hasattr(loader.sampler, "set_epoch"):
                 loader.sampler.set_epoch(epoch)
@@ -94,12 +108,17 @@ class MatrixFlowExperiment:
                     step += 1
                     self.algo.global_step = step
                     losses.append(loss.detach())
-                    if max_steps is not None and step >= max_steps:
+                    if every > 0 and step % every == 0 and self.rank == 0:
+                        from ..io_formats import save_checkpoint
+                        os.makedirs(ck_dir, exist_ok=True)
+                        save_checkpoint(self.algo, os.path.join(ck_dir, f"step_{step:07d}.ckpt"), optimizer=opt,
+                                        global_step=step, epoch=epoch)
+                    if max_steps is not None and step - start_step >= max_steps:
                         break
             epoch += 1
             if max_steps is None and epochs < 0:
                 break          # "epochs: -1" means until stopped in the reference; one pass without a step budget
-        return {"train/loss": [float(x) for x in losses], "steps": step}
+        return {"train/loss": [float(x) for x in losses], "steps": step - start_step, "global_step": step}
 
     @torch.no_grad()
     def validate(self, max_batches: Optional[int] = None):

@@ -61,12 +61,24 @@ class FusedAdam(torch.optim.Optimizer):
             p.data = view                      # the module's parameters now alias the flat buffer
         self._flat_p, self._offsets, self._n = flat, offs, off
         self._flat_g = torch.zeros(off, device=dev, dtype=torch.float32)
-        self._m = torch.zeros(off, device=dev, dtype=torch.float32)
-        self._v = torch.zeros(off, device=dev, dtype=torch.float32)
+        m = torch.zeros(off, device=dev, dtype=torch.float32)
+        v = torch.zeros(off, device=dev, dtype=torch.float32)
         self._sumsq = torch.zeros(1, device=dev, dtype=torch.float32)
         for p, o in zip(params, offs):         # torch.optim-compatible state views (state_dict / checkpoints)
-            self.state[p] = {"step": torch.tensor(0.0), "exp_avg": self._m[o:o + p.numel()].view_as(p),
-                             "exp_avg_sq": self._v[o:o + p.numel()].view_as(p)}
+            old = self.state.get(p)            # state restored by load_state_dict (resume) moves into the flat buffers
+            mv, vv = m[o:o + p.numel()].view_as(p), v[o:o + p.numel()].view_as(p)
+            step = torch.tensor(0.0)
+            if old:
+                mv.copy_(old["exp_avg"])
+                vv.copy_(old["exp_avg_sq"])
+                step = torch.as_tensor(old["step"]).detach().float().cpu().clone()
+                self.step_count = int(step)
+            self.state[p] = {"step": step, "exp_avg": mv, "exp_avg_sq": vv}
+        self._m, self._v = m, v
+
+    def load_state_dict(self, state_dict):
+        super().load_state_dict(state_dict)
+        self._flat_p = None                    # re-flatten on the next step: picks the restored moments up
 
     def _still_flat(self) -> bool:
         if self._flat_p is None:

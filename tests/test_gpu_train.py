@@ -135,7 +135,7 @@ def test_training_step_and_fused_adam():
         assert all(gr is not None and torch.isfinite(gr).all() for gr in grads)
         opt.step()
         opt.zero_grad(set_to_none=True)
-        losses.append(float(loss))
+        losses.append(float(loss.detach()))
     assert losses[-1] < losses[0], losses
     # the module API of the reference: training_step returns a scalar that carries the graph
     loss = algo.training_step((img, tgt, flow), 0)
@@ -249,3 +249,35 @@ def test_backward_through_the_internal_padding():
         assert (q - r).norm().item() <= 1e-4 * denom, (k, (q - r).norm().item() / denom)
         assert (p.grad - r).norm().item() <= 1e-4 * denom, (k, (p.grad - r).norm().item() / denom)
     print(f"padded-vs-ragged worst rel L2 {worst:.2e}; run-to-run {noise:.2e}")
+
+
+def test_checkpoint_and_resume(tmp_path):
+    """ModelCheckpoint(every_n_train_steps) + fit(ckpt_path=...) (exp_base.py:184-190,213): a run resumed from the step-2
+    checkpoint reproduces the third step of the uninterrupted run (parameters and Adam moments restored)."""
+    from opticalflowdiffusion_b200.config import compose
+    from opticalflowdiffusion_b200.experiments import build_experiment
+    ov = ["algorithm.target=flow", "algorithm.gpu_augment=true", "dataset.height=32", "dataset.width=32", "dataset.length=8",
+          "experiment.training.data.batch_size=2", "experiment.training.data.shuffle=false",
+          "experiment.training.checkpointing.every_n_train_steps=2", f"+output_dir={tmp_path}"]
+
+    def run(ckpt, steps):
+        import random
+        random.seed(0)
+        torch.manual_seed(0)
+        exp = build_experiment(compose(ov), None, ckpt)
+        exp.algo.preprocess = (lambda f: (lambda batch, aug=True: f(batch, aug=False)))(exp.algo.preprocess)   # no RNG in the data
+        torch.manual_seed(123)                       # same t / noise draws in both runs from here on
+        out = exp.train(max_steps=steps)
+        return exp, out
+
+    exp_a, out_a = run(None, 2)
+    ck = tmp_path / "checkpoints" / "step_0000002.ckpt"
+    assert ck.exists() and out_a["global_step"] == 2
+    m_a = exp_a.algo.optimizers._m.clone()
+    exp_b, out_b = run(str(ck), 0)
+    assert out_b["global_step"] == 2
+    for (k, a), b in zip(exp_a.algo.state_dict().items(), exp_b.algo.state_dict().values()):
+        assert torch.equal(a.cpu(), b.cpu()), k
+    # the restored moments land in the flat buffers at the first step
+    exp_b.algo.optimizers._flatten()
+    assert torch.equal(exp_b.algo.optimizers._m.cpu(), m_a.cpu()) and exp_b.algo.optimizers.step_count == 2
