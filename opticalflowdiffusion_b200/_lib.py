@@ -144,3 +144,23 @@ def require_cuda(*tensors):
     for t in tensors:
         if t is not None and not t.is_cuda:
             raise FlowDiffError("libflowdiff operates on CUDA tensors only (no CPU fallback)")
+
+
+class nvtx_range:
+    """NVTX range around a region of kernel launches when FD_NVTX=1 (ncu / nsys can then filter by range:
+    `ncu --nvtx --nvtx-include "unet.backward/"`); a no-op otherwise."""
+
+    enabled = os.environ.get("FD_NVTX", "0") not in ("", "0")
+
+    def __init__(self, name: str):
+        self.name = name
+
+    def __enter__(self):
+        if self.enabled:
+            torch.cuda.nvtx.range_push(self.name)
+        return self
+
+    def __exit__(self, *exc):
+        if self.enabled:
+            torch.cuda.nvtx.range_pop()
+        return False

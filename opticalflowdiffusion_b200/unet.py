@@ -264,7 +264,8 @@ class Unet(UnetParams, TrainMixin):
         kernels (unet_train.py); under ``torch.no_grad()`` (sampling, validation) it is the inference path."""
         if torch.is_grad_enabled() and not return_taps and any(p.requires_grad for p in self.parameters()):
             return UnetFunction.apply(self, x, external_cond, time, nan_mask, *self.parameters())
-        return self._forward_infer(x, external_cond, time, nan_mask, return_taps)
+        with _lib.nvtx_range("unet.forward"):
+            return self._forward_infer(x, external_cond, time, nan_mask, return_taps)
 
     @torch.no_grad()
     def _forward_infer(self, x: Tensor, external_cond: Optional[Tensor], time: Optional[Tensor], nan_mask: bool = False,

@@ -407,7 +407,8 @@ class UnetFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, unet, x, cond, time, nan_mask, *params):
-        out, backward = unet.forward_train(x, cond, time, nan_mask)
+        with _lib.nvtx_range("unet.forward_train"):
+            out, backward = unet.forward_train(x, cond, time, nan_mask)
         ctx.unet = unet
         ctx.run_backward = backward
         return out
@@ -421,7 +422,8 @@ class UnetFunction(torch.autograd.Function):
                                "(retain_graph / double backward are not supported on this path)")
         gb = unet.grad_buffer
         gb.zero_()
-        ctx.run_backward(dout)
+        with _lib.nvtx_range("unet.backward"):
+            ctx.run_backward(dout)
         ctx.run_backward = None
         # hand autograd its own copy of the flat buffer's views: p.grad accumulation (+=) must not alias the
         # buffer the next backward zero-fills
