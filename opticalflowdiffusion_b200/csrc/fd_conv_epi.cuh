@@ -71,7 +71,6 @@ __device__ __forceinline__ void conv_epilogue(const EpiCtx& ec, NextTile next_ti
     const int half = ew >> 2;                 // which chunk parity this warp owns
     const int row = quarter * 32 + lane;      // accumulator row = pixel within the tile
     const int rr = row / ec.Wt, ww = row - rr * ec.Wt;
-    const bool issuer = (et == 0);
     float st_s[CPW > 0 ? CPW : 1][GIC], st_q[CPW > 0 ? CPW : 1][GIC];
 #pragma unroll
     for (int a = 0; a < (CPW > 0 ? CPW : 1); ++a)
@@ -134,7 +133,7 @@ __device__ __forceinline__ void conv_epilogue(const EpiCtx& ec, NextTile next_ti
       for (int slab = 0; slab < (BLOCK_N + 63) / 64; ++slab) {
         const uint32_t buf = o_smem + (slab_count % NBUF) * kSlabBytes;
         ++slab_count;
-        if (issuer) tma_store_wait_read<NBUF - 1>();      // the store that last used this buffer has read it
+        if (ew == 0 && elect_one_sync()) tma_store_wait_read<NBUF - 1>();   // the store that last used this buffer has read it
         named_bar_sync(1, kEpiThreads);
         const int ci = slab * 2 + half;                   // this warp's chunk inside the slab
         const int c = ci * 32;
@@ -196,7 +195,7 @@ __device__ __forceinline__ void conv_epilogue(const EpiCtx& ec, NextTile next_ti
           else mbar_arrive(ec.tempty0 + 8u * as);     // all TMEM reads of this tile are done
         }
         named_bar_sync(1, kEpiThreads);
-        if (issuer) {
+        if (ew == 0 && elect_one_sync()) {                 // elect.sync: straight-line UTMASTG (see fd_tc.cuh)
           const int cc = n0 + slab * 64;
           if (ec.shuffle_cq > 0) {
             const int pq = cc / ec.shuffle_cq;          // p1 * 2 + p2
@@ -209,7 +208,8 @@ __device__ __forceinline__ void conv_epilogue(const EpiCtx& ec, NextTile next_ti
       }
     }
     flush_stats();
-    if (issuer) tma_store_wait_all();
+    __syncwarp();
+    if (ew == 0 && elect_one_sync()) tma_store_wait_all();     // same elected lane as the stores (bulk groups are per thread)
   }
 }
 

@@ -33,7 +33,7 @@ namespace {
 
 constexpr int kBlockK = 64;
 constexpr int kATileBytes = kBlockM * kBlockK * 2;  // 16 KiB
-constexpr int kThreads = 64 + kEpiThreads;          // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+constexpr int kThreads = 64 + kEpiThreads + 32;     // warp 0 TMA (A), warp 1 MMA, warps 2..9 epilogue, warp 10 TMA (B)
 
 struct ConvParams {
   int N, H, W;        // images, output rows, output columns (after flattening / merging)
@@ -57,8 +57,8 @@ template <int BLOCK_N, int SH = 0>
 struct Cfg {
   static constexpr int kBTileBytes = BLOCK_N * kBlockK * 2;
   static constexpr int kStageBytes = kATileBytes + kBTileBytes;
-  static constexpr int kStages = SH ? 3 : (BLOCK_N == 64 ? 7 : (BLOCK_N == 128 ? 5 : 4));
-  static constexpr int kStoreBufs = SH ? (BLOCK_N / 64 > 2 ? BLOCK_N / 64 : 2) : (BLOCK_N == 256 ? 1 : 2);   // staging slabs
+  static constexpr int kStages = SH ? 3 : (BLOCK_N == 64 ? 7 : (BLOCK_N == 128 ? 6 : 4));
+  static constexpr int kStoreBufs = SH ? (BLOCK_N / 64 > 2 ? BLOCK_N / 64 : 2) : (BLOCK_N == 64 ? 2 : 1);   // staging slabs
   static constexpr int kTmemCols = 2 * BLOCK_N;
   static constexpr int kTailBytes = 256 /*barriers*/ + 2 * BLOCK_N * 4 /*bias*/ + kEpiWarps * 16 * 4 /*stats*/ + 64;
   static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + kStoreBufs * kSlabBytes + kTailBytes;
@@ -102,7 +102,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
     tma_prefetch_desc(&map_b);
     tma_prefetch_desc(&map_out);
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(full_bar(s), 1);
+      mbar_init(full_bar(s), 2);           // one arrive.expect_tx from each of the two producer threads
       mbar_init(empty_bar(s), 1);
     }
     for (int s = 0; s < 2; ++s) {
@@ -117,9 +117,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
   tc_fence_after();
   const uint32_t tmem_base = *s_tmem;
 
-  if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
+  if (warp == 0 || warp == 10) {
+    // ===================== TMA producers: warp 0 loads the activation tiles, warp 10 the weight tiles ==============
+    // Measured (ncu on the N = 128 tiles: tensor pipe 43 % active, shared-memory pipe 43 %, L2 45 %): ONE thread issuing
+    // both cp.async.bulk.tensor ops of a K-block (+ mbarrier wait / expect_tx) needs ~600 cycles per K-block, more than the
+    // 256 cycles its four N = 128 MMAs take -- the kernel was TMA-issue bound.  Two producer threads halve that.
+    const bool loads_a = warp == 0;
+    if (elect_one_sync()) {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -132,17 +136,21 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
         int tap = 0, chunk = 0;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
-          mbar_expect_tx(full_bar(stage), C::kStageBytes);
-          const CUtensorMap* ma = chunk < p.chunks0 ? &map_a0 : &map_a1;
-          const int c0 = (chunk < p.chunks0 ? chunk : chunk - p.chunks0) * kBlockK;
-          const uint32_t dst_a = a_smem + stage * kATileBytes;
-          if (p.mode == 0) {
-            const int ky = tap / p.KW, kx = tap - ky * p.KW;
-            tma_load_5d(dst_a, ma, full_bar(stage), c0, w0 + kx - p.pad_w, h0 + ky - p.pad_h, img, 0);
+          if (loads_a) {
+            mbar_expect_tx(full_bar(stage), kATileBytes);
+            const CUtensorMap* ma = chunk < p.chunks0 ? &map_a0 : &map_a1;
+            const int c0 = (chunk < p.chunks0 ? chunk : chunk - p.chunks0) * kBlockK;
+            const uint32_t dst_a = a_smem + stage * kATileBytes;
+            if (p.mode == 0) {
+              const int ky = tap / p.KW, kx = tap - ky * p.KW;
+              tma_load_5d(dst_a, ma, full_bar(stage), c0, w0 + kx - p.pad_w, h0 + ky - p.pad_h, img, 0);
+            } else {
+              tma_load_5d(dst_a, ma, full_bar(stage), c0, tap & 1, w0, tap >> 1, h0);
+            }
           } else {
-            tma_load_5d(dst_a, ma, full_bar(stage), c0, tap & 1, w0, tap >> 1, h0);
+            mbar_expect_tx(full_bar(stage), C::kBTileBytes);
+            tma_load_2d(b_smem + stage * C::kBTileBytes, &map_b, full_bar(stage), kb * kBlockK, n_tile * BLOCK_N);
           }
-          tma_load_2d(b_smem + stage * C::kBTileBytes, &map_b, full_bar(stage), kb * kBlockK, n_tile * BLOCK_N);
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
           if (++chunk == cpt) { chunk = 0; ++tap; }
         }
@@ -163,7 +171,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(full_bar(stage), phase);
         tc_fence_after();
-        if (lane == 0) {
+        if (elect_one_sync()) {
           const uint64_t adesc = umma_desc_sw128(a_smem + stage * kATileBytes);
           const uint64_t bdesc = umma_desc_sw128(b_smem + stage * C::kBTileBytes);
 #pragma unroll
@@ -178,7 +186,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
     }
-  } else {
+  } else if (warp >= 2 && warp < 2 + kEpiWarps) {
     // ===================== epilogue (warps 2..9) =====================
     EpiCtx ec;
     ec.tmem_base = tmem_base;
@@ -346,7 +354,7 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_
 
   if (warp == 0) {
     // ===================== TMA producer (both CTAs) =====================
-    if (lane == 0) {
+    if (elect_one_sync()) {
       int stage = 0;
       uint32_t phase = 0;
       for (int st = pair; st < super_tiles; st += npairs) {
@@ -388,7 +396,7 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
-          if (lane == 0) {
+          if (elect_one_sync()) {
             const uint64_t adesc = umma_desc_sw128(a_smem + stage * kATileBytes);
             const uint64_t bdesc = umma_desc_sw128(b_smem + stage * C::kBHalfBytes);
 #pragma unroll
@@ -402,7 +410,7 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_
         }
       }
     }
-  } else {
+  } else if (warp >= 2 && warp < 2 + kEpiWarps) {
     // ===================== epilogue (warps 2..9 of both CTAs): own 128 TMEM lanes =====================
     EpiCtx ec;
     ec.tmem_base = tmem_base;

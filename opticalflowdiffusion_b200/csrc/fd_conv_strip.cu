@@ -78,7 +78,6 @@ __device__ __forceinline__ void strip_epilogue2(const EpiCtx& ec, NextTile next_
   const int quarter = warp & 3, group = ew >> 2;
   const int gt = (ew & 3) * 32 + lane;               // thread index inside the group: 0..127
   const int row = quarter * 32 + lane;
-  const bool issuer = (gt == 0);
   const int bar_id = 1 + group;
   float* const bias_s = ec.s_bias + group * kC;
   float* const s_stats = ec.s_stats + group * 64;    // [4 warps][16]
@@ -177,7 +176,7 @@ __device__ __forceinline__ void strip_epilogue2(const EpiCtx& ec, NextTile next_
 #pragma unroll
       for (int j = 0; j < 16; ++j) packed[hc * 16 + j] = fd_pack_bf16(v[2 * j], v[2 * j + 1]);
     }
-    if (issuer) tma_store_wait_read<0>();              // this group's previous store has read the slab
+    if ((ew & 3) == 0 && elect_one_sync()) tma_store_wait_read<0>();   // this group's previous store has read the slab
     named_bar_sync(bar_id, 128);
     const uint32_t rbase = buf + (uint32_t)row * 128u;
 #pragma unroll
@@ -189,13 +188,14 @@ __device__ __forceinline__ void strip_epilogue2(const EpiCtx& ec, NextTile next_
     }
     fence_proxy_async_smem();
     named_bar_sync(bar_id, 128);
-    if (issuer) {
+    if ((ew & 3) == 0 && elect_one_sync()) {             // the group's first warp; elect.sync keeps UTMASTG straight-line
       tma_store_5d(ec.map_out, buf, 0, w0, h, img, 0);
       tma_store_commit();
     }
   }
   flush_stats();
-  if (issuer) tma_store_wait_all();
+  __syncwarp();
+  if ((ew & 3) == 0 && elect_one_sync()) tma_store_wait_all();
 }
 
 template <int GPT>
@@ -244,7 +244,7 @@ conv3x3_strip_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_co
 
   if (warp == 0) {
     // ===================== TMA producer: weights once, then one strip per input row =====================
-    if (lane == 0) {
+    if (elect_one_sync()) {
       mbar_expect_tx(wfull_bar, kWBytes);
       for (int tap = 0; tap < 9; ++tap)
         tma_load_2d(w_smem + tap * kWTapBytes, &map_w, wfull_bar, tap * p.w_kstride + p.w_k0, 0);
@@ -286,7 +286,7 @@ conv3x3_strip_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_co
           mbar_wait(full_bar(s % kNS), (s / kNS) & 1u);
         }
         tc_fence_after();
-        if (lane == 0) {
+        if (elect_one_sync()) {
           const uint32_t tmem_d = tmem_base + as * kC;
 #pragma unroll
           for (int ky = 0; ky < 3; ++ky) {

@@ -115,7 +115,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
   const uint32_t tmem_base = *s_tmem;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one_sync()) {
       int stage = 0;
       uint32_t phase = 0;
       const int ky = tap / p.KW, kx = tap - ky * p.KW;
@@ -151,7 +151,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
     for (int t = t_begin; t < t_end; ++t) {
       mbar_wait(full_bar(stage), phase);
       tc_fence_after();
-      if (lane == 0) {
+      if (elect_one_sync()) {
         const uint32_t sa = base + stage * C::kStageBytes;
         const uint32_t sb = sa + C::kABytes;
 #pragma unroll

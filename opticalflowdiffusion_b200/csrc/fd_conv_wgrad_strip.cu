@@ -126,7 +126,7 @@ wgrad3x3_strip_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_c
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    if (elect_one_sync()) {
       uint32_t seq = 0, dseq = 0;
       for (long u = u_begin; u < u_end;) {
         const Item it = next_item(p, u, u_end);
@@ -164,7 +164,7 @@ wgrad3x3_strip_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_c
       if (it.pair != cur_pair) {
         if (cur_pair >= 0) {
           // hand the finished accumulators to the flush warps and wait until they are drained
-          if (lane == 0) umma_commit(acc_full);
+          if (elect_one_sync()) umma_commit(acc_full);
           __syncwarp();
           mbar_wait(acc_empty, flushes & 1u);
           tc_fence_after();
@@ -181,7 +181,7 @@ wgrad3x3_strip_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_c
         }
         mbar_wait(dfull_bar((dseq0 + i) % kNSD), ((dseq0 + i) / kNSD) & 1u);
         tc_fence_after();
-        if (lane == 0) {
+        if (elect_one_sync()) {
           const uint32_t dy = dy_base + ((dseq0 + i) % kNSD) * kDyTx;
 #pragma unroll
           for (int ky = 0; ky < 3; ++ky) {
@@ -208,7 +208,7 @@ wgrad3x3_strip_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_c
       dseq0 += rows;
       u += rows;
     }
-    if (cur_pair >= 0 && lane == 0) umma_commit(acc_full);
+    if (cur_pair >= 0 && elect_one_sync()) umma_commit(acc_full);
     __syncwarp();
   } else {
     // ===================== flush: TMEM -> dW (fp32 reductions), once per block pair this CTA touched

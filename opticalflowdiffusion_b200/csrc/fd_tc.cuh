@@ -11,6 +11,17 @@ namespace fdtc {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// One elected lane of a fully converged warp (elect.sync).  The single-thread issue sites (TMA, tcgen05.mma / .commit) use
+// this instead of `lane == 0`: under `if (lane == 0)` the compiler cannot prove that the uniform-datapath operands of
+// UTCHMMA / UTCBAR / UTMALDG are warp-uniform and wraps EVERY such instruction in an ELECT + BRA.U.ANY waterfall loop
+// (measured with ncu's source view on the N = 128 tiles: ~600 cycles to issue the 4 MMAs + 2 commits of a K-block that
+// occupy the tensor pipe for 256); with elect.sync the issue sequence is straight-line SASS.
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
 // ---- mbarrier ----------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
