@@ -32,6 +32,7 @@ struct EpiCtx {
   double* gn_stats;
   int H, W, Cout, Wt;
   int shuffle_cq;               // > 0: pixel-shuffle store (dgrad of Downsample): map_out is (Cq, 2, W, 2, H), Cq = Cout / 4
+  int dbg;                      // diagnostics (FD_CONV_DBG): 8 = barrier handshakes only, no epilogue work
   int tempty_remote;            // != 0 (CTA pairs, non-leader): "accumulator drained" arrives on the LEADER CTA's barrier
 };
 
@@ -127,6 +128,12 @@ __device__ __forceinline__ void conv_epilogue(const EpiCtx& ec, NextTile next_ti
 
       mbar_wait(ec.tfull0 + 8u * as, aphase);
       tc_fence_after();
+      if (ec.dbg & 8) {
+        tc_fence_before();
+        if (ec.tempty_remote) mbar_arrive_cluster(ec.tempty0 + 8u * as, 0);
+        else mbar_arrive(ec.tempty0 + 8u * as);
+        continue;
+      }
       const long pix = ((long)img * ec.H + h) * ec.W + w;
       const __nv_bfloat16* rrow = ec.residual ? ec.residual + pix * ec.Cout + n0 : nullptr;
 #pragma unroll

@@ -329,6 +329,7 @@ conv3x3_strip_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_co
     ec.H = p.H; ec.W = p.W; ec.Cout = kC; ec.Wt = kTileW;
     ec.shuffle_cq = 0;
     ec.tempty_remote = 0;
+    ec.dbg = 0;
     int item = blockIdx.x, j = 0, n = 0, w0 = 0, ra = 0, rb = 0;
     bool have = false;
     auto next = [&](int, EpiTile& t) {

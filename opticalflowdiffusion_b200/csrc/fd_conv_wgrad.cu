@@ -144,29 +144,37 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
       }
     }
   } else if (warp == 1) {
+    // one elected lane runs the whole loop; the next stage's barrier wait and descriptor bases (general registers) come before
+    // this stage's commit so that only register-to-uniform moves separate two stages' MMAs (see conv_igemm_kernel)
     constexpr uint32_t idesc = umma_idesc_bf16_mn(128, BN);
-    int stage = 0;
-    uint32_t phase = 0;
-    const uint32_t lbo_a = nchunk == 2 ? (uint32_t)kChunkBytes : 0u;   // single chunk: rows 64..127 alias rows 0..63 (ignored)
-    for (int t = t_begin; t < t_end; ++t) {
-      mbar_wait(full_bar(stage), phase);
-      tc_fence_after();
-      if (elect_one_sync()) {
-        const uint32_t sa = base + stage * C::kStageBytes;
-        const uint32_t sb = sa + C::kABytes;
+    if (elect_one_sync()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t lbo_a = nchunk == 2 ? (uint32_t)kChunkBytes : 0u;   // single chunk: rows 64..127 alias rows 0..63 (ignored)
+      const uint64_t adesc0 = umma_desc_mn_sw128(base, lbo_a);
+      const uint64_t bdesc0 = umma_desc_mn_sw128(base + C::kABytes, (uint32_t)kChunkBytes);
+      uint64_t ad = opaque64(adesc0), bd = opaque64(bdesc0);
+      bool waited = false;
+      for (int t = t_begin; t < t_end; ++t) {
+        if (!waited) mbar_wait(full_bar(stage), phase);
+        tc_fence_after();
 #pragma unroll
         for (int k = 0; k < kPx / 16; ++k) {
-          // 16 pixels = two 8-row swizzle atoms = 2048 B further along K
-          const uint64_t adesc = umma_desc_mn_sw128(sa + k * 2048, lbo_a);
-          const uint64_t bdesc = umma_desc_mn_sw128(sb + k * 2048, (uint32_t)kChunkBytes);
-          umma_bf16(tmem_base, adesc, bdesc, idesc, (t != t_begin || k != 0) ? 1u : 0u);
+          // 16 pixels = two 8-row swizzle atoms = 2048 B further along K (+128 in the address field)
+          umma_bf16(tmem_base, ad + (uint64_t)(k * (2048 >> 4)), bd + (uint64_t)(k * (2048 >> 4)), idesc,
+                    (t != t_begin || k != 0) ? 1u : 0u);
         }
-        umma_commit(empty_bar(stage));
+        const uint32_t cur_empty = empty_bar(stage);
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        ad = opaque64(adesc0 + (uint64_t)(stage * (C::kStageBytes >> 4)));
+        bd = opaque64(bdesc0 + (uint64_t)(stage * (C::kStageBytes >> 4)));
+        waited = t + 1 < t_end;
+        if (waited) mbar_wait(full_bar(stage), phase);
+        umma_commit(cur_empty);
         if (t == t_end - 1) umma_commit(done_bar);
       }
-      __syncwarp();
-      if (++stage == STAGES) { stage = 0; phase ^= 1u; }
     }
+    __syncwarp();
   } else if (t_end > t_begin) {
     // epilogue: TMEM lane = input channel row, column = output channel
     const int quarter = warp & 3;
