@@ -25,12 +25,19 @@
 // one N = 192 instruction per kernel row on the unshifted strip with the kx shift done in the epilogue by warp shuffles --
 // 44 % less operand traffic, but 192 accumulator columns leave room for only two TMEM stages and the longer epilogue
 // (3 x tcgen05.ld, quarter-to-quarter row exchange) then sits on the critical path.
+#include <stdlib.h>
+
 #include "fd_conv_epi.cuh"
 
 using namespace fdtc;
 
 namespace {
 
+#ifdef FD_CONV_DIAG
+constexpr bool kDiag = true;
+#else
+constexpr bool kDiag = false;
+#endif
 constexpr int kC = 64;                         // input = output channels
 constexpr int kTileW = 128;                    // output pixels per tile (one image row segment)
 constexpr int kStripPx = kTileW + 2;           // + left/right halo
@@ -43,9 +50,27 @@ constexpr int kThreads = 64 + kEpiThreads + 32;  // warp 0 TMA, warps 1 and 10 M
 constexpr int kTail = 256 + 2 * kC * 4 + kEpiWarps * 16 * 4 + 64;
 constexpr int kSmemBytes = 1024 + kWBytes + kNS * kStripBytes + 2 * kSlabBytes + kTail;
 
+// A operand from tensor memory ("TS" form): staged there by tcgen05.cp, which reads the same canonical K-major SWIZZLE_128B
+// shared-memory layout as the SS-form instruction (scripts/micro/umma_ts.cu: bit-identical products, also with the start
+// shifted by whole 128-byte pixel rows; 32.0 cycles per 128x64x16 instruction instead of 48.0)
+__device__ __forceinline__ void utccp_128x256b(uint32_t tmem_dst, uint64_t sdesc) {
+  asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;" ::"r"(tmem_dst), "l"(sdesc) : "memory");
+}
+__device__ __forceinline__ void umma_ts_bf16(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+constexpr int kATmemCol0 = 2 * kC;             // TS variant: accumulators in columns [0, 128), A ring in [128, 512)
+constexpr int kATmemSlotCols = 3 * (kC / 2);   // one strip = 3 kx-shifted copies x 32 columns (64 bf16 per lane)
+constexpr int kATmemSlots = 4;                 // 3 strips in use + 1 being staged
+
 struct StripParams {
   int N, H, W;
-  int wblocks, segs, seg_rows, total_items;
+  int wblocks, total_rows;   // column blocks per image; N * wblocks * H output rows in (image, column block, row) order
   int tile_w;                // output pixels per tile
   int base_offset_mode;      // 2 (default): base_offset 0 -- correct; 1: (addr >> 7) & 7 -- measured WRONG, kept as an experiment
   int c_off;                 // first input channel of this pass inside the source tensor (0 or 64)
@@ -53,17 +78,32 @@ struct StripParams {
   const float* bias;
   const __nv_bfloat16* residual;
   double* gn_stats;
+  int pf;                    // L2 prefetch distance in rows (0 = off)
+  int dbg;                   // FD_CONV_DBG in FD_CONV_DIAG builds: 4 = no MMAs, 8 = epilogue handshakes only, 64 = no tcgen05.cp
 };
 
-__device__ __forceinline__ void decode_item(const StripParams& p, int item, int& n, int& w0, int& ra, int& rb) {
-  const int seg = item % p.segs;
-  const int rest = item / p.segs;
-  const int wb = rest % p.wblocks;
-  n = rest / p.wblocks;
-  w0 = wb * p.tile_w;
-  ra = seg * p.seg_rows;
-  rb = min(p.H, ra + p.seg_rows);
-}
+// Work split: the N * wblocks * H output rows (128-pixel tiles), ordered (image, column block, row), are cut into gridDim.x
+// equal contiguous ranges, one per CTA.  A CTA walks its range as 1-3 runs of consecutive rows of one column ("items");
+// every run costs two extra halo strips, so long runs are cheap, and the ranges differ by at most one tile (the former
+// round-robin over 16..64-row segments left 180 vs 200 tiles on different SMs and paid the halo ten times per CTA).
+struct StripWalk {
+  int cur, end;
+  __device__ __forceinline__ explicit StripWalk(const StripParams& p) {
+    cur = (int)((long)p.total_rows * blockIdx.x / gridDim.x);
+    end = (int)((long)p.total_rows * (blockIdx.x + 1) / gridDim.x);
+  }
+  __device__ __forceinline__ bool next(const StripParams& p, int& n, int& w0, int& ra, int& rb) {
+    if (cur >= end) return false;
+    const int col = cur / p.H;
+    ra = cur - col * p.H;
+    const int rows = min(p.H - ra, end - cur);
+    rb = ra + rows;
+    n = col / p.wblocks;
+    w0 = (col - n * p.wblocks) * p.tile_w;
+    cur += rows;
+    return true;
+  }
+};
 
 // Epilogue of the classic (nine N = 64 taps) variant.  Measured: with all 8 epilogue warps working on ONE tile the
 // kernel spends ~2800 cycles per tile although the MMAs need 1728 and the epilogue only issues ~700 cycles' worth of
@@ -125,6 +165,11 @@ __device__ __forceinline__ void strip_epilogue2(const EpiCtx& ec, NextTile next_
     }
     mbar_wait(ec.tfull0 + 8u * as, aphase);
     tc_fence_after();
+    if (kDiag && (ec.dbg & 8)) {
+      tc_fence_before();
+      mbar_arrive(ec.tempty0 + 8u * as);
+      continue;
+    }
     uint32_t acc[2][32];
     const uint32_t taddr = ec.tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * kC);
     tmem_ld32(taddr, acc[0]);
@@ -198,7 +243,7 @@ __device__ __forceinline__ void strip_epilogue2(const EpiCtx& ec, NextTile next_
   if ((ew & 3) == 0 && elect_one_sync()) tma_store_wait_all();
 }
 
-template <int GPT>
+template <int GPT, bool TS>
 __global__ void __launch_bounds__(kThreads, 1)
 conv3x3_strip_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CUtensorMap map_w,
                      const __grid_constant__ CUtensorMap map_out, const StripParams p) {
@@ -235,7 +280,7 @@ conv3x3_strip_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_co
     }
     fence_barrier_init();
   }
-  constexpr uint32_t kTmemCols = 2 * kC;
+  constexpr uint32_t kTmemCols = TS ? 512 : 2 * kC;
   if (warp == 1) tmem_alloc(smem_u32(s_tmem), kTmemCols);
   tc_fence_before();
   __syncthreads();
@@ -249,19 +294,152 @@ conv3x3_strip_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_co
       for (int tap = 0; tap < 9; ++tap)
         tma_load_2d(w_smem + tap * kWTapBytes, &map_w, wfull_bar, tap * p.w_kstride + p.w_k0, 0);
       uint32_t seq = 0;
-      for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
-        int n, w0, ra, rb;
-        decode_item(p, item, n, w0, ra, rb);
+      StripWalk walk(p);
+      int n, w0, ra, rb;
+      while (walk.next(p, n, w0, ra, rb)) {
+        // The ring holds ~4 strips of lookahead = ~3 us of work, about the DRAM latency under load: rows are prefetched
+        // into L2 kPF rows ahead of their load so the loads themselves only see L2 latency.
+        if (p.pf > 0)
+          for (int y = ra - 1; y < ra - 1 + p.pf && y <= rb; ++y) tma_prefetch_l2_5d(&map_in, p.c_off, w0 - 1, y, n, 0);
         for (int y = ra - 1; y <= rb; ++y, ++seq) {
           const int slot = seq % kNS;
           const uint32_t phase = (seq / kNS) & 1u;
+          if (p.pf > 0 && y + p.pf <= rb) tma_prefetch_l2_5d(&map_in, p.c_off, w0 - 1, y + p.pf, n, 0);
           mbar_wait(empty_bar(slot), phase ^ 1u);
           mbar_expect_tx(full_bar(slot), kStripTx);
           tma_load_5d(s_smem + slot * kStripBytes, &map_in, full_bar(slot), p.c_off, w0 - 1, y, n, 0);
         }
       }
     }
-  } else if (warp == 1 || warp == 10) {
+  } else if (TS && warp == 1) {
+    // ===================== MMA issuer, A operand from tensor memory =====================
+    // The SS form reads (128 + 64) * 32 B of shared memory per 128x64x16 instruction = 48 cycles at 128 B/clk, and the nine
+    // taps re-read every strip nine times: 216 KB per tile, which made this kernel shared-memory bound (file header).  Here
+    // every input strip is copied to tensor memory ONCE per kx shift (tcgen05.cp.128x256b, 12 copies = 48 KB of reads per
+    // strip), a 4-slot ring of 96 columns, and the 36 MMAs of a tile read only their 2 KB weight slices from shared memory:
+    // 72 + 48 KB per tile instead of 216, and the instruction runs at the tensor rate (32 cycles).  tcgen05.cp and
+    // tcgen05.mma issued by one thread execute in issue order, so the ring needs no barriers of its own; a strip's
+    // shared-memory slot is handed back to the TMA producer by a commit right after its copies.
+    if (elect_one_sync()) {
+      constexpr uint32_t idesc = umma_idesc_bf16(kBlockM, kC);
+      mbar_wait(wfull_bar, 0);
+      tc_fence_after();
+      const uint64_t bdesc0 = umma_desc_sw128(w_smem);
+      const uint32_t a_tmem0 = tmem_base + kATmemCol0;
+      // copy cursor: walks the same (item, row) sequence as the TMA producer, `cseq` = strips staged so far
+      StripWalk cwalk(p);
+      int c_left = 0;
+      uint32_t cseq = 0;
+      auto copy_strip = [&]() {
+        const uint32_t slot = cseq % kNS;
+        mbar_wait(full_bar(slot), (cseq / kNS) & 1u);
+        tc_fence_after();
+        const uint32_t dst = a_tmem0 + (cseq % kATmemSlots) * kATmemSlotCols;
+        const uint64_t sd = umma_desc_sw128(s_smem + slot * kStripBytes);
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+          for (int k = 0; k < kC / 16; ++k)
+            if (!(kDiag && (p.dbg & 64)))
+            utccp_128x256b(dst + kx * (kC / 2) + k * 8, sd + (uint64_t)(kx * 8 + 2 * k));   // +8: one 128-byte pixel row
+        umma_commit(empty_bar(slot));
+        ++cseq;
+      };
+      auto strips_left = [&]() {                     // is there another strip in this CTA's sequence?
+        while (c_left == 0) {
+          int cn, cw0, cra, crb;
+          if (!cwalk.next(p, cn, cw0, cra, crb)) return false;
+          c_left = crb - cra + 2;
+        }
+        return true;
+      };
+      uint32_t seq0 = 0;
+      int iter = 0;
+      long long dg_t0 = 0, dg_wait = 0, dg_copy = 0, dg_mma = 0;
+      int dg_inter = 0, dg_block = 0;
+      unsigned long long dg_ns0 = 0;
+      if (kDiag) {
+        dg_t0 = clock64();
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dg_ns0));
+      }
+      StripWalk walk(p);
+      int n, w0, ra, rb;
+      while (walk.next(p, n, w0, ra, rb)) {
+        const int rows = rb - ra;
+        for (int j = 0; j < rows; ++j, ++iter) {
+          const uint32_t f = seq0 + j;                // first strip (ky = 0) of this tile
+          long long dg_c = 0;
+          if (kDiag) dg_c = clock64();
+          while (cseq < f + 3) {                      // (item starts; in steady state the strip was staged one tile ahead)
+            strips_left();
+            copy_strip();
+            --c_left;
+            if (kDiag) ++dg_block;
+          }
+          if (kDiag) dg_copy += clock64() - dg_c;
+          const int as = iter & 1;
+          long long dg_a = 0;
+          if (kDiag) dg_a = clock64();
+          mbar_wait(tempty_bar(as), ((iter >> 1) & 1) ^ 1u);
+          if (kDiag) dg_wait += clock64() - dg_a;
+          tc_fence_after();
+          const uint32_t tmem_d = tmem_base + as * kC;
+          // Stage the next strip (its ring slot held strip f - 1, whose last reader was the previous tile) WHILE this tile's
+          // MMAs run: scripts/micro/umma_ts.cu measures 1332 cycles per tile with one copy after every third MMA against
+          // 1803 with the twelve copies issued back to back (36 MMAs alone: 1152).  If the strip has not landed yet the
+          // MMAs go first and the copies follow.
+          const bool more = cseq < f + 4 && strips_left();
+          const uint32_t cslot = cseq % kNS;
+          const bool inter = more && mbar_try_wait(full_bar(cslot), (cseq / kNS) & 1u);
+          const uint32_t cdst = a_tmem0 + (cseq % kATmemSlots) * kATmemSlotCols;
+          const uint64_t csd = umma_desc_sw128(s_smem + cslot * kStripBytes);
+          if (inter) tc_fence_after();
+          long long dg_m = 0;
+          if (kDiag) { dg_m = clock64(); dg_inter += inter; }
+#pragma unroll
+          for (int ky = 0; ky < 3; ++ky) {
+            const uint32_t a_strip = a_tmem0 + ((f + ky) % kATmemSlots) * kATmemSlotCols;
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+              const uint64_t bdesc = bdesc0 + (uint64_t)((ky * 3 + kx) * (kWTapBytes >> 4));
+#pragma unroll
+              for (int k = 0; k < kC / 16; ++k) {
+                if (!(kDiag && (p.dbg & 4)))
+                  umma_ts_bf16(tmem_d, a_strip + kx * (kC / 2) + k * 8, bdesc + (uint64_t)(2 * k), idesc, (ky | kx | k) != 0 ? 1u : 0u);
+                const int m = (ky * 3 + kx) * 4 + k;
+                if (m % 3 == 2 && inter && !(kDiag && (p.dbg & 64))) {
+                  const int c = m / 3, ckx = c >> 2, ck = c & 3;
+                  utccp_128x256b(cdst + ckx * (kC / 2) + ck * 8, csd + (uint64_t)(ckx * 8 + 2 * ck));
+                }
+              }
+            }
+          }
+          umma_commit(tfull_bar(as));
+          if (kDiag) { dg_mma += clock64() - dg_m; dg_c = clock64(); }
+          if (inter) {
+            umma_commit(empty_bar(cslot));
+            ++cseq;
+            --c_left;
+          } else if (more) {
+            copy_strip();
+            --c_left;
+            if (kDiag) ++dg_block;
+          }
+          if (kDiag) dg_copy += clock64() - dg_c;
+        }
+        seq0 += rows + 2;
+      }
+      if (kDiag && (p.dbg & 128) && (blockIdx.x == 0 || blockIdx.x == 77)) {
+        unsigned long long ns1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns1));
+        const long long cyc = clock64() - dg_t0;
+        printf("strip TS issuer block %d: %d tiles, %lld cycles (%.0f / tile), waiting for tempty %lld, mma issue %lld, copies (blocking path) %lld, "
+               "interleaved %d blocking %d, %llu ns -> %.2f GHz\n", blockIdx.x,
+               iter, cyc, (double)cyc / iter, dg_wait, dg_mma, dg_copy, dg_inter, dg_block, ns1 - dg_ns0, (double)cyc / (double)(ns1 - dg_ns0));
+      }
+    }
+    __syncwarp();
+  } else if (!TS && (warp == 1 || warp == 10)) {
     // ===================== MMA issuers =====================
     // A 128x64x16 UMMA occupies the tensor core for only 32 cycles, less than one thread needs to issue the next
     // one (descriptor -> uniform-register traffic), so ONE issuer leaves the pipe ~60 % idle (ncu: 40 % active).
@@ -271,9 +449,9 @@ conv3x3_strip_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_co
     mbar_wait(wfull_bar, 0);
     uint32_t seq0 = 0;       // sequence number of the first strip (input row ra-1) of the current item
     int iter = 0;
-    for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
-      int n, w0, ra, rb;
-      decode_item(p, item, n, w0, ra, rb);
+    StripWalk walk(p);
+    int n, w0, ra, rb;
+    while (walk.next(p, n, w0, ra, rb)) {
       const int rows = rb - ra;
       for (int j = 0; j < rows; ++j, ++iter) {
         const int as = iter & 1;
@@ -329,20 +507,13 @@ conv3x3_strip_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_co
     ec.H = p.H; ec.W = p.W; ec.Cout = kC; ec.Wt = kTileW;
     ec.shuffle_cq = 0;
     ec.tempty_remote = 0;
-    ec.dbg = 0;
-    int item = blockIdx.x, j = 0, n = 0, w0 = 0, ra = 0, rb = 0;
-    bool have = false;
+    ec.dbg = kDiag ? p.dbg : 0;
+    StripWalk walk(p);
+    int j = 0, n = 0, w0 = 0, ra = 0, rb = 0;
     auto next = [&](int, EpiTile& t) {
-      while (true) {
-        if (!have) {
-          if (item >= p.total_items) return false;
-          decode_item(p, item, n, w0, ra, rb);
-          j = 0;
-          have = true;
-        }
-        if (ra + j < rb) break;
-        have = false;
-        item += gridDim.x;
+      while (ra + j >= rb) {
+        if (!walk.next(p, n, w0, ra, rb)) return false;
+        j = 0;
       }
       t.img = n;
       t.h0 = ra + j;
@@ -379,17 +550,7 @@ int fd_conv3x3_strip_launch(const void* src0, int C0, const void* src1, int C1, 
   p.N = N; p.H = H; p.W = W;
   p.tile_w = kTileW;
   p.wblocks = (W + p.tile_w - 1) / p.tile_w;
-  // rows per item: 16..64, chosen for the best last-wave fill (ties -> taller segments: fewer halo reloads)
-  int best_segs = 1;
-  double best_eff = -1.0;
-  for (int segs = (H + 63) / 64; segs <= (H + 15) / 16; ++segs) {
-    const long items = (long)N * p.wblocks * segs;
-    const double eff = (double)items / (double)(((items + sms - 1) / sms) * sms);
-    if (eff > best_eff + 1e-9) { best_eff = eff; best_segs = segs; }
-  }
-  p.seg_rows = (H + best_segs - 1) / best_segs;
-  p.segs = (H + p.seg_rows - 1) / p.seg_rows;
-  p.total_items = N * p.wblocks * p.segs;
+  p.total_rows = N * p.wblocks * H;
   p.base_offset_mode = base_offset_mode;
   p.w_kstride = cin;
   CUtensorMap mw, mo;
@@ -404,12 +565,27 @@ int fd_conv3x3_strip_launch(const void* src0, int C0, const void* src1, int C1, 
     const uint32_t box[2] = {64, 64};
     if (int e = make_tmap_bf16(&mw, wpacked, 2, dims, str, box)) return e;
   }
-  const int grid = p.total_items < sms ? p.total_items : sms;
+  const int grid = p.total_rows < sms ? p.total_rows : sms;
   static bool attr_set = false;
   if (!attr_set) {
-    FD_CUDA(cudaFuncSetAttribute(conv3x3_strip_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    FD_CUDA(cudaFuncSetAttribute(conv3x3_strip_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    FD_CUDA(cudaFuncSetAttribute(conv3x3_strip_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    FD_CUDA(cudaFuncSetAttribute(conv3x3_strip_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    FD_CUDA(cudaFuncSetAttribute(conv3x3_strip_kernel<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    FD_CUDA(cudaFuncSetAttribute(conv3x3_strip_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     attr_set = true;
+  }
+  // FD_STRIP_TS=1: A operand from tensor memory (see the TS issuer).  Measured equal to the shared-memory-operand variant on
+  // the layers it serves (64->64: 0.229 vs 0.227 ms, 128->64: 0.525 vs 0.536 ms at 8x440x1024): once the operand reads are gone
+  // the layer sits on its HBM traffic (922 MB = 0.141 ms at the copy peak, 0.175 ms measured with MMAs and copies
+  // disabled), so the default stays the long-tested SS variant.  Read per call so tests can exercise both.
+  const char* ets = getenv("FD_STRIP_TS");
+  const bool ts = ets != nullptr && atoi(ets) != 0 && base_offset_mode != 1;
+  {
+    const char* e = getenv("FD_STRIP_PF");           // L2 prefetch distance in rows; measured no gain (0.229 -> 0.231 ms), off
+    p.pf = e ? atoi(e) : 0;
+    static int dbg = -1;
+    if (dbg < 0) { const char* d = getenv("FD_CONV_DBG"); dbg = d ? atoi(d) : 0; }
+    p.dbg = dbg;
   }
   for (int pass = 0; pass < passes; ++pass) {
     const bool last = pass == passes - 1;
@@ -427,10 +603,13 @@ int fd_conv3x3_strip_launch(const void* src0, int C0, const void* src1, int C1, 
     // pass 0 adds the caller's residual (if any), pass 1 the partial sum of pass 0
     p.residual = static_cast<const __nv_bfloat16*>(pass > 0 ? out : residual);
     p.gn_stats = last ? gn_stats : nullptr;
-    if (p.gn_stats != nullptr)
-      conv3x3_strip_kernel<8><<<grid, kThreads, kSmemBytes, st>>>(mi, mw, mo, p);
-    else
-      conv3x3_strip_kernel<0><<<grid, kThreads, kSmemBytes, st>>>(mi, mw, mo, p);
+    if (p.gn_stats != nullptr) {
+      if (ts) conv3x3_strip_kernel<8, true><<<grid, kThreads, kSmemBytes, st>>>(mi, mw, mo, p);
+      else conv3x3_strip_kernel<8, false><<<grid, kThreads, kSmemBytes, st>>>(mi, mw, mo, p);
+    } else {
+      if (ts) conv3x3_strip_kernel<0, true><<<grid, kThreads, kSmemBytes, st>>>(mi, mw, mo, p);
+      else conv3x3_strip_kernel<0, false><<<grid, kThreads, kSmemBytes, st>>>(mi, mw, mo, p);
+    }
     FD_LAUNCH_CHECK();
   }
   return FD_OK;
