@@ -250,6 +250,20 @@ FD_API int fd_final_conv_bwd(const void* x, const float* w, const float* dout, v
 /* dgrad weights from the forward's packed weights: wd[ci][(T-1-tap)*Cout + co] = wpacked[co][tap*Cin + ci]
  * (for kind 1 use T = 1, Cin = 4*C).  The data gradient is then fd_conv_igemm(_ex) on dy with wd. */
 FD_API int fd_prep_weight_dgrad(const void* wpacked, void* wd, int Cout, int Cin, int taps, void* stream);
+/* Batched forms: ONE launch for all the layers of a model (a training step re-packs ~80 weight tensors; 230 launches of
+ * 5-13 us each otherwise).  `table` is a DEVICE array of n_layers records of 8 x int64:
+ *   fd_prep_weight_batch        {w (float*), packed (bf16*), 0, Cout, Cin, KH, KW, kind | standardize << 8}
+ *   fd_prep_weight_dgrad_batch  {wpacked, wd, 0, Cout, Cin, taps, 0, 0}
+ *   fd_prep_weight_bwd_batch    {g, w, dw, Cout, Cin, KH, KW, kind | standardize << 8}
+ * with the per-layer arguments of the single-layer functions; `blk_start` is a DEVICE int32[n_layers + 1] array of prefix sums
+ * of the layers' block counts (Cout blocks per layer; ceil(Cin/32) * ceil(Cout/32) * taps for the dgrad form) and
+ * total_blocks = blk_start[n_layers]. */
+FD_API int fd_prep_weight_batch(const long long* table, const int* blk_start, int n_layers, int total_blocks, float eps,
+                                void* stream);
+FD_API int fd_prep_weight_dgrad_batch(const long long* table, const int* blk_start, int n_layers, int total_blocks,
+                                      void* stream);
+FD_API int fd_prep_weight_bwd_batch(const long long* table, const int* blk_start, int n_layers, int total_blocks, float eps,
+                                    void* stream);
 /* fd_conv_wgrad result (fp32 packed [Cout][K]) -> parameter gradient dw (+=, torch layout), through the
  * weight-standardisation backward when standardize != 0 (arguments as fd_prep_weight). */
 FD_API int fd_prep_weight_bwd(const float* g, const float* w, float* dw, int Cout, int Cin, int KH, int KW, int kind,

@@ -73,6 +73,9 @@ SIGNATURES = {
     "fd_bias_grad": (c_int, [_P, _P, _L, _I, _P]),
     "fd_final_conv_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "fd_prep_weight_dgrad": (c_int, [_P, _P, _I, _I, _I, _P]),
+    "fd_prep_weight_batch": (c_int, [_P, _P, _I, _I, _F, _P]),
+    "fd_prep_weight_dgrad_batch": (c_int, [_P, _P, _I, _I, _P]),
+    "fd_prep_weight_bwd_batch": (c_int, [_P, _P, _I, _I, _F, _P]),
     "fd_prep_weight_bwd": (c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _P]),
     "fd_linear_bwd_w": (c_int, [_P, _L, _P, _L, _P, _P, _I, _I, _I, _I, _P]),
     "fd_linear_bwd_x": (c_int, [_P, _L, _P, _P, _L, _P, _L, _I, _I, _I, _I, _P]),

@@ -95,12 +95,10 @@ __global__ void __launch_bounds__(256) pack_input_kernel(const float* __restrict
 // weight standardisation (:106-114) + bf16 packing into the implicit-GEMM K order.  One block per
 // output channel; statistics in fp32 (biased variance), two passes like the reference's reduce.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) prep_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ packed,
-                                                          int Cout, int Cin, int KH, int KW, int kind, int standardize,
-                                                          float eps, int Kpacked) {
+__device__ __forceinline__ void prep_weight_body(const float* __restrict__ w, __nv_bfloat16* __restrict__ packed, int Cin,
+                                                 int KH, int KW, int kind, int standardize, float eps, int Kpacked, int o) {
   __shared__ float red[32];
   __shared__ float s_mean, s_rstd;
-  const int o = blockIdx.x;
   const int n = Cin * KH * KW;
   const float* wo = w + (long)o * n;
   float mean = 0.f, rstd = 1.f;
@@ -142,6 +140,27 @@ __global__ void __launch_bounds__(256) prep_weight_kernel(const float* __restric
     }
     po[k] = __float2bfloat16((wo[i] - mean) * rstd);
   }
+}
+
+__global__ void __launch_bounds__(256) prep_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ packed,
+                                                          int Cout, int Cin, int KH, int KW, int kind, int standardize,
+                                                          float eps, int Kpacked) {
+  prep_weight_body(w, packed, Cin, KH, KW, kind, standardize, eps, Kpacked, blockIdx.x);
+}
+
+// all layers in one launch: block -> (layer, output channel) through the prefix sums of the layers' block counts
+__global__ void __launch_bounds__(256) prep_weight_batch_kernel(const long long* __restrict__ table,
+                                                                const int* __restrict__ blk_start, int n_layers, float eps) {
+  int lo = 0, hi = n_layers;
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (blk_start[mid] <= (int)blockIdx.x) lo = mid; else hi = mid;
+  }
+  const long long* r = table + (long)lo * 8;
+  const int Cin = (int)r[4], KH = (int)r[5], KW = (int)r[6], kind = (int)(r[7] & 0xff), ws = (int)((r[7] >> 8) & 1);
+  const int Kp = kind == 2 ? KH * 64 : Cin * KH * KW;
+  prep_weight_body(reinterpret_cast<const float*>(r[0]), reinterpret_cast<__nv_bfloat16*>(r[1]), Cin, KH, KW, kind, ws, eps, Kp,
+                   (int)blockIdx.x - blk_start[lo]);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -479,6 +498,13 @@ int fd_prep_weight(const float* w, void* packed, int Cout, int Cin, int KH, int 
   const int Kp = kind == 2 ? KH * 64 : Cin * KH * KW;
   prep_weight_kernel<<<Cout, 256, 0, (cudaStream_t)stream>>>(w, static_cast<__nv_bfloat16*>(packed), Cout, Cin, KH, KW,
                                                              kind, standardize, eps, Kp);
+  FD_LAUNCH_CHECK();
+  return FD_OK;
+}
+
+int fd_prep_weight_batch(const long long* table, const int* blk_start, int n_layers, int total_blocks, float eps, void* stream) {
+  FD_REQUIRE(table && blk_start && n_layers > 0 && total_blocks > 0, "prep_weight_batch: bad argument");
+  prep_weight_batch_kernel<<<total_blocks, 256, 0, (cudaStream_t)stream>>>(table, blk_start, n_layers, eps);
   FD_LAUNCH_CHECK();
   return FD_OK;
 }

@@ -137,16 +137,30 @@ class Unet(UnetParams, TrainMixin):
         if self._convs is None:
             self._build_conv_table()
         st = _lib.stream()
+        recs, blocks, dev = [], [0], None
         for pc in self._convs.values():
             w = pc.src.weight
             _lib.require_cuda(w)
+            dev = w.device
             cout, cin, kh, kw = w.shape
             kp = 7 * 64 if pc.kind == 2 else cin * kh * kw
             if pc.w is None or pc.w.device != w.device:
                 pc.w = torch.empty(cout, kp, device=w.device, dtype=BF16)
-            _lib.check(lib.fd_prep_weight(_lib.ptr(w.detach().float().contiguous()), _lib.ptr(pc.w), cout, cin, kh, kw,
-                                          pc.kind, int(pc.ws), self.WS_EPS, st))
+            if w.dtype == torch.float32 and w.is_contiguous():
+                # batched below: one launch standardises + packs every layer (a training step re-packs all ~80 of them)
+                recs.append([w.data_ptr(), pc.w.data_ptr(), 0, cout, cin, kh, kw, pc.kind | (int(pc.ws) << 8)])
+                blocks.append(blocks[-1] + cout)
+            else:
+                _lib.check(lib.fd_prep_weight(_lib.ptr(w.detach().float().contiguous()), _lib.ptr(pc.w), cout, cin, kh, kw,
+                                              pc.kind, int(pc.ws), self.WS_EPS, st))
             pc.bias = pc.src.bias.detach().float().contiguous() if pc.src.bias is not None else None
+        if recs:
+            key = tuple(tuple(r) for r in recs)
+            cur = getattr(self, "_prep_table", None)
+            if cur is None or cur[0] != key or cur[1].device != dev:
+                cur = (key, torch.tensor(recs, dtype=torch.int64).to(dev), torch.tensor(blocks, dtype=torch.int32).to(dev))
+                self._prep_table = cur
+            _lib.check(lib.fd_prep_weight_batch(_lib.ptr(cur[1]), _lib.ptr(cur[2]), len(recs), blocks[-1], self.WS_EPS, st))
         ws, bs, off = [], [], 0
         self._tproj_off = {}
         for name, rb in self._resblocks:

@@ -30,6 +30,16 @@ Tensor = torch.Tensor
 BF16 = torch.bfloat16
 
 
+def _batch_table(owner, attr: str, recs, blocks, dev):
+    """Device copies of a batched-prep table (8 x int64 per layer) and its block prefix sums, cached on `owner`."""
+    key = tuple(tuple(r) for r in recs)
+    cur = getattr(owner, attr, None)
+    if cur is None or cur[0] != key or cur[1].device != dev:
+        cur = (key, torch.tensor(recs, dtype=torch.int64).to(dev), torch.tensor(blocks, dtype=torch.int32).to(dev))
+        setattr(owner, attr, cur)
+    return cur[1], cur[2]
+
+
 class GradBuffer:
     """One flat fp32 buffer with a view per parameter (in ``module.parameters()`` order)."""
 
@@ -113,6 +123,7 @@ class TrainMixin:
         if getattr(self, "_dgrad_versions", None) == self._prepared_versions:
             return
         lib, st = self._lib, _lib.stream()
+        recs, blocks = [], [0]
         for name, pc in self._convs.items():
             if pc.kind == 2 or name.endswith((".to_kv", ".to_q")):
                 continue
@@ -123,8 +134,41 @@ class TrainMixin:
             if wd is None or wd.device != pc.w.device:
                 wd = torch.empty(cin, taps * cout, device=pc.w.device, dtype=BF16)
                 pc.wd = wd
-            _lib.check(lib.fd_prep_weight_dgrad(_lib.ptr(pc.w), _lib.ptr(wd), cout, cin, taps, st))
+            recs.append([pc.w.data_ptr(), wd.data_ptr(), 0, cout, cin, taps, 0, 0])
+            blocks.append(blocks[-1] + ((cin + 31) // 32) * ((cout + 31) // 32) * taps)
+        # one launch for all layers (fd_prep_weight_dgrad_batch); the table is rebuilt only when a buffer moved
+        table, blk = _batch_table(self, "_dgrad_table", recs, blocks, next(iter(self._convs.values())).w.device)
+        _lib.check(lib.fd_prep_weight_dgrad_batch(_lib.ptr(table), _lib.ptr(blk), len(recs), blocks[-1], st))
         self._dgrad_versions = self._prepared_versions
+
+    def _wgrad_workspace(self):
+        """Flat fp32 buffer holding the packed weight gradient of every convolution (``fd_conv_wgrad`` accumulates into
+        it) and the table for the single ``fd_prep_weight_bwd_batch`` launch that unpacks all of them at the end of the
+        backward (78 zero-fills + 74 unpack launches per step otherwise)."""
+        gb = self._gb
+        convs = [(n, pc) for n, pc in self._convs.items() if id(getattr(pc.src, "weight", None)) in gb.by_id]
+        key = (gb.flat.data_ptr(),) + tuple(pc.src.weight.data_ptr() for _, pc in convs)
+        ws = getattr(self, "_gw_ws", None)
+        if ws is not None and ws["key"] == key:
+            return ws
+        offs, off = [], 0
+        for _, pc in convs:
+            offs.append(off)
+            off += (pc.w.numel() + 3) // 4 * 4
+        dev = gb.flat.device
+        flat = torch.zeros(off, device=dev, dtype=torch.float32)
+        views, recs, blocks = {}, [], [0]
+        for (name, pc), o in zip(convs, offs):
+            v = flat[o:o + pc.w.numel()].view(pc.w.shape)
+            views[name] = v
+            wt = pc.src.weight
+            recs.append([v.data_ptr(), wt.data_ptr(), gb.of(wt).data_ptr(), wt.shape[0], wt.shape[1], wt.shape[2], wt.shape[3],
+                         pc.kind | (int(pc.ws) << 8)])
+            blocks.append(blocks[-1] + wt.shape[0])
+        ws = {"key": key, "flat": flat, "views": views, "n": len(recs), "blocks": blocks[-1],
+              "table": torch.tensor(recs, dtype=torch.int64).to(dev), "blk": torch.tensor(blocks, dtype=torch.int32).to(dev)}
+        self._gw_ws = ws
+        return ws
 
     # ------------------------------------------------------------------ recorded ops
     def _t_conv(self, tape: Tape, name: str, src0: Tensor, src1: Optional[Tensor] = None,
@@ -143,12 +187,11 @@ class TrainMixin:
             mod = pc.src
             if mod.bias is not None and stats is None:      # with statistics the GroupNorm backward delivers it
                 _lib.check(lib.fd_bias_grad(_lib.ptr(dy), _lib.ptr(gb.of(mod.bias)), n * h * w, cout, st))
-            gw = torch.zeros(pc.w.shape, device=dy.device, dtype=torch.float32)
+            # packed weight gradient into this conv's slice of the workspace (zeroed at the start of the backward); the
+            # unpacking + weight-standardisation backward of ALL convs is one launch at the end (forward_train.backward)
+            gw = self._gw_ws["views"][name]
             _lib.check(lib.fd_conv_wgrad(_lib.ptr(src0), c0, _lib.ptr(src1), c1, _lib.ptr(dy), _lib.ptr(gw), n, h, w, cout,
                                          pc.kh, pc.kw, pc.pad[0], pc.pad[1], pc.mode, st))
-            wt = mod.weight
-            _lib.check(lib.fd_prep_weight_bwd(_lib.ptr(gw), _lib.ptr(wt), _lib.ptr(gb.of(wt)), wt.shape[0], wt.shape[1],
-                                              wt.shape[2], wt.shape[3], pc.kind, int(pc.ws), self.WS_EPS, st))
             if not need_dgrad:
                 return
             if pc.mode == 1:
@@ -395,7 +438,11 @@ class TrainMixin:
                                              _lib.ptr(gb.of(fc.weight)), _lib.ptr(gb.of(fc.bias)), B, H * W, self.dim,
                                              self.out_dim, st))
             tape.g[id(h_last)] = dh
+            ws = self._wgrad_workspace()
+            ws["flat"].zero_()
             tape.run()
+            _lib.check(lib.fd_prep_weight_bwd_batch(_lib.ptr(ws["table"]), _lib.ptr(ws["blk"]), ws["n"], ws["blocks"],
+                                                    self.WS_EPS, st))
 
         if ph or pw:
             out = out[:, :, pad[2]:pad[2] + H0, pad[0]:pad[0] + W0].contiguous()

@@ -17,7 +17,12 @@ algo = FlowDiffuser(compose(["algorithm.target=flow", "algorithm.sampling_timest
 cond = (2 * synthetic_frames(B, H, W, 0) - 1).cuda()
 x = torch.randn(B, 2, H, W, device="cuda")
 t = torch.full((B,), 999, device="cuda", dtype=torch.long)
-for i in range(int(os.environ.get("FORWARDS", 2))):
+n_fwd = int(os.environ.get("FORWARDS", 2))
+for i in range(n_fwd):
+    if i == n_fwd - 1:
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()        # ncu --profile-from-start off: only the last (warm) forward is captured
     out = algo.unet(x, cond, t)
 torch.cuda.synchronize()
+torch.cuda.profiler.stop()
 print("ok", float(out.abs().mean()))
