@@ -27,6 +27,7 @@ sys.path.insert(0, ROOT)
 H, W, BATCH, DDIM_STEPS, TIMESTEPS = 436, 1024, 8, 50, 1000
 CONV_GF_PER_SAMPLE = 1590.3      # algorithmic conv GFLOP per UNet forward at 440x1024
 FWD_GF_PER_SAMPLE = 1635.28      # whole forward (conv + attention matmuls)
+CONV_DRAM_BYTES_PER_FORWARD = 38.411e9   # measured DRAM traffic of the conv launches of one batch-8 forward (profiles/r1_forward_traffic_v5.txt)
 CONFIG = {"workload": "flow_diffuser DDIM-50 sampling, Sintel-shaped synthetic 436x1024 (UNet runs on 440x1024), "
                       "target=flow, batch 8 per GPU, random-init weights seed 0",
           "batch_per_gpu": BATCH, "ddim_steps": DDIM_STEPS, "timesteps": TIMESTEPS, "parallelism": "batch-sharded replicas",
@@ -240,7 +241,9 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         "clocks": clk,
         "roofline": {"bound": "tensor", "kernel": "conv_igemm_kernel (tcgen05 implicit GEMM, all %d conv launches of one forward)" % conv_launches,
                      "achieved": conv_tf, "peak": peaks["tf_sustained"], "unit": "TFLOP/s", "frac": conv_tf / peaks["tf_sustained"],
-                     "traffic": None, "peak_source": peaks["src"] + " (sustained: the kernel is timed inside a long step)",
+                     "traffic": CONV_DRAM_BYTES_PER_FORWARD, "traffic_source": "profiles/r1_forward_traffic_v5.txt: ncu dram__bytes_read.sum + "
+                     "dram__bytes_write.sum summed over the conv launches of ONE forward at this batch (same unit as `achieved`: one "
+                     "forward's conv launches); algorithmic FLOPs, not bytes, bound these kernels", "peak_source": peaks["src"] + " (sustained: the kernel is timed inside a long step)",
                      "conv_share_of_forward": conv_s / fwd_s, "forward_ms": fwd_s * 1e3,
                      "whole_step_tflops": FWD_GF_PER_SAMPLE * DDIM_STEPS * 1e9 * value / 1e12},
     }
