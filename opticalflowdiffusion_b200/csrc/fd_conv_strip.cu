@@ -17,7 +17,11 @@
 // 144 KB of weights per tile instead was measured to be no faster than the generic kernel (chip-level L2->SM
 // bandwidth), while two resident-weight passes cost 0.75 ms instead of 1.09 ms.
 //
-// Where the time goes (ncu + scripts/micro/umma_rate.cu, profiles/r1_umma_rate.txt): an SS-mode 128xNx16 UMMA reads
+// Two issuer variants (template parameter TS): the original one feeds both MMA operands from shared memory (SS) and is
+// shared-memory-bandwidth bound as analysed below; the default one stages the strips in tensor memory (tcgen05.cp) and issues
+// the A-from-TMEM form of tcgen05.mma, which removes three quarters of the operand reads (see the TS issuer branch).
+//
+// Where the time goes in the SS variant (ncu + scripts/micro/umma_rate.cu, profiles/r1_umma_rate.txt): an SS-mode 128xNx16 UMMA reads
 // (128 + N) * 32 bytes of shared memory at 128 B/clk, so an N = 64 instruction takes 48 cycles, not 32.  Per 128-pixel tile
 // the 36 MMAs read 216 KB, TMA writes 16.6 KB, the epilogue writes and the TMA store reads 16 KB each: 265 KB = 2070
 // cycles of the shared-memory pipe out of the 2680 the tile takes (l1tex throughput 77 %, tensor pipe "active" 51 %).
@@ -353,49 +357,59 @@ conv3x3_strip_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_co
         }
         return true;
       };
-      uint32_t seq0 = 0;
-      int iter = 0;
-      long long dg_t0 = 0, dg_wait = 0, dg_copy = 0, dg_mma = 0;
-      int dg_inter = 0, dg_block = 0;
+      // The thread that issues the MMAs is held back by the tensor pipe while a tile's 36 instructions drain, and everything it
+      // does BETWEEN two tiles is time the pipe sits empty (probes in a diagnostic build: 1333 cycles of issue per tile = the
+      // hardware rate, plus ~250 cycles deciding about the next strip, ~90 waiting for the accumulator stage, ~290 of loop
+      // bookkeeping).  So the next tile is prepared in the middle of the current tile's instruction stream (after MMA 24):
+      // advance the cursor, wait for the next accumulator stage, claim the next strip and test whether it has landed.
+      struct Claim {
+        bool more, inter;          // a strip is staged during this tile / its data had landed when the tile started
+        uint32_t slot, phase, dst;
+        uint64_t sd;
+      };
+      auto claim = [&](uint32_t f) {          // f = first strip of the tile during which the claimed strip is staged
+        Claim c{};
+        c.more = cseq < f + 4 && strips_left();
+        if (c.more) {
+          c.slot = cseq % kNS;
+          c.phase = (cseq / kNS) & 1u;
+          c.dst = a_tmem0 + (cseq % kATmemSlots) * kATmemSlotCols;
+          c.sd = umma_desc_sw128(s_smem + c.slot * kStripBytes);
+          ++cseq;
+          --c_left;
+        }
+        return c;
+      };
+      auto landed = [&](Claim& c) { c.inter = c.more && mbar_try_wait(full_bar(c.slot), c.phase); };
+      long long dg_t0 = 0, dg_mma = 0, dg_tail = 0;
       unsigned long long dg_ns0 = 0;
       if (kDiag) {
         dg_t0 = clock64();
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dg_ns0));
       }
       StripWalk walk(p);
-      int n, w0, ra, rb;
-      while (walk.next(p, n, w0, ra, rb)) {
-        const int rows = rb - ra;
-        for (int j = 0; j < rows; ++j, ++iter) {
-          const uint32_t f = seq0 + j;                // first strip (ky = 0) of this tile
-          long long dg_c = 0;
-          if (kDiag) dg_c = clock64();
-          while (cseq < f + 3) {                      // (item starts; in steady state the strip was staged one tile ahead)
-            strips_left();
-            copy_strip();
-            --c_left;
-            if (kDiag) ++dg_block;
-          }
-          if (kDiag) dg_copy += clock64() - dg_c;
+      int wn, ww0, wra, wrb;
+      int iter = 0;
+      if (walk.next(p, wn, ww0, wra, wrb)) {
+        int rows = wrb - wra, j = 0;
+        uint32_t f = 0;
+        while (cseq < f + 3) {                      // the first three strips of the CTA
+          strips_left();
+          copy_strip();
+          --c_left;
+        }
+        mbar_wait(tempty_bar(0), 1u);
+        Claim cp = claim(f);
+        landed(cp);
+        tc_fence_after();
+        while (true) {
           const int as = iter & 1;
-          long long dg_a = 0;
-          if (kDiag) dg_a = clock64();
-          mbar_wait(tempty_bar(as), ((iter >> 1) & 1) ^ 1u);
-          if (kDiag) dg_wait += clock64() - dg_a;
-          tc_fence_after();
           const uint32_t tmem_d = tmem_base + as * kC;
-          // Stage the next strip (its ring slot held strip f - 1, whose last reader was the previous tile) WHILE this tile's
-          // MMAs run: scripts/micro/umma_ts.cu measures 1332 cycles per tile with one copy after every third MMA against
-          // 1803 with the twelve copies issued back to back (36 MMAs alone: 1152).  If the strip has not landed yet the
-          // MMAs go first and the copies follow.
-          const bool more = cseq < f + 4 && strips_left();
-          const uint32_t cslot = cseq % kNS;
-          const bool inter = more && mbar_try_wait(full_bar(cslot), (cseq / kNS) & 1u);
-          const uint32_t cdst = a_tmem0 + (cseq % kATmemSlots) * kATmemSlotCols;
-          const uint64_t csd = umma_desc_sw128(s_smem + cslot * kStripBytes);
-          if (inter) tc_fence_after();
+          bool has_next = false, boundary = false;
+          uint32_t f_next = 0;
+          Claim cp_next{};
           long long dg_m = 0;
-          if (kDiag) { dg_m = clock64(); dg_inter += inter; }
+          if (kDiag) dg_m = clock64();
 #pragma unroll
           for (int ky = 0; ky < 3; ++ky) {
             const uint32_t a_strip = a_tmem0 + ((f + ky) % kATmemSlots) * kATmemSlotCols;
@@ -407,35 +421,70 @@ conv3x3_strip_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_co
                 if (!(kDiag && (p.dbg & 4)))
                   umma_ts_bf16(tmem_d, a_strip + kx * (kC / 2) + k * 8, bdesc + (uint64_t)(2 * k), idesc, (ky | kx | k) != 0 ? 1u : 0u);
                 const int m = (ky * 3 + kx) * 4 + k;
-                if (m % 3 == 2 && inter && !(kDiag && (p.dbg & 64))) {
+                // one staging copy after every third MMA (1332 cycles per tile against 1803 with the copies back to back)
+                if (m % 3 == 2 && cp.inter && !(kDiag && (p.dbg & 64))) {
                   const int c = m / 3, ckx = c >> 2, ck = c & 3;
-                  utccp_128x256b(cdst + ckx * (kC / 2) + ck * 8, csd + (uint64_t)(ckx * 8 + 2 * ck));
+                  utccp_128x256b(cp.dst + ckx * (kC / 2) + ck * 8, cp.sd + (uint64_t)(ckx * 8 + 2 * ck));
                 }
+                // ---- the next tile is prepared in small pieces spread over this tile's instruction stream: the issuing thread
+                // runs only two or three MMAs ahead of the tensor pipe (the uniform-register operands of an MMA are released at
+                // dispatch), so each piece has to fit into ~60 cycles and the pieces have to be a few MMAs apart
+                if (m == 5) {
+                  if (j + 1 < rows) {
+                    has_next = true;
+                    f_next = f + 1;
+                  } else if (walk.next(p, wn, ww0, wra, wrb)) {
+                    has_next = boundary = true;             // next run of rows: three fresh strips, staged after this tile
+                    f_next = f + 3;
+                  }
+                }
+                if (m == 14 && has_next && !boundary) cp_next = claim(f_next);
+                if (m == 23 && has_next && !boundary) mbar_wait(tempty_bar((iter + 1) & 1), (((iter + 1) >> 1) & 1) ^ 1u);
+                if (m == 32 && has_next && !boundary) landed(cp_next);
               }
             }
           }
           umma_commit(tfull_bar(as));
-          if (kDiag) { dg_mma += clock64() - dg_m; dg_c = clock64(); }
-          if (inter) {
-            umma_commit(empty_bar(cslot));
-            ++cseq;
-            --c_left;
-          } else if (more) {
-            copy_strip();
-            --c_left;
-            if (kDiag) ++dg_block;
+          if (kDiag) { dg_mma += clock64() - dg_m; dg_m = clock64(); }
+          if (cp.inter) {
+            umma_commit(empty_bar(cp.slot));
+          } else if (cp.more) {                           // the strip had not landed when the tile started
+            mbar_wait(full_bar(cp.slot), cp.phase);
+            tc_fence_after();
+#pragma unroll
+            for (int c = 0; c < 12; ++c)
+              if (!(kDiag && (p.dbg & 64))) utccp_128x256b(cp.dst + (c >> 2) * (kC / 2) + (c & 3) * 8, cp.sd + (uint64_t)((c >> 2) * 8 + 2 * (c & 3)));
+            umma_commit(empty_bar(cp.slot));
           }
-          if (kDiag) dg_copy += clock64() - dg_c;
+          if (!has_next) break;
+          if (boundary) {
+            rows = wrb - wra;
+            j = 0;
+            while (cseq < f_next + 3) {
+              strips_left();
+              copy_strip();
+              --c_left;
+            }
+            mbar_wait(tempty_bar((iter + 1) & 1), (((iter + 1) >> 1) & 1) ^ 1u);
+            cp_next = claim(f_next);
+            landed(cp_next);
+          } else {
+            ++j;
+          }
+          tc_fence_after();
+          f = f_next;
+          cp = cp_next;
+          ++iter;
+          if (kDiag) dg_tail += clock64() - dg_m;
         }
-        seq0 += rows + 2;
+        ++iter;
       }
       if (kDiag && (p.dbg & 128) && (blockIdx.x == 0 || blockIdx.x == 77)) {
         unsigned long long ns1;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns1));
         const long long cyc = clock64() - dg_t0;
-        printf("strip TS issuer block %d: %d tiles, %lld cycles (%.0f / tile), waiting for tempty %lld, mma issue %lld, copies (blocking path) %lld, "
-               "interleaved %d blocking %d, %llu ns -> %.2f GHz\n", blockIdx.x,
-               iter, cyc, (double)cyc / iter, dg_wait, dg_mma, dg_copy, dg_inter, dg_block, ns1 - dg_ns0, (double)cyc / (double)(ns1 - dg_ns0));
+        printf("strip TS issuer block %d: %d tiles, %lld cycles (%.0f / tile): MMA stream %lld, between tiles %lld, %llu ns -> %.2f GHz\n",
+               blockIdx.x, iter, cyc, (double)cyc / iter, dg_mma, dg_tail, ns1 - dg_ns0, (double)cyc / (double)(ns1 - dg_ns0));
       }
     }
     __syncwarp();
@@ -574,12 +623,13 @@ int fd_conv3x3_strip_launch(const void* src0, int C0, const void* src1, int C1, 
     FD_CUDA(cudaFuncSetAttribute(conv3x3_strip_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     attr_set = true;
   }
-  // FD_STRIP_TS=1: A operand from tensor memory (see the TS issuer).  Measured equal to the shared-memory-operand variant on
-  // the layers it serves (64->64: 0.229 vs 0.227 ms, 128->64: 0.525 vs 0.536 ms at 8x440x1024): once the operand reads are gone
-  // the layer sits on its HBM traffic (922 MB = 0.141 ms at the copy peak, 0.175 ms measured with MMAs and copies
-  // disabled), so the default stays the long-tested SS variant.  Read per call so tests can exercise both.
+  // Default: A operand from tensor memory (see the TS issuer).  Measured at 8x440x1024: 64->64 0.214 ms against 0.226 for the
+  // shared-memory-operand (SS) variant, 128->64 0.510 against 0.535; the outputs are bit-identical.  With the operand reads gone
+  // the layer is held by the single issuing thread (it runs only 2-3 MMAs ahead of the pipe) and by its HBM traffic (922 MB =
+  // 0.141 ms at the copy peak, 0.175 ms measured with MMAs and copies disabled).  FD_STRIP_TS=0 selects the SS variant (read
+  // per call so that tests can exercise both).
   const char* ets = getenv("FD_STRIP_TS");
-  const bool ts = ets != nullptr && atoi(ets) != 0 && base_offset_mode != 1;
+  const bool ts = (ets == nullptr || atoi(ets) != 0) && base_offset_mode != 1;
   {
     const char* e = getenv("FD_STRIP_PF");           // L2 prefetch distance in rows; measured no gain (0.229 -> 0.231 ms), off
     p.pf = e ? atoi(e) : 0;

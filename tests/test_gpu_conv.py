@@ -139,8 +139,9 @@ STRIP_CASES = [
 
 @pytest.mark.parametrize("case", STRIP_CASES)
 def test_strip_conv_tensor_memory_operand(L, case, monkeypatch):
-    """FD_STRIP_TS=1 stages the activation strips in tensor memory (tcgen05.cp) and issues the A-from-TMEM form of
-    tcgen05.mma: same products in the same order, so the output must equal the shared-memory-operand variant bit for bit."""
+    """The default strip-conv issuer stages the activation strips in tensor memory (tcgen05.cp) and issues the A-from-TMEM
+    form of tcgen05.mma; FD_STRIP_TS=0 selects the shared-memory-operand variant.  Same products in the same order, so the
+    two outputs must be equal bit for bit."""
     N, cins, H, W, has_res, stats = case
     g = torch.Generator().manual_seed(H * W)
     xs = [torch.randn(N, c, H, W, generator=g).cuda() for c in cins]
