@@ -138,6 +138,8 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     torch.cuda.set_device(dev)
     lib = _lib.load(check_device=True)
     if world > 1:
+        # NCCL prints its version banner to stdout when NCCL_DEBUG is set on the box; stdout carries exactly one JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     cfg = compose(["algorithm.target=flow", f"algorithm.sampling_timesteps={DDIM_STEPS}",
                    f"algorithm.image_size=[{H},{W}]", "algorithm.return_all_timesteps=true",
