@@ -304,3 +304,69 @@ def test_adam_clip(L):
         L.check(lib.fd_adam_step(L.ptr(p), L.ptr(grad), L.ptr(m), L.ptr(v), n, 1e-3, 0.9, 0.999, 1e-8, 1e-2, step, L.ptr(ss),
                                  100.0, 1.0, L.stream()))
         assert torch.allclose(p, ref.detach(), rtol=1e-5, atol=1e-6), (p - ref.detach()).abs().max()
+
+
+def test_weight_prep_batched_equals_per_layer(L):
+    """fd_prep_weight_batch / _dgrad_batch / _bwd_batch (one launch over a device table of layers) against the per-layer
+    entry points: identical arithmetic per block, so the results must be bit-equal."""
+    lib = L.load()
+    g = torch.Generator().manual_seed(11)
+    layers = [  # Cout, Cin, KH, KW, kind, standardize
+        (64, 64, 3, 3, 0, 1), (128, 192, 3, 3, 0, 1), (64, 9, 7, 7, 2, 0), (128, 256, 1, 1, 1, 0), (384, 64, 1, 1, 0, 0),
+        (40, 72, 3, 3, 0, 1),
+    ]
+    ws = [torch.randn(co, ci, kh, kw, generator=g).cuda() for co, ci, kh, kw, _, _ in layers]
+
+    def kp(l):
+        co, ci, kh, kw, kind, _ = l
+        return kh * 64 if kind == 2 else ci * kh * kw
+
+    # --- forward packing
+    ref = [torch.empty(l[0], kp(l), device="cuda", dtype=torch.bfloat16) for l in layers]
+    out = [torch.zeros_like(r) for r in ref]
+    for l, w, r in zip(layers, ws, ref):
+        L.check(lib.fd_prep_weight(L.ptr(w), L.ptr(r), l[0], l[1], l[2], l[3], l[4], l[5], 1e-5, L.stream()))
+    recs = [[w.data_ptr(), o.data_ptr(), 0, l[0], l[1], l[2], l[3], l[4] | (l[5] << 8)] for l, w, o in zip(layers, ws, out)]
+    blk = [0]
+    for l in layers:
+        blk.append(blk[-1] + l[0])
+    table = torch.tensor(recs, dtype=torch.int64).cuda()
+    blk_t = torch.tensor(blk, dtype=torch.int32).cuda()
+    L.check(lib.fd_prep_weight_batch(L.ptr(table), L.ptr(blk_t), len(layers), blk[-1], 1e-5, L.stream()))
+    torch.cuda.synchronize()
+    for r, o in zip(ref, out):
+        assert torch.equal(r, o)
+
+    # --- dgrad weights (kinds 0 / 1 only)
+    dl = [(l, r) for l, r in zip(layers, ref) if l[4] != 2]
+    dref, dout, drecs, dblk = [], [], [], [0]
+    for l, packed in dl:
+        co, ci, kh, kw, kind, _ = l
+        taps = 1 if kind == 1 else kh * kw
+        cin = packed.shape[1] // taps
+        a = torch.empty(cin, taps * co, device="cuda", dtype=torch.bfloat16)
+        b = torch.zeros_like(a)
+        L.check(lib.fd_prep_weight_dgrad(L.ptr(packed), L.ptr(a), co, cin, taps, L.stream()))
+        dref.append(a)
+        dout.append(b)
+        drecs.append([packed.data_ptr(), b.data_ptr(), 0, co, cin, taps, 0, 0])
+        dblk.append(dblk[-1] + ((cin + 31) // 32) * ((co + 31) // 32) * taps)
+    dtable, dblk_t = torch.tensor(drecs, dtype=torch.int64).cuda(), torch.tensor(dblk, dtype=torch.int32).cuda()
+    L.check(lib.fd_prep_weight_dgrad_batch(L.ptr(dtable), L.ptr(dblk_t), len(drecs), dblk[-1], L.stream()))
+    torch.cuda.synchronize()
+    for a, b in zip(dref, dout):
+        assert torch.equal(a, b)
+
+    # --- wgrad unpacking + weight-standardisation backward
+    gs = [torch.randn(l[0], kp(l), generator=g).cuda() for l in layers]
+    bref = [torch.full_like(w, 0.25) for w in ws]
+    bout = [torch.full_like(w, 0.25) for w in ws]
+    for l, gp, w, d in zip(layers, gs, ws, bref):
+        L.check(lib.fd_prep_weight_bwd(L.ptr(gp), L.ptr(w), L.ptr(d), l[0], l[1], l[2], l[3], l[4], l[5], 1e-5, L.stream()))
+    brecs = [[gp.data_ptr(), w.data_ptr(), d.data_ptr(), l[0], l[1], l[2], l[3], l[4] | (l[5] << 8)]
+             for l, gp, w, d in zip(layers, gs, ws, bout)]
+    btable = torch.tensor(brecs, dtype=torch.int64).cuda()
+    L.check(lib.fd_prep_weight_bwd_batch(L.ptr(btable), L.ptr(blk_t), len(layers), blk[-1], 1e-5, L.stream()))
+    torch.cuda.synchronize()
+    for a, b in zip(bref, bout):
+        assert torch.equal(a, b)
