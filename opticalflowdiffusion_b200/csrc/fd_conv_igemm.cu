@@ -123,6 +123,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *s_tmem;
+  fd_grid_dependency_wait();      // the prologue above may overlap the previous kernel's tail (fd_launch_pdl)
 
   if (warp == 0 || warp == 10) {
     // ===================== TMA producers: warp 0 loads the activation tiles, warp 10 the weight tiles ==============
@@ -412,6 +413,7 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_
   cluster_sync_all();                                   // peers' barriers are initialised before anyone signals them
   tc_fence_after();
   const uint32_t tmem_base = *s_tmem;
+  fd_grid_dependency_wait();
 
   if (warp == 0 || warp == 10) {
     // ===================== TMA producers (both CTAs): warp 0 activation tiles, warp 10 weight half-tiles ==========
@@ -547,7 +549,7 @@ int launch_pair(const CUtensorMap& ma0, const CUtensorMap& ma1, const CUtensorMa
   }
   int grid = p.total_tiles < sms ? p.total_tiles : sms;
   grid &= ~1;
-  conv_igemm_pair_kernel<BLOCK_N, GPT><<<grid, kThreads, C::kSmemBytes, st>>>(ma0, ma1, mb, mo, p);
+  FD_CUDA(fd_launch_pdl(conv_igemm_pair_kernel<BLOCK_N, GPT>, dim3(grid), dim3(kThreads), C::kSmemBytes, st, ma0, ma1, mb, mo, p));
   FD_LAUNCH_CHECK();
   return FD_OK;
 }
@@ -582,7 +584,7 @@ int launch(const CUtensorMap& ma0, const CUtensorMap& ma1, const CUtensorMap& mb
     attr_set = true;
   }
   const int grid = p.total_tiles < sms ? p.total_tiles : sms;
-  conv_igemm_kernel<BLOCK_N, GPT, SH><<<grid, kThreads, C::kSmemBytes, st>>>(ma0, ma1, mb, mo, p);
+  FD_CUDA(fd_launch_pdl(conv_igemm_kernel<BLOCK_N, GPT, SH>, dim3(grid), dim3(kThreads), C::kSmemBytes, st, ma0, ma1, mb, mo, p));
   FD_LAUNCH_CHECK();
   return FD_OK;
 }

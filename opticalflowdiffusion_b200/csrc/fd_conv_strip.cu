@@ -290,6 +290,7 @@ conv3x3_strip_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_co
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *s_tmem;
+  fd_grid_dependency_wait();      // the prologue above may overlap the previous kernel's tail (fd_launch_pdl)
 
   if (warp == 0) {
     // ===================== TMA producer: weights once, then one strip per input row =====================
@@ -654,11 +655,11 @@ int fd_conv3x3_strip_launch(const void* src0, int C0, const void* src1, int C1, 
     p.residual = static_cast<const __nv_bfloat16*>(pass > 0 ? out : residual);
     p.gn_stats = last ? gn_stats : nullptr;
     if (p.gn_stats != nullptr) {
-      if (ts) conv3x3_strip_kernel<8, true><<<grid, kThreads, kSmemBytes, st>>>(mi, mw, mo, p);
-      else conv3x3_strip_kernel<8, false><<<grid, kThreads, kSmemBytes, st>>>(mi, mw, mo, p);
+      if (ts) FD_CUDA(fd_launch_pdl(conv3x3_strip_kernel<8, true>, dim3(grid), dim3(kThreads), kSmemBytes, st, mi, mw, mo, p));
+      else FD_CUDA(fd_launch_pdl(conv3x3_strip_kernel<8, false>, dim3(grid), dim3(kThreads), kSmemBytes, st, mi, mw, mo, p));
     } else {
-      if (ts) conv3x3_strip_kernel<0, true><<<grid, kThreads, kSmemBytes, st>>>(mi, mw, mo, p);
-      else conv3x3_strip_kernel<0, false><<<grid, kThreads, kSmemBytes, st>>>(mi, mw, mo, p);
+      if (ts) FD_CUDA(fd_launch_pdl(conv3x3_strip_kernel<0, true>, dim3(grid), dim3(kThreads), kSmemBytes, st, mi, mw, mo, p));
+      else FD_CUDA(fd_launch_pdl(conv3x3_strip_kernel<0, false>, dim3(grid), dim3(kThreads), kSmemBytes, st, mi, mw, mo, p));
     }
     FD_LAUNCH_CHECK();
   }
