@@ -50,17 +50,20 @@ struct GnCoef {
 __device__ __forceinline__ void gn_fold(const double* __restrict__ stats, const float* __restrict__ gamma,
                                         const float* __restrict__ beta, const float* __restrict__ scale_shift,
                                         long ss_stride, int n, int chunk, int C, long HW, float eps, GnCoef& k) {
+  // C % 64 == 0, so the channels-per-group count is a multiple of 8 and the thread's 8 channels share ONE group: the
+  // double-precision mean / rstd are computed once per thread.  (Per channel, i.e. 8 x 3 double divisions / square roots per
+  // thread, this prologue was ~20 us of every launch -- measured: 46 us for a 72 MB reduce at 46x96x512.)
   const int cpg = C >> 3;
   const double cnt = (double)HW * cpg;
+  const int g = (chunk * 8) / cpg;
+  const double s = stats[((long)n * 8 + g) * 2], ss = stats[((long)n * 8 + g) * 2 + 1];
+  const double mean = s / cnt;
+  double var = ss / cnt - mean * mean;
+  if (var < 0.0) var = 0.0;
+  const float rstd = (float)(1.0 / sqrt(var + (double)eps));
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int c = chunk * 8 + j;
-    const int g = c / cpg;
-    const double s = stats[((long)n * 8 + g) * 2], ss = stats[((long)n * 8 + g) * 2 + 1];
-    const double mean = s / cnt;
-    double var = ss / cnt - mean * mean;
-    if (var < 0.0) var = 0.0;
-    const float rstd = (float)(1.0 / sqrt(var + (double)eps));
     float ga = __ldg(gamma + c) * rstd;
     float be = __ldg(beta + c) - (float)mean * ga;
     if (scale_shift != nullptr) {
@@ -147,7 +150,7 @@ __global__ void __launch_bounds__(256, 2) gn_bwd_reduce_kernel(const __nv_bfloat
   }
 }
 
-// one block per sample, one thread per channel
+// one block per sample: blockDim = (C channels, 1024 / C slices of the reduce kernel's blocks)
 __global__ void __launch_bounds__(1024) gn_bwd_finalize_kernel(const float* __restrict__ partial, int nblocks,
                                                                const double* __restrict__ stats,
                                                                const float* __restrict__ gamma, const float* __restrict__ beta,
@@ -158,6 +161,7 @@ __global__ void __launch_bounds__(1024) gn_bwd_finalize_kernel(const float* __re
                                                                float eps) {
   __shared__ float s_g[8][2];
   __shared__ float s_c[1024][2];
+  __shared__ float s_p[1024 * 3];          // [blockDim.y slices][C][3]
   const int n = blockIdx.x, c = threadIdx.x;
   const int cpg = C >> 3;
   const int g = c / cpg;
@@ -168,45 +172,62 @@ __global__ void __launch_bounds__(1024) gn_bwd_finalize_kernel(const float* __re
   if (var < 0.0) var = 0.0;
   const float rstd = (float)(1.0 / sqrt(var + (double)eps));
   const float mean = (float)mean_d;
-  // fixed order over the reduce kernel's blocks; eight independent partial sums so that the (latency-bound) loads overlap:
-  // with one accumulator this tiny kernel took 42 us per launch, 2.8 % of a training step
-  constexpr int U = 8;
-  float a0[U], a1[U], a2[U];
+  // Sum of the reduce kernel's per-block partials in a FIXED order (run-to-run stable), spread over blockDim.y slices of
+  // blocks with four independent accumulators each: the loop is pure load latency (one thread per channel walking all ~150
+  // blocks took 42 us per launch).
+  float S0, S1, S2;
+  {
+    constexpr int U = 4;
+    float a0[U], a1[U], a2[U];
 #pragma unroll
-  for (int u = 0; u < U; ++u) a0[u] = a1[u] = a2[u] = 0.f;
-  const float* pn = partial + ((long)n * nblocks * C + c) * 3;
-  int b = 0;
-  for (; b + U <= nblocks; b += U) {
+    for (int u = 0; u < U; ++u) a0[u] = a1[u] = a2[u] = 0.f;
+    const float* pn = partial + ((long)n * nblocks * C + c) * 3;
+    const int S = blockDim.y, sl = threadIdx.y;
+    int bb = sl;
+    for (; bb + (U - 1) * S < nblocks; bb += U * S) {
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const float* pb = pn + (long)(b + u) * C * 3;
-      a0[u] += pb[0];
-      a1[u] += pb[1];
-      a2[u] += pb[2];
+      for (int u = 0; u < U; ++u) {
+        const float* pb = pn + (long)(bb + u * S) * C * 3;
+        a0[u] += pb[0];
+        a1[u] += pb[1];
+        a2[u] += pb[2];
+      }
+    }
+    for (; bb < nblocks; bb += S) {
+      const float* pb = pn + (long)bb * C * 3;
+      a0[0] += pb[0];
+      a1[0] += pb[1];
+      a2[0] += pb[2];
+    }
+    float* mine = s_p + ((long)sl * C + c) * 3;
+    mine[0] = (a0[0] + a0[1]) + (a0[2] + a0[3]);
+    mine[1] = (a1[0] + a1[1]) + (a1[2] + a1[3]);
+    mine[2] = (a2[0] + a2[1]) + (a2[2] + a2[3]);
+    __syncthreads();
+    S0 = S1 = S2 = 0.f;
+    for (int q = 0; q < S; ++q) {
+      const float* o = s_p + ((long)q * C + c) * 3;
+      S0 += o[0];
+      S1 += o[1];
+      S2 += o[2];
     }
   }
-  for (; b < nblocks; ++b) {
-    const float* pb = pn + (long)b * C * 3;
-    a0[0] += pb[0];
-    a1[0] += pb[1];
-    a2[0] += pb[2];
-  }
-  const float S0 = ((a0[0] + a0[1]) + (a0[2] + a0[3])) + ((a0[4] + a0[5]) + (a0[6] + a0[7]));
-  const float S1 = ((a1[0] + a1[1]) + (a1[2] + a1[3])) + ((a1[4] + a1[5]) + (a1[6] + a1[7]));
-  const float S2 = ((a2[0] + a2[1]) + (a2[2] + a2[3])) + ((a2[4] + a2[5]) + (a2[6] + a2[7]));
+  const bool lead = threadIdx.y == 0;                  // slice 0 holds the full sums and does the rest of the (tiny) work
   const float Sx = rstd * (S1 - mean * S0);            // sum dz * xh
   const float ga = gamma[c], be = beta[c];
   const float sc = scale_shift != nullptr ? scale_shift[(long)n * ss_stride + c] + 1.f : 1.f;
-  atomicAdd(dgamma + c, sc * Sx);
-  atomicAdd(dbeta + c, sc * S0);
-  if (dss != nullptr) {
-    dss[(long)n * ss_stride + c] = ga * Sx + be * S0;  // d scale = sum dz * y
-    dss[(long)n * ss_stride + C + c] = S0;             // d shift
+  if (lead) {
+    atomicAdd(dgamma + c, sc * Sx);
+    atomicAdd(dbeta + c, sc * S0);
+    if (dss != nullptr) {
+      dss[(long)n * ss_stride + c] = ga * Sx + be * S0;  // d scale = sum dz * y
+      dss[(long)n * ss_stride + C + c] = S0;             // d shift
+    }
+    s_c[c][0] = sc * ga * S0;                            // dxh summed over the pixels of this channel
+    s_c[c][1] = sc * ga * Sx;                            // ... dxh * xh
   }
-  s_c[c][0] = sc * ga * S0;                            // dxh summed over the pixels of this channel
-  s_c[c][1] = sc * ga * Sx;                            // ... dxh * xh
   __syncthreads();
-  if (c < 8) {                                         // group sums in channel order
+  if (lead && c < 8) {                                   // group sums in channel order
     float a = 0.f, b = 0.f;
     for (int i = 0; i < cpg; ++i) {
       a += s_c[c * cpg + i][0];
@@ -216,6 +237,7 @@ __global__ void __launch_bounds__(1024) gn_bwd_finalize_kernel(const float* __re
     s_g[c][1] = b;
   }
   __syncthreads();
+  if (!lead) return;
   const float m1 = s_g[g][0] / (float)cnt, m2 = s_g[g][1] / (float)cnt;
   const float Q = -rstd * rstd * m2;
   const float R = -rstd * m1 - Q * mean;
@@ -741,7 +763,7 @@ int fd_gn_silu_bwd(const void* h, const void* da, const double* gn_stats, const 
   gn_bwd_reduce_kernel<<<dim3((unsigned)bx, (unsigned)N), ppb * chunks, (size_t)ppb * C * 3 * sizeof(float), st>>>(
       hp, dp, gn_stats, gamma, beta, scale_shift, ss_stride, partial, (long)HW, C, eps);
   FD_LAUNCH_CHECK();
-  gn_bwd_finalize_kernel<<<N, C, 0, st>>>(partial, (int)bx, gn_stats, gamma, beta, scale_shift, ss_stride, dgamma, dbeta,
+  gn_bwd_finalize_kernel<<<N, dim3((unsigned)C, (unsigned)(1024 / C)), 0, st>>>(partial, (int)bx, gn_stats, gamma, beta, scale_shift, ss_stride, dgamma, dbeta,
                                           dscale_shift, dbias, coef, (long)HW, C, eps);
   FD_LAUNCH_CHECK();
   long bx2 = ((long)HW + ppb * 4 - 1) / (ppb * 4);

@@ -181,16 +181,18 @@ __global__ void __launch_bounds__(256) gn_silu_kernel(const __nv_bfloat16* __res
   const int ppb = blockDim.x / chunks;     // pixels per block pass
   const int cpg = C >> 3;                  // channels per group (8 groups)
   float a[8], b[8];
+  // C % 64 == 0: the thread's 8 channels share one group, so the double-precision mean / rstd are computed once per thread
+  // (8 x 3 double divisions / square roots per thread cost ~20 us of every launch)
   const double cnt = (double)HW * cpg;
+  const int g = (chunk * 8) / cpg;
+  const double s = stats[((long)n * 8 + g) * 2], ss = stats[((long)n * 8 + g) * 2 + 1];
+  const double mean = s / cnt;
+  double var = ss / cnt - mean * mean;
+  if (var < 0.0) var = 0.0;
+  const float rstd = (float)(1.0 / sqrt(var + (double)eps));
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int c = chunk * 8 + j;
-    const int g = c / cpg;
-    const double s = stats[((long)n * 8 + g) * 2], ss = stats[((long)n * 8 + g) * 2 + 1];
-    const double mean = s / cnt;
-    double var = ss / cnt - mean * mean;
-    if (var < 0.0) var = 0.0;
-    const float rstd = (float)(1.0 / sqrt(var + (double)eps));
     float ga = __ldg(gamma + c) * rstd;
     float be = __ldg(beta + c) - (float)mean * ga;
     if (scale_shift != nullptr) {
