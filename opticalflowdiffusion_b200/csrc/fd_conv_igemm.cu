@@ -443,8 +443,12 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_
             const uint32_t fb = (uint32_t)opaque32((int)full_bar(stage));
             const uint32_t dst = (uint32_t)opaque32((int)(a_smem + stage * kATileBytes));
             mbar_wait(empty_bar(stage), phase ^ 1u);
-            if (leader) mbar_expect_tx(fb, 2 * kATileBytes);                          // both CTAs' activation tiles
-            tma2_load_5d(dst, reinterpret_cast<const CUtensorMap*>(ma), fb, c0, c1, c2, c3, c4);
+            if (kDiag && (p.dbg & 1)) {
+              if (leader) mbar_arrive(fb);
+            } else {
+              if (leader) mbar_expect_tx(fb, 2 * kATileBytes);                        // both CTAs' activation tiles
+              tma2_load_5d(dst, reinterpret_cast<const CUtensorMap*>(ma), fb, c0, c1, c2, c3, c4);
+            }
             if (++stage == STAGES) { stage = 0; phase ^= 1u; }
             if (++chunk == cpt_) {
               chunk = 0;
@@ -462,8 +466,12 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_
             const uint32_t dst = (uint32_t)opaque32((int)(b_smem + stage * C::kBHalfBytes));
             const int ck = opaque32(k0), cn = opaque32(n0);
             mbar_wait(empty_bar(stage), phase ^ 1u);
-            if (leader) mbar_expect_tx(fb, 2 * C::kBHalfBytes);                      // both CTAs' halves of the weight tile
-            tma2_load_2d(dst, reinterpret_cast<const CUtensorMap*>(mb), fb, ck, cn);
+            if (kDiag && (p.dbg & 2)) {
+              if (leader) mbar_arrive(fb);
+            } else {
+              if (leader) mbar_expect_tx(fb, 2 * C::kBHalfBytes);                    // both CTAs' halves of the weight tile
+              tma2_load_2d(dst, reinterpret_cast<const CUtensorMap*>(mb), fb, ck, cn);
+            }
             if (++stage == STAGES) { stage = 0; phase ^= 1u; }
           }
         }
@@ -490,7 +498,8 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_
           tc_fence_after();
 #pragma unroll
           for (int k = 0; k < kBlockK / 16; ++k)
-            umma2_bf16(tmem_d, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+            if (!(kDiag && (p.dbg & 4)))
+              umma2_bf16(tmem_d, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
           const uint32_t cur_empty = empty_bar(stage);
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
           ad = opaque64(adesc0 + (uint64_t)(stage * (kATileBytes >> 4)));
