@@ -49,7 +49,9 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t rank)
 // GPT = GroupNorm groups covered by one N-tile (8 when Cout == BLOCK_N, 4 when Cout == 2*BLOCK_N, 0 = no statistics).
 // Must be called by warps 2..9 of the CTA (threads 64..319); next_tile(iter, tile) enumerates this CTA's tiles in
 // the same order as the MMA warp.
-template <int BLOCK_N, int GPT, int NBUF, class NextTile>
+// NACC = accumulator stages in TMEM (tile `iter` uses stage iter % NACC, columns [stage * BLOCK_N, +BLOCK_N); barriers tfull /
+// tempty of stage s at +8 s)
+template <int BLOCK_N, int GPT, int NBUF, int NACC = 2, class NextTile>
 __device__ __forceinline__ void conv_epilogue(const EpiCtx& ec, NextTile next_tile) {
   constexpr int NCHUNK = BLOCK_N / 32;                 // 32-column accumulator chunks per tile
   constexpr int CPW = NCHUNK / 2;                      // chunks per epilogue warp
@@ -111,8 +113,8 @@ __device__ __forceinline__ void conv_epilogue(const EpiCtx& ec, NextTile next_ti
 
     EpiTile tc;
     for (int iter = 0; next_tile(iter, tc); ++iter) {
-      const int as = iter & 1;
-      const uint32_t aphase = (iter >> 1) & 1;
+      const int as = iter % NACC;
+      const uint32_t aphase = (iter / NACC) & 1;
       const int n_tile = tc.n_tile, img = tc.img, h0 = tc.h0, w0 = tc.w0;
       const int h = h0 + rr, w = w0 + ww;
       const bool valid = (h < ec.H) && (w < ec.W);
@@ -122,7 +124,7 @@ __device__ __forceinline__ void conv_epilogue(const EpiCtx& ec, NextTile next_ti
         st_img = img;
         st_ntile = n_tile;
       }
-      float* bias_s = s_bias + as * BLOCK_N;
+      float* bias_s = s_bias + (as & 1) * BLOCK_N;
       for (int i = et; i < BLOCK_N; i += kEpiThreads) bias_s[i] = ec.bias ? __ldg(ec.bias + n0 + i) : 0.f;
       // (the slab barrier below also publishes the bias)
 

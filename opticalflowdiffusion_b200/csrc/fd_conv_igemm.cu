@@ -335,36 +335,42 @@ __device__ __forceinline__ void umma2_commit(uint32_t bar) {
                : "memory");
 }
 
-template <int BLOCK_N>
+// MT = M-tiles (128 pixels each) per CTA and K-block.  MT = 2 (N = 128 only): the pair works on FOUR M-tiles that share one
+// weight tile, so a K-block moves 32 KB of activations + 8 KB of weights per CTA for eight 64-cycle MMAs = 80 B/clk instead
+// of 96 -- the N = 128 tiles are bound by the L2 -> SM delivery rate (~74 B/clk/SM measured, profiles/r1_conv_diag_n128.txt).
+template <int BLOCK_N, int MT = 1>
 struct PairCfg {
   static constexpr int kBHalfBytes = (BLOCK_N / 2) * kBlockK * 2;   // this CTA's half of the weight tile's rows
-  static constexpr int kStageBytes = kATileBytes + kBHalfBytes;     // 32 / 24 KiB
-  static constexpr int kStages = BLOCK_N == 256 ? 5 : 7;
+  static constexpr int kStageBytes = MT * kATileBytes + kBHalfBytes;     // 32 / 24 / 40 KiB
+  static constexpr int kStages = MT == 2 ? 4 : (BLOCK_N == 256 ? 5 : 7);
   static constexpr int kStoreBufs = 2;
-  static constexpr int kTmemCols = 2 * BLOCK_N;
+  static constexpr int kAcc = 2 * MT;                               // accumulator stages
+  static constexpr int kTmemCols = kAcc * BLOCK_N;
   static constexpr int kTailBytes = 256 + 2 * BLOCK_N * 4 + kEpiWarps * 16 * 4 + 64;
   static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + kStoreBufs * kSlabBytes + kTailBytes;
+  static_assert(kTmemCols <= 512, "accumulators do not fit tensor memory");
 };
 
-template <int BLOCK_N, int GPT>
+template <int BLOCK_N, int GPT, int MT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
                        const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_out,
                        const ConvParams p) {
-  using C = PairCfg<BLOCK_N>;
+  using C = PairCfg<BLOCK_N, MT>;
   constexpr int STAGES = C::kStages;
   constexpr int NBUF = C::kStoreBufs;
+  constexpr int NACC = C::kAcc;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
   const uint32_t a_smem = base;
-  const uint32_t b_smem = base + STAGES * kATileBytes;
+  const uint32_t b_smem = base + STAGES * MT * kATileBytes;
   const uint32_t o_smem = base + STAGES * C::kStageBytes;
   const uint32_t bar_base = o_smem + NBUF * kSlabBytes;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
   auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
-  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 2 + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + NACC + s); };
   uint8_t* gtail = gbase + STAGES * C::kStageBytes + NBUF * kSlabBytes + 256;
   float* s_bias = reinterpret_cast<float*>(gtail);
   float* s_stats = reinterpret_cast<float*>(gtail + 2 * BLOCK_N * 4);
@@ -377,11 +383,11 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_
   const int cpt = p.chunks0 + p.chunks1;
   const int num_kb = p.taps * cpt;
   const int tiles_per_img = p.tiles_w * p.tiles_h;
-  const int super_tiles = p.total_tiles / 2;            // (pair of M-tiles) x N-tile; the host guarantees an even M count
+  const int super_tiles = p.total_tiles / (2 * MT);     // (2 MT M-tiles) x N-tile; the host guarantees the M count divides
 
-  auto decode = [&](int st, int& n_tile, int& img, int& h0, int& w0) {
+  auto decode = [&](int st, int m, int& n_tile, int& img, int& h0, int& w0) {
     n_tile = st % p.n_tiles;
-    const int m_tile = 2 * (st / p.n_tiles) + (int)rank;
+    const int m_tile = 2 * MT * (st / p.n_tiles) + (int)rank * MT + m;
     img = m_tile / tiles_per_img;
     const int rem = m_tile - img * tiles_per_img;
     h0 = (rem / p.tiles_w) * p.R;
@@ -397,7 +403,7 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_
       mbar_init(full_bar(s), 2);                       // the leader's two producer threads (expect_tx for both CTAs' bytes)
       mbar_init(empty_bar(s), 1);
     }
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < NACC; ++s) {
       mbar_init(tfull_bar(s), 1);
       mbar_init(tempty_bar(s), 2 * kEpiThreads);       // both CTAs' epilogues arrive on the leader's barrier
     }
@@ -428,26 +434,36 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_
         const int chunks0 = opaque32(p.chunks0), KW = opaque32(p.KW), cpt_ = opaque32(cpt);
         const uint64_t m0 = opaque64(reinterpret_cast<uint64_t>(&map_a0)), m1 = opaque64(reinterpret_cast<uint64_t>(&map_a1));
         for (int st = st0; st < super_tiles; st += ststep) {
-          int n_tile, img, h0, w0;
-          decode(st, n_tile, img, h0, w0);
-          const int bw = mode0 ? w0 - p.pad_w : 0, bh = mode0 ? h0 - p.pad_h : 0;
+          int n_tile, img[MT], h0[MT], w0[MT], bw[MT], bh[MT];
+#pragma unroll
+          for (int m = 0; m < MT; ++m) {
+            decode(st, m, n_tile, img[m], h0[m], w0[m]);
+            bw[m] = mode0 ? w0[m] - p.pad_w : 0;
+            bh[m] = mode0 ? h0[m] - p.pad_h : 0;
+          }
           int kx = 0, ky = 0, chunk = 0;
           for (int kb = 0; kb < nkb; ++kb) {
             const bool first = chunk < chunks0;
             const uint64_t ma = opaque64(first ? m0 : m1);
             const int c0 = opaque32((first ? chunk : chunk - chunks0) * kBlockK);
-            const int c1 = opaque32(bw + kx);
-            const int c2 = opaque32(mode0 ? bh + ky : w0);
-            const int c3 = opaque32(mode0 ? img : ky);
-            const int c4 = opaque32(mode0 ? 0 : h0);
+            int c1[MT], c2[MT], c3[MT], c4[MT];
+#pragma unroll
+            for (int m = 0; m < MT; ++m) {
+              c1[m] = opaque32(bw[m] + kx);
+              c2[m] = opaque32(mode0 ? bh[m] + ky : w0[m]);
+              c3[m] = opaque32(mode0 ? img[m] : ky);
+              c4[m] = opaque32(mode0 ? 0 : h0[m]);
+            }
             const uint32_t fb = (uint32_t)opaque32((int)full_bar(stage));
-            const uint32_t dst = (uint32_t)opaque32((int)(a_smem + stage * kATileBytes));
+            const uint32_t dst = (uint32_t)opaque32((int)(a_smem + stage * MT * kATileBytes));
             mbar_wait(empty_bar(stage), phase ^ 1u);
             if (kDiag && (p.dbg & 1)) {
               if (leader) mbar_arrive(fb);
             } else {
-              if (leader) mbar_expect_tx(fb, 2 * kATileBytes);                        // both CTAs' activation tiles
-              tma2_load_5d(dst, reinterpret_cast<const CUtensorMap*>(ma), fb, c0, c1, c2, c3, c4);
+              if (leader) mbar_expect_tx(fb, 2 * MT * kATileBytes);                   // both CTAs' activation tiles
+#pragma unroll
+              for (int m = 0; m < MT; ++m)
+                tma2_load_5d(dst + m * kATileBytes, reinterpret_cast<const CUtensorMap*>(ma), fb, c0, c1[m], c2[m], c3[m], c4[m]);
             }
             if (++stage == STAGES) { stage = 0; phase ^= 1u; }
             if (++chunk == cpt_) {
@@ -488,26 +504,33 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_
       bool waited = false;
       uint64_t ad = opaque64(adesc0), bd = opaque64(bdesc0);
       for (int st = pair; st < super_tiles; st += npairs, ++iter) {
-        const int as = iter & 1;
+        const int as0 = (iter & 1) * MT;                      // this super-tile's first accumulator stage
         const uint32_t aphase = (iter >> 1) & 1;
-        mbar_wait(tempty_bar(as), aphase ^ 1u);
+#pragma unroll
+        for (int m = 0; m < MT; ++m) mbar_wait(tempty_bar(as0 + m), aphase ^ 1u);
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + as * BLOCK_N;
+        const uint32_t tmem_d = tmem_base + as0 * BLOCK_N;
         for (int kb = 0; kb < num_kb; ++kb) {
           if (!waited) mbar_wait(full_bar(stage), phase);
           tc_fence_after();
 #pragma unroll
-          for (int k = 0; k < kBlockK / 16; ++k)
-            if (!(kDiag && (p.dbg & 4)))
-              umma2_bf16(tmem_d, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+          for (int m = 0; m < MT; ++m)
+#pragma unroll
+            for (int k = 0; k < kBlockK / 16; ++k)
+              if (!(kDiag && (p.dbg & 4)))
+                umma2_bf16(tmem_d + m * BLOCK_N, ad + (uint64_t)(m * (kATileBytes >> 4) + 2 * k), bd + (uint64_t)(2 * k), idesc,
+                           (kb | k) != 0 ? 1u : 0u);
           const uint32_t cur_empty = empty_bar(stage);
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
-          ad = opaque64(adesc0 + (uint64_t)(stage * (kATileBytes >> 4)));
+          ad = opaque64(adesc0 + (uint64_t)(stage * (MT * kATileBytes >> 4)));
           bd = opaque64(bdesc0 + (uint64_t)(stage * (C::kBHalfBytes >> 4)));
           waited = kb + 1 < num_kb;
           if (waited) mbar_wait(full_bar(stage), phase);
           umma2_commit(cur_empty);
-          if (kb == num_kb - 1) umma2_commit(tfull_bar(as));
+          if (kb == num_kb - 1) {
+#pragma unroll
+            for (int m = 0; m < MT; ++m) umma2_commit(tfull_bar(as0 + m));
+          }
         }
       }
     }
@@ -529,10 +552,10 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_
     ec.shuffle_cq = p.shuffle_cq;
     ec.tempty_remote = rank != 0;
     ec.dbg = kDiag ? p.dbg : 0;
-    conv_epilogue<BLOCK_N, GPT, NBUF>(ec, [&](int iter, EpiTile& t) {
-      const int st = pair + iter * npairs;
+    conv_epilogue<BLOCK_N, GPT, NBUF, NACC>(ec, [&](int iter, EpiTile& t) {
+      const int st = pair + (iter / MT) * npairs;
       if (st >= super_tiles) return false;
-      decode(st, t.n_tile, t.img, t.h0, t.w0);
+      decode(st, iter % MT, t.n_tile, t.img, t.h0, t.w0);
       return true;
     });
   }
@@ -546,19 +569,21 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_
   }
 }
 
-template <int BLOCK_N, int GPT>
+template <int BLOCK_N, int GPT, int MT = 1>
 int launch_pair(const CUtensorMap& ma0, const CUtensorMap& ma1, const CUtensorMap& mb, const CUtensorMap& mo, const ConvParams& p,
                 int sms, cudaStream_t st) {
-  using C = PairCfg<BLOCK_N>;
+  using C = PairCfg<BLOCK_N, MT>;
   static bool attr_set = false;
   if (!attr_set) {
-    FD_CUDA(cudaFuncSetAttribute(conv_igemm_pair_kernel<BLOCK_N, GPT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    FD_CUDA(cudaFuncSetAttribute(conv_igemm_pair_kernel<BLOCK_N, GPT, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  C::kSmemBytes));
     attr_set = true;
   }
-  int grid = p.total_tiles < sms ? p.total_tiles : sms;
+  const int units = p.total_tiles / MT;                  // CTA-sized work units
+  int grid = units < sms ? units : sms;
   grid &= ~1;
-  FD_CUDA(fd_launch_pdl(conv_igemm_pair_kernel<BLOCK_N, GPT>, dim3(grid), dim3(kThreads), C::kSmemBytes, st, ma0, ma1, mb, mo, p));
+  FD_CUDA(fd_launch_pdl(conv_igemm_pair_kernel<BLOCK_N, GPT, MT>, dim3(grid), dim3(kThreads), C::kSmemBytes, st, ma0, ma1, mb, mo,
+                        p));
   FD_LAUNCH_CHECK();
   return FD_OK;
 }
@@ -767,7 +792,12 @@ int fd_conv_igemm_ex(const void* src0, int C0, const void* src1, int C1, const v
     if (!stats) return launch_pair<256, 0>(ma0, ma1, mb, mo, p, sms, st);
     return p.n_tiles == 1 ? launch_pair<256, 8>(ma0, ma1, mb, mo, p, sms, st) : launch_pair<256, 4>(ma0, ma1, mb, mo, p, sms, st);
   }
-  if (use_pair) return stats ? launch_pair<128, 8>(ma0, ma1, mb, mo, p, sms, st) : launch_pair<128, 0>(ma0, ma1, mb, mo, p, sms, st);
+  if (use_pair) {
+    // four M-tiles per pair (two per CTA) when the M-tile count allows it: FD_CONV_PAIR=3 keeps two (A/B measurements)
+    const bool mt2 = pair_mode != 3 && ((long)p.N * p.tiles_w * p.tiles_h) % 4 == 0 && p.total_tiles >= 4;
+    if (mt2) return stats ? launch_pair<128, 8, 2>(ma0, ma1, mb, mo, p, sms, st) : launch_pair<128, 0, 2>(ma0, ma1, mb, mo, p, sms, st);
+    return stats ? launch_pair<128, 8>(ma0, ma1, mb, mo, p, sms, st) : launch_pair<128, 0>(ma0, ma1, mb, mo, p, sms, st);
+  }
   if (block_n == 256) {
     if (!stats) return launch<256, 0>(ma0, ma1, mb, mo, p, sms, st);
     return p.n_tiles == 1 ? launch<256, 8>(ma0, ma1, mb, mo, p, sms, st) : launch<256, 4>(ma0, ma1, mb, mo, p, sms, st);

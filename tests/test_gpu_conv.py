@@ -94,6 +94,10 @@ CASES = [
     (2, (128,), 128, 9, 30, (3, 3), (1, 1), True, True, False),         # ... N = 128, residual
     (2, (64,), 64, 30, 256, (3, 3), (1, 1), True, True, True),          # rolling-strip kernel with a residual (dgrad accumulation)
     (1, (64, 64), 64, 9, 130, (3, 3), (1, 1), False, True, False),      # two passes: caller's residual, then the partial sum
+    (2, (128,), 128, 32, 64, (3, 3), (1, 1), True, False, True),        # N = 128 CTA pairs, two M-tiles per CTA (32 M-tiles)
+    (2, (64, 64), 128, 16, 128, (3, 3), (1, 1), True, True, True),      # ... two sources + residual
+    (1, (128,), 128, 24, 64, (3, 3), (1, 1), True, False, True),        # 12 M-tiles: one M-tile per CTA (count % 4 != 0 is 0 here -> 2 per CTA), 3 super-tiles
+    (1, (128,), 128, 20, 64, (3, 3), (1, 1), False, False, False),      # 10 M-tiles: % 4 != 0 -> one M-tile per CTA
 ]
 
 
