@@ -342,8 +342,8 @@ template <int BLOCK_N, int MT = 1>
 struct PairCfg {
   static constexpr int kBHalfBytes = (BLOCK_N / 2) * kBlockK * 2;   // this CTA's half of the weight tile's rows
   static constexpr int kStageBytes = MT * kATileBytes + kBHalfBytes;     // 32 / 24 / 40 KiB
-  static constexpr int kStages = MT == 2 ? 4 : (BLOCK_N == 256 ? 5 : 7);
-  static constexpr int kStoreBufs = 2;
+  static constexpr int kStages = MT == 2 ? 5 : (BLOCK_N == 256 ? 5 : 7);
+  static constexpr int kStoreBufs = MT == 2 ? 1 : 2;             // MT = 2: the fifth ring stage is worth more than a second slab
   static constexpr int kAcc = 2 * MT;                               // accumulator stages
   static constexpr int kTmemCols = kAcc * BLOCK_N;
   static constexpr int kTailBytes = 256 + 2 * BLOCK_N * 4 + kEpiWarps * 16 * 4 + 64;
