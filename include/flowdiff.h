@@ -152,6 +152,17 @@ FD_API int fd_conv_igemm_ex(const void* src0, int C0, const void* src1, int C1, 
                      int N, int H, int W, int Cout, int KH, int KW, int pad_h, int pad_w, int mode,
                      int out_mode, void* stream);
 
+/* 3x3 / pad 1 / 64 -> 64 channel convolution whose INPUT is activated on the fly:
+ *   out = conv3x3(silu(GroupNorm(src) * (scale + 1) + shift)) (+ bias, + residual, + GroupNorm statistics of out)
+ * i.e. fd_gn_silu (Block.forward, denoising_diffusion.py:176-187) fused into the consuming block2.proj convolution
+ * (ResnetBlock.forward :202-214): the activated tensor is never written to memory.  in_stats are the (sum, sum of squares)
+ * statistics of src as produced by the convolution that wrote it; the other arguments as fd_gn_silu / fd_conv_igemm.
+ * Bit-identical to fd_gn_silu followed by fd_conv_igemm.  Needs W >= 64. */
+FD_API int fd_conv3x3_gnsilu_in(const void* src, const double* in_stats, const float* in_gamma, const float* in_beta,
+                                const float* in_scale_shift, long in_ss_stride, float in_eps, const void* wpacked,
+                                const float* bias, const void* residual, void* out, double* gn_stats, int N, int H, int W,
+                                void* stream);
+
 /* Weight gradient of the same convolutions (autograd of the nn.Conv2d calls above) on tcgen05, K = pixels:
  *   dw[co][tap*Cin + ci] += sum_{n,h,w} src[n, h+dy(tap), w+dx(tap), ci] * dy[n,h,w,co]      (fp32, packed order of
  * fd_prep_weight kind 0 / 1; caller zero-fills).  src = concat(src0, src1) as in fd_conv_igemm; mode as there

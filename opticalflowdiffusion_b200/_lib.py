@@ -72,6 +72,7 @@ SIGNATURES = {
     "fd_add_bf16": (c_int, [_P, _P, _P, _L, _P]),
     "fd_bias_grad": (c_int, [_P, _P, _L, _I, _P]),
     "fd_final_conv_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
+    "fd_conv3x3_gnsilu_in": (c_int, [_P, _P, _P, _P, _P, _L, _F, _P, _P, _P, _P, _P, _I, _I, _I, _P]),
     "fd_prep_weight_dgrad": (c_int, [_P, _P, _I, _I, _I, _P]),
     "fd_prep_weight_batch": (c_int, [_P, _P, _I, _I, _F, _P]),
     "fd_prep_weight_dgrad_batch": (c_int, [_P, _P, _I, _I, _P]),

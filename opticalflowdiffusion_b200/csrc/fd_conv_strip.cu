@@ -50,7 +50,8 @@ constexpr int kStripBytes = 136 * 128;         // slot size: multiple of 1024 ke
 constexpr int kNS = 5;                         // strips in flight: 3 in use + 2 prefetched (6 measured no faster)
 constexpr int kWTapBytes = kC * kC * 2;        // one tap of weights: [64 cout][64 cin] bf16
 constexpr int kWBytes = 9 * kWTapBytes;        // 72 KB, resident
-constexpr int kThreads = 64 + kEpiThreads + 32;  // warp 0 TMA, warps 1 and 10 MMA issuers (even / odd tiles), warps 2..9 epilogue
+constexpr int kThreads = 64 + kEpiThreads + 64;  // warp 0 TMA, warp 1 MMA issuer, warps 2..9 epilogue; warps 10, 11: second SS issuer /
+                                                 // the input transform of the fused GroupNorm + SiLU variant
 constexpr int kTail = 256 + 2 * kC * 4 + kEpiWarps * 16 * 4 + 64;
 constexpr int kSmemBytes = 1024 + kWBytes + kNS * kStripBytes + 2 * kSlabBytes + kTail;
 
@@ -82,6 +83,14 @@ struct StripParams {
   const float* bias;
   const __nv_bfloat16* residual;
   double* gn_stats;
+  // fused input transform (TS variant only): the strips are activated in shared memory, x -> silu(a[c] x + b[c]) with the
+  // GroupNorm statistics of the INPUT tensor folded into a, b exactly as gn_silu_kernel does (Block.forward :176-187)
+  const double* in_stats;    // [N][8][2] or null (no transform)
+  const float* in_gamma;
+  const float* in_beta;
+  const float* in_ss;        // (scale | shift) rows or null
+  long in_ss_stride;
+  float in_eps;
   int pf;                    // L2 prefetch distance in rows (0 = off)
   int dbg;                   // FD_CONV_DBG in FD_CONV_DIAG builds: 4 = no MMAs, 8 = epilogue handshakes only, 64 = no tcgen05.cp
 };
@@ -263,6 +272,8 @@ conv3x3_strip_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_co
   auto empty_bar = [&](int s) { return bar_base + 8u * (1 + kNS + s); };
   auto tfull_bar = [&](int s) { return bar_base + 8u * (1 + 2 * kNS + s); };
   auto tempty_bar = [&](int s) { return bar_base + 8u * (3 + 2 * kNS + s); };
+  auto xfull_bar = [&](int s) { return bar_base + 8u * (5 + 2 * kNS + s); };   // strip transformed (fused GroupNorm input)
+  const bool fuse_in = TS && p.in_stats != nullptr;
   uint8_t* gtail = gbase + kWBytes + kNS * kStripBytes + 2 * kSlabBytes + 256;
   float* s_bias = reinterpret_cast<float*>(gtail);
   float* s_stats = reinterpret_cast<float*>(gtail + 2 * kC * 4);
@@ -277,6 +288,7 @@ conv3x3_strip_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_co
     for (int s = 0; s < kNS; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
+      mbar_init(xfull_bar(s), 64);        // the two transform warps
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
@@ -335,9 +347,11 @@ conv3x3_strip_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_co
       StripWalk cwalk(p);
       int c_left = 0;
       uint32_t cseq = 0;
+      // "the strip is ready": landed (TMA) or, with the fused input transform, landed and activated
+      auto ready_bar = [&](uint32_t slot) { return fuse_in ? xfull_bar(slot) : full_bar(slot); };
       auto copy_strip = [&]() {
         const uint32_t slot = cseq % kNS;
-        mbar_wait(full_bar(slot), (cseq / kNS) & 1u);
+        mbar_wait(ready_bar(slot), (cseq / kNS) & 1u);
         tc_fence_after();
         const uint32_t dst = a_tmem0 + (cseq % kATmemSlots) * kATmemSlotCols;
         const uint64_t sd = umma_desc_sw128(s_smem + slot * kStripBytes);
@@ -381,7 +395,7 @@ conv3x3_strip_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_co
         }
         return c;
       };
-      auto landed = [&](Claim& c) { c.inter = c.more && mbar_try_wait(full_bar(c.slot), c.phase); };
+      auto landed = [&](Claim& c) { c.inter = c.more && mbar_try_wait(ready_bar(c.slot), c.phase); };
       long long dg_t0 = 0, dg_mma = 0, dg_tail = 0;
       unsigned long long dg_ns0 = 0;
       if (kDiag) {
@@ -450,7 +464,7 @@ conv3x3_strip_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_co
           if (cp.inter) {
             umma_commit(empty_bar(cp.slot));
           } else if (cp.more) {                           // the strip had not landed when the tile started
-            mbar_wait(full_bar(cp.slot), cp.phase);
+            mbar_wait(ready_bar(cp.slot), cp.phase);
             tc_fence_after();
 #pragma unroll
             for (int c = 0; c < 12; ++c)
@@ -489,6 +503,78 @@ conv3x3_strip_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_co
       }
     }
     __syncwarp();
+  } else if (TS && (warp == 10 || warp == 11)) {
+    // ===================== fused input transform: GroupNorm affine + SiLU on the landed strip, in place =====================
+    // Replaces the separate gn_silu pass over the producer's output (one read + one write of the tensor) for the convs whose
+    // input is only consumed here (ResnetBlock block1 -> block2, :202-214).  64 threads: thread = (8-channel granule q, row
+    // r0 + 8 i); rows / pixels outside the image were zero-filled by TMA and must stay zero (the padding applies to the
+    // ACTIVATED tensor), so they are skipped.  Arithmetic identical to gn_silu_kernel -> bit-identical conv input.
+    if (fuse_in) {
+      const int tl = (warp - 10) * 32 + lane;
+      const int q = tl & 7, r0 = tl >> 3;
+      float a[8], b[8];
+      int cur_n = -1;
+      uint32_t seq = 0;
+      StripWalk walk(p);
+      int n, w0, ra, rb;
+      while (walk.next(p, n, w0, ra, rb)) {
+        if (n != cur_n) {
+          cur_n = n;
+          const int C = kC, cpg = C >> 3;
+          const double cnt = (double)p.H * (double)p.W * cpg;
+          const int g = (q * 8) / cpg;
+          const double sm = p.in_stats[((long)n * 8 + g) * 2], ss = p.in_stats[((long)n * 8 + g) * 2 + 1];
+          const double mean = sm / cnt;
+          double var = ss / cnt - mean * mean;
+          if (var < 0.0) var = 0.0;
+          const float rstd = (float)(1.0 / sqrt(var + (double)p.in_eps));
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int c = q * 8 + j;
+            float ga = __ldg(p.in_gamma + c) * rstd;
+            float be = __ldg(p.in_beta + c) - (float)mean * ga;
+            if (p.in_ss != nullptr) {
+              const float sc = __ldg(p.in_ss + (long)n * p.in_ss_stride + c) + 1.f;
+              const float sh = __ldg(p.in_ss + (long)n * p.in_ss_stride + C + c);
+              ga *= sc;
+              be = be * sc + sh;
+            }
+            a[j] = ga;
+            b[j] = be;
+          }
+        }
+        for (int y = ra - 1; y <= rb; ++y, ++seq) {
+          const uint32_t slot = seq % kNS;
+          mbar_wait(full_bar(slot), (seq / kNS) & 1u);
+          if (y >= 0 && y < p.H) {
+            uint8_t* sp = gbase + kWBytes + slot * kStripBytes;
+#pragma unroll 4
+            for (int r = r0; r < kStripPx; r += 8) {
+              const int x = w0 - 1 + r;
+              if (x < 0 || x >= p.W) continue;
+              uint4* gp = reinterpret_cast<uint4*>(sp + r * 128 + ((q ^ (r & 7)) << 4));
+              const uint4 v = *gp;
+              const uint32_t xw[4] = {v.x, v.y, v.z, v.w};
+              float o[8];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 f = fd_unpack_bf16(xw[e]);
+                o[2 * e] = fd_silu(a[2 * e] * f.x + b[2 * e]);
+                o[2 * e + 1] = fd_silu(a[2 * e + 1] * f.y + b[2 * e + 1]);
+              }
+              uint4 w4;
+              w4.x = fd_pack_bf16(o[0], o[1]);
+              w4.y = fd_pack_bf16(o[2], o[3]);
+              w4.z = fd_pack_bf16(o[4], o[5]);
+              w4.w = fd_pack_bf16(o[6], o[7]);
+              *gp = w4;
+            }
+          }
+          fence_proxy_async_smem();       // generic-proxy writes -> visible to tcgen05.cp (async proxy)
+          mbar_arrive(xfull_bar(slot));
+        }
+      }
+    }
   } else if (!TS && (warp == 1 || warp == 10)) {
     // ===================== MMA issuers =====================
     // A 128x64x16 UMMA occupies the tensor core for only 32 cycles, less than one thread needs to issue the next
@@ -586,8 +672,35 @@ conv3x3_strip_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_co
 }  // namespace
 
 // (C0, C1) in {(64, 0), (64, 64), (128, 0)}; Cout = 64; 3x3, pad 1
+struct StripInputNorm {           // fused GroupNorm + SiLU on the input (null stats = none)
+  const double* stats;
+  const float *gamma, *beta, *scale_shift;
+  long ss_stride;
+  float eps;
+};
+
+static int strip_launch(const void* src0, int C0, const void* src1, int C1, const void* wpacked, const float* bias,
+                        const void* residual, void* out, double* gn_stats, int N, int H, int W, int base_offset_mode,
+                        const StripInputNorm& in, cudaStream_t st);
+
 int fd_conv3x3_strip_launch(const void* src0, int C0, const void* src1, int C1, const void* wpacked, const float* bias,
                             const void* residual, void* out, double* gn_stats, int N, int H, int W, int base_offset_mode, cudaStream_t st) {
+  return strip_launch(src0, C0, src1, C1, wpacked, bias, residual, out, gn_stats, N, H, W, base_offset_mode, StripInputNorm{}, st);
+}
+
+extern "C" int fd_conv3x3_gnsilu_in(const void* src, const double* in_stats, const float* in_gamma, const float* in_beta,
+                                    const float* in_scale_shift, long in_ss_stride, float in_eps, const void* wpacked,
+                                    const float* bias, const void* residual, void* out, double* gn_stats, int N, int H, int W,
+                                    void* stream) {
+  FD_REQUIRE(src && in_stats && in_gamma && in_beta && wpacked && out && N > 0 && H > 0 && W >= 64,
+             "conv3x3_gnsilu_in: bad argument (needs 64 -> 64 channels, W >= 64)");
+  StripInputNorm in{in_stats, in_gamma, in_beta, in_scale_shift, in_ss_stride, in_eps};
+  return strip_launch(src, 64, nullptr, 0, wpacked, bias, residual, out, gn_stats, N, H, W, 2, in, (cudaStream_t)stream);
+}
+
+static int strip_launch(const void* src0, int C0, const void* src1, int C1, const void* wpacked, const float* bias,
+                        const void* residual, void* out, double* gn_stats, int N, int H, int W, int base_offset_mode,
+                        const StripInputNorm& in, cudaStream_t st) {
   static int sms = 0;
   if (sms == 0) {
     int dev = 0;
@@ -630,7 +743,13 @@ int fd_conv3x3_strip_launch(const void* src0, int C0, const void* src1, int C1, 
   // 0.141 ms at the copy peak, 0.175 ms measured with MMAs and copies disabled).  FD_STRIP_TS=0 selects the SS variant (read
   // per call so that tests can exercise both).
   const char* ets = getenv("FD_STRIP_TS");
-  const bool ts = (ets == nullptr || atoi(ets) != 0) && base_offset_mode != 1;
+  const bool ts = in.stats != nullptr || ((ets == nullptr || atoi(ets) != 0) && base_offset_mode != 1);   // the fused input transform lives in the TS issuer
+  p.in_stats = in.stats;
+  p.in_gamma = in.gamma;
+  p.in_beta = in.beta;
+  p.in_ss = in.scale_shift;
+  p.in_ss_stride = in.ss_stride;
+  p.in_eps = in.eps;
   {
     const char* e = getenv("FD_STRIP_PF");           // L2 prefetch distance in rows; measured no gain (0.229 -> 0.231 ms), off
     p.pf = e ? atoi(e) : 0;

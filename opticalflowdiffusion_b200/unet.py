@@ -19,6 +19,8 @@ from __future__ import annotations
 
 from typing import Dict, List, Optional, Tuple
 
+import os
+
 import torch
 
 from . import _lib
@@ -45,6 +47,11 @@ class Unet(UnetParams, TrainMixin):
     """Unet(dim=64, channels=C_in, out_dim=2): same constructor meaning as the reference (:272-293)."""
 
     GN_EPS = 1e-5       # nn.GroupNorm default (:176)
+    # block1's GroupNorm + SiLU applied inside the block2.proj strip conv (fd_conv3x3_gnsilu_in).  Bit-identical, removes five
+    # full-resolution gn_silu passes per forward -- but measured SLOWER on the DDIM-50 benchmark (6.62 vs 6.87 flows/s): two
+    # transform warps are all the register budget allows next to the 168-register epilogue, and ~1100 instructions per strip
+    # and thread put them on the critical path.  Off by default (FD_FUSE_GN=1 enables it); see DESIGN.md section 6.
+    FUSE_GN_INPUT = os.environ.get("FD_FUSE_GN", "0") != "0"
     WS_EPS = 1e-5       # WeightStandardizedConv2d with fp32 input (:107)
     LN_EPS = 1e-5       # LayerNorm with fp32 input (:122)
 
@@ -197,6 +204,24 @@ class Unet(UnetParams, TrainMixin):
             ev[1].record()
         return out
 
+    def _conv_gnsilu_in(self, name: str, src: Tensor, in_stats: Tensor, norm, ss: Optional[Tensor], ss_off: int,
+                        stats: Optional[Tensor]) -> Tensor:
+        pc = self._convs[name]
+        n, h, w, _ = src.shape
+        out = torch.empty(n, h, w, pc.cout, device=src.device, dtype=BF16)
+        timing = getattr(self, "_conv_timing", None)
+        if timing is not None:
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            timing.append((name, 2.0 * n * h * w * pc.cout * pc.w.shape[1], ev))
+            ev[0].record()
+        ss_ptr = ss.data_ptr() + 4 * ss_off if ss is not None else None
+        _lib.check(self._lib.fd_conv3x3_gnsilu_in(_lib.ptr(src), _lib.ptr(in_stats), _lib.ptr(norm.weight), _lib.ptr(norm.bias),
+                                                  ss_ptr, ss.shape[1] if ss is not None else 0, self.GN_EPS, _lib.ptr(pc.w),
+                                                  _lib.ptr(pc.bias), None, _lib.ptr(out), _lib.ptr(stats), n, h, w, self._st))
+        if timing is not None:
+            ev[1].record()
+        return out
+
     def _gn_silu(self, x: Tensor, stats: Tensor, norm, ss: Optional[Tensor], ss_off: int,
                  residual: Optional[Tensor]) -> Tensor:
         n, h, w, c = x.shape
@@ -218,8 +243,14 @@ class Unet(UnetParams, TrainMixin):
         """ResnetBlock.forward (:202-214)."""
         st1, st2 = self._next_stats(), self._next_stats()
         h1 = self._conv(name + ".block1.proj", x0, x1, stats=st1)
-        a1 = self._gn_silu(h1, st1, rb.block1.norm, ss, self._tproj_off[name], None)
-        h2 = self._conv(name + ".block2.proj", a1, stats=st2)
+        pc2 = self._convs[name + ".block2.proj"]
+        if h1.shape[-1] == 64 and pc2.cout == 64 and h1.shape[2] >= 128 and self.FUSE_GN_INPUT:
+            # 64 -> 64 at full resolution: GroupNorm + scale/shift + SiLU of h1 is applied to the input strips inside the
+            # conv (fd_conv3x3_gnsilu_in), the activated tensor never goes through HBM (bit-identical to the two-pass form)
+            h2 = self._conv_gnsilu_in(name + ".block2.proj", h1, st1, rb.block1.norm, ss, self._tproj_off[name], st2)
+        else:
+            a1 = self._gn_silu(h1, st1, rb.block1.norm, ss, self._tproj_off[name], None)
+            h2 = self._conv(name + ".block2.proj", a1, stats=st2)
         if (name + ".res_conv") in self._convs:
             a2 = self._gn_silu(h2, st2, rb.block2.norm, None, 0, None)
             return self._conv(name + ".res_conv", x0, x1, residual=a2)

@@ -161,3 +161,42 @@ def test_strip_conv_tensor_memory_operand(L, case, monkeypatch):
     assert torch.equal(out_ss, out_ts)
     if stats:
         assert torch.allclose(gn_ss, gn_ts, rtol=1e-12, atol=1e-9)
+
+
+@pytest.mark.parametrize("case", [(2, 37, 256, True), (1, 21, 200, False), (3, 5, 130, True), (1, 70, 64, True)])
+def test_strip_conv_fused_groupnorm_input(L, case):
+    """fd_conv3x3_gnsilu_in = fd_gn_silu (GroupNorm affine + scale/shift + SiLU, Block.forward :176-187) fused into the 64 -> 64
+    strip convolution that consumes it: must equal the two-pass form bit for bit (same arithmetic on the strip in shared
+    memory; rows / pixels outside the image stay zero = padding of the ACTIVATED tensor)."""
+    lib = L.load()
+    N, H, W, use_ss = case
+    g = torch.Generator().manual_seed(H * W + N)
+    x = (torch.randn(N, H, W, 64, generator=g) * 1.5 + 0.3).to(torch.bfloat16).cuda()
+    w = (torch.randn(64, 64, 3, 3, generator=g) / 24.0).cuda()
+    wp = pack_w(w)
+    bias = torch.randn(64, generator=g).cuda()
+    gamma, beta = torch.randn(64, generator=g).cuda(), torch.randn(64, generator=g).cuda()
+    ss = (torch.randn(N, 192, generator=g) * 0.5).cuda() if use_ss else None
+    ss_ptr = ss.data_ptr() + 4 * 32 if use_ss else None          # (scale | shift) rows start at an offset, as in the UNet
+    r = x.float().permute(0, 3, 1, 2).double().reshape(N, 8, -1)
+    in_stats = torch.stack((r.sum(-1), (r * r).sum(-1)), -1).contiguous()
+    # two passes
+    act = torch.empty_like(x)
+    L.check(lib.fd_gn_silu(L.ptr(x), L.ptr(in_stats), L.ptr(gamma), L.ptr(beta), ss_ptr, 192 if use_ss else 0, None, L.ptr(act),
+                           N, H * W, 64, 1e-5, L.stream()))
+    ref = torch.empty(N, H, W, 64, device="cuda", dtype=torch.bfloat16)
+    gn_ref = torch.zeros(N, 8, 2, device="cuda", dtype=torch.float64)
+    L.check(lib.fd_conv_igemm(L.ptr(act), 64, None, 0, L.ptr(wp), L.ptr(bias), None, L.ptr(ref), L.ptr(gn_ref), N, H, W, 64, 3, 3,
+                              1, 1, 0, L.stream()))
+    # fused
+    out = torch.empty_like(ref)
+    gn = torch.zeros_like(gn_ref)
+    L.check(lib.fd_conv3x3_gnsilu_in(L.ptr(x), L.ptr(in_stats), L.ptr(gamma), L.ptr(beta), ss_ptr, 192 if use_ss else 0, 1e-5,
+                                     L.ptr(wp), L.ptr(bias), None, L.ptr(out), L.ptr(gn), N, H, W, L.stream()))
+    torch.cuda.synchronize()
+    assert torch.equal(out, ref)
+    # (W < 128 sends the two-pass reference through the generic kernel, whose fp32 partial sums are grouped differently)
+    assert torch.allclose(gn, gn_ref, rtol=1e-12 if W >= 128 else 1e-6, atol=1e-9 if W >= 128 else 1e-3)
+    # and against torch on the same bf16-rounded activation
+    y = F.conv2d(act.float().permute(0, 3, 1, 2), w.to(torch.bfloat16).float(), bias, padding=1)
+    close(out.permute(0, 3, 1, 2).float(), y)
