@@ -347,8 +347,28 @@ def run_train_leg(args, algo_cfg, rank: int, world: int, dev):
     def step_resident():
         return one_step(batch_dev)
 
+    # e2e: every step uploads its own inputs from pinned host memory and reads the loss back; like a DataLoader with
+    # pin_memory + prefetch, the upload of step i+1 runs on a copy stream while step i computes (all inside the timed region)
+    copy_stream = torch.cuda.Stream(device=dev)
+    pending = []
+
+    def upload():
+        copy_stream.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(copy_stream):
+            b = tuple(t.to(dev, non_blocking=True) for t in (img_h, tgt_h, flow_h))
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        return b, ev
+
     def step_e2e():
-        batch = tuple(t.to(dev, non_blocking=True) for t in (img_h, tgt_h, flow_h))
+        if not pending:
+            pending.append(upload())
+        batch, ev = pending.pop()
+        cur = torch.cuda.current_stream()
+        cur.wait_event(ev)
+        for t in batch:
+            t.record_stream(cur)
+        pending.append(upload())
         loss = one_step(batch)
         loss_host.copy_(loss.detach(), non_blocking=True)
         torch.cuda.synchronize()
