@@ -157,7 +157,8 @@ FD_API int fd_conv_igemm_ex(const void* src0, int C0, const void* src1, int C1, 
  * i.e. fd_gn_silu (Block.forward, denoising_diffusion.py:176-187) fused into the consuming block2.proj convolution
  * (ResnetBlock.forward :202-214): the activated tensor is never written to memory.  in_stats are the (sum, sum of squares)
  * statistics of src as produced by the convolution that wrote it; the other arguments as fd_gn_silu / fd_conv_igemm.
- * Bit-identical to fd_gn_silu followed by fd_conv_igemm.  Needs W >= 64. */
+ * Same folded coefficients as fd_gn_silu; the in-kernel SiLU uses tanh.approx (within 2^-10 of fd_silu before the bf16
+ * rounding of the activation).  Needs W >= 64. */
 FD_API int fd_conv3x3_gnsilu_in(const void* src, const double* in_stats, const float* in_gamma, const float* in_beta,
                                 const float* in_scale_shift, long in_ss_stride, float in_eps, const void* wpacked,
                                 const float* bias, const void* residual, void* out, double* gn_stats, int N, int H, int W,

@@ -73,6 +73,17 @@ constexpr int kATmemCol0 = 2 * kC;             // TS variant: accumulators in co
 constexpr int kATmemSlotCols = 3 * (kC / 2);   // one strip = 3 kx-shifted copies x 32 columns (64 bf16 per lane)
 constexpr int kATmemSlots = 4;                 // 3 strips in use + 1 being staged
 
+// silu(z) = z sigmoid(z) = h + h tanh(h), h = z / 2: ONE MUFU op (tanh.approx, 2^-11 relative) instead of the ex2 + rcp of
+// fd_silu.  The fused input transform runs on two warps = two of the SM's four MUFU units; with two MUFU ops per element it
+// needed ~2100 cycles per strip (more than a tile's MMAs), with one ~1050.  The result differs from fd_silu by < 2^-10
+// relative before the bf16 rounding (2^-9) that follows.
+__device__ __forceinline__ float silu_tanh(float z) {
+  const float h = 0.5f * z;
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+  return fmaf(h, t, h);
+}
+
 struct StripParams {
   int N, H, W;
   int wblocks, total_rows;   // column blocks per image; N * wblocks * H output rows in (image, column block, row) order
@@ -508,7 +519,7 @@ conv3x3_strip_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_co
     // Replaces the separate gn_silu pass over the producer's output (one read + one write of the tensor) for the convs whose
     // input is only consumed here (ResnetBlock block1 -> block2, :202-214).  64 threads: thread = (8-channel granule q, row
     // r0 + 8 i); rows / pixels outside the image were zero-filled by TMA and must stay zero (the padding applies to the
-    // ACTIVATED tensor), so they are skipped.  Arithmetic identical to gn_silu_kernel -> bit-identical conv input.
+    // ACTIVATED tensor), so they are skipped.  Same folded coefficients as gn_silu_kernel; the SiLU uses one MUFU op (silu_tanh).
     if (fuse_in) {
       const int tl = (warp - 10) * 32 + lane;
       const int q = tl & 7, r0 = tl >> 3;
@@ -559,8 +570,8 @@ conv3x3_strip_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_co
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
                 const float2 f = fd_unpack_bf16(xw[e]);
-                o[2 * e] = fd_silu(a[2 * e] * f.x + b[2 * e]);
-                o[2 * e + 1] = fd_silu(a[2 * e + 1] * f.y + b[2 * e + 1]);
+                o[2 * e] = silu_tanh(a[2 * e] * f.x + b[2 * e]);
+                o[2 * e + 1] = silu_tanh(a[2 * e + 1] * f.y + b[2 * e + 1]);
               }
               uint4 w4;
               w4.x = fd_pack_bf16(o[0], o[1]);

@@ -47,10 +47,11 @@ class Unet(UnetParams, TrainMixin):
     """Unet(dim=64, channels=C_in, out_dim=2): same constructor meaning as the reference (:272-293)."""
 
     GN_EPS = 1e-5       # nn.GroupNorm default (:176)
-    # block1's GroupNorm + SiLU applied inside the block2.proj strip conv (fd_conv3x3_gnsilu_in).  Bit-identical, removes five
-    # full-resolution gn_silu passes per forward -- but measured SLOWER on the DDIM-50 benchmark (6.62 vs 6.87 flows/s): two
-    # transform warps are all the register budget allows next to the 168-register epilogue, and ~1100 instructions per strip
-    # and thread put them on the critical path.  Off by default (FD_FUSE_GN=1 enables it); see DESIGN.md section 6.
+    # block1's GroupNorm + SiLU applied inside the block2.proj strip conv (fd_conv3x3_gnsilu_in).  Removes five
+    # full-resolution gn_silu passes per forward -- but measured slightly SLOWER on the DDIM-50 benchmark (6.79 vs 6.85
+    # flows/s): two transform warps are all the register budget allows next to the 168-register epilogue, and ~1050
+    # instructions per strip and thread put them on the critical path.  Off by default (FD_FUSE_GN=1 enables it); see
+    # DESIGN.md section 6.
     FUSE_GN_INPUT = os.environ.get("FD_FUSE_GN", "0") != "0"
     WS_EPS = 1e-5       # WeightStandardizedConv2d with fp32 input (:107)
     LN_EPS = 1e-5       # LayerNorm with fp32 input (:122)
@@ -246,7 +247,7 @@ class Unet(UnetParams, TrainMixin):
         pc2 = self._convs[name + ".block2.proj"]
         if h1.shape[-1] == 64 and pc2.cout == 64 and h1.shape[2] >= 128 and self.FUSE_GN_INPUT:
             # 64 -> 64 at full resolution: GroupNorm + scale/shift + SiLU of h1 is applied to the input strips inside the
-            # conv (fd_conv3x3_gnsilu_in), the activated tensor never goes through HBM (bit-identical to the two-pass form)
+            # conv (fd_conv3x3_gnsilu_in), the activated tensor never goes through HBM
             h2 = self._conv_gnsilu_in(name + ".block2.proj", h1, st1, rb.block1.norm, ss, self._tproj_off[name], st2)
         else:
             a1 = self._gn_silu(h1, st1, rb.block1.norm, ss, self._tproj_off[name], None)

@@ -166,8 +166,8 @@ def test_strip_conv_tensor_memory_operand(L, case, monkeypatch):
 @pytest.mark.parametrize("case", [(2, 37, 256, True), (1, 21, 200, False), (3, 5, 130, True), (1, 70, 64, True)])
 def test_strip_conv_fused_groupnorm_input(L, case):
     """fd_conv3x3_gnsilu_in = fd_gn_silu (GroupNorm affine + scale/shift + SiLU, Block.forward :176-187) fused into the 64 -> 64
-    strip convolution that consumes it: must equal the two-pass form bit for bit (same arithmetic on the strip in shared
-    memory; rows / pixels outside the image stay zero = padding of the ACTIVATED tensor)."""
+    strip convolution that consumes it, against the two-pass form (same folded coefficients on the strip in shared memory; rows /
+    pixels outside the image stay zero = padding of the ACTIVATED tensor)."""
     lib = L.load()
     N, H, W, use_ss = case
     g = torch.Generator().manual_seed(H * W + N)
@@ -194,9 +194,12 @@ def test_strip_conv_fused_groupnorm_input(L, case):
     L.check(lib.fd_conv3x3_gnsilu_in(L.ptr(x), L.ptr(in_stats), L.ptr(gamma), L.ptr(beta), ss_ptr, 192 if use_ss else 0, 1e-5,
                                      L.ptr(wp), L.ptr(bias), None, L.ptr(out), L.ptr(gn), N, H, W, L.stream()))
     torch.cuda.synchronize()
-    assert torch.equal(out, ref)
-    # (W < 128 sends the two-pass reference through the generic kernel, whose fp32 partial sums are grouped differently)
-    assert torch.allclose(gn, gn_ref, rtol=1e-12 if W >= 128 else 1e-6, atol=1e-9 if W >= 128 else 1e-3)
+    # the in-kernel SiLU uses tanh.approx (one MUFU op) instead of ex2 + rcp: the activation differs from fd_gn_silu's by
+    # < 2^-10 relative before its bf16 rounding, i.e. an occasional 1-ulp flip of a conv input -> compare at that level
+    err = (out.float() - ref.float()).abs()
+    assert err.max().item() <= 2.5e-2 * ref.float().abs().max().item() and err.mean().item() <= 1e-3 * ref.float().abs().mean().item(), \
+        (err.max().item(), err.mean().item())
+    assert torch.allclose(gn, gn_ref, rtol=2e-3, atol=0.5)
     # and against torch on the same bf16-rounded activation
     y = F.conv2d(act.float().permute(0, 3, 1, 2), w.to(torch.bfloat16).float(), bias, padding=1)
     close(out.permute(0, 3, 1, 2).float(), y)
