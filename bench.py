@@ -123,7 +123,7 @@ def run_reference(args, rank: int):
             "cpu_baseline": {"value": value, "unit": "flows/s", "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "flows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    _emit(line)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -148,7 +148,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     if args.skip_sample:
         tr = run_train_leg(args, cfg.algorithm, rank, world, dev)
         if rank == 0:
-            print(json.dumps({"train": tr, "n_gpus": world}))
+            _emit({"train": tr, "n_gpus": world})
         return
     algo = FlowDiffuser(cfg.algorithm).to(dev)
     algo.unet.prepare()
@@ -268,7 +268,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                                 "kind": "port",
                                 "sample": "one of the 50 DDIM steps of ONE 436x1024 sample (UNet forward + update) on the host "
                                           "cores after one warm-up, x50 extrapolated"}
-    print(json.dumps(line))
+    _emit(line)
     if world > 1:
         pass
 
@@ -423,6 +423,20 @@ def run_train_leg(args, algo_cfg, rank: int, world: int, dev):
                       "reference Augmentor semantics, decisions on the host, arithmetic in 4 launches), Adam lr 1e-5 wd 1e-6, clip 100, gradient all-reduce over NCCL when n_gpus > 1"}
 
 
+_REAL_STDOUT = None
+
+
+def _emit(obj):
+    """The one JSON line of this run, on the process's original stdout."""
+    text = json.dumps(obj) + "\n"
+    sys.stdout.flush()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(text)
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, text.encode())
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -436,6 +450,12 @@ def main():
     ap.add_argument("--skip-train", action="store_true", help="omit the training leg (BASELINE configs[2])")
     ap.add_argument("--skip-sample", action="store_true", help="training leg only (debug; prints a reduced line)")
     args = ap.parse_args()
+    # stdout carries exactly ONE JSON line: libraries that chat on file descriptor 1 (NCCL prints its version banner there)
+    # are sent to stderr for the duration of the run; _emit() writes the result to the real stdout
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
