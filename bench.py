@@ -246,6 +246,8 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                      "traffic": CONV_DRAM_BYTES_PER_FORWARD, "traffic_source": "profiles/r1_forward_traffic_v5.txt: ncu dram__bytes_read.sum + "
                      "dram__bytes_write.sum summed over the conv launches of ONE forward at this batch (same unit as `achieved`: one "
                      "forward's conv launches); algorithmic FLOPs, not bytes, bound these kernels", "peak_source": peaks["src"] + " (sustained: the kernel is timed inside a long step)",
+                     "note": "5 of these launches (the full-resolution block2.proj strip convs) also apply the preceding GroupNorm + SiLU "
+                             "to their input strips (fd_conv3x3_gnsilu_in) unless FD_FUSE_GN=0; their time is counted, the activation FLOPs are not",
                      "conv_share_of_forward": conv_s / fwd_s, "forward_ms": fwd_s * 1e3,
                      "whole_step_tflops": FWD_GF_PER_SAMPLE * DDIM_STEPS * 1e9 * value / 1e12},
     }

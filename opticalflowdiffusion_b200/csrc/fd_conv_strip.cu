@@ -550,28 +550,36 @@ conv3x3_strip_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_co
               ga *= sc;
               be = be * sc + sh;
             }
-            a[j] = ga;
-            b[j] = be;
+            a[j] = 0.5f * ga;             // halved: the transform works on h = z / 2 (see below)
+            b[j] = 0.5f * be;
           }
         }
         for (int y = ra - 1; y <= rb; ++y, ++seq) {
           const uint32_t slot = seq % kNS;
           mbar_wait(full_bar(slot), (seq / kNS) & 1u);
           if (y >= 0 && y < p.H) {
-            uint8_t* sp = gbase + kWBytes + slot * kStripBytes;
+            // rows r of the strip <-> pixels x = w0 - 1 + r; only [rlo, rhi) lie inside the image.  r advances by 8, so the
+            // swizzle term (r & 7) == r0 is constant and the granule address advances by 1024 B.
+            const int rlo = w0 > 0 ? 0 : 1 - w0;
+            const int rhi = min(kStripPx, p.W - w0 + 1);
+            int r = r0 < rlo ? r0 + (((rlo - r0) + 7) & ~7) : r0;
+            uint8_t* gp8 = gbase + kWBytes + slot * kStripBytes + r * 128 + ((q ^ r0) << 4);
 #pragma unroll 4
-            for (int r = r0; r < kStripPx; r += 8) {
-              const int x = w0 - 1 + r;
-              if (x < 0 || x >= p.W) continue;
-              uint4* gp = reinterpret_cast<uint4*>(sp + r * 128 + ((q ^ (r & 7)) << 4));
+            for (; r < rhi; r += 8, gp8 += 1024) {
+              uint4* gp = reinterpret_cast<uint4*>(gp8);
               const uint4 v = *gp;
               const uint32_t xw[4] = {v.x, v.y, v.z, v.w};
               float o[8];
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
-                const float2 f = fd_unpack_bf16(xw[e]);
-                o[2 * e] = silu_tanh(a[2 * e] * f.x + b[2 * e]);
-                o[2 * e + 1] = silu_tanh(a[2 * e + 1] * f.y + b[2 * e + 1]);
+                // silu(z) = h + h tanh(h), h = z / 2 = fma(a / 2, x, b / 2) (exact scaling): 3 instructions per element
+                const float h0 = fmaf(a[2 * e], __uint_as_float(xw[e] << 16), b[2 * e]);
+                const float h1 = fmaf(a[2 * e + 1], __uint_as_float(xw[e] & 0xffff0000u), b[2 * e + 1]);
+                float t0, t1;
+                asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(h0));
+                asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(h1));
+                o[2 * e] = fmaf(h0, t0, h0);
+                o[2 * e + 1] = fmaf(h1, t1, h1);
               }
               uint4 w4;
               w4.x = fd_pack_bf16(o[0], o[1]);

@@ -47,12 +47,11 @@ class Unet(UnetParams, TrainMixin):
     """Unet(dim=64, channels=C_in, out_dim=2): same constructor meaning as the reference (:272-293)."""
 
     GN_EPS = 1e-5       # nn.GroupNorm default (:176)
-    # block1's GroupNorm + SiLU applied inside the block2.proj strip conv (fd_conv3x3_gnsilu_in).  Removes five
-    # full-resolution gn_silu passes per forward -- but measured slightly SLOWER on the DDIM-50 benchmark (6.79 vs 6.85
-    # flows/s): two transform warps are all the register budget allows next to the 168-register epilogue, and ~1050
-    # instructions per strip and thread put them on the critical path.  Off by default (FD_FUSE_GN=1 enables it); see
-    # DESIGN.md section 6.
-    FUSE_GN_INPUT = os.environ.get("FD_FUSE_GN", "0") != "0"
+    # block1's GroupNorm + SiLU applied inside the block2.proj strip conv (fd_conv3x3_gnsilu_in, inference path): removes five
+    # full-resolution gn_silu passes per forward.  Measured on the DDIM-50 benchmark: 7.08-7.11 vs 6.96 flows/s (the first
+    # two versions of the in-kernel transform were slower than the separate pass; see DESIGN.md section 4).  FD_FUSE_GN=0
+    # selects the two-pass form.
+    FUSE_GN_INPUT = os.environ.get("FD_FUSE_GN", "1") != "0"
     WS_EPS = 1e-5       # WeightStandardizedConv2d with fp32 input (:107)
     LN_EPS = 1e-5       # LayerNorm with fp32 input (:122)
 
