@@ -49,7 +49,7 @@ class Unet(UnetParams, TrainMixin):
     GN_EPS = 1e-5       # nn.GroupNorm default (:176)
     # block1's GroupNorm + SiLU applied inside the block2.proj strip conv (fd_conv3x3_gnsilu_in, inference path): removes five
     # full-resolution gn_silu passes per forward.  Measured on the DDIM-50 benchmark: 7.08-7.11 vs 6.96 flows/s (the first
-    # two versions of the in-kernel transform were slower than the separate pass; see DESIGN.md section 4).  FD_FUSE_GN=0
+    # two versions of the in-kernel transform were slower than the separate pass; see DESIGN.md section 6).  FD_FUSE_GN=0
     # selects the two-pass form.
     FUSE_GN_INPUT = os.environ.get("FD_FUSE_GN", "1") != "0"
     WS_EPS = 1e-5       # WeightStandardizedConv2d with fp32 input (:107)
