@@ -11,7 +11,8 @@ arithmetic of:
 
   * ``Unet.forward``                     denoising_diffusion.py:272-417 (blocks :81-268)
   * the sigmoid beta schedule + buffers  denoising_diffusion.py:448-461, 511-583
-  * ``q_sample`` / ``p_losses`` / ``_loss`` (target=flow path)   :806-812, :823-891, :893-983
+  * ``q_sample`` / ``p_losses`` / ``_loss`` (target=flow, and the joint / target pyramid)   :806-812, :823-891, :893-983
+  * ``UnetWithWarp.forward``             flow_diffuser.py:38-63
   * ``model_predictions`` / ``ddim_sample`` / ``p_sample`` loops  :634-664, :731-774, :677-729
   * ``warp_backward_flow``               warp.py:95-119
   * the three forward-splat kernels      softsplat_new.py:352-423, 489-565, 600-700
@@ -355,6 +356,59 @@ def p_losses_flow(sd, sched, x0: Tensor, cond: Tensor, t: Tensor, noise: Tensor,
     return torch.nanmean(nan_mse(out[:, :3], x0[:, :3], reduction="none"))
 
 
+def unet_with_warp(sd, x: Tensor, cond: Tensor, t: Tensor, flow_max: float = 20.0, full_output: bool = True,
+                   additional_out: bool = False, prefix: str = "") -> Tensor:
+    """UnetWithWarp.forward, flow_diffuser.py:38-63 (nan_safe=True): NaN -> 0 plus a 1-channel "any NaN" mask appended
+    to x; flow = Unet(...); warped = forward splat of cond[:, :3] along flow * flow_max; cat(warped, flow) when
+    ``full_output`` (target='joint'); the flow appended once more when ``additional_out`` (target='target')."""
+    x = x.clone()
+    nans = torch.isnan(x)
+    x[nans] = 0.0
+    mask = torch.any(nans, dim=1)[:, None]
+    flow = unet_forward(sd, torch.cat((x, mask), dim=1), cond, t, prefix)
+    out = warp_forward_flow(cond[:, :3], flow[:, :2] * flow_max)
+    if full_output:
+        out = torch.cat((out, flow), dim=1)
+    return torch.cat((out, flow), dim=1) if additional_out else out
+
+
+def pyramid_loss(image_out: Tensor, target: Tensor, flow_out: Optional[Tensor] = None, cond: Optional[Tensor] = None,
+                 flow_max: float = 20.0, levels=(2, 4, 8, 16)) -> Tensor:
+    """ConditionalDiffusion._loss, denoising_diffusion.py:893-983.  Level 1: NaN-filtered squared error of
+    (image_out, target) (:906-908).  With a flow target (``flow_out`` given) every level L in 2,4,8,16 adds the
+    NaN-filtered squared error between the splat of ``cond`` along the predicted flow at scale L and the splat of the
+    TARGET image along zero flow at scale L (:947-953; the a = b = 0 shifted copies are identities), times L^4 (:965);
+    all terms are concatenated and pooled by one nanmean (:973).  No SNR weight (:975-980), flow term disabled (:961-969)."""
+    terms = [nan_mse(image_out, target, reduction="none")]
+    if flow_out is not None:
+        for level in levels:
+            a = warp_forward_flow(cond[:, :3], flow_out * flow_max, scale=level)
+            b = warp_forward_flow(target[:, :3], torch.zeros_like(flow_out) * flow_max, scale=level)
+            terms.append(nan_mse(a, b, reduction="none") * level ** 4)
+    return torch.nanmean(torch.cat(terms, dim=0))
+
+
+def p_losses_joint(sd, sched, x0: Tensor, cond: Tensor, t: Tensor, noise: Tensor, flow_max: float = 20.0,
+                   prefix: str = "", model_out: Optional[Tensor] = None) -> Tensor:
+    """p_losses with target='joint' (x0 = cat(warped target image, normalised flow), 5 channels):
+    denoising_diffusion.py:823-891 with the ``target.shape[1] == 5`` dispatch of :886-887."""
+    if model_out is None:
+        x_t = q_sample(sched, x0, t, noise)
+        model_out = unet_with_warp(sd, x_t, cond, t, flow_max, True, False, prefix)
+    return pyramid_loss(model_out[:, :3], x0[:, :3], model_out[:, 3:], cond, flow_max)
+
+
+def p_losses_target(sd, sched, x0: Tensor, cond: Tensor, flow_tgt: Tensor, t: Tensor, noise: Tensor,
+                    flow_max: float = 20.0, prefix: str = "", model_out: Optional[Tensor] = None) -> Tensor:
+    """p_losses with target='target' (x0 = warped target image, ``additional_tgt`` = normalised flow): :868-885.
+    The model is called with additional_out=True, its last 2 channels are the flow prediction."""
+    if model_out is None:
+        x_t = q_sample(sched, x0, t, noise)
+        model_out = unet_with_warp(sd, x_t, cond, t, flow_max, False, True, prefix)
+    k = flow_tgt.shape[1]
+    return pyramid_loss(model_out[:, :-k], x0, model_out[:, -k:], cond, flow_max)
+
+
 # --------------------------------------------------------------------------------------
 # Backward warp (warp.py:95-119; arithmetic of torch grid_sample, bilinear/zeros/align_corners)
 # --------------------------------------------------------------------------------------
@@ -581,7 +635,10 @@ def warp_forward_flow(first: Tensor, flow: Tensor, scale: int = 1, set_nans: boo
     weights[torch.any(nans, dim=1)] = 0.0
     offset = [o % scale for o in offset]
     ten_in = torch.cat([first * weights[:, None], weights[:, None]], 1)
-    ret = splat_forward(ten_in, flow, scale, offset[0], offset[1])
+    if torch.is_grad_enabled() and (ten_in.requires_grad or flow.requires_grad):
+        ret = _SplatFn.apply(ten_in, flow, scale, offset[0], offset[1])      # softsplat_func under autograd (:339-733)
+    else:
+        ret = splat_forward(ten_in, flow, scale, offset[0], offset[1])
     img = ret[:, :-1]
     wsum = ret[:, -1:].expand_as(img)
     if set_nans:
