@@ -116,6 +116,11 @@ FD_API int fd_ddpm_step(const float* x, const float* model_out, const float* noi
  * Ctot = Cx + nan_mask + Cc must be <= 9. */
 FD_API int fd_pack_input(const float* x, const float* cond, void* packed, int B, int Cx, int Cc, int H, int W,
                   int nan_mask, void* stream);
+/* Same, with x / cond given as H0 x W0 planes that sit at (pad_top, pad_left) inside the H x W frame the UNet runs on
+ * (H, W multiples of 8: three pixel-unshuffle downsamples, :95-99); the border is replicate-padded on the fly, i.e.
+ * InputPadder(mode='sintel') (future/raft_utils.py:7-25) folded into the packing: 436x1024 -> 440x1024 costs no pass. */
+FD_API int fd_pack_input_pad(const float* x, const float* cond, void* packed, int B, int Cx, int Cc, int H0, int W0,
+                      int pad_top, int pad_left, int H, int W, int nan_mask, void* stream);
 
 /* Weight preparation.  w: fp32 [Cout][Cin][KH][KW] (torch layout) -> bf16 [Cout][K] K-major.
  * kind 0: K index = (ky*KW+kx)*Cin + ci                       (implicit-GEMM tap-major order)
@@ -215,6 +220,10 @@ FD_API int fd_attention(const void* qkv, void* out, int N, int HW, void* stream)
 /* final 1x1 conv (:361,417) 64 -> Cout (<=4) from bf16 NHWC to fp32 NCHW */
 FD_API int fd_final_conv(const void* x, const float* w, const float* bias, float* out, int N, int HW, int Cin,
                   int Cout, void* stream);
+/* Same on an (N,H,W,64) frame, writing only the H0 x W0 window at (pad_top, pad_left) as fp32 (N,Cout,H0,W0): the
+ * InputPadder.unpad crop (future/raft_utils.py:20-25) folded into the store. */
+FD_API int fd_final_conv_crop(const void* x, const float* w, const float* bias, float* out, int N, int H, int W, int Cin,
+                       int Cout, int pad_top, int pad_left, int H0, int W0, void* stream);
 
 /* ==== backward pass: the autograd graph `loss.backward()` walks in training_step (flow_diffuser.py:217-235,
  *      exp_base.py:193-214) for the modules above ================================================ */

@@ -24,7 +24,10 @@ constexpr int kPackPx = 256;       // pixels of one image row per block
 
 __global__ void __launch_bounds__(256) pack_input_kernel(const float* __restrict__ x, const float* __restrict__ cond,
                                                          __nv_bfloat16* __restrict__ packed, int B, int Cx, int Cc,
-                                                         int H, int W, int nan_mask, int segs) {
+                                                         int H, int W, int nan_mask, int segs, int H0, int W0, int pt,
+                                                         int pl) {
+  // x / cond are H0 x W0 planes placed at (pt, pl) inside the H x W frame the UNet runs on; the border is
+  // replicate-padded on the fly (InputPadder(mode='sintel') semantics, future/raft_utils.py:7-25): H0 = H, pt = 0 -> none
   // A block owns kPackPx consecutive pixels of one row: the <= 9 input planes (+3 halo pixels per side) are read
   // once, coalesced, into shared memory; then lane q of every 8-lane group writes the q-th 16-byte granule of its
   // pixel, so a warp store covers 4 pixels x 128 B of contiguous memory.
@@ -34,14 +37,15 @@ __global__ void __launch_bounds__(256) pack_input_kernel(const float* __restrict
   const long row = blockIdx.x / segs;              // b * H + h
   const int b = (int)(row / H), h = (int)(row % H);
   const int w0 = seg * kPackPx;
-  const long HW = (long)H * W;
+  const long HW = (long)H0 * W0;
   const int t = threadIdx.x;
+  const int hs = min(max(h - pt, 0), H0 - 1);
   for (int idx = t; idx < Ctot * (kPackPx + 6); idx += 256) {
     const int c = idx / (kPackPx + 6), i = idx - c * (kPackPx + 6);
     const int w = w0 + i - 3;
     float v = 0.f;
     if (w >= 0 && w < W) {
-      const long p = (long)h * W + w;
+      const long p = (long)hs * W0 + min(max(w - pl, 0), W0 - 1);
       if (c < Cx) {
         v = __ldg(x + ((long)b * Cx + c) * HW + p);
       } else if (nan_mask && c == Cx) {
@@ -408,7 +412,8 @@ __global__ void __launch_bounds__(256) time_proj_kernel(const float* __restrict_
 template <int PER>
 __global__ void __launch_bounds__(256) final_conv_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w,
                                                          const float* __restrict__ bias, float* __restrict__ out, int N,
-                                                         long HW, int Cout) {
+                                                         long HW, int Cout, int W, int H0, int W0, int pt, int pl) {
+  // the H0 x W0 window at (pt, pl) of the H x W frame is written (crop of the internal padding); W0 = W, pt = pl = 0 -> all
   constexpr int Cin = PER * 4;
   const int sub = threadIdx.x & 3;
   float wr[4][PER];
@@ -447,8 +452,9 @@ __global__ void __launch_bounds__(256) final_conv_kernel(const __nv_bfloat16* __
     }
     if (valid && sub < Cout) {       // lane `sub` writes output channel `sub`
       const long n = i / HW, p = i - n * HW;
+      const int hh = (int)(p / W) - pt, ww = (int)(p % W) - pl;
       const float r = sub == 0 ? acc[0] + br[0] : (sub == 1 ? acc[1] + br[1] : (sub == 2 ? acc[2] + br[2] : acc[3] + br[3]));
-      out[(n * Cout + sub) * HW + p] = r;
+      if (hh >= 0 && hh < H0 && ww >= 0 && ww < W0) out[((n * Cout + sub) * H0 + hh) * (long)W0 + ww] = r;
     }
   }
 }
@@ -487,7 +493,21 @@ int fd_pack_input(const float* x, const float* cond, void* packed, int B, int Cx
   const int segs = (W + kPackPx - 1) / kPackPx;
   FD_REQUIRE((long)B * H * segs < (1L << 31), "pack_input: too many rows");
   pack_input_kernel<<<(unsigned)((long)B * H * segs), 256, 0, (cudaStream_t)stream>>>(
-      x, cond, static_cast<__nv_bfloat16*>(packed), B, Cx, Cc, H, W, nan_mask, segs);
+      x, cond, static_cast<__nv_bfloat16*>(packed), B, Cx, Cc, H, W, nan_mask, segs, H, W, 0, 0);
+  FD_LAUNCH_CHECK();
+  return FD_OK;
+}
+
+int fd_pack_input_pad(const float* x, const float* cond, void* packed, int B, int Cx, int Cc, int H0, int W0, int pad_top,
+                      int pad_left, int H, int W, int nan_mask, void* stream) {
+  FD_REQUIRE(x && packed && B > 0 && H0 > 0 && W0 > 0 && Cx > 0 && Cc >= 0, "pack_input_pad: bad argument");
+  FD_REQUIRE(cond != nullptr || Cc == 0, "pack_input_pad: Cc > 0 needs cond");
+  FD_REQUIRE(pad_top >= 0 && pad_left >= 0 && pad_top + H0 <= H && pad_left + W0 <= W, "pack_input_pad: window outside the frame");
+  FD_REQUIRE(Cx + (nan_mask ? 1 : 0) + Cc <= 9, "pack_input_pad: at most 9 input channels (7 taps x 9 <= 64)");
+  const int segs = (W + kPackPx - 1) / kPackPx;
+  FD_REQUIRE((long)B * H * segs < (1L << 31), "pack_input_pad: too many rows");
+  pack_input_kernel<<<(unsigned)((long)B * H * segs), 256, 0, (cudaStream_t)stream>>>(
+      x, cond, static_cast<__nv_bfloat16*>(packed), B, Cx, Cc, H, W, nan_mask, segs, H0, W0, pad_top, pad_left);
   FD_LAUNCH_CHECK();
   return FD_OK;
 }
@@ -585,7 +605,19 @@ int fd_final_conv(const void* x, const float* w, const float* bias, float* out, 
   FD_REQUIRE(x && w && bias && out && N > 0 && HW > 0 && Cin % 8 == 0 && Cout >= 1 && Cout <= 4, "final_conv: bad argument");
   FD_REQUIRE(Cin == 64, "final_conv: the UNet's final conv has 64 input channels (got %d)", Cin);
   final_conv_kernel<16><<<egrid((long)N * HW * 4, 256), 256, 0, (cudaStream_t)stream>>>(
-      static_cast<const __nv_bfloat16*>(x), w, bias, out, N, (long)HW, Cout);
+      static_cast<const __nv_bfloat16*>(x), w, bias, out, N, (long)HW, Cout, HW, 1, HW, 0, 0);
+  FD_LAUNCH_CHECK();
+  return FD_OK;
+}
+
+int fd_final_conv_crop(const void* x, const float* w, const float* bias, float* out, int N, int H, int W, int Cin, int Cout,
+                       int pad_top, int pad_left, int H0, int W0, void* stream) {
+  FD_REQUIRE(x && w && bias && out && N > 0 && H > 0 && W > 0 && Cout >= 1 && Cout <= 4, "final_conv_crop: bad argument");
+  FD_REQUIRE(Cin == 64, "final_conv_crop: the UNet's final conv has 64 input channels (got %d)", Cin);
+  FD_REQUIRE(pad_top >= 0 && pad_left >= 0 && pad_top + H0 <= H && pad_left + W0 <= W && H0 > 0 && W0 > 0,
+             "final_conv_crop: window outside the frame");
+  final_conv_kernel<16><<<egrid((long)N * H * W * 4, 256), 256, 0, (cudaStream_t)stream>>>(
+      static_cast<const __nv_bfloat16*>(x), w, bias, out, N, (long)H * W, Cout, W, H0, W0, pad_top, pad_left);
   FD_LAUNCH_CHECK();
   return FD_OK;
 }

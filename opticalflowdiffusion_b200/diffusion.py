@@ -250,7 +250,16 @@ class ConditionalDiffusion(nn.Module):
         key = (tuple(shape), bool(return_all_timesteps), tuple(external_cond.shape), dev.index)
         if x_T is None:
             x_T = torch.randn(shape, device=dev)
+        # The graph holds raw pointers: to the packed bf16 weights and the concatenated time-MLP weights (both rewritten
+        # IN PLACE by prepare(), so calling it here before every replay is what keeps a replay after an optimiser step or
+        # a checkpoint load current) and to the parameter storages themselves (biases, GroupNorm / LayerNorm gains, the
+        # time MLP), which move when an optimiser flattens them or a module is moved: then the graph is re-captured.
+        self.model.prepare()
+        ptrs = hash(tuple(p.data_ptr() for p in self.model.parameters()))
         entry = self._graphs.get(key)
+        if entry is not None and entry[5] != ptrs:
+            entry = None
+            del self._graphs[key]
         if entry is None:
             s_cond = external_cond.detach().float().contiguous().clone()
             s_x = x_T.detach().to(dev).float().contiguous().clone()
@@ -264,9 +273,9 @@ class ConditionalDiffusion(nn.Module):
             n0 = lib.fd_launch_count()
             with torch.cuda.graph(graph):
                 s_out = self.ddim_sample(shape, return_all_timesteps, s_cond, x_T=s_x)
-            entry = (graph, s_cond, s_x, s_out, int(lib.fd_launch_count() - n0))
+            entry = (graph, s_cond, s_x, s_out, int(lib.fd_launch_count() - n0), ptrs)
             self._graphs[key] = entry
-        graph, s_cond, s_x, s_out, n_kernels = entry
+        graph, s_cond, s_x, s_out, n_kernels, _ = entry
         s_cond.copy_(external_cond)
         s_x.copy_(x_T)
         graph.replay()
@@ -284,8 +293,9 @@ class ConditionalDiffusion(nn.Module):
         else:
             hw = tuple(image_size) if image_size is not None else self.image_size
         shape = (batch_size, self.channels) + hw
+        from .unet import Unet
         if (use_cuda_graph and self.is_ddim_sampling and self.ddim_sampling_eta == 0.0 and additional_tgt is None
-                and external_cond is not None and kw.get("noises") is None):
+                and external_cond is not None and kw.get("noises") is None and isinstance(self.model, Unet)):
             return self._ddim_sample_graphed(shape, return_all_timesteps, external_cond, kw.get("x_T"))
         fn = self.ddim_sample if self.is_ddim_sampling else self.p_sample_loop
         return fn(shape, return_all_timesteps=return_all_timesteps, external_cond=external_cond,

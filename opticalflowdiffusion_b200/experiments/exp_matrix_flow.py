@@ -18,7 +18,7 @@ from ..datasets import SyntheticSintelDataset
 from ..io_formats import SintelFlowDataset, load_checkpoint
 from ..flow_diffuser import FlowDiffuser
 from ..flow_learner import FlowLearner
-from ..parallel import reduce_metrics
+from ..parallel import init_distributed, reduce_metrics, sync_module_from_rank0
 
 
 class MatrixFlowExperiment:
@@ -72,10 +72,13 @@ class MatrixFlowExperiment:
     def train(self, max_steps: Optional[int] = None):
         """exp_base.py:178-214 without Lightning: epochs over the training loader; gradient clipping
         (experiment.training.clipping, :192) and accumulate_grad_batches (:203) as configured."""
-        from ..optim import allreduce_gradients
+        from ..optim import GradSync, allreduce_gradients
         dev = torch.device("cuda", self.local_rank)
         torch.cuda.set_device(dev)
+        distributed = init_distributed(dev)          # WORLD_SIZE > 1: one NCCL process group (DDPStrategy, exp_base.py:198)
         self.algo.to(dev)
+        sync_module_from_rank0(self.algo)            # identical replicas, as DDP broadcasts at construction
+        self._synced = True
         self.algo.train()
         opt = self.algo.configure_optimizers()
         tr = self.cfg.experiment.training
@@ -84,7 +87,20 @@ class MatrixFlowExperiment:
             opt.max_grad_norm = float(clip)
         accum = int(tr.optim.accumulate_grad_batches)
         epochs = int(self.cfg.experiment.epochs)
-        losses, step, epoch = [], 0, 0
+        unet = getattr(self.algo, "unet", None)
+        unet = getattr(unet, "model", unet)          # FlowLearner wraps its UNet
+        if distributed and accum == 1 and hasattr(unet, "forward_train"):
+            # bucketed all-reduce overlapped with the backward; with gradient accumulation the exchange happens once per
+            # optimiser step instead (allreduce_gradients below), like DDP under no_sync()
+            GradSync(opt).attach(unet)
+        if epochs < 0 and max_steps is None:
+            max_steps = tr.get("max_steps") if hasattr(tr, "get") else None
+            if max_steps is None:
+                raise ValueError("experiment.epochs = -1 means 'train until stopped' (Lightning max_epochs=-1): give "
+                                 "experiment.training.max_steps or train(max_steps=...)")
+            max_steps = int(max_steps)
+        from collections import deque
+        losses, step, epoch = deque(maxlen=1024), 0, 0
         # checkpoint / resume (exp_base.py:184-190,213: ModelCheckpoint(every_n_train_steps) + fit(ckpt_path=...))
         ck_cfg = tr.get("checkpointing") if hasattr(tr, "get") else None
         every = int(ck_cfg.get("every_n_train_steps", 0)) if ck_cfg else 0
@@ -98,16 +114,19 @@ class MatrixFlowExperiment:
             loader = self._loader("training", tr)
             if hasattr(loader.sampler, "set_epoch"):
                 loader.sampler.set_epoch(epoch)
+            n_batches = len(loader)
             for i, batch in enumerate(loader):
                 loss = self.algo.training_step(tuple(t.to(dev, non_blocking=True) for t in batch), i)
                 (loss / accum).backward()
-                if (i + 1) % accum == 0:
+                if (i + 1) % accum == 0 or i + 1 == n_batches:      # a short last window is stepped, not carried over
                     allreduce_gradients(opt)
                     opt.step()
                     opt.zero_grad(set_to_none=True)
                     step += 1
                     self.algo.global_step = step
                     losses.append(loss.detach())
+                    if len(losses) == losses.maxlen and step % 256 == 0:
+                        losses = deque((float(x) for x in losses), maxlen=losses.maxlen)    # bounded, off the device
                     if every > 0 and step % every == 0 and self.rank == 0:
                         from ..io_formats import save_checkpoint
                         os.makedirs(ck_dir, exist_ok=True)
@@ -116,15 +135,17 @@ class MatrixFlowExperiment:
                     if max_steps is not None and step - start_step >= max_steps:
                         break
             epoch += 1
-            if max_steps is None and epochs < 0:
-                break          # "epochs: -1" means until stopped in the reference; one pass without a step budget
         return {"train/loss": [float(x) for x in losses], "steps": step - start_step, "global_step": step}
 
     @torch.no_grad()
     def validate(self, max_batches: Optional[int] = None):
         dev = torch.device("cuda", self.local_rank)
         torch.cuda.set_device(dev)
+        distributed = init_distributed(dev)
         self.algo.to(dev)
+        if distributed and not getattr(self, "_synced", False):
+            sync_module_from_rank0(self.algo)
+            self._synced = True
         limit = max_batches or int(self.cfg.experiment.validation.limit_batch)
         out = {}
         for i, batch in enumerate(self._loader("validation", self.cfg.experiment.validation)):

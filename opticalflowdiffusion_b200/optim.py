@@ -6,11 +6,18 @@ all-reduce (exp_base.py:198).
 
 ``FusedAdam`` keeps the parameters it owns as views of ONE flat fp32 buffer (plus flat ``exp_avg`` /
 ``exp_avg_sq``), so a step is two launches of ``libflowdiff.so``: ``fd_sumsq`` (gradient norm, stays on the
-device) and ``fd_adam_step`` (clip coefficient + decay + Adam).  ``allreduce_gradients`` exchanges the flat
-gradient with a single NCCL all-reduce -- 143 MB for the 35.7 M-parameter UNet, ~0.5 ms over NVLink against a
-~100 ms step, so there is nothing to gain from bucketing / overlapping it with the backward pass."""
+device) and ``fd_adam_step`` (clip coefficient + decay + Adam, i.e. the whole post-reduce pass is one kernel).
+
+Gradient exchange: ``GradSync`` is DDP's bucketed all-reduce.  The UNet's backward announces each of its eight
+contiguous gradient buckets as soon as the backward has walked past the bucket's layers (``unet_train.GRAD_GROUPS``,
+reverse layer order); the bucket is all-reduced over NCCL right away, asynchronously, while the rest of the backward
+keeps the SMs busy.  90 % of the 143 MB sit in the deep levels, which finish first; only the last bucket (init_conv,
+time MLP, the two full-resolution levels: ~2 MB) is exchanged after the last backward kernel.  Measured in round 1
+with ONE all-reduce after the backward: 0.28 ms (N = 1) -> 1.86 ms (N = 8) for all-reduce + clip + Adam of a 55 ms step.
+``allreduce_gradients`` is the un-overlapped single-collective form (gradient accumulation, foreign modules)."""
 from __future__ import annotations
 
+import os
 from typing import Callable, Iterable, Optional
 
 import torch
@@ -38,6 +45,7 @@ class FusedAdam(torch.optim.Optimizer):
         self._flat_p: Optional[torch.Tensor] = None
         self._offsets = None
         self._reduced: Optional[torch.Tensor] = None     # flat gradient already exchanged by allreduce_gradients
+        self._presynced = False                          # GradSync exchanged p.grad during the backward
         self.step_count = 0
 
     # ------------------------------------------------------------------ flat storage
@@ -117,6 +125,7 @@ class FusedAdam(torch.optim.Optimizer):
         lib = _lib.load(check_device=True)
         g = self._reduced if self._reduced is not None else self.flat_gradient()
         self._reduced = None
+        self._presynced = False
         grp = self.param_groups[0]
         self.step_count += 1
         st = _lib.stream()
@@ -140,13 +149,82 @@ class FusedAdam(torch.optim.Optimizer):
         return self._sumsq.sqrt() * self.grad_scale
 
 
+class GradSync:
+    """Bucketed, overlapped gradient all-reduce (DDPStrategy's exchange, exp_base.py:198).
+
+    ``attach(unet)`` registers it as the UNet's ``grad_sync``: during ``UnetFunction.backward`` the UNet calls
+    ``bucket_ready(flat, lo, hi)`` when elements [lo, hi) of its flat gradient buffer are final, and ``finish(flat)``
+    after its last kernel.  Each bucket is SUM-all-reduced asynchronously (NCCL runs it on its own stream, ordered
+    after the kernels launched so far); ``finish`` makes the launching stream wait for all of them.  The 1/world mean
+    is folded into the optimiser's ``grad_scale``.  ``comm_dtype=torch.bfloat16`` exchanges a bf16 copy of each bucket
+    (half the bytes; the reference's DDP exchanges fp32, which is the default here)."""
+
+    def __init__(self, optimizer: Optional["FusedAdam"] = None, group=None, comm_dtype: Optional[torch.dtype] = None):
+        self.optimizer, self.group = optimizer, group
+        self.comm_dtype = comm_dtype if comm_dtype not in (None, torch.float32) else None
+        self._pending = []
+        self._stage: Optional[torch.Tensor] = None
+        self.buckets_last_backward = 0
+        self.bytes_last_backward = 0
+
+    def world(self) -> int:
+        if not (dist.is_available() and dist.is_initialized()):
+            return 1
+        return dist.get_world_size(self.group)
+
+    def attach(self, unet) -> "GradSync":
+        unet.grad_sync = self
+        return self
+
+    @staticmethod
+    def detach(unet) -> None:
+        unet.grad_sync = None
+
+    def bucket_ready(self, flat: torch.Tensor, lo: int, hi: int) -> None:
+        if self.world() == 1:
+            return
+        if not self._pending:
+            self.buckets_last_backward = self.bytes_last_backward = 0
+        t = flat[lo:hi]
+        if self.comm_dtype is not None:
+            if self._stage is None or self._stage.numel() != flat.numel() or self._stage.device != flat.device:
+                self._stage = torch.empty(flat.numel(), device=flat.device, dtype=self.comm_dtype)
+            buf = self._stage[lo:hi]
+            buf.copy_(t)
+        else:
+            buf = t
+        work = dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+        self._pending.append((work, lo, hi, buf))
+        self.buckets_last_backward += 1
+        self.bytes_last_backward += buf.numel() * buf.element_size()
+
+    def finish(self, flat: torch.Tensor) -> None:
+        if not self._pending:
+            return
+        for work, lo, hi, buf in self._pending:
+            work.wait()                          # stream-orders the launching stream after the collective
+            if self.comm_dtype is not None:
+                flat[lo:hi].copy_(buf)
+        self._pending = []
+        if self.optimizer is not None:
+            self.optimizer.grad_scale = 1.0 / self.world()
+            self.optimizer._presynced = True     # allreduce_gradients() must not exchange this gradient again
+
+
 def allreduce_gradients(optimizer: FusedAdam, group=None) -> None:
-    """DDP's exchange step: SUM all-reduce of the flat gradient over NCCL (gloo in the CPU tests); the 1/world
-    mean is folded into the optimiser's ``grad_scale``."""
+    """DDP's exchange step in one collective: SUM all-reduce of the flat gradient over NCCL (gloo in the CPU tests); the
+    1/world mean is folded into the optimiser's ``grad_scale``.  No-op when ``GradSync`` already exchanged this
+    gradient bucket by bucket during the backward."""
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1 and not (dist.is_available() and dist.is_initialized()):
+        raise RuntimeError("WORLD_SIZE > 1 but torch.distributed is not initialised: the replicas would train "
+                           "independently (call dist.init_process_group before the first training step)")
     if not (dist.is_available() and dist.is_initialized()):
         return
     world = dist.get_world_size(group)
     if world == 1:
+        return
+    if getattr(optimizer, "_presynced", False):
+        optimizer._presynced = False
         return
     if not optimizer._still_flat():
         optimizer._flatten()

@@ -178,8 +178,16 @@ class Unet(UnetParams, TrainMixin):
             off += lin.weight.shape[0]
             ws.append(lin.weight.detach().float())
             bs.append(lin.bias.detach().float())
-        self._tproj_w = torch.cat(ws, 0).contiguous() if ws else None
-        self._tproj_b = torch.cat(bs, 0).contiguous() if bs else None
+        # written IN PLACE once allocated: a captured CUDA graph of the sampler holds these pointers (diffusion.py)
+        if ws:
+            rows = sum(w.shape[0] for w in ws)
+            if self._tproj_w is None or self._tproj_w.shape[0] != rows or self._tproj_w.device != ws[0].device:
+                self._tproj_w = torch.empty(rows, ws[0].shape[1], device=ws[0].device, dtype=torch.float32)
+                self._tproj_b = torch.empty(rows, device=ws[0].device, dtype=torch.float32)
+            torch.cat(ws, 0, out=self._tproj_w)
+            torch.cat(bs, 0, out=self._tproj_b)
+        else:
+            self._tproj_w = self._tproj_b = None
         self._prepared_versions = ver
 
     # ------------------------------------------------------------------ kernel wrappers
@@ -329,13 +337,10 @@ class Unet(UnetParams, TrainMixin):
         x = x.float()
         cond = external_cond.float() if external_cond is not None else None
         # three 2x pixel-unshuffle downsamples (:95-99) need H, W % 8 == 0 (436 -> 440): replicate-pad like the
-        # repo's own InputPadder(mode='sintel') (future/raft_utils.py:7-25) and crop the prediction back
+        # repo's own InputPadder(mode='sintel') (future/raft_utils.py:7-25) and crop the prediction back -- both folded
+        # into the first / last kernel (fd_pack_input_pad clamps its reads, fd_final_conv_crop writes the window only)
         ph, pw = (-H0) % 8, (-W0) % 8
         pad = (pw // 2, pw - pw // 2, ph // 2, ph - ph // 2)
-        if ph or pw:
-            x = torch.nn.functional.pad(x, pad, mode="replicate")
-            if cond is not None:
-                cond = torch.nn.functional.pad(cond, pad, mode="replicate")
         x = x.contiguous()
         cond = cond.contiguous() if cond is not None else None
         H, W = H0 + ph, W0 + pw
@@ -358,7 +363,8 @@ class Unet(UnetParams, TrainMixin):
 
         # init_conv 7x7 (:297,374) as a 7x1 conv over the horizontally unrolled input
         packed = torch.empty(B, H, W, 64, device=dev, dtype=BF16)
-        _lib.check(lib.fd_pack_input(_lib.ptr(x), _lib.ptr(cond), _lib.ptr(packed), B, Cx, Cc, H, W, int(nan_mask), st))
+        _lib.check(lib.fd_pack_input_pad(_lib.ptr(x), _lib.ptr(cond), _lib.ptr(packed), B, Cx, Cc, H0, W0, pad[2], pad[0],
+                                         H, W, int(nan_mask), st))
         h = self._conv("init_conv", packed)
         del packed
         r = h
@@ -402,13 +408,11 @@ class Unet(UnetParams, TrainMixin):
         h = self._resnet("final_res_block", self.final_res_block, h, r, ss)
         if return_taps:
             taps["final_res_block"] = h
-        out = torch.empty(B, self.out_dim, H, W, device=dev, dtype=torch.float32)
+        out = torch.empty(B, self.out_dim, H0, W0, device=dev, dtype=torch.float32)
         fc = self.final_conv
-        _lib.check(lib.fd_final_conv(_lib.ptr(h), _lib.ptr(fc.weight), _lib.ptr(fc.bias), _lib.ptr(out), B, H * W, self.dim,
-                                     self.out_dim, st))
+        _lib.check(lib.fd_final_conv_crop(_lib.ptr(h), _lib.ptr(fc.weight), _lib.ptr(fc.bias), _lib.ptr(out), B, H, W, self.dim,
+                                          self.out_dim, pad[2], pad[0], H0, W0, st))
         self._stats = None
-        if ph or pw:
-            out = out[:, :, pad[2]:pad[2] + H0, pad[0]:pad[0] + W0].contiguous()
         if return_taps:
             return out, {k: (v if v.dim() == 2 else v.permute(0, 3, 1, 2).float()) for k, v in taps.items()}
         return out

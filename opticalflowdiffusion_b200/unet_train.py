@@ -167,8 +167,78 @@ class TrainMixin:
             blocks.append(blocks[-1] + wt.shape[0])
         ws = {"key": key, "flat": flat, "views": views, "n": len(recs), "blocks": blocks[-1],
               "table": torch.tensor(recs, dtype=torch.int64).to(dev), "blk": torch.tensor(blocks, dtype=torch.int32).to(dev)}
+        # one sub-table per gradient bucket (GRAD_GROUPS): a bucket's weight gradients are unpacked -- and handed to the
+        # gradient exchange -- as soon as the backward has walked past its layers, not at the end of the backward
+        per = {}
+        for (name, _), rec in zip(convs, recs):
+            per.setdefault(self._grad_group_of(name), []).append(rec)
+        ws["groups"] = {}
+        for gname, grecs in per.items():
+            gblocks = [0]
+            for r in grecs:
+                gblocks.append(gblocks[-1] + r[3])
+            ws["groups"][gname] = (torch.tensor(grecs, dtype=torch.int64).to(dev), torch.tensor(gblocks, dtype=torch.int32).to(dev),
+                                   len(grecs), gblocks[-1])
         self._gw_ws = ws
         return ws
+
+    # ------------------------------------------------------------------ gradient buckets
+    # Buckets of the flat gradient in the order the backward completes them (reverse layer order).  Every bucket is a
+    # CONTIGUOUS range of the flat buffer (parameters are laid out in module order: init_conv, time_mlp, downs, ups, mid,
+    # final) -- the unit of DDP's bucketed all-reduce (exp_base.py:198), overlapped with the rest of the backward by
+    # optim.GradSync.  The deep levels hold 90 % of the parameters and finish first; the full-resolution levels, whose
+    # backward takes longest, hold almost none, so only the small "front" bucket is exchanged after the last kernel.
+    GRAD_GROUPS = ("final", "ups.23", "ups.1", "ups.0", "mid", "downs.3", "downs.2", "front")
+
+    @staticmethod
+    def _grad_group_of(name: str) -> str:
+        if name.startswith(("final_res_block", "final_conv")):
+            return "final"
+        if name.startswith(("ups.2", "ups.3")):
+            return "ups.23"
+        if name.startswith(("ups.1", "ups.0", "downs.3", "downs.2")):
+            return name[:name.index(".", name.index(".") + 1)]
+        if name.startswith("mid_"):
+            return "mid"
+        return "front"            # init_conv, time_mlp, downs.0, downs.1
+
+    def _grad_group_ranges(self):
+        """{group: (lo, hi)} element ranges of the flat gradient buffer."""
+        gb = self._gb
+        cached = getattr(self, "_gg_ranges", None)
+        if cached is not None and cached[0] is gb:
+            return cached[1]
+        base = gb.flat.data_ptr()
+        ranges = {}
+        for pname, p in self.named_parameters():
+            g = self._grad_group_of(pname)
+            v = gb.of(p)
+            lo = (v.data_ptr() - base) // 4
+            hi = (lo + v.numel() + 3) // 4 * 4
+            cur = ranges.get(g)
+            ranges[g] = (lo, hi) if cur is None else (min(cur[0], lo), max(cur[1], hi))
+        hi_all = gb.flat.numel()
+        spans = sorted(ranges.values())
+        assert spans[0][0] == 0 and all(a[1] == b[0] for a, b in zip(spans[:-1], spans[1:])) and spans[-1][1] <= hi_all, spans
+        self._gg_ranges = (gb, ranges)
+        return ranges
+
+    def _t_group_boundary(self, tape: "Tape", group: str):
+        """Recorded BEFORE a group's first forward op, hence run AFTER its last backward op: unpack the group's packed
+        weight gradients (+ weight-standardisation backward) into the flat buffer and announce the bucket."""
+        lib, st = self._lib, self._st
+
+        def bwd():
+            ws = self._gw_ws
+            ent = ws["groups"].get(group)
+            if ent is not None:
+                _lib.check(lib.fd_prep_weight_bwd_batch(_lib.ptr(ent[0]), _lib.ptr(ent[1]), ent[2], ent[3], self.WS_EPS, st))
+            sync = getattr(self, "grad_sync", None)
+            if sync is not None:
+                lo, hi = self._grad_group_ranges()[group]
+                sync.bucket_ready(self._gb.flat, lo, hi)
+
+        tape.record(bwd)
 
     # ------------------------------------------------------------------ recorded ops
     def _t_conv(self, tape: Tape, name: str, src0: Tensor, src1: Optional[Tensor] = None,
@@ -261,6 +331,15 @@ class TrainMixin:
     def _t_resnet(self, tape: Tape, name: str, rb, x0: Tensor, x1: Optional[Tensor], ss: Tensor, dss: Tensor,
                   need_dgrad: bool = True) -> Tensor:
         st1, st2 = self._next_stats(), self._next_stats()
+        if rb.mlp is not None and ss is not None:
+            lin, temb, gb, lib, st = rb.mlp[1], tape.temb, self._gb, self._lib, self._st
+
+            def mlp_bwd(o=self._tproj_off[name]):     # runs after block1's GroupNorm backward wrote this block's d(scale, shift)
+                _lib.check(lib.fd_linear_bwd_w(dss.data_ptr() + 4 * o, dss.shape[1], _lib.ptr(temb), self.time_dim,
+                                               _lib.ptr(gb.of(lin.weight)), _lib.ptr(gb.of(lin.bias)), dss.shape[0],
+                                               lin.weight.shape[0], self.time_dim, 1, st))
+
+            tape.record(mlp_bwd)
         h1 = self._t_conv(tape, name + ".block1.proj", x0, x1, stats=st1, need_dgrad=need_dgrad)
         a1 = self._t_gn_silu(tape, h1, st1, rb.block1.norm, ss, dss, self._tproj_off[name], None, rb.block1.proj.bias)
         h2 = self._t_conv(tape, name + ".block2.proj", a1, stats=st2)
@@ -345,6 +424,7 @@ class TrainMixin:
         tape = Tape(self)
         gb = self._gb
         ss = dss = None
+        self._t_group_boundary(tape, "front")        # first record = last to run: after init_conv and the time MLP
         if self.time_in:
             time = time.to(torch.int64).contiguous()
 
@@ -361,13 +441,11 @@ class TrainMixin:
             _lib.check(lib.fd_time_proj(_lib.ptr(temb), _lib.ptr(self._tproj_w), _lib.ptr(self._tproj_b), _lib.ptr(ss), B,
                                         self.time_dim, J, st))
 
+            tape.temb = temb
+
             def time_bwd():
+                # (each ResnetBlock's mlp Linear gradient was taken inside its own block: _t_resnet.mlp_bwd)
                 td = self.time_dim
-                for name, rb in self._resblocks:          # each ResnetBlock.mlp Linear reads its own column range of dss
-                    lin = rb.mlp[1]
-                    o, k = self._tproj_off[name], lin.weight.shape[0]
-                    _lib.check(lib.fd_linear_bwd_w(dss.data_ptr() + 4 * o, J, _lib.ptr(temb), td, _lib.ptr(gb.of(lin.weight)),
-                                                   _lib.ptr(gb.of(lin.bias)), B, k, td, 1, st))
                 dtemb = torch.empty(B, td, device=dev, dtype=torch.float32)
                 _lib.check(lib.fd_linear_bwd_x(_lib.ptr(dss), J, _lib.ptr(self._tproj_w), _lib.ptr(temb), td, _lib.ptr(dtemb), td,
                                                B, J, td, 1, st))
@@ -390,16 +468,21 @@ class TrainMixin:
         skips: List[Tensor] = []
         n_levels = len(self.downs)
         for i, (b1, b2, attn, down) in enumerate(self.downs):
+            if i >= 2:
+                self._t_group_boundary(tape, f"downs.{i}")
             h = self._t_resnet(tape, f"downs.{i}.0", b1, h, None, ss, dss)
             skips.append(h)
             h = self._t_resnet(tape, f"downs.{i}.1", b2, h, None, ss, dss)
             h = self._t_linear_attention(tape, f"downs.{i}.2", attn, h)
             skips.append(h)
             h = self._t_conv(tape, f"downs.{i}.3", h)
+        self._t_group_boundary(tape, "mid")
         h = self._t_resnet(tape, "mid_block1", self.mid_block1, h, None, ss, dss)
         h = self._t_attention(tape, "mid_attn", self.mid_attn, h)
         h = self._t_resnet(tape, "mid_block2", self.mid_block2, h, None, ss, dss)
         for i, (b1, b2, attn, up) in enumerate(self.ups):
+            if i <= 2:
+                self._t_group_boundary(tape, ("ups.0", "ups.1", "ups.23")[i])
             h = self._t_resnet(tape, f"ups.{i}.0", b1, h, skips.pop(), ss, dss)
             h = self._t_resnet(tape, f"ups.{i}.1", b2, h, skips.pop(), ss, dss)
             h = self._t_linear_attention(tape, f"ups.{i}.2", attn, h)
@@ -419,6 +502,7 @@ class TrainMixin:
                 del up_t
             else:
                 h = self._t_conv(tape, f"ups.{i}.3", h)
+        self._t_group_boundary(tape, "final")
         h = self._t_resnet(tape, "final_res_block", self.final_res_block, h, r, ss, dss)
         out = torch.empty(B, self.out_dim, H, W, device=dev, dtype=torch.float32)
         fc = self.final_conv
@@ -440,9 +524,7 @@ class TrainMixin:
             tape.g[id(h_last)] = dh
             ws = self._wgrad_workspace()
             ws["flat"].zero_()
-            tape.run()
-            _lib.check(lib.fd_prep_weight_bwd_batch(_lib.ptr(ws["table"]), _lib.ptr(ws["blk"]), ws["n"], ws["blocks"],
-                                                    self.WS_EPS, st))
+            tape.run()          # the group boundaries unpack the packed weight gradients bucket by bucket (_t_group_boundary)
 
         if ph or pw:
             out = out[:, :, pad[2]:pad[2] + H0, pad[0]:pad[0] + W0].contiguous()
@@ -472,6 +554,9 @@ class UnetFunction(torch.autograd.Function):
         with _lib.nvtx_range("unet.backward"):
             ctx.run_backward(dout)
         ctx.run_backward = None
+        sync = getattr(unet, "grad_sync", None)
+        if sync is not None:
+            sync.finish(gb.flat)          # the launching stream waits for the bucket all-reduces issued during the backward
         # hand autograd its own copy of the flat buffer's views: p.grad accumulation (+=) must not alias the
         # buffer the next backward zero-fills
         flat = gb.flat.clone()

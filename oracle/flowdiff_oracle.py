@@ -117,7 +117,7 @@ def _full_attention(sd, p: str, x: Tensor, heads: int = 4, dim_head: int = 32) -
 def time_embedding(sd, t: Tensor, dim: int = 64, prefix: str = "") -> Tensor:
     """SinusoidalPosEmb + time_mlp, denoising_diffusion.py:144-151, 319-324."""
     half = dim // 2
-    freq = torch.exp(torch.arange(half) * -(math.log(10000) / (half - 1)))
+    freq = torch.exp(torch.arange(half, device=t.device) * -(math.log(10000) / (half - 1)))
     e = t[:, None] * freq[None, :]
     e = torch.cat((e.sin(), e.cos()), dim=-1)
     e = F.linear(e, sd[prefix + "time_mlp.1.weight"], sd[prefix + "time_mlp.1.bias"])
@@ -279,7 +279,7 @@ def ddim_update(sched, x: Tensor, x0_raw: Tensor, time: int, time_next: int, eta
     model_predictions(clip_x_start=True) -> :653-656, then ddim_sample :752-767.
     Returns (next x, clipped x0)."""
     b = x.shape[0]
-    t = torch.full((b,), time, dtype=torch.long)
+    t = torch.full((b,), time, dtype=torch.long, device=x.device)
     x0 = torch.clamp(x0_raw, min=-1.0, max=1.0)
     eps = predict_noise_from_start(sched, x, t, x0)
     if time_next < 0:
@@ -296,7 +296,7 @@ def ddim_update(sched, x: Tensor, x0_raw: Tensor, time: int, time_next: int, eta
 def ddpm_update(sched, x: Tensor, x0_raw: Tensor, time: int, noise: Optional[Tensor]) -> Tuple[Tensor, Tensor]:
     """One ancestral step: p_mean_variance + p_sample, denoising_diffusion.py:666-698, 613-623."""
     b = x.shape[0]
-    t = torch.full((b,), time, dtype=torch.long)
+    t = torch.full((b,), time, dtype=torch.long, device=x.device)
     x0 = torch.clamp(x0_raw, -1.0, 1.0)
     mean = _ext(sched["posterior_mean_coef1"], t) * x0 + _ext(sched["posterior_mean_coef2"], t) * x
     logvar = _ext(sched["posterior_log_variance_clipped"], t)
@@ -314,7 +314,7 @@ def ddim_sample(sd, sched, x_T: Tensor, cond: Tensor, total_timesteps: int, samp
     x0s = []
     model = model or (lambda xx, cc, tt: unet_forward(sd, xx, cc, tt, prefix))
     for time, time_next in zip(times[:-1], times[1:]):
-        t = torch.full((x.shape[0],), time, dtype=torch.long)
+        t = torch.full((x.shape[0],), time, dtype=torch.long, device=x.device)
         out = model(x, cond, t)
         x, x0 = ddim_update(sched, x, out, time, time_next)
         traj.append(x)
@@ -331,7 +331,7 @@ def ddpm_sample(sd, sched, x_T: Tensor, cond: Tensor, total_timesteps: int, nois
     traj = [x]
     model = model or (lambda xx, cc, tt: unet_forward(sd, xx, cc, tt, prefix))
     for i, time in enumerate(reversed(range(total_timesteps))):
-        t = torch.full((x.shape[0],), time, dtype=torch.long)
+        t = torch.full((x.shape[0],), time, dtype=torch.long, device=x.device)
         out = model(x, cond, t)
         x, _ = ddpm_update(sched, x, out, time, noises[i] if time > 0 else None)
         traj.append(x)

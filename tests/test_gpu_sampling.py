@@ -162,3 +162,41 @@ def test_matrix_flow_resolution_1024x2048():
     assert a.shape == (1, 2, 1024, 2048) and torch.isfinite(a).all()
     assert float(a.abs().max()) <= 1.0 + 1e-6                      # x0 prediction is clamped to [-1, 1] (DDIM, :653-656)
     assert (a - b).abs().max().item() < 5e-3
+
+
+def test_cuda_graph_follows_weight_updates():
+    """A captured DDIM graph must not replay stale weights: after an in-place parameter update, after an
+    optimiser step that re-homes the parameters in flat buffers, and after load_state_dict, the replay equals the eager
+    sampler run with the current weights."""
+    m = make_algo(["algorithm.target=flow", "algorithm.sampling_timesteps=3", "algorithm.lr=1e-2"], seed=5)
+    B, H, W = 1, 32, 64
+    cond = (O.synthetic_frames(B, H, W, seed=8) * 2 - 1).cuda()
+    x_T = torch.randn(B, 2, H, W, generator=torch.Generator().manual_seed(9)).cuda()
+
+    def both():
+        g = m.model.sample(B, external_cond=cond, x_T=x_T, use_cuda_graph=True)
+        e = m.model.sample(B, external_cond=cond, x_T=x_T)
+        return g, e
+
+    g0, e0 = both()
+    assert (g0 - e0).abs().max().item() < 5e-3
+    with torch.no_grad():                                   # in-place update: same storages, new values
+        for p in m.unet.parameters():
+            p.mul_(1.05)
+    g1, e1 = both()
+    assert (g1 - e1).abs().max().item() < 5e-3
+    assert (g1 - g0).abs().max().item() > 1e-3              # the weights really changed the sample
+    opt = m.configure_optimizers()                           # FusedAdam: parameters move into one flat buffer
+    img = O.synthetic_frames(B, H, W, seed=1).cuda()
+    flow = (torch.randn(B, 2, H, W, generator=torch.Generator().manual_seed(3)) * 5).cuda()
+    loss = m.training_step((img, img, flow), 0)
+    loss.backward()
+    opt.step()
+    opt.zero_grad(set_to_none=True)
+    g2, e2 = both()
+    assert (g2 - e2).abs().max().item() < 5e-3
+    assert (g2 - g1).abs().max().item() > 1e-4
+    sd = {k: v.clone() * 0.9 for k, v in m.state_dict().items() if v.dtype.is_floating_point and k.startswith("unet.")}
+    m.load_state_dict(sd, strict=False)
+    g3, e3 = both()
+    assert (g3 - e3).abs().max().item() < 5e-3
