@@ -24,14 +24,56 @@ import torch
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-H, W, BATCH, DDIM_STEPS, TIMESTEPS = 436, 1024, 8, 50, 1000
-CONV_GF_PER_SAMPLE = 1590.3      # algorithmic conv GFLOP per UNet forward at 440x1024
-FWD_GF_PER_SAMPLE = 1635.28      # whole forward (conv + attention matmuls)
-CONV_DRAM_BYTES_PER_FORWARD = 38.411e9   # measured DRAM traffic of the conv launches of one batch-8 forward (profiles/r1_forward_traffic_v5.txt)
-CONFIG = {"workload": "flow_diffuser DDIM-50 sampling, Sintel-shaped synthetic 436x1024 (UNet runs on 440x1024), "
-                      "target=flow, batch 8 per GPU, random-init weights seed 0",
-          "batch_per_gpu": BATCH, "ddim_steps": DDIM_STEPS, "timesteps": TIMESTEPS, "parallelism": "batch-sharded replicas",
-          "l2": "working set >> L2: every bf16 activation tensor is 461 MB at full resolution, no reuse between steps"}
+DDIM_STEPS, TIMESTEPS = 50, 1000
+# --config selects the workload; the default is BASELINE.json configs[1] (the configuration `metric` is quoted on),
+# "matrix_flow_1024x2048" is configs[4] (the matrix_flow experiment's resolution; the reference itself cannot run it: its
+# N x N attention matrix is 17 GB per sample, denoising_diffusion.py:263-265)
+WORKLOADS = {
+    "ddim50_436x1024": dict(
+        H=436, W=1024, batch=8, metric="flows/sec DDIM-50 @436x1024",
+        conv_gf=1590.3,        # algorithmic conv GFLOP per UNet forward at 440x1024
+        fwd_gf=1635.28,        # whole forward (conv + attention matmuls)
+        attn_gf=25.4,          # mid attention, N = 7040 tokens
+        workload="flow_diffuser DDIM-50 sampling, Sintel-shaped synthetic 436x1024 (UNet runs on 440x1024), "
+                 "target=flow, batch 8 per GPU, random-init weights seed 0",
+        l2="working set >> L2: every bf16 activation tensor is 461 MB at full resolution, no reuse between steps"),
+    "matrix_flow_1024x2048": dict(
+        H=1024, W=2048, batch=2, metric="flows/sec DDIM-50 @1024x2048",
+        conv_gf=1590.3 * (1024 * 2048) / (440 * 1024),      # appendix A: M scales linearly with pixels (x4.655)
+        fwd_gf=8043.13,
+        attn_gf=549.8,         # mid attention, N = 32768 tokens
+        workload="matrix_flow experiment resolution: flow_diffuser DDIM-50 sampling, synthetic 1024x2048 frame pairs, "
+                 "target=flow, batch 2 per GPU, random-init weights seed 0",
+        l2="working set >> L2: every bf16 activation tensor is 537 MB at full resolution, no reuse between steps"),
+}
+WL = WORKLOADS["ddim50_436x1024"]
+H, W, BATCH = WL["H"], WL["W"], WL["batch"]
+CONV_GF_PER_SAMPLE, FWD_GF_PER_SAMPLE = WL["conv_gf"], WL["fwd_gf"]
+CONFIG = {}
+
+
+def select_workload(name: str):
+    global WL, H, W, BATCH, CONV_GF_PER_SAMPLE, FWD_GF_PER_SAMPLE, CONFIG
+    WL = WORKLOADS[name]
+    H, W, BATCH = WL["H"], WL["W"], WL["batch"]
+    CONV_GF_PER_SAMPLE, FWD_GF_PER_SAMPLE = WL["conv_gf"], WL["fwd_gf"]
+    CONFIG = {"workload": WL["workload"], "name": name, "batch_per_gpu": BATCH, "ddim_steps": DDIM_STEPS,
+              "timesteps": TIMESTEPS, "parallelism": "batch-sharded replicas", "l2": WL["l2"]}
+
+
+def conv_traffic():
+    """DRAM bytes (ncu dram__bytes_read.sum + dram__bytes_write.sum) of the conv launches of ONE forward of the
+    selected workload, from the committed capture of the shipped code (scripts/agg_traffic.py -> profiles/), or None."""
+    path = os.path.join(ROOT, "profiles", "r2_forward_traffic.json")
+    try:
+        with open(path) as f:
+            d = json.load(f)
+        ent = d.get(CONFIG.get("name", ""))
+        if ent:
+            return float(ent["conv_dram_bytes"]), "profiles/r2_forward_traffic.json: " + ent.get("source", "")
+    except Exception:  # noqa: BLE001
+        pass
+    return None, "no ncu capture of this workload committed"
 
 
 def load_peaks():
@@ -81,8 +123,14 @@ class ClockSampler:
 # CPU reference arm / cpu_baseline: the oracle's fp32 restatement of the reference algorithm
 # (the reference tree itself cannot travel to the GPU box) on all host threads.
 # ------------------------------------------------------------------------------------------------
-def cpu_reference_step_seconds(steps: int, warmup: int):
-    """Each step = ONE of the 50 DDIM steps of ONE 436x1024 sample (UNet forward + update); flows/s = 1/(50 t)."""
+CPU_SAMPLE_HW = {"ddim50_436x1024": (436, 1024), "matrix_flow_1024x2048": (256, 512)}
+
+
+def cpu_reference_step_seconds(steps: int, warmup: int, keep_io: bool = False):
+    """Each step = ONE of the 50 DDIM steps of ONE sample (UNet forward + update) -> flows/s = 1 / (50 t).
+    At 1024x2048 the reference's N x N attention matrix is 17 GB per sample (it cannot run there), so
+    the sample is a 256x512 crop and the time is scaled by the pixel ratio (x16; the attention term grows faster, so the
+    scaled time is a LOWER bound of the reference's cost).  Returns (seconds per full-size step, pixel scale, io)."""
     from oracle import flowdiff_oracle as O
     from opticalflowdiffusion_b200.unet_params import UnetParams
     # all host cores this process may use (torchrun pins OMP_NUM_THREADS=1 by default)
@@ -93,10 +141,12 @@ def cpu_reference_step_seconds(steps: int, warmup: int):
     torch.manual_seed(0)
     sd = UnetParams(64, channels=5, out_dim=2).state_dict()
     sched = O.make_schedule(TIMESTEPS)
-    cond = O.replicate_pad_to_multiple(O.synthetic_frames(1, H, W, seed=0) * 2 - 1)[0]
+    h, w = CPU_SAMPLE_HW[CONFIG["name"]]
+    scale = (H * W) / float(h * w)
+    cond = O.replicate_pad_to_multiple(O.synthetic_frames(1, h, w, seed=0) * 2 - 1)[0]
     x = torch.randn(1, 2, cond.shape[-2], cond.shape[-1], generator=torch.Generator().manual_seed(1234))
     times = O.ddim_times(TIMESTEPS, DDIM_STEPS)
-    ts = []
+    ts, out = [], None
     with torch.no_grad():
         for i in range(warmup + steps):
             t0 = time.perf_counter()
@@ -105,24 +155,168 @@ def cpu_reference_step_seconds(steps: int, warmup: int):
             O.ddim_update(sched, x, out, times[0], times[1])
             if i >= warmup:
                 ts.append(time.perf_counter() - t0)
-    return ts
+    io = (sd, x, cond, times[0], out) if keep_io else None
+    return ts, scale, io
+
+
+def cpu_sample_text(scale: float) -> str:
+    h, w = CPU_SAMPLE_HW[CONFIG["name"]]
+    txt = f"one of the {DDIM_STEPS} DDIM steps of ONE {h}x{w} sample (UNet forward + update) on the host cores, x{DDIM_STEPS} extrapolated"
+    if scale != 1.0:
+        txt += f", x{scale:.0f} by pixel count to {H}x{W} (the reference cannot allocate its attention matrix at that size)"
+    return txt
 
 
 def run_reference(args, rank: int):
     if rank != 0:
         return
-    ts = cpu_reference_step_seconds(args.steps, min(args.warmup, 1))
+    warm = max(0, args.warmup)
+    ts, scale, _ = cpu_reference_step_seconds(args.steps, warm)
     threads = torch.get_num_threads()
     t = sum(ts) / len(ts)
-    value = 1.0 / (DDIM_STEPS * t)
-    sample = "one of the 50 DDIM steps of ONE 436x1024 sample per step (UNet forward + update), x50 extrapolated"
-    line = {"impl": "reference", "metric": "flows/sec DDIM-50 @436x1024", "value": value, "unit": "flows/s",
-            "n_gpus": args.gpus, "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": t * 1e3 * DDIM_STEPS * BATCH,
+    value = 1.0 / (DDIM_STEPS * t * scale)
+    sample = cpu_sample_text(scale)
+    # ms_per_step is what one timed step of THIS run took (the bounded sample), so steps x ms_per_step fits the driver's
+    # clock; the whole-workload figure (one batch of BATCH flows) is extrapolated and labelled as such
+    line = {"impl": "reference", "metric": WL["metric"], "value": value, "unit": "flows/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": warm, "ms_per_step": t * 1e3,
+            "extrapolated": True, "sample_seconds_per_forward": t,
+            "ms_per_step_full_workload_extrapolated": t * scale * 1e3 * DDIM_STEPS * BATCH,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": CONFIG,
             "cpu_baseline": {"value": value, "unit": "flows/s", "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "flows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
+    _emit(line)
+
+
+# ------------------------------------------------------------------------------------------------
+# The GPU LIBRARY bar: the reference algorithm as PyTorch eager ops -- cuDNN convolutions,
+# cuBLAS / ATen attention, ATen norms -- on the SAME B200, TF32 on as main.py:79-80 sets it, and once under bf16 autocast
+# (Lightning's "bf16-mixed", exp_base.py:204).  The oracle's functional restatement is the same op sequence as the
+# reference's nn.Modules (denoising_diffusion.py:81-417); it runs here as the thing being *compared against*, never as a
+# fallback of the product path.
+# ------------------------------------------------------------------------------------------------
+def gpu_library_baseline(dev, full_loops: int = 1):
+    from oracle import flowdiff_oracle as O
+    from opticalflowdiffusion_b200.unet_params import UnetParams
+    torch.backends.cuda.matmul.allow_tf32 = True          # torch.set_float32_matmul_precision("high"), main.py:79-80
+    torch.backends.cudnn.allow_tf32 = True
+    torch.backends.cudnn.benchmark = True                 # give the library its best algorithm per shape
+    torch.manual_seed(0)
+    sd = {k: v.to(dev) for k, v in UnetParams(64, channels=5, out_dim=2).state_dict().items()}
+    sched = {k: v.to(dev) for k, v in O.make_schedule(TIMESTEPS).items()}
+    cond = O.replicate_pad_to_multiple(O.synthetic_frames(BATCH, H, W, seed=100) * 2 - 1)[0].to(dev)
+    x_T = torch.randn(BATCH, 2, cond.shape[-2], cond.shape[-1], device=dev)
+    pairs = list(zip(O.ddim_times(TIMESTEPS, DDIM_STEPS)[:-1], O.ddim_times(TIMESTEPS, DDIM_STEPS)[1:]))
+    res = {"what": "reference algorithm as PyTorch %s eager ops (cuDNN %s / cuBLAS) on this GPU, batch %d, %dx%d, DDIM-%d, "
+                   "cudnn.benchmark on" % (torch.__version__, torch.backends.cudnn.version(), BATCH, cond.shape[-2], cond.shape[-1],
+                                           DDIM_STEPS),
+           "unit": "flows/s"}
+
+    def loop(autocast: bool, n_steps: int):
+        x = x_T.clone()
+        with torch.no_grad():
+            for tm, tn in pairs[:n_steps]:
+                t = torch.full((BATCH,), tm, device=dev, dtype=torch.long)
+                with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+                    out = O.unet_forward(sd, x, cond, t)
+                x, _ = O.ddim_update(sched, x, out.float(), tm, tn)
+        return x
+
+    for name, autocast in (("tf32", False), ("bf16_autocast", True)):
+        try:
+            loop(autocast, 3)                 # warm-up: cuDNN algorithm search, allocator
+            torch.cuda.synchronize()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            for _ in range(full_loops):
+                loop(autocast, DDIM_STEPS)
+            e.record()
+            torch.cuda.synchronize()
+            sec = s.elapsed_time(e) * 1e-3 / full_loops
+            res[name] = {"value": BATCH / sec, "ms_per_step": sec * 1e3, "ms_per_forward": sec * 1e3 / DDIM_STEPS,
+                         "tflops": FWD_GF_PER_SAMPLE * BATCH * DDIM_STEPS / sec / 1e3}
+        except torch.OutOfMemoryError as ex:  # the N x N attention matrix (17 GB per sample at 1024x2048)
+            res[name] = {"unavailable": "out of memory: " + str(ex).split("\n")[0][:160]}
+        torch.cuda.empty_cache()
+    res["peak_mem_gib"] = torch.cuda.max_memory_allocated(dev) / 2 ** 30
+    torch.backends.cudnn.benchmark = False
+    return res
+
+
+def gpu_library_train_baseline(dev, batch: int):
+    """The same bar for the training step (BASELINE configs[2]): loss + backward (autograd through the eager ops) + Adam at
+    368x768, batch `batch`, TF32 and bf16 autocast."""
+    from oracle import flowdiff_oracle as O
+    from opticalflowdiffusion_b200.unet_params import UnetParams
+    torch.backends.cuda.matmul.allow_tf32 = True
+    torch.backends.cudnn.allow_tf32 = True
+    torch.backends.cudnn.benchmark = True
+    res = {"what": "p_losses (target=flow) + backward + torch.optim.Adam through PyTorch eager ops on this GPU, 368x768",
+           "unit": "samples/s"}
+    sched = {k: v.to(dev) for k, v in O.make_schedule(TIMESTEPS).items()}
+    for name, autocast in (("tf32", False), ("bf16_autocast", True)):
+        b = batch
+        while b >= 1:
+            try:
+                torch.manual_seed(0)
+                sd = {k: v.to(dev).requires_grad_(True) for k, v in UnetParams(64, channels=5, out_dim=2).state_dict().items()}
+                opt = torch.optim.Adam(list(sd.values()), lr=1e-5, weight_decay=1e-6)
+                cond = (O.synthetic_frames(b, TRAIN_H, TRAIN_W, seed=200) * 2 - 1).to(dev)
+                x0 = torch.clamp(torch.randn(b, 2, TRAIN_H, TRAIN_W, device=dev) * 0.25, -1, 1)
+                noise = torch.randn(b, 2, TRAIN_H, TRAIN_W, device=dev)
+                t = torch.randint(0, TIMESTEPS, (b,), device=dev)
+
+                def step():
+                    with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+                        loss = O.p_losses_flow(sd, sched, x0, cond, t, noise)
+                    loss.backward()
+                    torch.nn.utils.clip_grad_norm_(list(sd.values()), 100.0)
+                    opt.step()
+                    opt.zero_grad(set_to_none=True)
+
+                for _ in range(2):
+                    step()
+                torch.cuda.synchronize()
+                s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s.record()
+                for _ in range(3):
+                    step()
+                e.record()
+                torch.cuda.synchronize()
+                sec = s.elapsed_time(e) * 1e-3 / 3
+                res[name] = {"value": b / sec, "ms_per_step": sec * 1e3, "batch": b,
+                             "peak_mem_gib": torch.cuda.max_memory_allocated(dev) / 2 ** 30}
+                break
+            except torch.OutOfMemoryError:
+                res.setdefault("notes", []).append(f"{name}: batch {b} does not fit in memory through autograd of the eager ops")
+                b //= 2
+            finally:
+                sd = opt = None
+                torch.cuda.empty_cache()
+                torch.cuda.reset_peak_memory_stats(dev)
+    torch.backends.cudnn.benchmark = False
+    return res
+
+
+def run_torch_gpu(args, rank: int, local_rank: int):
+    """--impl torch-gpu: the GPU library bar as its own arm (rank 0 only)."""
+    if rank != 0:
+        return
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    res = gpu_library_baseline(dev, full_loops=max(1, args.steps))
+    clk = clocks.stop()
+    best = res.get("tf32", {})
+    line = {"impl": "torch-gpu", "metric": WL["metric"], "value": best.get("value"), "unit": "flows/s", "n_gpus": 1,
+            "steps": max(1, args.steps), "warmup": 1, "ms_per_step": best.get("ms_per_step"), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "tf32", "data": "synthetic", "config": CONFIG, "clocks": clk,
+            "gpu_library_baseline": res, "gpu_launches": 0}
+    if CONFIG["name"] == "ddim50_436x1024" and not args.skip_train:
+        line["gpu_library_train_baseline"] = gpu_library_train_baseline(dev, args.train_batch)
     _emit(line)
 
 
@@ -222,19 +416,49 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     fwd_s = s.elapsed_time(e) * 1e-3 / RF_REPS
     torch.set_grad_enabled(True)
 
-    train = None
-    if not args.skip_train:
+    # cpu_baseline (rank 0, N = 1): one DDIM step of one sample through the oracle on the host cores; its output doubles as
+    # the checker of a teacher-forced GPU forward on the very same input -> "parity" (the oracle is the checker here, the
+    # GPU forward compared with it is the product path)
+    cpu_base = parity = None
+    if world == 1 and rank == 0 and not args.no_cpu_baseline:
+        ts, scale, (sd_o, x_o, cond_o, t_o, out_o) = cpu_reference_step_seconds(1, 1, keep_io=True)
+        tcpu = sum(ts) / len(ts)
+        cpu_base = {"value": 1.0 / (DDIM_STEPS * tcpu * scale), "unit": "flows/s", "cores": torch.get_num_threads(),
+                    "kind": "port", "sample": cpu_sample_text(scale) + " after one warm-up"}
+        with torch.no_grad():
+            got = algo.unet(x_o.to(dev), cond_o.to(dev), torch.full((1,), t_o, device=dev, dtype=torch.long)).cpu()
+        err = (got - out_o).abs()
+        epe = torch.sqrt(((got.clamp(-1, 1) - out_o.clamp(-1, 1)) * 20.0).pow(2).sum(1)).mean().item()
+        parity = {"kind": "teacher-forced x0 prediction of one DDIM step (t = %d) vs the fp32 CPU oracle on the same input" % t_o,
+                  "shape": list(x_o.shape), "max_abs_err": err.max().item(), "mean_abs_err": err.mean().item(),
+                  "epe_px": epe, "tolerance": "max |err| <= 3e-2 on [-1, 1] data (tests/test_gpu_headline_parity.py)",
+                  "free_running": "DDIM-50 436x1024 EPE vs the oracle trajectory: tests/test_gpu_headline_parity.py, "
+                                  "numbers in profiles/r2_parity_headline.json"}
+        del sd_o, x_o, cond_o, out_o, got
+    default_wl = CONFIG["name"] == "ddim50_436x1024"
+    lib_base = None
+    if world == 1 and rank == 0 and not args.no_gpu_baseline:
         del algo
+        algo = None
         torch.cuda.empty_cache()
+        lib_base = gpu_library_baseline(dev)
+        if default_wl and not args.skip_train:
+            lib_base["train"] = gpu_library_train_baseline(dev, args.train_batch)
+    train = None
+    if not args.skip_train and default_wl:
+        algo = None
+        torch.cuda.empty_cache()
+        torch.cuda.reset_peak_memory_stats(dev)
         train = run_train_leg(args, cfg.algorithm, rank, world, dev)
     if rank != 0:
         return
     peaks = load_peaks()
+    traffic, traffic_src = conv_traffic()
     flows = world * BATCH * args.steps
     value = flows / t_res
     conv_tf = CONV_GF_PER_SAMPLE * BATCH * 1e9 / conv_s / 1e12
     line = {
-        "metric": "flows/sec DDIM-50 @436x1024", "value": value, "unit": "flows/s", "n_gpus": world, "steps": args.steps,
+        "metric": WL["metric"], "value": value, "unit": "flows/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": t_res / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": CONFIG,
         "e2e": {"value": flows / t_e2e, "unit": "flows/s", "h2d_bytes_per_step": cond_host.numel() * 4 + flow_host.numel() * 4,
@@ -243,17 +467,21 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         "clocks": clk,
         "roofline": {"bound": "tensor", "kernel": "conv_igemm_kernel (tcgen05 implicit GEMM, all %d conv launches of one forward)" % conv_launches,
                      "achieved": conv_tf, "peak": peaks["tf_sustained"], "unit": "TFLOP/s", "frac": conv_tf / peaks["tf_sustained"],
-                     "traffic": CONV_DRAM_BYTES_PER_FORWARD, "traffic_source": "profiles/r1_forward_traffic_v5.txt: ncu dram__bytes_read.sum + "
-                     "dram__bytes_write.sum summed over the conv launches of ONE forward at this batch (same unit as `achieved`: one "
-                     "forward's conv launches); algorithmic FLOPs, not bytes, bound these kernels", "peak_source": peaks["src"] + " (sustained: the kernel is timed inside a long step)",
-                     "note": "5 of these launches (the full-resolution block2.proj strip convs) also apply the preceding GroupNorm + SiLU "
-                             "to their input strips (fd_conv3x3_gnsilu_in) unless FD_FUSE_GN=0; their time is counted, the activation FLOPs are not",
+                     "traffic": traffic, "traffic_source": traffic_src + " (ncu dram__bytes_read.sum + dram__bytes_write.sum summed over "
+                     "the conv launches of ONE forward at this batch: the unit of `achieved`; algorithmic FLOPs, not bytes, bound these kernels)",
+                     "peak_source": peaks["src"] + " (sustained: the kernel is timed inside a long step)",
+                     "note": "launches that also apply the preceding GroupNorm + SiLU to their input (fused operand transform) "
+                             "carry that work in their time; the activation FLOPs are not counted",
                      "conv_share_of_forward": conv_s / fwd_s, "forward_ms": fwd_s * 1e3,
                      "whole_step_tflops": FWD_GF_PER_SAMPLE * DDIM_STEPS * 1e9 * value / 1e12},
     }
+    if parity is not None:
+        line["parity"] = parity
+    if lib_base is not None:
+        line["gpu_library_baseline"] = lib_base
     if train is not None:
         line["train"] = train
-    if world == 1 and not args.skip_warp:
+    if world == 1 and not args.skip_warp and default_wl:
         # BASELINE configs[3]: fused backward-warp + photometric / EPE microbench, 8x2x436x1024 flow over 3-channel frames,
         # L2 flushed between iterations; GB/s over the ALGORITHMIC bytes (fwd 40 B/px, bwd 60 B/px)
         sys.path.insert(0, os.path.join(ROOT, "scripts"))
@@ -263,16 +491,9 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                                    if k in ("photo_epe_fwd", "photo_epe_bwd", "backwarp_fwd", "backwarp_bwd", "splat_fwd",
                                             "splat_flowgrad")}
         line["warp_microbench"]["hbm_peak_GBps"] = peaks["hbm"]
-    if world == 1 and not args.no_cpu_baseline:
-        ts = cpu_reference_step_seconds(1, 1)
-        tcpu = sum(ts) / len(ts)
-        line["cpu_baseline"] = {"value": 1.0 / (DDIM_STEPS * tcpu), "unit": "flows/s", "cores": torch.get_num_threads(),
-                                "kind": "port",
-                                "sample": "one of the 50 DDIM steps of ONE 436x1024 sample (UNet forward + update) on the host "
-                                          "cores after one warm-up, x50 extrapolated"}
+    if cpu_base is not None:
+        line["cpu_baseline"] = cpu_base
     _emit(line)
-    if world > 1:
-        pass
 
 
 TRAIN_H, TRAIN_W = 368, 768
@@ -315,8 +536,8 @@ def run_train_leg(args, algo_cfg, rank: int, world: int, dev):
     import torch.distributed as dist
     from opticalflowdiffusion_b200 import FlowDiffuser, _lib
     from opticalflowdiffusion_b200.datasets import synthetic_frames
-    from opticalflowdiffusion_b200.optim import allreduce_gradients
-    from opticalflowdiffusion_b200.parallel import max_over_ranks
+    from opticalflowdiffusion_b200.optim import GradSync, allreduce_gradients
+    from opticalflowdiffusion_b200.parallel import max_over_ranks, sync_module_from_rank0
     lib = _lib.load()
     B = args.train_batch
     torch.manual_seed(0)
@@ -324,6 +545,12 @@ def run_train_leg(args, algo_cfg, rank: int, world: int, dev):
     algo.train()
     opt = algo.configure_optimizers()
     opt.max_grad_norm = 100.0                                   # experiment=matrix_flow: training.clipping = 100
+    sync = None
+    if world > 1:
+        sync_module_from_rank0(algo)
+        if not args.no_overlap:
+            # DDP's bucketed exchange, overlapped with the backward (optim.GradSync); --no-overlap = one all-reduce after it
+            sync = GradSync(opt, comm_dtype=torch.bfloat16 if args.grad_bf16 else None).attach(algo.unet)
     g = torch.Generator().manual_seed(7 + rank)
     img_h = synthetic_frames(B, TRAIN_H, TRAIN_W, seed=200 + rank).pin_memory()
     tgt_h = synthetic_frames(B, TRAIN_H, TRAIN_W, seed=300 + rank).pin_memory()
@@ -421,8 +648,13 @@ def run_train_leg(args, algo_cfg, rank: int, world: int, dev):
             "phases_ms": {"augment+preprocess": ev_aug.elapsed_time(ev[0]), "forward+loss": ev[0].elapsed_time(ev[1]), "backward": ev[1].elapsed_time(ev[2]),
                           "allreduce+clip+adam": ev[2].elapsed_time(ev[3])},
             "tensor_tflops": TRAIN_GF_PER_SAMPLE * value / 1e3 / world, "peak_mem_gib": peak_mem, "cpu_baseline": cpu,
+            "grad_exchange": ({"kind": "bucketed all-reduce overlapped with the backward (optim.GradSync)",
+                               "buckets": sync.buckets_last_backward, "bytes": sync.bytes_last_backward,
+                               "wire_dtype": "bf16" if args.grad_bf16 else "f32"} if sync is not None else
+                              {"kind": "none (1 GPU)" if world == 1 else "one all-reduce after the backward"}),
             "config": "flow_diffuser training step, target=flow, synthetic 368x768 crops, augmentation ON (GpuAugmentor: "
-                      "reference Augmentor semantics, decisions on the host, arithmetic in 4 launches), Adam lr 1e-5 wd 1e-6, clip 100, gradient all-reduce over NCCL when n_gpus > 1"}
+                      "reference Augmentor semantics, decisions on the host, arithmetic in 4 launches), Adam lr 1e-5 wd 1e-6, clip 100, "
+                      "gradient all-reduce over NCCL when n_gpus > 1"}
 
 
 _REAL_STDOUT = None
@@ -444,8 +676,13 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "torch-gpu"])
+    ap.add_argument("--config", default="ddim50_436x1024", choices=sorted(WORKLOADS),
+                    help="workload: BASELINE configs[1] (default, the headline) or configs[4] (matrix_flow resolution)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-baseline", action="store_true", help="omit the PyTorch-eager (cuDNN / cuBLAS) bar on the same GPU")
+    ap.add_argument("--no-overlap", action="store_true", help="training leg: one all-reduce after the backward instead of GradSync")
+    ap.add_argument("--grad-bf16", action="store_true", help="training leg: exchange gradient buckets as bf16")
     ap.add_argument("--graph", type=int, default=1, help="replay the DDIM loop as one CUDA graph (1) or launch eagerly (0)")
     ap.add_argument("--train-batch", type=int, default=8, help="per-GPU batch of the training leg (368x768 crops)")
     ap.add_argument("--skip-warp", action="store_true", help="omit the warp + photometric/EPE microbench (BASELINE configs[3])")
@@ -461,8 +698,12 @@ def main():
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    select_workload(args.config)
     if args.impl == "reference":
         run_reference(args, rank)
+        return
+    if args.impl == "torch-gpu":
+        run_torch_gpu(args, rank, local_rank)
         return
     run_ours(args, rank, world, local_rank)
     if world > 1:
