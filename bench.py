@@ -545,12 +545,12 @@ def run_train_leg(args, algo_cfg, rank: int, world: int, dev):
     algo.train()
     opt = algo.configure_optimizers()
     opt.max_grad_norm = 100.0                                   # experiment=matrix_flow: training.clipping = 100
-    sync = None
+    gsync = None
     if world > 1:
         sync_module_from_rank0(algo)
         if not args.no_overlap:
             # DDP's bucketed exchange, overlapped with the backward (optim.GradSync); --no-overlap = one all-reduce after it
-            sync = GradSync(opt, comm_dtype=torch.bfloat16 if args.grad_bf16 else None).attach(algo.unet)
+            gsync = GradSync(opt, comm_dtype=torch.bfloat16 if args.grad_bf16 else None).attach(algo.unet)
     g = torch.Generator().manual_seed(7 + rank)
     img_h = synthetic_frames(B, TRAIN_H, TRAIN_W, seed=200 + rank).pin_memory()
     tgt_h = synthetic_frames(B, TRAIN_H, TRAIN_W, seed=300 + rank).pin_memory()
@@ -649,8 +649,8 @@ def run_train_leg(args, algo_cfg, rank: int, world: int, dev):
                           "allreduce+clip+adam": ev[2].elapsed_time(ev[3])},
             "tensor_tflops": TRAIN_GF_PER_SAMPLE * value / 1e3 / world, "peak_mem_gib": peak_mem, "cpu_baseline": cpu,
             "grad_exchange": ({"kind": "bucketed all-reduce overlapped with the backward (optim.GradSync)",
-                               "buckets": sync.buckets_last_backward, "bytes": sync.bytes_last_backward,
-                               "wire_dtype": "bf16" if args.grad_bf16 else "f32"} if sync is not None else
+                               "buckets": gsync.buckets_last_backward, "bytes": gsync.bytes_last_backward,
+                               "wire_dtype": "bf16" if args.grad_bf16 else "f32"} if gsync is not None else
                               {"kind": "none (1 GPU)" if world == 1 else "one all-reduce after the backward"}),
             "config": "flow_diffuser training step, target=flow, synthetic 368x768 crops, augmentation ON (GpuAugmentor: "
                       "reference Augmentor semantics, decisions on the host, arithmetic in 4 launches), Adam lr 1e-5 wd 1e-6, clip 100, "

@@ -156,6 +156,14 @@ FD_API int fd_conv_igemm_ex(const void* src0, int C0, const void* src1, int C1, 
                      const float* bias, const void* residual, void* out, double* gn_stats,
                      int N, int H, int W, int Cout, int KH, int KW, int pad_h, int pad_w, int mode,
                      int out_mode, void* stream);
+/* fd_conv_igemm whose residual input is a RAW conv output h2 that still needs its GroupNorm(8) + SiLU
+ * (ResnetBlock with a res_conv, :212-214: out = res_conv(x) + silu(GroupNorm(h2))): the epilogue folds
+ * res_stats ([N][8][2] sum / sum of squares of h2, as accumulated by the producing conv), gamma, beta into per-channel
+ * coefficients and applies them to the residual on the fly -- the activated tensor never goes through HBM. */
+FD_API int fd_conv_igemm_rt(const void* src0, int C0, const void* src1, int C1, const void* wpacked, const float* bias,
+                     const void* residual_raw, const double* res_stats, const float* res_gamma, const float* res_beta,
+                     float eps, void* out, int N, int H, int W, int Cout, int KH, int KW, int pad_h, int pad_w, void* stream);
+
 
 /* 3x3 / pad 1 / 64 -> 64 channel convolution whose INPUT is activated on the fly:
  *   out = conv3x3(silu(GroupNorm(src) * (scale + 1) + shift)) (+ bias, + residual, + GroupNorm statistics of out)

@@ -34,7 +34,22 @@ struct EpiCtx {
   int shuffle_cq;               // > 0: pixel-shuffle store (dgrad of Downsample): map_out is (Cq, 2, W, 2, H), Cq = Cout / 4
   int dbg;                      // diagnostics (FD_CONV_DBG): 8 = barrier handshakes only, no epilogue work
   int tempty_remote;            // != 0 (CTA pairs, non-leader): "accumulator drained" arrives on the LEADER CTA's barrier
+  // Residual transform (ResnetBlock with a res_conv, :212-214: out = res_conv(x) + silu(GroupNorm(h2))): when rt_stats is
+  // set, `residual` is the RAW conv output h2 of block2.proj and the epilogue applies block2's GroupNorm + SiLU to it
+  // on the fly, so the activated tensor never goes through HBM (one read of h2 instead of read + write + read).
+  const double* rt_stats;       // [N][8][2] (sum, sum of squares) of the residual tensor per (sample, group), or null
+  const float* rt_gamma;        // [Cout]
+  const float* rt_beta;         // [Cout]
+  float rt_eps;
+  float* s_rt;                  // [2 accumulator-stage parities][2][BLOCK_N]: folded a[c], b[c] of the current (image, N-tile)
 };
+
+// silu(z) = z sigmoid(z) = h + h tanh(h), h = z / 2: one MUFU op (tanh.approx, 2^-11 relative; outputs are bf16)
+__device__ __forceinline__ float epi_silu_half(float h) {
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+  return fmaf(h, t, h);
+}
 
 // arrive on the mbarrier at the same shared-memory offset in CTA `rank` of the cluster
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t rank) {
@@ -126,7 +141,25 @@ __device__ __forceinline__ void conv_epilogue(const EpiCtx& ec, NextTile next_ti
       }
       float* bias_s = s_bias + (as & 1) * BLOCK_N;
       for (int i = et; i < BLOCK_N; i += kEpiThreads) bias_s[i] = ec.bias ? __ldg(ec.bias + n0 + i) : 0.f;
-      // (the slab barrier below also publishes the bias)
+      float* rt_s = ec.s_rt + (as & 1) * 2 * BLOCK_N;
+      if (ec.rt_stats != nullptr) {
+        // same folding as gn_silu_kernel (double-precision mean / variance), pre-scaled by 1/2 for epi_silu_half
+        const int cpg = ec.Cout >> 3;
+        const double cnt = (double)ec.H * (double)ec.W * (double)cpg;
+        for (int i = et; i < BLOCK_N; i += kEpiThreads) {
+          const int c = n0 + i;
+          const int g = c / cpg;
+          const double s = ec.rt_stats[((long)img * 8 + g) * 2], ss = ec.rt_stats[((long)img * 8 + g) * 2 + 1];
+          const double mean = s / cnt;
+          double var = ss / cnt - mean * mean;
+          if (var < 0.0) var = 0.0;
+          const float rstd = (float)(1.0 / sqrt(var + (double)ec.rt_eps));
+          const float ga = __ldg(ec.rt_gamma + c) * rstd;
+          rt_s[i] = 0.5f * ga;
+          rt_s[BLOCK_N + i] = 0.5f * (__ldg(ec.rt_beta + c) - (float)mean * ga);
+        }
+      }
+      // (the slab barrier below also publishes the bias and the folded coefficients)
 
       mbar_wait(ec.tfull0 + 8u * as, aphase);
       tc_fence_after();
@@ -163,11 +196,25 @@ __device__ __forceinline__ void conv_epilogue(const EpiCtx& ec, NextTile next_ti
           for (int q = 0; q < 4; ++q) {
             const uint4 r4 = __ldg(reinterpret_cast<const uint4*>(rrow + c) + q);
             const uint32_t rw[4] = {r4.x, r4.y, r4.z, r4.w};
+            if (ec.rt_stats != nullptr) {
+              const float4 a0 = *reinterpret_cast<const float4*>(rt_s + c + q * 8), a1 = *reinterpret_cast<const float4*>(rt_s + c + q * 8 + 4);
+              const float4 b0 = *reinterpret_cast<const float4*>(rt_s + BLOCK_N + c + q * 8),
+                           b1 = *reinterpret_cast<const float4*>(rt_s + BLOCK_N + c + q * 8 + 4);
+              const float aa[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+              const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float2 f = fd_unpack_bf16(rw[e]);
-              v[q * 8 + e * 2] += f.x;
-              v[q * 8 + e * 2 + 1] += f.y;
+              for (int e = 0; e < 4; ++e) {
+                const float2 f = fd_unpack_bf16(rw[e]);
+                v[q * 8 + e * 2] += epi_silu_half(fmaf(aa[e * 2], f.x, bb[e * 2]));
+                v[q * 8 + e * 2 + 1] += epi_silu_half(fmaf(aa[e * 2 + 1], f.y, bb[e * 2 + 1]));
+              }
+            } else {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 f = fd_unpack_bf16(rw[e]);
+                v[q * 8 + e * 2] += f.x;
+                v[q * 8 + e * 2 + 1] += f.y;
+              }
             }
           }
         }

@@ -56,6 +56,11 @@ struct ConvParams {
   int shuffle_cq;     // > 0: pixel-shuffle store, out is (N, 2H, 2W, Cout/4)
   int dbg;            // FD_CONV_DBG (diagnostics only, results are garbage): 1 = skip A loads, 2 = skip B loads, 4 = skip MMAs,
                       // 8 = skip the epilogue's work (barrier handshakes only)
+  // residual transform (fd_conv_igemm_rt): `residual` is a raw conv output whose GroupNorm + SiLU the epilogue applies
+  const double* rt_stats;
+  const float* rt_gamma;
+  const float* rt_beta;
+  float rt_eps;
 };
 
 // SH ("store heavy"): few K-blocks per tile (1x1 convs), so the epilogue / output stores dominate: shallow operand
@@ -67,7 +72,8 @@ struct Cfg {
   static constexpr int kStages = SH ? 3 : (BLOCK_N == 64 ? 7 : (BLOCK_N == 128 ? 6 : 4));
   static constexpr int kStoreBufs = SH ? (BLOCK_N / 64 > 2 ? BLOCK_N / 64 : 2) : (BLOCK_N == 64 ? 2 : 1);   // staging slabs
   static constexpr int kTmemCols = 2 * BLOCK_N;
-  static constexpr int kTailBytes = 256 /*barriers*/ + 2 * BLOCK_N * 4 /*bias*/ + kEpiWarps * 16 * 4 /*stats*/ + 64;
+  static constexpr int kTailBytes = 256 /*barriers*/ + 2 * BLOCK_N * 4 /*bias*/ + kEpiWarps * 16 * 4 /*stats*/ + 64 +
+                                    4 * BLOCK_N * 4 /*residual-transform coefficients*/;
   static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + kStoreBufs * kSlabBytes + kTailBytes;
 };
 
@@ -96,6 +102,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
   float* s_bias = reinterpret_cast<float*>(gtail);                       // [2][BLOCK_N]
   float* s_stats = reinterpret_cast<float*>(gtail + 2 * BLOCK_N * 4);    // [8 warps][16]
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(gtail + 2 * BLOCK_N * 4 + kEpiWarps * 16 * 4);
+  float* s_rt = reinterpret_cast<float*>(gtail + 2 * BLOCK_N * 4 + kEpiWarps * 16 * 4 + 64);        // [2][2][BLOCK_N]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -264,6 +271,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
     ec.shuffle_cq = p.shuffle_cq;
     ec.tempty_remote = 0;
     ec.dbg = kDiag ? p.dbg : 0;
+    ec.rt_stats = p.rt_stats; ec.rt_gamma = p.rt_gamma; ec.rt_beta = p.rt_beta; ec.rt_eps = p.rt_eps; ec.s_rt = s_rt;
     conv_epilogue<BLOCK_N, GPT, NBUF>(ec, [&](int iter, EpiTile& t) {
       const int tile = blockIdx.x + iter * gridDim.x;
       if (tile >= p.total_tiles) return false;
@@ -346,7 +354,7 @@ struct PairCfg {
   static constexpr int kStoreBufs = MT == 2 ? 1 : 2;             // MT = 2: the fifth ring stage is worth more than a second slab
   static constexpr int kAcc = 2 * MT;                               // accumulator stages
   static constexpr int kTmemCols = kAcc * BLOCK_N;
-  static constexpr int kTailBytes = 256 + 2 * BLOCK_N * 4 + kEpiWarps * 16 * 4 + 64;
+  static constexpr int kTailBytes = 256 + 2 * BLOCK_N * 4 + kEpiWarps * 16 * 4 + 64 + 4 * BLOCK_N * 4;
   static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + kStoreBufs * kSlabBytes + kTailBytes;
   static_assert(kTmemCols <= 512, "accumulators do not fit tensor memory");
 };
@@ -375,6 +383,7 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_
   float* s_bias = reinterpret_cast<float*>(gtail);
   float* s_stats = reinterpret_cast<float*>(gtail + 2 * BLOCK_N * 4);
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(gtail + 2 * BLOCK_N * 4 + kEpiWarps * 16 * 4);
+  float* s_rt = reinterpret_cast<float*>(gtail + 2 * BLOCK_N * 4 + kEpiWarps * 16 * 4 + 64);        // [2][2][BLOCK_N]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -552,6 +561,7 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_
     ec.shuffle_cq = p.shuffle_cq;
     ec.tempty_remote = rank != 0;
     ec.dbg = kDiag ? p.dbg : 0;
+    ec.rt_stats = p.rt_stats; ec.rt_gamma = p.rt_gamma; ec.rt_beta = p.rt_beta; ec.rt_eps = p.rt_eps; ec.s_rt = s_rt;
     conv_epilogue<BLOCK_N, GPT, NBUF, NACC>(ec, [&](int iter, EpiTile& t) {
       const int st = pair + (iter / MT) * npairs;
       if (st >= super_tiles) return false;
@@ -630,6 +640,11 @@ int fd_conv3x3_strip_launch(const void* src0, int C0, const void* src1, int C1, 
                             void* out, double* gn_stats, int N, int H, int W, int base_offset_mode,
                             cudaStream_t st);   // fd_conv_strip.cu
 
+static int conv_igemm_impl(const void* src0, int C0, const void* src1, int C1, const void* wpacked, const float* bias,
+                           const void* residual, void* out, double* gn_stats, int N, int H, int W, int Cout, int KH, int KW,
+                           int pad_h, int pad_w, int mode, int out_mode, const double* rt_stats, const float* rt_gamma,
+                           const float* rt_beta, float rt_eps, void* stream);
+
 extern "C" {
 
 int fd_conv_igemm(const void* src0, int C0, const void* src1, int C1, const void* wpacked, const float* bias,
@@ -642,6 +657,25 @@ int fd_conv_igemm(const void* src0, int C0, const void* src1, int C1, const void
 int fd_conv_igemm_ex(const void* src0, int C0, const void* src1, int C1, const void* wpacked, const float* bias,
                      const void* residual, void* out, double* gn_stats, int N, int H, int W, int Cout, int KH, int KW,
                      int pad_h, int pad_w, int mode, int out_mode, void* stream) {
+  return conv_igemm_impl(src0, C0, src1, C1, wpacked, bias, residual, out, gn_stats, N, H, W, Cout, KH, KW, pad_h, pad_w, mode,
+                         out_mode, nullptr, nullptr, nullptr, 0.f, stream);
+}
+
+int fd_conv_igemm_rt(const void* src0, int C0, const void* src1, int C1, const void* wpacked, const float* bias,
+                     const void* residual_raw, const double* res_stats, const float* res_gamma, const float* res_beta, float eps,
+                     void* out, int N, int H, int W, int Cout, int KH, int KW, int pad_h, int pad_w, void* stream) {
+  FD_REQUIRE(residual_raw && res_stats && res_gamma && res_beta, "conv_igemm_rt: null pointer");
+  FD_REQUIRE(Cout % 64 == 0 && (Cout / 8) > 0, "conv_igemm_rt: Cout=%d", Cout);
+  return conv_igemm_impl(src0, C0, src1, C1, wpacked, bias, residual_raw, out, nullptr, N, H, W, Cout, KH, KW, pad_h, pad_w, 0, 0,
+                         res_stats, res_gamma, res_beta, eps, stream);
+}
+
+}  // extern "C"
+
+static int conv_igemm_impl(const void* src0, int C0, const void* src1, int C1, const void* wpacked, const float* bias,
+                           const void* residual, void* out, double* gn_stats, int N, int H, int W, int Cout, int KH, int KW,
+                           int pad_h, int pad_w, int mode, int out_mode, const double* rt_stats, const float* rt_gamma,
+                           const float* rt_beta, float rt_eps, void* stream) {
   FD_REQUIRE(out_mode == 0 || out_mode == 1, "conv_igemm: out_mode %d", out_mode);
   FD_REQUIRE(out_mode == 0 || (mode == 0 && KH == 1 && KW == 1 && pad_h == 0 && pad_w == 0 && C1 == 0 &&
                                residual == nullptr && gn_stats == nullptr && Cout % 256 == 0),
@@ -664,7 +698,7 @@ int fd_conv_igemm_ex(const void* src0, int C0, const void* src1, int C1, const v
     }
     const bool chans_ok = (C0 == 64 && (C1 == 0 || C1 == 64)) || (C0 == 128 && C1 == 0);
     if (strip_mode > 0 && mode == 0 && KH == 3 && KW == 3 && pad_h == 1 && pad_w == 1 && chans_ok && Cout == 64 &&
-        W >= 128 && out_mode == 0)
+        W >= 128 && out_mode == 0 && rt_stats == nullptr)
       return fd_conv3x3_strip_launch(src0, C0, src1, C1, wpacked, bias, residual, out, gn_stats, N, H, W, strip_mode,
                                      (cudaStream_t)stream);
   }
@@ -682,6 +716,7 @@ int fd_conv_igemm_ex(const void* src0, int C0, const void* src1, int C1, const v
   p.bias = bias;
   p.residual = static_cast<const __nv_bfloat16*>(residual);
   p.gn_stats = gn_stats;
+  p.rt_stats = rt_stats; p.rt_gamma = rt_gamma; p.rt_beta = rt_beta; p.rt_eps = rt_eps;
   CUtensorMap ma0, ma1, mb, mo;
   TileShape ts;
   if (mode == 0) {
@@ -690,7 +725,7 @@ int fd_conv_igemm_ex(const void* src0, int C0, const void* src1, int C1, const v
       // no halo: rows of all images merge; the real (h, w) geometry is kept for the shuffled store
       n = 1;
       h = N * H;
-    } else if (KH == 1 && KW == 1 && pad_h == 0 && pad_w == 0 && gn_stats == nullptr) {
+    } else if (KH == 1 && KW == 1 && pad_h == 0 && pad_w == 0 && gn_stats == nullptr && rt_stats == nullptr) {
       // 1x1: no halo, so every pixel of the batch is one long row -> full 128-pixel tiles for any W
       FD_REQUIRE((long)N * H * W < (1L << 31), "conv_igemm: too many pixels");
       w = N * H * W;
@@ -805,5 +840,3 @@ int fd_conv_igemm_ex(const void* src0, int C0, const void* src1, int C1, const v
   if (block_n == 128) return stats ? launch<128, 8>(ma0, ma1, mb, mo, p, sms, st) : launch<128, 0>(ma0, ma1, mb, mo, p, sms, st);
   return stats ? launch<64, 8>(ma0, ma1, mb, mo, p, sms, st) : launch<64, 0>(ma0, ma1, mb, mo, p, sms, st);
 }
-
-}  // extern "C"

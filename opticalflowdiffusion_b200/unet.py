@@ -52,6 +52,10 @@ class Unet(UnetParams, TrainMixin):
     # two versions of the in-kernel transform were slower than the separate pass).  FD_FUSE_GN=0
     # selects the two-pass form.
     FUSE_GN_INPUT = os.environ.get("FD_FUSE_GN", "1") != "0"
+    # block2's GroupNorm + SiLU applied to the residual input inside the res_conv's epilogue (fd_conv_igemm_rt, inference
+    # path): the 9 ResnetBlocks that have a res_conv (ups.*, final_res_block) lose their second gn_silu pass -- 4.4 GB of
+    # HBM traffic per batch-8 forward at 440x1024.  FD_FUSE_GN_RES=0 selects the two-pass form.
+    FUSE_GN_RESIDUAL = os.environ.get("FD_FUSE_GN_RES", "1") != "0"
     WS_EPS = 1e-5       # WeightStandardizedConv2d with fp32 input (:107)
     LN_EPS = 1e-5       # LayerNorm with fp32 input (:122)
 
@@ -230,6 +234,25 @@ class Unet(UnetParams, TrainMixin):
             ev[1].record()
         return out
 
+    def _conv_res_gn(self, name: str, src0: Tensor, src1: Optional[Tensor], raw: Tensor, raw_stats: Tensor, norm) -> Tensor:
+        """res_conv(x) + silu(GroupNorm(raw)) (:212-214) in one launch: the GroupNorm apply rides in the conv's epilogue."""
+        pc = self._convs[name]
+        n, h, w, c0 = src0.shape
+        c1 = src1.shape[-1] if src1 is not None else 0
+        out = torch.empty(n, h, w, pc.cout, device=src0.device, dtype=BF16)
+        timing = getattr(self, "_conv_timing", None)
+        if timing is not None:
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            timing.append((name, 2.0 * n * h * w * pc.cout * pc.w.shape[1], ev))
+            ev[0].record()
+        _lib.check(self._lib.fd_conv_igemm_rt(_lib.ptr(src0), c0, _lib.ptr(src1), c1, _lib.ptr(pc.w), _lib.ptr(pc.bias),
+                                              _lib.ptr(raw), _lib.ptr(raw_stats), _lib.ptr(norm.weight), _lib.ptr(norm.bias),
+                                              self.GN_EPS, _lib.ptr(out), n, h, w, pc.cout, pc.kh, pc.kw, pc.pad[0], pc.pad[1],
+                                              self._st))
+        if timing is not None:
+            ev[1].record()
+        return out
+
     def _gn_silu(self, x: Tensor, stats: Tensor, norm, ss: Optional[Tensor], ss_off: int,
                  residual: Optional[Tensor]) -> Tensor:
         n, h, w, c = x.shape
@@ -260,6 +283,8 @@ class Unet(UnetParams, TrainMixin):
             a1 = self._gn_silu(h1, st1, rb.block1.norm, ss, self._tproj_off[name], None)
             h2 = self._conv(name + ".block2.proj", a1, stats=st2)
         if (name + ".res_conv") in self._convs:
+            if self.FUSE_GN_RESIDUAL:
+                return self._conv_res_gn(name + ".res_conv", x0, x1, h2, st2, rb.block2.norm)
             a2 = self._gn_silu(h2, st2, rb.block2.norm, None, 0, None)
             return self._conv(name + ".res_conv", x0, x1, residual=a2)
         assert x1 is None

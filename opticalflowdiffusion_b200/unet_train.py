@@ -242,8 +242,14 @@ class TrainMixin:
 
     # ------------------------------------------------------------------ recorded ops
     def _t_conv(self, tape: Tape, name: str, src0: Tensor, src1: Optional[Tensor] = None,
-                residual: Optional[Tensor] = None, stats: Optional[Tensor] = None, need_dgrad: bool = True) -> Tensor:
-        out = self._conv(name, src0, src1, residual, stats)
+                residual: Optional[Tensor] = None, stats: Optional[Tensor] = None, need_dgrad: bool = True,
+                res_gn=None) -> Tensor:
+        """``res_gn = (h2, stats2, norm, producing conv's bias)``: the residual is silu(GroupNorm(h2)), applied inside the
+        conv's epilogue (fd_conv_igemm_rt); its backward is the GroupNorm + SiLU backward with this conv's dy as upstream."""
+        if res_gn is not None:
+            out = self._conv_res_gn(name, src0, src1, res_gn[0], res_gn[1], res_gn[2])
+        else:
+            out = self._conv(name, src0, src1, residual, stats)
         pc = self._convs[name]
         lib, st, gb = self._lib, self._st, self._gb
 
@@ -254,6 +260,14 @@ class TrainMixin:
             c1 = src1.shape[-1] if src1 is not None else 0
             if residual is not None:
                 tape.add_grad(residual, dy)
+            if res_gn is not None:
+                h2, st2, norm, conv_bias = res_gn
+                dh = torch.empty_like(h2)
+                wsb = torch.empty(lib.fd_gn_silu_bwd_workspace_floats(n, cout), device=h2.device, dtype=torch.float32)
+                _lib.check(lib.fd_gn_silu_bwd(_lib.ptr(h2), _lib.ptr(dy), _lib.ptr(st2), _lib.ptr(norm.weight), _lib.ptr(norm.bias),
+                                              None, 0, _lib.ptr(dh), _lib.ptr(gb.of(norm.weight)), _lib.ptr(gb.of(norm.bias)), None,
+                                              _lib.ptr(gb.of(conv_bias)), _lib.ptr(wsb), n, h * w, cout, self.GN_EPS, st))
+                tape.add_grad(h2, dh)
             mod = pc.src
             if mod.bias is not None and stats is None:      # with statistics the GroupNorm backward delivers it
                 _lib.check(lib.fd_bias_grad(_lib.ptr(dy), _lib.ptr(gb.of(mod.bias)), n * h * w, cout, st))
@@ -344,6 +358,9 @@ class TrainMixin:
         a1 = self._t_gn_silu(tape, h1, st1, rb.block1.norm, ss, dss, self._tproj_off[name], None, rb.block1.proj.bias)
         h2 = self._t_conv(tape, name + ".block2.proj", a1, stats=st2)
         if (name + ".res_conv") in self._convs:
+            if self.FUSE_GN_RESIDUAL:
+                return self._t_conv(tape, name + ".res_conv", x0, x1, need_dgrad=need_dgrad,
+                                    res_gn=(h2, st2, rb.block2.norm, rb.block2.proj.bias))
             a2 = self._t_gn_silu(tape, h2, st2, rb.block2.norm, None, None, 0, None, rb.block2.proj.bias)
             return self._t_conv(tape, name + ".res_conv", x0, x1, residual=a2, need_dgrad=need_dgrad)
         assert x1 is None

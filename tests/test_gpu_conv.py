@@ -203,3 +203,45 @@ def test_strip_conv_fused_groupnorm_input(L, case):
     # and against torch on the same bf16-rounded activation
     y = F.conv2d(act.float().permute(0, 3, 1, 2), w.to(torch.bfloat16).float(), bias, padding=1)
     close(out.permute(0, 3, 1, 2).float(), y)
+
+
+@pytest.mark.parametrize("shape", [(2, 64, 64, 64, 37, 150), (1, 128, 64, 128, 22, 64), (2, 256, 128, 256, 11, 32),
+                                   (1, 512, 256, 512, 7, 16), (8, 64, 64, 64, 16, 128)])
+def test_conv_residual_groupnorm_epilogue(L, shape):
+    """fd_conv_igemm_rt: out = conv1x1(cat(x0, x1)) + silu(GroupNorm(h2)) with block2's GroupNorm apply folded into the
+    res_conv's epilogue (ResnetBlock.forward :212-214) == the two-pass form (fd_gn_silu, then the conv with a residual) and
+    == fp32 torch.  Statistics of h2 come from a producing conv (its epilogue accumulates them), like in the UNet."""
+    lib = L.load()
+    N, C0, C1, Cout, H, W = shape
+    g = torch.Generator().manual_seed(Cout + H)
+    x0 = torch.randn(N, C0, H, W, generator=g).cuda()
+    x1 = torch.randn(N, C1, H, W, generator=g).cuda()
+    w = (torch.randn(Cout, C0 + C1, 1, 1, generator=g) / (C0 + C1) ** 0.5).cuda()
+    bias = torch.randn(Cout, generator=g).cuda()
+    gamma = (torch.randn(Cout, generator=g) * 0.3 + 1).cuda()
+    beta = (torch.randn(Cout, generator=g) * 0.2).cuda()
+    # h2 and its statistics from a producing 3x3 conv
+    a1 = torch.randn(N, Cout, H, W, generator=g).cuda()
+    w2 = (torch.randn(Cout, Cout, 3, 3, generator=g) / (9 * Cout) ** 0.5 * 1.5).cuda()
+    b2 = torch.randn(Cout, generator=g).cuda() * 0.1
+    h2, st2 = run_conv(L, [a1], w2, b2, (1, 1), stats=True)
+    h2q = nhwc_bf16(h2)
+    s0, s1 = nhwc_bf16(x0), nhwc_bf16(x1)
+    wp = pack_w(w)
+    out = torch.empty(N, H, W, Cout, device="cuda", dtype=torch.bfloat16)
+    L.check(lib.fd_conv_igemm_rt(L.ptr(s0), C0, L.ptr(s1), C1, L.ptr(wp), L.ptr(bias), L.ptr(h2q), L.ptr(st2), L.ptr(gamma),
+                                 L.ptr(beta), 1e-5, L.ptr(out), N, H, W, Cout, 1, 1, 0, 0, L.stream()))
+    # two-pass form
+    a2 = torch.empty_like(h2q)
+    L.check(lib.fd_gn_silu(L.ptr(h2q), L.ptr(st2), L.ptr(gamma), L.ptr(beta), None, 0, None, L.ptr(a2), N, H * W, Cout, 1e-5,
+                           L.stream()))
+    two = torch.empty_like(out)
+    L.check(lib.fd_conv_igemm(L.ptr(s0), C0, L.ptr(s1), C1, L.ptr(wp), L.ptr(bias), L.ptr(a2), L.ptr(two), None, N, H, W, Cout,
+                              1, 1, 0, 0, 0, L.stream()))
+    torch.cuda.synchronize()
+    got, two = out.permute(0, 3, 1, 2).float(), two.permute(0, 3, 1, 2).float()
+    ref = ref_conv([x0, x1], w, bias, (0, 0)) + F.silu(F.group_norm(h2q.permute(0, 3, 1, 2).float(), 8, gamma, beta, eps=1e-5))
+    scale = ref.abs().max().item()
+    assert (got - ref).abs().max().item() <= 1.2e-2 * scale, ((got - ref).abs().max().item(), scale)
+    assert (got - two).abs().max().item() <= 1.6e-2 * scale          # the two-pass form rounds the activated tensor to bf16
+    assert (got - ref).abs().mean().item() <= 2e-3 * ref.abs().mean().item() + 1e-6
