@@ -222,6 +222,20 @@ FD_API int fd_linattn_apply_fused(const void* x, const float* g1, const void* wq
                                   const float* bias, const float* g2, void* out, int N, int HW, int C, float eps,
                                   void* stream);
 
+/* Residual(PreNorm(LinearAttention)) (:81-87,127-135,216-244) for C in {64,128} on tcgen05 / TMEM / TMA: two passes over
+ * x, no intermediate tensor in HBM (csrc/fd_linattn_tc.cu).
+ * fd_linattn_tc_prep (once per weight update): to_qkv.weight fp32 [384][C] and the PreNorm gain g1[C] ->
+ *   wq, wk bf16 [128][C] (rows scaled by g1 and log2 e), sq, sk fp32 [128] (their row sums), mk fp32 [128] (upper bound of
+ *   the k logit = the pixel-softmax shift), wv fp32 [128][C].
+ * fd_linattn_tc: x, out bf16 (N,HW,C); wout fp32 [C][128], bout fp32 [C] (to_out.0), g2 fp32 [C] (to_out.1.g);
+ *   workspace: fd_linattn_tc_workspace_floats(N, HW, C) floats. */
+FD_API size_t fd_linattn_tc_workspace_floats(int N, int HW, int C);
+FD_API int fd_linattn_tc_prep(const float* wqkv, const float* g1, void* wq, float* sq, void* wk, float* sk, float* mk,
+                       float* wv, int C, void* stream);
+FD_API int fd_linattn_tc(const void* x, const void* wk, const float* sk, const float* mk, const void* wq, const float* sq,
+                  const float* wv, const float* wout, const float* bout, const float* g2, void* out, float* workspace,
+                  int N, int HW, int C, float eps, void* stream);
+
 /* Attention core (:256-267): softmax(q^T k * 32^-0.5) v, flash-style, bf16 (N,HW,384) -> (N,HW,128) */
 FD_API int fd_attention(const void* qkv, void* out, int N, int HW, void* stream);
 

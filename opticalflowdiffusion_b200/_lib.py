@@ -49,6 +49,9 @@ SIGNATURES = {
     "fd_time_embed": (c_int, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _P]),
     "fd_time_proj": (c_int, [_P, _P, _P, _P, _I, _I, _I, _P]),
     "fd_linattn_workspace_floats": (c_size_t, [_I, _I]),
+    "fd_linattn_tc_workspace_floats": (c_size_t, [_I, _I, _I]),
+    "fd_linattn_tc_prep": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _P]),
+    "fd_linattn_tc": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _P]),
     "fd_linattn": (c_int, [_P, _P, _P, _I, _I, _P]),
     "fd_linattn_context": (c_int, [_P, _I, _P, _P, _I, _I, _P]),
     "fd_linattn_apply_fused": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _P]),

@@ -56,6 +56,9 @@ class Unet(UnetParams, TrainMixin):
     # path): the 9 ResnetBlocks that have a res_conv (ups.*, final_res_block) lose their second gn_silu pass -- 4.4 GB of
     # HBM traffic per batch-8 forward at 440x1024.  FD_FUSE_GN_RES=0 selects the two-pass form.
     FUSE_GN_RESIDUAL = os.environ.get("FD_FUSE_GN_RES", "1") != "0"
+    # Residual(PreNorm(LinearAttention)) for C in {64, 128} as two tcgen05 / TMA passes over x (fd_linattn_tc, inference
+    # path): no LayerNorm output, qkv or attention tensor in HBM.  FD_LINATTN_TC=0 selects the mma.sync kernels.
+    LINATTN_TC = os.environ.get("FD_LINATTN_TC", "1") != "0"
     WS_EPS = 1e-5       # WeightStandardizedConv2d with fp32 input (:107)
     LN_EPS = 1e-5       # LayerNorm with fp32 input (:122)
 
@@ -133,6 +136,12 @@ class Unet(UnetParams, TrainMixin):
         add_res("final_res_block", self.final_res_block)
         self._convs = convs
 
+    def _linattn_blocks(self):
+        for i, stage in enumerate(self.downs):
+            yield f"downs.{i}.2", stage[2]
+        for i, stage in enumerate(self.ups):
+            yield f"ups.{i}.2", stage[2]
+
     def _versions(self):
         return (self.weights_epoch,) + tuple(p._version for p in self.parameters()) + \
             tuple(p.data_ptr() for p in self.parameters())
@@ -182,6 +191,24 @@ class Unet(UnetParams, TrainMixin):
             off += lin.weight.shape[0]
             ws.append(lin.weight.detach().float())
             bs.append(lin.bias.detach().float())
+        # operands of the tcgen05 LinearAttention blocks (fd_linattn_tc_prep): buffers allocated once, rewritten in place
+        la = getattr(self, "_la_tc", None)
+        if la is None:
+            la = self._la_tc = {}
+        for name, res in self._linattn_blocks():
+            fn = res.fn.fn
+            if fn.dim not in (64, 128):
+                continue
+            wqkv = fn.to_qkv.weight
+            ent = la.get(name)
+            if ent is None or ent["wq"].device != wqkv.device:
+                dv, C = wqkv.device, fn.dim
+                ent = la[name] = {"wq": torch.empty(128, C, device=dv, dtype=BF16), "wk": torch.empty(128, C, device=dv, dtype=BF16),
+                                  "sq": torch.empty(128, device=dv), "sk": torch.empty(128, device=dv),
+                                  "mk": torch.empty(128, device=dv), "wv": torch.empty(128, C, device=dv)}
+            _lib.check(lib.fd_linattn_tc_prep(_lib.ptr(wqkv.detach().float().contiguous()), _lib.ptr(res.fn.norm.g), _lib.ptr(ent["wq"]),
+                                              _lib.ptr(ent["sq"]), _lib.ptr(ent["wk"]), _lib.ptr(ent["sk"]), _lib.ptr(ent["mk"]),
+                                              _lib.ptr(ent["wv"]), fn.dim, st))
         # written IN PLACE once allocated: a captured CUDA graph of the sampler holds these pointers (diffusion.py)
         if ws:
             rows = sum(w.shape[0] for w in ws)
@@ -293,6 +320,16 @@ class Unet(UnetParams, TrainMixin):
     def _linear_attention(self, name: str, res, x: Tensor) -> Tensor:
         """Residual(PreNorm(LinearAttention)) (:81-87,127-135,229-244)."""
         n, h, w, c = x.shape
+        ent = self._la_tc.get(name) if self.LINATTN_TC and not getattr(self, "_no_fused_attn", False) else None
+        if ent is not None:
+            fn = res.fn.fn
+            out = torch.empty_like(x)
+            ws = torch.empty(self._lib.fd_linattn_tc_workspace_floats(n, h * w, c), device=x.device, dtype=torch.float32)
+            _lib.check(self._lib.fd_linattn_tc(_lib.ptr(x), _lib.ptr(ent["wk"]), _lib.ptr(ent["sk"]), _lib.ptr(ent["mk"]),
+                                               _lib.ptr(ent["wq"]), _lib.ptr(ent["sq"]), _lib.ptr(ent["wv"]),
+                                               _lib.ptr(fn.to_out[0].weight), _lib.ptr(fn.to_out[0].bias), _lib.ptr(fn.to_out[1].g),
+                                               _lib.ptr(out), _lib.ptr(ws), n, h * w, c, self.LN_EPS, self._st))
+            return out
         if (name + ".to_kv") in self._convs and not getattr(self, "_no_fused_attn", False):
             # C in {64,128}: k|v through the conv engine, then ONE fused pass for q / softmax / context / to_out /
             # LayerNorm / residual (the q third of to_qkv and to_out run as in-kernel GEMMs)

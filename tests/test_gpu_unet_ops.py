@@ -254,3 +254,51 @@ def test_linear_attention_block_fused(L, C):
     L.check(lib.fd_linattn_apply_fused(L.ptr(xc), L.ptr(g1), L.ptr(wq), L.ptr(ctx_t), L.ptr(wout), L.ptr(b), L.ptr(g2),
                                        L.ptr(out), N, H * W, C, 1e-5, L.stream()))
     assert rel_err(nchw(out).cpu(), ref) < 2e-2
+
+
+@pytest.mark.parametrize("C", [64, 128])
+@pytest.mark.parametrize("nhw", [(2, 9, 14), (1, 40, 72), (3, 16, 128), (8, 24, 64)])
+def test_linear_attention_block_tcgen05(L, C, nhw):
+    """fd_linattn_tc (tcgen05 / TMEM / TMA, two passes over x, no intermediate tensor) == the oracle's
+    Residual(PreNorm(LinearAttention)) block (denoising_diffusion.py:81-87,127-135,216-244).  Shapes: a single ragged tile,
+    several tiles per CTA with a ragged last one, several samples, more samples than fit one CTA range each.
+    Tolerance: relative L2 <= 2e-2 (bf16 operands: x, the scaled q / k weights, exp(k), softmax(q), the folded context)."""
+    lib = L.load()
+    N, H, W = nhw
+    g = torch.Generator().manual_seed(C + H * W)
+    x = (torch.randn(N, C, H, W, generator=g) * 1.5 + 0.3).to(BF).float()
+    sd = {"norm.g": torch.randn(1, C, 1, 1, generator=g) * 0.3 + 1,
+          "fn.to_qkv.weight": torch.randn(384, C, 1, 1, generator=g) / C ** 0.5 * 2.0,
+          "fn.to_out.0.weight": torch.randn(C, 128, 1, 1, generator=g) / 128 ** 0.5 * 30,
+          "fn.to_out.0.bias": torch.randn(C, generator=g) * 0.1,
+          "fn.to_out.1.g": torch.randn(1, C, 1, 1, generator=g) * 0.3 + 1}
+    ref = O._linear_attention(sd, "", x)
+    xc = nhwc(x.cuda())
+    wqkv = sd["fn.to_qkv.weight"].reshape(384, C).contiguous().cuda()
+    g1, g2 = sd["norm.g"].reshape(C).contiguous().cuda(), sd["fn.to_out.1.g"].reshape(C).contiguous().cuda()
+    wout, bout = sd["fn.to_out.0.weight"].reshape(C, 128).contiguous().cuda(), sd["fn.to_out.0.bias"].cuda()
+    wq, wk = torch.empty(128, C, device="cuda", dtype=BF), torch.empty(128, C, device="cuda", dtype=BF)
+    sq, sk, mk = (torch.empty(128, device="cuda") for _ in range(3))
+    wv = torch.empty(128, C, device="cuda")
+    L.check(lib.fd_linattn_tc_prep(L.ptr(wqkv), L.ptr(g1), L.ptr(wq), L.ptr(sq), L.ptr(wk), L.ptr(sk), L.ptr(mk), L.ptr(wv), C,
+                                   L.stream()))
+    # the softmax shift is an upper bound of every k logit (Cauchy-Schwarz on the LayerNorm output)
+    y = O._chan_layernorm(x, sd["norm.g"])
+    k = torch.einsum("jc,nchw->njhw", wqkv[128:256].cpu(), y) * 1.4426950408889634
+    assert bool((k.amax(dim=(0, 2, 3)) <= mk.cpu() + 1e-3).all())
+    out = torch.empty_like(xc)
+    ws = torch.empty(lib.fd_linattn_tc_workspace_floats(N, H * W, C), device="cuda")
+    L.check(lib.fd_linattn_tc(L.ptr(xc), L.ptr(wk), L.ptr(sk), L.ptr(mk), L.ptr(wq), L.ptr(sq), L.ptr(wv), L.ptr(wout), L.ptr(bout),
+                              L.ptr(g2), L.ptr(out), L.ptr(ws), N, H * W, C, 1e-5, L.stream()))
+    torch.cuda.synchronize()
+    got = nchw(out).cpu()
+    assert torch.isfinite(got).all()
+    err = rel_err(got, ref)
+    # the attention branch alone (the residual x dominates the norm of the block's output)
+    err_branch = rel_err(got - x, ref - x)
+    print(f"C={C} {nhw}: rel L2 {err:.3e}, attention branch {err_branch:.3e}")
+    assert err < 2e-2 and err_branch < 4e-2
+    out2 = torch.empty_like(xc)
+    L.check(lib.fd_linattn_tc(L.ptr(xc), L.ptr(wk), L.ptr(sk), L.ptr(mk), L.ptr(wq), L.ptr(sq), L.ptr(wv), L.ptr(wout), L.ptr(bout),
+                              L.ptr(g2), L.ptr(out2), L.ptr(ws), N, H * W, C, 1e-5, L.stream()))
+    assert torch.equal(out, out2)          # fixed-order reductions: run-to-run bit-stable
