@@ -95,6 +95,7 @@ __device__ __forceinline__ void conv_epilogue(const EpiCtx& ec, NextTile next_ti
 #pragma unroll
       for (int b = 0; b < GIC; ++b) st_s[a][b] = st_q[a][b] = 0.f;
     int st_img = -1, st_ntile = 0;
+    int rt_img = -1, rt_ntile = -1;
     uint32_t slab_count = 0;
 
     auto flush_stats = [&]() {
@@ -141,9 +142,14 @@ __device__ __forceinline__ void conv_epilogue(const EpiCtx& ec, NextTile next_ti
       }
       float* bias_s = s_bias + (as & 1) * BLOCK_N;
       for (int i = et; i < BLOCK_N; i += kEpiThreads) bias_s[i] = ec.bias ? __ldg(ec.bias + n0 + i) : 0.f;
-      float* rt_s = ec.s_rt + (as & 1) * 2 * BLOCK_N;
-      if (ec.rt_stats != nullptr) {
-        // same folding as gn_silu_kernel (double-precision mean / variance), pre-scaled by 1/2 for epi_silu_half
+      float* rt_s = ec.s_rt;
+      if (ec.rt_stats != nullptr && (img != rt_img || n_tile != rt_ntile)) {
+        // Folded once per (image, N-tile), not per tile: the double-precision divisions / square root have a latency of
+        // thousands of cycles on this part (measured: +200 us on a full-resolution 1x1 conv when done for every tile).
+        // Safe to overwrite in place: every read of the previous coefficients precedes the last slab barrier of the
+        // previous tile.  Same folding as gn_silu_kernel, pre-scaled by 1/2 for epi_silu_half.
+        rt_img = img;
+        rt_ntile = n_tile;
         const int cpg = ec.Cout >> 3;
         const double cnt = (double)ec.H * (double)ec.W * (double)cpg;
         for (int i = et; i < BLOCK_N; i += kEpiThreads) {
@@ -161,6 +167,16 @@ __device__ __forceinline__ void conv_epilogue(const EpiCtx& ec, NextTile next_ti
       }
       // (the slab barrier below also publishes the bias and the folded coefficients)
 
+      // The residual row of the first slab is requested BEFORE waiting for the accumulator, the next slab's while this one
+      // is processed: measured on the full-resolution 1x1 res_convs, a load issued after the wait exposes the whole DRAM
+      // latency once per tile (8 warps x 64 B in flight per SM = ~3 TB/s over the chip).
+      const long pix = ((long)img * ec.H + h) * ec.W + w;
+      const __nv_bfloat16* rrow = (ec.residual && valid) ? ec.residual + pix * ec.Cout + n0 : nullptr;
+      uint4 rpre[4];
+      if (rrow != nullptr) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) rpre[q] = __ldg(reinterpret_cast<const uint4*>(rrow + half * 32) + q);
+      }
       mbar_wait(ec.tfull0 + 8u * as, aphase);
       tc_fence_after();
       if (ec.dbg & 8) {
@@ -169,8 +185,6 @@ __device__ __forceinline__ void conv_epilogue(const EpiCtx& ec, NextTile next_ti
         else mbar_arrive(ec.tempty0 + 8u * as);
         continue;
       }
-      const long pix = ((long)img * ec.H + h) * ec.W + w;
-      const __nv_bfloat16* rrow = ec.residual ? ec.residual + pix * ec.Cout + n0 : nullptr;
 #pragma unroll
       for (int slab = 0; slab < (BLOCK_N + 63) / 64; ++slab) {
         const uint32_t buf = o_smem + (slab_count % NBUF) * kSlabBytes;
@@ -191,10 +205,17 @@ __device__ __forceinline__ void conv_epilogue(const EpiCtx& ec, NextTile next_ti
           v[j4 * 4 + 2] = __uint_as_float(acc[j4 * 4 + 2]) + b4.z;
           v[j4 * 4 + 3] = __uint_as_float(acc[j4 * 4 + 3]) + b4.w;
         }
-        if (rrow != nullptr && valid) {
+        if (rrow != nullptr) {
+          uint4 rcur[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) rcur[q] = rpre[q];
+          if (slab + 1 < (BLOCK_N + 63) / 64) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) rpre[q] = __ldg(reinterpret_cast<const uint4*>(rrow + c + 64) + q);
+          }
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            const uint4 r4 = __ldg(reinterpret_cast<const uint4*>(rrow + c) + q);
+            const uint4 r4 = rcur[q];
             const uint32_t rw[4] = {r4.x, r4.y, r4.z, r4.w};
             if (ec.rt_stats != nullptr) {
               const float4 a0 = *reinterpret_cast<const float4*>(rt_s + c + q * 8), a1 = *reinterpret_cast<const float4*>(rt_s + c + q * 8 + 4);

@@ -23,9 +23,11 @@
 //           linattn_combine_kernel  partials -> M^T bf16 [N][C][128]         (tiny)
 //   pass 2  linattn_apply_kernel  x -> out                                  [MMA1: q logits, MMA2: q_hat M; LayerNorm + x]
 //
-// Warp roles in both passes (320 threads, one CTA per SM, contiguous tile ranges inside one sample):
-//   warp 0 TMA producer, warp 1 TMEM allocator + single-thread tcgen05.mma issuer, warps 2..9 epilogue (TMEM lane quarter =
-//   warp % 4; the two warps of a quarter split the columns).
+// Warp roles in both passes (576 threads, one CTA per SM, contiguous tile ranges inside one sample):
+//   warp 0 TMA producer, warp 1 TMEM allocator + single-thread tcgen05.mma issuer, warps 2..17 epilogue (TMEM lane quarter =
+//   warp % 4; the four warps of a quarter split the columns, 32 each).
+#include <stdlib.h>
+
 #include "fd_tc.cuh"
 
 using namespace fdtc;
@@ -33,8 +35,9 @@ using namespace fdtc;
 namespace {
 
 constexpr int kTilePx = 128;
-constexpr int kLaThreads = 320;
-constexpr int kLaEpi = 256;
+constexpr int kLaEpiWarps = 16;               // four per TMEM lane quarter: each thread owns 32 of a row's 128 logit columns
+constexpr int kLaEpi = kLaEpiWarps * 32;
+constexpr int kLaThreads = 64 + kLaEpi;
 constexpr float kLog2e = 1.4426950408889634f;
 
 // MN-major SWIZZLE_128B operand (see fd_conv_wgrad.cu): 128-byte rows along M/N, 8 K-rows per 1024-byte atom (SBO),
@@ -71,28 +74,74 @@ __device__ __forceinline__ void la_tma_store_3d(const CUtensorMap* m, uint32_t s
                : "memory");
 }
 
-// mean / rstd of one pixel row of the landed x tile (64-channel chunks of [128 px][128 B]; the swizzle permutes the 16-byte
-// granules inside the row, which a sum does not care about)
+// ---- packed fp32x2 arithmetic (FFMA2 / FMUL2 / FADD2 of sm_100): the epilogues are instruction-issue bound
+__device__ __forceinline__ uint64_t pk2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ uint64_t pk2u(uint32_t lo, uint32_t hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+  return r;
+}
+__device__ __forceinline__ float2 up2(uint64_t v) {
+  float2 f;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(f.x), "=f"(f.y) : "l"(v));
+  return f;
+}
+__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ uint64_t fmul2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+
+// LayerNorm statistics of a pixel row, shared by the two threads that own the row inside one warp group (`half` 0 / 1): each
+// sums half of the row's 16-byte granules, the partial (sum, sum of squares) go through shared memory, the two warps meet on a
+// 64-thread named barrier (`bar_id`).  `sx` = [2 halves][128 rows] float2, double buffered by the caller.
 template <int C>
-__device__ __forceinline__ void la_row_stats(uint32_t x_tile, int row, float eps, float& mu, float& r, float& sigma) {
+__device__ __forceinline__ void la_row_stats2(uint32_t x_tile, int row, int half, int bar_id, float2* sx, float eps, float& mu,
+                                              float& r, float& sigma) {
   float s = 0.f, q = 0.f;
 #pragma unroll
-  for (int ch = 0; ch < C / 64; ++ch)
+  for (int gg = 0; gg < C / 16; ++gg) {
+    const int g = half * (C / 16) + gg;          // granule of the row: 64-channel chunk g >> 3, 16-byte column g & 7
+    // physical column (g ^ row) & 7: the rows a quarter-warp reads in one phase hit different banks
+    const uint4 v = la_ld16(x_tile + (g >> 3) * 16384 + row * 128 + (((g & 7) ^ row) & 7) * 16);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-    for (int g = 0; g < 8; ++g) {
-      const uint4 v = la_ld16(x_tile + ch * 16384 + row * 128 + g * 16);
-      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float2 f = fd_unpack_bf16(w[e]);
-        s += f.x + f.y;
-        q = fmaf(f.x, f.x, fmaf(f.y, f.y, q));
-      }
+    for (int e = 0; e < 4; ++e) {
+      const float2 f = fd_unpack_bf16(w[e]);
+      s += f.x + f.y;
+      q = fmaf(f.x, f.x, fmaf(f.y, f.y, q));
     }
-  mu = s * (1.f / C);
-  const float var = fmaxf(q * (1.f / C) - mu * mu, 0.f);
-  sigma = sqrtf(var + eps);
-  r = 1.f / sigma;
+  }
+  sx[half * 128 + row] = make_float2(s, q);
+  named_bar_sync(bar_id, 64);
+  const float2 o = sx[(half ^ 1) * 128 + row];
+  mu = (s + o.x) * (1.f / C);
+  const float var = fmaxf((q + o.y) * (1.f / C) - mu * mu, 0.f);
+  r = rsqrtf(var + eps);
+  sigma = (var + eps) * r;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -148,15 +197,22 @@ template <int C>
 struct CtxCfg {
   static constexpr int kChunks = C / 64;
   static constexpr int kXBytes = kChunks * 16384;          // x tile: 64-channel chunks of [128 px][128 B]
-  static constexpr int kStages = C == 64 ? 4 : 3;
+  // deep ring: a slot is held from the TMA load until MMA2 of its tile has retired, i.e. through the whole epilogue; with 4
+  // slots only ~2 loads per SM were in flight and the kernel ran at the DRAM latency (4.4 TB/s with ALL work skipped)
+  static constexpr int kStages = C == 64 ? 5 : 3;
   static constexpr int kWBytes = kChunks * 16384;          // Wk' [128 rows][C], K-major, 64-channel chunks
   static constexpr int kPBytes = 32768;                    // P' [128 px][128 d]: two 64-d chunks (MN-major A of MMA2)
   static constexpr int kAuxBytes = 4096;                   // aux [16 rows][128 px] K-major: two 64-px chunks of 2 KB
+  // P' / aux buffers.  Three (tile i uses buffer i % 3): the group that wrote tile i writes tile i + 2 next, into the buffer
+  // tile i - 1 used, whose MMA2 retired before MMA2(i) even started -- so MMA2(i) overlaps the exps of tile i + 2.  With two
+  // buffers (one per group) the group waits for its own MMA2 and the two times add up (measured: FD_LA_DBG).
+  static constexpr int kNP = C == 64 ? 3 : 2;
   static constexpr int kOffW = kStages * kXBytes;
   static constexpr int kOffP = kOffW + kWBytes;
-  static constexpr int kOffAux = kOffP + 2 * kPBytes;
-  static constexpr int kOffConst = kOffAux + 2 * kAuxBytes;   // sk[128], mk[128]
-  static constexpr int kOffBar = kOffConst + 1024;
+  static constexpr int kOffAux = kOffP + kNP * kPBytes;
+  static constexpr int kOffConst = kOffAux + kNP * kAuxBytes;   // sk[128], -mk[128]
+  static constexpr int kOffSx = kOffConst + 1024;             // [2 tile parities][4 parts][128 rows] float2
+  static constexpr int kOffBar = kOffSx + 8192;
   static constexpr int kSmemBytes = 1024 + kOffBar + 256;
 };
 
@@ -166,6 +222,8 @@ struct CtxParams {
   const float* sk;
   const float* mk;
   float* partial;             // [N * cps][128 d][C + 4]: G[d][0..C), T[d], den[d]
+  int dbg;                    // FD_LA_DBG (diagnostics, results are garbage): 1 skip epilogue math, 2 skip MMA2 + aux, 4 skip row
+                              // statistics, 8 skip MMA1
 };
 
 template <int C>
@@ -186,10 +244,11 @@ linattn_ctx_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
   const uint32_t wfull = bar + 8u * (2 * S);
   auto d1full = [&](int s) { return bar + 8u * (2 * S + 1 + s); };
   auto d1empty = [&](int s) { return bar + 8u * (2 * S + 3 + s); };
+  constexpr int NP = Cf::kNP;
   auto pfull = [&](int s) { return bar + 8u * (2 * S + 5 + s); };
-  auto pempty = [&](int s) { return bar + 8u * (2 * S + 7 + s); };
-  const uint32_t accfull = bar + 8u * (2 * S + 9);
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(gbase + Cf::kOffBar + 8 * (2 * S + 10));
+  auto pempty = [&](int s) { return bar + 8u * (2 * S + 5 + NP + s); };
+  const uint32_t accfull = bar + 8u * (2 * S + 5 + 2 * NP);
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(gbase + Cf::kOffBar + 8 * (2 * S + 6 + 2 * NP));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n = blockIdx.x / p.cps, jc = blockIdx.x % p.cps;
@@ -206,8 +265,10 @@ linattn_ctx_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
     mbar_init(wfull, 1);
     for (int s = 0; s < 2; ++s) {
       mbar_init(d1full(s), 1);
-      mbar_init(d1empty(s), kLaEpi);
-      mbar_init(pfull(s), kLaEpi);
+      mbar_init(d1empty(s), kLaEpi / 2);       // one warp group (8 warps) owns accumulator stage s
+    }
+    for (int s = 0; s < NP; ++s) {
+      mbar_init(pfull(s), kLaEpi / 2);
       mbar_init(pempty(s), 1);
     }
     mbar_init(accfull, 1);
@@ -246,30 +307,34 @@ linattn_ctx_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
         mbar_wait(xfull(s), (i / S) & 1);
         tc_fence_after();
         const uint64_t xd = umma_desc_sw128(x_smem + s * Cf::kXBytes);
+        if (!(p.dbg & 8)) {
 #pragma unroll
-        for (int ch = 0; ch < NCH; ++ch)
+          for (int ch = 0; ch < NCH; ++ch)
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_bf16(tmem_base + as * 128, xd + (uint64_t)(ch * 1024 + 2 * k), wdesc + (uint64_t)(ch * 1024 + 2 * k), id1,
-                      (ch | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < 4; ++k)
+              umma_bf16(tmem_base + as * 128, xd + (uint64_t)(ch * 1024 + 2 * k), wdesc + (uint64_t)(ch * 1024 + 2 * k), id1,
+                        (ch | k) != 0 ? 1u : 0u);
+        }
         umma_commit(d1full(as));
       };
       if (nt > 0) mma1(0);
       for (int i = 0; i < nt; ++i) {
         if (i + 1 < nt) mma1(i + 1);
-        const int pb = i & 1, s = i % S;
-        mbar_wait(pfull(pb), (i >> 1) & 1);
+        const int pb = i % NP, s = i % S;
+        mbar_wait(pfull(pb), (i / NP) & 1);
         tc_fence_after();
         const uint64_t pd = la_desc_mn(p_smem + pb * Cf::kPBytes, 16384);
         const uint64_t xd = la_desc_mn(x_smem + s * Cf::kXBytes, 16384);
         const uint64_t ad = umma_desc_sw128(aux_smem + pb * Cf::kAuxBytes);
+        if (!(p.dbg & 2)) {
 #pragma unroll
-        for (int ks = 0; ks < 8; ++ks)       // 16 pixels per step = two 8-pixel atoms = 2048 B
-          umma_bf16(tmem_base + 256, pd + (uint64_t)(ks * 128), xd + (uint64_t)(ks * 128), id2, (i | ks) != 0 ? 1u : 0u);
+          for (int ks = 0; ks < 8; ++ks)       // 16 pixels per step = two 8-pixel atoms = 2048 B
+            umma_bf16(tmem_base + 256, pd + (uint64_t)(ks * 128), xd + (uint64_t)(ks * 128), id2, (i | ks) != 0 ? 1u : 0u);
 #pragma unroll
-        for (int ks = 0; ks < 8; ++ks)
-          umma_bf16(tmem_base + 384, pd + (uint64_t)(ks * 128), ad + (uint64_t)((ks >> 2) * 128 + 2 * (ks & 3)), id3,
-                    (i | ks) != 0 ? 1u : 0u);
+          for (int ks = 0; ks < 8; ++ks)
+            umma_bf16(tmem_base + 384, pd + (uint64_t)(ks * 128), ad + (uint64_t)((ks >> 2) * 128 + 2 * (ks & 3)), id3,
+                      (i | ks) != 0 ? 1u : 0u);
+        }
         umma_commit(xempty(s));
         umma_commit(pempty(pb));
       }
@@ -277,25 +342,33 @@ linattn_ctx_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
     }
     __syncwarp();
   } else {
-    // ===================== epilogue warps 2..9 =====================
-    const int et = threadIdx.x - 64;
-    const int quarter = warp & 3, half = (warp - 2) >> 2;
+    // ===================== epilogue warps 2..17: two groups of 8 warps on alternating tiles =====================
+    // The exp of 128 x 128 logits per tile keeps the MUFU pipe busy for 1024 cycles; everything else a tile needs (row
+    // statistics, TMEM loads, barrier round trips) overlaps it only if ANOTHER tile's exps are in flight meanwhile (measured
+    // with FD_LA_DBG: with one group the parts simply add up).  Group g owns tiles i = g (mod 2), i.e. accumulator stage g
+    // and P' buffer g.  Inside a group the two warps of a TMEM lane quarter split a row's 128 logit columns (2 heads each).
+    const int et = threadIdx.x - 64, ew = warp - 2;
+    const int grp = ew >> 3, half = (ew >> 2) & 1, quarter = warp & 3;
+    const int part = ew >> 2;                                  // 0..3, used for the final accumulator read-out only
     const int row = quarter * 32 + lane;
     if (et < 128) s_sk[et] = __ldg(p.sk + et);
-    else s_mk[et - 128] = __ldg(p.mk + et - 128);
-    for (int i = et; i < 2 * Cf::kAuxBytes / 16; i += kLaEpi) la_st16(aux_smem + i * 16, 0u, 0u, 0u, 0u);   // rows 4..15 stay zero
+    else if (et < 256) s_mk[et - 128] = -__ldg(p.mk + et - 128);
+    for (int i = et; i < NP * Cf::kAuxBytes / 16; i += kLaEpi) la_st16(aux_smem + i * 16, 0u, 0u, 0u, 0u);   // rows 4..15 stay zero
     named_bar_sync(1, kLaEpi);
+    float2* s_sx = reinterpret_cast<float2*>(gbase + Cf::kOffSx) + grp * 512;       // [group][use parity][half][row]
     const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
-    for (int i = 0; i < nt; ++i) {
-      const int s = i % S, pb = i & 1, as = i & 1;
+    const int as = grp;
+    for (int i = grp; i < nt; i += 2) {
+      const int s = i % S, u = i >> 1, pb = i % NP;
       mbar_wait(xfull(s), (i / S) & 1);
-      float mu, r, sigma;
-      la_row_stats<C>(x_smem + s * Cf::kXBytes, row, p.eps, mu, r, sigma);
+      float mu = 0.f, r = 1.f, sigma = 1.f;
+      if (!(p.dbg & 4))
+        la_row_stats2<C>(x_smem + s * Cf::kXBytes, row, half, 4 + grp * 4 + quarter, s_sx + (u & 1) * 256, p.eps, mu, r, sigma);
       const bool valid = (t0 + i) * kTilePx + row < p.HW;
-      const float nrm = -r * mu;
-      const float rv = valid ? r : 0.f;
-      mbar_wait(pempty(pb), ((i >> 1) & 1) ^ 1u);
-      mbar_wait(d1full(as), (i >> 1) & 1);
+      const uint64_t nrm2 = pk2(-r * mu, -r * mu), r2 = pk2(r, r);
+      const uint64_t rv2 = valid ? r2 : 0ull;
+      mbar_wait(pempty(pb), ((i / NP) & 1) ^ 1u);
+      mbar_wait(d1full(as), u & 1);
       tc_fence_after();
 #pragma unroll
       for (int cc = 0; cc < 2; ++cc) {
@@ -307,18 +380,19 @@ linattn_ctx_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
           tc_fence_before();
           mbar_arrive(d1empty(as));
         }
+        if (p.dbg & 1) continue;
         uint32_t pk[16];
 #pragma unroll
         for (int j4 = 0; j4 < 8; ++j4) {
-          const float4 s4 = *reinterpret_cast<const float4*>(s_sk + col0 + j4 * 4);
-          const float4 m4 = *reinterpret_cast<const float4*>(s_mk + col0 + j4 * 4);
+          const ulonglong2 s4 = *reinterpret_cast<const ulonglong2*>(s_sk + col0 + j4 * 4);
+          const ulonglong2 m4 = *reinterpret_cast<const ulonglong2*>(s_mk + col0 + j4 * 4);
           // k' - m = r acc - r mu s_j - m_j  (log2 e folded into Wk'); P' = exp2(.) r_p, zero for rows past the sample
-          const float p0 = la_ex2(fmaf(r, __uint_as_float(acc[j4 * 4 + 0]), fmaf(nrm, s4.x, -m4.x))) * rv;
-          const float p1 = la_ex2(fmaf(r, __uint_as_float(acc[j4 * 4 + 1]), fmaf(nrm, s4.y, -m4.y))) * rv;
-          const float p2 = la_ex2(fmaf(r, __uint_as_float(acc[j4 * 4 + 2]), fmaf(nrm, s4.z, -m4.z))) * rv;
-          const float p3 = la_ex2(fmaf(r, __uint_as_float(acc[j4 * 4 + 3]), fmaf(nrm, s4.w, -m4.w))) * rv;
-          pk[j4 * 2] = fd_pack_bf16(p0, p1);
-          pk[j4 * 2 + 1] = fd_pack_bf16(p2, p3);
+          const float2 a0 = up2(ffma2(r2, pk2u(acc[j4 * 4 + 0], acc[j4 * 4 + 1]), ffma2(nrm2, s4.x, m4.x)));
+          const float2 a1 = up2(ffma2(r2, pk2u(acc[j4 * 4 + 2], acc[j4 * 4 + 3]), ffma2(nrm2, s4.y, m4.y)));
+          const float2 p0 = up2(fmul2(pk2(la_ex2(a0.x), la_ex2(a0.y)), rv2));
+          const float2 p1 = up2(fmul2(pk2(la_ex2(a1.x), la_ex2(a1.y)), rv2));
+          pk[j4 * 2] = fd_pack_bf16(p0.x, p0.y);
+          pk[j4 * 2 + 1] = fd_pack_bf16(p1.x, p1.y);
         }
         const uint32_t rbase = p_smem + pb * Cf::kPBytes + half * 16384 + row * 128;
 #pragma unroll
@@ -347,21 +421,19 @@ linattn_ctx_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
     mbar_wait(accfull, 0);
     tc_fence_after();
     float* out = p.partial + ((long)blockIdx.x * 128 + row) * (C + 4);
-#pragma unroll
-    for (int cb = 0; cb < C / 64; ++cb) {
-      const int col0 = half * (C / 2) + cb * 32;
+    if (part < C / 32) {
       uint32_t acc[32];
-      tmem_ld32(tmem_base + lane_off + (uint32_t)(256 + col0), acc);
+      tmem_ld32(tmem_base + lane_off + (uint32_t)(256 + part * 32), acc);
       tmem_ld_wait();
 #pragma unroll
       for (int j4 = 0; j4 < 8; ++j4)
-        *reinterpret_cast<float4*>(out + col0 + j4 * 4) =
+        *reinterpret_cast<float4*>(out + part * 32 + j4 * 4) =
             make_float4(__uint_as_float(acc[j4 * 4]), __uint_as_float(acc[j4 * 4 + 1]), __uint_as_float(acc[j4 * 4 + 2]),
                         __uint_as_float(acc[j4 * 4 + 3]));
     }
-    if (half == 0) {
-      uint32_t acc[32];
-      tmem_ld32(tmem_base + lane_off + 384u, acc);       // columns 0..3 = T hi/lo, den hi/lo parts (16..31 unused)
+    if (part == 3) {
+      uint32_t acc[16];
+      tmem_ld16(tmem_base + lane_off + 384u, acc);       // columns 0..3 = T hi/lo, den hi/lo parts
       tmem_ld_wait();
       *reinterpret_cast<float4*>(out + C) = make_float4(__uint_as_float(acc[0]) + __uint_as_float(acc[1]),
                                                         __uint_as_float(acc[2]) + __uint_as_float(acc[3]), 0.f, 0.f);
@@ -376,51 +448,62 @@ linattn_ctx_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
 }
 
 // ------------------------------------------------------------------------------------------------
-// combine: partials of one sample -> M^T[co][d] = sum_{e in head(d)} ctx[d][e] W_out[co][e]   (bf16 [N][C][128])
+// combine: partials of one (sample, head) -> M^T[co][d] = sum_{e in head(d)} ctx[d][e] W_out[co][e]   (bf16 [N][C][128])
 //   ctx[d][e] = 32^-0.5 / (HW den[d]) sum_c (G[d][c] - T[d]) W'_v[e][c]
-// one block per sample, thread d; partials are added in a fixed order (run-to-run bit-stable)
+// grid (N, 4 heads), 256 threads; partials are added in a fixed order (run-to-run bit-stable)
 // ------------------------------------------------------------------------------------------------
 template <int C>
-__global__ void __launch_bounds__(128) linattn_tc_combine_kernel(const float* __restrict__ partial, const float* __restrict__ wv,
+__global__ void __launch_bounds__(256) linattn_tc_combine_kernel(const float* __restrict__ partial, const float* __restrict__ wv,
                                                                  const float* __restrict__ wout, __nv_bfloat16* __restrict__ mt,
                                                                  int cps, int HW) {
-  const int n = blockIdx.x, d = threadIdx.x;
-  float g[C];
-#pragma unroll
-  for (int c = 0; c < C; ++c) g[c] = 0.f;
-  float T = 0.f, den = 0.f;
-  for (int j = 0; j < cps; ++j) {
-    const float* src = partial + (((long)n * cps + j) * 128 + d) * (C + 4);
-#pragma unroll
-    for (int c4 = 0; c4 < C / 4; ++c4) {
-      const float4 v = *reinterpret_cast<const float4*>(src + c4 * 4);
-      g[c4 * 4] += v.x;
-      g[c4 * 4 + 1] += v.y;
-      g[c4 * 4 + 2] += v.z;
-      g[c4 * 4 + 3] += v.w;
+  __shared__ float s_g[32][C + 1];
+  __shared__ float s_wv[32][C + 1];
+  __shared__ float s_ctx[32][33];
+  __shared__ float s_T[32], s_den[32];
+  const int n = blockIdx.x, head = blockIdx.y, t = threadIdx.x;
+  constexpr int V4 = (C + 4) / 4;
+  for (int idx = t; idx < 32 * V4; idx += 256) {
+    const int dd = idx / V4, v = idx - dd * V4;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int j = 0; j < cps; ++j) {
+      const float4 x = *reinterpret_cast<const float4*>(partial + (((long)n * cps + j) * 128 + head * 32 + dd) * (C + 4) + v * 4);
+      a.x += x.x;
+      a.y += x.y;
+      a.z += x.z;
+      a.w += x.w;
     }
-    T += src[C];
-    den += src[C + 1];
+    if (v < C / 4) {
+      s_g[dd][v * 4] = a.x;
+      s_g[dd][v * 4 + 1] = a.y;
+      s_g[dd][v * 4 + 2] = a.z;
+      s_g[dd][v * 4 + 3] = a.w;
+    } else {
+      s_T[dd] = a.x;
+      s_den[dd] = a.y;
+    }
   }
-#pragma unroll
-  for (int c = 0; c < C; ++c) g[c] -= T;
-  const float inv = 0.17677669529663687f / (den * (float)HW);      // 32^-0.5 (q scale, :238), 1 / HW (v, :240), softmax denominator
-  const int head = d >> 5;
-  float ctx[32];
-#pragma unroll
-  for (int e = 0; e < 32; ++e) {
-    const float* w = wv + (long)(head * 32 + e) * C;
+  for (int idx = t; idx < 32 * C; idx += 256) {
+    const int e = idx / C, c = idx - e * C;
+    s_wv[e][c] = __ldg(wv + (long)(head * 32 + e) * C + c);
+  }
+  __syncthreads();
+  for (int o = t; o < 1024; o += 256) {
+    const int dd = o >> 5, e = o & 31;
+    const float T = s_T[dd];
     float a = 0.f;
-#pragma unroll
-    for (int c = 0; c < C; ++c) a = fmaf(g[c], __ldg(w + c), a);
-    ctx[e] = a * inv;
+#pragma unroll 8
+    for (int c = 0; c < C; ++c) a = fmaf(s_g[dd][c] - T, s_wv[e][c], a);
+    // 32^-0.5 (q scale, :238), 1 / HW (v, :240), softmax denominator
+    s_ctx[dd][e] = a * (0.17677669529663687f / (s_den[dd] * (float)HW));
   }
-  for (int co = 0; co < C; ++co) {
+  __syncthreads();
+  for (int o = t; o < 32 * C; o += 256) {
+    const int dd = o & 31, co = o >> 5;
     const float* w = wout + (long)co * 128 + head * 32;
     float a = 0.f;
 #pragma unroll
-    for (int e = 0; e < 32; ++e) a = fmaf(ctx[e], __ldg(w + e), a);
-    mt[((long)n * C + co) * 128 + d] = __float2bfloat16(a);
+    for (int e = 0; e < 32; ++e) a = fmaf(s_ctx[dd][e], __ldg(w + e), a);
+    mt[((long)n * C + co) * 128 + head * 32 + dd] = __float2bfloat16(a);
   }
 }
 
@@ -431,20 +514,21 @@ template <int C>
 struct ApTcCfg {
   static constexpr int kChunks = C / 64;
   static constexpr int kXBytes = kChunks * 16384;
-  static constexpr int kStages = C == 64 ? 4 : 2;
+  static constexpr int kStages = C == 64 ? 6 : 2;
   static constexpr int kWBytes = kChunks * 16384;          // Wq' [128 rows][C]
   static constexpr int kMBytes = 2 * C * 128;              // M^T [C rows][128 d]: two 64-d chunks of [C][128 B]
   static constexpr int kQBytes = 32768;                    // q_hat [128 px][128 d]: two 64-d chunks (K-major A of MMA2)
   static constexpr int kNQ = C == 64 ? 2 : 1;
   static constexpr int kOBytes = kChunks * 16384;          // output staging: one 64-channel slab per chunk
-  static constexpr int kNO = C == 64 ? 2 : 1;
+  static constexpr int kNO = 1;
   static constexpr int kOffW = kStages * kXBytes;
   static constexpr int kOffM = kOffW + kWBytes;
   static constexpr int kOffQ = kOffM + kMBytes;
   static constexpr int kOffO = kOffQ + kNQ * kQBytes;
-  static constexpr int kOffConst = kOffO + kNO * kOBytes;    // sq[128], bout[C], g2[C]  (<= 1.5 KB) | sx[2][2][128][2] (4 KB)
-  static constexpr int kOffSx = kOffConst + 2048;
-  static constexpr int kOffBar = kOffSx + 4096;
+  static constexpr int kOffConst = kOffO + kNO * kOBytes;    // sq[128], bout[C], g2[C]  (<= 1.5 KB)
+  static constexpr int kOffSx = kOffConst + 2048;            // partial-sum exchange of the output group: [2 uses][2 parities][2][128] float2
+  static constexpr int kOffRs = kOffSx + 8192;               // (mu, rstd) of x per row, [2 tile parities][128] float2
+  static constexpr int kOffBar = kOffRs + 2048;
   static constexpr int kSmemBytes = 1024 + kOffBar + 256;
 };
 
@@ -454,6 +538,7 @@ struct ApParams {
   const float* sq;
   const float* bout;
   const float* g2;
+  int dbg;
 };
 
 template <int C>
@@ -465,7 +550,6 @@ linattn_apply_kernel_tc(const __grid_constant__ CUtensorMap map_x, const __grid_
   constexpr int NCH = Cf::kChunks;
   constexpr int NQ = Cf::kNQ;
   constexpr int NO = Cf::kNO;
-  constexpr int NCB = C / 64;          // 32-column chunks of this thread's half of the output row
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
@@ -474,7 +558,7 @@ linattn_apply_kernel_tc(const __grid_constant__ CUtensorMap map_x, const __grid_
   float* s_sq = reinterpret_cast<float*>(gbase + Cf::kOffConst);
   float* s_b = s_sq + 128;
   float* s_g2 = s_b + C;
-  float2* s_sx = reinterpret_cast<float2*>(gbase + Cf::kOffSx);      // [tile parity][half][row]
+  float2* s_sx = reinterpret_cast<float2*>(gbase + Cf::kOffSx);      // [softmax | output group][tile parity][half][row]
   const uint32_t bar = base + Cf::kOffBar;
   auto xfull = [&](int s) { return bar + 8u * s; };
   auto xempty = [&](int s) { return bar + 8u * (S + s); };
@@ -485,7 +569,8 @@ linattn_apply_kernel_tc(const __grid_constant__ CUtensorMap map_x, const __grid_
   auto qempty = [&](int s) { return bar + 8u * (2 * S + 7 + s); };
   auto d2full = [&](int s) { return bar + 8u * (2 * S + 9 + s); };
   auto d2empty = [&](int s) { return bar + 8u * (2 * S + 11 + s); };
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(gbase + Cf::kOffBar + 8 * (2 * S + 13));
+  auto sfull = [&](int s) { return bar + 8u * (2 * S + 13 + s); };
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(gbase + Cf::kOffBar + 8 * (2 * S + 15));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n = blockIdx.x / p.cps, jc = blockIdx.x % p.cps;
@@ -499,16 +584,17 @@ linattn_apply_kernel_tc(const __grid_constant__ CUtensorMap map_x, const __grid_
     tma_prefetch_desc(&map_out);
     for (int s = 0; s < S; ++s) {
       mbar_init(xfull(s), 1);
-      mbar_init(xempty(s), kLaEpi);
+      mbar_init(xempty(s), kLaEpi / 2);        // the output group is the only reader of the x tile besides the tensor core
     }
     mbar_init(wfull, 1);
     for (int s = 0; s < 2; ++s) {
+      mbar_init(sfull(s), kLaEpi / 2);
       mbar_init(d1full(s), 1);
-      mbar_init(d1empty(s), kLaEpi);
-      mbar_init(qfull(s), kLaEpi);
+      mbar_init(d1empty(s), kLaEpi / 2);       // softmax group (warps 2..9)
+      mbar_init(qfull(s), kLaEpi / 2);
       mbar_init(qempty(s), 1);
       mbar_init(d2full(s), 1);
-      mbar_init(d2empty(s), kLaEpi);
+      mbar_init(d2empty(s), kLaEpi / 2);       // output group (warps 10..17)
     }
     fence_barrier_init();
   }
@@ -545,12 +631,14 @@ linattn_apply_kernel_tc(const __grid_constant__ CUtensorMap map_x, const __grid_
         mbar_wait(xfull(s), (i / S) & 1);
         tc_fence_after();
         const uint64_t xd = umma_desc_sw128(x_smem + s * Cf::kXBytes);
+        if (!(p.dbg & 8)) {
 #pragma unroll
-        for (int ch = 0; ch < NCH; ++ch)
+          for (int ch = 0; ch < NCH; ++ch)
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_bf16(tmem_base + as * 128, xd + (uint64_t)(ch * 1024 + 2 * k), wdesc + (uint64_t)(ch * 1024 + 2 * k), id1,
-                      (ch | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < 4; ++k)
+              umma_bf16(tmem_base + as * 128, xd + (uint64_t)(ch * 1024 + 2 * k), wdesc + (uint64_t)(ch * 1024 + 2 * k), id1,
+                        (ch | k) != 0 ? 1u : 0u);
+        }
         umma_commit(d1full(as));
       };
       if (nt > 0) mma1(0);
@@ -561,147 +649,193 @@ linattn_apply_kernel_tc(const __grid_constant__ CUtensorMap map_x, const __grid_
         mbar_wait(d2empty(as), ((i >> 1) & 1) ^ 1u);
         tc_fence_after();
         const uint64_t qd = umma_desc_sw128(q_smem + qb * Cf::kQBytes);
+        if (!(p.dbg & 2)) {
 #pragma unroll
-        for (int ks = 0; ks < 8; ++ks)       // K = 128 d: two 64-d chunks x four 16-element steps
-          umma_bf16(tmem_base + 256 + as * 128, qd + (uint64_t)((ks >> 2) * 1024 + 2 * (ks & 3)),
-                    mdesc + (uint64_t)((ks >> 2) * (C * 128 >> 4) + 2 * (ks & 3)), id2, ks != 0 ? 1u : 0u);
+          for (int ks = 0; ks < 8; ++ks)       // K = 128 d: two 64-d chunks x four 16-element steps
+            umma_bf16(tmem_base + 256 + as * 128, qd + (uint64_t)((ks >> 2) * 1024 + 2 * (ks & 3)),
+                      mdesc + (uint64_t)((ks >> 2) * (C * 128 >> 4) + 2 * (ks & 3)), id2, ks != 0 ? 1u : 0u);
+        }
         umma_commit(d2full(as));
         umma_commit(qempty(qb));
       }
     }
     __syncwarp();
   } else {
-    // ===================== epilogue warps 2..9 =====================
+    // ===================== epilogue warps 2..17: softmax group (2..9) and output group (10..17) =====================
+    // The two epilogues of a tile are bound by different pipes (softmax: MUFU, 128 x 128 exps; output: FMA + shared memory), so
+    // they run CONCURRENTLY on different warps, one tile apart, coupled only through the mbarriers (measured with FD_LA_DBG:
+    // run back to back by the same warps their times add up).  Inside a group the two warps of a TMEM lane quarter split the
+    // row's columns and exchange their partial row statistics through shared memory on a 64-thread named barrier.
     const int ew = warp - 2, et = threadIdx.x - 64;
-    const int quarter = warp & 3, half = ew >> 2;
+    const int grp = ew >> 3, half = (ew >> 2) & 1, quarter = warp & 3;
     const int row = quarter * 32 + lane;
     for (int i = et; i < 128 + 2 * C; i += kLaEpi)
       s_sq[i] = i < 128 ? __ldg(p.sq + i) : (i < 128 + C ? __ldg(p.bout + i - 128) : __ldg(p.g2 + i - 128 - C));
     named_bar_sync(1, kLaEpi);
     const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
-    uint32_t slab_count = 0;
 
-    auto epi_a = [&](int i) {       // q logits -> softmax over d per head -> q_hat tile
-      const int s = i % S, qb = i % NQ, as = i & 1;
-      mbar_wait(xfull(s), (i / S) & 1);
-      float mu, r, sigma;
-      la_row_stats<C>(x_smem + s * Cf::kXBytes, row, p.eps, mu, r, sigma);
-      const float nrm = -r * mu;
-      mbar_wait(qempty(qb), ((i / NQ) & 1) ^ 1u);
-      mbar_wait(d1full(as), (i >> 1) & 1);
-      tc_fence_after();
-#pragma unroll
-      for (int hh = 0; hh < 2; ++hh) {
-        const int col0 = (half * 2 + hh) * 32;        // one head = 32 columns = one TMEM load
-        uint32_t acc[32];
-        tmem_ld32(tmem_base + lane_off + (uint32_t)(as * 128 + col0), acc);
+    float2* s_rs = reinterpret_cast<float2*>(gbase + Cf::kOffRs);
+    if (grp == 0) {
+      // ---- q logits -> softmax over d per head -> q_hat tile (K-major A operand of MMA2).  The row statistics of x come from
+      // the output group (it has the slack); both heads of a thread are processed interleaved (64 independent exps in flight).
+      for (int i = 0; i < nt; ++i) {
+        const int qb = i % NQ, as = i & 1;
+        mbar_wait(sfull(i & 1), (i >> 1) & 1);
+        const float2 st = s_rs[(i & 1) * 128 + row];
+        const float r = st.y;
+        const uint64_t nrm2 = pk2(-r * st.x, -r * st.x), r2 = pk2(r, r);
+        mbar_wait(qempty(qb), ((i / NQ) & 1) ^ 1u);
+        mbar_wait(d1full(as), (i >> 1) & 1);
+        tc_fence_after();
+        uint32_t acc[2][32];
+        tmem_ld32(tmem_base + lane_off + (uint32_t)(as * 128 + half * 64), acc[0]);
+        tmem_ld32(tmem_base + lane_off + (uint32_t)(as * 128 + half * 64 + 32), acc[1]);
         tmem_ld_wait();
-        if (hh == 1) {
-          tc_fence_before();
-          mbar_arrive(d1empty(as));
+        tc_fence_before();
+        mbar_arrive(d1empty(as));
+        if (p.dbg & 1) {
+          fence_proxy_async_smem();
+          mbar_arrive(qfull(qb));
+          continue;
         }
-        float v[32];
-        float mx = -INFINITY;
+        float mx[2] = {-INFINITY, -INFINITY};
 #pragma unroll
-        for (int j4 = 0; j4 < 8; ++j4) {
-          const float4 s4 = *reinterpret_cast<const float4*>(s_sq + col0 + j4 * 4);
-          v[j4 * 4 + 0] = fmaf(r, __uint_as_float(acc[j4 * 4 + 0]), nrm * s4.x);
-          v[j4 * 4 + 1] = fmaf(r, __uint_as_float(acc[j4 * 4 + 1]), nrm * s4.y);
-          v[j4 * 4 + 2] = fmaf(r, __uint_as_float(acc[j4 * 4 + 2]), nrm * s4.z);
-          v[j4 * 4 + 3] = fmaf(r, __uint_as_float(acc[j4 * 4 + 3]), nrm * s4.w);
-          mx = fmaxf(mx, fmaxf(fmaxf(v[j4 * 4], v[j4 * 4 + 1]), fmaxf(v[j4 * 4 + 2], v[j4 * 4 + 3])));
+        for (int hh = 0; hh < 2; ++hh) {
+          const int col0 = (half * 2 + hh) * 32;        // one head = 32 columns
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const ulonglong2 s4 = *reinterpret_cast<const ulonglong2*>(s_sq + col0 + j4 * 4);
+            const float2 a0 = up2(ffma2(r2, pk2u(acc[hh][j4 * 4 + 0], acc[hh][j4 * 4 + 1]), fmul2(nrm2, s4.x)));
+            const float2 a1 = up2(ffma2(r2, pk2u(acc[hh][j4 * 4 + 2], acc[hh][j4 * 4 + 3]), fmul2(nrm2, s4.y)));
+            acc[hh][j4 * 4 + 0] = __float_as_uint(a0.x);
+            acc[hh][j4 * 4 + 1] = __float_as_uint(a0.y);
+            acc[hh][j4 * 4 + 2] = __float_as_uint(a1.x);
+            acc[hh][j4 * 4 + 3] = __float_as_uint(a1.y);
+            mx[hh] = fmaxf(mx[hh], fmaxf(fmaxf(a0.x, a0.y), fmaxf(a1.x, a1.y)));
+          }
         }
-        float sum = 0.f;
+        float sum[2] = {0.f, 0.f};
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          v[j] = la_ex2(v[j] - mx);
-          sum += v[j];
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            const float e = la_ex2(__uint_as_float(acc[hh][j]) - mx[hh]);
+            acc[hh][j] = __float_as_uint(e);
+            sum[hh] += e;
+          }
         }
-        const float inv = __fdividef(1.f, sum);
         const uint32_t rbase = q_smem + qb * Cf::kQBytes + half * 16384 + row * 128;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const uint32_t piece = (uint32_t)(hh * 4 + q) ^ (uint32_t)(row & 7);
-          la_st16(rbase + piece * 16u, fd_pack_bf16(v[q * 8] * inv, v[q * 8 + 1] * inv), fd_pack_bf16(v[q * 8 + 2] * inv, v[q * 8 + 3] * inv),
-                  fd_pack_bf16(v[q * 8 + 4] * inv, v[q * 8 + 5] * inv), fd_pack_bf16(v[q * 8 + 6] * inv, v[q * 8 + 7] * inv));
-        }
-      }
-      fence_proxy_async_smem();
-      mbar_arrive(qfull(qb));
-    };
-
-    auto epi_b = [&](int i) {       // q_hat M + b -> LayerNorm_g2 -> + x -> bf16 -> TMA store
-      const int s = i % S, as = i & 1;
-      mbar_wait(d2full(as), (i >> 1) & 1);
-      tc_fence_after();
-      float o[NCB * 32];
-      float sm = 0.f, sq2 = 0.f;
+        for (int hh = 0; hh < 2; ++hh) {
+          const float inv = __fdividef(1.f, sum[hh]);
+          const uint64_t inv2 = pk2(inv, inv);
 #pragma unroll
-      for (int cb = 0; cb < NCB; ++cb) {
-        const int col0 = half * (C / 2) + cb * 32;
-        uint32_t acc[32];
-        tmem_ld32(tmem_base + lane_off + (uint32_t)(256 + as * 128 + col0), acc);
-        tmem_ld_wait();
+          for (int q = 0; q < 4; ++q) {
+            uint32_t w[4];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float x = __uint_as_float(acc[j]) + s_b[col0 + j];
-          o[cb * 32 + j] = x;
-          sm += x;
-          sq2 = fmaf(x, x, sq2);
-        }
-      }
-      tc_fence_before();
-      mbar_arrive(d2empty(as));
-      float2* sx = s_sx + (i & 1) * 256;
-      sx[half * 128 + row] = make_float2(sm, sq2);
-      const uint32_t ob = slab_count % NO;
-      ++slab_count;
-      if (ew == 0 && elect_one_sync()) tma_store_wait_read<NO - 1>();      // the store that last used this staging buffer has read it
-      named_bar_sync(2, kLaEpi);
-      const float2 other = sx[(half ^ 1) * 128 + row];
-      const float mean = (sm + other.x) * (1.f / C);
-      const float var = fmaxf((sq2 + other.y) * (1.f / C) - mean * mean, 0.f);
-      const float rstd = rsqrtf(var + p.eps);
-#pragma unroll
-      for (int cb = 0; cb < NCB; ++cb) {
-        const int col0 = half * (C / 2) + cb * 32;       // absolute output channel of o[cb * 32]
-        const int chunk = col0 >> 6, g0 = (col0 & 63) >> 3;
-        const uint32_t xrow = x_smem + s * Cf::kXBytes + chunk * 16384 + row * 128;
-        const uint32_t orow = o_smem + ob * Cf::kOBytes + chunk * 16384 + row * 128;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const uint32_t piece = (uint32_t)(g0 + q) ^ (uint32_t)(row & 7);
-          const uint4 xr = la_ld16(xrow + piece * 16u);
-          const uint32_t xw[4] = {xr.x, xr.y, xr.z, xr.w};
-          uint32_t ow[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float2 f = fd_unpack_bf16(xw[e]);
-            const int j = cb * 32 + q * 8 + e * 2;
-            const float y0 = fmaf((o[j] - mean) * rstd, s_g2[col0 + q * 8 + e * 2], f.x);
-            const float y1 = fmaf((o[j + 1] - mean) * rstd, s_g2[col0 + q * 8 + e * 2 + 1], f.y);
-            ow[e] = fd_pack_bf16(y0, y1);
+            for (int e = 0; e < 4; ++e) {
+              const float2 f = up2(fmul2(pk2u(acc[hh][q * 8 + e * 2], acc[hh][q * 8 + e * 2 + 1]), inv2));
+              w[e] = fd_pack_bf16(f.x, f.y);
+            }
+            const uint32_t piece = (uint32_t)(hh * 4 + q) ^ (uint32_t)(row & 7);
+            la_st16(rbase + piece * 16u, w[0], w[1], w[2], w[3]);
           }
-          la_st16(orow + piece * 16u, ow[0], ow[1], ow[2], ow[3]);
+        }
+        fence_proxy_async_smem();
+        mbar_arrive(qfull(qb));
+      }
+    } else {
+      // ---- q_hat M + b -> LayerNorm_g2 -> + x -> bf16 -> TMA store
+      constexpr int CPT = C / 2;           // output channels per thread (32 or 64)
+      const int gw = ew - 8;               // 0..7 inside the group
+      const int col0 = half * CPT;
+      uint32_t slab_count = 0;
+      // LayerNorm statistics of the x rows for the softmax group, one tile ahead of this group's own work.  No "empty"
+      // barrier is needed for s_rs: statistics of tile j + 2 are written after this group finished the output of tile j,
+      // which needed MMA2(j), which needed the softmax group to be done with tile j (and its statistics).
+      auto x_stats = [&](int j) {
+        const int sj = j % S;
+        mbar_wait(xfull(sj), (j / S) & 1);
+        float mu = 0.f, r = 1.f, sigma = 1.f;
+        if (!(p.dbg & 4)) la_row_stats2<C>(x_smem + sj * Cf::kXBytes, row, half, 8 + quarter, s_sx + (j & 1) * 256, p.eps, mu, r, sigma);
+        if (half == 0) s_rs[(j & 1) * 128 + row] = make_float2(mu, r);
+        mbar_arrive(sfull(j & 1));
+      };
+      if (nt > 0) x_stats(0);
+      for (int i = 0; i < nt; ++i) {
+        const int s = i % S, as = i & 1;
+        if (i + 1 < nt) x_stats(i + 1);
+        mbar_wait(d2full(as), (i >> 1) & 1);
+        tc_fence_after();
+        uint64_t o[CPT / 2];
+        uint64_t sm2 = 0ull, sq22 = 0ull;
+#pragma unroll
+        for (int cb = 0; cb < CPT / 32; ++cb) {
+          uint32_t acc[32];
+          tmem_ld32(tmem_base + lane_off + (uint32_t)(256 + as * 128 + col0 + cb * 32), acc);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const uint64_t x = fadd2(pk2u(acc[2 * j], acc[2 * j + 1]), *reinterpret_cast<const uint64_t*>(s_b + col0 + cb * 32 + 2 * j));
+            o[cb * 16 + j] = x;
+            sm2 = fadd2(sm2, x);
+            sq22 = ffma2(x, x, sq22);
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(d2empty(as));
+        const uint32_t ob = slab_count % NO;
+        ++slab_count;
+        if (p.dbg & 16) {
+          mbar_arrive(xempty(s));
+          continue;
+        }
+        const float2 smf = up2(sm2), sqf = up2(sq22);
+        const float sm = smf.x + smf.y, sq2 = sqf.x + sqf.y;
+        float2* sx = s_sx + 512 + (i & 1) * 256;
+        sx[half * 128 + row] = make_float2(sm, sq2);
+        if (gw == 0 && elect_one_sync()) tma_store_wait_read<NO - 1>();      // the store that last used this staging buffer has read it
+        named_bar_sync(2, kLaEpi / 2);       // (also orders the statistics exchange: all 8 warps are past their stores to sx)
+        const float2 other = sx[(half ^ 1) * 128 + row];
+        const float mean = (sm + other.x) * (1.f / C);
+        const float var = fmaxf((sq2 + other.y) * (1.f / C) - mean * mean, 0.f);
+        const float rstd = rsqrtf(var + p.eps);
+        const uint64_t rstd2 = pk2(rstd, rstd), nmr2 = pk2(-mean * rstd, -mean * rstd);
+#pragma unroll
+        for (int cb = 0; cb < CPT / 32; ++cb) {
+          const int c0 = col0 + cb * 32;       // absolute output channel of o[cb * 16]
+          const int chunk = c0 >> 6, g0 = (c0 & 63) >> 3;
+          const uint32_t xrow = x_smem + s * Cf::kXBytes + chunk * 16384 + row * 128;
+          const uint32_t orow = o_smem + ob * Cf::kOBytes + chunk * 16384 + row * 128;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const uint32_t piece = (uint32_t)(g0 + q) ^ (uint32_t)(row & 7);
+            const uint4 xr = la_ld16(xrow + piece * 16u);
+            const uint32_t xw[4] = {xr.x, xr.y, xr.z, xr.w};
+            uint32_t ow[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 f = fd_unpack_bf16(xw[e]);
+              // ((o - mean) rstd) g2 + x
+              const uint64_t nrm = ffma2(o[cb * 16 + q * 4 + e], rstd2, nmr2);
+              const float2 y = up2(ffma2(nrm, *reinterpret_cast<const uint64_t*>(s_g2 + c0 + q * 8 + e * 2), pk2(f.x, f.y)));
+              ow[e] = fd_pack_bf16(y.x, y.y);
+            }
+            la_st16(orow + piece * 16u, ow[0], ow[1], ow[2], ow[3]);
+          }
+        }
+        fence_proxy_async_smem();
+        mbar_arrive(xempty(s));              // this group's reads of the x tile (the residual) are done
+        named_bar_sync(3, kLaEpi / 2);
+        if (gw == 0 && elect_one_sync() && !(p.dbg & 32)) {
+          for (int ch = 0; ch < NCH; ++ch)
+            la_tma_store_3d(&map_out, o_smem + ob * Cf::kOBytes + ch * 16384, ch * 64, (t0 + i) * kTilePx, n);
+          tma_store_commit();
         }
       }
-      fence_proxy_async_smem();
-      mbar_arrive(xempty(s));              // this thread's reads of the x tile (statistics in epi_a, residual here) are done
-      named_bar_sync(3, kLaEpi);
-      if (ew == 0 && elect_one_sync()) {
-        for (int ch = 0; ch < NCH; ++ch)
-          la_tma_store_3d(&map_out, o_smem + ob * Cf::kOBytes + ch * 16384, ch * 64, (t0 + i) * kTilePx, n);
-        tma_store_commit();
-      }
-    };
-
-    if (nt > 0) epi_a(0);
-    for (int i = 0; i < nt; ++i) {
-      if (i + 1 < nt) epi_a(i + 1);
-      epi_b(i);
+      __syncwarp();
+      if (gw == 0 && elect_one_sync()) tma_store_wait_all();
     }
-    __syncwarp();
-    if (ew == 0 && elect_one_sync()) tma_store_wait_all();
   }
   tc_fence_before();
   __syncthreads();
@@ -753,12 +887,14 @@ int run_tc(const void* x, const void* wk, const float* sk, const float* mk, cons
     FD_CUDA(cudaFuncSetAttribute(linattn_apply_kernel_tc<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, ApTcCfg<C>::kSmemBytes));
     attr_set = true;
   }
-  CtxParams cp{N, HW, cps, tiles, eps, sk, mk, partial};
+  static int la_dbg = -1;
+  if (la_dbg < 0) { const char* e = getenv("FD_LA_DBG"); la_dbg = e ? atoi(e) : 0; }
+  CtxParams cp{N, HW, cps, tiles, eps, sk, mk, partial, la_dbg & 15};
   FD_CUDA(fd_launch_pdl(linattn_ctx_kernel<C>, dim3(N * cps), dim3(kLaThreads), CtxCfg<C>::kSmemBytes, st, map_x, map_wk, cp));
   FD_LAUNCH_CHECK();
-  linattn_tc_combine_kernel<C><<<N, 128, 0, st>>>(partial, wv, wout, mt, cps, HW);
+  linattn_tc_combine_kernel<C><<<dim3(N, 4), 256, 0, st>>>(partial, wv, wout, mt, cps, HW);
   FD_LAUNCH_CHECK();
-  ApParams ap{N, HW, cps, tiles, eps, sq, bout, g2};
+  ApParams ap{N, HW, cps, tiles, eps, sq, bout, g2, la_dbg >> 4};
   FD_CUDA(fd_launch_pdl(linattn_apply_kernel_tc<C>, dim3(N * cps), dim3(kLaThreads), ApTcCfg<C>::kSmemBytes, st, map_x, map_wq, map_m,
                         map_out, ap));
   FD_LAUNCH_CHECK();
