@@ -10,6 +10,8 @@
 //   (flash-style) kernel: S and P never leave registers, so the reference's N x N matrix (6.3 GB at
 //   batch 8, 440x1024) is never materialised.  bf16 mma.sync m16n8k16 with fp32 accumulation and
 //   online softmax; 1.6 % of the forward FLOPs.
+#include <stdlib.h>
+
 #include "fd_mma.cuh"
 
 using namespace fdmma;
@@ -723,6 +725,8 @@ int launch_apply_fused(const void* x, const float* g1, const void* wq, const voi
 
 }  // namespace
 
+int fd_attention_tc_launch(const void* qkv, void* out, float* lse, int N, int HW, cudaStream_t st);   // fd_attention_tc.cu
+
 extern "C" {
 
 size_t fd_linattn_workspace_floats(int N, int HW) {
@@ -817,6 +821,15 @@ int fd_attention(const void* qkv, void* out, int N, int HW, void* stream) {
 int fd_attention_lse(const void* qkv, void* out, float* lse, int N, int HW, void* stream) {
   FD_REQUIRE(qkv && out && N > 0 && HW > 0, "attention: bad argument");
   FD_REQUIRE(N <= 65535, "attention: batch too large");
+  {
+    // default: the tcgen05 / TMEM / TMA kernel (fd_attention_tc.cu); FD_ATTN_TC=0 selects the mma.sync kernel below
+    static int tc = -1;
+    if (tc < 0) {
+      const char* e = getenv("FD_ATTN_TC");
+      tc = e ? atoi(e) : 1;
+    }
+    if (tc) return fd_attention_tc_launch(qkv, out, lse, N, HW, (cudaStream_t)stream);
+  }
   const float scale_log2 = 0.17677669529663687f * 1.4426950408889634f;   // 32^-0.5 * log2(e)
   attention_kernel<<<dim3((HW + kBQ - 1) / kBQ, kHeads, N), 256, 0, (cudaStream_t)stream>>>(
       static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(out), lse, HW, scale_log2);
