@@ -320,6 +320,50 @@ def run_torch_gpu(args, rank: int, local_rank: int):
     _emit(line)
 
 
+def tiny_config(dev):
+    """BASELINE configs[0]: the reference's own CPU-runnable case -- batch 1, 64x128 frame pair, target=flow.  The reference
+    algorithm (oracle port, all host threads) is timed on one full DDIM-50 sampling pass and on 20 of the 1000 DDPM steps
+    it runs as shipped (flow_diffuser.py:118-127 never passes sampling_timesteps); this implementation on DDIM-50 and the
+    full DDPM-1000 chain, CUDA-graph off (launch-bound at this size)."""
+    from oracle import flowdiff_oracle as O
+    from opticalflowdiffusion_b200 import FlowDiffuser
+    from opticalflowdiffusion_b200.config import compose
+    h, w = 64, 128
+    res = {"shape": [1, 2, h, w]}
+    for name, steps in (("ddim50", 50), ("ddpm1000", None)):
+        ov = ["algorithm.target=flow", f"algorithm.image_size=[{h},{w}]", "algorithm.return_all_timesteps=false"]
+        if steps:
+            ov.append(f"algorithm.sampling_timesteps={steps}")
+        torch.manual_seed(0)
+        algo = FlowDiffuser(compose(ov).algorithm).to(dev)
+        cond = (O.synthetic_frames(1, h, w, seed=0) * 2 - 1).to(dev)
+        zero = torch.zeros(1, 2, h, w, device=dev)
+        algo.sample(cond, zero)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        algo.sample(cond, zero)
+        torch.cuda.synchronize()
+        res[name + "_gpu_s"] = time.perf_counter() - t0
+        if name == "ddim50":
+            sd = {k: v.detach().cpu() for k, v in algo.unet.state_dict().items()}
+    sched = O.make_schedule(TIMESTEPS)
+    cond_c = O.synthetic_frames(1, h, w, seed=0) * 2 - 1
+    x = torch.randn(1, 2, h, w, generator=torch.Generator().manual_seed(1))
+    with torch.no_grad():
+        O.unet_forward(sd, x, cond_c, torch.tensor([999]))            # warm-up
+        t0 = time.perf_counter()
+        O.ddim_sample(sd, sched, x, cond_c, TIMESTEPS, 50)
+        res["ddim50_reference_cpu_s"] = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        for tt in range(999, 979, -1):
+            out = O.unet_forward(sd, x, cond_c, torch.tensor([tt]))
+            x, _ = O.ddpm_update(sched, x, out, tt, torch.zeros_like(x))
+        res["ddpm1000_reference_cpu_s_extrapolated"] = (time.perf_counter() - t0) * 50.0
+    res["cores"] = torch.get_num_threads()
+    res["ddim50_speedup"] = res["ddim50_reference_cpu_s"] / res["ddim50_gpu_s"]
+    return res
+
+
 # ------------------------------------------------------------------------------------------------
 def run_ours(args, rank: int, world: int, local_rank: int):
     import torch.distributed as dist
@@ -436,6 +480,9 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                                   "numbers in profiles/r2_parity_headline.json"}
         del sd_o, x_o, cond_o, out_o, got
     default_wl = CONFIG["name"] == "ddim50_436x1024"
+    tiny = None
+    if world == 1 and rank == 0 and default_wl and not args.no_cpu_baseline:
+        tiny = tiny_config(dev)
     lib_base = None
     if world == 1 and rank == 0 and not args.no_gpu_baseline:
         del algo
@@ -477,6 +524,8 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     }
     if parity is not None:
         line["parity"] = parity
+    if tiny is not None:
+        line["config1_tiny"] = tiny
     if lib_base is not None:
         line["gpu_library_baseline"] = lib_base
     if train is not None:

@@ -60,8 +60,15 @@ class GpuAugmentor:
                     ffloats[f][4], ffloats[f][5] = float(k1[0]), float(k1[1])
         probe = torch.empty((1, 1, H, W))
         for i in range(B):                                  # whole_augs (augmentation.py:34-56)
+            # RandomApply draws once; the RandomHorizontalFlip(p=1.0) / RandomVerticalFlip(p=1.0) it wraps draws AGAIN
+            # (augmentation.py:34-42): the second number is consumed to keep the stream aligned with the reference
+            # (found by tests/test_augmentor_reference_golden.py against the reference's own Augmentor)
             iints[i][0] = int(torch.rand(1) < 0.3)
+            if iints[i][0]:
+                torch.rand(1)
             iints[i][1] = int(torch.rand(1) < 0.3)
+            if iints[i][1]:
+                torch.rand(1)
             if torch.rand(1) < 0.15:
                 top, left, h, w = T.RandomResizedCrop.get_params(probe, [0.8, 1.0], [0.9, 1.1])
                 iints[i][2:7] = [1, int(top), int(left), int(h), int(w)]

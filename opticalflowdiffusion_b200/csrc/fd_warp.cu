@@ -14,95 +14,11 @@
 // bit-identical to the reference's CPU output (oracle/flowdiff_oracle.py:backwarp).
 #include <stdlib.h>
 
-#include "fd_common.cuh"
+#include "fd_warp_common.cuh"
+
+using namespace fdwarp;
 
 namespace {
-
-struct BwGeom {
-  float wm1n, hm1n;    // max(W-1,1), max(H-1,1): the reference's normalisation divisor
-  float half_w, half_h;  // (W-1)/2, (H-1)/2: grid_sample's align_corners un-normalisation
-  float wl, hl;        // W-1, H-1 as float (bounds)
-  int H, W;
-};
-
-static BwGeom make_geom(int H, int W) {
-  BwGeom g;
-  g.H = H;
-  g.W = W;
-  g.wm1n = (float)(W - 1 > 1 ? W - 1 : 1);
-  g.hm1n = (float)(H - 1 > 1 ? H - 1 : 1);
-  g.half_w = (float)((double)(W - 1) / 2.0);
-  g.half_h = (float)((double)(H - 1) / 2.0);
-  g.wl = (float)(W - 1);
-  g.hl = (float)(H - 1);
-  return g;
-}
-
-struct BwTaps {
-  float nw, ne, sw, se;  // bilinear weights
-  float wx, ex, ny, sy;  // fractional parts and complements
-  int x0, y0;
-  bool okx0, okx1, oky0, oky1;
-};
-
-// flow_dx = flow[:,1], flow_dy = flow[:,0] (the reference flips the channels, warp.py:105)
-__device__ __forceinline__ void bw_taps(float flow_dx, float flow_dy, int x, int y, const BwGeom& g, BwTaps& t) {
-  const float vx = __fadd_rn((float)x, flow_dx);
-  const float vy = __fadd_rn((float)y, flow_dy);
-  const float gx = __fsub_rn(__fdiv_rn(__fmul_rn(2.f, vx), g.wm1n), 1.f);
-  const float gy = __fsub_rn(__fdiv_rn(__fmul_rn(2.f, vy), g.hm1n), 1.f);
-  const float ix = __fmul_rn(__fadd_rn(gx, 1.f), g.half_w);
-  const float iy = __fmul_rn(__fadd_rn(gy, 1.f), g.half_h);
-  const float x0f = floorf(ix), y0f = floorf(iy);
-  const float x1f = __fadd_rn(x0f, 1.f), y1f = __fadd_rn(y0f, 1.f);
-  t.wx = __fsub_rn(ix, x0f);
-  t.ex = __fsub_rn(1.f, t.wx);
-  t.ny = __fsub_rn(iy, y0f);
-  t.sy = __fsub_rn(1.f, t.ny);
-  t.nw = __fmul_rn(t.sy, t.ex);
-  t.ne = __fmul_rn(t.sy, t.wx);
-  t.sw = __fmul_rn(t.ny, t.ex);
-  t.se = __fmul_rn(t.ny, t.wx);
-  t.okx0 = (x0f >= 0.f) && (x0f <= g.wl);
-  t.okx1 = (x1f >= 0.f) && (x1f <= g.wl);
-  t.oky0 = (y0f >= 0.f) && (y0f <= g.hl);
-  t.oky1 = (y1f >= 0.f) && (y1f <= g.hl);
-  t.x0 = (t.okx0 || t.okx1) ? (int)x0f : 0;
-  t.y0 = (t.oky0 || t.oky1) ? (int)y0f : 0;
-}
-
-__device__ __forceinline__ float bw_mask(const BwTaps& t) {
-  float m = __fmul_rn((t.okx0 && t.oky0) ? 1.f : 0.f, t.nw);
-  m = __fmaf_rn((t.okx1 && t.oky0) ? 1.f : 0.f, t.ne, m);
-  m = __fmaf_rn((t.okx0 && t.oky1) ? 1.f : 0.f, t.sw, m);
-  m = __fmaf_rn((t.okx1 && t.oky1) ? 1.f : 0.f, t.se, m);
-  if (m < 0.999f) m = 0.f;   // warp.py:116
-  if (m > 0.f) m = 1.f;      // warp.py:117
-  return m;
-}
-
-struct BwVals {
-  float nw, ne, sw, se;
-};
-
-__device__ __forceinline__ BwVals bw_gather(const float* __restrict__ plane, const BwTaps& t, int W) {
-  BwVals v;
-  const float* r0 = plane + (long)t.y0 * W + t.x0;
-  const float* r1 = r0 + W;
-  v.nw = (t.okx0 && t.oky0) ? __ldg(r0) : 0.f;
-  v.ne = (t.okx1 && t.oky0) ? __ldg(r0 + 1) : 0.f;
-  v.sw = (t.okx0 && t.oky1) ? __ldg(r1) : 0.f;
-  v.se = (t.okx1 && t.oky1) ? __ldg(r1 + 1) : 0.f;
-  return v;
-}
-
-__device__ __forceinline__ float bw_sample(const BwVals& v, const BwTaps& t) {
-  float o = __fmul_rn(v.nw, t.nw);
-  o = __fmaf_rn(v.ne, t.ne, o);
-  o = __fmaf_rn(v.sw, t.sw, o);
-  o = __fmaf_rn(v.se, t.se, o);
-  return o;
-}
 
 template <int VEC>
 struct Vec;
@@ -462,7 +378,28 @@ static int check_dims(int B, int C, int H, int W) {
   return FD_OK;
 }
 
+static bool use_tiled(int W) {
+  static int on = -1;
+  if (on < 0) {
+    // default OFF: measured on B200 at 8x436x1024 the tiled kernels are SLOWER (photo_epe fwd 144 vs 77 us, bwd 288 vs
+    // 247 us, backwarp fwd 111 vs 88 us): a 16-row tile needs a +-12 pixel halo, so the window fill moves as many bytes
+    // through L2 as the per-tap gathers did, and the per-channel barriers + 128 registers cost occupancy.  These kernels
+    // are bound by instruction issue / latency, not by the gather (profiles/r2_warp_tiled_ab.txt).
+    const char* e = getenv("FD_WARP_TILED");
+    on = e ? atoi(e) : 0;
+  }
+  return on && W % 4 == 0;
+}
+
 }  // namespace
+
+// fd_warp_tiled.cu: 16 x 128 pixel tiles with the sampled frame staged in shared memory (default when W % 4 == 0)
+int fd_warp_tiles(int B, int H, int W);
+int fd_warp_fwd_tiled(int mode, const float* frame1, const float* frame2, const float* flow, const float* flow_gt, float* out,
+                      float* mask, float* partials, int B, int C, int H, int W, cudaStream_t st);
+int fd_warp_bwd_tiled(int mode, const float* frame1, const float* frame2, const float* flow, const float* flow_gt, const float* gout,
+                      const float* sums, float g_photo, float g_epe, float* gflow, float* gframe2, int B, int C, int H, int W,
+                      cudaStream_t st);
 
 extern "C" {
 
@@ -471,6 +408,7 @@ int fd_backwarp_fwd(const float* image, const float* flow, float* out, float* ma
   if (int e = check_dims(B, C, H, W)) return e;
   FD_REQUIRE(image && flow && out, "backwarp_fwd: null pointer");
   cudaStream_t st = (cudaStream_t)stream;
+  if (use_tiled(W)) return fd_warp_fwd_tiled(0, nullptr, image, flow, nullptr, out, mask, nullptr, B, C, H, W, st);
   const BwGeom g = make_geom(H, W);
   const int vec = pick_vec(W);
   const long items = (long)B * H * (W / vec);
@@ -491,6 +429,7 @@ int fd_backwarp_bwd(const float* image, const float* flow, const float* gout, fl
   cudaStream_t st = (cudaStream_t)stream;
   const BwGeom g = make_geom(H, W);
   if (gimage) FD_CUDA(cudaMemsetAsync(gimage, 0, sizeof(float) * (size_t)B * C * H * W, st));
+  if (use_tiled(W)) return fd_warp_bwd_tiled(0, nullptr, image, flow, nullptr, gout, nullptr, 0.f, 0.f, gflow, gimage, B, C, H, W, st);
   const int vec = pick_vec(W);
   const long items = (long)B * H * (W / vec);
   if (vec == 4)
@@ -505,7 +444,8 @@ int fd_backwarp_bwd(const float* image, const float* flow, const float* gout, fl
 
 size_t fd_photo_epe_workspace_floats(int B, int H, int W) {
   const long items = (long)B * H * (W / pick_vec(W));
-  return (size_t)photo_grid(items) * 3;
+  const size_t a = (size_t)photo_grid(items) * 3, b = (size_t)fd_warp_tiles(B, H, W) * 3;
+  return a > b ? a : b;
 }
 
 int fd_backwarp_photo_epe_fwd(const float* frame1, const float* frame2, const float* flow, const float* flow_gt,
@@ -513,6 +453,12 @@ int fd_backwarp_photo_epe_fwd(const float* frame1, const float* frame2, const fl
   if (int e = check_dims(B, C, H, W)) return e;
   FD_REQUIRE(frame1 && frame2 && flow && flow_gt && sums && partials, "photo_epe_fwd: null pointer");
   cudaStream_t st = (cudaStream_t)stream;
+  if (use_tiled(W)) {
+    if (int e = fd_warp_fwd_tiled(1, frame1, frame2, flow, flow_gt, nullptr, nullptr, partials, B, C, H, W, st)) return e;
+    finalize_sums_kernel<3><<<1, 256, 0, st>>>(partials, fd_warp_tiles(B, H, W), sums, (float)((double)B * H * W), 3);
+    FD_LAUNCH_CHECK();
+    return FD_OK;
+  }
   const BwGeom g = make_geom(H, W);
   const int vec = pick_vec(W);
   const long items = (long)B * H * (W / vec);
@@ -537,6 +483,8 @@ int fd_backwarp_photo_epe_bwd(const float* frame1, const float* frame2, const fl
   cudaStream_t st = (cudaStream_t)stream;
   const BwGeom g = make_geom(H, W);
   if (gframe2) FD_CUDA(cudaMemsetAsync(gframe2, 0, sizeof(float) * (size_t)B * C * H * W, st));
+  if (use_tiled(W))
+    return fd_warp_bwd_tiled(1, frame1, frame2, flow, flow_gt, nullptr, sums, g_photo, g_epe, gflow, gframe2, B, C, H, W, st);
   const int vec = pick_vec(W);
   const long items = (long)B * H * (W / vec);
   if (vec == 4)

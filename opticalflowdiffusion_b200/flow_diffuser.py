@@ -96,9 +96,11 @@ class Augmentor:
     def _geometric(self, item: Tensor) -> Tensor:
         TF = self._T.functional
         if torch.rand(1) < 0.3:
+            torch.rand(1)      # the wrapped RandomHorizontalFlip(p=1.0) draws its own number (augmentation.py:34-37)
             item = TF.hflip(item)
             item[:, -1] = -item[:, -1]
         if torch.rand(1) < 0.3:
+            torch.rand(1)      # RandomVerticalFlip(p=1.0), :39-42
             item = TF.vflip(item)
             item[:, -2] = -item[:, -2]
         if torch.rand(1) < 0.15:
