@@ -69,7 +69,9 @@ template <int BLOCK_N, int SH = 0>
 struct Cfg {
   static constexpr int kBTileBytes = BLOCK_N * kBlockK * 2;
   static constexpr int kStageBytes = kATileBytes + kBTileBytes;
-  static constexpr int kStages = SH ? 3 : (BLOCK_N == 64 ? 7 : (BLOCK_N == 128 ? 6 : 4));
+  // SH: the tile is a pure stream (2-4 K-blocks, then 16-64 KB of output): the ring depth sets how many bytes an SM keeps in
+  // flight against the DRAM latency -- 3 stages left the 128 -> 64 res_convs at 4.0 TB/s
+  static constexpr int kStages = SH ? (BLOCK_N == 64 ? 6 : (BLOCK_N == 128 ? 5 : 3)) : (BLOCK_N == 64 ? 7 : (BLOCK_N == 128 ? 6 : 4));
   static constexpr int kStoreBufs = SH ? (BLOCK_N / 64 > 2 ? BLOCK_N / 64 : 2) : (BLOCK_N == 64 ? 2 : 1);   // staging slabs
   static constexpr int kTmemCols = 2 * BLOCK_N;
   static constexpr int kTailBytes = 256 /*barriers*/ + 2 * BLOCK_N * 4 /*bias*/ + kEpiWarps * 16 * 4 /*stats*/ + 64 +

@@ -424,15 +424,18 @@ __global__ void __launch_bounds__(256) final_conv_kernel(const __nv_bfloat16* __
   float br[4];
 #pragma unroll
   for (int o = 0; o < 4; ++o) br[o] = o < Cout ? __ldg(bias + o) : 0.f;
-  const long total = (long)N * HW;
-  const long gstride = ((long)gridDim.x * blockDim.x) >> 2;
-  const long iters = (total + gstride - 1) / gstride;
-  long i = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 2;
-  for (long it = 0; it < iters; ++it, i += gstride) {
+  // 32-bit pixel arithmetic (the host checks N * HW < 2^31): the three 64-bit divisions per pixel of the first version cost
+  // more instructions than the 64 FMAs
+  const unsigned total = (unsigned)((long)N * HW);
+  const unsigned gstride = (gridDim.x * blockDim.x) >> 2;
+  const unsigned uHW = (unsigned)HW, uW = (unsigned)W;
+  const unsigned iters = (total + gstride - 1) / gstride;
+  unsigned i = (blockIdx.x * blockDim.x + threadIdx.x) >> 2;
+  for (unsigned it = 0; it < iters; ++it, i += gstride) {
     const bool valid = i < total;
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
     if (valid) {
-      const uint4* row = reinterpret_cast<const uint4*>(x + i * Cin + sub * PER);
+      const uint4* row = reinterpret_cast<const uint4*>(x + (long)i * Cin + sub * PER);
 #pragma unroll
       for (int q = 0; q < PER / 8; ++q) {
         const uint4 xv = __ldg(row + q);
@@ -451,10 +454,11 @@ __global__ void __launch_bounds__(256) final_conv_kernel(const __nv_bfloat16* __
       acc[o] += __shfl_xor_sync(0xffffffffu, acc[o], 2);
     }
     if (valid && sub < Cout) {       // lane `sub` writes output channel `sub`
-      const long n = i / HW, p = i - n * HW;
-      const int hh = (int)(p / W) - pt, ww = (int)(p % W) - pl;
+      const unsigned n = i / uHW, p = i - n * uHW;
+      const unsigned hq = p / uW;
+      const int hh = (int)hq - pt, ww = (int)(p - hq * uW) - pl;
       const float r = sub == 0 ? acc[0] + br[0] : (sub == 1 ? acc[1] + br[1] : (sub == 2 ? acc[2] + br[2] : acc[3] + br[3]));
-      if (hh >= 0 && hh < H0 && ww >= 0 && ww < W0) out[((n * Cout + sub) * H0 + hh) * (long)W0 + ww] = r;
+      if (hh >= 0 && hh < H0 && ww >= 0 && ww < W0) out[(((long)n * Cout + sub) * H0 + hh) * (long)W0 + ww] = r;
     }
   }
 }
@@ -604,6 +608,7 @@ int fd_final_conv(const void* x, const float* w, const float* bias, float* out, 
                   void* stream) {
   FD_REQUIRE(x && w && bias && out && N > 0 && HW > 0 && Cin % 8 == 0 && Cout >= 1 && Cout <= 4, "final_conv: bad argument");
   FD_REQUIRE(Cin == 64, "final_conv: the UNet's final conv has 64 input channels (got %d)", Cin);
+  FD_REQUIRE((long)N * HW < (1L << 31), "final_conv: too many pixels");
   final_conv_kernel<16><<<egrid((long)N * HW * 4, 256), 256, 0, (cudaStream_t)stream>>>(
       static_cast<const __nv_bfloat16*>(x), w, bias, out, N, (long)HW, Cout, HW, 1, HW, 0, 0);
   FD_LAUNCH_CHECK();
@@ -616,6 +621,7 @@ int fd_final_conv_crop(const void* x, const float* w, const float* bias, float* 
   FD_REQUIRE(Cin == 64, "final_conv_crop: the UNet's final conv has 64 input channels (got %d)", Cin);
   FD_REQUIRE(pad_top >= 0 && pad_left >= 0 && pad_top + H0 <= H && pad_left + W0 <= W && H0 > 0 && W0 > 0,
              "final_conv_crop: window outside the frame");
+  FD_REQUIRE((long)N * H * W < (1L << 31), "final_conv_crop: too many pixels");
   final_conv_kernel<16><<<egrid((long)N * H * W * 4, 256), 256, 0, (cudaStream_t)stream>>>(
       static_cast<const __nv_bfloat16*>(x), w, bias, out, N, (long)H * W, Cout, W, H0, W0, pad_top, pad_left);
   FD_LAUNCH_CHECK();
