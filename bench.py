@@ -519,7 +519,11 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                      "the conv launches of ONE forward at this batch: the unit of `achieved`; algorithmic FLOPs, not bytes, bound these kernels)",
                      "peak_source": peaks["src"] + " (sustained: the kernel is timed inside a long step)",
                      "note": "launches that also apply the preceding GroupNorm + SiLU to their input (fused operand transform) "
-                             "carry that work in their time; the activation FLOPs are not counted",
+                             "carry that work in their time; the activation FLOPs are not counted.  `achieved` uses the ALGORITHMIC "
+                             "conv FLOPs of the reference's layers (SURVEY.md appendix A); the three Upsample convs (12.5 % of them) "
+                             "execute 4/9 of their MACs here (sub-pixel phase decomposition, fd_conv_igemm_up): executed MACs are "
+                             "7.0 % fewer than algorithmic",
+                     "executed_over_algorithmic_flops": 1.0 - (199.2 / 1590.3) * (5.0 / 9.0),
                      "conv_share_of_forward": conv_s / fwd_s, "forward_ms": fwd_s * 1e3,
                      "whole_step_tflops": FWD_GF_PER_SAMPLE * DDIM_STEPS * 1e9 * value / 1e12},
     }

@@ -156,6 +156,14 @@ FD_API int fd_conv_igemm_ex(const void* src0, int C0, const void* src1, int C1, 
                      const float* bias, const void* residual, void* out, double* gn_stats,
                      int N, int H, int W, int Cout, int KH, int KW, int pad_h, int pad_w, int mode,
                      int out_mode, void* stream);
+/* Upsample (:89-93): nearest x2 + 3x3 conv (pad 1) WITHOUT materialising the up-sampled tensor: four 2x2 convolutions on the
+ * low-resolution grid, one per output phase, with the coinciding taps' weights added (2.25x fewer MACs).
+ * fd_prep_weight_upconv: w fp32 [Cout][Cin][3][3] -> packed bf16 [4 phases][Cout][4*Cin].
+ * fd_conv_igemm_up: src bf16 (N,H,W,Cin) -> out bf16 (N,2H,2W,Cout), bias fp32 [Cout] or NULL. */
+FD_API int fd_prep_weight_upconv(const float* w, void* packed, int Cout, int Cin, void* stream);
+FD_API int fd_conv_igemm_up(const void* src, int Cin, const void* wpacked4, const float* bias, void* out, int N, int H, int W,
+                     int Cout, void* stream);
+
 /* fd_conv_igemm whose residual input is a RAW conv output h2 that still needs its GroupNorm(8) + SiLU
  * (ResnetBlock with a res_conv, :212-214: out = res_conv(x) + silu(GroupNorm(h2))): the epilogue folds
  * res_stats ([N][8][2] sum / sum of squares of h2, as accumulated by the producing conv), gamma, beta into per-channel

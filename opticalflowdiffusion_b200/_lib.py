@@ -62,6 +62,8 @@ SIGNATURES = {
     "fd_nhwc_bf16_to_nchw": (c_int, [_P, _P, _I, _I, _I, _P]),
     "fd_conv_igemm": (c_int, [_P, _I, _P, _I, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
     "fd_conv_igemm_ex": (c_int, [_P, _I, _P, _I, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
+    "fd_prep_weight_upconv": (c_int, [_P, _P, _I, _I, _P]),
+    "fd_conv_igemm_up": (c_int, [_P, _I, _P, _P, _P, _I, _I, _I, _I, _P]),
     "fd_conv_igemm_rt": (c_int, [_P, _I, _P, _I, _P, _P, _P, _P, _P, _P, _F, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
     "fd_attention_lse": (c_int, [_P, _P, _P, _I, _I, _P]),
     "fd_attention_bwd_workspace_floats": (c_size_t, [_I, _I]),

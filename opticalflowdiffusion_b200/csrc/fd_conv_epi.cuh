@@ -32,6 +32,8 @@ struct EpiCtx {
   double* gn_stats;
   int H, W, Cout, Wt;
   int shuffle_cq;               // > 0: pixel-shuffle store (dgrad of Downsample): map_out is (Cq, 2, W, 2, H), Cq = Cout / 4
+  int phase;                    // >= 0: sub-pixel phase store (fd_conv_igemm_up): map_out is (Cout, 2, W, 2, N*H), the tile goes to
+                                // rows 2 (img H + h) + (phase >> 1), columns 2 w + (phase & 1) of the up-sampled output
   int dbg;                      // diagnostics (FD_CONV_DBG): 8 = barrier handshakes only, no epilogue work
   int tempty_remote;            // != 0 (CTA pairs, non-leader): "accumulator drained" arrives on the LEADER CTA's barrier
   // Residual transform (ResnetBlock with a res_conv, :212-214: out = res_conv(x) + silu(GroupNorm(h2))): when rt_stats is
@@ -277,6 +279,8 @@ __device__ __forceinline__ void conv_epilogue(const EpiCtx& ec, NextTile next_ti
           if (ec.shuffle_cq > 0) {
             const int pq = cc / ec.shuffle_cq;          // p1 * 2 + p2
             tma_store_5d(ec.map_out, buf, cc - pq * ec.shuffle_cq, pq & 1, w0, pq >> 1, h0);
+          } else if (ec.phase >= 0) {
+            tma_store_5d(ec.map_out, buf, cc, ec.phase & 1, w0, ec.phase >> 1, img * ec.H + h0);
           } else {
             tma_store_5d(ec.map_out, buf, cc, w0, h0, img, 0);
           }

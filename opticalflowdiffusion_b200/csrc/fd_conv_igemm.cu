@@ -61,6 +61,7 @@ struct ConvParams {
   const float* rt_gamma;
   const float* rt_beta;
   float rt_eps;
+  int phase;          // >= 0: sub-pixel phase store (out_mode 2)
 };
 
 // SH ("store heavy"): few K-blocks per tile (1x1 convs), so the epilogue / output stores dominate: shallow operand
@@ -274,6 +275,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
     ec.tempty_remote = 0;
     ec.dbg = kDiag ? p.dbg : 0;
     ec.rt_stats = p.rt_stats; ec.rt_gamma = p.rt_gamma; ec.rt_beta = p.rt_beta; ec.rt_eps = p.rt_eps; ec.s_rt = s_rt;
+    ec.phase = p.phase;
     conv_epilogue<BLOCK_N, GPT, NBUF>(ec, [&](int iter, EpiTile& t) {
       const int tile = blockIdx.x + iter * gridDim.x;
       if (tile >= p.total_tiles) return false;
@@ -564,6 +566,7 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_
     ec.tempty_remote = rank != 0;
     ec.dbg = kDiag ? p.dbg : 0;
     ec.rt_stats = p.rt_stats; ec.rt_gamma = p.rt_gamma; ec.rt_beta = p.rt_beta; ec.rt_eps = p.rt_eps; ec.s_rt = s_rt;
+    ec.phase = p.phase;
     conv_epilogue<BLOCK_N, GPT, NBUF, NACC>(ec, [&](int iter, EpiTile& t) {
       const int st = pair + (iter / MT) * npairs;
       if (st >= super_tiles) return false;
@@ -619,6 +622,23 @@ TileShape pick_tile(int H, int W) {
   return best;
 }
 
+// the same restricted to R | H: the phase store (out_mode 2) addresses rows of all images as one dimension, so a tile must not
+// overhang the bottom of its image (the TMA store could not clip it)
+TileShape pick_tile_rows_divide(int H, int W) {
+  TileShape best{1, 128};
+  long best_cost = -1;
+  for (int wt = 128; wt >= 8; wt >>= 1) {
+    const int r = 128 / wt;
+    if (H % r != 0) continue;
+    const long cost = (long)((W + wt - 1) / wt) * wt * (long)H;
+    if (best_cost < 0 || cost < best_cost) {
+      best_cost = cost;
+      best = TileShape{r, wt};
+    }
+  }
+  return best;
+}
+
 template <int BLOCK_N, int GPT, int SH = 0>
 int launch(const CUtensorMap& ma0, const CUtensorMap& ma1, const CUtensorMap& mb, const CUtensorMap& mo,
            const ConvParams& p, int sms, cudaStream_t st) {
@@ -645,7 +665,7 @@ int fd_conv3x3_strip_launch(const void* src0, int C0, const void* src1, int C1, 
 static int conv_igemm_impl(const void* src0, int C0, const void* src1, int C1, const void* wpacked, const float* bias,
                            const void* residual, void* out, double* gn_stats, int N, int H, int W, int Cout, int KH, int KW,
                            int pad_h, int pad_w, int mode, int out_mode, const double* rt_stats, const float* rt_gamma,
-                           const float* rt_beta, float rt_eps, void* stream);
+                           const float* rt_beta, float rt_eps, void* stream, int phase = -1);
 
 extern "C" {
 
@@ -672,14 +692,31 @@ int fd_conv_igemm_rt(const void* src0, int C0, const void* src1, int C1, const v
                          res_stats, res_gamma, res_beta, eps, stream);
 }
 
+int fd_conv_igemm_up(const void* src, int Cin, const void* wpacked4, const float* bias, void* out, int N, int H, int W, int Cout,
+                     void* stream) {
+  FD_REQUIRE(src && wpacked4 && out, "conv_igemm_up: null pointer");
+  FD_REQUIRE(Cin % 64 == 0 && Cout % 64 == 0, "conv_igemm_up: Cin=%d Cout=%d must be multiples of 64", Cin, Cout);
+  const __nv_bfloat16* w4 = static_cast<const __nv_bfloat16*>(wpacked4);
+  for (int ph = 0; ph < 4; ++ph) {
+    // phase (a, b): 2x2 taps on the low-resolution grid, tap (ty, tx) reads (i + ty - (1 - a), j + tx - (1 - b))
+    const int a = ph >> 1, b = ph & 1;
+    if (int e = conv_igemm_impl(src, Cin, nullptr, 0, w4 + (size_t)ph * Cout * 4 * Cin, bias, nullptr, out, nullptr, N, H, W, Cout, 2, 2,
+                                1 - a, 1 - b, 0, 2, nullptr, nullptr, nullptr, 0.f, stream, ph))
+      return e;
+  }
+  return FD_OK;
+}
+
 }  // extern "C"
 
 static int conv_igemm_impl(const void* src0, int C0, const void* src1, int C1, const void* wpacked, const float* bias,
                            const void* residual, void* out, double* gn_stats, int N, int H, int W, int Cout, int KH, int KW,
                            int pad_h, int pad_w, int mode, int out_mode, const double* rt_stats, const float* rt_gamma,
-                           const float* rt_beta, float rt_eps, void* stream) {
-  FD_REQUIRE(out_mode == 0 || out_mode == 1, "conv_igemm: out_mode %d", out_mode);
-  FD_REQUIRE(out_mode == 0 || (mode == 0 && KH == 1 && KW == 1 && pad_h == 0 && pad_w == 0 && C1 == 0 &&
+                           const float* rt_beta, float rt_eps, void* stream, int phase) {
+  FD_REQUIRE(out_mode == 0 || out_mode == 1 || out_mode == 2, "conv_igemm: out_mode %d", out_mode);
+  FD_REQUIRE(out_mode != 2 || (mode == 0 && phase >= 0 && phase < 4 && residual == nullptr && gn_stats == nullptr && rt_stats == nullptr),
+             "conv_igemm: the phase store takes a plain conv (no residual / statistics)");
+  FD_REQUIRE(out_mode != 1 || (mode == 0 && KH == 1 && KW == 1 && pad_h == 0 && pad_w == 0 && C1 == 0 &&
                                residual == nullptr && gn_stats == nullptr && Cout % 256 == 0),
              "conv_igemm: the pixel-shuffle store is for 1x1 convs with Cout %% 256 == 0, no residual / statistics");
   FD_REQUIRE(src0 && wpacked && out, "conv_igemm: null pointer");
@@ -719,6 +756,7 @@ static int conv_igemm_impl(const void* src0, int C0, const void* src1, int C1, c
   p.residual = static_cast<const __nv_bfloat16*>(residual);
   p.gn_stats = gn_stats;
   p.rt_stats = rt_stats; p.rt_gamma = rt_gamma; p.rt_beta = rt_beta; p.rt_eps = rt_eps;
+  p.phase = out_mode == 2 ? phase : -1;
   CUtensorMap ma0, ma1, mb, mo;
   TileShape ts;
   if (mode == 0) {
@@ -739,7 +777,7 @@ static int conv_igemm_impl(const void* src0, int C0, const void* src1, int C1, c
     p.taps = KH * KW;
     p.pad_h = pad_h;
     p.pad_w = pad_w;
-    ts = pick_tile(h, w);
+    ts = out_mode == 2 ? pick_tile_rows_divide(h, w) : pick_tile(h, w);
     const uint32_t box[5] = {64, (uint32_t)ts.Wt, (uint32_t)ts.R, 1, 1};
     {
       const uint64_t dims[5] = {(uint64_t)C0, (uint64_t)w, (uint64_t)h, (uint64_t)n, 1};
@@ -791,7 +829,7 @@ static int conv_igemm_impl(const void* src0, int C0, const void* src1, int C1, c
     if (dbg < 0) { const char* e = getenv("FD_CONV_DBG"); dbg = e ? atoi(e) : 0; }
     p.dbg = dbg;
   }
-  const bool use_pair = pair_mode && (block_n == 256 || (block_n == 128 && pair_mode >= 2)) && !store_heavy_ && out_mode == 0 &&
+  const bool use_pair = pair_mode && (block_n == 256 || (block_n == 128 && pair_mode >= 2)) && !store_heavy_ && out_mode != 1 &&
                         ((long)p.N * p.tiles_w * p.tiles_h) % 2 == 0 && p.total_tiles >= 2;
   {
     const uint64_t K = (uint64_t)p.taps * (C0 + C1);
@@ -806,6 +844,13 @@ static int conv_igemm_impl(const void* src0, int C0, const void* src1, int C1, c
     p.shuffle_cq = (int)cq;
     const uint64_t dims[5] = {cq, 2, (uint64_t)p.W, 2, (uint64_t)p.H};
     const uint64_t str[4] = {cq * 2, 2 * cq * 2, (uint64_t)2 * p.W * cq * 2, (uint64_t)4 * p.W * cq * 2};
+    const uint32_t box[5] = {64, 1, (uint32_t)ts.Wt, 1, (uint32_t)ts.R};
+    if (int e = make_tmap_bf16(&mo, out, 5, dims, str, box)) return e;
+  } else if (out_mode == 2) {
+    // sub-pixel phase store: out is (N, 2H, 2W, Cout); the tile of low-resolution pixels (h, w) goes to (2h + a, 2w + b)
+    const uint64_t c = (uint64_t)Cout;
+    const uint64_t dims[5] = {c, 2, (uint64_t)p.W, 2, (uint64_t)p.N * p.H};
+    const uint64_t str[4] = {c * 2, 2 * c * 2, (uint64_t)2 * p.W * c * 2, (uint64_t)4 * p.W * c * 2};
     const uint32_t box[5] = {64, 1, (uint32_t)ts.Wt, 1, (uint32_t)ts.R};
     if (int e = make_tmap_bf16(&mo, out, 5, dims, str, box)) return e;
   } else {

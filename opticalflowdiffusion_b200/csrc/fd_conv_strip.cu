@@ -664,6 +664,7 @@ conv3x3_strip_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_co
     ec.tempty_remote = 0;
     ec.dbg = kDiag ? p.dbg : 0;
     ec.rt_stats = nullptr; ec.rt_gamma = nullptr; ec.rt_beta = nullptr; ec.rt_eps = 0.f; ec.s_rt = nullptr;
+    ec.phase = -1;
     StripWalk walk(p);
     int j = 0, n = 0, w0 = 0, ra = 0, rb = 0;
     auto next = [&](int, EpiTile& t) {

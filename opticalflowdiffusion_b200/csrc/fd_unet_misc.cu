@@ -152,6 +152,28 @@ __global__ void __launch_bounds__(256) prep_weight_kernel(const float* __restric
   prep_weight_body(w, packed, Cin, KH, KW, kind, standardize, eps, Kpacked, blockIdx.x);
 }
 
+// Upsample (:89-93) = nearest x2 followed by a 3x3 conv.  On the LOW-resolution grid that is four 2x2 convolutions, one per output
+// phase (a, b) = (row, column parity): output row 2i + a reads up-sampled rows 2i + a - 1 .. 2i + a + 1, i.e. source rows
+// {i-1, i, i} (a = 0) or {i, i, i+1} (a = 1), so the three row taps collapse to two with the weights of the coinciding taps
+// ADDED (same for columns).  2.25x fewer MACs than the conv on the up-sampled tensor, which is never materialised.
+//   packed[p = a*2+b][co][(ty*2+tx)*Cin + ci] = sum over ky in rows(a, ty), kx in cols(b, tx) of w[co][ci][ky][kx]
+//   rows(0,0) = {0}, rows(0,1) = {1,2}, rows(1,0) = {0,1}, rows(1,1) = {2}; tap ty reads source row i + ty - (1 - a).
+__global__ void __launch_bounds__(256) prep_weight_upconv_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ packed,
+                                                                 int Cout, int Cin) {
+  const int co = blockIdx.x, p = blockIdx.y, a = p >> 1, b = p & 1;
+  const float* wc = w + (long)co * Cin * 9;
+  __nv_bfloat16* dst = packed + ((long)p * Cout + co) * 4 * Cin;
+  for (int k = threadIdx.x; k < 4 * Cin; k += 256) {
+    const int t = k / Cin, ci = k - t * Cin, ty = t >> 1, tx = t & 1;
+    const int ky0 = a == 0 ? (ty == 0 ? 0 : 1) : (ty == 0 ? 0 : 2), ky1 = a == 0 ? (ty == 0 ? 0 : 2) : (ty == 0 ? 1 : 2);
+    const int kx0 = b == 0 ? (tx == 0 ? 0 : 1) : (tx == 0 ? 0 : 2), kx1 = b == 0 ? (tx == 0 ? 0 : 2) : (tx == 0 ? 1 : 2);
+    float acc = 0.f;
+    for (int ky = ky0; ky <= ky1; ++ky)
+      for (int kx = kx0; kx <= kx1; ++kx) acc += wc[(ci * 3 + ky) * 3 + kx];
+    dst[k] = __float2bfloat16(acc);
+  }
+}
+
 // all layers in one launch: block -> (layer, output channel) through the prefix sums of the layers' block counts
 __global__ void __launch_bounds__(256) prep_weight_batch_kernel(const long long* __restrict__ table,
                                                                 const int* __restrict__ blk_start, int n_layers, float eps) {
@@ -525,6 +547,13 @@ int fd_prep_weight(const float* w, void* packed, int Cout, int Cin, int KH, int 
   const int Kp = kind == 2 ? KH * 64 : Cin * KH * KW;
   prep_weight_kernel<<<Cout, 256, 0, (cudaStream_t)stream>>>(w, static_cast<__nv_bfloat16*>(packed), Cout, Cin, KH, KW,
                                                              kind, standardize, eps, Kp);
+  FD_LAUNCH_CHECK();
+  return FD_OK;
+}
+
+int fd_prep_weight_upconv(const float* w, void* packed, int Cout, int Cin, void* stream) {
+  FD_REQUIRE(w && packed && Cout > 0 && Cin > 0, "prep_weight_upconv: bad argument");
+  prep_weight_upconv_kernel<<<dim3(Cout, 4), 256, 0, (cudaStream_t)stream>>>(w, static_cast<__nv_bfloat16*>(packed), Cout, Cin);
   FD_LAUNCH_CHECK();
   return FD_OK;
 }

@@ -245,3 +245,32 @@ def test_conv_residual_groupnorm_epilogue(L, shape):
     assert (got - ref).abs().max().item() <= 1.2e-2 * scale, ((got - ref).abs().max().item(), scale)
     assert (got - two).abs().max().item() <= 1.6e-2 * scale          # the two-pass form rounds the activated tensor to bf16
     assert (got - ref).abs().mean().item() <= 2e-3 * ref.abs().mean().item() + 1e-6
+
+
+@pytest.mark.parametrize("shape", [(2, 64, 64, 9, 20), (1, 128, 64, 22, 64), (2, 256, 128, 11, 32), (1, 512, 256, 7, 16),
+                                   (1, 64, 64, 6, 130), (3, 64, 128, 5, 13)])
+def test_upsample_conv_phase_decomposition(L, shape):
+    """fd_conv_igemm_up: Upsample = nearest x2 + conv3x3(pad 1) (denoising_diffusion.py:89-93) computed as four 2x2 phase
+    convolutions on the low-resolution tensor == conv3x3 on the materialised up-sampled tensor (torch fp32, bf16-rounded
+    input and weights).  The phase weights are sums of up to four fp32 weights rounded ONCE to bf16, so the tolerance is the
+    bf16 weight rounding (2^-9 relative per product) on top of the output rounding: max |err| <= 1.5e-2 of the output scale."""
+    lib = L.load()
+    N, Cin, Cout, H, W = shape
+    g = torch.Generator().manual_seed(Cin + H)
+    x = torch.randn(N, Cin, H, W, generator=g).cuda()
+    w = (torch.randn(Cout, Cin, 3, 3, generator=g) / (9 * Cin) ** 0.5).cuda()
+    bias = torch.randn(Cout, generator=g).cuda()
+    w4 = torch.empty(4, Cout, 4 * Cin, device="cuda", dtype=torch.bfloat16)
+    L.check(lib.fd_prep_weight_upconv(L.ptr(w), L.ptr(w4), Cout, Cin, L.stream()))
+    xs = nhwc_bf16(x)
+    out = torch.full((N, 2 * H, 2 * W, Cout), float("nan"), device="cuda", dtype=torch.bfloat16)
+    L.check(lib.fd_conv_igemm_up(L.ptr(xs), Cin, L.ptr(w4), L.ptr(bias), L.ptr(out), N, H, W, Cout, L.stream()))
+    torch.cuda.synchronize()
+    got = out.permute(0, 3, 1, 2).float()
+    assert torch.isfinite(got).all()                     # every output pixel of every phase was written
+    up = F.interpolate(x.to(torch.bfloat16).float(), scale_factor=2, mode="nearest")
+    ref = F.conv2d(up, w, bias, padding=1)
+    scale = ref.abs().max().item()
+    err = (got - ref).abs().max().item()
+    assert err <= 1.5e-2 * scale, (err, scale)
+    assert (got - ref).abs().mean().item() <= 2.5e-3 * ref.abs().mean().item() + 1e-6
