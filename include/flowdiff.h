@@ -172,6 +172,16 @@ FD_API int fd_conv_igemm_rt(const void* src0, int C0, const void* src1, int C1, 
                      const void* residual_raw, const double* res_stats, const float* res_gamma, const float* res_beta,
                      float eps, void* out, int N, int H, int W, int Cout, int KH, int KW, int pad_h, int pad_w, void* stream);
 
+/* The UNet's last two lines in one launch (Unet.forward, denoising_diffusion.py:414-417: the final ResnetBlock's
+ * res_conv + residual, then final_conv 1x1 64 -> out_dim): fd_conv_igemm_rt for a 1x1 conv with Cout = 64 whose epilogue
+ * applies final_conv (head_w fp32 [head_n][64], head_b fp32 [head_n], head_n <= 4) to the fp32 tile and writes
+ * out_nchw fp32 (N, head_n, H0, W0) = the H0 x W0 window at (pad_top, pad_left) of the padded H x W grid
+ * (InputPadder.unpad).  The 64-channel activation never goes through HBM. */
+FD_API int fd_conv_igemm_rt_head(const void* src0, int C0, const void* src1, int C1, const void* wpacked, const float* bias,
+                     const void* residual_raw, const double* res_stats, const float* res_gamma, const float* res_beta,
+                     float eps, const float* head_w, const float* head_b, int head_n, float* out_nchw, int N, int H, int W,
+                     int H0, int W0, int pad_top, int pad_left, void* stream);
+
 
 /* 3x3 / pad 1 / 64 -> 64 channel convolution whose INPUT is activated on the fly:
  *   out = conv3x3(silu(GroupNorm(src) * (scale + 1) + shift)) (+ bias, + residual, + GroupNorm statistics of out)

@@ -65,6 +65,7 @@ SIGNATURES = {
     "fd_prep_weight_upconv": (c_int, [_P, _P, _I, _I, _P]),
     "fd_conv_igemm_up": (c_int, [_P, _I, _P, _P, _P, _I, _I, _I, _I, _P]),
     "fd_conv_igemm_rt": (c_int, [_P, _I, _P, _I, _P, _P, _P, _P, _P, _P, _F, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
+    "fd_conv_igemm_rt_head": (c_int, [_P, _I, _P, _I, _P, _P, _P, _P, _P, _P, _F, _P, _P, _I, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
     "fd_attention_lse": (c_int, [_P, _P, _P, _I, _I, _P]),
     "fd_attention_bwd_workspace_floats": (c_size_t, [_I, _I]),
     "fd_attention_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _I, _I, _P]),

@@ -32,6 +32,14 @@ struct EpiCtx {
   double* gn_stats;
   int H, W, Cout, Wt;
   int shuffle_cq;               // > 0: pixel-shuffle store (dgrad of Downsample): map_out is (Cq, 2, W, 2, H), Cq = Cout / 4
+  // Output head (BLOCK_N == 64 only; Unet.forward's last two lines, :416-417): when head_out is set the tile is NOT stored;
+  // instead the 1x1 final conv (64 -> head_n <= 4 channels, fp32 weights head_w [head_n][64], bias head_b) is applied to the
+  // fp32 values of each pixel and written as fp32 NCHW, cropped to the head_h0 x head_w0 window at (head_pt, head_pl).
+  float* head_out;
+  const float* head_w;
+  const float* head_b;
+  int head_n, head_h0, head_w0, head_pt, head_pl;
+  float* s_head;                // [head_n * 64 weights | 8 warps x 32 lanes x 4 partial dot products]
   int phase;                    // >= 0: sub-pixel phase store (fd_conv_igemm_up): map_out is (Cout, 2, W, 2, N*H), the tile goes to
                                 // rows 2 (img H + h) + (phase >> 1), columns 2 w + (phase & 1) of the up-sampled output
   int dbg;                      // diagnostics (FD_CONV_DBG): 8 = barrier handshakes only, no epilogue work
@@ -98,6 +106,10 @@ __device__ __forceinline__ void conv_epilogue(const EpiCtx& ec, NextTile next_ti
       for (int b = 0; b < GIC; ++b) st_s[a][b] = st_q[a][b] = 0.f;
     int st_img = -1, st_ntile = 0;
     int rt_img = -1, rt_ntile = -1;
+    if (BLOCK_N == 64 && ec.head_out != nullptr) {
+      for (int i = et; i < ec.head_n * 64; i += kEpiThreads) ec.s_head[i] = __ldg(ec.head_w + i);
+      // (published by the first slab barrier)
+    }
     uint32_t slab_count = 0;
 
     auto flush_stats = [&]() {
@@ -255,6 +267,42 @@ __device__ __forceinline__ void conv_epilogue(const EpiCtx& ec, NextTile next_ti
             st_s[slab][b] += s;
             st_q[slab][b] += q;
           }
+        }
+        if (BLOCK_N == 64 && ec.head_out != nullptr) {
+          // this warp holds 32 of the pixel's 64 channels: partial dot products, the other half comes from warp ew ^ 4
+          const float* hw = ec.s_head;
+          float* hx = ec.s_head + 256 + (ew * 32 + lane) * 4;
+          float d[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int o = 0; o < 4; ++o) {
+            if (o < ec.head_n) {
+#pragma unroll
+              for (int j4 = 0; j4 < 8; ++j4) {
+                const float4 w4 = *reinterpret_cast<const float4*>(hw + o * 64 + c + j4 * 4);      // (broadcast reads)
+                d[o] = fmaf(v[j4 * 4 + 0], w4.x, d[o]);
+                d[o] = fmaf(v[j4 * 4 + 1], w4.y, d[o]);
+                d[o] = fmaf(v[j4 * 4 + 2], w4.z, d[o]);
+                d[o] = fmaf(v[j4 * 4 + 3], w4.w, d[o]);
+              }
+            }
+          }
+          *reinterpret_cast<float4*>(hx) = make_float4(d[0], d[1], d[2], d[3]);
+          tc_fence_before();
+          if (ec.tempty_remote) mbar_arrive_cluster(ec.tempty0 + 8u * as, 0);
+          else mbar_arrive(ec.tempty0 + 8u * as);
+          named_bar_sync(1, kEpiThreads);
+          if (half == 0 && valid) {
+            const float4 o4 = *reinterpret_cast<const float4*>(ec.s_head + 256 + ((ew ^ 4) * 32 + lane) * 4);
+            const float r4[4] = {d[0] + o4.x, d[1] + o4.y, d[2] + o4.z, d[3] + o4.w};
+            const int hh = h - ec.head_pt, wq = w - ec.head_pl;
+            if (hh >= 0 && hh < ec.head_h0 && wq >= 0 && wq < ec.head_w0) {
+#pragma unroll
+              for (int o = 0; o < 4; ++o)
+                if (o < ec.head_n)
+                  ec.head_out[(((long)img * ec.head_n + o) * ec.head_h0 + hh) * (long)ec.head_w0 + wq] = r4[o] + __ldg(ec.head_b + o);
+            }
+          }
+          continue;       // (the next tile's first slab barrier orders the reuse of the exchange buffer)
         }
         // 64-byte piece of this row inside the 128-byte slab row, 16-byte granules XOR-swizzled by (row & 7)
         const uint32_t rbase = buf + (uint32_t)row * 128u;

@@ -62,6 +62,11 @@ struct ConvParams {
   const float* rt_beta;
   float rt_eps;
   int phase;          // >= 0: sub-pixel phase store (out_mode 2)
+  // output head (fd_conv_igemm_rt_head): final 1x1 conv applied in the epilogue instead of storing the tile
+  float* head_out;
+  const float* head_w;
+  const float* head_b;
+  int head_n, head_h0, head_w0, head_pt, head_pl;
 };
 
 // SH ("store heavy"): few K-blocks per tile (1x1 convs), so the epilogue / output stores dominate: shallow operand
@@ -75,8 +80,9 @@ struct Cfg {
   static constexpr int kStages = SH ? (BLOCK_N == 64 ? 6 : (BLOCK_N == 128 ? 5 : 3)) : (BLOCK_N == 64 ? 7 : (BLOCK_N == 128 ? 6 : 4));
   static constexpr int kStoreBufs = SH ? (BLOCK_N / 64 > 2 ? BLOCK_N / 64 : 2) : (BLOCK_N == 64 ? 2 : 1);   // staging slabs
   static constexpr int kTmemCols = 2 * BLOCK_N;
+  static constexpr int kHeadBytes = BLOCK_N == 64 ? (256 + kEpiWarps * 32 * 4) * 4 : 0;      // output-head weights + exchange
   static constexpr int kTailBytes = 256 /*barriers*/ + 2 * BLOCK_N * 4 /*bias*/ + kEpiWarps * 16 * 4 /*stats*/ + 64 +
-                                    4 * BLOCK_N * 4 /*residual-transform coefficients*/;
+                                    4 * BLOCK_N * 4 /*residual-transform coefficients*/ + kHeadBytes;
   static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + kStoreBufs * kSlabBytes + kTailBytes;
 };
 
@@ -106,6 +112,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
   float* s_stats = reinterpret_cast<float*>(gtail + 2 * BLOCK_N * 4);    // [8 warps][16]
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(gtail + 2 * BLOCK_N * 4 + kEpiWarps * 16 * 4);
   float* s_rt = reinterpret_cast<float*>(gtail + 2 * BLOCK_N * 4 + kEpiWarps * 16 * 4 + 64);        // [2][2][BLOCK_N]
+  float* s_head = s_rt + 4 * BLOCK_N;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -276,6 +283,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
     ec.dbg = kDiag ? p.dbg : 0;
     ec.rt_stats = p.rt_stats; ec.rt_gamma = p.rt_gamma; ec.rt_beta = p.rt_beta; ec.rt_eps = p.rt_eps; ec.s_rt = s_rt;
     ec.phase = p.phase;
+    ec.head_out = p.head_out; ec.head_w = p.head_w; ec.head_b = p.head_b; ec.head_n = p.head_n; ec.s_head = s_head;
+    ec.head_h0 = p.head_h0; ec.head_w0 = p.head_w0; ec.head_pt = p.head_pt; ec.head_pl = p.head_pl;
     conv_epilogue<BLOCK_N, GPT, NBUF>(ec, [&](int iter, EpiTile& t) {
       const int tile = blockIdx.x + iter * gridDim.x;
       if (tile >= p.total_tiles) return false;
@@ -388,6 +397,7 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_
   float* s_stats = reinterpret_cast<float*>(gtail + 2 * BLOCK_N * 4);
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(gtail + 2 * BLOCK_N * 4 + kEpiWarps * 16 * 4);
   float* s_rt = reinterpret_cast<float*>(gtail + 2 * BLOCK_N * 4 + kEpiWarps * 16 * 4 + 64);        // [2][2][BLOCK_N]
+  float* s_head = nullptr;      // (the output head is an N = 64, single-CTA feature)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -567,6 +577,8 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_
     ec.dbg = kDiag ? p.dbg : 0;
     ec.rt_stats = p.rt_stats; ec.rt_gamma = p.rt_gamma; ec.rt_beta = p.rt_beta; ec.rt_eps = p.rt_eps; ec.s_rt = s_rt;
     ec.phase = p.phase;
+    ec.head_out = p.head_out; ec.head_w = p.head_w; ec.head_b = p.head_b; ec.head_n = p.head_n; ec.s_head = s_head;
+    ec.head_h0 = p.head_h0; ec.head_w0 = p.head_w0; ec.head_pt = p.head_pt; ec.head_pl = p.head_pl;
     conv_epilogue<BLOCK_N, GPT, NBUF, NACC>(ec, [&](int iter, EpiTile& t) {
       const int st = pair + (iter / MT) * npairs;
       if (st >= super_tiles) return false;
@@ -662,10 +674,17 @@ int fd_conv3x3_strip_launch(const void* src0, int C0, const void* src1, int C1, 
                             void* out, double* gn_stats, int N, int H, int W, int base_offset_mode,
                             cudaStream_t st);   // fd_conv_strip.cu
 
+struct HeadArgs {           // fd_conv_igemm_rt_head: see EpiCtx::head_*
+  float* out;
+  const float* w;
+  const float* b;
+  int n, h0, w0, pt, pl;
+};
+
 static int conv_igemm_impl(const void* src0, int C0, const void* src1, int C1, const void* wpacked, const float* bias,
                            const void* residual, void* out, double* gn_stats, int N, int H, int W, int Cout, int KH, int KW,
                            int pad_h, int pad_w, int mode, int out_mode, const double* rt_stats, const float* rt_gamma,
-                           const float* rt_beta, float rt_eps, void* stream, int phase = -1);
+                           const float* rt_beta, float rt_eps, void* stream, int phase = -1, const struct HeadArgs* head = nullptr);
 
 extern "C" {
 
@@ -692,6 +711,19 @@ int fd_conv_igemm_rt(const void* src0, int C0, const void* src1, int C1, const v
                          res_stats, res_gamma, res_beta, eps, stream);
 }
 
+int fd_conv_igemm_rt_head(const void* src0, int C0, const void* src1, int C1, const void* wpacked, const float* bias,
+                          const void* residual_raw, const double* res_stats, const float* res_gamma, const float* res_beta, float eps,
+                          const float* head_w, const float* head_b, int head_n, float* out_nchw, int N, int H, int W, int H0, int W0,
+                          int pad_top, int pad_left, void* stream) {
+  FD_REQUIRE(residual_raw && res_stats && res_gamma && res_beta && head_w && head_b && out_nchw, "conv_igemm_rt_head: null pointer");
+  FD_REQUIRE(head_n >= 1 && head_n <= 4, "conv_igemm_rt_head: head_n=%d (1..4)", head_n);
+  FD_REQUIRE(H0 > 0 && W0 > 0 && pad_top >= 0 && pad_left >= 0 && pad_top + H0 <= H && pad_left + W0 <= W,
+             "conv_igemm_rt_head: crop %dx%d at (%d, %d) outside %dx%d", H0, W0, pad_top, pad_left, H, W);
+  const HeadArgs ha{out_nchw, head_w, head_b, head_n, H0, W0, pad_top, pad_left};
+  return conv_igemm_impl(src0, C0, src1, C1, wpacked, bias, residual_raw, nullptr, nullptr, N, H, W, 64, 1, 1, 0, 0, 0, 0,
+                         res_stats, res_gamma, res_beta, eps, stream, -1, &ha);
+}
+
 int fd_conv_igemm_up(const void* src, int Cin, const void* wpacked4, const float* bias, void* out, int N, int H, int W, int Cout,
                      void* stream) {
   FD_REQUIRE(src && wpacked4 && out, "conv_igemm_up: null pointer");
@@ -712,7 +744,10 @@ int fd_conv_igemm_up(const void* src, int Cin, const void* wpacked4, const float
 static int conv_igemm_impl(const void* src0, int C0, const void* src1, int C1, const void* wpacked, const float* bias,
                            const void* residual, void* out, double* gn_stats, int N, int H, int W, int Cout, int KH, int KW,
                            int pad_h, int pad_w, int mode, int out_mode, const double* rt_stats, const float* rt_gamma,
-                           const float* rt_beta, float rt_eps, void* stream, int phase) {
+                           const float* rt_beta, float rt_eps, void* stream, int phase, const HeadArgs* head) {
+  FD_REQUIRE(head == nullptr || (Cout == 64 && rt_stats != nullptr && out_mode == 0 && mode == 0 && gn_stats == nullptr && KH == 1 && KW == 1),
+             "conv_igemm: the output head takes a 1x1 residual-transform conv with Cout = 64");
+  if (head != nullptr && out == nullptr) out = const_cast<void*>(src0);      // (tensor map only; the head never stores the tile)
   FD_REQUIRE(out_mode == 0 || out_mode == 1 || out_mode == 2, "conv_igemm: out_mode %d", out_mode);
   FD_REQUIRE(out_mode != 2 || (mode == 0 && phase >= 0 && phase < 4 && residual == nullptr && gn_stats == nullptr && rt_stats == nullptr),
              "conv_igemm: the phase store takes a plain conv (no residual / statistics)");
@@ -757,6 +792,10 @@ static int conv_igemm_impl(const void* src0, int C0, const void* src1, int C1, c
   p.gn_stats = gn_stats;
   p.rt_stats = rt_stats; p.rt_gamma = rt_gamma; p.rt_beta = rt_beta; p.rt_eps = rt_eps;
   p.phase = out_mode == 2 ? phase : -1;
+  if (head != nullptr) {
+    p.head_out = head->out; p.head_w = head->w; p.head_b = head->b; p.head_n = head->n;
+    p.head_h0 = head->h0; p.head_w0 = head->w0; p.head_pt = head->pt; p.head_pl = head->pl;
+  }
   CUtensorMap ma0, ma1, mb, mo;
   TileShape ts;
   if (mode == 0) {

@@ -665,6 +665,8 @@ conv3x3_strip_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_co
     ec.dbg = kDiag ? p.dbg : 0;
     ec.rt_stats = nullptr; ec.rt_gamma = nullptr; ec.rt_beta = nullptr; ec.rt_eps = 0.f; ec.s_rt = nullptr;
     ec.phase = -1;
+    ec.head_out = nullptr; ec.head_w = nullptr; ec.head_b = nullptr; ec.head_n = 0; ec.s_head = nullptr;
+    ec.head_h0 = ec.head_w0 = ec.head_pt = ec.head_pl = 0;
     StripWalk walk(p);
     int j = 0, n = 0, w0 = 0, ra = 0, rb = 0;
     auto next = [&](int, EpiTile& t) {

@@ -62,6 +62,9 @@ class Unet(UnetParams, TrainMixin):
     # Upsample (nearest x2 + 3x3 conv, :89-93) as four 2x2 phase convolutions on the low-resolution tensor (fd_conv_igemm_up,
     # inference path): 2.25x fewer MACs for 12.5 % of the forward's conv FLOPs, no up-sampled tensor.  FD_UPCONV=0: two passes.
     UPCONV_PHASES = os.environ.get("FD_UPCONV", "1") != "0"
+    # final ResnetBlock's res_conv + final_conv + un-pad crop as one launch (fd_conv_igemm_rt_head, inference path): the last
+    # 64-channel activation (461 MB at batch 8, 440x1024) is neither written nor re-read.  FD_FUSE_HEAD=0: two launches.
+    FUSE_HEAD = os.environ.get("FD_FUSE_HEAD", "1") != "0"
     WS_EPS = 1e-5       # WeightStandardizedConv2d with fp32 input (:107)
     LN_EPS = 1e-5       # LayerNorm with fp32 input (:122)
 
@@ -314,8 +317,30 @@ class Unet(UnetParams, TrainMixin):
                                                self.LN_EPS, self._st))
         return out
 
-    def _resnet(self, name: str, rb: _ResnetBlock, x0: Tensor, x1: Optional[Tensor], ss: Optional[Tensor]) -> Tensor:
-        """ResnetBlock.forward (:202-214)."""
+    def _conv_res_gn_head(self, name: str, src0: Tensor, src1: Optional[Tensor], raw: Tensor, raw_stats: Tensor, norm,
+                          head: tuple) -> Tensor:
+        """_conv_res_gn followed by final_conv and the un-pad crop (:416-417) in the same launch: fd_conv_igemm_rt_head."""
+        pc = self._convs[name]
+        n, h, w, c0 = src0.shape
+        c1 = src1.shape[-1] if src1 is not None else 0
+        fc, h0, w0, pt, pl = head
+        out = torch.empty(n, self.out_dim, h0, w0, device=src0.device, dtype=torch.float32)
+        timing = getattr(self, "_conv_timing", None)
+        if timing is not None:
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            timing.append((name, 2.0 * n * h * w * pc.cout * pc.w.shape[1], ev))
+            ev[0].record()
+        _lib.check(self._lib.fd_conv_igemm_rt_head(_lib.ptr(src0), c0, _lib.ptr(src1), c1, _lib.ptr(pc.w), _lib.ptr(pc.bias),
+                                                   _lib.ptr(raw), _lib.ptr(raw_stats), _lib.ptr(norm.weight), _lib.ptr(norm.bias),
+                                                   self.GN_EPS, _lib.ptr(fc.weight), _lib.ptr(fc.bias), self.out_dim, _lib.ptr(out),
+                                                   n, h, w, h0, w0, pt, pl, self._st))
+        if timing is not None:
+            ev[1].record()
+        return out
+
+    def _resnet(self, name: str, rb: _ResnetBlock, x0: Tensor, x1: Optional[Tensor], ss: Optional[Tensor],
+                head: Optional[tuple] = None) -> Tensor:
+        """ResnetBlock.forward (:202-214).  head = (final_conv, H0, W0, pad_top, pad_left): also apply the output head."""
         st1, st2 = self._next_stats(), self._next_stats()
         h1 = self._conv(name + ".block1.proj", x0, x1, stats=st1)
         pc2 = self._convs[name + ".block2.proj"]
@@ -328,6 +353,8 @@ class Unet(UnetParams, TrainMixin):
             h2 = self._conv(name + ".block2.proj", a1, stats=st2)
         if (name + ".res_conv") in self._convs:
             if self.FUSE_GN_RESIDUAL:
+                if head is not None:
+                    return self._conv_res_gn_head(name + ".res_conv", x0, x1, h2, st2, rb.block2.norm, head)
                 return self._conv_res_gn(name + ".res_conv", x0, x1, h2, st2, rb.block2.norm)
             a2 = self._gn_silu(h2, st2, rb.block2.norm, None, 0, None)
             return self._conv(name + ".res_conv", x0, x1, residual=a2)
@@ -498,11 +525,17 @@ class Unet(UnetParams, TrainMixin):
                 del up_t
             else:
                 h = self._conv(f"ups.{i}.3", h)
+        fc = self.final_conv
+        if (self.FUSE_HEAD and self.FUSE_GN_RESIDUAL and not return_taps and self.dim == 64 and self.out_dim <= 4 and
+                "final_res_block.res_conv" in self._convs and self._convs["final_res_block.res_conv"].kh == 1):
+            # final ResnetBlock's res_conv + residual + final_conv + crop in one launch (the 64-channel tensor is never stored)
+            out = self._resnet("final_res_block", self.final_res_block, h, r, ss, head=(fc, H0, W0, pad[2], pad[0]))
+            self._stats = None
+            return out
         h = self._resnet("final_res_block", self.final_res_block, h, r, ss)
         if return_taps:
             taps["final_res_block"] = h
         out = torch.empty(B, self.out_dim, H0, W0, device=dev, dtype=torch.float32)
-        fc = self.final_conv
         _lib.check(lib.fd_final_conv_crop(_lib.ptr(h), _lib.ptr(fc.weight), _lib.ptr(fc.bias), _lib.ptr(out), B, H, W, self.dim,
                                           self.out_dim, pad[2], pad[0], H0, W0, st))
         self._stats = None

@@ -247,6 +247,56 @@ def test_conv_residual_groupnorm_epilogue(L, shape):
     assert (got - ref).abs().mean().item() <= 2e-3 * ref.abs().mean().item() + 1e-6
 
 
+@pytest.mark.parametrize("shape", [(2, 64, 64, 24, 40, 21, 37, 2, 1, 2), (1, 64, 64, 16, 136, 16, 136, 0, 0, 2),
+                                   (3, 64, 64, 9, 20, 5, 20, 3, 0, 3), (1, 128, 0, 40, 72, 33, 70, 7, 2, 1)])
+def test_conv_residual_groupnorm_output_head(L, shape):
+    """fd_conv_igemm_rt_head: the UNet's tail (final ResnetBlock's res_conv + silu(GroupNorm(h2)), final_conv 1x1, un-pad crop;
+    Unet.forward :414-417 + InputPadder.unpad) in one launch == fd_conv_igemm_rt followed by fd_final_conv_crop (which reads the
+    bf16-rounded activation: the fused head uses the fp32 tile, so it is the closer of the two to fp32 torch) == fp32 torch."""
+    lib = L.load()
+    N, C0, C1, H, W, H0, W0, pt, pl, nout = shape
+    g = torch.Generator().manual_seed(H * W + nout)
+    x0 = torch.randn(N, C0, H, W, generator=g).cuda()
+    x1 = torch.randn(N, C1, H, W, generator=g).cuda() if C1 else None
+    w = (torch.randn(64, C0 + C1, 1, 1, generator=g) / (C0 + C1) ** 0.5).cuda()
+    bias = torch.randn(64, generator=g).cuda()
+    gamma = (torch.randn(64, generator=g) * 0.3 + 1).cuda()
+    beta = (torch.randn(64, generator=g) * 0.2).cuda()
+    hw_ = (torch.randn(nout, 64, 1, 1, generator=g) / 8).cuda()
+    hb = torch.randn(nout, generator=g).cuda()
+    a1 = torch.randn(N, 64, H, W, generator=g).cuda()
+    w2 = (torch.randn(64, 64, 3, 3, generator=g) / (9 * 64) ** 0.5 * 1.5).cuda()
+    b2 = torch.randn(64, generator=g).cuda() * 0.1
+    h2, st2 = run_conv(L, [a1], w2, b2, (1, 1), stats=True)
+    h2q = nhwc_bf16(h2)
+    s0 = nhwc_bf16(x0)
+    s1 = nhwc_bf16(x1) if C1 else None
+    wp = pack_w(w)
+    got = torch.full((N, nout, H0, W0), float("nan"), device="cuda")
+    L.check(lib.fd_conv_igemm_rt_head(L.ptr(s0), C0, L.ptr(s1), C1, L.ptr(wp), L.ptr(bias), L.ptr(h2q), L.ptr(st2), L.ptr(gamma),
+                                      L.ptr(beta), 1e-5, L.ptr(hw_), L.ptr(hb), nout, L.ptr(got), N, H, W, H0, W0, pt, pl, L.stream()))
+    mid = torch.empty(N, H, W, 64, device="cuda", dtype=torch.bfloat16)
+    L.check(lib.fd_conv_igemm_rt(L.ptr(s0), C0, L.ptr(s1), C1, L.ptr(wp), L.ptr(bias), L.ptr(h2q), L.ptr(st2), L.ptr(gamma),
+                                 L.ptr(beta), 1e-5, L.ptr(mid), N, H, W, 64, 1, 1, 0, 0, L.stream()))
+    two = torch.empty_like(got)
+    L.check(lib.fd_final_conv_crop(L.ptr(mid), L.ptr(hw_), L.ptr(hb), L.ptr(two), N, H, W, 64, nout, pt, pl, H0, W0, L.stream()))
+    torch.cuda.synchronize()
+    assert torch.isfinite(got).all()                     # every pixel of the window was written
+    full = ref_conv([x0] + ([x1] if C1 else []), w, bias, (0, 0)) + \
+        F.silu(F.group_norm(h2q.permute(0, 3, 1, 2).float(), 8, gamma, beta, eps=1e-5))
+    ref = F.conv2d(full, hw_, hb)[:, :, pt:pt + H0, pl:pl + W0]
+    scale = ref.abs().max().item()
+    e_got, e_two = (got - ref).abs().max().item(), (two - ref).abs().max().item()
+    assert e_got <= 6e-3 * scale, (e_got, scale)         # bf16 inputs / weights of the 1x1 conv, tanh.approx SiLU; no output rounding
+    assert (got - two).abs().max().item() <= 1.2e-2 * scale
+    assert (got - ref).abs().mean().item() <= max(1.5 * (two - ref).abs().mean().item(), 1e-3 * scale), (e_got, e_two)
+    again = torch.empty_like(got)
+    L.check(lib.fd_conv_igemm_rt_head(L.ptr(s0), C0, L.ptr(s1), C1, L.ptr(wp), L.ptr(bias), L.ptr(h2q), L.ptr(st2), L.ptr(gamma),
+                                      L.ptr(beta), 1e-5, L.ptr(hw_), L.ptr(hb), nout, L.ptr(again), N, H, W, H0, W0, pt, pl, L.stream()))
+    torch.cuda.synchronize()
+    assert torch.equal(got, again)                       # no atomics on this path: bit-stable
+
+
 @pytest.mark.parametrize("shape", [(2, 64, 64, 9, 20), (1, 128, 64, 22, 64), (2, 256, 128, 11, 32), (1, 512, 256, 7, 16),
                                    (1, 64, 64, 6, 130), (3, 64, 128, 5, 13)])
 def test_upsample_conv_phase_decomposition(L, shape):

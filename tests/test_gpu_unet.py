@@ -86,3 +86,34 @@ def test_unet_vs_oracle_64x128():
     out3 = net(x.cuda(), cond.cuda(), t.cuda())
     assert out3.requires_grad
     assert (out3.detach().cpu() - ref).abs().max().item() < 3e-2
+
+
+def test_unet_fused_output_head_padded_shape():
+    """Inference forward at a shape that needs replicate padding (44x140 -> 48x144): the fused tail (FD_FUSE_HEAD:
+    res_conv + GroupNorm residual + final_conv + crop in one launch) == the two-launch tail == the oracle (InputPadder
+    pad / unpad around the fp32 forward, utils.py:6-27 + denoising_diffusion.py:414-417)."""
+    import torch.nn.functional as F
+    net = build_unet(3, 5)
+    sd = {k: v.clone() for k, v in net.state_dict().items()}
+    net = net.cuda()
+    g = torch.Generator().manual_seed(5)
+    B, H, W = 2, 44, 140
+    x = torch.randn(B, 2, H, W, generator=g)
+    cond = O.synthetic_frames(B, H, W, seed=6) * 2 - 1
+    t = torch.tensor([12, 903])
+    ph, pw = (-H) % 8, (-W) % 8
+    pad = [pw // 2, pw - pw // 2, ph // 2, ph - ph // 2]
+    with torch.no_grad():
+        ref = O.unet_forward(sd, F.pad(x, pad, mode="replicate"), F.pad(cond, pad, mode="replicate"), t)
+        ref = ref[..., pad[2]:pad[2] + H, pad[0]:pad[0] + W]
+        assert net.FUSE_HEAD
+        fused = net(x.cuda(), cond.cuda(), t.cuda())
+        net.FUSE_HEAD = False
+        try:
+            two = net(x.cuda(), cond.cuda(), t.cuda())
+        finally:
+            del net.FUSE_HEAD
+    assert fused.shape == two.shape == (B, 2, H, W)
+    assert (fused.cpu() - ref).abs().max().item() < 3e-2
+    assert (two.cpu() - ref).abs().max().item() < 3e-2
+    assert (fused - two).abs().max().item() < 1e-2
