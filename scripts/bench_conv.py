@@ -1,4 +1,8 @@
-"""Times fd_conv_igemm on the implicit-GEMM shapes of SURVEY.md appendix A (batch 8, 440x1024)."""
+"""Times fd_conv_igemm on the implicit-GEMM shapes of SURVEY.md appendix A (batch 8, 440x1024) and, with CUDNN=1, the library
+bar for the same layers: torch.nn.functional.conv2d through cuDNN the way the reference runs it (fp32 NCHW tensors with TF32
+allowed, main.py:79-80 / denoising_diffusion.py:114) and in the library's best configuration (bf16, channels_last), each with
+cudnn.benchmark on.  The library legs include the concat of the two sources that the UNet's skip connections need
+(torch.cat, denoising_diffusion.py:400-408) only when CAT=1; by default they get the already-concatenated tensor for free."""
 import json
 import os
 import sys
@@ -56,6 +60,37 @@ def main():
         flops = 2.0 * N * H * W * cout * k * k * (c0 + c1)
         res[name] = {"ms": round(t * 1e3, 3), "TFLOPs": round(flops / t / 1e12, 1)}
         del x0, x1, out
+        if os.environ.get("CUDNN"):
+            import torch.nn.functional as F
+            torch.backends.cudnn.benchmark = True
+            torch.backends.cuda.matmul.allow_tf32 = True
+            torch.backends.cudnn.allow_tf32 = True
+            for tag, dt, cl in (("cudnn_tf32_nchw", torch.float32, False), ("cudnn_bf16_nhwc", torch.bfloat16, True)):
+                xs = [torch.randn(N, c, H, W, device="cuda", dtype=dt) for c in (c0, c1) if c]
+                w = (torch.randn(cout, c0 + c1, k, k, device="cuda") * 0.02).to(dt)
+                b = torch.zeros(cout, device="cuda", dtype=dt)
+                if cl:
+                    xs = [t_.contiguous(memory_format=torch.channels_last) for t_ in xs]
+                    w = w.contiguous(memory_format=torch.channels_last)
+                cat_inside = bool(os.environ.get("CAT")) and len(xs) > 1
+                xin = xs[0] if len(xs) == 1 else torch.cat(xs, 1)
+
+                def lib_fn():
+                    return F.conv2d(torch.cat(xs, 1) if cat_inside else xin, w, b, padding=k // 2)
+                for _ in range(3):
+                    lib_fn()
+                torch.cuda.synchronize()
+                s.record()
+                for _ in range(iters):
+                    lib_fn()
+                e.record()
+                torch.cuda.synchronize()
+                tl = s.elapsed_time(e) * 1e-3 / iters
+                res[name][tag + "_ms"] = round(tl * 1e3, 3)
+                res[name][tag + "_TFLOPs"] = round(flops / tl / 1e12, 1)
+                del xs, xin, w
+            res[name]["speedup_vs_tf32"] = round(res[name]["cudnn_tf32_nchw_ms"] / res[name]["ms"], 2)
+            res[name]["speedup_vs_bf16"] = round(res[name]["cudnn_bf16_nhwc_ms"] / res[name]["ms"], 2)
     print(json.dumps(res, indent=1))
 
 
