@@ -121,11 +121,17 @@ FD_API int fd_pack_input(const float* x, const float* cond, void* packed, int B,
  * InputPadder(mode='sintel') (future/raft_utils.py:7-25) folded into the packing: 436x1024 -> 440x1024 costs no pass. */
 FD_API int fd_pack_input_pad(const float* x, const float* cond, void* packed, int B, int Cx, int Cc, int H0, int W0,
                       int pad_top, int pad_left, int H, int W, int nan_mask, void* stream);
+/* More than 9 input channels (latent mode: flow_diffuser.py:98-110 builds the UNet over latent_dim + ... = 33-35 channels,
+ * flow_pred.py:31-37 the decoder over latent_dim + 3): same NaN / mask / replicate-pad semantics, packed as plain bf16
+ * (B,H,W,64) with the channels zero-padded to 64; init_conv then runs as a 49-tap fd_conv_igemm with kind-3 weights. */
+FD_API int fd_pack_input_wide(const float* x, const float* cond, void* packed, int B, int Cx, int Cc, int H0, int W0,
+                      int pad_top, int pad_left, int H, int W, int nan_mask, void* stream);
 
 /* Weight preparation.  w: fp32 [Cout][Cin][KH][KW] (torch layout) -> bf16 [Cout][K] K-major.
  * kind 0: K index = (ky*KW+kx)*Cin + ci                       (implicit-GEMM tap-major order)
  * kind 1: pixel-unshuffle 1x1 (:95-99): Cin = 4*C, torch channel c*4+p1*2+p2 -> K = (p1*2+p2)*C + c
  * kind 2: 7x7 init conv as 7 taps of 64: K = ky*64 + kx*Cin + ci, zero padded
+ * kind 3: tap-major over an input zero-padded to 64 channels: K = (ky*KW+kx)*64 + ci (Cin <= 64; the wide init conv)
  * standardize != 0 applies WeightStandardizedConv2d (:106-114) with eps before packing. */
 FD_API int fd_prep_weight(const float* w, void* packed, int Cout, int Cin, int KH, int KW, int kind,
                    int standardize, float eps, void* stream);
@@ -257,7 +263,7 @@ FD_API int fd_linattn_tc(const void* x, const void* wk, const float* sk, const f
 /* Attention core (:256-267): softmax(q^T k * 32^-0.5) v, flash-style, bf16 (N,HW,384) -> (N,HW,128) */
 FD_API int fd_attention(const void* qkv, void* out, int N, int HW, void* stream);
 
-/* final 1x1 conv (:361,417) 64 -> Cout (<=4) from bf16 NHWC to fp32 NCHW */
+/* final 1x1 conv (:361,417) 64 -> Cout (<= 64; four output channels per launch) from bf16 NHWC to fp32 NCHW */
 FD_API int fd_final_conv(const void* x, const float* w, const float* bias, float* out, int N, int HW, int Cin,
                   int Cout, void* stream);
 /* Same on an (N,H,W,64) frame, writing only the H0 x W0 window at (pad_top, pad_left) as fp32 (N,Cout,H0,W0): the

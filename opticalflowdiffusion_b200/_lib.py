@@ -42,6 +42,7 @@ SIGNATURES = {
     "fd_ddpm_step": (c_int, [_P, _P, _P, _P, _P, _L, _F, _F, _F, _P]),
     "fd_pack_input": (c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "fd_pack_input_pad": (c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
+    "fd_pack_input_wide": (c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
     "fd_prep_weight": (c_int, [_P, _P, _I, _I, _I, _I, _I, _I, _F, _P]),
     "fd_gn_silu": (c_int, [_P, _P, _P, _P, _P, _L, _P, _P, _I, _I, _I, _F, _P]),
     "fd_chan_layernorm": (c_int, [_P, _P, _P, _P, _L, _I, _F, _P]),

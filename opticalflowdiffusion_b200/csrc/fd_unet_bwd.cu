@@ -585,6 +585,7 @@ __device__ __forceinline__ void prep_weight_bwd_body(const float* __restrict__ g
     const int ci = i / (KW * KH);
     if (kind == 0) return (ky * KW + kx) * Cin + ci;
     if (kind == 1) return (ci & 3) * (Cin / 4) + (ci >> 2);
+    if (kind == 3) return (ky * KW + kx) * 64 + ci;
     return ky * 64 + kx * Cin + ci;
   };
   if (!standardize) {
@@ -637,7 +638,7 @@ __global__ void __launch_bounds__(256) prep_weight_bwd_batch_kernel(const long l
   const int l = batch_find_layer(blk_start, n_layers, (int)blockIdx.x);
   const long long* r = table + (long)l * 8;
   const int Cin = (int)r[4], KH = (int)r[5], KW = (int)r[6], kind = (int)(r[7] & 0xff), ws = (int)((r[7] >> 8) & 1);
-  const int Kp = kind == 2 ? KH * 64 : Cin * KH * KW;
+  const int Kp = kind == 2 ? KH * 64 : (kind == 3 ? KH * KW * 64 : Cin * KH * KW);
   prep_weight_bwd_body(reinterpret_cast<const float*>(r[0]), reinterpret_cast<const float*>(r[1]), reinterpret_cast<float*>(r[2]),
                        Cin, KH, KW, kind, ws, eps, Kp, (int)blockIdx.x - blk_start[l]);
 }
@@ -850,10 +851,11 @@ int fd_prep_weight_dgrad(const void* wpacked, void* wd, int Cout, int Cin, int t
 int fd_prep_weight_bwd(const float* g, const float* w, float* dw, int Cout, int Cin, int KH, int KW, int kind,
                        int standardize, float eps, void* stream) {
   FD_REQUIRE(g && w && dw && Cout > 0 && Cin > 0 && KH > 0 && KW > 0, "prep_weight_bwd: bad argument");
-  FD_REQUIRE(kind >= 0 && kind <= 2, "prep_weight_bwd: kind %d", kind);
+  FD_REQUIRE(kind >= 0 && kind <= 3, "prep_weight_bwd: kind %d", kind);
+  FD_REQUIRE(kind != 3 || Cin <= 64, "prep_weight_bwd: kind 3 needs Cin <= 64");
   FD_REQUIRE(kind != 1 || (Cin % 4 == 0 && KH == 1 && KW == 1), "prep_weight_bwd: kind 1 is a 1x1 over 4*C channels");
   FD_REQUIRE(kind != 2 || KW * Cin <= 64, "prep_weight_bwd: kind 2 needs KW*Cin <= 64");
-  const int Kp = kind == 2 ? KH * 64 : Cin * KH * KW;
+  const int Kp = kind == 2 ? KH * 64 : (kind == 3 ? KH * KW * 64 : Cin * KH * KW);
   prep_weight_bwd_kernel<<<Cout, 256, 0, (cudaStream_t)stream>>>(g, w, dw, Cout, Cin, KH, KW, kind, standardize, eps, Kp);
   FD_LAUNCH_CHECK();
   return FD_OK;

@@ -95,6 +95,62 @@ __global__ void __launch_bounds__(256) pack_input_kernel(const float* __restrict
   }
 }
 
+// Wide variant for more than 9 input channels (latent mode: flow_diffuser.py:98-110 builds a Unet over latent_dim + ... = 33-35
+// channels, flow_pred.py:31-37 one over latent_dim + 3): plain NHWC with the channels zero-padded to 64; init_conv then runs
+// as a 49-tap implicit GEMM (weights in fd_prep_weight's kind-3 layout).  Same NaN / mask / replicate-pad semantics as above.
+constexpr int kWidePx = 64;
+
+__global__ void __launch_bounds__(256) pack_input_wide_kernel(const float* __restrict__ x, const float* __restrict__ cond,
+                                                              __nv_bfloat16* __restrict__ packed, int B, int Cx, int Cc, int H,
+                                                              int W, int nan_mask, int segs, int H0, int W0, int pt, int pl) {
+  __shared__ float s_in[64][kWidePx + 1];
+  const int Ctot = Cx + (nan_mask ? 1 : 0) + Cc;
+  const int seg = blockIdx.x % segs;
+  const long row = blockIdx.x / segs;              // b * H + h
+  const int b = (int)(row / H), h = (int)(row % H);
+  const int w0 = seg * kWidePx;
+  const long HW = (long)H0 * W0;
+  const int t = threadIdx.x;
+  const int hs = min(max(h - pt, 0), H0 - 1);
+  for (int idx = t; idx < 64 * kWidePx; idx += 256) {
+    const int c = idx / kWidePx, i = idx - c * kWidePx;
+    const int w = w0 + i;
+    float v = 0.f;
+    if (c < Ctot && w < W) {
+      const long p = (long)hs * W0 + min(max(w - pl, 0), W0 - 1);
+      if (c < Cx) v = __ldg(x + ((long)b * Cx + c) * HW + p);
+      else if (nan_mask && c == Cx) v = 0.f;
+      else v = __ldg(cond + ((long)b * Cc + (c - Cx - (nan_mask ? 1 : 0))) * HW + p);
+    }
+    s_in[c][i] = v;
+  }
+  __syncthreads();
+  if (nan_mask) {
+    for (int i = t; i < kWidePx; i += 256) {
+      bool any_nan = false;
+      for (int c = 0; c < Cx; ++c) {
+        const float v = s_in[c][i];
+        if (v != v) { any_nan = true; s_in[c][i] = 0.f; }
+      }
+      s_in[Cx][i] = any_nan ? 1.f : 0.f;
+    }
+    __syncthreads();
+  }
+  const int q = t & 7;
+  uint4* dst = reinterpret_cast<uint4*>(packed + (row * W + w0) * 64);
+#pragma unroll
+  for (int it = 0; it < kWidePx / 32; ++it) {
+    const int px = it * 32 + (t >> 3);
+    if (w0 + px >= W) break;
+    uint4 o;
+    o.x = fd_pack_bf16(s_in[q * 8 + 0][px], s_in[q * 8 + 1][px]);
+    o.y = fd_pack_bf16(s_in[q * 8 + 2][px], s_in[q * 8 + 3][px]);
+    o.z = fd_pack_bf16(s_in[q * 8 + 4][px], s_in[q * 8 + 5][px]);
+    o.w = fd_pack_bf16(s_in[q * 8 + 6][px], s_in[q * 8 + 7][px]);
+    dst[px * 8 + q] = o;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // weight standardisation (:106-114) + bf16 packing into the implicit-GEMM K order.  One block per
 // output channel; statistics in fp32 (biased variance), two passes like the reference's reduce.
@@ -124,7 +180,7 @@ __device__ __forceinline__ void prep_weight_body(const float* __restrict__ w, __
     rstd = s_rstd;
   }
   __nv_bfloat16* po = packed + (long)o * Kpacked;
-  if (kind == 2) {
+  if (kind >= 2) {
     for (int k = threadIdx.x; k < Kpacked; k += blockDim.x) po[k] = __float2bfloat16(0.f);
     __syncthreads();
   }
@@ -139,8 +195,10 @@ __device__ __forceinline__ void prep_weight_body(const float* __restrict__ w, __
     } else if (kind == 1) {
       const int C = Cin / 4;
       k = (ci & 3) * C + (ci >> 2);       // torch channel c*4 + p1*2 + p2 -> (p1*2+p2)*C + c
-    } else {
+    } else if (kind == 2) {
       k = ky * 64 + kx * Cin + ci;
+    } else {
+      k = (ky * KW + kx) * 64 + ci;       // kind 3: tap-major over an input zero-padded to 64 channels (wide init_conv)
     }
     po[k] = __float2bfloat16((wo[i] - mean) * rstd);
   }
@@ -184,7 +242,7 @@ __global__ void __launch_bounds__(256) prep_weight_batch_kernel(const long long*
   }
   const long long* r = table + (long)lo * 8;
   const int Cin = (int)r[4], KH = (int)r[5], KW = (int)r[6], kind = (int)(r[7] & 0xff), ws = (int)((r[7] >> 8) & 1);
-  const int Kp = kind == 2 ? KH * 64 : Cin * KH * KW;
+  const int Kp = kind == 2 ? KH * 64 : (kind == 3 ? KH * KW * 64 : Cin * KH * KW);
   prep_weight_body(reinterpret_cast<const float*>(r[0]), reinterpret_cast<__nv_bfloat16*>(r[1]), Cin, KH, KW, kind, ws, eps, Kp,
                    (int)blockIdx.x - blk_start[lo]);
 }
@@ -434,7 +492,13 @@ __global__ void __launch_bounds__(256) time_proj_kernel(const float* __restrict_
 template <int PER>
 __global__ void __launch_bounds__(256) final_conv_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w,
                                                          const float* __restrict__ bias, float* __restrict__ out, int N,
-                                                         long HW, int Cout, int W, int H0, int W0, int pt, int pl) {
+                                                         long HW, int CoutAll, int W, int H0, int W0, int pt, int pl,
+                                                         int o_base) {
+  // output channels o_base .. o_base + 3 of CoutAll (the host loops over groups of four: the flow UNet has 2, the latent
+  // autoencoder's encoder 16)
+  const int Cout = min(CoutAll - o_base, 4);
+  w += (long)o_base * (PER * 4);
+  bias += o_base;
   // the H0 x W0 window at (pt, pl) of the H x W frame is written (crop of the internal padding); W0 = W, pt = pl = 0 -> all
   constexpr int Cin = PER * 4;
   const int sub = threadIdx.x & 3;
@@ -480,7 +544,7 @@ __global__ void __launch_bounds__(256) final_conv_kernel(const __nv_bfloat16* __
       const unsigned hq = p / uW;
       const int hh = (int)hq - pt, ww = (int)(p - hq * uW) - pl;
       const float r = sub == 0 ? acc[0] + br[0] : (sub == 1 ? acc[1] + br[1] : (sub == 2 ? acc[2] + br[2] : acc[3] + br[3]));
-      if (hh >= 0 && hh < H0 && ww >= 0 && ww < W0) out[(((long)n * Cout + sub) * H0 + hh) * (long)W0 + ww] = r;
+      if (hh >= 0 && hh < H0 && ww >= 0 && ww < W0) out[(((long)n * CoutAll + o_base + sub) * H0 + hh) * (long)W0 + ww] = r;
     }
   }
 }
@@ -538,13 +602,28 @@ int fd_pack_input_pad(const float* x, const float* cond, void* packed, int B, in
   return FD_OK;
 }
 
+int fd_pack_input_wide(const float* x, const float* cond, void* packed, int B, int Cx, int Cc, int H0, int W0, int pad_top,
+                       int pad_left, int H, int W, int nan_mask, void* stream) {
+  FD_REQUIRE(x && packed && B > 0 && H0 > 0 && W0 > 0 && Cx > 0 && Cc >= 0, "pack_input_wide: bad argument");
+  FD_REQUIRE(cond != nullptr || Cc == 0, "pack_input_wide: Cc > 0 needs cond");
+  FD_REQUIRE(pad_top >= 0 && pad_left >= 0 && pad_top + H0 <= H && pad_left + W0 <= W, "pack_input_wide: window outside the frame");
+  FD_REQUIRE(Cx + (nan_mask ? 1 : 0) + Cc <= 64, "pack_input_wide: at most 64 input channels");
+  const int segs = (W + kWidePx - 1) / kWidePx;
+  FD_REQUIRE((long)B * H * segs < (1L << 31), "pack_input_wide: too many rows");
+  pack_input_wide_kernel<<<(unsigned)((long)B * H * segs), 256, 0, (cudaStream_t)stream>>>(
+      x, cond, static_cast<__nv_bfloat16*>(packed), B, Cx, Cc, H, W, nan_mask, segs, H0, W0, pad_top, pad_left);
+  FD_LAUNCH_CHECK();
+  return FD_OK;
+}
+
 int fd_prep_weight(const float* w, void* packed, int Cout, int Cin, int KH, int KW, int kind, int standardize, float eps,
                    void* stream) {
   FD_REQUIRE(w && packed && Cout > 0 && Cin > 0 && KH > 0 && KW > 0, "prep_weight: bad argument");
-  FD_REQUIRE(kind >= 0 && kind <= 2, "prep_weight: kind %d", kind);
+  FD_REQUIRE(kind >= 0 && kind <= 3, "prep_weight: kind %d", kind);
+  FD_REQUIRE(kind != 3 || Cin <= 64, "prep_weight: kind 3 needs Cin <= 64");
   FD_REQUIRE(kind != 1 || (Cin % 4 == 0 && KH == 1 && KW == 1), "prep_weight: kind 1 is a 1x1 over 4*C channels");
   FD_REQUIRE(kind != 2 || KW * Cin <= 64, "prep_weight: kind 2 needs KW*Cin <= 64");
-  const int Kp = kind == 2 ? KH * 64 : Cin * KH * KW;
+  const int Kp = kind == 2 ? KH * 64 : (kind == 3 ? KH * KW * 64 : Cin * KH * KW);
   prep_weight_kernel<<<Cout, 256, 0, (cudaStream_t)stream>>>(w, static_cast<__nv_bfloat16*>(packed), Cout, Cin, KH, KW,
                                                              kind, standardize, eps, Kp);
   FD_LAUNCH_CHECK();
@@ -635,25 +714,29 @@ int fd_time_proj(const float* temb, const float* w, const float* bias, float* ou
 
 int fd_final_conv(const void* x, const float* w, const float* bias, float* out, int N, int HW, int Cin, int Cout,
                   void* stream) {
-  FD_REQUIRE(x && w && bias && out && N > 0 && HW > 0 && Cin % 8 == 0 && Cout >= 1 && Cout <= 4, "final_conv: bad argument");
+  FD_REQUIRE(x && w && bias && out && N > 0 && HW > 0 && Cin % 8 == 0 && Cout >= 1 && Cout <= 64, "final_conv: bad argument");
   FD_REQUIRE(Cin == 64, "final_conv: the UNet's final conv has 64 input channels (got %d)", Cin);
   FD_REQUIRE((long)N * HW < (1L << 31), "final_conv: too many pixels");
-  final_conv_kernel<16><<<egrid((long)N * HW * 4, 256), 256, 0, (cudaStream_t)stream>>>(
-      static_cast<const __nv_bfloat16*>(x), w, bias, out, N, (long)HW, Cout, HW, 1, HW, 0, 0);
-  FD_LAUNCH_CHECK();
+  for (int o = 0; o < Cout; o += 4) {
+    final_conv_kernel<16><<<egrid((long)N * HW * 4, 256), 256, 0, (cudaStream_t)stream>>>(
+        static_cast<const __nv_bfloat16*>(x), w, bias, out, N, (long)HW, Cout, HW, 1, HW, 0, 0, o);
+    FD_LAUNCH_CHECK();
+  }
   return FD_OK;
 }
 
 int fd_final_conv_crop(const void* x, const float* w, const float* bias, float* out, int N, int H, int W, int Cin, int Cout,
                        int pad_top, int pad_left, int H0, int W0, void* stream) {
-  FD_REQUIRE(x && w && bias && out && N > 0 && H > 0 && W > 0 && Cout >= 1 && Cout <= 4, "final_conv_crop: bad argument");
+  FD_REQUIRE(x && w && bias && out && N > 0 && H > 0 && W > 0 && Cout >= 1 && Cout <= 64, "final_conv_crop: bad argument");
   FD_REQUIRE(Cin == 64, "final_conv_crop: the UNet's final conv has 64 input channels (got %d)", Cin);
   FD_REQUIRE(pad_top >= 0 && pad_left >= 0 && pad_top + H0 <= H && pad_left + W0 <= W && H0 > 0 && W0 > 0,
              "final_conv_crop: window outside the frame");
   FD_REQUIRE((long)N * H * W < (1L << 31), "final_conv_crop: too many pixels");
-  final_conv_kernel<16><<<egrid((long)N * H * W * 4, 256), 256, 0, (cudaStream_t)stream>>>(
-      static_cast<const __nv_bfloat16*>(x), w, bias, out, N, (long)H * W, Cout, W, H0, W0, pad_top, pad_left);
-  FD_LAUNCH_CHECK();
+  for (int o = 0; o < Cout; o += 4) {
+    final_conv_kernel<16><<<egrid((long)N * H * W * 4, 256), 256, 0, (cudaStream_t)stream>>>(
+        static_cast<const __nv_bfloat16*>(x), w, bias, out, N, (long)H * W, Cout, W, H0, W0, pad_top, pad_left, o);
+    FD_LAUNCH_CHECK();
+  }
   return FD_OK;
 }
 

@@ -15,6 +15,7 @@ minimal stand-in with the attributes the reference touches (``log_dict``, ``log`
 """
 from __future__ import annotations
 
+import os
 import random
 from typing import Optional, Sequence, Tuple
 
@@ -162,19 +163,35 @@ class FlowDiffuser(_Base):
         self.latent = cfg.latent
         self.target = cfg.target
         if self.latent:
-            raise NotImplementedError("latent mode needs the px8q8g0m autoencoder checkpoint (flow_diffuser.py:81-95), "
-                                      "which cannot exist offline; out of scope (SURVEY.md section 2)")
+            # flow_diffuser.py:81-95: a frozen Autoencoder whose weights come from the FlowPred run named by cfg.ae.  The
+            # reference fetches that checkpoint from wandb; here it is read from the same local path the reference caches
+            # it under, or from cfg.ae_checkpoint -- absent both, the autoencoder keeps its initialisation (and says so).
+            from .flow_pred import Autoencoder, load_autoencoder
+            self.ae = Autoencoder(cfg)
+            path = _cfg_get(cfg, "ae_checkpoint")
+            if not path:
+                cached = os.path.join("outputs", "loaded_checkpoints", "diffusion_control", str(_cfg_get(cfg, "ae", "")), "model.ckpt")
+                path = cached if os.path.exists(cached) else None
+            self.ae_loaded = load_autoencoder(self.ae, path)
+            if not self.ae_loaded:
+                import warnings
+                warnings.warn("latent mode without an autoencoder checkpoint (algorithm.ae_checkpoint): randomly initialised "
+                              "encoder / decoder")
+            for p_ in self.ae.parameters():
+                p_.requires_grad = False
         if not self.is_diffusion:
             raise NotImplementedError("is_diffusion=false (plain regression) is not on the flow_diffuser hot path")
         self._augmentor: Optional[Augmentor] = None
-        self.dim = 3
+        self.dim = cfg.latent_dim if self.latent else 3                                  # flow_diffuser.py:98
         unet_dims = {"target": self.dim + 1, "joint": self.dim + 3}.get(self.target, 2)
         self.unet = Unet(64, channels=self.dim + unet_dims, out_dim=2)
         if self.target in ("target", "joint"):
             self._model = UnetWithWarp(cfg, self.unet, full_output=self.target == "joint")
         else:
             self._model = self.unet
-        channels = 2 + int(self.target == "target") + 3 * int(self.target == "joint")
+        # (flow_diffuser.py:122: in latent mode the reference passes latent_dim whatever the target -- kept: it is the channel
+        # count of the sampler's initial noise, so latent sampling works for target='target' exactly as far as it does there)
+        channels = cfg.latent_dim if self.latent else 2 + int(self.target == "target") + 3 * int(self.target == "joint")
         self.model = ConditionalDiffusion(
             self._model, _cfg_get(cfg, "image_size", 128), objective="pred_x0", channels=channels, auto_normalize=False,
             noise_space="image" if cfg.noiser == "image" else "flow", timesteps=cfg.timesteps,
@@ -214,7 +231,10 @@ class FlowDiffuser(_Base):
             batch = self.augmentor(batch)
         img, tgt, flow = batch
         flow = torch.clamp(flow / self.flow_max, -1.0, 1.0)
-        img = 2 * img - 1.0
+        if self.latent:                                                                 # flow_diffuser.py:143-148
+            img = torch.clamp(self.ae.encode(img) / self.latent_max, -1.0, 1.0)
+        else:
+            img = 2 * img - 1.0
         if self.target == "target":
             first = W.warp(img, None, flow * self.flow_max, mode="forward")
         elif self.target == "joint":
@@ -281,8 +301,9 @@ class FlowDiffuser(_Base):
             p_flows = p_flows[:, -1] * self.flow_max
         else:
             p_flows = p_flows[:, -1]
-        mse = W.nan_mse(samples.contiguous(), tgt.contiguous() * 1.0) if torch.isnan(samples).any() else \
-            torch.nn.functional.mse_loss(samples, tgt)
+        mse_tgt = self.ae.encode(tgt) if self.latent else tgt                           # flow_diffuser.py:255
+        mse = W.nan_mse(samples.contiguous(), mse_tgt.contiguous() * 1.0) if torch.isnan(samples).any() else \
+            torch.nn.functional.mse_loss(samples, mse_tgt)
         metrics = {"val/loss": loss, "val/mse": mse, **self._stats("val", "cond", cond), **self._stats("val", "flow", flow),
                    **self._stats("val", "samples", torch.nan_to_num(samples)), **self._stats("val", "p_flow", p_flows)}
         if self.target in ("target", "joint"):
@@ -297,7 +318,11 @@ class FlowDiffuser(_Base):
             import torchvision
             bsz = img.shape[0]
             flos = torchvision.utils.flow_to_image(torch.cat((flow, p_flows, flow - p_flows), dim=0)) / 255.0
+            shown = torch.nan_to_num(samples)
+            if self.latent:                                                             # flow_diffuser.py:304-309
+                shown = self.ae.decode(shown * self.latent_max, img)
+                self.logger.log_image(key="dec_gt", images=list(torch.chunk(self.ae(img, flow), bsz)), step=self.global_step)
             for key, val in (("original", img), ("target", tgt), ("gt_flow", flos[:bsz]), ("target_p", flos[bsz:2 * bsz]),
-                             ("difference", flos[2 * bsz:]), ("samples", torch.nan_to_num(samples))):
+                             ("difference", flos[2 * bsz:]), ("samples", shown)):
                 self.logger.log_image(key=key, images=list(torch.chunk(val, bsz)), step=self.global_step)
         return None

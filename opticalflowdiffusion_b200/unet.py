@@ -71,9 +71,12 @@ class Unet(UnetParams, TrainMixin):
     def __init__(self, dim: int = 64, channels: int = 5, out_dim: int = 2, dim_mults=(1, 2, 4, 8), groups: int = 8,
                  time_in: bool = True):
         super().__init__(dim, channels, out_dim, tuple(dim_mults), groups, time_in)
-        assert dim == 64 and tuple(dim_mults) == (1, 2, 4, 8) and groups == 8, \
-            "the sm_100a path is specialised to the flow_diffuser UNet (dim 64, mults 1-2-4-8, 8 groups)"
-        assert channels <= 9, "init_conv takes at most 9 input channels (7 taps x 9 <= 64)"
+        assert dim == 64 and tuple(dim_mults) in ((1, 2, 4, 8), (1, 2, 4)) and groups == 8, \
+            "the sm_100a path is specialised to the flow_diffuser UNets (dim 64, mults 1-2-4-8 or 1-2-4, 8 groups)"
+        assert channels <= 64, "init_conv takes at most 64 input channels"
+        # <= 9 channels: 7 horizontal taps x 9 channels fit one 64-wide K chunk (init_conv as a 7x1 conv, kind 2); more
+        # (latent mode, flow_diffuser.py:98-110 / flow_pred.py:23-37): channels zero-padded to 64, 49-tap implicit GEMM (kind 3)
+        self._wide_input = channels > 9
         self._convs: Optional[Dict[str, _PackedConv]] = None
         self._resblocks: List[Tuple[str, _ResnetBlock]] = []
         self._tproj_w: Optional[Tensor] = None
@@ -88,7 +91,9 @@ class Unet(UnetParams, TrainMixin):
 
         def add(name, mod, kind=0, ws=False, mode=0):
             kh, kw = mod.weight.shape[2:]
-            if kind == 2:
+            if kind == 2 and self._wide_input:
+                convs[name] = _PackedConv(mod, 3, False, 7, 7, (3, 3), 0)
+            elif kind == 2:
                 convs[name] = _PackedConv(mod, 2, False, 7, 1, (3, 0), 0)
             else:
                 convs[name] = _PackedConv(mod, kind, ws, kh, kw, (kh // 2, kw // 2), mode)
@@ -169,7 +174,7 @@ class Unet(UnetParams, TrainMixin):
             _lib.require_cuda(w)
             dev = w.device
             cout, cin, kh, kw = w.shape
-            kp = 7 * 64 if pc.kind == 2 else cin * kh * kw
+            kp = 7 * 64 if pc.kind == 2 else (49 * 64 if pc.kind == 3 else cin * kh * kw)
             if pc.w is None or pc.w.device != w.device:
                 pc.w = torch.empty(cout, kp, device=w.device, dtype=BF16)
             if w.dtype == torch.float32 and w.is_contiguous():
@@ -253,7 +258,7 @@ class Unet(UnetParams, TrainMixin):
         timing = getattr(self, "_conv_timing", None)
         if timing is not None:      # bench.py's roofline pass: CUDA events around every conv launch
             ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-            flops = 2.0 * n * h * w * pc.cout * pc.w.shape[1] if pc.kind != 2 else 2.0 * n * h * w * pc.cout * 49 * self.channels
+            flops = 2.0 * n * h * w * pc.cout * pc.w.shape[1] if pc.kind < 2 else 2.0 * n * h * w * pc.cout * 49 * self.channels
             timing.append((name, flops, ev))
             ev[0].record()
         _lib.check(self._lib.fd_conv_igemm(_lib.ptr(src0), c0, _lib.ptr(src1), c1, _lib.ptr(pc.w), _lib.ptr(pc.bias),
@@ -422,6 +427,11 @@ class Unet(UnetParams, TrainMixin):
         With autograd enabled (training_step) the call is one ``UnetFunction`` node whose backward runs the backward
         kernels (unet_train.py); under ``torch.no_grad()`` (sampling, validation) it is the inference path."""
         if torch.is_grad_enabled() and not return_taps and any(p.requires_grad for p in self.parameters()):
+            if len(self.downs) != 4 or not self.time_in:
+                raise NotImplementedError(
+                    "the backward kernels cover the flow_diffuser UNet (four levels, time input); the three-level autoencoder "
+                    "UNets (flow_pred.py:23-37) are used frozen (flow_diffuser.py:93-94): call them under torch.no_grad() or "
+                    "set requires_grad_(False)")
             return UnetFunction.apply(self, x, external_cond, time, nan_mask, *self.parameters())
         with _lib.nvtx_range("unet.forward"):
             return self._forward_infer(x, external_cond, time, nan_mask, return_taps)
@@ -445,7 +455,8 @@ class Unet(UnetParams, TrainMixin):
         # three 2x pixel-unshuffle downsamples (:95-99) need H, W % 8 == 0 (436 -> 440): replicate-pad like the
         # repo's own InputPadder(mode='sintel') (future/raft_utils.py:7-25) and crop the prediction back -- both folded
         # into the first / last kernel (fd_pack_input_pad clamps its reads, fd_final_conv_crop writes the window only)
-        ph, pw = (-H0) % 8, (-W0) % 8
+        mult = 2 ** (len(self.downs) - 1)                # 8, or 4 for the three-level autoencoder UNets (flow_pred.py:23-37)
+        ph, pw = (-H0) % mult, (-W0) % mult
         pad = (pw // 2, pw - pw // 2, ph // 2, ph - ph // 2)
         x = x.contiguous()
         cond = cond.contiguous() if cond is not None else None
@@ -469,8 +480,8 @@ class Unet(UnetParams, TrainMixin):
 
         # init_conv 7x7 (:297,374) as a 7x1 conv over the horizontally unrolled input
         packed = torch.empty(B, H, W, 64, device=dev, dtype=BF16)
-        _lib.check(lib.fd_pack_input_pad(_lib.ptr(x), _lib.ptr(cond), _lib.ptr(packed), B, Cx, Cc, H0, W0, pad[2], pad[0],
-                                         H, W, int(nan_mask), st))
+        pack = lib.fd_pack_input_wide if self._wide_input else lib.fd_pack_input_pad
+        _lib.check(pack(_lib.ptr(x), _lib.ptr(cond), _lib.ptr(packed), B, Cx, Cc, H0, W0, pad[2], pad[0], H, W, int(nan_mask), st))
         h = self._conv("init_conv", packed)
         del packed
         r = h

@@ -125,7 +125,7 @@ class TrainMixin:
         lib, st = self._lib, _lib.stream()
         recs, blocks = [], [0]
         for name, pc in self._convs.items():
-            if pc.kind == 2 or name.endswith((".to_kv", ".to_q")):
+            if pc.kind >= 2 or name.endswith((".to_kv", ".to_q")):
                 continue
             cout, k = pc.w.shape
             taps = 1 if pc.kind == 1 else pc.kh * pc.kw
@@ -479,7 +479,11 @@ class TrainMixin:
         self._stats = torch.zeros(2 * len(self._resblocks), B, 8, 2, device=dev, dtype=torch.float64)
         self._stats_i = 0
         packed = torch.empty(B, H, W, 64, device=dev, dtype=BF16)
-        _lib.check(lib.fd_pack_input(_lib.ptr(x), _lib.ptr(cond), _lib.ptr(packed), B, Cx, Cc, H, W, int(nan_mask), st))
+        if self._wide_input:
+            _lib.check(lib.fd_pack_input_wide(_lib.ptr(x), _lib.ptr(cond), _lib.ptr(packed), B, Cx, Cc, H, W, 0, 0, H, W,
+                                              int(nan_mask), st))
+        else:
+            _lib.check(lib.fd_pack_input(_lib.ptr(x), _lib.ptr(cond), _lib.ptr(packed), B, Cx, Cc, H, W, int(nan_mask), st))
         h = self._t_conv(tape, "init_conv", packed, need_dgrad=False)
         r = h
         skips: List[Tensor] = []

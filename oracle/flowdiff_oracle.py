@@ -134,7 +134,8 @@ def _pixel_unshuffle2(x: Tensor) -> Tensor:
 
 def unet_forward(sd: Dict[str, Tensor], x: Tensor, cond: Optional[Tensor], t: Tensor,
                  prefix: str = "", return_taps: bool = False):
-    """Unet.forward, denoising_diffusion.py:363-417 (dim=64, mults (1,2,4,8), no self-cond).
+    """Unet.forward, denoising_diffusion.py:363-417 (dim=64, no self-cond; the number of levels -- four for the flow UNet,
+    three for the latent autoencoder's UNets, flow_pred.py:23-37 -- is read from the parameter names).
 
     ``sd`` holds the reference's parameter names (``init_conv.weight`` ...) under ``prefix``.
     ``return_taps`` additionally returns named intermediates for per-layer parity tests.
@@ -151,7 +152,7 @@ def unet_forward(sd: Dict[str, Tensor], x: Tensor, cond: Optional[Tensor], t: Te
         temb = time_embedding(sd, t)
         taps["temb"] = temb
     skips: List[Tensor] = []
-    n_levels = 4
+    n_levels = sum(1 for i in range(8) if f"downs.{i}.0.block1.proj.weight" in sd)
     for i in range(n_levels):
         p = f"downs.{i}."
         x = _resnet_block(sd, p + "0.", x, temb)
@@ -194,6 +195,34 @@ def unet_forward(sd: Dict[str, Tensor], x: Tensor, cond: Optional[Tensor], t: Te
     if return_taps:
         return out, taps
     return out
+
+
+def autoencoder_encode(sd, x: Tensor, prefix: str = "") -> Tensor:
+    """Autoencoder.encode, flow_pred.py:49-50: clamp(model_enc(2x - 1), -1, 1); ``sd`` holds ``model_enc.*`` / ``model_dec.*``."""
+    return torch.clamp(unet_forward(sd, 2 * x - 1.0, None, None, prefix=prefix + "model_enc."), -1.0, 1.0)
+
+
+def autoencoder_decode(sd, latent: Tensor, x: Tensor, prefix: str = "") -> Tensor:
+    """Autoencoder.decode, flow_pred.py:53-57."""
+    out = unet_forward(sd, torch.cat((latent, 2 * x - 1), dim=1), None, None, prefix=prefix + "model_dec.")
+    return (torch.clamp(out, -1.0, 1.0) + 1.0) / 2.0
+
+
+def autoencoder_forward(sd, x: Tensor, flow: Tensor, prefix: str = "") -> Tensor:
+    """Autoencoder.forward, flow_pred.py:38-47: encode, forward-splat the latent along ``flow`` (pixels), decode."""
+    lat = warp_forward_flow(autoencoder_encode(sd, x, prefix), flow)
+    return autoencoder_decode(sd, lat, x, prefix)
+
+
+def latent_preprocess(ae_sd, img: Tensor, flow: Tensor, flow_max: float = 20.0, latent_max: float = 2.0, target: str = "target"):
+    """FlowDiffuser.preprocess with ``latent: true`` (flow_diffuser.py:136-168, aug off): the conditioning frame is the
+    clamped, scaled latent; the diffusion target its forward splat along the ground-truth flow (+ the flow for 'joint')."""
+    flow_n = torch.clamp(flow / flow_max, -1.0, 1.0)
+    cond = torch.clamp(autoencoder_encode(ae_sd, img) / latent_max, -1.0, 1.0)
+    first = warp_forward_flow(cond, flow_n * flow_max)
+    if target == "joint":
+        first = torch.cat((first, flow_n), dim=1)
+    return first, cond, flow_n
 
 
 # --------------------------------------------------------------------------------------
@@ -357,23 +386,24 @@ def p_losses_flow(sd, sched, x0: Tensor, cond: Tensor, t: Tensor, noise: Tensor,
 
 
 def unet_with_warp(sd, x: Tensor, cond: Tensor, t: Tensor, flow_max: float = 20.0, full_output: bool = True,
-                   additional_out: bool = False, prefix: str = "") -> Tensor:
+                   additional_out: bool = False, prefix: str = "", dim: int = 3) -> Tensor:
     """UnetWithWarp.forward, flow_diffuser.py:38-63 (nan_safe=True): NaN -> 0 plus a 1-channel "any NaN" mask appended
     to x; flow = Unet(...); warped = forward splat of cond[:, :3] along flow * flow_max; cat(warped, flow) when
-    ``full_output`` (target='joint'); the flow appended once more when ``additional_out`` (target='target')."""
+    ``full_output`` (target='joint'); the flow appended once more when ``additional_out`` (target='target').
+    ``dim`` = 3, or latent_dim in latent mode (flow_diffuser.py:25)."""
     x = x.clone()
     nans = torch.isnan(x)
     x[nans] = 0.0
     mask = torch.any(nans, dim=1)[:, None]
     flow = unet_forward(sd, torch.cat((x, mask), dim=1), cond, t, prefix)
-    out = warp_forward_flow(cond[:, :3], flow[:, :2] * flow_max)
+    out = warp_forward_flow(cond[:, :dim], flow[:, :2] * flow_max)
     if full_output:
         out = torch.cat((out, flow), dim=1)
     return torch.cat((out, flow), dim=1) if additional_out else out
 
 
 def pyramid_loss(image_out: Tensor, target: Tensor, flow_out: Optional[Tensor] = None, cond: Optional[Tensor] = None,
-                 flow_max: float = 20.0, levels=(2, 4, 8, 16)) -> Tensor:
+                 flow_max: float = 20.0, levels=(2, 4, 8, 16), dim: int = 3) -> Tensor:
     """ConditionalDiffusion._loss, denoising_diffusion.py:893-983.  Level 1: NaN-filtered squared error of
     (image_out, target) (:906-908).  With a flow target (``flow_out`` given) every level L in 2,4,8,16 adds the
     NaN-filtered squared error between the splat of ``cond`` along the predicted flow at scale L and the splat of the
@@ -382,8 +412,8 @@ def pyramid_loss(image_out: Tensor, target: Tensor, flow_out: Optional[Tensor] =
     terms = [nan_mse(image_out, target, reduction="none")]
     if flow_out is not None:
         for level in levels:
-            a = warp_forward_flow(cond[:, :3], flow_out * flow_max, scale=level)
-            b = warp_forward_flow(target[:, :3], torch.zeros_like(flow_out) * flow_max, scale=level)
+            a = warp_forward_flow(cond[:, :dim], flow_out * flow_max, scale=level)       # UnetWithWarp._warp slices by dim
+            b = warp_forward_flow(target[:, :dim], torch.zeros_like(flow_out) * flow_max, scale=level)
             terms.append(nan_mse(a, b, reduction="none") * level ** 4)
     return torch.nanmean(torch.cat(terms, dim=0))
 
@@ -399,14 +429,14 @@ def p_losses_joint(sd, sched, x0: Tensor, cond: Tensor, t: Tensor, noise: Tensor
 
 
 def p_losses_target(sd, sched, x0: Tensor, cond: Tensor, flow_tgt: Tensor, t: Tensor, noise: Tensor,
-                    flow_max: float = 20.0, prefix: str = "", model_out: Optional[Tensor] = None) -> Tensor:
+                    flow_max: float = 20.0, prefix: str = "", model_out: Optional[Tensor] = None, dim: int = 3) -> Tensor:
     """p_losses with target='target' (x0 = warped target image, ``additional_tgt`` = normalised flow): :868-885.
     The model is called with additional_out=True, its last 2 channels are the flow prediction."""
     if model_out is None:
         x_t = q_sample(sched, x0, t, noise)
-        model_out = unet_with_warp(sd, x_t, cond, t, flow_max, False, True, prefix)
+        model_out = unet_with_warp(sd, x_t, cond, t, flow_max, False, True, prefix, dim)
     k = flow_tgt.shape[1]
-    return pyramid_loss(model_out[:, :-k], x0, model_out[:, -k:], cond, flow_max)
+    return pyramid_loss(model_out[:, :-k], x0, model_out[:, -k:], cond, flow_max, dim=dim)
 
 
 # --------------------------------------------------------------------------------------
