@@ -263,6 +263,12 @@ FD_API int fd_linattn_tc(const void* x, const void* wk, const float* sk, const f
 /* Attention core (:256-267): softmax(q^T k * 32^-0.5) v, flash-style, bf16 (N,HW,384) -> (N,HW,128) */
 FD_API int fd_attention(const void* qkv, void* out, int N, int HW, void* stream);
 
+/* Logging reductions of training_step / validation_step (flow_diffuser.py:221-232, 262-282) in one pass: x fp32 (B, inner)
+ * -> out4 = {torch.min(x), torch.max(x), torch.mean(x), torch.mean(torch.std(x, dim=0))} (unbiased std over the batch axis;
+ * NaN propagation as torch).  workspace: fd_tensor_stats_workspace_floats(inner) floats.  Deterministic, no host sync. */
+FD_API size_t fd_tensor_stats_workspace_floats(long inner);
+FD_API int fd_tensor_stats(const float* x, int B, long inner, float* out4, float* workspace, void* stream);
+
 /* final 1x1 conv (:361,417) 64 -> Cout (<= 64; four output channels per launch) from bf16 NHWC to fp32 NCHW */
 FD_API int fd_final_conv(const void* x, const float* w, const float* bias, float* out, int N, int HW, int Cin,
                   int Cout, void* stream);

@@ -97,6 +97,8 @@ SIGNATURES = {
     "fd_aug_blur3": (c_int, [_P, _P, _P, _P, _I, _I, _I, _P]),
     "fd_aug_geometric": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P]),
     "fd_loss_workspace_floats": (c_size_t, [_L]),
+    "fd_tensor_stats_workspace_floats": (c_size_t, [_L]),
+    "fd_tensor_stats": (c_int, [_P, _I, _L, _P, _P, _P]),
     "fd_soft_charb_fwd": (c_int, [_P, _P, _P, _P, _I, _I, _I, _P]),
     "fd_soft_charb_bwd": (c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _P]),
     "fd_edge_smooth_fwd": (c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),

@@ -117,8 +117,8 @@ class FlowLearner(_Base):
     # ------------------------------------------------------------------ steps
     @staticmethod
     def _stats(prefix: str, name: str, x: Tensor):
-        return {f"{prefix}/{name}_min": torch.min(x), f"{prefix}/{name}_max": torch.max(x),
-                f"{prefix}/{name}_mean": torch.mean(x), f"{prefix}/{name}_std": torch.mean(torch.std(x, dim=0))}
+        from .flow_diffuser import logged_stats
+        return logged_stats(prefix, name, x)
 
     def training_step(self, batch, batch_idx):
         tgt, cond, flow = self.preprocess(batch, aug=bool(_cfg_get(self.cfg, "train_aug", True)))

@@ -427,9 +427,9 @@ class Unet(UnetParams, TrainMixin):
         With autograd enabled (training_step) the call is one ``UnetFunction`` node whose backward runs the backward
         kernels (unet_train.py); under ``torch.no_grad()`` (sampling, validation) it is the inference path."""
         if torch.is_grad_enabled() and not return_taps and any(p.requires_grad for p in self.parameters()):
-            if len(self.downs) != 4 or not self.time_in:
+            if len(self.downs) != 4:
                 raise NotImplementedError(
-                    "the backward kernels cover the flow_diffuser UNet (four levels, time input); the three-level autoencoder "
+                    "the backward kernels cover the four-level UNets (flow_diffuser, flow_learner); the three-level autoencoder "
                     "UNets (flow_pred.py:23-37) are used frozen (flow_diffuser.py:93-94): call them under torch.no_grad() or "
                     "set requires_grad_(False)")
             return UnetFunction.apply(self, x, external_cond, time, nan_mask, *self.parameters())

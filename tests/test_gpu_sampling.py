@@ -200,3 +200,31 @@ def test_cuda_graph_follows_weight_updates():
     m.load_state_dict(sd, strict=False)
     g3, e3 = both()
     assert (g3 - e3).abs().max().item() < 5e-3
+
+
+@pytest.mark.parametrize("shape", [(8, 3, 46, 96), (2, 2, 7, 5), (1, 5, 16, 16), (5, 1, 300, 301)])
+def test_logged_statistics_one_pass(shape):
+    """fd_tensor_stats (the min / max / mean / mean-of-batch-std the reference logs every step with eager reductions,
+    flow_diffuser.py:221-232, 262-282) == torch; NaN propagation and the B = 1 case (std of one value = NaN) included."""
+    from opticalflowdiffusion_b200.flow_diffuser import logged_stats
+    g = torch.Generator().manual_seed(shape[-1])
+    x = (torch.randn(*shape, generator=g) * 3 + 0.5).cuda()
+    got = logged_stats("train", "cond", x)
+    ref = {"train/cond_min": torch.min(x), "train/cond_max": torch.max(x), "train/cond_mean": torch.mean(x),
+           "train/cond_std": torch.mean(torch.std(x, dim=0))}
+    assert set(got) == set(ref)
+    for k in ref:
+        a, b = float(got[k]), float(ref[k])
+        if b != b:
+            assert a != a, k                       # B = 1: torch.std over one value is NaN
+        elif k.endswith(("_min", "_max")):
+            assert a == b, k
+        else:
+            assert abs(a - b) <= 2e-6 * max(1.0, abs(b)), (k, a, b)
+    again = logged_stats("train", "cond", x)
+    assert all(torch.equal(got[k], again[k]) or float(got[k]) != float(got[k]) for k in got)      # deterministic
+    if shape[0] > 1:
+        x[0, 0, 1, 2] = float("nan")
+        got = logged_stats("val", "flow", x)
+        for k, fn in (("val/flow_min", torch.min), ("val/flow_max", torch.max), ("val/flow_mean", torch.mean)):
+            assert float(got[k]) != float(got[k]) and float(fn(x)) != float(fn(x))
