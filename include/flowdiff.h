@@ -52,6 +52,11 @@ FD_API int fd_backwarp_fwd(const float* image, const float* flow, float* out, fl
 FD_API int fd_backwarp_bwd(const float* image, const float* flow, const float* gout,
                     float* gimage, float* gflow, int B, int C, int H, int W, void* stream);
 
+/* Self-test of the warp kernels' division: the normalisation `2 v / (W - 1)` of warp.py:107-108 is computed with the
+ * reciprocal half of `__fdiv_rn`'s own instruction sequence hoisted out of the pixel loop (fd_warp_common.cuh:bw_div_rn);
+ * this runs ALL 2^32 numerator bit patterns for one divisor against `__fdiv_rn` and counts the differences (expected: 0). */
+FD_API int fd_warp_div_selftest(float divisor, unsigned long long* mismatches, void* stream);
+
 /* fused warp + Charbonnier photometric + end-point error (BASELINE config #4):
  *   warped, mask = backwarp(frame2, flow)
  *   sums[0] = sum(mask * sqrt((frame1-warped)^2 + 1e-6))   losses.py:3-6,46-47

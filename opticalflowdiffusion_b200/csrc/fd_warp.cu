@@ -1,9 +1,11 @@
 // Backward bilinear warp (warp.py:95-119 of the reference) and the fused
 // warp + Charbonnier photometric + end-point-error objective (losses.py:3-6,46-47).
 //
-// HBM-bound gather/scatter work on fp32 NCHW planes.  Layout choices:
-//   * one thread owns VEC (=4 when W % 4 == 0) consecutive pixels of a row, so flow / flow_gt /
-//     frame1 / out / mask move as 128-bit coalesced accesses;
+// Gather/scatter work on fp32 NCHW planes.  The FORWARD operations on three-channel frames with W % 4 == 0 run the
+// shared-memory window kernels of fd_warp_win.cu (TMA-staged frame, 1.5-2x faster on the config-#4 white-noise flow);
+// the kernels in this file serve every other shape and all the backward passes.  Layout choices:
+//   * one thread owns VEC (1, 2 or 4 when W allows; 2 by default) consecutive pixels of a row, so flow / flow_gt /
+//     frame1 / out / mask move as wide coalesced accesses; a block walks (row, segment) jobs, no per-thread divisions;
 //   * the 4-tap gathers of the warped frame go through the read-only path (L1/L2 resident: a
 //     warp's taps fall in a few rows of the source plane);
 //   * the scatter of the image gradient merges contributions that hit the same address inside a
@@ -49,30 +51,45 @@ struct Vec<4> {
   }
 };
 
-// A thread's item = VEC consecutive pixels of one row: item -> (b, y, x)
+// Work decomposition without per-thread divisions.  A "row job" = (image row r = b * H + y, segment of blockDim.x * VEC
+// pixels of it); blocks walk the jobs grid-stride, thread t of a block owns VEC consecutive pixels of the segment.  The first
+// version mapped a flat 64-bit item index to (b, y, x) with three 64-bit divisions PER THREAD per item: ncu showed 298
+// executed instructions per pixel in the fused photometric forward, most of them division emulation (IMAD chains + CALLs).
+// Here the two divisions are 32-bit, once per job, on block-uniform values; offsets inside a plane are 32-bit (H * W < 2^31
+// is checked on the host), only the plane base is 64-bit.
+struct RowJob {
+  int b, y, x;      // x = first of the thread's VEC pixels
+  bool valid;       // x < W (ragged last segment)
+};
 template <int VEC>
-__device__ __forceinline__ void item_to_byx(long item, int H, int W, int& b, int& y, int& x) {
-  const int wq = W / VEC;
-  x = (int)(item % wq) * VEC;
-  const long r = item / wq;
-  y = (int)(r % H);
-  b = (int)(r / H);
+__device__ __forceinline__ RowJob row_job(unsigned job, unsigned segs, unsigned H, int W) {
+  const unsigned row = job / segs, seg = job - row * segs;
+  const unsigned b = row / H;
+  RowJob r;
+  r.b = (int)b;
+  r.y = (int)(row - b * H);
+  r.x = (int)((seg * blockDim.x + threadIdx.x) * VEC);
+  r.valid = r.x < W;
+  return r;
 }
+static unsigned row_segs(int W, int vec, int threads) { return (unsigned)((W / vec + threads - 1) / threads); }
 
 // ---------------------------------------------------------------------------------------------
 // forward: out, mask
 // ---------------------------------------------------------------------------------------------
-template <int VEC>
+template <int VEC, int CT>
 __global__ void __launch_bounds__(256, VEC == 4 ? 2 : 4) backwarp_fwd_kernel(const float* __restrict__ image,
                                                            const float* __restrict__ flow,
                                                            float* __restrict__ out, float* __restrict__ mask,
-                                                           int B, int C, BwGeom g, long items) {
+                                                           int B, int C, BwGeom g, unsigned segs, unsigned jobs) {
   const int H = g.H, W = g.W;
   const long HW = (long)H * W;
-  for (long item = (long)blockIdx.x * blockDim.x + threadIdx.x; item < items; item += (long)gridDim.x * blockDim.x) {
-    int b, y, x;
-    item_to_byx<VEC>(item, H, W, b, y, x);
-    const long pix = (long)y * W + x;
+  const BwDiv dv = bw_divisors(g);
+  for (unsigned job = blockIdx.x; job < jobs; job += gridDim.x) {
+    const RowJob rj = row_job<VEC>(job, segs, (unsigned)H, W);
+    if (!rj.valid) continue;
+    const int b = rj.b, y = rj.y, x = rj.x;
+    const int pix = y * W + x;
     Vec<VEC> fdy, fdx;
     fdy.load(flow + ((long)b * 2 + 0) * HW + pix);
     fdx.load(flow + ((long)b * 2 + 1) * HW + pix);
@@ -80,10 +97,12 @@ __global__ void __launch_bounds__(256, VEC == 4 ? 2 : 4) backwarp_fwd_kernel(con
     Vec<VEC> m;
 #pragma unroll
     for (int j = 0; j < VEC; ++j) {
-      bw_taps(fdx.v[j], fdy.v[j], x + j, y, g, t[j]);
+      bw_taps(fdx.v[j], fdy.v[j], x + j, y, g, dv, t[j]);
       m.v[j] = bw_mask(t[j]);
     }
-    for (int c = 0; c < C; ++c) {
+    const int Cn = CT > 0 ? CT : C;          // CT = 3: the RGB case unrolled, all three channels' gathers in flight at once
+#pragma unroll
+    for (int c = 0; c < Cn; ++c) {
       const float* plane = image + ((long)b * C + c) * HW;
       Vec<VEC> o;
 #pragma unroll
@@ -97,22 +116,20 @@ __global__ void __launch_bounds__(256, VEC == 4 ? 2 : 4) backwarp_fwd_kernel(con
 // ---------------------------------------------------------------------------------------------
 // backward of sum(out * gout): gimage (scatter), gflow (gather)
 // ---------------------------------------------------------------------------------------------
-template <int VEC>
+template <int VEC, int CT>
 __global__ void __launch_bounds__(256, VEC == 4 ? 1 : 3) backwarp_bwd_kernel(const float* __restrict__ image,
                                                            const float* __restrict__ flow,
                                                            const float* __restrict__ gout,
                                                            float* __restrict__ gimage, float* __restrict__ gflow,
-                                                           int B, int C, BwGeom g, long items) {
+                                                           int B, int C, BwGeom g, unsigned segs, unsigned jobs) {
   const int H = g.H, W = g.W;
   const long HW = (long)H * W;
-  const int lane = threadIdx.x & 31;
-  for (long base = (long)blockIdx.x * blockDim.x + (threadIdx.x & ~31); base < items;
-       base += (long)gridDim.x * blockDim.x) {
-    const long item = base + lane;
-    const bool valid = item < items;
-    int b = 0, y = 0, x = 0;
-    if (valid) item_to_byx<VEC>(item, H, W, b, y, x);
-    const long pix = (long)y * W + x;
+  const BwDiv dv = bw_divisors(g);
+  for (unsigned job = blockIdx.x; job < jobs; job += gridDim.x) {        // (whole warps stay together: fd_scatter_merged)
+    const RowJob rj = row_job<VEC>(job, segs, (unsigned)H, W);
+    const bool valid = rj.valid;
+    const int b = rj.b, y = rj.y, x = valid ? rj.x : 0;
+    const int pix = y * W + x;
     Vec<VEC> fdy, fdx;
 #pragma unroll
     for (int j = 0; j < VEC; ++j) fdy.v[j] = fdx.v[j] = 0.f;
@@ -124,10 +141,12 @@ __global__ void __launch_bounds__(256, VEC == 4 ? 1 : 3) backwarp_bwd_kernel(con
     float dix[VEC], diy[VEC];
 #pragma unroll
     for (int j = 0; j < VEC; ++j) {
-      bw_taps(fdx.v[j], fdy.v[j], x + j, y, g, t[j]);
+      bw_taps(fdx.v[j], fdy.v[j], x + j, y, g, dv, t[j]);
       dix[j] = diy[j] = 0.f;
     }
-    for (int c = 0; c < C; ++c) {
+    const int Cn = CT > 0 ? CT : C;
+#pragma unroll
+    for (int c = 0; c < Cn; ++c) {
       const long plane_off = ((long)b * C + c) * HW;
       Vec<VEC> go;
 #pragma unroll
@@ -178,26 +197,28 @@ __global__ void __launch_bounds__(256, VEC == 4 ? 1 : 3) backwarp_bwd_kernel(con
 // ---------------------------------------------------------------------------------------------
 constexpr int kPhotoThreads = 256;
 
-static int photo_grid(long items) {
-  long blocks = (items + kPhotoThreads - 1) / kPhotoThreads;
+static int photo_grid(long items) {        // items = row jobs
+  long blocks = items;
   const long cap = (long)FD_NUM_SMS * 8;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   return (int)blocks;
 }
 
-template <int VEC>
+template <int VEC, int CT>
 __global__ void __launch_bounds__(kPhotoThreads, VEC == 4 ? 2 : 4) photo_epe_fwd_kernel(
     const float* __restrict__ frame1, const float* __restrict__ frame2, const float* __restrict__ flow,
-    const float* __restrict__ flow_gt, float* __restrict__ partials, int B, int C, BwGeom g, long items) {
+    const float* __restrict__ flow_gt, float* __restrict__ partials, int B, int C, BwGeom g, unsigned segs, unsigned jobs) {
   __shared__ float red[3 * 32];
   const int H = g.H, W = g.W;
   const long HW = (long)H * W;
+  const BwDiv dv = bw_divisors(g);
   float s[3] = {0.f, 0.f, 0.f};
-  for (long item = (long)blockIdx.x * blockDim.x + threadIdx.x; item < items; item += (long)gridDim.x * blockDim.x) {
-    int b, y, x;
-    item_to_byx<VEC>(item, H, W, b, y, x);
-    const long pix = (long)y * W + x;
+  for (unsigned job = blockIdx.x; job < jobs; job += gridDim.x) {
+    const RowJob rj = row_job<VEC>(job, segs, (unsigned)H, W);
+    if (!rj.valid) continue;
+    const int b = rj.b, y = rj.y, x = rj.x;
+    const int pix = y * W + x;
     const long fo = (long)b * 2 * HW + pix;
     Vec<VEC> f0, f1, g0, g1;
     f0.load(flow + fo);
@@ -208,13 +229,15 @@ __global__ void __launch_bounds__(kPhotoThreads, VEC == 4 ? 2 : 4) photo_epe_fwd
     float m[VEC];
 #pragma unroll
     for (int j = 0; j < VEC; ++j) {
-      bw_taps(f1.v[j], f0.v[j], x + j, y, g, t[j]);
+      bw_taps(f1.v[j], f0.v[j], x + j, y, g, dv, t[j]);
       m[j] = bw_mask(t[j]);
       const float du = f0.v[j] - g0.v[j], dv = f1.v[j] - g1.v[j];
       const float e2 = du * du + dv * dv;
       s[2] += e2 > 0.f ? e2 * rsqrtf(e2) : 0.f;
     }
-    for (int c = 0; c < C; ++c) {
+    const int Cn = CT > 0 ? CT : C;
+#pragma unroll
+    for (int c = 0; c < Cn; ++c) {
       const long po = ((long)b * C + c) * HW;
       Vec<VEC> a;
       a.load(frame1 + po + pix);
@@ -263,23 +286,21 @@ __global__ void __launch_bounds__(256) finalize_sums_kernel(const float* __restr
   }
 }
 
-template <int VEC>
+template <int VEC, int CT>
 __global__ void __launch_bounds__(256, VEC == 4 ? 1 : 3) photo_epe_bwd_kernel(
     const float* __restrict__ frame1, const float* __restrict__ frame2, const float* __restrict__ flow,
     const float* __restrict__ flow_gt, const float* __restrict__ sums, float g_photo, float g_epe,
-    float* __restrict__ gflow, float* __restrict__ gframe2, int B, int C, BwGeom g, long items) {
+    float* __restrict__ gflow, float* __restrict__ gframe2, int B, int C, BwGeom g, unsigned segs, unsigned jobs) {
   const int H = g.H, W = g.W;
   const long HW = (long)H * W;
-  const int lane = threadIdx.x & 31;
+  const BwDiv dv = bw_divisors(g);
   const float kp = g_photo / __ldg(sums + 1);
   const float ke = g_epe / __ldg(sums + 3);
-  for (long base = (long)blockIdx.x * blockDim.x + (threadIdx.x & ~31); base < items;
-       base += (long)gridDim.x * blockDim.x) {
-    const long item = base + lane;
-    const bool valid = item < items;
-    int b = 0, y = 0, x = 0;
-    if (valid) item_to_byx<VEC>(item, H, W, b, y, x);
-    const long pix = (long)y * W + x;
+  for (unsigned job = blockIdx.x; job < jobs; job += gridDim.x) {        // (whole warps stay together: fd_scatter_merged)
+    const RowJob rj = row_job<VEC>(job, segs, (unsigned)H, W);
+    const bool valid = rj.valid;
+    const int b = rj.b, y = rj.y, x = valid ? rj.x : 0;
+    const int pix = y * W + x;
     const long fo = (long)b * 2 * HW + pix;
     Vec<VEC> f0, f1, g0, g1;
 #pragma unroll
@@ -294,11 +315,13 @@ __global__ void __launch_bounds__(256, VEC == 4 ? 1 : 3) photo_epe_bwd_kernel(
     float m[VEC], dix[VEC], diy[VEC];
 #pragma unroll
     for (int j = 0; j < VEC; ++j) {
-      bw_taps(f1.v[j], f0.v[j], x + j, y, g, t[j]);
+      bw_taps(f1.v[j], f0.v[j], x + j, y, g, dv, t[j]);
       m[j] = bw_mask(t[j]);
       dix[j] = diy[j] = 0.f;
     }
-    for (int c = 0; c < C; ++c) {
+    const int Cn = CT > 0 ? CT : C;
+#pragma unroll
+    for (int c = 0; c < Cn; ++c) {
       const long po = ((long)b * C + c) * HW;
       Vec<VEC> a;
 #pragma unroll
@@ -352,8 +375,9 @@ __global__ void __launch_bounds__(256, VEC == 4 ? 1 : 3) photo_epe_bwd_kernel(
   }
 }
 
-static int stream_grid(long items, int threads) {
-  long blocks = (items + threads - 1) / threads;
+static int stream_grid(long items, int threads) {        // items = row jobs (one block-iteration each)
+  (void)threads;
+  long blocks = items;
   const long cap = (long)FD_NUM_SMS * 16;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
@@ -370,6 +394,33 @@ static int pick_vec(int W) {
   int v = forced > 0 ? forced : 2;
   while (v > 1 && W % v != 0) v >>= 1;
   return v;
+}
+
+// kernel<VEC, CT> for the runtime (vec, C): CT = 3 unrolls the RGB case
+#define FD_WARP_DISPATCH(kern, ...)                       \
+  do {                                                    \
+    if (vec == 4) {                                       \
+      if (C == 3) kern<4, 3> __VA_ARGS__; else kern<4, 0> __VA_ARGS__; \
+    } else if (vec == 2) {                                \
+      if (C == 3) kern<2, 3> __VA_ARGS__; else kern<2, 0> __VA_ARGS__; \
+    } else {                                              \
+      if (C == 3) kern<1, 3> __VA_ARGS__; else kern<1, 0> __VA_ARGS__; \
+    }                                                     \
+  } while (0)
+
+// Exhaustive check of bw_div_rn (fd_warp_common.cuh) against __fdiv_rn: all 2^32 numerator bit patterns for one divisor.
+__global__ void __launch_bounds__(256) div_selftest_kernel(float c, unsigned long long* __restrict__ mismatches) {
+  const BwRcp rc = bw_rcp(c);
+  unsigned long long bad = 0;
+  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < (1ull << 32);
+       i += (unsigned long long)gridDim.x * blockDim.x) {
+    const float a = __uint_as_float((unsigned)i);
+    const unsigned got = __float_as_uint(bw_div_rn(a, rc)), want = __float_as_uint(__fdiv_rn(a, c));
+    const bool both_nan = (got & 0x7fffffffu) > 0x7f800000u && (want & 0x7fffffffu) > 0x7f800000u;
+    if (got != want && !both_nan) ++bad;
+  }
+  bad = __reduce_add_sync(0xffffffffu, (unsigned)bad);      // (per-thread counts stay far below 2^32 / 32)
+  if ((threadIdx.x & 31) == 0 && bad) atomicAdd(mismatches, bad);
 }
 
 static int check_dims(int B, int C, int H, int W) {
@@ -401,6 +452,22 @@ int fd_warp_bwd_tiled(int mode, const float* frame1, const float* frame2, const 
                       const float* sums, float g_photo, float g_epe, float* gflow, float* gframe2, int B, int C, int H, int W,
                       cudaStream_t st);
 
+// fd_warp_win.cu: forward kernels with the sampled frame staged in shared memory by TMA (three-channel frames, W % 4 == 0)
+int fd_warp_win_grid(int B, int H, int W);
+int fd_warp_fwd_win(int mode, const float* frame1, const float* frame2, const float* flow, const float* flow_gt, float* out,
+                    float* mask, float* partials, float* sums, int B, int H, int W, cudaStream_t st);
+
+// FD_WARP_WIN=0 selects the one-thread-per-pixel-group gather kernels for every shape
+static bool use_win(int C, int W, const void* a, const void* b, const void* c, const void* d) {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("FD_WARP_WIN");
+    on = e ? atoi(e) : 1;
+  }
+  auto al = [](const void* q) { return q == nullptr || (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  return on && C == 3 && W % 4 == 0 && W >= 64 && al(a) && al(b) && al(c) && al(d);
+}
+
 extern "C" {
 
 int fd_backwarp_fwd(const float* image, const float* flow, float* out, float* mask, int B, int C, int H, int W,
@@ -409,15 +476,13 @@ int fd_backwarp_fwd(const float* image, const float* flow, float* out, float* ma
   FD_REQUIRE(image && flow && out, "backwarp_fwd: null pointer");
   cudaStream_t st = (cudaStream_t)stream;
   if (use_tiled(W)) return fd_warp_fwd_tiled(0, nullptr, image, flow, nullptr, out, mask, nullptr, B, C, H, W, st);
+  if (use_win(C, W, image, flow, out, mask)) return fd_warp_fwd_win(0, nullptr, image, flow, nullptr, out, mask, nullptr, nullptr, B, H, W, st);
   const BwGeom g = make_geom(H, W);
   const int vec = pick_vec(W);
-  const long items = (long)B * H * (W / vec);
-  if (vec == 4)
-    backwarp_fwd_kernel<4><<<stream_grid(items, 256), 256, 0, st>>>(image, flow, out, mask, B, C, g, items);
-  else if (vec == 2)
-    backwarp_fwd_kernel<2><<<stream_grid(items, 256), 256, 0, st>>>(image, flow, out, mask, B, C, g, items);
-  else
-    backwarp_fwd_kernel<1><<<stream_grid(items, 256), 256, 0, st>>>(image, flow, out, mask, B, C, g, items);
+  const unsigned segs = row_segs(W, vec, 256);
+  const long items = (long)B * H * segs;                       // row jobs
+  FD_REQUIRE(items < (1L << 31), "backwarp: too many row segments");
+  FD_WARP_DISPATCH(backwarp_fwd_kernel, <<<stream_grid(items, 256), 256, 0, st>>>(image, flow, out, mask, B, C, g, segs, (unsigned)items));
   FD_LAUNCH_CHECK();
   return FD_OK;
 }
@@ -431,21 +496,28 @@ int fd_backwarp_bwd(const float* image, const float* flow, const float* gout, fl
   if (gimage) FD_CUDA(cudaMemsetAsync(gimage, 0, sizeof(float) * (size_t)B * C * H * W, st));
   if (use_tiled(W)) return fd_warp_bwd_tiled(0, nullptr, image, flow, nullptr, gout, nullptr, 0.f, 0.f, gflow, gimage, B, C, H, W, st);
   const int vec = pick_vec(W);
-  const long items = (long)B * H * (W / vec);
-  if (vec == 4)
-    backwarp_bwd_kernel<4><<<stream_grid(items, 256), 256, 0, st>>>(image, flow, gout, gimage, gflow, B, C, g, items);
-  else if (vec == 2)
-    backwarp_bwd_kernel<2><<<stream_grid(items, 256), 256, 0, st>>>(image, flow, gout, gimage, gflow, B, C, g, items);
-  else
-    backwarp_bwd_kernel<1><<<stream_grid(items, 256), 256, 0, st>>>(image, flow, gout, gimage, gflow, B, C, g, items);
+  const unsigned segs = row_segs(W, vec, 256);
+  const long items = (long)B * H * segs;                       // row jobs
+  FD_REQUIRE(items < (1L << 31), "backwarp: too many row segments");
+  FD_WARP_DISPATCH(backwarp_bwd_kernel, <<<stream_grid(items, 256), 256, 0, st>>>(image, flow, gout, gimage, gflow, B, C, g, segs, (unsigned)items));
+  FD_LAUNCH_CHECK();
+  return FD_OK;
+}
+
+int fd_warp_div_selftest(float divisor, unsigned long long* mismatches, void* stream) {
+  FD_REQUIRE(mismatches != nullptr, "warp_div_selftest: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  FD_CUDA(cudaMemsetAsync(mismatches, 0, sizeof(unsigned long long), st));
+  div_selftest_kernel<<<FD_NUM_SMS * 8, 256, 0, st>>>(divisor, mismatches);
   FD_LAUNCH_CHECK();
   return FD_OK;
 }
 
 size_t fd_photo_epe_workspace_floats(int B, int H, int W) {
-  const long items = (long)B * H * (W / pick_vec(W));
+  const long items = (long)B * H * row_segs(W, pick_vec(W), 256);
   const size_t a = (size_t)photo_grid(items) * 3, b = (size_t)fd_warp_tiles(B, H, W) * 3;
-  return a > b ? a : b;
+  const size_t c = (size_t)fd_warp_win_grid(B, H, W) * 3 + 1;      // + the ticket counter
+  return a > b ? (a > c ? a : c) : (b > c ? b : c);
 }
 
 int fd_backwarp_photo_epe_fwd(const float* frame1, const float* frame2, const float* flow, const float* flow_gt,
@@ -459,16 +531,16 @@ int fd_backwarp_photo_epe_fwd(const float* frame1, const float* frame2, const fl
     FD_LAUNCH_CHECK();
     return FD_OK;
   }
+  if (use_win(C, W, frame1, frame2, flow, flow_gt)) {
+    return fd_warp_fwd_win(1, frame1, frame2, flow, flow_gt, nullptr, nullptr, partials, sums, B, H, W, st);
+  }
   const BwGeom g = make_geom(H, W);
   const int vec = pick_vec(W);
-  const long items = (long)B * H * (W / vec);
+  const unsigned segs = row_segs(W, vec, 256);
+  const long items = (long)B * H * segs;                       // row jobs
+  FD_REQUIRE(items < (1L << 31), "backwarp: too many row segments");
   const int grid = photo_grid(items);
-  if (vec == 4)
-    photo_epe_fwd_kernel<4><<<grid, kPhotoThreads, 0, st>>>(frame1, frame2, flow, flow_gt, partials, B, C, g, items);
-  else if (vec == 2)
-    photo_epe_fwd_kernel<2><<<grid, kPhotoThreads, 0, st>>>(frame1, frame2, flow, flow_gt, partials, B, C, g, items);
-  else
-    photo_epe_fwd_kernel<1><<<grid, kPhotoThreads, 0, st>>>(frame1, frame2, flow, flow_gt, partials, B, C, g, items);
+  FD_WARP_DISPATCH(photo_epe_fwd_kernel, <<<grid, kPhotoThreads, 0, st>>>(frame1, frame2, flow, flow_gt, partials, B, C, g, segs, (unsigned)items));
   FD_LAUNCH_CHECK();
   finalize_sums_kernel<3><<<1, 256, 0, st>>>(partials, grid, sums, (float)((double)B * H * W), 3);
   FD_LAUNCH_CHECK();
@@ -486,13 +558,10 @@ int fd_backwarp_photo_epe_bwd(const float* frame1, const float* frame2, const fl
   if (use_tiled(W))
     return fd_warp_bwd_tiled(1, frame1, frame2, flow, flow_gt, nullptr, sums, g_photo, g_epe, gflow, gframe2, B, C, H, W, st);
   const int vec = pick_vec(W);
-  const long items = (long)B * H * (W / vec);
-  if (vec == 4)
-    photo_epe_bwd_kernel<4><<<stream_grid(items, 256), 256, 0, st>>>(frame1, frame2, flow, flow_gt, sums, g_photo, g_epe, gflow, gframe2, B, C, g, items);
-  else if (vec == 2)
-    photo_epe_bwd_kernel<2><<<stream_grid(items, 256), 256, 0, st>>>(frame1, frame2, flow, flow_gt, sums, g_photo, g_epe, gflow, gframe2, B, C, g, items);
-  else
-    photo_epe_bwd_kernel<1><<<stream_grid(items, 256), 256, 0, st>>>(frame1, frame2, flow, flow_gt, sums, g_photo, g_epe, gflow, gframe2, B, C, g, items);
+  const unsigned segs = row_segs(W, vec, 256);
+  const long items = (long)B * H * segs;                       // row jobs
+  FD_REQUIRE(items < (1L << 31), "backwarp: too many row segments");
+  FD_WARP_DISPATCH(photo_epe_bwd_kernel, <<<stream_grid(items, 256), 256, 0, st>>>(frame1, frame2, flow, flow_gt, sums, g_photo, g_epe, gflow, gframe2, B, C, g, segs, (unsigned)items));
   FD_LAUNCH_CHECK();
   return FD_OK;
 }

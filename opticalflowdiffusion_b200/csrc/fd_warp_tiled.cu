@@ -49,7 +49,8 @@ struct CTap {
 __device__ __forceinline__ void make_ctap(float fdx, float fdy, int x, int y, const BwGeom& g, int wy0, int wx0, bool exists,
                                           CTap& c, float& mask) {
   BwTaps t;
-  bw_taps(fdx, fdy, x, y, g, t);
+  const BwDiv dv = bw_divisors(g);
+  bw_taps(fdx, fdy, x, y, g, dv, t);
   mask = bw_mask(t);
   const int ry = t.y0 - wy0, rx = t.x0 - wx0;
   const bool inwin = ry >= 0 && ry + 1 < kWH && rx >= 0 && rx + 1 < kWW;

@@ -1,0 +1,325 @@
+// Backward bilinear warp (warp.py:95-119) and the fused warp + Charbonnier photometric + end-point-error forward
+// (losses.py:3-6,46-47) with the sampled frame staged in shared memory by TMA -- the forward kernels of BASELINE config #4.
+//
+// Why: the config's flow is white noise (sigma = 4 px), so the 12 bilinear taps of a pixel land in 12 different 32-byte
+// sectors and a warp-wide gather instruction touches ~24 sectors in ~5.5 L1 wavefronts (ncu, profiles/r2_prof_warp_summary.txt:
+// the one-thread-per-pixel kernels of fd_warp.cu sit at 65-73 % of the L1 data-pipe peak and move 3.9x the DRAM bytes from
+// L2 to L1).  Shared memory has no sectors: a random 4-byte gather costs its bank conflicts (~3.4 wavefronts per warp
+// instruction for 32 random banks) and nothing else, and the fill is one asynchronous bulk copy.
+//
+//   * persistent blocks (one per SM) walk 16 x 128 pixel tiles; for each tile ONE 3-d TMA load brings the
+//     (16 + 2R + 1) x (128 + 2R + 4) window (R = 16 px = 4 sigma) of all three planes of the sampled frame into one of two
+//     96 KB shared-memory buffers -- out-of-image parts arrive as zeros, which is exactly grid_sample's zero padding;
+//   * the load of tile i + 1 is in flight while tile i is computed; the thread's own flow / target / frame1 values of tile
+//     i + 1 are prefetched into registers at the same time, so a tile never waits for DRAM;
+//   * a thread owns two consecutive pixels of a tile row (1024 threads per block); taps that fall outside the window (|flow| > 16 px: 6e-5 of the
+//     taps of the config) take the global-memory path of fd_warp.cu with the reference's validity tests.
+// Geometry, weights and the accumulation order are fd_warp_common.cuh's (the reference's op sequence), so `out` / `mask` stay
+// bit-identical to fd_warp.cu and to the reference.  Three-channel frames with W % 4 == 0 only (else fd_warp.cu runs).
+#include <cuda.h>
+#include <stdlib.h>
+
+#include "fd_tc.cuh"
+#include "fd_warp_common.cuh"
+
+using namespace fdwarp;
+using namespace fdtc;
+
+namespace {
+
+constexpr int kTH = 16, kTW = 128, kR = 16, kC = 3;
+constexpr int kWH = kTH + 2 * kR + 1;            // 49 window rows: the south taps reach one row below the cell
+constexpr int kWW = kTW + 2 * kR + 4;            // 164 window columns (16-byte multiple; east taps reach one column further)
+constexpr int kWin = kWH * kWW;                  // floats per plane window
+constexpr int kBufBytes = ((kC * kWin * 4 + 127) / 128) * 128;
+constexpr int kTxBytes = kC * kWin * 4;          // bytes one TMA box delivers (out-of-bounds parts count)
+#ifndef FD_WIN_PX
+#define FD_WIN_PX 4
+#endif
+constexpr int kPx = FD_WIN_PX;                   // consecutive pixels per thread
+constexpr int kThreads = kTH * kTW / kPx;        // 1024: 16 rows x 64 pairs (32 warps hide the division / gather latencies)
+constexpr int kSmemBytes = 2 * kBufBytes + 128 /*barriers*/ + 128 /*alignment slack*/;
+
+struct WinParams {
+  const float* frame1;     // MODE 1
+  const float* frame2;     // the sampled frame (global fallback path)
+  const float* flow;
+  const float* flow_gt;    // MODE 1
+  float* out;              // MODE 0
+  float* mask;             // MODE 0 (may be null)
+  float* partials;         // MODE 1: [grid][3] floats, then one unsigned ticket counter (zeroed by the host before the launch)
+  float* sums;             // MODE 1: {photo sum, mask sum, EPE sum, pixel count}, written by the last block to finish
+  BwGeom g;
+  int B, tiles_x, tiles_y, ntiles;
+  int dbg;                 // FD_WARP_WIN_DBG: 1 = no compute, 2 = no TMA (timing isolation only: wrong results)
+};
+
+template <int N> struct VecT;
+template <> struct VecT<2> { using type = float2; };
+template <> struct VecT<4> { using type = float4; };
+using PxVec = VecT<kPx>::type;
+__device__ __forceinline__ void unpack(const float2& v, float (&o)[2]) { o[0] = v.x; o[1] = v.y; }
+[[maybe_unused]] __device__ __forceinline__ void unpack(const float4& v, float (&o)[4]) { o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w; }
+__device__ __forceinline__ float2 pack(const float (&o)[2]) { return make_float2(o[0], o[1]); }
+[[maybe_unused]] __device__ __forceinline__ float4 pack(const float (&o)[4]) { return make_float4(o[0], o[1], o[2], o[3]); }
+
+struct TileAt {
+  int b, y0, x0;
+};
+__device__ __forceinline__ TileAt tile_at(unsigned t, unsigned tiles_x, unsigned tiles_y) {      // once per tile, unsigned
+  TileAt r;
+  const unsigned row = t / tiles_x, b = row / tiles_y;
+  r.x0 = (int)((t - row * tiles_x) * kTW);
+  r.b = (int)b;
+  r.y0 = (int)((row - b * tiles_y) * kTH);
+  return r;
+}
+__device__ __forceinline__ float rsqrt_approx(float x) {      // one MUFU.RSQ (rsqrtf adds a denormal-range fix-up; x >= 1e-6 here)
+  float y;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float lds_f32(uint32_t addr) {      // explicit shared-space load (a generic pointer would compile to LD)
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
+
+// MODE 0: out / mask.  MODE 1: photometric + EPE partial sums.
+template <int MODE>
+__global__ void __launch_bounds__(kThreads, 1) warp_win_fwd_kernel(const __grid_constant__ CUtensorMap map_f2, const WinParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+  const uint32_t win0 = smem_u32(base);               // two window buffers, kBufBytes apart
+  const uint32_t bar0 = win0 + 2 * kBufBytes;
+  __shared__ float red[3 * 32];
+  const int tid = threadIdx.x;
+  const BwGeom g = p.g;
+  const BwDiv dv = bw_divisors(g);
+  const int H = g.H, W = g.W;
+  const long HW = (long)H * W;
+  if (tid == 0) {
+    tma_prefetch_desc(&map_f2);
+    mbar_init(bar0, 1);
+    mbar_init(bar0 + 8, 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+  constexpr int kGroups = kTW / kPx;                 // pixel groups per tile row
+  const int ry = tid / kGroups, cx = (tid % kGroups) * kPx;       // the thread's row / first column inside a tile
+
+  auto issue = [&](const TileAt& a, int buf) {        // thread 0 only
+    mbar_expect_tx(bar0 + 8 * buf, kTxBytes);
+    tma_load_3d(win0 + buf * kBufBytes, &map_f2, bar0 + 8 * buf, a.x0 - kR, a.y0 - kR, a.b * kC);
+  };
+  // the thread's own streamed values of a tile: flow (dy, dx), and for MODE 1 the target flow and frame1
+  struct Own {
+    PxVec f0, f1, g0, g1, a[kC];
+    bool exists;
+  };
+  auto load_own = [&](const TileAt& a, Own& o) {
+    const int y = a.y0 + ry, x = a.x0 + cx;
+    o.exists = y < H && x < W;                        // (W % 4 == 0: a pixel group is whole or absent)
+    if (!o.exists) return;
+    const long fo = (long)a.b * 2 * HW + (long)y * W + x;
+    o.f0 = __ldg(reinterpret_cast<const PxVec*>(p.flow + fo));
+    o.f1 = __ldg(reinterpret_cast<const PxVec*>(p.flow + fo + HW));
+    if (MODE == 1) {
+      o.g0 = __ldg(reinterpret_cast<const PxVec*>(p.flow_gt + fo));
+      o.g1 = __ldg(reinterpret_cast<const PxVec*>(p.flow_gt + fo + HW));
+      const long po = (long)a.b * kC * HW + (long)y * W + x;
+#pragma unroll
+      for (int c = 0; c < kC; ++c) o.a[c] = __ldg(reinterpret_cast<const PxVec*>(p.frame1 + po + c * HW));
+    }
+  };
+
+  float s[3] = {0.f, 0.f, 0.f};
+  int tile = blockIdx.x;
+  Own nxt;
+  nxt.exists = false;
+  TileAt ta_next = tile_at(tile < p.ntiles ? tile : 0, p.tiles_x, p.tiles_y);
+  // tile += gridDim.x as a mixed-radix addition on (tile column, tile row, image): the two divisions per tile of tile_at
+  // were 4 % of the instruction stream
+  const unsigned g1 = gridDim.x / p.tiles_x;
+  const int step_x = (int)(gridDim.x - g1 * p.tiles_x) * kTW, step_b = (int)(g1 / p.tiles_y);
+  const int step_y = (int)(g1 - (unsigned)step_b * p.tiles_y) * kTH;
+  const int lim_x = p.tiles_x * kTW, lim_y = p.tiles_y * kTH;
+  if (tile < p.ntiles) {
+    if (tid == 0 && !(p.dbg & 2)) issue(ta_next, 0);
+    load_own(ta_next, nxt);
+  }
+  for (int it = 0; tile < p.ntiles; ++it, tile += gridDim.x) {
+    const int buf = it & 1;
+    const int next = tile + gridDim.x;
+    const Own cur = nxt;
+    const TileAt a = ta_next;
+    if (next < p.ntiles) {
+      ta_next.x0 += step_x;
+      const int cx1 = ta_next.x0 >= lim_x;
+      ta_next.x0 -= cx1 * lim_x;
+      ta_next.y0 += step_y + cx1 * kTH;
+      const int cy1 = ta_next.y0 >= lim_y;
+      ta_next.y0 -= cy1 * lim_y;
+      ta_next.b += step_b + cy1;
+      if (tid == 0 && !(p.dbg & 2)) issue(ta_next, buf ^ 1);             // (buffer buf ^ 1 was released by the barrier that ended iteration it - 1)
+      load_own(ta_next, nxt);
+    }
+    if (!(p.dbg & 2)) mbar_wait(bar0 + 8 * buf, (uint32_t)(it >> 1) & 1u);
+    if (cur.exists && !(p.dbg & 1)) {
+      const int y = a.y0 + ry, x = a.x0 + cx;
+      const int wy0 = a.y0 - kR, wx0 = a.x0 - kR;
+      const uint32_t w0 = win0 + buf * kBufBytes;
+      float fdy[kPx], fdx[kPx];
+      unpack(cur.f0, fdy);
+      unpack(cur.f1, fdx);
+      float o[kC][kPx], m[kPx];
+#pragma unroll
+      for (int j = 0; j < kPx; ++j) {
+        BwTaps t;
+        bw_taps(fdx[j], fdy[j], x + j, y, g, dv, t);
+        m[j] = bw_mask(t);
+        const int wy = t.y0 - wy0, wx = t.x0 - wx0;
+        // A cell with no valid column (row) was clamped to column (row) 0 by bw_taps -- all of its taps are invalid although
+        // the clamped address holds image data: such cells (far outside the image) take the checked global path.  For every
+        // other in-window cell the zero padding that came with the copy IS the validity test: taps outside the image read 0.
+        const bool inwin = wy >= 0 && wy + 1 < kWH && wx >= 0 && wx + 1 < kWW && (t.okx0 || t.okx1) && (t.oky0 || t.oky1);
+        if (inwin) {
+          const uint32_t q = w0 + (uint32_t)(wy * kWW + wx) * 4u;
+#pragma unroll
+          for (int c = 0; c < kC; ++c) {
+            BwVals v;
+            v.nw = lds_f32(q + (c * kWin) * 4);
+            v.ne = lds_f32(q + (c * kWin + 1) * 4);
+            v.sw = lds_f32(q + (c * kWin + kWW) * 4);
+            v.se = lds_f32(q + (c * kWin + kWW + 1) * 4);
+            o[c][j] = bw_sample(v, t);
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < kC; ++c) o[c][j] = bw_sample(bw_gather(p.frame2 + ((long)a.b * kC + c) * HW, t, W), t);
+        }
+      }
+      if (MODE == 0) {
+        const long po = (long)a.b * kC * HW + (long)y * W + x;
+#pragma unroll
+        for (int c = 0; c < kC; ++c) {
+          *reinterpret_cast<PxVec*>(p.out + po + c * HW) = pack(o[c]);
+          if (p.mask != nullptr) *reinterpret_cast<PxVec*>(p.mask + po + c * HW) = pack(m);
+        }
+      } else {
+        float gdy[kPx], gdx[kPx];
+        unpack(cur.g0, gdy);
+        unpack(cur.g1, gdx);
+#pragma unroll
+        for (int j = 0; j < kPx; ++j) {
+          const float du = fdy[j] - gdy[j], dv = fdx[j] - gdx[j];
+          const float e2 = du * du + dv * dv;
+          s[2] += e2 > 0.f ? e2 * rsqrt_approx(e2) : 0.f;      // (ftz: |d| < 1e-19 px counts as 0)
+        }
+#pragma unroll
+        for (int c = 0; c < kC; ++c) {
+          float av[kPx];
+          unpack(cur.a[c], av);
+#pragma unroll
+          for (int j = 0; j < kPx; ++j) {
+            const float d = av[j] - o[c][j];
+            const float q2 = d * d + 1e-6f;
+            s[0] += m[j] * (q2 * rsqrt_approx(q2));     // sqrt(q2), q2 >= 1e-6 (as fd_warp.cu)
+            s[1] += m[j];
+          }
+        }
+      }
+    }
+    __syncthreads();      // every read of win[buf] is done: the next iteration may refill it
+  }
+  if (MODE == 1) {
+    fd_block_sum<3>(s, red);
+    __shared__ int s_last;
+    if (tid == 0) {
+      p.partials[blockIdx.x * 3 + 0] = s[0];
+      p.partials[blockIdx.x * 3 + 1] = s[1];
+      p.partials[blockIdx.x * 3 + 2] = s[2];
+      __threadfence();
+      unsigned* ticket = reinterpret_cast<unsigned*>(p.partials + (size_t)gridDim.x * 3);
+      s_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    // The last block to finish reduces the per-block partials in a FIXED order in double precision (deterministic whatever
+    // the block completion order), which saves the separate one-block finalize launch (~7 us of a ~50 us operation).
+    if (s_last && tid < 32) {
+      __threadfence();
+      double acc[3] = {0.0, 0.0, 0.0};
+      for (unsigned k = tid; k < gridDim.x; k += 32) {
+        const volatile float* q = p.partials + (size_t)k * 3;
+        acc[0] += (double)q[0];
+        acc[1] += (double)q[1];
+        acc[2] += (double)q[2];
+      }
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
+      if (tid == 0) {
+        p.sums[0] = (float)acc[0];
+        p.sums[1] = (float)acc[1];
+        p.sums[2] = (float)acc[2];
+        p.sums[3] = (float)((double)p.B * H * W);
+      }
+    }
+  }
+}
+
+}  // namespace
+
+int fd_warp_win_grid(int B, int H, int W) {
+  const long tiles = (long)B * ((H + kTH - 1) / kTH) * ((W + kTW - 1) / kTW);
+  return (int)(tiles < FD_NUM_SMS ? tiles : FD_NUM_SMS);
+}
+
+// mode 0: out / mask; mode 1: sums[4] = {photo sum, mask sum, EPE sum, pixel count}, partials = workspace of
+// fd_warp_win_grid * 3 + 1 floats.  C == 3, W % 4 == 0.
+int fd_warp_fwd_win(int mode, const float* frame1, const float* frame2, const float* flow, const float* flow_gt, float* out,
+                    float* mask, float* partials, float* sums, int B, int H, int W, cudaStream_t st) {
+  FD_REQUIRE(W % 4 == 0, "warp_win: W %% 4 != 0");
+  FD_REQUIRE((reinterpret_cast<uintptr_t>(frame2) & 15) == 0 && (reinterpret_cast<uintptr_t>(flow) & 15) == 0,
+             "warp_win: 16-byte aligned tensors");
+  WinParams p{};
+  p.frame1 = frame1; p.frame2 = frame2; p.flow = flow; p.flow_gt = flow_gt; p.out = out; p.mask = mask; p.partials = partials; p.sums = sums;
+  p.g = make_geom(H, W);
+  p.B = B;
+  p.tiles_x = (W + kTW - 1) / kTW;
+  p.tiles_y = (H + kTH - 1) / kTH;
+  const long tiles = (long)B * p.tiles_x * p.tiles_y;
+  FD_REQUIRE(tiles < (1L << 31), "warp_win: too many tiles");
+  p.ntiles = (int)tiles;
+  {
+    static int dbg = -1;
+    if (dbg < 0) { const char* e = getenv("FD_WARP_WIN_DBG"); dbg = e ? atoi(e) : 0; }
+    p.dbg = dbg;
+  }
+  CUtensorMap map;
+  {
+    const uint64_t dims[3] = {(uint64_t)W, (uint64_t)H, (uint64_t)B * kC};
+    const uint64_t str[2] = {(uint64_t)W * 4, (uint64_t)H * W * 4};
+    const uint32_t box[3] = {(uint32_t)kWW, (uint32_t)kWH, (uint32_t)kC};
+    if (int e = make_tmap_f32_plain(&map, frame2, 3, dims, str, box)) return e;
+  }
+  const int grid = fd_warp_win_grid(B, H, W);
+  static bool attr_done[2] = {false, false};
+  if (mode == 0) {
+    if (!attr_done[0]) {
+      FD_CUDA(cudaFuncSetAttribute(warp_win_fwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+      attr_done[0] = true;
+    }
+    warp_win_fwd_kernel<0><<<grid, kThreads, kSmemBytes, st>>>(map, p);
+  } else {
+    if (!attr_done[1]) {
+      FD_CUDA(cudaFuncSetAttribute(warp_win_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+      attr_done[1] = true;
+    }
+    FD_CUDA(cudaMemsetAsync(partials + (size_t)grid * 3, 0, sizeof(unsigned), st));      // the ticket counter
+    warp_win_fwd_kernel<1><<<grid, kThreads, kSmemBytes, st>>>(map, p);
+  }
+  FD_LAUNCH_CHECK();
+  return FD_OK;
+}

@@ -227,3 +227,16 @@ def test_full_size_properties(W):
     p, e = W.photometric_epe(img, img, zero, zero)
     np.testing.assert_allclose(p.item(), 1e-3, rtol=1e-4)
     assert e.item() == 0.0
+
+
+@pytest.mark.parametrize("divisor", [1023.0, 435.0, 1.0, 3.0, 767.0, 367.0, 2047.0, 47.0, 16777216.0, 0.5, 3e7])
+def test_hoisted_reciprocal_division_is_exact(divisor):
+    """bw_div_rn == __fdiv_rn for EVERY fp32 numerator (2^32 bit patterns; NaNs compared as a class): the warp kernels'
+    coordinate normalisation (warp.py:107-108) stays bit-identical to the reference with the reciprocal computed once per
+    thread.  Divisors outside 1 .. 2^24 (last two cases) take __fdiv_rn itself."""
+    from opticalflowdiffusion_b200 import _lib
+    lib = _lib.load()
+    bad = torch.full((1,), -1, dtype=torch.int64, device="cuda")
+    _lib.check(lib.fd_warp_div_selftest(divisor, _lib.ptr(bad), _lib.stream()))
+    torch.cuda.synchronize()
+    assert int(bad.item()) == 0, int(bad.item())
