@@ -457,15 +457,19 @@ int fd_warp_win_grid(int B, int H, int W);
 int fd_warp_fwd_win(int mode, const float* frame1, const float* frame2, const float* flow, const float* flow_gt, float* out,
                     float* mask, float* partials, float* sums, int B, int H, int W, cudaStream_t st);
 
+int fd_warp_bwd_win(int mode, const float* frame1, const float* frame2, const float* flow, const float* flow_gt, const float* gout,
+                    const float* sums, float g_photo, float g_epe, float* gflow, float* gimage, int B, int H, int W, cudaStream_t st);
+
 // FD_WARP_WIN=0 selects the one-thread-per-pixel-group gather kernels for every shape
-static bool use_win(int C, int W, const void* a, const void* b, const void* c, const void* d) {
+static bool use_win(int C, int W, const void* a, const void* b, const void* c, const void* d, const void* e2 = nullptr,
+                    const void* f = nullptr) {
   static int on = -1;
   if (on < 0) {
     const char* e = getenv("FD_WARP_WIN");
     on = e ? atoi(e) : 1;
   }
   auto al = [](const void* q) { return q == nullptr || (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
-  return on && C == 3 && W % 4 == 0 && W >= 64 && al(a) && al(b) && al(c) && al(d);
+  return on && C == 3 && W % 4 == 0 && W >= 64 && al(a) && al(b) && al(c) && al(d) && al(e2) && al(f);
 }
 
 extern "C" {
@@ -495,6 +499,8 @@ int fd_backwarp_bwd(const float* image, const float* flow, const float* gout, fl
   const BwGeom g = make_geom(H, W);
   if (gimage) FD_CUDA(cudaMemsetAsync(gimage, 0, sizeof(float) * (size_t)B * C * H * W, st));
   if (use_tiled(W)) return fd_warp_bwd_tiled(0, nullptr, image, flow, nullptr, gout, nullptr, 0.f, 0.f, gflow, gimage, B, C, H, W, st);
+  if (use_win(C, W, image, flow, gout, gimage, gflow))
+    return fd_warp_bwd_win(0, nullptr, image, flow, nullptr, gout, nullptr, 0.f, 0.f, gflow, gimage, B, H, W, st);
   const int vec = pick_vec(W);
   const unsigned segs = row_segs(W, vec, 256);
   const long items = (long)B * H * segs;                       // row jobs
@@ -557,6 +563,8 @@ int fd_backwarp_photo_epe_bwd(const float* frame1, const float* frame2, const fl
   if (gframe2) FD_CUDA(cudaMemsetAsync(gframe2, 0, sizeof(float) * (size_t)B * C * H * W, st));
   if (use_tiled(W))
     return fd_warp_bwd_tiled(1, frame1, frame2, flow, flow_gt, nullptr, sums, g_photo, g_epe, gflow, gframe2, B, C, H, W, st);
+  if (use_win(C, W, frame1, frame2, flow, flow_gt, gflow, gframe2))
+    return fd_warp_bwd_win(1, frame1, frame2, flow, flow_gt, nullptr, sums, g_photo, g_epe, gflow, gframe2, B, H, W, st);
   const int vec = pick_vec(W);
   const unsigned segs = row_segs(W, vec, 256);
   const long items = (long)B * H * segs;                       // row jobs
