@@ -86,6 +86,13 @@ FD_API int fd_splat_flowgrad(const float* in, const float* flow, const float* go
 FD_API int fd_splat_prepare(const float* first, float* ten_in, int B, int C, int HW, void* stream);
 /* warp_forward_flow post-processing (warp.py:139-156): img[b,c] = splat[b,C]>0 ? splat[b,c] : NaN; splat is (B,C+1,HW) */
 FD_API int fd_splat_finish(const float* splat, float* img, int B, int C, int HW, int set_nans, void* stream);
+/* warp_forward_flow(warp_style='sum') for THREE-channel images in two launches (warp.py:121-156; prepare + splat + finish
+ * fused): `acc` is a caller-provided workspace of 4*B*(H/scale)*(W/scale) floats, 16-byte aligned, in which the splat is
+ * accumulated pixel-interleaved (r, g, b, weight) so that a tap is one 128-bit vector reduction; img (B,3,H/s,W/s) receives
+ * the image (holes -> NaN when set_nans), wsum (B,1,H/s,W/s, may be NULL) the splatted weight, ten_in (B,4,H,W, may be
+ * NULL) the prepared splat input for the backward kernels (fd_splat_ingrad / fd_splat_flowgrad). */
+FD_API int fd_forward_warp_sum3(const float* first, const float* flow, float* ten_in, float* acc, float* img, float* wsum,
+                     int B, int H, int W, int scale, int off_x, int off_y, int set_nans, void* stream);
 
 /* ---- NaN-aware MSE: warp.py:260-271 + torch.nanmean (denoising_diffusion.py:908,973) --------
  * sums[0] = sum over non-NaN pairs of (pred-target)^2, sums[1] = count, sums[2] = their ratio; strided channel-slice views:

@@ -415,6 +415,75 @@ __global__ void __launch_bounds__(256) splat_finish_kernel(const float* __restri
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// warp_forward_flow for three-channel images as TWO launches (prepare + splat + finish of the generic path fused):
+//   * the accumulation buffer is pixel-interleaved (B, Ho, Wo, 4) = (r, g, b, weight), so a tap is ONE 128-bit
+//     red.global.add.v4.f32 instead of four scalar reductions on four planes -- the scatter of the config-#4 flow is bound by
+//     the number of L2 reduction operations (57 M scalar ones per call at 8 x 436 x 1024), not by bytes;
+//   * NaN -> weight 0 and the weight channel (splat_prepare) are computed on the fly; ten_in is written only when the caller
+//     keeps it for the backward; NaN source pixels (all four values zero) issue no reductions at all;
+//   * the finish pass reads the interleaved sums once and writes the planar image (holes -> NaN) and the weight-sum plane.
+// Same tap geometry and products as splat_fwd_kernel (splat_taps, __fmul_rn); the sums differ by the order of the atomics only.
+// ---------------------------------------------------------------------------------------------
+template <bool WRITE_IN>
+__global__ void __launch_bounds__(256) splat_fwd3_kernel(const float* __restrict__ first, const float* __restrict__ flow,
+                                                         float* __restrict__ ten_in, float* __restrict__ acc, int B, int H, int W,
+                                                         int Ho, int Wo, int scale, int off_x, int off_y, unsigned segs,
+                                                         unsigned jobs) {
+  const long HW = (long)H * W;
+  for (unsigned job = blockIdx.x; job < jobs; job += gridDim.x) {
+    const unsigned row = job / segs, seg = job - row * segs;
+    const unsigned b = row / (unsigned)H;
+    const int y = (int)(row - b * (unsigned)H), x = (int)(seg * blockDim.x + threadIdx.x);
+    if (x >= W) continue;
+    const int pix = y * W + x;
+    const float fx = __ldg(flow + ((long)b * 2 + 0) * HW + pix), fy = __ldg(flow + ((long)b * 2 + 1) * HW + pix);
+    float v[3];
+    bool any_nan = false;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      v[c] = __ldg(first + ((long)b * 3 + c) * HW + pix);
+      any_nan |= isnan(v[c]);
+    }
+    const float w = any_nan ? 0.f : 1.f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) v[c] = isnan(v[c]) ? 0.f : v[c] * w;
+    if (WRITE_IN) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) ten_in[((long)b * 4 + c) * HW + pix] = v[c];
+      ten_in[((long)b * 4 + 3) * HW + pix] = w;
+    }
+    if (any_nan) continue;                         // four zeros: nothing to add
+    SplatTaps t;
+    splat_taps<KIND_OUT>(fx, fy, x, y, H, W, Ho, Wo, scale, off_x, off_y, t);
+    float* cell = acc + (((long)b * Ho + t.y0) * Wo + t.x0) * 4;
+    auto red4 = [&](float* dst, float wt) {
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(__fmul_rn(v[0], wt)), "f"(__fmul_rn(v[1], wt)),
+                   "f"(__fmul_rn(v[2], wt)), "f"(__fmul_rn(w, wt))
+                   : "memory");
+    };
+    if (t.okx0 && t.oky0) red4(cell, t.nw);
+    if (t.okx1 && t.oky0) red4(cell + 4, t.ne);
+    if (t.okx0 && t.oky1) red4(cell + (long)Wo * 4, t.sw);
+    if (t.okx1 && t.oky1) red4(cell + (long)Wo * 4 + 4, t.se);
+  }
+}
+
+__global__ void __launch_bounds__(256) splat_finish3_kernel(const float* __restrict__ acc, float* __restrict__ img,
+                                                            float* __restrict__ wsum, int B, long HWo, int set_nans) {
+  const long total = (long)B * HWo;
+  const float qnan = __int_as_float(0x7fc00000);
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const long b = i / HWo, p = i - b * HWo;
+    const float4 a = __ldg(reinterpret_cast<const float4*>(acc) + i);
+    const bool keep = !set_nans || a.w > 0.f;
+    img[(b * 3 + 0) * HWo + p] = keep ? a.x : qnan;
+    img[(b * 3 + 1) * HWo + p] = keep ? a.y : qnan;
+    img[(b * 3 + 2) * HWo + p] = keep ? a.z : qnan;
+    if (wsum != nullptr) wsum[i] = a.w;
+  }
+}
+
 int sgrid(long items) {
   long blocks = (items + 255) / 256;
   const long cap = (long)FD_NUM_SMS * 16;
@@ -449,6 +518,31 @@ int fd_splat_fwd(const float* in, const float* flow, float* out, int B, int C, i
     const long items = (long)B * H * W;
     splat_fwd_kernel<1><<<sgrid(items), 256, 0, st>>>(in, flow, out, B, C, H, W, Ho, Wo, scale, off_x, off_y, items);
   }
+  FD_LAUNCH_CHECK();
+  return FD_OK;
+}
+
+int fd_forward_warp_sum3(const float* first, const float* flow, float* ten_in, float* acc, float* img, float* wsum, int B, int H,
+                         int W, int scale, int off_x, int off_y, int set_nans, void* stream) {
+  if (int e = check(B, 3, H, W, scale, off_x, off_y)) return e;
+  FD_REQUIRE(first && flow && acc && img, "forward_warp_sum3: null pointer");
+  FD_REQUIRE((reinterpret_cast<uintptr_t>(acc) & 15) == 0, "forward_warp_sum3: the accumulation buffer must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int Ho = H / scale, Wo = W / scale;
+  FD_CUDA(cudaMemsetAsync(acc, 0, sizeof(float) * 4 * (size_t)B * Ho * Wo, st));
+  const unsigned segs = (unsigned)((W + 255) / 256);
+  const long jobs = (long)B * H * segs;
+  FD_REQUIRE(jobs < (1L << 31), "forward_warp_sum3: too many row segments");
+  long grid = jobs;
+  if (grid > (long)FD_NUM_SMS * 16) grid = (long)FD_NUM_SMS * 16;
+  if (ten_in != nullptr)
+    splat_fwd3_kernel<true><<<(unsigned)grid, 256, 0, st>>>(first, flow, ten_in, acc, B, H, W, Ho, Wo, scale, off_x, off_y, segs,
+                                                             (unsigned)jobs);
+  else
+    splat_fwd3_kernel<false><<<(unsigned)grid, 256, 0, st>>>(first, flow, nullptr, acc, B, H, W, Ho, Wo, scale, off_x, off_y, segs,
+                                                              (unsigned)jobs);
+  FD_LAUNCH_CHECK();
+  splat_finish3_kernel<<<sgrid((long)B * Ho * Wo), 256, 0, st>>>(acc, img, wsum, B, (long)Ho * Wo, set_nans);
   FD_LAUNCH_CHECK();
   return FD_OK;
 }

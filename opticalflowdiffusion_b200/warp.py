@@ -8,6 +8,8 @@ SURVEY.md section 2).  All tensors must be CUDA fp32; there is no CPU path.
 """
 from __future__ import annotations
 
+import os
+
 from typing import Optional, Sequence, Tuple
 
 import torch
@@ -167,6 +169,10 @@ def softsplat(tenIn: Tensor, tenFlow: Tensor, tenMetric: Optional[Tensor], strMo
     return tenOut
 
 
+# warp_forward_flow on three-channel images through the fused two-launch path (FD_SPLAT_SUM3=0: prepare / splat / finish)
+FUSED_SUM3 = os.environ.get("FD_SPLAT_SUM3", "1") != "0"
+
+
 class _ForwardWarpSumFn(torch.autograd.Function):
     """warp_forward_flow(warp_style='sum') as three launches: prepare (NaN -> weight 0, append the
     weight channel), splat, finish (holes -> NaN).  Gradient flows to ``flow`` only (cond has no
@@ -178,6 +184,20 @@ class _ForwardWarpSumFn(torch.autograd.Function):
         B, C, H, W = first.shape
         lib = _lib.load()
         st = _lib.stream()
+        if C == 3 and FUSED_SUM3:
+            # two launches, pixel-interleaved accumulation (one 128-bit reduction per tap): fd_forward_warp_sum3
+            Ho, Wo = H // scale, W // scale
+            need_bwd = bool(ctx.needs_input_grad[0] or ctx.needs_input_grad[1])
+            ten_in = torch.empty(B, 4, H, W, device=first.device, dtype=torch.float32) if need_bwd else None
+            acc = torch.empty(B, Ho, Wo, 4, device=first.device, dtype=torch.float32)
+            img = torch.empty(B, 3, Ho, Wo, device=first.device, dtype=torch.float32)
+            wsum = torch.empty(B, 1, Ho, Wo, device=first.device, dtype=torch.float32) if need_bwd else None
+            _lib.check(lib.fd_forward_warp_sum3(_lib.ptr(first), _lib.ptr(flow), _lib.ptr(ten_in), _lib.ptr(acc), _lib.ptr(img),
+                                                _lib.ptr(wsum), B, H, W, scale, off_x, off_y, int(bool(set_nans)), st))
+            if need_bwd:
+                ctx.save_for_backward(ten_in, flow, wsum)
+            ctx.geom = (scale, off_x, off_y, bool(set_nans))
+            return img
         ten_in = torch.empty(B, C + 1, H, W, device=first.device, dtype=torch.float32)
         _lib.check(lib.fd_splat_prepare(_lib.ptr(first), _lib.ptr(ten_in), B, C, H * W, st))
         Ho, Wo = H // scale, W // scale

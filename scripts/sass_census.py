@@ -1,5 +1,5 @@
 """Per-kernel census of the Blackwell-specific SASS in lib/libflowdiff.so (cuobjdump -sass, sm_100a):
-UTCHMMA (tcgen05.mma), UTCCP (tcgen05.cp), LDTM / STTM (tcgen05.ld / st), UTMALDG / UTMASTG (TMA load / store),
+UTCHMMA (tcgen05.mma), UTCCP (tcgen05.cp), LDTM / STTM (tcgen05.ld / st), UTMALDG / UTMASTG / UTMAREDG (TMA load / store / reduce),
 UTCBAR (tcgen05.commit), SYNCS (mbarrier), plus the legacy tensor path HMMA (mma.sync) and LDGSTS (cp.async).
 Usage: python scripts/sass_census.py > profiles/r2_sass_census.txt"""
 import collections
@@ -10,7 +10,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "opticalflowdiffusion_b200", "lib", "libflowdiff.so")
-OPS = ("UTCHMMA", "UTCCP", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UTCBAR", "SYNCS", "HMMA", "LDGSTS", "FFMA2", "MUFU")
+OPS = ("UTCHMMA", "UTCCP", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UTMAREDG", "UTCBAR", "SYNCS", "HMMA", "LDGSTS", "FFMA2", "MUFU")
 
 
 def main():
