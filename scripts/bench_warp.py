@@ -77,6 +77,21 @@ def measure(iters=50, warmup=10):
     rec("splat_fwd", t, (8 + 12 + 12) * px)
     t = timeit(lambda: _lib.check(lib.fd_splat_flowgrad(P(f2), P(flow), P(out), P(gflow), B, C, H, W, 1, 0, 0, st)), flush=flush, iters=iters, warmup=warmup)
     rec("splat_flowgrad", t, (8 + 12 + 12 + 8) * px)
+    # warp_forward_flow on a three-channel image (what UnetWithWarp / the pyramid loss call): generic three launches vs the
+    # fused two-launch path with pixel-interleaved accumulation; bytes: image 12 + flow 8 + output 12 per pixel
+    ten_in = torch.empty(B, 4, H, W, device="cuda")
+    ret = torch.empty(B, 4, H, W, device="cuda")
+    acc = torch.empty(B, H, W, 4, device="cuda")
+
+    def generic():
+        _lib.check(lib.fd_splat_prepare(P(f2), P(ten_in), B, C, H * W, st))
+        _lib.check(lib.fd_splat_fwd(P(ten_in), P(flow), P(ret), B, C + 1, H, W, 1, 0, 0, st))
+        _lib.check(lib.fd_splat_finish(P(ret), P(so), B, C, H * W, 1, st))
+    t = timeit(generic, flush=flush, iters=iters, warmup=warmup)
+    rec("forward_warp_sum_3launch", t, (12 + 8 + 12) * px)
+    t = timeit(lambda: _lib.check(lib.fd_forward_warp_sum3(P(f2), P(flow), None, P(acc), P(so), None, B, H, W, 1, 0, 0, 1, st)),
+               flush=flush, iters=iters, warmup=warmup)
+    rec("forward_warp_sum_fused", t, (12 + 8 + 12) * px)
     # CLEAN_L2=1: the same launches with a clean L2 (see _timeit).  Measured: within 5 % of the dirty-L2 numbers
     # (photo_epe_fwd 72.7 vs 76.8 us), i.e. the write-back of the flush buffer is not what bounds these kernels.
     for name, fn in zip(list(res), legs if os.environ.get("CLEAN_L2") else []):
