@@ -74,6 +74,9 @@ constexpr int kATmemSlotCols = 3 * (kC / 2);   // one strip = 3 kx-shifted copie
 constexpr int kATmemSlots = 4;                 // 3 strips in use + 1 being staged
 
 // silu(z) = z sigmoid(z) = h + h tanh(h), h = z / 2: ONE MUFU op (tanh.approx, 2^-11 relative) instead of the ex2 + rcp of
+// (Round 2: FOUR transform warps, one per scheduler / MUFU unit, with their own 14-warp template variant, made the fused launch
+// faster when timed alone -- conv roofline fraction 0.80-0.83 vs 0.77-0.79 -- and left DDIM-50 unchanged on the same box,
+// 9.53 vs 9.51 flows/s (scripts/ab_bench.py with FD_LIBFLOWDIFF): the board is power-capped, the step is energy-bound.  Not kept.)
 // fd_silu.  The fused input transform runs on two warps = two of the SM's four MUFU units; with two MUFU ops per element it
 // needed ~2100 cycles per strip (more than a tile's MMAs), with one ~1050.  The result differs from fd_silu by < 2^-10
 // relative before the bf16 rounding (2^-9) that follows.

@@ -52,8 +52,9 @@ class _SqErrSums(torch.autograd.Function):
         ws = torch.empty(lib.fd_nan_mse_workspace_floats(1, 1, n), device=a.device, dtype=torch.float32)
         _lib.check(lib.fd_nan_mse_fwd(_lib.ptr(a), _lib.ptr(b), _lib.ptr(sums), _lib.ptr(ws), 1, 1, n, n, n, _lib.stream()))
         ctx.save_for_backward(a, b)
-        ctx.mark_non_differentiable(sums)
-        return sums[0].clone(), sums[1].clone()
+        num, den = sums[0].clone(), sums[1].clone()
+        ctx.mark_non_differentiable(den)
+        return num, den
 
     @staticmethod
     def backward(ctx, gnum: Tensor, _gden):
@@ -61,8 +62,11 @@ class _SqErrSums(torch.autograd.Function):
         n = a.numel()
         ga = torch.empty_like(a)
         lib = _lib.load()
-        unit = torch.tensor([0.0, 1.0, 0.0], device=a.device, dtype=torch.float32)      # "count" 1: plain 2 (a - b) g
-        _lib.check(lib.fd_nan_mse_bwd(_lib.ptr(a), _lib.ptr(b), _lib.ptr(unit), float(gnum), _lib.ptr(ga), 1, 1, n, n, n, n,
+        # the kernel scales by 2 * upstream / sums[1]: the upstream gradient stays on the device as sums[1] = 1 / g (reading
+        # it on the host would be a device-to-host sync at the head of every backward pass)
+        unit = torch.zeros(3, device=a.device, dtype=torch.float32)
+        unit[1] = 1.0 / gnum.detach().float()
+        _lib.check(lib.fd_nan_mse_bwd(_lib.ptr(a), _lib.ptr(b), _lib.ptr(unit), 1.0, _lib.ptr(ga), 1, 1, n, n, n, n,
                                       _lib.stream()))
         return ga, None
 

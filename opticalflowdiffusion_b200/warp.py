@@ -88,8 +88,13 @@ class _PhotoEpeFn(torch.autograd.Function):
         gflow = torch.empty_like(flow) if ctx.needs_input_grad[2] else None
         gframe2 = torch.empty_like(frame2) if ctx.needs_input_grad[1] else None
         lib = _lib.load()
+        # the kernel scales by g_photo / sums[1] and g_epe / sums[3]: the upstream gradients stay on the device, folded into
+        # a copy of the sums (no device-to-host read in the backward pass)
+        sg = sums.clone()
+        sg[1] = sums[1] / g_photo.detach().float()
+        sg[3] = sums[3] / g_epe.detach().float()
         _lib.check(lib.fd_backwarp_photo_epe_bwd(_lib.ptr(frame1), _lib.ptr(frame2), _lib.ptr(flow),
-                                                 _lib.ptr(flow_gt), _lib.ptr(sums), float(g_photo), float(g_epe),
+                                                 _lib.ptr(flow_gt), _lib.ptr(sg), 1.0, 1.0,
                                                  _lib.ptr(gflow), _lib.ptr(gframe2), B, C, H, W, _lib.stream()))
         return None, gframe2, gflow, None
 
@@ -295,7 +300,9 @@ class _NanMseFn(torch.autograd.Function):
         n = pred.numel()
         gpred = torch.empty_like(pred)
         lib = _lib.load()
-        _lib.check(lib.fd_nan_mse_bwd(_lib.ptr(pred), _lib.ptr(target), _lib.ptr(sums), float(g), _lib.ptr(gpred),
+        sg = sums.clone()
+        sg[1] = sums[1] / g.detach().float()          # upstream gradient folded in on the device (no host read)
+        _lib.check(lib.fd_nan_mse_bwd(_lib.ptr(pred), _lib.ptr(target), _lib.ptr(sg), 1.0, _lib.ptr(gpred),
                                       1, 1, n, n, n, n, _lib.stream()))
         return gpred, None
 
