@@ -429,28 +429,7 @@ static int check_dims(int B, int C, int H, int W) {
   return FD_OK;
 }
 
-static bool use_tiled(int W) {
-  static int on = -1;
-  if (on < 0) {
-    // default OFF: measured on B200 at 8x436x1024 the tiled kernels are SLOWER (photo_epe fwd 144 vs 77 us, bwd 288 vs
-    // 247 us, backwarp fwd 111 vs 88 us): a 16-row tile needs a +-12 pixel halo, so the window fill moves as many bytes
-    // through L2 as the per-tap gathers did, and the per-channel barriers + 128 registers cost occupancy.  These kernels
-    // are bound by instruction issue / latency, not by the gather (profiles/r2_warp_tiled_ab.txt).
-    const char* e = getenv("FD_WARP_TILED");
-    on = e ? atoi(e) : 0;
-  }
-  return on && W % 4 == 0;
-}
-
 }  // namespace
-
-// fd_warp_tiled.cu: 16 x 128 pixel tiles with the sampled frame staged in shared memory (default when W % 4 == 0)
-int fd_warp_tiles(int B, int H, int W);
-int fd_warp_fwd_tiled(int mode, const float* frame1, const float* frame2, const float* flow, const float* flow_gt, float* out,
-                      float* mask, float* partials, int B, int C, int H, int W, cudaStream_t st);
-int fd_warp_bwd_tiled(int mode, const float* frame1, const float* frame2, const float* flow, const float* flow_gt, const float* gout,
-                      const float* sums, float g_photo, float g_epe, float* gflow, float* gframe2, int B, int C, int H, int W,
-                      cudaStream_t st);
 
 // fd_warp_win.cu: forward kernels with the sampled frame staged in shared memory by TMA (three-channel frames, W % 4 == 0)
 int fd_warp_win_grid(int B, int H, int W);
@@ -479,7 +458,6 @@ int fd_backwarp_fwd(const float* image, const float* flow, float* out, float* ma
   if (int e = check_dims(B, C, H, W)) return e;
   FD_REQUIRE(image && flow && out, "backwarp_fwd: null pointer");
   cudaStream_t st = (cudaStream_t)stream;
-  if (use_tiled(W)) return fd_warp_fwd_tiled(0, nullptr, image, flow, nullptr, out, mask, nullptr, B, C, H, W, st);
   if (use_win(C, W, image, flow, out, mask)) return fd_warp_fwd_win(0, nullptr, image, flow, nullptr, out, mask, nullptr, nullptr, B, H, W, st);
   const BwGeom g = make_geom(H, W);
   const int vec = pick_vec(W);
@@ -498,7 +476,6 @@ int fd_backwarp_bwd(const float* image, const float* flow, const float* gout, fl
   cudaStream_t st = (cudaStream_t)stream;
   const BwGeom g = make_geom(H, W);
   if (gimage) FD_CUDA(cudaMemsetAsync(gimage, 0, sizeof(float) * (size_t)B * C * H * W, st));
-  if (use_tiled(W)) return fd_warp_bwd_tiled(0, nullptr, image, flow, nullptr, gout, nullptr, 0.f, 0.f, gflow, gimage, B, C, H, W, st);
   if (use_win(C, W, image, flow, gout, gimage, gflow))
     return fd_warp_bwd_win(0, nullptr, image, flow, nullptr, gout, nullptr, 0.f, 0.f, gflow, gimage, B, H, W, st);
   const int vec = pick_vec(W);
@@ -521,9 +498,9 @@ int fd_warp_div_selftest(float divisor, unsigned long long* mismatches, void* st
 
 size_t fd_photo_epe_workspace_floats(int B, int H, int W) {
   const long items = (long)B * H * row_segs(W, pick_vec(W), 256);
-  const size_t a = (size_t)photo_grid(items) * 3, b = (size_t)fd_warp_tiles(B, H, W) * 3;
+  const size_t a = (size_t)photo_grid(items) * 3;
   const size_t c = (size_t)fd_warp_win_grid(B, H, W) * 3 + 1;      // + the ticket counter
-  return a > b ? (a > c ? a : c) : (b > c ? b : c);
+  return a > c ? a : c;
 }
 
 int fd_backwarp_photo_epe_fwd(const float* frame1, const float* frame2, const float* flow, const float* flow_gt,
@@ -531,12 +508,6 @@ int fd_backwarp_photo_epe_fwd(const float* frame1, const float* frame2, const fl
   if (int e = check_dims(B, C, H, W)) return e;
   FD_REQUIRE(frame1 && frame2 && flow && flow_gt && sums && partials, "photo_epe_fwd: null pointer");
   cudaStream_t st = (cudaStream_t)stream;
-  if (use_tiled(W)) {
-    if (int e = fd_warp_fwd_tiled(1, frame1, frame2, flow, flow_gt, nullptr, nullptr, partials, B, C, H, W, st)) return e;
-    finalize_sums_kernel<3><<<1, 256, 0, st>>>(partials, fd_warp_tiles(B, H, W), sums, (float)((double)B * H * W), 3);
-    FD_LAUNCH_CHECK();
-    return FD_OK;
-  }
   if (use_win(C, W, frame1, frame2, flow, flow_gt)) {
     return fd_warp_fwd_win(1, frame1, frame2, flow, flow_gt, nullptr, nullptr, partials, sums, B, H, W, st);
   }
@@ -561,8 +532,6 @@ int fd_backwarp_photo_epe_bwd(const float* frame1, const float* frame2, const fl
   cudaStream_t st = (cudaStream_t)stream;
   const BwGeom g = make_geom(H, W);
   if (gframe2) FD_CUDA(cudaMemsetAsync(gframe2, 0, sizeof(float) * (size_t)B * C * H * W, st));
-  if (use_tiled(W))
-    return fd_warp_bwd_tiled(1, frame1, frame2, flow, flow_gt, nullptr, sums, g_photo, g_epe, gflow, gframe2, B, C, H, W, st);
   if (use_win(C, W, frame1, frame2, flow, flow_gt, gflow, gframe2))
     return fd_warp_bwd_win(1, frame1, frame2, flow, flow_gt, nullptr, sums, g_photo, g_epe, gflow, gframe2, B, H, W, st);
   const int vec = pick_vec(W);
