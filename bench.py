@@ -447,7 +447,9 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         algo.unet(x_T, cond_dev, t)
     torch.cuda.synchronize()
     conv_s = sum(ev[0].elapsed_time(ev[1]) for _, _, ev in algo.unet._conv_timing) * 1e-3 / RF_REPS
-    conv_launches = len(algo.unet._conv_timing) // RF_REPS
+    n_up = sum(1 for name, _, _ in algo.unet._conv_timing if name.startswith("ups.") and name.endswith(".3")) // RF_REPS
+    n_phase = 3 * (n_up - 1) if getattr(algo.unet, "UPCONV_PHASES", False) and n_up > 1 else 0      # an Upsample conv = 4 phase launches
+    conv_launches = len(algo.unet._conv_timing) // RF_REPS + n_phase
     algo.unet._conv_timing = None
     algo.unet(x_T, cond_dev, t)
     torch.cuda.synchronize()
