@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(kThreads, 1) warp_win_fwd_kernel(const __grid_
       for (int j = 0; j < kPx; ++j) {
         BwTaps t;
         bw_taps(fdx[j], fdy[j], x + j, y, g, dv, t);
-        m[j] = bw_mask(t);
+        m[j] = bw_mask_fast(t);
         const int wy = t.y0 - wy0, wx = t.x0 - wx0;
         // A cell with no valid column (row) was clamped to column (row) 0 by bw_taps -- all of its taps are invalid although
         // the clamped address holds image data: such cells (far outside the image) take the checked global path.  For every

@@ -203,7 +203,7 @@ __global__ void __launch_bounds__(kThreads, 1) warp_win_bwd_kernel(const __grid_
     for (int j = 0; j < kPx; ++j) {
       BwTaps t;
       bw_taps(fdx[j], fdy[j], x + j, y, g, dv, t);
-      m[j] = MODE == 1 ? bw_mask(t) : 1.f;
+      m[j] = MODE == 1 ? bw_mask_fast(t) : 1.f;
       const int wy = t.y0 - wy0, wxx = t.x0 - wx0;
       inw[j] = cur.exists && wy >= 0 && wy + 1 < kWH && wxx >= 0 && wxx + 1 < kWW && (t.okx0 || t.okx1) && (t.oky0 || t.oky1);
       cell[j] = (uint32_t)(wy * kWW + wxx) * 4u;
