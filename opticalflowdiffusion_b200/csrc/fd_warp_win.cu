@@ -102,6 +102,8 @@ __global__ void __launch_bounds__(kThreads, 1) warp_win_fwd_kernel(const __grid_
     tma_prefetch_desc(&map_f2);
     mbar_init(bar0, 1);
     mbar_init(bar0 + 8, 1);
+    mbar_init(bar0 + 16, kThreads);      // "buffer 0 / 1 has been read by every thread" (no block barrier per tile: the warps
+    mbar_init(bar0 + 24, kThreads);      //  drift up to one tile apart, only the issuing thread waits)
     fence_barrier_init();
   }
   __syncthreads();
@@ -161,7 +163,11 @@ __global__ void __launch_bounds__(kThreads, 1) warp_win_fwd_kernel(const __grid_
       const int cy1 = ta_next.y0 >= lim_y;
       ta_next.y0 -= cy1 * lim_y;
       ta_next.b += step_b + cy1;
-      if (tid == 0 && !(p.dbg & 2)) issue(ta_next, buf ^ 1);             // (buffer buf ^ 1 was released by the barrier that ended iteration it - 1)
+      if (tid == 0 && !(p.dbg & 2)) {
+        // buffer buf ^ 1 was last read by tile it - 1: its (it - 1) / 2-th use
+        if (it > 0) mbar_wait(bar0 + 16 + 8 * (buf ^ 1), (uint32_t)((it - 1) >> 1) & 1u);
+        issue(ta_next, buf ^ 1);
+      }
       load_own(ta_next, nxt);
     }
     if (!(p.dbg & 2)) mbar_wait(bar0 + 8 * buf, (uint32_t)(it >> 1) & 1u);
@@ -230,7 +236,7 @@ __global__ void __launch_bounds__(kThreads, 1) warp_win_fwd_kernel(const __grid_
         }
       }
     }
-    __syncthreads();      // every read of win[buf] is done: the next iteration may refill it
+    mbar_arrive(bar0 + 16 + 8 * buf);      // this thread's reads of win[buf] are done
   }
   if (MODE == 1) {
     fd_block_sum<3>(s, red);
