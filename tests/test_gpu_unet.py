@@ -106,7 +106,8 @@ def test_unet_fused_output_head_padded_shape():
     with torch.no_grad():
         ref = O.unet_forward(sd, F.pad(x, pad, mode="replicate"), F.pad(cond, pad, mode="replicate"), t)
         ref = ref[..., pad[2]:pad[2] + H, pad[0]:pad[0] + W]
-        assert net.FUSE_HEAD
+        if not (net.FUSE_HEAD and net.FUSE_GN_RESIDUAL):
+            pytest.skip("the fused tail is switched off by FD_FUSE_HEAD / FD_FUSE_GN_RES")
         fused = net(x.cuda(), cond.cuda(), t.cuda())
         net.FUSE_HEAD = False
         try:
