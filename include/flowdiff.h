@@ -52,6 +52,18 @@ FD_API int fd_backwarp_fwd(const float* image, const float* flow, float* out, fl
 FD_API int fd_backwarp_bwd(const float* image, const float* flow, const float* gout,
                     float* gimage, float* gflow, int B, int C, int H, int W, void* stream);
 
+/* Backward passes with a caller-provided workspace (fd_warp_bwd_workspace_floats(B, H, W) floats, 16-byte aligned): on
+ * three-channel frames with W % 4 == 0 the gradient of the sampled frame is accumulated pixel-interleaved in the workspace
+ * with ONE 128-bit reduction per bilinear tap (4 instead of 12 L2 reduction operations per pixel; the gathers read the frame
+ * from TMA-staged shared-memory windows) and converted to the planar gradient by a second launch.  Same arguments and
+ * results as fd_backwarp_bwd / fd_backwarp_photo_epe_bwd, which serve every other shape (and a NULL workspace). */
+FD_API size_t fd_warp_bwd_workspace_floats(int B, int H, int W);
+FD_API int fd_backwarp_bwd_ws(const float* image, const float* flow, const float* gout, float* gimage, float* gflow,
+                     float* workspace, int B, int C, int H, int W, void* stream);
+FD_API int fd_backwarp_photo_epe_bwd_ws(const float* frame1, const float* frame2, const float* flow, const float* flow_gt,
+                     const float* sums, float g_photo, float g_epe, float* gflow, float* gframe2, float* workspace,
+                     int B, int C, int H, int W, void* stream);
+
 /* Self-test of the warp kernels' division: the normalisation `2 v / (W - 1)` of warp.py:107-108 is computed with the
  * reciprocal half of `__fdiv_rn`'s own instruction sequence hoisted out of the pixel loop (fd_warp_common.cuh:bw_div_rn);
  * this runs ALL 2^32 numerator bit patterns for one divisor against `__fdiv_rn` and counts the differences (expected: 0). */

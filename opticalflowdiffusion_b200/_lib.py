@@ -28,6 +28,9 @@ SIGNATURES = {
     "fd_backwarp_bwd": (c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "fd_photo_epe_workspace_floats": (c_size_t, [_I, _I, _I]),
     "fd_warp_div_selftest": (c_int, [_F, _P, _P]),
+    "fd_warp_bwd_workspace_floats": (c_size_t, [_I, _I, _I]),
+    "fd_backwarp_bwd_ws": (c_int, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
+    "fd_backwarp_photo_epe_bwd_ws": (c_int, [_P, _P, _P, _P, _P, _F, _F, _P, _P, _P, _I, _I, _I, _I, _P]),
     "fd_backwarp_photo_epe_fwd": (c_int, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "fd_backwarp_photo_epe_bwd": (c_int, [_P, _P, _P, _P, _P, _F, _F, _P, _P, _I, _I, _I, _I, _P]),
     "fd_splat_fwd": (c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),

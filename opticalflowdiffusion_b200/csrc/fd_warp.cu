@@ -439,6 +439,10 @@ int fd_warp_fwd_win(int mode, const float* frame1, const float* frame2, const fl
 int fd_warp_bwd_win(int mode, const float* frame1, const float* frame2, const float* flow, const float* flow_gt, const float* gout,
                     const float* sums, float g_photo, float g_epe, float* gflow, float* gimage, int B, int H, int W, cudaStream_t st);
 
+int fd_warp_bwd_win2(int mode, const float* frame1, const float* frame2, const float* flow, const float* flow_gt, const float* gout,
+                     const float* fsums, float g_photo, float g_epe, float* gflow, float* gimage, float* acc, int B, int H, int W,
+                     cudaStream_t st);
+
 // FD_WARP_WIN=0 selects the one-thread-per-pixel-group gather kernels for every shape
 static bool use_win(int C, int W, const void* a, const void* b, const void* c, const void* d, const void* e2 = nullptr,
                     const void* f = nullptr) {
@@ -494,6 +498,34 @@ int fd_warp_div_selftest(float divisor, unsigned long long* mismatches, void* st
   div_selftest_kernel<<<FD_NUM_SMS * 8, 256, 0, st>>>(divisor, mismatches);
   FD_LAUNCH_CHECK();
   return FD_OK;
+}
+
+// Backward passes with a caller-provided workspace of fd_warp_bwd_workspace_floats(B, H, W) floats (16-byte aligned): on
+// three-channel frames with W % 4 == 0 the frame gradient is accumulated pixel-interleaved in it, one 128-bit reduction per
+// tap (4 instead of 12 L2 reduction operations per pixel), and converted to the planar gradient by a second launch; every
+// other shape runs the workspace-free entry points above.
+size_t fd_warp_bwd_workspace_floats(int B, int H, int W) { return (size_t)4 * B * H * W; }
+
+int fd_backwarp_bwd_ws(const float* image, const float* flow, const float* gout, float* gimage, float* gflow, float* workspace,
+                       int B, int C, int H, int W, void* stream) {
+  if (int e = check_dims(B, C, H, W)) return e;
+  FD_REQUIRE(image && flow && gout, "backwarp_bwd_ws: null pointer");
+  if (workspace != nullptr && use_win(C, W, image, flow, gout, gimage, gflow, workspace))
+    return fd_warp_bwd_win2(2, nullptr, image, flow, nullptr, gout, nullptr, 0.f, 0.f, gflow, gimage, workspace, B, H, W,
+                            (cudaStream_t)stream);
+  return fd_backwarp_bwd(image, flow, gout, gimage, gflow, B, C, H, W, stream);
+}
+
+int fd_backwarp_photo_epe_bwd_ws(const float* frame1, const float* frame2, const float* flow, const float* flow_gt,
+                                 const float* sums, float g_photo, float g_epe, float* gflow, float* gframe2, float* workspace,
+                                 int B, int C, int H, int W, void* stream) {
+  if (int e = check_dims(B, C, H, W)) return e;
+  FD_REQUIRE(frame1 && frame2 && flow && flow_gt && sums, "photo_epe_bwd_ws: null pointer");
+  if (workspace != nullptr && use_win(C, W, frame1, frame2, flow, flow_gt, gflow, gframe2) &&
+      (reinterpret_cast<uintptr_t>(workspace) & 15) == 0)
+    return fd_warp_bwd_win2(3, frame1, frame2, flow, flow_gt, nullptr, sums, g_photo, g_epe, gflow, gframe2, workspace, B, H, W,
+                            (cudaStream_t)stream);
+  return fd_backwarp_photo_epe_bwd(frame1, frame2, flow, flow_gt, sums, g_photo, g_epe, gflow, gframe2, B, C, H, W, stream);
 }
 
 size_t fd_photo_epe_workspace_floats(int B, int H, int W) {

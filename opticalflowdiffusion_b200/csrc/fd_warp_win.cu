@@ -49,6 +49,12 @@ struct WinParams {
   float* mask;             // MODE 0 (may be null)
   float* partials;         // MODE 1: [grid][3] floats, then one unsigned ticket counter (zeroed by the host before the launch)
   float* sums;             // MODE 1: {photo sum, mask sum, EPE sum, pixel count}, written by the last block to finish
+  // backward modes (2: plain warp given gout, 3: fused photometric + EPE objective given the forward sums)
+  const float* gout;       // MODE 2
+  const float* fsums;      // MODE 3: forward sums
+  float g_photo, g_epe;    // MODE 3
+  float* gflow;            // may be null (MODE 2)
+  float* acc;              // (B, H, W, 4) pixel-interleaved gradient of the sampled frame, zeroed by the host; may be null
   BwGeom g;
   int B, tiles_x, tiles_y, ntiles;
   int dbg;                 // FD_WARP_WIN_DBG: 1 = no compute, 2 = no TMA (timing isolation only: wrong results)
@@ -85,7 +91,7 @@ __device__ __forceinline__ float lds_f32(uint32_t addr) {      // explicit share
   return v;
 }
 
-// MODE 0: out / mask.  MODE 1: photometric + EPE partial sums.
+// MODE 0: out / mask.  MODE 1: photometric + EPE partial sums.  MODE 2 / 3: their backward passes (see WinParams).
 template <int MODE>
 __global__ void __launch_bounds__(kThreads, 1) warp_win_fwd_kernel(const __grid_constant__ CUtensorMap map_f2, const WinParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -126,14 +132,22 @@ __global__ void __launch_bounds__(kThreads, 1) warp_win_fwd_kernel(const __grid_
     const long fo = (long)a.b * 2 * HW + (long)y * W + x;
     o.f0 = __ldg(reinterpret_cast<const PxVec*>(p.flow + fo));
     o.f1 = __ldg(reinterpret_cast<const PxVec*>(p.flow + fo + HW));
-    if (MODE == 1) {
+    if (MODE == 1 || MODE == 3) {
       o.g0 = __ldg(reinterpret_cast<const PxVec*>(p.flow_gt + fo));
       o.g1 = __ldg(reinterpret_cast<const PxVec*>(p.flow_gt + fo + HW));
+    }
+    if (MODE != 0) {
+      const float* src = MODE == 2 ? p.gout : p.frame1;
       const long po = (long)a.b * kC * HW + (long)y * W + x;
 #pragma unroll
-      for (int c = 0; c < kC; ++c) o.a[c] = __ldg(reinterpret_cast<const PxVec*>(p.frame1 + po + c * HW));
+      for (int c = 0; c < kC; ++c) o.a[c] = __ldg(reinterpret_cast<const PxVec*>(src + po + c * HW));
     }
   };
+  float kp = 0.f, ke = 0.f;
+  if (MODE == 3) {
+    kp = p.g_photo / __ldg(p.fsums + 1);
+    ke = p.g_epe / __ldg(p.fsums + 3);
+  }
 
   float s[3] = {0.f, 0.f, 0.f};
   int tile = blockIdx.x;
@@ -178,6 +192,76 @@ __global__ void __launch_bounds__(kThreads, 1) warp_win_fwd_kernel(const __grid_
       float fdy[kPx], fdx[kPx];
       unpack(cur.f0, fdy);
       unpack(cur.f1, fdx);
+      if (MODE >= 2) {
+        // ---- backward: gradient of the flow (gather) and of the sampled frame (one 128-bit reduction per tap into the
+        // pixel-interleaved buffer: the three channels of a tap share their address) ----
+        float av[kC][kPx];
+#pragma unroll
+        for (int c = 0; c < kC; ++c) unpack(cur.a[c], av[c]);
+        float gxo[kPx], gyo[kPx];
+#pragma unroll
+        for (int j = 0; j < kPx; ++j) {
+          BwTaps t;
+          bw_taps(fdx[j], fdy[j], x + j, y, g, dv, t);
+          const float mj = MODE == 3 ? bw_mask_fast(t) : 1.f;
+          const int wy = t.y0 - wy0, wx = t.x0 - wx0;
+          const bool inwin = wy >= 0 && wy + 1 < kWH && wx >= 0 && wx + 1 < kWW && (t.okx0 || t.okx1) && (t.oky0 || t.oky1);
+          const uint32_t q = w0 + (uint32_t)(wy * kWW + wx) * 4u;
+          float gw[kC], dix = 0.f, diy = 0.f;
+#pragma unroll
+          for (int c = 0; c < kC; ++c) {
+            BwVals v;
+            if (inwin) {
+              v.nw = lds_f32(q + (c * kWin) * 4);
+              v.ne = lds_f32(q + (c * kWin + 1) * 4);
+              v.sw = lds_f32(q + (c * kWin + kWW) * 4);
+              v.se = lds_f32(q + (c * kWin + kWW + 1) * 4);
+            } else {
+              v = bw_gather(p.frame2 + ((long)a.b * kC + c) * HW, t, W);
+            }
+            if (MODE == 3) {
+              const float d = av[c][j] - bw_sample(v, t);
+              gw[c] = -kp * mj * d * rsqrt_approx(d * d + 1e-6f);      // dL/dwarped; one MUFU (2 ulp) for 1 / sqrt
+            } else {
+              gw[c] = av[c][j];
+            }
+            dix += gw[c] * ((v.ne - v.nw) * t.sy + (v.se - v.sw) * t.ny);
+            diy += gw[c] * ((v.sw - v.nw) * t.ex + (v.se - v.ne) * t.wx);
+          }
+          gxo[j] = bw_div_rn(dix * g.half_w, dv.w) * 2.f;
+          gyo[j] = bw_div_rn(diy * g.half_h, dv.h) * 2.f;
+          if (p.acc != nullptr && (MODE == 2 || gw[0] != 0.f || gw[1] != 0.f || gw[2] != 0.f)) {
+            float* cell = p.acc + (((long)a.b * H + t.y0) * W + t.x0) * 4;
+            auto red4 = [&](float* dst, float wt) {
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(gw[0] * wt), "f"(gw[1] * wt),
+                           "f"(gw[2] * wt), "f"(0.f)
+                           : "memory");
+            };
+            if (t.okx0 && t.oky0) red4(cell, t.nw);
+            if (t.okx1 && t.oky0) red4(cell + 4, t.ne);
+            if (t.okx0 && t.oky1) red4(cell + (long)W * 4, t.sw);
+            if (t.okx1 && t.oky1) red4(cell + (long)W * 4 + 4, t.se);
+          }
+        }
+        if (p.gflow != nullptr) {
+          if (MODE == 3) {
+            float gdy[kPx], gdx[kPx];
+            unpack(cur.g0, gdy);
+            unpack(cur.g1, gdx);
+#pragma unroll
+            for (int j = 0; j < kPx; ++j) {
+              const float du = fdy[j] - gdy[j], dvv = fdx[j] - gdx[j];
+              const float n2 = du * du + dvv * dvv;
+              const float inv = n2 > 0.f ? ke * rsqrt_approx(n2) : 0.f;
+              gyo[j] += du * inv;
+              gxo[j] += dvv * inv;
+            }
+          }
+          const long fo = (long)a.b * 2 * HW + (long)y * W + x;
+          *reinterpret_cast<PxVec*>(p.gflow + fo) = pack(gyo);
+          *reinterpret_cast<PxVec*>(p.gflow + fo + HW) = pack(gxo);
+        }
+      } else {
       float o[kC][kPx], m[kPx];
 #pragma unroll
       for (int j = 0; j < kPx; ++j) {
@@ -235,6 +319,7 @@ __global__ void __launch_bounds__(kThreads, 1) warp_win_fwd_kernel(const __grid_
           }
         }
       }
+      }   // forward modes
     }
     mbar_arrive(bar0 + 16 + 8 * buf);      // this thread's reads of win[buf] are done
   }
@@ -275,11 +360,74 @@ __global__ void __launch_bounds__(kThreads, 1) warp_win_fwd_kernel(const __grid_
   }
 }
 
+// pixel-interleaved gradient (B, H, W, 4) -> planar (B, 3, H, W)
+__global__ void __launch_bounds__(256) acc_to_planes3_kernel(const float* __restrict__ acc, float* __restrict__ g, int B, long HW) {
+  const long total = (long)B * HW;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const long b = i / HW, p = i - b * HW;
+    const float4 a = __ldg(reinterpret_cast<const float4*>(acc) + i);
+    g[(b * 3 + 0) * HW + p] = a.x;
+    g[(b * 3 + 1) * HW + p] = a.y;
+    g[(b * 3 + 2) * HW + p] = a.z;
+  }
+}
+
 }  // namespace
 
 int fd_warp_win_grid(int B, int H, int W) {
   const long tiles = (long)B * ((H + kTH - 1) / kTH) * ((W + kTW - 1) / kTW);
   return (int)(tiles < FD_NUM_SMS ? tiles : FD_NUM_SMS);
+}
+
+// Backward passes on the forward kernel's skeleton (same TMA windows for the gathers): mode 2 = plain warp given gout, mode 3 =
+// fused photometric + EPE objective.  The gradient of the sampled frame is accumulated in `acc` (B, H, W, 4 floats, 16-byte
+// aligned workspace) with one 128-bit reduction per tap and converted to the planar `gimage` by a second launch.
+int fd_warp_bwd_win2(int mode, const float* frame1, const float* frame2, const float* flow, const float* flow_gt, const float* gout,
+                     const float* fsums, float g_photo, float g_epe, float* gflow, float* gimage, float* acc, int B, int H, int W,
+                     cudaStream_t st) {
+  FD_REQUIRE(W % 4 == 0 && (mode == 2 || mode == 3), "warp_win_bwd2: bad argument");
+  FD_REQUIRE(gimage == nullptr || (acc != nullptr && (reinterpret_cast<uintptr_t>(acc) & 15) == 0), "warp_win_bwd2: workspace");
+  WinParams p{};
+  p.frame1 = frame1; p.frame2 = frame2; p.flow = flow; p.flow_gt = flow_gt; p.gout = gout; p.fsums = fsums;
+  p.g_photo = g_photo; p.g_epe = g_epe; p.gflow = gflow; p.acc = gimage != nullptr ? acc : nullptr;
+  p.g = make_geom(H, W);
+  p.B = B;
+  p.tiles_x = (W + kTW - 1) / kTW;
+  p.tiles_y = (H + kTH - 1) / kTH;
+  const long tiles = (long)B * p.tiles_x * p.tiles_y;
+  FD_REQUIRE(tiles < (1L << 31), "warp_win_bwd2: too many tiles");
+  p.ntiles = (int)tiles;
+  CUtensorMap map;
+  {
+    const uint64_t dims[3] = {(uint64_t)W, (uint64_t)H, (uint64_t)B * kC};
+    const uint64_t str[2] = {(uint64_t)W * 4, (uint64_t)H * W * 4};
+    const uint32_t box[3] = {(uint32_t)kWW, (uint32_t)kWH, (uint32_t)kC};
+    if (int e = make_tmap_f32_plain(&map, frame2, 3, dims, str, box)) return e;
+  }
+  if (p.acc != nullptr) FD_CUDA(cudaMemsetAsync(acc, 0, sizeof(float) * 4 * (size_t)B * H * W, st));
+  const int grid = fd_warp_win_grid(B, H, W);
+  static bool attr_done[2] = {false, false};
+  if (mode == 2) {
+    if (!attr_done[0]) {
+      FD_CUDA(cudaFuncSetAttribute(warp_win_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+      attr_done[0] = true;
+    }
+    warp_win_fwd_kernel<2><<<grid, kThreads, kSmemBytes, st>>>(map, p);
+  } else {
+    if (!attr_done[1]) {
+      FD_CUDA(cudaFuncSetAttribute(warp_win_fwd_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+      attr_done[1] = true;
+    }
+    warp_win_fwd_kernel<3><<<grid, kThreads, kSmemBytes, st>>>(map, p);
+  }
+  FD_LAUNCH_CHECK();
+  if (gimage != nullptr) {
+    long blocks = ((long)B * H * W + 255) / 256;
+    if (blocks > (long)FD_NUM_SMS * 16) blocks = (long)FD_NUM_SMS * 16;
+    acc_to_planes3_kernel<<<(unsigned)blocks, 256, 0, st>>>(acc, gimage, B, (long)H * W);
+    FD_LAUNCH_CHECK();
+  }
+  return FD_OK;
 }
 
 // mode 0: out / mask; mode 1: sums[4] = {photo sum, mask sum, EPE sum, pixel count}, partials = workspace of

@@ -31,6 +31,15 @@ def _f32c(t: Tensor) -> Tensor:
 # --------------------------------------------------------------------------------------
 
 
+def _bwd_workspace(lib, image: Tensor, need_image_grad: bool) -> Optional[Tensor]:
+    """Workspace of the warp backward kernels (pixel-interleaved frame gradient, fd_warp_bwd_workspace_floats): only the
+    three-channel W % 4 == 0 path uses it."""
+    B, C, H, W = image.shape
+    if not need_image_grad or C != 3 or W % 4 != 0:
+        return None
+    return torch.empty(lib.fd_warp_bwd_workspace_floats(B, H, W), device=image.device, dtype=torch.float32)
+
+
 class _BackwarpFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, image: Tensor, flow: Tensor):
@@ -54,8 +63,9 @@ class _BackwarpFn(torch.autograd.Function):
         gimage = torch.empty_like(image) if ctx.needs_input_grad[0] else None
         gflow = torch.empty_like(flow) if ctx.needs_input_grad[1] else None
         lib = _lib.load()
-        _lib.check(lib.fd_backwarp_bwd(_lib.ptr(image), _lib.ptr(flow), _lib.ptr(gout), _lib.ptr(gimage),
-                                       _lib.ptr(gflow), B, C, H, W, _lib.stream()))
+        ws = _bwd_workspace(lib, image, gimage is not None)
+        _lib.check(lib.fd_backwarp_bwd_ws(_lib.ptr(image), _lib.ptr(flow), _lib.ptr(gout), _lib.ptr(gimage),
+                                          _lib.ptr(gflow), _lib.ptr(ws), B, C, H, W, _lib.stream()))
         return gimage, gflow
 
 
@@ -93,9 +103,10 @@ class _PhotoEpeFn(torch.autograd.Function):
         sg = sums.clone()
         sg[1] = sums[1] / g_photo.detach().float()
         sg[3] = sums[3] / g_epe.detach().float()
-        _lib.check(lib.fd_backwarp_photo_epe_bwd(_lib.ptr(frame1), _lib.ptr(frame2), _lib.ptr(flow),
-                                                 _lib.ptr(flow_gt), _lib.ptr(sg), 1.0, 1.0,
-                                                 _lib.ptr(gflow), _lib.ptr(gframe2), B, C, H, W, _lib.stream()))
+        ws = _bwd_workspace(lib, frame2, gframe2 is not None)
+        _lib.check(lib.fd_backwarp_photo_epe_bwd_ws(_lib.ptr(frame1), _lib.ptr(frame2), _lib.ptr(flow),
+                                                    _lib.ptr(flow_gt), _lib.ptr(sg), 1.0, 1.0,
+                                                    _lib.ptr(gflow), _lib.ptr(gframe2), _lib.ptr(ws), B, C, H, W, _lib.stream()))
         return None, gframe2, gflow, None
 
 

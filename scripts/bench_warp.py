@@ -66,12 +66,18 @@ def measure(iters=50, warmup=10):
 
     t = timeit(lambda: _lib.check(lib.fd_backwarp_photo_epe_fwd(P(f1), P(f2), P(flow), P(gt), P(sums), P(ws), B, C, H, W, st)), flush=flush, iters=iters, warmup=warmup)
     rec("photo_epe_fwd", t, 40 * px)
-    t = timeit(lambda: _lib.check(lib.fd_backwarp_photo_epe_bwd(P(f1), P(f2), P(flow), P(gt), P(sums), 1.0, 1.0, P(gflow), P(gf2), B, C, H, W, st)), flush=flush, iters=iters, warmup=warmup)
+    wsb = torch.empty(lib.fd_warp_bwd_workspace_floats(B, H, W), device="cuda")
+    t = timeit(lambda: _lib.check(lib.fd_backwarp_photo_epe_bwd_ws(P(f1), P(f2), P(flow), P(gt), P(sums), 1.0, 1.0, P(gflow), P(gf2), P(wsb), B, C, H, W, st)), flush=flush, iters=iters, warmup=warmup)
     rec("photo_epe_bwd", t, 60 * px)
     t = timeit(lambda: _lib.check(lib.fd_backwarp_fwd(P(f2), P(flow), P(out), P(mask), B, C, H, W, st)), flush=flush, iters=iters, warmup=warmup)
     rec("backwarp_fwd", t, (8 + 12 + 12 + 12) * px)
-    t = timeit(lambda: _lib.check(lib.fd_backwarp_bwd(P(f2), P(flow), P(out), P(gf2), P(gflow), B, C, H, W, st)), flush=flush, iters=iters, warmup=warmup)
+    t = timeit(lambda: _lib.check(lib.fd_backwarp_bwd_ws(P(f2), P(flow), P(out), P(gf2), P(gflow), P(wsb), B, C, H, W, st)), flush=flush, iters=iters, warmup=warmup)
     rec("backwarp_bwd", t, (8 + 12 + 12 + 12 + 8) * px)
+    # the workspace-free entry points (frame gradient accumulated in shared-memory windows, TMA reduce-add)
+    t = timeit(lambda: _lib.check(lib.fd_backwarp_photo_epe_bwd(P(f1), P(f2), P(flow), P(gt), P(sums), 1.0, 1.0, P(gflow), P(gf2), B, C, H, W, st)), flush=flush, iters=iters, warmup=warmup)
+    rec("photo_epe_bwd_no_workspace", t, 60 * px)
+    t = timeit(lambda: _lib.check(lib.fd_backwarp_bwd(P(f2), P(flow), P(out), P(gf2), P(gflow), B, C, H, W, st)), flush=flush, iters=iters, warmup=warmup)
+    rec("backwarp_bwd_no_workspace", t, (8 + 12 + 12 + 12 + 8) * px)
     so = torch.empty_like(f2)
     t = timeit(lambda: _lib.check(lib.fd_splat_fwd(P(f2), P(flow), P(so), B, C, H, W, 1, 0, 0, st)), flush=flush, iters=iters, warmup=warmup)
     rec("splat_fwd", t, (8 + 12 + 12) * px)
