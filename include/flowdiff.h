@@ -98,6 +98,12 @@ FD_API int fd_splat_flowgrad(const float* in, const float* flow, const float* go
 FD_API int fd_splat_prepare(const float* first, float* ten_in, int B, int C, int HW, void* stream);
 /* warp_forward_flow post-processing (warp.py:139-156): img[b,c] = splat[b,C]>0 ? splat[b,c] : NaN; splat is (B,C+1,HW) */
 FD_API int fd_splat_finish(const float* splat, float* img, int B, int C, int HW, int set_nans, void* stream);
+/* fd_splat_fwd with a caller-provided workspace (fd_splat_fwd_workspace_floats floats, 16-byte aligned): for C = 3 or 4 the
+ * splat is accumulated pixel-interleaved with one 128-bit reduction per tap and copied out to the planar `out`; every other
+ * channel count (or a NULL workspace) runs fd_splat_fwd.  Same results up to the order of the atomics. */
+FD_API size_t fd_splat_fwd_workspace_floats(int B, int H, int W, int scale);
+FD_API int fd_splat_fwd_ws(const float* in, const float* flow, float* out, float* workspace, int B, int C, int H, int W,
+                     int scale, int off_x, int off_y, void* stream);
 /* warp_forward_flow(warp_style='sum') for THREE-channel images in two launches (warp.py:121-156; prepare + splat + finish
  * fused): `acc` is a caller-provided workspace of 4*B*(H/scale)*(W/scale) floats, 16-byte aligned, in which the splat is
  * accumulated pixel-interleaved (r, g, b, weight) so that a tap is one 128-bit vector reduction; img (B,3,H/s,W/s) receives

@@ -38,6 +38,8 @@ SIGNATURES = {
     "fd_splat_flowgrad": (c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
     "fd_splat_prepare": (c_int, [_P, _P, _I, _I, _I, _P]),
     "fd_splat_finish": (c_int, [_P, _P, _I, _I, _I, _I, _P]),
+    "fd_splat_fwd_workspace_floats": (c_size_t, [_I, _I, _I, _I]),
+    "fd_splat_fwd_ws": (c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
     "fd_forward_warp_sum3": (c_int, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
     "fd_nan_mse_workspace_floats": (c_size_t, [_I, _I, _I]),
     "fd_nan_mse_fwd": (c_int, [_P, _P, _P, _P, _I, _I, _I, _L, _L, _P]),

@@ -484,6 +484,51 @@ __global__ void __launch_bounds__(256) splat_finish3_kernel(const float* __restr
   }
 }
 
+// fd_splat_fwd for 3 or 4 input channels through the same pixel-interleaved accumulation (one 128-bit reduction per tap; a
+// fourth channel of zeros for C = 3), then a planar copy-out: fd_splat_fwd_ws.
+template <int C>
+__global__ void __launch_bounds__(256) splat_fwd_il_kernel(const float* __restrict__ in, const float* __restrict__ flow,
+                                                           float* __restrict__ acc, int B, int H, int W, int Ho, int Wo, int scale,
+                                                           int off_x, int off_y, unsigned segs, unsigned jobs) {
+  const long HW = (long)H * W;
+  for (unsigned job = blockIdx.x; job < jobs; job += gridDim.x) {
+    const unsigned row = job / segs, seg = job - row * segs;
+    const unsigned b = row / (unsigned)H;
+    const int y = (int)(row - b * (unsigned)H), x = (int)(seg * blockDim.x + threadIdx.x);
+    if (x >= W) continue;
+    const int pix = y * W + x;
+    const float fx = __ldg(flow + ((long)b * 2 + 0) * HW + pix), fy = __ldg(flow + ((long)b * 2 + 1) * HW + pix);
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int c = 0; c < C; ++c) v[c] = __ldg(in + ((long)b * C + c) * HW + pix);
+    SplatTaps t;
+    splat_taps<KIND_OUT>(fx, fy, x, y, H, W, Ho, Wo, scale, off_x, off_y, t);
+    float* cell = acc + (((long)b * Ho + t.y0) * Wo + t.x0) * 4;
+    auto red4 = [&](float* dst, float wt) {
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(__fmul_rn(v[0], wt)), "f"(__fmul_rn(v[1], wt)),
+                   "f"(__fmul_rn(v[2], wt)), "f"(C == 4 ? __fmul_rn(v[3], wt) : 0.f)
+                   : "memory");
+    };
+    if (t.okx0 && t.oky0) red4(cell, t.nw);
+    if (t.okx1 && t.oky0) red4(cell + 4, t.ne);
+    if (t.okx0 && t.oky1) red4(cell + (long)Wo * 4, t.sw);
+    if (t.okx1 && t.oky1) red4(cell + (long)Wo * 4 + 4, t.se);
+  }
+}
+
+template <int C>
+__global__ void __launch_bounds__(256) il_to_planes_kernel(const float* __restrict__ acc, float* __restrict__ out, int B, long HWo) {
+  const long total = (long)B * HWo;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const long b = i / HWo, p = i - b * HWo;
+    const float4 a = __ldg(reinterpret_cast<const float4*>(acc) + i);
+    out[(b * C + 0) * HWo + p] = a.x;
+    out[(b * C + 1) * HWo + p] = a.y;
+    out[(b * C + 2) * HWo + p] = a.z;
+    if (C == 4) out[(b * C + 3) * HWo + p] = a.w;
+  }
+}
+
 int sgrid(long items) {
   long blocks = (items + 255) / 256;
   const long cap = (long)FD_NUM_SMS * 16;
@@ -517,6 +562,35 @@ int fd_splat_fwd(const float* in, const float* flow, float* out, int B, int C, i
   } else {
     const long items = (long)B * H * W;
     splat_fwd_kernel<1><<<sgrid(items), 256, 0, st>>>(in, flow, out, B, C, H, W, Ho, Wo, scale, off_x, off_y, items);
+  }
+  FD_LAUNCH_CHECK();
+  return FD_OK;
+}
+
+size_t fd_splat_fwd_workspace_floats(int B, int H, int W, int scale) { return (size_t)4 * B * (H / scale) * (W / scale); }
+
+int fd_splat_fwd_ws(const float* in, const float* flow, float* out, float* workspace, int B, int C, int H, int W, int scale,
+                    int off_x, int off_y, void* stream) {
+  if (workspace == nullptr || (C != 3 && C != 4) || (reinterpret_cast<uintptr_t>(workspace) & 15) != 0)
+    return fd_splat_fwd(in, flow, out, B, C, H, W, scale, off_x, off_y, stream);
+  if (int e = check(B, C, H, W, scale, off_x, off_y)) return e;
+  FD_REQUIRE(in && flow && out, "splat_fwd_ws: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int Ho = H / scale, Wo = W / scale;
+  FD_CUDA(cudaMemsetAsync(workspace, 0, sizeof(float) * 4 * (size_t)B * Ho * Wo, st));
+  const unsigned segs = (unsigned)((W + 255) / 256);
+  const long jobs = (long)B * H * segs;
+  FD_REQUIRE(jobs < (1L << 31), "splat_fwd_ws: too many row segments");
+  long grid = jobs;
+  if (grid > (long)FD_NUM_SMS * 16) grid = (long)FD_NUM_SMS * 16;
+  if (C == 3) {
+    splat_fwd_il_kernel<3><<<(unsigned)grid, 256, 0, st>>>(in, flow, workspace, B, H, W, Ho, Wo, scale, off_x, off_y, segs, (unsigned)jobs);
+    FD_LAUNCH_CHECK();
+    il_to_planes_kernel<3><<<sgrid((long)B * Ho * Wo), 256, 0, st>>>(workspace, out, B, (long)Ho * Wo);
+  } else {
+    splat_fwd_il_kernel<4><<<(unsigned)grid, 256, 0, st>>>(in, flow, workspace, B, H, W, Ho, Wo, scale, off_x, off_y, segs, (unsigned)jobs);
+    FD_LAUNCH_CHECK();
+    il_to_planes_kernel<4><<<sgrid((long)B * Ho * Wo), 256, 0, st>>>(workspace, out, B, (long)Ho * Wo);
   }
   FD_LAUNCH_CHECK();
   return FD_OK;

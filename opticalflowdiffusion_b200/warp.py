@@ -131,8 +131,11 @@ class softsplat_func(torch.autograd.Function):
         B, C, H, W = tenIn.shape
         out = torch.empty(B, C, H // scale, W // scale, device=tenIn.device, dtype=torch.float32)
         lib = _lib.load()
-        _lib.check(lib.fd_splat_fwd(_lib.ptr(tenIn), _lib.ptr(tenFlow), _lib.ptr(out), B, C, H, W,
-                                    int(scale), int(offset_x), int(offset_y), _lib.stream()))
+        ws = None
+        if C in (3, 4):      # pixel-interleaved accumulation: one vector reduction per tap instead of C scalar ones
+            ws = torch.empty(lib.fd_splat_fwd_workspace_floats(B, H, W, int(scale)), device=tenIn.device, dtype=torch.float32)
+        _lib.check(lib.fd_splat_fwd_ws(_lib.ptr(tenIn), _lib.ptr(tenFlow), _lib.ptr(out), _lib.ptr(ws), B, C, H, W,
+                                       int(scale), int(offset_x), int(offset_y), _lib.stream()))
         ctx.save_for_backward(tenIn, tenFlow)
         ctx.geom = (int(scale), int(offset_x), int(offset_y))
         return out

@@ -79,8 +79,11 @@ def measure(iters=50, warmup=10):
     t = timeit(lambda: _lib.check(lib.fd_backwarp_bwd(P(f2), P(flow), P(out), P(gf2), P(gflow), B, C, H, W, st)), flush=flush, iters=iters, warmup=warmup)
     rec("backwarp_bwd_no_workspace", t, (8 + 12 + 12 + 12 + 8) * px)
     so = torch.empty_like(f2)
-    t = timeit(lambda: _lib.check(lib.fd_splat_fwd(P(f2), P(flow), P(so), B, C, H, W, 1, 0, 0, st)), flush=flush, iters=iters, warmup=warmup)
+    wss = torch.empty(lib.fd_splat_fwd_workspace_floats(B, H, W, 1), device="cuda")
+    t = timeit(lambda: _lib.check(lib.fd_splat_fwd_ws(P(f2), P(flow), P(so), P(wss), B, C, H, W, 1, 0, 0, st)), flush=flush, iters=iters, warmup=warmup)
     rec("splat_fwd", t, (8 + 12 + 12) * px)
+    t = timeit(lambda: _lib.check(lib.fd_splat_fwd(P(f2), P(flow), P(so), B, C, H, W, 1, 0, 0, st)), flush=flush, iters=iters, warmup=warmup)
+    rec("splat_fwd_no_workspace", t, (8 + 12 + 12) * px)
     t = timeit(lambda: _lib.check(lib.fd_splat_flowgrad(P(f2), P(flow), P(out), P(gflow), B, C, H, W, 1, 0, 0, st)), flush=flush, iters=iters, warmup=warmup)
     rec("splat_flowgrad", t, (8 + 12 + 12 + 8) * px)
     # warp_forward_flow on a three-channel image (what UnetWithWarp / the pyramid loss call): generic three launches vs the

@@ -240,3 +240,48 @@ def test_hoisted_reciprocal_division_is_exact(divisor):
     _lib.check(lib.fd_warp_div_selftest(divisor, _lib.ptr(bad), _lib.stream()))
     torch.cuda.synchronize()
     assert int(bad.item()) == 0, int(bad.item())
+
+
+@pytest.mark.parametrize("C", [3, 4])
+@pytest.mark.parametrize("geom", [(1, 0, 0), (2, 1, 0), (4, 1, 3)])
+def test_splat_forward_interleaved_accumulation(C, geom):
+    """fd_splat_fwd_ws (pixel-interleaved accumulation, one 128-bit reduction per tap, planar copy-out) == fd_splat_fwd
+    (softsplat_new.py:352-423, golden-pinned by the tests above) up to the order of the atomics, NaN / Inf / far flows
+    included; and fd_forward_warp_sum3 == prepare + splat + finish."""
+    from opticalflowdiffusion_b200 import _lib
+    lib = _lib.load()
+    scale, ox, oy = geom
+    B, H, W = 2, 24, 40
+    g = torch.Generator().manual_seed(C * 10 + scale)
+    x = torch.randn(B, C, H, W, generator=g).cuda()
+    flow = (torch.randn(B, 2, H, W, generator=g) * 3).cuda()
+    flow[0, 0, 3, 4] = float("nan")
+    flow[1, 1, 5, 6] = float("inf")
+    flow[0, :, 0, 0] = -50.0
+    Ho, Wo = H // scale, W // scale
+    P, st = _lib.ptr, _lib.stream()
+    ref = torch.empty(B, C, Ho, Wo, device="cuda")
+    got = torch.full_like(ref, float("nan"))
+    ws = torch.empty(lib.fd_splat_fwd_workspace_floats(B, H, W, scale), device="cuda")
+    _lib.check(lib.fd_splat_fwd(P(x), P(flow), P(ref), B, C, H, W, scale, ox, oy, st))
+    _lib.check(lib.fd_splat_fwd_ws(P(x), P(flow), P(got), P(ws), B, C, H, W, scale, ox, oy, st))
+    torch.cuda.synchronize()
+    assert torch.isfinite(got).all()
+    assert (got - ref).abs().max().item() <= 1e-5 * max(1.0, ref.abs().max().item())
+    if C == 3:
+        first = x.clone()
+        first[0, 1, 7, 8] = float("nan")                      # NaN source pixel: weight 0
+        ten_in = torch.empty(B, 4, H, W, device="cuda")
+        ret = torch.empty(B, 4, Ho, Wo, device="cuda")
+        img_ref = torch.empty(B, 3, Ho, Wo, device="cuda")
+        _lib.check(lib.fd_splat_prepare(P(first), P(ten_in), B, 3, H * W, st))
+        _lib.check(lib.fd_splat_fwd(P(ten_in), P(flow), P(ret), B, 4, H, W, scale, ox, oy, st))
+        _lib.check(lib.fd_splat_finish(P(ret), P(img_ref), B, 3, Ho * Wo, 1, st))
+        ten2, acc = torch.empty_like(ten_in), torch.empty(B, Ho, Wo, 4, device="cuda")
+        img, wsum = torch.empty_like(img_ref), torch.empty(B, 1, Ho, Wo, device="cuda")
+        _lib.check(lib.fd_forward_warp_sum3(P(first), P(flow), P(ten2), P(acc), P(img), P(wsum), B, H, W, scale, ox, oy, 1, st))
+        torch.cuda.synchronize()
+        assert torch.equal(ten2, ten_in)
+        assert torch.equal(torch.isnan(img), torch.isnan(img_ref))
+        assert (img.nan_to_num() - img_ref.nan_to_num()).abs().max().item() <= 1e-5 * max(1.0, ref.abs().max().item())
+        assert (wsum[:, 0] - ret[:, 3]).abs().max().item() <= 1e-5
