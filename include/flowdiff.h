@@ -420,8 +420,10 @@ FD_API int fd_soft_charb_fwd(const float* S, const float* T, float* sums, float*
 FD_API int fd_soft_charb_bwd(const float* S, const float* T, const float* sums, const float* upstream, float* gS,
                       int B, int C, int HW, void* stream);
 /* All scale^2 offsets of one pyramid level at once (the loop of flow_learner.py:184-196): offset index k = a*scale + b
- * <-> offset = [a, b]; stacked tensors (K, B, C, H/scale, W/scale).  splat_*_multi: the per-offset arithmetic of
- * fd_splat_fwd / _ingrad / _flowgrad, the two gradient kernels summing over k (C must be 4 for them).
+ * <-> offset = [a, b].  The stacked splats and their gradients are PIXEL-INTERLEAVED, (K, B, H/scale, W/scale, 4) with the four
+ * channels (r, g, b, weight) of a cell adjacent (16-byte aligned), so that a bilinear tap is one 128-bit reduction / load: the
+ * splat input has C = 4 channels, soft_charb_multi takes C = 3 (+ the weight).  splat_*_multi: the per-offset arithmetic of
+ * fd_splat_fwd / _ingrad / _flowgrad, the two gradient kernels summing over k.
  * soft_charb_multi: sums [K][3], out[0] = mean_k mean_k; bwd: gS = d(upstream[0] * out[0])/dS. */
 FD_API int fd_splat_fwd_multi(const float* in, const float* flow, float* out, int B, int C, int H, int W, int scale, void* stream);
 FD_API int fd_splat_ingrad_multi(const float* flow, const float* gout, float* gin, int B, int C, int H, int W, int scale,

@@ -77,20 +77,21 @@ __global__ void __launch_bounds__(256) sum2_finalize_kernel(const float* __restr
 __global__ void __launch_bounds__(kThreads) soft_charb_multi_fwd_kernel(const float* __restrict__ S, const float* __restrict__ T,
                                                                        float* __restrict__ partials, int B, int C, long HW) {
   __shared__ float red[64];
+  // S, T: the stacked splats in the pixel-interleaved layout of fd_splat_fwd_multi, (K, B, HW, 4) = (r, g, b, weight)
   const int k = blockIdx.y;
-  const float* Sk = S + (long)k * B * (C + 1) * HW;
-  const float* Tk = T + (long)k * B * (C + 1) * HW;
+  const float4* Sk = reinterpret_cast<const float4*>(S) + (long)k * B * HW;
+  const float4* Tk = reinterpret_cast<const float4*>(T) + (long)k * B * HW;
   float acc[2] = {0.f, 0.f};
   const long total = (long)B * HW;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-    const long b = i / HW, p = i - b * HW;
-    const float* s = Sk + b * (C + 1) * HW + p;
-    const float* t = Tk + b * (C + 1) * HW + p;
-    const float sw = s[(long)C * HW], tw = t[(long)C * HW];
+    const float4 s4 = __ldg(Sk + i), t4 = __ldg(Tk + i);
+    const float sv[3] = {s4.x, s4.y, s4.z}, tv[3] = {t4.x, t4.y, t4.z};
+    const float sw = s4.w, tw = t4.w;
     if (!(sw > 0.f)) continue;
     const float sn = sw + kNormEps, tn = tw + kNormEps;
-    for (int c = 0; c < C; ++c) {
-      const float d = t[(long)c * HW] / tn - s[(long)c * HW] / sn;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float d = tv[c] / tn - sv[c] / sn;
       if (d != d) continue;
       acc[0] += sqrtf(d * d + kCharbEps2);
       acc[1] += 1.f;
@@ -134,33 +135,30 @@ __global__ void __launch_bounds__(kThreads) soft_charb_multi_bwd_kernel(const fl
                                                                        int B, int C, long HW, int K) {
   const int k = blockIdx.y;
   const float g = upstream[0] / ((float)K * sums[k * 3 + 1]);
-  const float* Sk = S + (long)k * B * (C + 1) * HW;
-  const float* Tk = T + (long)k * B * (C + 1) * HW;
-  float* gk = gS + (long)k * B * (C + 1) * HW;
+  const float4* Sk = reinterpret_cast<const float4*>(S) + (long)k * B * HW;      // interleaved (K, B, HW, 4), like gS
+  const float4* Tk = reinterpret_cast<const float4*>(T) + (long)k * B * HW;
+  float4* gk = reinterpret_cast<float4*>(gS) + (long)k * B * HW;
   const long total = (long)B * HW;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-    const long b = i / HW, p = i - b * HW;
-    const float* s = Sk + b * (C + 1) * HW + p;
-    const float* t = Tk + b * (C + 1) * HW + p;
-    float* gs = gk + b * (C + 1) * HW + p;
-    const float sw = s[(long)C * HW], tw = t[(long)C * HW];
-    float gw = 0.f;
+    const float4 s4 = __ldg(Sk + i), t4 = __ldg(Tk + i);
+    const float svv[3] = {s4.x, s4.y, s4.z}, tvv[3] = {t4.x, t4.y, t4.z};
+    const float sw = s4.w, tw = t4.w;
+    float gw = 0.f, gc[3] = {0.f, 0.f, 0.f};
     const bool live = sw > 0.f;
     const float sn = sw + kNormEps, tn = tw + kNormEps;
-    for (int c = 0; c < C; ++c) {
-      float gc = 0.f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
       if (live) {
-        const float sv = s[(long)c * HW];
-        const float d = t[(long)c * HW] / tn - sv / sn;
+        const float sv = svv[c];
+        const float d = tvv[c] / tn - sv / sn;
         if (d == d) {
           const float dw = -g * d * rsqrtf(d * d + kCharbEps2);
-          gc = dw / sn;
+          gc[c] = dw / sn;
           gw -= dw * sv / (sn * sn);
         }
       }
-      gs[(long)c * HW] = gc;
     }
-    gs[(long)C * HW] = gw;
+    gk[i] = make_float4(gc[0], gc[1], gc[2], gw);
   }
 }
 
@@ -330,6 +328,7 @@ size_t fd_soft_charb_multi_workspace_floats(int B, int HW, int K) { return (size
 int fd_soft_charb_multi_fwd(const float* S, const float* T, float* sums, float* out, float* partials, int B, int C, int HW, int K,
                             void* stream) {
   FD_REQUIRE(S && T && sums && out && partials && B > 0 && C > 0 && HW > 0 && K > 0 && K <= 65535, "soft_charb_multi_fwd: bad argument");
+  FD_REQUIRE(C == 3, "soft_charb_multi_fwd: the stacked splats are pixel-interleaved (r, g, b, weight): C must be 3, got %d", C);
   const int grid = multi_grid((long)B * HW, K);
   soft_charb_multi_fwd_kernel<<<dim3(grid, K), kThreads, 0, (cudaStream_t)stream>>>(S, T, partials, B, C, (long)HW);
   FD_LAUNCH_CHECK();
@@ -341,6 +340,7 @@ int fd_soft_charb_multi_fwd(const float* S, const float* T, float* sums, float* 
 int fd_soft_charb_multi_bwd(const float* S, const float* T, const float* sums, const float* upstream, float* gS, int B, int C,
                             int HW, int K, void* stream) {
   FD_REQUIRE(S && T && sums && upstream && gS && B > 0 && C > 0 && HW > 0 && K > 0 && K <= 65535, "soft_charb_multi_bwd: bad argument");
+  FD_REQUIRE(C == 3, "soft_charb_multi_bwd: the stacked splats are pixel-interleaved (r, g, b, weight): C must be 3, got %d", C);
   soft_charb_multi_bwd_kernel<<<dim3(multi_grid((long)B * HW, K), K), kThreads, 0, (cudaStream_t)stream>>>(S, T, sums, upstream, gS,
                                                                                                           B, C, (long)HW, K);
   FD_LAUNCH_CHECK();

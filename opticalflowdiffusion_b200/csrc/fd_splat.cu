@@ -258,41 +258,40 @@ __global__ void __launch_bounds__(256) splat_flowgrad_kernel(const float* __rest
 // ---------------------------------------------------------------------------------------------
 // All scale^2 offsets of one pyramid level in ONE launch (FlowLearner's loss loops `for a in range(level): for b in
 // range(level): softsplat(..., scale=level, offset=[a, b])`, flow_learner.py:184-196 -- 832 splat pairs per step).
-// Offset index k = a * scale + b -> (off_x, off_y) = (a, b); outputs / output gradients are stacked (K, B, C, Ho, Wo).
+// Offset index k = a * scale + b -> (off_x, off_y) = (a, b); outputs / output gradients are stacked pixel-interleaved, (K, B, Ho, Wo, 4).
 // The per-offset arithmetic is the single-offset kernels' (same taps, same order); the two gather kernels sum the
 // K contributions of a source pixel in registers instead of K separate passes.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) splat_fwd_multi_kernel(const float* __restrict__ in, const float* __restrict__ flow,
-                                                              float* __restrict__ out, int B, int C, int H, int W, int Ho,
+                                                              float* __restrict__ out, int B, int H, int W, int Ho,
                                                               int Wo, int scale, long items) {
+  // Four input channels (r, g, b, weight); the stacked output is pixel-interleaved (K, B, Ho, Wo, 4), so a tap is one 128-bit
+  // reduction.  The scatter is bound by the NUMBER of L2 reduction operations (at level L every output cell receives ~L^2
+  // contributions per offset): per-channel scalar reductions made this kernel 64 % of a FlowLearner step (ncu launch list).
   const int k = blockIdx.y;
   const int off_x = k / scale, off_y = k - off_x * scale;
   const long HW = (long)H * W, HWo = (long)Ho * Wo;
-  float* outk = out + (long)k * B * C * HWo;
-  const int lane = threadIdx.x & 31;
-  for (long base = (long)blockIdx.x * blockDim.x + (threadIdx.x & ~31); base < items; base += (long)gridDim.x * blockDim.x) {
-    const long item = base + lane;
-    const bool valid = item < items;
-    int b = 0, y = 0, x = 0;
-    if (valid) s_item_to_byx<1>(item, H, W, b, y, x);
+  float* outk = out + (long)k * B * HWo * 4;
+  for (long item = (long)blockIdx.x * blockDim.x + threadIdx.x; item < items; item += (long)gridDim.x * blockDim.x) {
+    int b, y, x;
+    s_item_to_byx<1>(item, H, W, b, y, x);
     const long pix = (long)y * W + x;
-    const float fx = valid ? __ldg(flow + ((long)b * 2 + 0) * HW + pix) : 0.f;
-    const float fy = valid ? __ldg(flow + ((long)b * 2 + 1) * HW + pix) : 0.f;
+    const float fx = __ldg(flow + ((long)b * 2 + 0) * HW + pix), fy = __ldg(flow + ((long)b * 2 + 1) * HW + pix);
     SplatTaps t;
     splat_taps<KIND_OUT>(fx, fy, x, y, H, W, Ho, Wo, scale, off_x, off_y, t);
-    const int r0 = t.y0 * Wo + t.x0;
-    int a0[2], a1[2];
-    a0[0] = (valid && t.okx0 && t.oky0) ? r0 : -1;
-    a0[1] = (valid && t.okx1 && t.oky0) ? r0 + 1 : -1;
-    a1[0] = (valid && t.okx0 && t.oky1) ? r0 + Wo : -1;
-    a1[1] = (valid && t.okx1 && t.oky1) ? r0 + Wo + 1 : -1;
-    for (int c = 0; c < C; ++c) {
-      const float a = valid ? __ldg(in + ((long)b * C + c) * HW + pix) : 0.f;
-      float v0[2] = {__fmul_rn(a, t.nw), __fmul_rn(a, t.ne)}, v1[2] = {__fmul_rn(a, t.sw), __fmul_rn(a, t.se)};
-      float* plane = outk + ((long)b * C + c) * HWo;
-      fd_scatter_merged<2>(plane, a0, v0);
-      fd_scatter_merged<2>(plane, a1, v1);
-    }
+    float v[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) v[c] = __ldg(in + ((long)b * 4 + c) * HW + pix);
+    float* cell = outk + (((long)b * Ho + t.y0) * Wo + t.x0) * 4;
+    auto red4 = [&](float* dst, float wt) {
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(__fmul_rn(v[0], wt)), "f"(__fmul_rn(v[1], wt)),
+                   "f"(__fmul_rn(v[2], wt)), "f"(__fmul_rn(v[3], wt))
+                   : "memory");
+    };
+    if (t.okx0 && t.oky0) red4(cell, t.nw);
+    if (t.okx1 && t.oky0) red4(cell + 4, t.ne);
+    if (t.okx0 && t.oky1) red4(cell + (long)Wo * 4, t.sw);
+    if (t.okx1 && t.oky1) red4(cell + (long)Wo * 4 + 4, t.se);
   }
 }
 
@@ -315,15 +314,19 @@ __global__ void __launch_bounds__(256) splat_ingrad_multi_kernel(const float* __
       SplatTaps t;
       splat_taps<KIND_INGRAD>(fx, fy, x, y, H, W, Ho, Wo, scale, off_x, off_y, t);
       const int r0 = t.y0 * Wo + t.x0;
-      const float* gk = gout + ((long)k * B + b) * C * HWo;
+      const float4* gk = reinterpret_cast<const float4*>(gout) + ((long)k * B + b) * HWo;      // interleaved (K, B, Ho, Wo, 4)
+      const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4 g_nw = (t.okx0 && t.oky0) ? __ldg(gk + r0) : z, g_ne = (t.okx1 && t.oky0) ? __ldg(gk + r0 + 1) : z;
+      const float4 g_sw = (t.okx0 && t.oky1) ? __ldg(gk + r0 + Wo) : z, g_se = (t.okx1 && t.oky1) ? __ldg(gk + r0 + Wo + 1) : z;
+      const float gn[4][4] = {{g_nw.x, g_ne.x, g_sw.x, g_se.x}, {g_nw.y, g_ne.y, g_sw.y, g_se.y},
+                              {g_nw.z, g_ne.z, g_sw.z, g_se.z}, {g_nw.w, g_ne.w, g_sw.w, g_se.w}};
 #pragma unroll
       for (int c = 0; c < C; ++c) {
-        const float* plane = gk + (long)c * HWo;
         float a = 0.f;
-        a += tap_or_zero(plane, t.okx0 && t.oky0, r0) * t.nw;
-        a += tap_or_zero(plane, t.okx1 && t.oky0, r0 + 1) * t.ne;
-        a += tap_or_zero(plane, t.okx0 && t.oky1, r0 + Wo) * t.sw;
-        a += tap_or_zero(plane, t.okx1 && t.oky1, r0 + Wo + 1) * t.se;
+        a += gn[c][0] * t.nw;
+        a += gn[c][1] * t.ne;
+        a += gn[c][2] * t.sw;
+        a += gn[c][3] * t.se;
         acc[c] += a;
       }
     }
@@ -355,15 +358,16 @@ __global__ void __launch_bounds__(256) splat_flowgrad_multi_kernel(const float* 
       ok = t.ok;
       const int r0 = t.y0 * Wo + t.x0;
       const float x0 = (float)t.x0, y0 = (float)t.y0, x1 = (float)(t.x0 + 1), y1 = (float)(t.y0 + 1);
-      const float* gk = gout + ((long)k * B + b) * C * HWo;
+      const float4* gk = reinterpret_cast<const float4*>(gout) + ((long)k * B + b) * HWo;      // interleaved (K, B, Ho, Wo, 4)
+      const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4 q_nw = (t.okx0 && t.oky0) ? __ldg(gk + r0) : z, q_ne = (t.okx1 && t.oky0) ? __ldg(gk + r0 + 1) : z;
+      const float4 q_sw = (t.okx0 && t.oky1) ? __ldg(gk + r0 + Wo) : z, q_se = (t.okx1 && t.oky1) ? __ldg(gk + r0 + Wo + 1) : z;
+      const float gn[4][4] = {{q_nw.x, q_ne.x, q_sw.x, q_se.x}, {q_nw.y, q_ne.y, q_sw.y, q_se.y},
+                              {q_nw.z, q_ne.z, q_sw.z, q_se.z}, {q_nw.w, q_ne.w, q_sw.w, q_se.w}};
       float kx = 0.f, ky = 0.f;
 #pragma unroll
       for (int c = 0; c < C; ++c) {
-        const float* plane = gk + (long)c * HWo;
-        const float g_nw = tap_or_zero(plane, t.okx0 && t.oky0, r0);
-        const float g_ne = tap_or_zero(plane, t.okx1 && t.oky0, r0 + 1);
-        const float g_sw = tap_or_zero(plane, t.okx0 && t.oky1, r0 + Wo);
-        const float g_se = tap_or_zero(plane, t.okx1 && t.oky1, r0 + Wo + 1);
+        const float g_nw = gn[c][0], g_ne = gn[c][1], g_sw = gn[c][2], g_se = gn[c][3];
         kx += g_nw * a[c] * (-1.f * (y1 - t.fy)) * t.dyy;
         kx += g_ne * a[c] * (+1.f * (y1 - t.fy)) * t.dyy;
         kx += g_sw * a[c] * (-1.f * (t.fy - y0)) * t.dyy;
@@ -658,6 +662,8 @@ int fd_splat_flowgrad(const float* in, const float* flow, const float* gout, flo
 int fd_splat_fwd_multi(const float* in, const float* flow, float* out, int B, int C, int H, int W, int scale, void* stream) {
   if (int e = check(B, C, H, W, scale, 0, 0)) return e;
   FD_REQUIRE(in && flow && out && scale * scale <= 65535, "splat_fwd_multi: bad argument");
+  FD_REQUIRE(C == 4, "splat_fwd_multi: built for the 4-channel soft splat input (3 colours + weight), got C=%d", C);
+  FD_REQUIRE((reinterpret_cast<uintptr_t>(out) & 15) == 0, "splat_fwd_multi: out must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
   const int Ho = H / scale, Wo = W / scale, K = scale * scale;
   FD_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)K * B * C * Ho * Wo, st));
@@ -665,7 +671,7 @@ int fd_splat_fwd_multi(const float* in, const float* flow, float* out, int B, in
   int gx = sgrid(items);
   const int cap = (FD_NUM_SMS * 16 + K - 1) / K;
   if (gx > cap) gx = cap;
-  splat_fwd_multi_kernel<<<dim3(gx, K), 256, 0, st>>>(in, flow, out, B, C, H, W, Ho, Wo, scale, items);
+  splat_fwd_multi_kernel<<<dim3(gx, K), 256, 0, st>>>(in, flow, out, B, H, W, Ho, Wo, scale, items);
   FD_LAUNCH_CHECK();
   return FD_OK;
 }

@@ -425,7 +425,8 @@ class _SoftLevelLossFn(torch.autograd.Function):
         B, C1, H, W = ten_in.shape
         lib, st = _lib.load(), _lib.stream()
         K, Ho, Wo = level * level, H // level, W // level
-        S = torch.empty(K, B, C1, Ho, Wo, device=ten_in.device, dtype=torch.float32)
+        assert C1 == 4, C1
+        S = torch.empty(K, B, Ho, Wo, C1, device=ten_in.device, dtype=torch.float32)      # pixel-interleaved (r, g, b, weight)
         T = torch.empty_like(S)
         _lib.check(lib.fd_splat_fwd_multi(_lib.ptr(ten_in), _lib.ptr(flow), _lib.ptr(S), B, C1, H, W, level, st))
         zero = torch.zeros_like(flow)
@@ -443,7 +444,7 @@ class _SoftLevelLossFn(torch.autograd.Function):
     def backward(ctx, g: Tensor):
         ten_in, flow, S, T, sums = ctx.saved_tensors
         level = ctx.level
-        K, B, C1, Ho, Wo = S.shape
+        K, B, Ho, Wo, C1 = S.shape
         H, W = ten_in.shape[-2:]
         lib, st = _lib.load(), _lib.stream()
         g = g.detach().float().reshape(1).contiguous()
