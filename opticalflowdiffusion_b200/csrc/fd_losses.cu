@@ -329,6 +329,7 @@ int fd_soft_charb_multi_fwd(const float* S, const float* T, float* sums, float* 
                             void* stream) {
   FD_REQUIRE(S && T && sums && out && partials && B > 0 && C > 0 && HW > 0 && K > 0 && K <= 65535, "soft_charb_multi_fwd: bad argument");
   FD_REQUIRE(C == 3, "soft_charb_multi_fwd: the stacked splats are pixel-interleaved (r, g, b, weight): C must be 3, got %d", C);
+  FD_REQUIRE(((reinterpret_cast<uintptr_t>(S) | reinterpret_cast<uintptr_t>(T)) & 15) == 0, "soft_charb_multi_fwd: 16-byte aligned S, T");
   const int grid = multi_grid((long)B * HW, K);
   soft_charb_multi_fwd_kernel<<<dim3(grid, K), kThreads, 0, (cudaStream_t)stream>>>(S, T, partials, B, C, (long)HW);
   FD_LAUNCH_CHECK();
@@ -341,6 +342,8 @@ int fd_soft_charb_multi_bwd(const float* S, const float* T, const float* sums, c
                             int HW, int K, void* stream) {
   FD_REQUIRE(S && T && sums && upstream && gS && B > 0 && C > 0 && HW > 0 && K > 0 && K <= 65535, "soft_charb_multi_bwd: bad argument");
   FD_REQUIRE(C == 3, "soft_charb_multi_bwd: the stacked splats are pixel-interleaved (r, g, b, weight): C must be 3, got %d", C);
+  FD_REQUIRE(((reinterpret_cast<uintptr_t>(S) | reinterpret_cast<uintptr_t>(T) | reinterpret_cast<uintptr_t>(gS)) & 15) == 0,
+             "soft_charb_multi_bwd: 16-byte aligned S, T, gS");
   soft_charb_multi_bwd_kernel<<<dim3(multi_grid((long)B * HW, K), K), kThreads, 0, (cudaStream_t)stream>>>(S, T, sums, upstream, gS,
                                                                                                           B, C, (long)HW, K);
   FD_LAUNCH_CHECK();

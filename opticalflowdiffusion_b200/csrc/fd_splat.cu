@@ -16,6 +16,8 @@
 //   flowgrad : that branch always; Y uses "* offset_y" instead of the abs/% form; the derivative
 //              factor is 1/scale only in the last branch ("freeze gradient") and channel 0 (d/dx)
 //              is scaled by the Y factor, channel 1 by the X factor               (:626-672)
+#include <initializer_list>
+
 #include "fd_common.cuh"
 
 namespace {
@@ -533,6 +535,13 @@ __global__ void __launch_bounds__(256) il_to_planes_kernel(const float* __restri
   }
 }
 
+// 128-bit accesses need 16-byte aligned planes (a view at an odd float offset is a legal argument)
+bool al16(std::initializer_list<const void*> ptrs) {
+  for (const void* q : ptrs)
+    if (q != nullptr && (reinterpret_cast<uintptr_t>(q) & 15) != 0) return false;
+  return true;
+}
+
 int sgrid(long items) {
   long blocks = (items + 255) / 256;
   const long cap = (long)FD_NUM_SMS * 16;
@@ -560,7 +569,7 @@ int fd_splat_fwd(const float* in, const float* flow, float* out, int B, int C, i
   cudaStream_t st = (cudaStream_t)stream;
   const int Ho = H / scale, Wo = W / scale;
   FD_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)B * C * Ho * Wo, st));
-  if (W % 4 == 0) {
+  if (W % 4 == 0 && al16({in, flow})) {
     const long items = (long)B * H * (W / 4);
     splat_fwd_kernel<4><<<sgrid(items), 256, 0, st>>>(in, flow, out, B, C, H, W, Ho, Wo, scale, off_x, off_y, items);
   } else {
@@ -631,7 +640,7 @@ int fd_splat_ingrad(const float* flow, const float* gout, float* gin, int B, int
   FD_REQUIRE(flow && gout && gin, "splat_ingrad: null pointer");
   cudaStream_t st = (cudaStream_t)stream;
   const int Ho = H / scale, Wo = W / scale;
-  if (W % 4 == 0) {
+  if (W % 4 == 0 && al16({flow, gin})) {
     const long items = (long)B * H * (W / 4);
     splat_ingrad_kernel<4><<<sgrid(items), 256, 0, st>>>(flow, gout, gin, B, C, H, W, Ho, Wo, scale, off_x, off_y, items);
   } else {
@@ -648,7 +657,7 @@ int fd_splat_flowgrad(const float* in, const float* flow, const float* gout, flo
   FD_REQUIRE(in && flow && gout && gflow, "splat_flowgrad: null pointer");
   cudaStream_t st = (cudaStream_t)stream;
   const int Ho = H / scale, Wo = W / scale;
-  if (W % 4 == 0) {
+  if (W % 4 == 0 && al16({in, flow, gflow})) {
     const long items = (long)B * H * (W / 4);
     splat_flowgrad_kernel<4><<<sgrid(items), 256, 0, st>>>(in, flow, gout, gflow, B, C, H, W, Ho, Wo, scale, off_x, off_y, items);
   } else {
@@ -681,6 +690,7 @@ int fd_splat_ingrad_multi(const float* flow, const float* gout, float* gin, int 
   if (int e = check(B, C, H, W, scale, 0, 0)) return e;
   FD_REQUIRE(flow && gout && gin, "splat_ingrad_multi: null pointer");
   FD_REQUIRE(C == 4, "splat_ingrad_multi: built for the 4-channel soft splat input (3 colours + weight), got C=%d", C);
+  FD_REQUIRE((reinterpret_cast<uintptr_t>(gout) & 15) == 0, "splat_ingrad_multi: gout must be 16-byte aligned");
   const long items = (long)B * H * W;
   splat_ingrad_multi_kernel<4><<<sgrid(items), 256, 0, (cudaStream_t)stream>>>(flow, gout, gin, B, H, W, H / scale, W / scale,
                                                                              scale, items);

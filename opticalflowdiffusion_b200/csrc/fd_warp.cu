@@ -16,6 +16,8 @@
 // bit-identical to the reference's CPU output (oracle/flowdiff_oracle.py:backwarp).
 #include <stdlib.h>
 
+#include <initializer_list>
+
 #include "fd_warp_common.cuh"
 
 using namespace fdwarp;
@@ -423,6 +425,15 @@ __global__ void __launch_bounds__(256) div_selftest_kernel(float c, unsigned lon
   if ((threadIdx.x & 31) == 0 && bad) atomicAdd(mismatches, bad);
 }
 
+// pick_vec restricted by the alignment of the tensors (a view at an odd float offset is a legal argument): VEC consecutive
+// floats are moved as one access, so every plane base must be a multiple of 4 * VEC bytes (H * W * 4 is, when VEC | W)
+static int vec_for(int W, std::initializer_list<const void*> ptrs) {
+  int v = pick_vec(W);
+  for (const void* q : ptrs)
+    while (v > 1 && q != nullptr && (reinterpret_cast<uintptr_t>(q) % (4u * (unsigned)v)) != 0) v >>= 1;
+  return v;
+}
+
 static int check_dims(int B, int C, int H, int W) {
   FD_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0, "backwarp: non-positive dimension B=%d C=%d H=%d W=%d", B, C, H, W);
   FD_REQUIRE((long)H * W < (1L << 31), "backwarp: plane too large");
@@ -464,7 +475,7 @@ int fd_backwarp_fwd(const float* image, const float* flow, float* out, float* ma
   cudaStream_t st = (cudaStream_t)stream;
   if (use_win(C, W, image, flow, out, mask)) return fd_warp_fwd_win(0, nullptr, image, flow, nullptr, out, mask, nullptr, nullptr, B, H, W, st);
   const BwGeom g = make_geom(H, W);
-  const int vec = pick_vec(W);
+  const int vec = vec_for(W, {image, flow, out, mask});
   const unsigned segs = row_segs(W, vec, 256);
   const long items = (long)B * H * segs;                       // row jobs
   FD_REQUIRE(items < (1L << 31), "backwarp: too many row segments");
@@ -482,7 +493,7 @@ int fd_backwarp_bwd(const float* image, const float* flow, const float* gout, fl
   if (gimage) FD_CUDA(cudaMemsetAsync(gimage, 0, sizeof(float) * (size_t)B * C * H * W, st));
   if (use_win(C, W, image, flow, gout, gimage, gflow))
     return fd_warp_bwd_win(0, nullptr, image, flow, nullptr, gout, nullptr, 0.f, 0.f, gflow, gimage, B, H, W, st);
-  const int vec = pick_vec(W);
+  const int vec = vec_for(W, {image, flow, gout, gimage, gflow});
   const unsigned segs = row_segs(W, vec, 256);
   const long items = (long)B * H * segs;                       // row jobs
   FD_REQUIRE(items < (1L << 31), "backwarp: too many row segments");
@@ -529,7 +540,7 @@ int fd_backwarp_photo_epe_bwd_ws(const float* frame1, const float* frame2, const
 }
 
 size_t fd_photo_epe_workspace_floats(int B, int H, int W) {
-  const long items = (long)B * H * row_segs(W, pick_vec(W), 256);
+  const long items = (long)B * H * row_segs(W, 1, 256);        // (the narrowest vector width: the largest grid)
   const size_t a = (size_t)photo_grid(items) * 3;
   const size_t c = (size_t)fd_warp_win_grid(B, H, W) * 3 + 1;      // + the ticket counter
   return a > c ? a : c;
@@ -544,7 +555,7 @@ int fd_backwarp_photo_epe_fwd(const float* frame1, const float* frame2, const fl
     return fd_warp_fwd_win(1, frame1, frame2, flow, flow_gt, nullptr, nullptr, partials, sums, B, H, W, st);
   }
   const BwGeom g = make_geom(H, W);
-  const int vec = pick_vec(W);
+  const int vec = vec_for(W, {frame1, frame2, flow, flow_gt});
   const unsigned segs = row_segs(W, vec, 256);
   const long items = (long)B * H * segs;                       // row jobs
   FD_REQUIRE(items < (1L << 31), "backwarp: too many row segments");
@@ -566,7 +577,7 @@ int fd_backwarp_photo_epe_bwd(const float* frame1, const float* frame2, const fl
   if (gframe2) FD_CUDA(cudaMemsetAsync(gframe2, 0, sizeof(float) * (size_t)B * C * H * W, st));
   if (use_win(C, W, frame1, frame2, flow, flow_gt, gflow, gframe2))
     return fd_warp_bwd_win(1, frame1, frame2, flow, flow_gt, nullptr, sums, g_photo, g_epe, gflow, gframe2, B, H, W, st);
-  const int vec = pick_vec(W);
+  const int vec = vec_for(W, {frame1, frame2, flow, flow_gt, gflow, gframe2});
   const unsigned segs = row_segs(W, vec, 256);
   const long items = (long)B * H * segs;                       // row jobs
   FD_REQUIRE(items < (1L << 31), "backwarp: too many row segments");

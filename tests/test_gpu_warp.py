@@ -285,3 +285,74 @@ def test_splat_forward_interleaved_accumulation(C, geom):
         assert torch.equal(torch.isnan(img), torch.isnan(img_ref))
         assert (img.nan_to_num() - img_ref.nan_to_num()).abs().max().item() <= 1e-5 * max(1.0, ref.abs().max().item())
         assert (wsum[:, 0] - ret[:, 3]).abs().max().item() <= 1e-5
+
+
+def _misaligned(t):
+    """A copy of ``t`` whose data pointer is NOT 16-byte aligned: the warp entry points then take the gather kernels of
+    fd_warp.cu instead of the TMA-window kernels (both must give the same results)."""
+    buf = torch.empty(t.numel() + 1, device=t.device, dtype=t.dtype)
+    v = buf[1:].view(t.shape)
+    v.copy_(t)
+    assert v.data_ptr() % 16 != 0
+    return v
+
+
+@pytest.mark.parametrize("shape", [(1, 50, 68), (2, 17, 132), (3, 16, 128), (1, 97, 260), (1, 1024, 2048)])
+def test_window_kernels_equal_gather_kernels(shape):
+    """The shared-memory-window kernels (fd_warp_win*.cu: tiles of 16 x 128, 16-pixel halo, TMA zero fill, border tiles,
+    out-of-window fallback) against the one-thread-per-pixel gather kernels on ragged / small / large shapes with flows that
+    leave the window and the image: forward output and mask bit-identical, sums and gradients to the order of the atomics."""
+    from opticalflowdiffusion_b200 import _lib
+    lib = _lib.load()
+    B, H, Wd = shape
+    g = torch.Generator().manual_seed(H + Wd)
+    flow = torch.randn(B, 2, H, Wd, generator=g) * 5
+    flow[0, :, H // 2, Wd // 3] = torch.tensor([40.0, -33.0])          # outside the 16-pixel window
+    flow[0, :, 0, 0] = torch.tensor([-3.0 * H, 2.0 * Wd])              # far outside the image (clamped cell)
+    flow = flow.cuda()
+    f1, f2 = torch.rand(B, 3, H, Wd, generator=g).cuda(), torch.rand(B, 3, H, Wd, generator=g).cuda()
+    gt = (flow.cpu() + torch.randn(B, 2, H, Wd, generator=g)).cuda()
+    gout = torch.randn(B, 3, H, Wd, generator=g).cuda()
+    P, st = _lib.ptr, _lib.stream()
+    mf, m1, m2, mg, mo = (_misaligned(t) for t in (flow, f1, f2, gt, gout))
+
+    def fwd(f2_, fl_):
+        out, mask = torch.empty_like(f2), torch.empty_like(f2)
+        _lib.check(lib.fd_backwarp_fwd(P(f2_), P(fl_), P(out), P(mask), B, 3, H, Wd, st))
+        return out, mask
+    (o_w, m_w), (o_g, m_g) = fwd(f2, flow), fwd(m2, mf)
+    assert torch.equal(o_w, o_g) and torch.equal(m_w, m_g)
+
+    def photo(a1, a2, fl_, gt_):
+        sums = torch.empty(4, device="cuda")
+        ws = torch.empty(lib.fd_photo_epe_workspace_floats(B, H, Wd), device="cuda")
+        _lib.check(lib.fd_backwarp_photo_epe_fwd(P(a1), P(a2), P(fl_), P(gt_), P(sums), P(ws), B, 3, H, Wd, st))
+        return sums
+    s_w, s_g = photo(f1, f2, flow, gt), photo(m1, m2, mf, mg)
+    assert torch.allclose(s_w, s_g, rtol=2e-5, atol=1e-3), (s_w, s_g)
+
+    def close(a, b):
+        return (a - b).abs().max().item() <= 2e-5 * max(b.abs().max().item(), 1e-12)
+    wsb = torch.empty(lib.fd_warp_bwd_workspace_floats(B, H, Wd), device="cuda")
+    res = []
+    for (a1, a2, fl_, gt_, use_ws) in ((f1, f2, flow, gt, True), (f1, f2, flow, gt, False), (m1, m2, mf, mg, False)):
+        gfl, gf2 = torch.empty_like(flow), torch.full_like(f2, float("nan"))
+        if use_ws:
+            _lib.check(lib.fd_backwarp_photo_epe_bwd_ws(P(a1), P(a2), P(fl_), P(gt_), P(s_g), 1.0, 0.5, P(gfl), P(gf2), P(wsb),
+                                                        B, 3, H, Wd, st))
+        else:
+            _lib.check(lib.fd_backwarp_photo_epe_bwd(P(a1), P(a2), P(fl_), P(gt_), P(s_g), 1.0, 0.5, P(gfl), P(gf2), B, 3, H, Wd, st))
+        res.append((gfl, gf2))
+    for gfl, gf2 in res[:2]:
+        assert close(gfl, res[2][0]) and close(gf2, res[2][1])
+    res = []
+    for (a2, fl_, go_, use_ws) in ((f2, flow, gout, True), (f2, flow, gout, False), (m2, mf, mo, False)):
+        gim, gfl = torch.full_like(f2, float("nan")), torch.empty_like(flow)
+        if use_ws:
+            _lib.check(lib.fd_backwarp_bwd_ws(P(a2), P(fl_), P(go_), P(gim), P(gfl), P(wsb), B, 3, H, Wd, st))
+        else:
+            _lib.check(lib.fd_backwarp_bwd(P(a2), P(fl_), P(go_), P(gim), P(gfl), B, 3, H, Wd, st))
+        res.append((gim, gfl))
+    torch.cuda.synchronize()
+    for gim, gfl in res[:2]:
+        assert close(gim, res[2][0]) and close(gfl, res[2][1])
