@@ -270,6 +270,9 @@ __global__ void __launch_bounds__(256) splat_fwd_multi_kernel(const float* __res
   // Four input channels (r, g, b, weight); the stacked output is pixel-interleaved (K, B, Ho, Wo, 4), so a tap is one 128-bit
   // reduction.  The scatter is bound by the NUMBER of L2 reduction operations (at level L every output cell receives ~L^2
   // contributions per offset): per-channel scalar reductions made this kernel 64 % of a FlowLearner step (ncu launch list).
+  // Measured and not kept: summing the lanes with equal footprints in registers first (match.any + 16 shuffles per group
+  // member, leaders issue the reductions) cut the reductions ~10x at the high levels and made the objective SLOWER
+  // (12.8 vs 9.6 ms): with vector reductions the kernel is bound by instruction issue, not by the L2 any more.
   const int k = blockIdx.y;
   const int off_x = k / scale, off_y = k - off_x * scale;
   const long HW = (long)H * W, HWo = (long)Ho * Wo;
