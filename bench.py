@@ -700,6 +700,10 @@ def run_train_leg(args, algo_cfg, rank: int, world: int, dev):
     l0 = lib.fd_launch_count()
     t_res = timed(step_resident, steps)
     launches = int(lib.fd_launch_count() - l0)
+    for _ in range(3):                             # warm-up of the e2e path itself: the copy stream's allocator pool, pinned rings
+        step_e2e()
+    drain_e2e()
+    e2e_state["host_losses"].clear()
     t_e2e = timed(step_e2e, steps, finish=drain_e2e)
     assert len(e2e_state["host_losses"]) == steps, "every e2e step must deliver its loss to the host"
     # phase split of one step (events on the launching stream)

@@ -150,7 +150,10 @@ __global__ void __launch_bounds__(256, 2) gn_bwd_reduce_kernel(const __nv_bfloat
   }
 }
 
-// one block per sample: blockDim = (C channels, 1024 / C slices of the reduce kernel's blocks)
+// one block per (sample, group): blockDim = (C / 8 channels of the group, S slices of the reduce kernel's blocks).  The first
+// version ran one block per SAMPLE with 1024 / C slices: for C = 512 a thread walked 75 partial blocks (47 us per launch,
+// 12-47 us over the 38 GroupNorms of a step, pure load latency on 8 SMs); per-group blocks give 8x the blocks and up to
+// 32 slices whatever C is.
 __global__ void __launch_bounds__(1024) gn_bwd_finalize_kernel(const float* __restrict__ partial, int nblocks,
                                                                const double* __restrict__ stats,
                                                                const float* __restrict__ gamma, const float* __restrict__ beta,
@@ -159,12 +162,12 @@ __global__ void __launch_bounds__(1024) gn_bwd_finalize_kernel(const float* __re
                                                                float* __restrict__ dss, float* __restrict__ dbias,
                                                                float* __restrict__ coef /* [N][8][2] */, long HW, int C,
                                                                float eps) {
-  __shared__ float s_g[8][2];
-  __shared__ float s_c[1024][2];
-  __shared__ float s_p[1024 * 3];          // [blockDim.y slices][C][3]
-  const int n = blockIdx.x, c = threadIdx.x;
+  __shared__ float s_g[2];
+  __shared__ float s_c[128][2];            // channels of the group (C <= 1024)
+  __shared__ float s_p[1024 * 3];          // [blockDim.y slices][C / 8][3]
+  const int n = blockIdx.x, g = blockIdx.y;
   const int cpg = C >> 3;
-  const int g = c / cpg;
+  const int cl = threadIdx.x, c = g * cpg + cl;
   const double cnt = (double)HW * cpg;
   const double s = stats[((long)n * 8 + g) * 2], ss = stats[((long)n * 8 + g) * 2 + 1];
   const double mean_d = s / cnt;
@@ -173,8 +176,7 @@ __global__ void __launch_bounds__(1024) gn_bwd_finalize_kernel(const float* __re
   const float rstd = (float)(1.0 / sqrt(var + (double)eps));
   const float mean = (float)mean_d;
   // Sum of the reduce kernel's per-block partials in a FIXED order (run-to-run stable), spread over blockDim.y slices of
-  // blocks with four independent accumulators each: the loop is pure load latency (one thread per channel walking all ~150
-  // blocks took 42 us per launch).
+  // blocks with four independent accumulators each: the loop is pure load latency.
   float S0, S1, S2;
   {
     constexpr int U = 4;
@@ -199,17 +201,19 @@ __global__ void __launch_bounds__(1024) gn_bwd_finalize_kernel(const float* __re
       a1[0] += pb[1];
       a2[0] += pb[2];
     }
-    float* mine = s_p + ((long)sl * C + c) * 3;
+    float* mine = s_p + ((long)sl * cpg + cl) * 3;
     mine[0] = (a0[0] + a0[1]) + (a0[2] + a0[3]);
     mine[1] = (a1[0] + a1[1]) + (a1[2] + a1[3]);
     mine[2] = (a2[0] + a2[1]) + (a2[2] + a2[3]);
     __syncthreads();
     S0 = S1 = S2 = 0.f;
-    for (int q = 0; q < S; ++q) {
-      const float* o = s_p + ((long)q * C + c) * 3;
-      S0 += o[0];
-      S1 += o[1];
-      S2 += o[2];
+    if (sl == 0) {
+      for (int q = 0; q < S; ++q) {
+        const float* o = s_p + ((long)q * cpg + cl) * 3;
+        S0 += o[0];
+        S1 += o[1];
+        S2 += o[2];
+      }
     }
   }
   const bool lead = threadIdx.y == 0;                  // slice 0 holds the full sums and does the rest of the (tiny) work
@@ -223,25 +227,25 @@ __global__ void __launch_bounds__(1024) gn_bwd_finalize_kernel(const float* __re
       dss[(long)n * ss_stride + c] = ga * Sx + be * S0;  // d scale = sum dz * y
       dss[(long)n * ss_stride + C + c] = S0;             // d shift
     }
-    s_c[c][0] = sc * ga * S0;                            // dxh summed over the pixels of this channel
-    s_c[c][1] = sc * ga * Sx;                            // ... dxh * xh
+    s_c[cl][0] = sc * ga * S0;                           // dxh summed over the pixels of this channel
+    s_c[cl][1] = sc * ga * Sx;                           // ... dxh * xh
   }
   __syncthreads();
-  if (lead && c < 8) {                                   // group sums in channel order
+  if (lead && cl == 0) {                                 // group sums in channel order
     float a = 0.f, b = 0.f;
     for (int i = 0; i < cpg; ++i) {
-      a += s_c[c * cpg + i][0];
-      b += s_c[c * cpg + i][1];
+      a += s_c[i][0];
+      b += s_c[i][1];
     }
-    s_g[c][0] = a;
-    s_g[c][1] = b;
+    s_g[0] = a;
+    s_g[1] = b;
   }
   __syncthreads();
   if (!lead) return;
-  const float m1 = s_g[g][0] / (float)cnt, m2 = s_g[g][1] / (float)cnt;
+  const float m1 = s_g[0] / (float)cnt, m2 = s_g[1] / (float)cnt;
   const float Q = -rstd * rstd * m2;
   const float R = -rstd * m1 - Q * mean;
-  if (c % cpg == 0) {
+  if (cl == 0) {
     coef[((long)n * 8 + g) * 2] = Q;
     coef[((long)n * 8 + g) * 2 + 1] = R;
   }
@@ -764,8 +768,9 @@ int fd_gn_silu_bwd(const void* h, const void* da, const double* gn_stats, const 
   gn_bwd_reduce_kernel<<<dim3((unsigned)bx, (unsigned)N), ppb * chunks, (size_t)ppb * C * 3 * sizeof(float), st>>>(
       hp, dp, gn_stats, gamma, beta, scale_shift, ss_stride, partial, (long)HW, C, eps);
   FD_LAUNCH_CHECK();
-  gn_bwd_finalize_kernel<<<N, dim3((unsigned)C, (unsigned)(1024 / C)), 0, st>>>(partial, (int)bx, gn_stats, gamma, beta, scale_shift, ss_stride, dgamma, dbeta,
-                                          dscale_shift, dbias, coef, (long)HW, C, eps);
+  const int cpg = C / 8, slices = 1024 / cpg < 32 ? 1024 / cpg : 32;
+  gn_bwd_finalize_kernel<<<dim3((unsigned)N, 8), dim3((unsigned)cpg, (unsigned)slices), 0, st>>>(
+      partial, (int)bx, gn_stats, gamma, beta, scale_shift, ss_stride, dgamma, dbeta, dscale_shift, dbias, coef, (long)HW, C, eps);
   FD_LAUNCH_CHECK();
   long bx2 = ((long)HW + ppb * 4 - 1) / (ppb * 4);
   const long cap2 = (long)FD_NUM_SMS * 16 / N + 1;

@@ -433,17 +433,20 @@ __global__ void __launch_bounds__(256) upsample2x_kernel(const uint4* __restrict
   }
 }
 
-// SinusoidalPosEmb + Linear + GELU(erf) + Linear (:144-151, 319-324); one block per batch element
-__global__ void __launch_bounds__(256) time_embed_kernel(const int64_t* __restrict__ t, const float* __restrict__ w1,
-                                                         const float* __restrict__ b1, const float* __restrict__ w2,
-                                                         const float* __restrict__ b2, float* __restrict__ temb,
-                                                         float* __restrict__ pe_out, float* __restrict__ pre_out, int dim,
-                                                         int time_dim) {
+// SinusoidalPosEmb + Linear + GELU(erf) + Linear (:144-151, 319-324); one block per batch element, one WARP per output
+// feature (lanes stride the input features: coalesced weight rows, 8 loads per lane).  The first version gave every thread a
+// whole weight row -- 256 dependent, uncoalesced loads -- and took 50 us at the head of every DDIM step.
+__global__ void __launch_bounds__(1024) time_embed_kernel(const int64_t* __restrict__ t, const float* __restrict__ w1,
+                                                          const float* __restrict__ b1, const float* __restrict__ w2,
+                                                          const float* __restrict__ b2, float* __restrict__ temb,
+                                                          float* __restrict__ pe_out, float* __restrict__ pre_out, int dim,
+                                                          int time_dim) {
   extern __shared__ float sm[];
   float* pe = sm;             // [dim]
   float* hid = sm + dim;      // [time_dim]
   const int b = blockIdx.x;
   const int half = dim / 2;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   const float tv = (float)t[b];
   const float lg = logf(10000.f) / (float)(half - 1);
   for (int i = threadIdx.x; i < half; i += blockDim.x) {
@@ -457,17 +460,22 @@ __global__ void __launch_bounds__(256) time_embed_kernel(const int64_t* __restri
     }
   }
   __syncthreads();
-  for (int j = threadIdx.x; j < time_dim; j += blockDim.x) {
-    float acc = b1[j];
-    for (int k = 0; k < dim; ++k) acc += pe[k] * __ldg(w1 + (long)j * dim + k);
-    hid[j] = 0.5f * acc * (1.f + erff(acc * 0.70710678118654752440f));
-    if (pre_out != nullptr) pre_out[(long)b * time_dim + j] = acc;
+  for (int j = warp; j < time_dim; j += nwarps) {
+    float acc = 0.f;
+    for (int k = lane; k < dim; k += 32) acc += pe[k] * __ldg(w1 + (long)j * dim + k);
+    acc = fd_warp_sum(acc);
+    if (lane == 0) {
+      acc += b1[j];
+      hid[j] = 0.5f * acc * (1.f + erff(acc * 0.70710678118654752440f));
+      if (pre_out != nullptr) pre_out[(long)b * time_dim + j] = acc;
+    }
   }
   __syncthreads();
-  for (int j = threadIdx.x; j < time_dim; j += blockDim.x) {
-    float acc = b2[j];
-    for (int k = 0; k < time_dim; ++k) acc += hid[k] * __ldg(w2 + (long)j * time_dim + k);
-    temb[(long)b * time_dim + j] = acc;
+  for (int j = warp; j < time_dim; j += nwarps) {
+    float acc = 0.f;
+    for (int k = lane; k < time_dim; k += 32) acc += hid[k] * __ldg(w2 + (long)j * time_dim + k);
+    acc = fd_warp_sum(acc);
+    if (lane == 0) temb[(long)b * time_dim + j] = acc + b2[j];
   }
 }
 
@@ -697,7 +705,7 @@ int fd_time_embed(const int64_t* t, const float* w1, const float* b1, const floa
 int fd_time_embed_save(const int64_t* t, const float* w1, const float* b1, const float* w2, const float* b2, float* temb,
                        float* pe, float* pre, int B, int dim, int time_dim, void* stream) {
   FD_REQUIRE(t && w1 && b1 && w2 && b2 && temb && B > 0 && dim >= 4 && dim % 2 == 0 && time_dim > 0, "time_embed: bad argument");
-  time_embed_kernel<<<B, 256, (dim + time_dim) * sizeof(float), (cudaStream_t)stream>>>(t, w1, b1, w2, b2, temb, pe, pre, dim,
+  time_embed_kernel<<<B, 1024, (dim + time_dim) * sizeof(float), (cudaStream_t)stream>>>(t, w1, b1, w2, b2, temb, pe, pre, dim,
                                                                                        time_dim);
   FD_LAUNCH_CHECK();
   return FD_OK;
