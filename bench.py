@@ -86,6 +86,17 @@ def load_peaks():
         return {"hbm": 6650.0, "tf_burst": 1590.0, "tf_sustained": 1400.0, "src": "fallback (B200_PROFILING.md)"}
 
 
+def load_red_rate():
+    """Measured rate of red.global.add.v4.f32 to white-noise addresses (reductions / s) from profiles/r2_red_rate.txt, or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r2_red_rate.txt")) as f:
+            rates = [float(l.split("us")[1].split("G reductions/s")[0]) for l in f
+                     if l.startswith("v4.f32, white-noise") and "G reductions/s" in l]
+        return max(rates) * 1e9 if rates else None
+    except Exception:  # noqa: BLE001
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
 
@@ -547,6 +558,20 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                                    if k in ("photo_epe_fwd", "photo_epe_bwd", "backwarp_fwd", "backwarp_bwd", "splat_fwd",
                                             "splat_flowgrad")}
         line["warp_microbench"]["hbm_peak_GBps"] = peaks["hbm"]
+        # The three scatter legs (forward splat, gradient of the sampled frame) are bound by the L2's reduction units, not by
+        # DRAM: they issue 4 pixel-interleaved 128-bit red.global.add per pixel to white-noise addresses, and the chip executes
+        # those at the rate scripts/micro/red_rate.cu measures for exactly this pattern (profiles/r2_red_rate.txt).
+        red = load_red_rate()
+        if red is not None:
+            n_red = 4 * BATCH * H * W
+            for k in ("splat_fwd", "photo_epe_bwd", "backwarp_bwd"):
+                leg = line["warp_microbench"].get(k)
+                if leg:
+                    leg["l2_reductions"] = n_red
+                    leg["l2_reduction_floor_us"] = round(n_red / red * 1e6, 1)
+                    leg["frac_of_l2_reduction_rate"] = round(n_red / (leg["us"] * 1e-6) / red, 3)
+            line["warp_microbench"]["l2_reductions_per_s"] = red
+            line["warp_microbench"]["l2_reduction_source"] = "profiles/r2_red_rate.txt (scripts/micro/red_rate.cu on this pool's B200)"
     if cpu_base is not None:
         line["cpu_baseline"] = cpu_base
     _emit(line)

@@ -542,7 +542,7 @@ int fd_backwarp_photo_epe_bwd_ws(const float* frame1, const float* frame2, const
 size_t fd_photo_epe_workspace_floats(int B, int H, int W) {
   const long items = (long)B * H * row_segs(W, 1, 256);        // (the narrowest vector width: the largest grid)
   const size_t a = (size_t)photo_grid(items) * 3;
-  const size_t c = (size_t)fd_warp_win_grid(B, H, W) * 3 + 1;      // + the ticket counter
+  const size_t c = (size_t)fd_warp_win_grid(B, H, W) * 3 + 4;      // + the 8-byte aligned 64-bit ticket word
   return a > c ? a : c;
 }
 

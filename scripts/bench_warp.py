@@ -12,13 +12,17 @@ from opticalflowdiffusion_b200 import _lib  # noqa: E402
 
 
 def _timeit(fn, iters=50, warmup=10, flush=None, clean=None):
-    """Median launch-to-completion time.  flush: a buffer larger than L2 that is WRITTEN before every launch (cold inputs; L2
-    is left full of dirty lines whose write-back then competes with the kernel for DRAM).  clean: a second buffer that is READ
-    after the write, so that the kernel starts with cold inputs and an L2 of clean lines (nothing to write back)."""
+    """Median device time of fn() between two CUDA events on the launching stream.  flush: a buffer larger than L2 that is
+    WRITTEN before every launch (cold inputs; L2 is left full of dirty lines whose write-back then competes with the kernel for
+    DRAM).  clean: a second buffer that is READ after the write, so that the kernel starts with cold inputs and an L2 of clean
+    lines (nothing to write back).  All iterations are enqueued before the one synchronisation at the end: the 70 us flush in
+    front of every timed launch keeps the stream busy, so the events bracket the kernels' execution (what ncu's
+    gpu__time_duration reports, profiles/r2_warp_launch_table.txt) and not the host's launch latency -- with a
+    synchronisation per iteration every number carried ~6 us of it (backwarp_fwd: 41.0 us against 35.1 us under ncu)."""
     for _ in range(warmup):
         fn()
     torch.cuda.synchronize()
-    ts = []
+    evs = []
     for _ in range(iters):
         if flush is not None:
             flush.zero_()
@@ -28,9 +32,9 @@ def _timeit(fn, iters=50, warmup=10, flush=None, clean=None):
         s.record()
         fn()
         e.record()
-        torch.cuda.synchronize()
-        ts.append(s.elapsed_time(e) * 1e-3)
-    ts.sort()
+        evs.append((s, e))
+    torch.cuda.synchronize()
+    ts = sorted(s.elapsed_time(e) * 1e-3 for s, e in evs)
     return ts[len(ts) // 2]
 
 

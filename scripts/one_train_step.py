@@ -1,5 +1,6 @@
-"""One training step (batch 8, 368x768 crops, target=flow) after two warm-up steps: the command profiled by ncu for
-profiles/ (run with `--profile-from-start off`: only the last step is inside cudaProfilerStart/Stop)."""
+"""One training step (batch 8, 368x768 crops, target=flow; TARGET=joint / target selects the splat + pyramid-loss objectives)
+after two warm-up steps: the command profiled by ncu for profiles/ (run with `--profile-from-start off`: only the last step is
+inside cudaProfilerStart/Stop)."""
 import os
 import sys
 
@@ -13,7 +14,8 @@ from opticalflowdiffusion_b200.datasets import synthetic_frames  # noqa: E402
 B = int(os.environ.get("BATCH", 8))
 H, W = int(os.environ.get("HEIGHT", 368)), int(os.environ.get("WIDTH", 768))
 torch.manual_seed(0)
-algo = FlowDiffuser(compose(["algorithm.target=flow"]).algorithm).cuda()
+TARGET = os.environ.get("TARGET", "flow")
+algo = FlowDiffuser(compose([f"algorithm.target={TARGET}", "algorithm.zero_init=false"]).algorithm).cuda()
 opt = algo.configure_optimizers()
 opt.max_grad_norm = 100.0
 img, tgt = synthetic_frames(B, H, W, 1).cuda(), synthetic_frames(B, H, W, 2).cuda()
@@ -23,8 +25,8 @@ for i in range(n):
     if i == n - 1:
         torch.cuda.synchronize()
         torch.cuda.profiler.start()
-    first, cond, _ = algo.preprocess((img, tgt, flow), aug=False)
-    loss = algo.loss(first, cond, None)
+    first, cond, fl = algo.preprocess((img, tgt, flow), aug=False)
+    loss = algo.loss(first, cond, fl)
     loss.backward()
     opt.step()
     opt.zero_grad(set_to_none=True)

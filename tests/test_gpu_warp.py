@@ -356,3 +356,49 @@ def test_window_kernels_equal_gather_kernels(shape):
     torch.cuda.synchronize()
     for gim, gfl in res[:2]:
         assert close(gim, res[2][0]) and close(gfl, res[2][1])
+
+
+def test_photo_epe_ticket_needs_no_clean_workspace():
+    """The window kernel finds its last block through a {launch tag, count} word in the caller's workspace (no memset in front
+    of the kernel): whatever the workspace holds -- zeros, all ones, the word an ABORTED launch would leave behind -- and when the
+    very same launch is replayed from a CUDA graph (same tag every time), the sums are those of a clean run, bit for bit (the
+    partials are reduced in a fixed order)."""
+    from opticalflowdiffusion_b200 import _lib
+    lib = _lib.load()
+    B, H, Wd = 2, 70, 256
+    g = torch.Generator().manual_seed(11)
+    flow = (torch.randn(B, 2, H, Wd, generator=g) * 4).cuda()
+    f1, f2 = torch.rand(B, 3, H, Wd, generator=g).cuda(), torch.rand(B, 3, H, Wd, generator=g).cuda()
+    gt = (flow.cpu() + torch.randn(B, 2, H, Wd, generator=g)).cuda()
+    P = _lib.ptr
+    n_ws = lib.fd_photo_epe_workspace_floats(B, H, Wd)
+
+    def run(ws, stream=None):
+        sums = torch.full((4,), float("nan"), device="cuda")
+        _lib.check(lib.fd_backwarp_photo_epe_fwd(P(f1), P(f2), P(flow), P(gt), P(sums), P(ws), B, 3, H, Wd,
+                                                 stream if stream is not None else _lib.stream()))
+        return sums
+
+    ref = run(torch.zeros(n_ws, device="cuda"))
+    assert torch.isfinite(ref).all()
+    for fill in (float("nan"), 1.0, -3.0e38):
+        assert torch.equal(run(torch.full((n_ws,), fill, device="cuda")), ref), fill
+    ints = torch.full((n_ws,), -1, device="cuda", dtype=torch.int32)              # tag 0xffffffff, count 0xffffffff
+    assert torch.equal(run(ints.view(torch.float32)), ref)
+    ws = torch.empty(n_ws, device="cuda")
+    for _ in range(3):                                                          # one workspace, consecutive launches
+        assert torch.equal(run(ws), ref)
+    # graph replay: the tag is baked into the captured launch
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        run(ws, side.cuda_stream)                                               # warm-up on the capture stream
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=side):
+            out = run(ws, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.current_stream().wait_stream(side)
+    for _ in range(3):
+        out.fill_(float("nan"))
+        graph.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(out, ref)
