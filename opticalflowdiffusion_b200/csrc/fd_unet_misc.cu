@@ -252,6 +252,11 @@ __global__ void __launch_bounds__(256) prep_weight_batch_kernel(const long long*
 // y = silu(a[c] * x + b[c]) (+ res);  a = rstd*gamma*(scale+1), b = (beta - mean*rstd*gamma)*(scale+1) + shift
 // grid = (pixel blocks, N); thread owns one 8-channel chunk for a strided set of pixels.
 // ---------------------------------------------------------------------------------------------
+// TANH: silu(z) = h + h tanh(h), h = z / 2 -- ONE MUFU op per element (tanh.approx, 2^-11 relative, before a bf16 rounding of
+// 2^-9) as in the fused forms of this transform (fd_conv_strip.cu: silu_tanh, fd_conv_epi.cuh: epi_silu_half), instead of the
+// ex2 + rcp of fd_silu: at 4 B of traffic per element the two MUFU ops of fd_silu were 114 us of pipe time per full-resolution
+// launch against 142 us of DRAM time.  FD_GN_SILU_EXP=1 selects the exp form.
+template <bool TANH>
 __global__ void __launch_bounds__(256) gn_silu_kernel(const __nv_bfloat16* __restrict__ x, const double* __restrict__ stats,
                                                       const float* __restrict__ gamma, const float* __restrict__ beta,
                                                       const float* __restrict__ scale_shift, long ss_stride,
@@ -285,8 +290,8 @@ __global__ void __launch_bounds__(256) gn_silu_kernel(const __nv_bfloat16* __res
       ga *= sc;
       be = be * sc + sh;
     }
-    a[j] = ga;
-    b[j] = be;
+    a[j] = TANH ? 0.5f * ga : ga;            // (exact scaling: the TANH form works on h = z / 2)
+    b[j] = TANH ? 0.5f * be : be;
   }
   const long base = (long)n * HW;
   constexpr int U = 4;     // pixels in flight per thread: U independent 16-byte loads before any use
@@ -312,8 +317,17 @@ __global__ void __launch_bounds__(256) gn_silu_kernel(const __nv_bfloat16* __res
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const float2 f = fd_unpack_bf16(xw[e]);
-        y[2 * e] = fd_silu(a[2 * e] * f.x + b[2 * e]);
-        y[2 * e + 1] = fd_silu(a[2 * e + 1] * f.y + b[2 * e + 1]);
+        if (TANH) {
+          const float h0 = fmaf(a[2 * e], f.x, b[2 * e]), h1 = fmaf(a[2 * e + 1], f.y, b[2 * e + 1]);
+          float t0, t1;
+          asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(h0));
+          asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(h1));
+          y[2 * e] = fmaf(h0, t0, h0);
+          y[2 * e + 1] = fmaf(h1, t1, h1);
+        } else {
+          y[2 * e] = fd_silu(a[2 * e] * f.x + b[2 * e]);
+          y[2 * e + 1] = fd_silu(a[2 * e + 1] * f.y + b[2 * e + 1]);
+        }
       }
       if (residual != nullptr) {
         const uint32_t rw[4] = {rv[u].x, rv[u].y, rv[u].z, rv[u].w};
@@ -663,9 +677,19 @@ int fd_gn_silu(const void* x, const double* gn_stats, const float* gamma, const 
   const long cap = (long)FD_NUM_SMS * 16 / N + 1;
   if (bx > cap) bx = cap;
   dim3 grid((unsigned)bx, (unsigned)N);
-  FD_CUDA(fd_launch_pdl(gn_silu_kernel, grid, dim3(ppb * chunks), 0, (cudaStream_t)stream,
-                        static_cast<const __nv_bfloat16*>(x), gn_stats, gamma, beta, scale_shift, ss_stride,
-                        static_cast<const __nv_bfloat16*>(residual), static_cast<__nv_bfloat16*>(out), (long)HW, C, eps));
+  static int exp_form = -1;
+  if (exp_form < 0) {
+    const char* e = getenv("FD_GN_SILU_EXP");
+    exp_form = e ? atoi(e) : 0;
+  }
+  if (exp_form)
+    FD_CUDA(fd_launch_pdl(gn_silu_kernel<false>, grid, dim3(ppb * chunks), 0, (cudaStream_t)stream,
+                          static_cast<const __nv_bfloat16*>(x), gn_stats, gamma, beta, scale_shift, ss_stride,
+                          static_cast<const __nv_bfloat16*>(residual), static_cast<__nv_bfloat16*>(out), (long)HW, C, eps));
+  else
+    FD_CUDA(fd_launch_pdl(gn_silu_kernel<true>, grid, dim3(ppb * chunks), 0, (cudaStream_t)stream,
+                          static_cast<const __nv_bfloat16*>(x), gn_stats, gamma, beta, scale_shift, ss_stride,
+                          static_cast<const __nv_bfloat16*>(residual), static_cast<__nv_bfloat16*>(out), (long)HW, C, eps));
   FD_LAUNCH_CHECK();
   return FD_OK;
 }
