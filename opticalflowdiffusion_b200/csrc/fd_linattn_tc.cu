@@ -464,14 +464,39 @@ __global__ void __launch_bounds__(256) linattn_tc_combine_kernel(const float* __
   constexpr int V4 = (C + 4) / 4;
   for (int idx = t; idx < 32 * V4; idx += 256) {
     const int dd = idx / V4, v = idx - dd * V4;
-    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int j = 0; j < cps; ++j) {
-      const float4 x = *reinterpret_cast<const float4*>(partial + (((long)n * cps + j) * 128 + head * 32 + dd) * (C + 4) + v * 4);
-      a.x += x.x;
-      a.y += x.y;
-      a.z += x.z;
-      a.w += x.w;
+    // six loads in flight per thread, six accumulators combined in a fixed order: one dependent load after another over the
+    // ~18 CTAs of a sample made this kernel pure L2 latency (34 us per launch for 3 MB of partials)
+    constexpr int U = 6;
+    float4 acc[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float* src = partial + (((long)n * cps) * 128 + head * 32 + dd) * (C + 4) + v * 4;
+    constexpr long kStep = 128L * (C + 4);
+    int j = 0;
+    for (; j + U <= cps; j += U) {
+      float4 x[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) x[u] = *reinterpret_cast<const float4*>(src + (long)(j + u) * kStep);
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        acc[u].x += x[u].x;
+        acc[u].y += x[u].y;
+        acc[u].z += x[u].z;
+        acc[u].w += x[u].w;
+      }
     }
+    for (int u = 0; j < cps; ++j, ++u) {
+      const float4 x = *reinterpret_cast<const float4*>(src + (long)j * kStep);
+      acc[u].x += x.x;
+      acc[u].y += x.y;
+      acc[u].z += x.z;
+      acc[u].w += x.w;
+    }
+    float4 a;
+    a.x = ((acc[0].x + acc[1].x) + (acc[2].x + acc[3].x)) + (acc[4].x + acc[5].x);
+    a.y = ((acc[0].y + acc[1].y) + (acc[2].y + acc[3].y)) + (acc[4].y + acc[5].y);
+    a.z = ((acc[0].z + acc[1].z) + (acc[2].z + acc[3].z)) + (acc[4].z + acc[5].z);
+    a.w = ((acc[0].w + acc[1].w) + (acc[2].w + acc[3].w)) + (acc[4].w + acc[5].w);
     if (v < C / 4) {
       s_g[dd][v * 4] = a.x;
       s_g[dd][v * 4 + 1] = a.y;
