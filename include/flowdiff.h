@@ -245,6 +245,12 @@ FD_API int fd_conv_wgrad(const void* src0, int C0, const void* src1, int C1, con
 FD_API int fd_gn_silu(const void* x, const double* gn_stats, const float* gamma, const float* beta,
                const float* scale_shift, long ss_stride, const void* residual, void* out,
                int N, int HW, int C, float eps, void* stream);
+/* The same transform with SiLU as h + h tanh(h), h = z/2 (one tanh.approx per element, within 2^-10 of fd_gn_silu before
+ * the bf16 rounding): what the inference forward (sampling) calls; the fused forms of this transform (fd_conv3x3_gnsilu_in,
+ * fd_conv_igemm_rt) use the same expression. */
+FD_API int fd_gn_silu_fast(const void* x, const double* gn_stats, const float* gamma, const float* beta,
+               const float* scale_shift, long ss_stride, const void* residual, void* out,
+               int N, int HW, int C, float eps, void* stream);
 
 /* channel LayerNorm (:116-125) over C per pixel, out = (x-mean)*rsqrt(var+eps)*g (+ residual) */
 FD_API int fd_chan_layernorm(const void* x, const float* g, const void* residual, void* out,

@@ -52,6 +52,7 @@ SIGNATURES = {
     "fd_pack_input_wide": (c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
     "fd_prep_weight": (c_int, [_P, _P, _I, _I, _I, _I, _I, _I, _F, _P]),
     "fd_gn_silu": (c_int, [_P, _P, _P, _P, _P, _L, _P, _P, _I, _I, _I, _F, _P]),
+    "fd_gn_silu_fast": (c_int, [_P, _P, _P, _P, _P, _L, _P, _P, _I, _I, _I, _F, _P]),
     "fd_chan_layernorm": (c_int, [_P, _P, _P, _P, _L, _I, _F, _P]),
     "fd_upsample2x": (c_int, [_P, _P, _I, _I, _I, _I, _P]),
     "fd_time_embed": (c_int, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _P]),

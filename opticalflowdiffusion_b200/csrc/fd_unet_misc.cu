@@ -252,10 +252,11 @@ __global__ void __launch_bounds__(256) prep_weight_batch_kernel(const long long*
 // y = silu(a[c] * x + b[c]) (+ res);  a = rstd*gamma*(scale+1), b = (beta - mean*rstd*gamma)*(scale+1) + shift
 // grid = (pixel blocks, N); thread owns one 8-channel chunk for a strided set of pixels.
 // ---------------------------------------------------------------------------------------------
-// TANH: silu(z) = h + h tanh(h), h = z / 2 -- ONE MUFU op per element (tanh.approx, 2^-11 relative, before a bf16 rounding of
-// 2^-9) as in the fused forms of this transform (fd_conv_strip.cu: silu_tanh, fd_conv_epi.cuh: epi_silu_half), instead of the
-// ex2 + rcp of fd_silu: at 4 B of traffic per element the two MUFU ops of fd_silu were 114 us of pipe time per full-resolution
-// launch against 142 us of DRAM time.  FD_GN_SILU_EXP=1 selects the exp form.
+// TANH (fd_gn_silu_fast, the inference forward): silu(z) = h + h tanh(h), h = z / 2 -- ONE MUFU op per element (tanh.approx,
+// 2^-11 relative, before a bf16 rounding of 2^-9) as in the fused forms of this transform (fd_conv_strip.cu: silu_tanh,
+// fd_conv_epi.cuh: epi_silu_half), instead of the ex2 + rcp of fd_silu: at 4 B of traffic per element the two MUFU ops of
+// fd_silu were 114 us of pipe time per full-resolution launch against 142 us of DRAM time.  fd_gn_silu (the training forward)
+// keeps the exp form: the training step gains nothing from the other one (measured), and its parity tests were pinned on it.
 template <bool TANH>
 __global__ void __launch_bounds__(256) gn_silu_kernel(const __nv_bfloat16* __restrict__ x, const double* __restrict__ stats,
                                                       const float* __restrict__ gamma, const float* __restrict__ beta,
@@ -666,8 +667,9 @@ int fd_prep_weight_batch(const long long* table, const int* blk_start, int n_lay
   return FD_OK;
 }
 
-int fd_gn_silu(const void* x, const double* gn_stats, const float* gamma, const float* beta, const float* scale_shift,
-               long ss_stride, const void* residual, void* out, int N, int HW, int C, float eps, void* stream) {
+static int gn_silu_launch(bool tanh_form, const void* x, const double* gn_stats, const float* gamma, const float* beta,
+                          const float* scale_shift, long ss_stride, const void* residual, void* out, int N, int HW, int C,
+                          float eps, void* stream) {
   FD_REQUIRE(x && gn_stats && gamma && beta && out && N > 0 && HW > 0, "gn_silu: bad argument");
   FD_REQUIRE(C % 64 == 0 && C <= 2048, "gn_silu: C=%d must be a multiple of 64", C);
   const int chunks = C / 8;
@@ -677,21 +679,26 @@ int fd_gn_silu(const void* x, const double* gn_stats, const float* gamma, const 
   const long cap = (long)FD_NUM_SMS * 16 / N + 1;
   if (bx > cap) bx = cap;
   dim3 grid((unsigned)bx, (unsigned)N);
-  static int exp_form = -1;
-  if (exp_form < 0) {
-    const char* e = getenv("FD_GN_SILU_EXP");
-    exp_form = e ? atoi(e) : 0;
-  }
-  if (exp_form)
-    FD_CUDA(fd_launch_pdl(gn_silu_kernel<false>, grid, dim3(ppb * chunks), 0, (cudaStream_t)stream,
+  if (tanh_form)
+    FD_CUDA(fd_launch_pdl(gn_silu_kernel<true>, grid, dim3(ppb * chunks), 0, (cudaStream_t)stream,
                           static_cast<const __nv_bfloat16*>(x), gn_stats, gamma, beta, scale_shift, ss_stride,
                           static_cast<const __nv_bfloat16*>(residual), static_cast<__nv_bfloat16*>(out), (long)HW, C, eps));
   else
-    FD_CUDA(fd_launch_pdl(gn_silu_kernel<true>, grid, dim3(ppb * chunks), 0, (cudaStream_t)stream,
+    FD_CUDA(fd_launch_pdl(gn_silu_kernel<false>, grid, dim3(ppb * chunks), 0, (cudaStream_t)stream,
                           static_cast<const __nv_bfloat16*>(x), gn_stats, gamma, beta, scale_shift, ss_stride,
                           static_cast<const __nv_bfloat16*>(residual), static_cast<__nv_bfloat16*>(out), (long)HW, C, eps));
   FD_LAUNCH_CHECK();
   return FD_OK;
+}
+
+int fd_gn_silu(const void* x, const double* gn_stats, const float* gamma, const float* beta, const float* scale_shift,
+               long ss_stride, const void* residual, void* out, int N, int HW, int C, float eps, void* stream) {
+  return gn_silu_launch(false, x, gn_stats, gamma, beta, scale_shift, ss_stride, residual, out, N, HW, C, eps, stream);
+}
+
+int fd_gn_silu_fast(const void* x, const double* gn_stats, const float* gamma, const float* beta, const float* scale_shift,
+                    long ss_stride, const void* residual, void* out, int N, int HW, int C, float eps, void* stream) {
+  return gn_silu_launch(true, x, gn_stats, gamma, beta, scale_shift, ss_stride, residual, out, N, HW, C, eps, stream);
 }
 
 int fd_chan_layernorm(const void* x, const float* g, const void* residual, void* out, long npix, int C, float eps,

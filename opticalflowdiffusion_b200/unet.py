@@ -56,6 +56,7 @@ class Unet(UnetParams, TrainMixin):
     # path): the 9 ResnetBlocks that have a res_conv (ups.*, final_res_block) lose their second gn_silu pass -- 4.4 GB of
     # HBM traffic per batch-8 forward at 440x1024.  FD_FUSE_GN_RES=0 selects the two-pass form.
     FUSE_GN_RESIDUAL = os.environ.get("FD_FUSE_GN_RES", "1") != "0"
+    GN_SILU_EXP = os.environ.get("FD_GN_SILU_EXP", "0") != "0"
     # Residual(PreNorm(LinearAttention)) for C in {64, 128} as two tcgen05 / TMA passes over x (fd_linattn_tc, inference
     # path): no LayerNorm output, qkv or attention tensor in HBM.  FD_LINATTN_TC=0 selects the mma.sync kernels.
     LINATTN_TC = os.environ.get("FD_LINATTN_TC", "1") != "0"
@@ -310,9 +311,11 @@ class Unet(UnetParams, TrainMixin):
         n, h, w, c = x.shape
         out = torch.empty_like(x)
         ss_ptr = ss.data_ptr() + 4 * ss_off if ss is not None else None
-        _lib.check(self._lib.fd_gn_silu(_lib.ptr(x), _lib.ptr(stats), _lib.ptr(norm.weight), _lib.ptr(norm.bias), ss_ptr,
-                                        ss.shape[1] if ss is not None else 0, _lib.ptr(residual), _lib.ptr(out), n,
-                                        h * w, c, self.GN_EPS, self._st))
+        # inference forward: the one-MUFU SiLU of the fused kernels (FD_GN_SILU_EXP=1: the exp form everywhere); the training
+        # forward (autograd on) keeps the exp form its parity tests were pinned on
+        fn = self._lib.fd_gn_silu if (torch.is_grad_enabled() or self.GN_SILU_EXP) else self._lib.fd_gn_silu_fast
+        _lib.check(fn(_lib.ptr(x), _lib.ptr(stats), _lib.ptr(norm.weight), _lib.ptr(norm.bias), ss_ptr,
+                      ss.shape[1] if ss is not None else 0, _lib.ptr(residual), _lib.ptr(out), n, h * w, c, self.GN_EPS, self._st))
         return out
 
     def _chan_ln(self, x: Tensor, g: Tensor, residual: Optional[Tensor] = None) -> Tensor:
