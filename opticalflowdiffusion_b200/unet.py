@@ -307,13 +307,14 @@ class Unet(UnetParams, TrainMixin):
         return out
 
     def _gn_silu(self, x: Tensor, stats: Tensor, norm, ss: Optional[Tensor], ss_off: int,
-                 residual: Optional[Tensor]) -> Tensor:
+                 residual: Optional[Tensor], exact: bool = False) -> Tensor:
         n, h, w, c = x.shape
         out = torch.empty_like(x)
         ss_ptr = ss.data_ptr() + 4 * ss_off if ss is not None else None
         # inference forward: the one-MUFU SiLU of the fused kernels (FD_GN_SILU_EXP=1: the exp form everywhere); the training
-        # forward (autograd on) keeps the exp form its parity tests were pinned on
-        fn = self._lib.fd_gn_silu if (torch.is_grad_enabled() or self.GN_SILU_EXP) else self._lib.fd_gn_silu_fast
+        # forward (exact=True from unet_train._t_gn_silu; grad mode cannot tell the two apart, it is off inside
+        # autograd.Function.forward) keeps the exp form its parity tests were pinned on
+        fn = self._lib.fd_gn_silu if (exact or self.GN_SILU_EXP) else self._lib.fd_gn_silu_fast
         _lib.check(fn(_lib.ptr(x), _lib.ptr(stats), _lib.ptr(norm.weight), _lib.ptr(norm.bias), ss_ptr,
                       ss.shape[1] if ss is not None else 0, _lib.ptr(residual), _lib.ptr(out), n, h * w, c, self.GN_EPS, self._st))
         return out

@@ -303,7 +303,7 @@ class TrainMixin:
 
     def _t_gn_silu(self, tape: Tape, h: Tensor, stats: Tensor, norm, ss: Optional[Tensor], dss: Optional[Tensor], ss_off: int,
                    residual: Optional[Tensor], conv_bias) -> Tensor:
-        out = self._gn_silu(h, stats, norm, ss, ss_off, residual)
+        out = self._gn_silu(h, stats, norm, ss, ss_off, residual, exact=True)
         lib, st, gb = self._lib, self._st, self._gb
 
         def bwd():
