@@ -26,3 +26,12 @@ def test_single_json_line_on_stdout():
     assert len(lines) == 1, r.stdout
     assert json.loads(lines[0]) == {"metric": "flows/sec DDIM-50 @436x1024", "value": 1.5}
     assert "NCCL version" in r.stderr and "python-level chatter" in r.stderr
+
+
+def test_reduction_rate_profile_is_parsed():
+    """bench.py's `frac_of_l2_reduction_rate` divides by the rate measured by scripts/micro/red_rate.cu for the white-noise
+    scatter pattern (profiles/r2_red_rate.txt): the committed profile must parse to a plausible number of reductions / s."""
+    sys.path.insert(0, ROOT)
+    import bench
+    rate = bench.load_red_rate()
+    assert rate is not None and 1e11 < rate < 1e12, rate
