@@ -74,7 +74,9 @@ FD_API int fd_warp_div_selftest(float divisor, unsigned long long* mismatches, v
  *   sums[0] = sum(mask * sqrt((frame1-warped)^2 + 1e-6))   losses.py:3-6,46-47
  *   sums[1] = sum(mask)                                     (over B*C*H*W, like the reference's mask)
  *   sums[2] = sum_px sqrt(du^2 + dv^2),  sums[3] = B*H*W
- * partials: workspace of fd_photo_epe_workspace_floats(B,H,W) floats.  Deterministic. */
+ * partials: workspace of fd_photo_epe_workspace_floats(B,H,W) floats, 4-byte aligned, ANY contents on entry (the kernel's
+ * last-block ticket is a {launch tag, count} word that it claims and clears itself; one workspace per call in flight).
+ * Deterministic. */
 FD_API size_t fd_photo_epe_workspace_floats(int B, int H, int W);
 FD_API int fd_backwarp_photo_epe_fwd(const float* frame1, const float* frame2, const float* flow,
                               const float* flow_gt, float* sums, float* partials,
